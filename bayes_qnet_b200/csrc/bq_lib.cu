@@ -1,0 +1,634 @@
+// libbq_b200.so -- C-ABI of the B200-native bayes-qnet hot path (declared in include/bq_capi.h).
+//
+// Host side of the library: validates and flattens the network, builds the colour-class sweep
+// schedule, owns device memory and the stream, launches the kernels in bq_static.cuh (static queue
+// order: single-server FIFO + delay stations) and bq_dynamic.cuh (multi-server FIFO, processor
+// sharing).  No torch types, no exceptions across the boundary.  There is no CPU fallback: without a
+// CUDA device bq_create fails with BQ_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/bq_capi.h"
+#include "bq_static.cuh"
+
+using namespace bq;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(BQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+struct bq_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int E = 0, Q = 0, P = 0, C = 0;
+    long long chain_offset = 0;
+    unsigned long long seed = 0;
+    unsigned int sweep_counter = 0;
+    bool static_order = true;
+    int threads = 512;
+    bool use_smem = true;
+    size_t smem_bytes = 0;
+    // host copies
+    std::vector<int> q_type, q_k, q_dist, q_poff;
+    std::vector<int> qid, tid, prev_byt, next_byt, prev_byq, next_byq;
+    std::vector<uint8_t> obs_a, obs_d;
+    std::vector<int> color_off, order;
+    std::vector<SchedRec> recs;
+    // device
+    int4 *d_rec = nullptr;
+    int *d_color_off = nullptr, *d_ev_q = nullptr, *d_ev_p = nullptr, *d_ev_pt = nullptr;
+    int *d_q_events = nullptr, *d_q_off = nullptr, *d_q_type = nullptr, *d_q_dist = nullptr,
+        *d_q_poff = nullptr;
+    double *d_state = nullptr, *d_theta = nullptr;
+    long long *d_stats = nullptr;
+    double *d_tr_theta = nullptr, *d_tr_wait = nullptr, *d_tr_logp = nullptr;
+    int trace_cap = 0, trace_len = 0;
+    double *d_scratch = nullptr;  // logcond x/out
+    int scratch_n = 0;
+    long long n_sweeps = 0, n_launches = 0;
+    float last_ms = 0.f;
+    bool timed = false;
+};
+
+extern "C" const char *bq_last_error(void) { return g_err.c_str(); }
+extern "C" int bq_version(void) { return 100; }
+extern "C" int bq_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BQ_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// schedule: resample-eligible events -> neighbourhood records -> conflict-free colour classes
+// ---------------------------------------------------------------------------------------------
+static SchedRec make_rec(const bq_handle *h, int e) {
+    SchedRec r;
+    r.e = e;
+    r.pt_e = h->prev_byt[e];
+    r.p = h->prev_byq[e];
+    r.n = h->next_byq[e];
+    r.pt_n = (r.n >= 0) ? h->prev_byt[r.n] : -1;
+    r.e1 = h->next_byt[e];
+    r.p1 = -1; r.pt_p1 = -1; r.pt_n1 = -1;
+    r.q0 = h->qid[e];
+    r.q1 = -1;
+    r.pad = 0;
+    if (r.e1 >= 0) {
+        r.q1 = h->qid[r.e1];
+        r.p1 = h->prev_byq[r.e1];
+        if (r.p1 >= 0) r.pt_p1 = h->prev_byt[r.p1];
+        int n1 = h->next_byq[r.e1];
+        if (n1 >= 0) r.pt_n1 = h->prev_byt[n1];
+    }
+    return r;
+}
+
+// events whose departure time the conditional of r.e reads (besides its own)
+static int rec_reads(const bq_handle *h, const SchedRec &r, int out[8]) {
+    int n = 0;
+    auto add = [&](int x) { if (x >= 0) out[n++] = x; };
+    add(r.pt_e);
+    if (h->q_type[r.q0] == Q_GGK) { add(r.p); add(r.n); if (r.n >= 0) add(r.pt_n); }
+    if (r.e1 >= 0) {
+        add(r.e1);
+        if (h->q_type[r.q1] == Q_GGK) { add(r.p1); add(r.pt_p1); add(r.pt_n1); }
+    }
+    return n;
+}
+
+static bool eligible(const bq_handle *h, int e) {
+    // qnet.pyx:688: not evt.obs_d and (not evt_next or not evt_next.obs_a)
+    if (h->obs_d[e]) return false;
+    int e1 = h->next_byt[e];
+    return e1 < 0 || !h->obs_a[e1];
+}
+
+static int build_schedule(bq_handle *h) {
+    const int E = h->E;
+    std::vector<int> elig;
+    for (int e = 0; e < E; ++e)
+        if (eligible(h, e)) elig.push_back(e);
+    const int n = (int)elig.size();
+    std::vector<int> slot(E, -1);
+    for (int i = 0; i < n; ++i) slot[elig[i]] = i;
+    std::vector<SchedRec> recs(n);
+    // adjacency among eligible events: a reads b  =>  a -- b
+    std::vector<std::vector<int>> adj(n);
+    for (int i = 0; i < n; ++i) {
+        recs[i] = make_rec(h, elig[i]);
+        int rd[8];
+        int nr = rec_reads(h, recs[i], rd);
+        for (int k = 0; k < nr; ++k) {
+            int j = slot[rd[k]];
+            if (j >= 0 && j != i) { adj[i].push_back(j); adj[j].push_back(i); }
+        }
+    }
+    // greedy colouring, smallest available colour
+    std::vector<int> color(n, -1);
+    int n_colors = 0;
+    std::vector<int> mark;
+    for (int i = 0; i < n; ++i) {
+        mark.assign(n_colors + 1, 0);
+        for (int j : adj[i])
+            if (color[j] >= 0) mark[color[j]] = 1;
+        int c = 0;
+        while (c < n_colors && mark[c]) ++c;
+        color[i] = c;
+        if (c == n_colors) ++n_colors;
+    }
+    // classes; inside a class sort by (queue of e, queue of e1, e) so warps are homogeneous
+    h->color_off.assign(n_colors + 1, 0);
+    for (int i = 0; i < n; ++i) h->color_off[color[i] + 1]++;
+    for (int c = 0; c < n_colors; ++c) h->color_off[c + 1] += h->color_off[c];
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) {
+        if (color[a] != color[b]) return color[a] < color[b];
+        if (recs[a].q0 != recs[b].q0) return recs[a].q0 < recs[b].q0;
+        if (recs[a].q1 != recs[b].q1) return recs[a].q1 < recs[b].q1;
+        return recs[a].e < recs[b].e;
+    });
+    h->recs.resize(n);
+    h->order.resize(n);
+    for (int i = 0; i < n; ++i) { h->recs[i] = recs[idx[i]]; h->order[i] = recs[idx[i]].e; }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t upload(T **dst, const void *src, size_t n) {
+    cudaError_t e = cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+static size_t static_smem_bytes(const bq_handle *h, bool smem_state) {
+    size_t Epad = smem_state ? (size_t)((h->E + 1) & ~1) : 0;
+    size_t b = (Epad + 34 * 8 + 8 + ((h->P + 1) & ~1)) * sizeof(double);
+    b += (size_t)h->Q * (sizeof(QConst) + sizeof(SuffStat)) + (size_t)h->Q * 3 * sizeof(int);
+    return (b + 15) & ~(size_t)15;
+}
+
+static void fill_args(const bq_handle *h, SweepArgs &A) {
+    memset(&A, 0, sizeof(A));
+    A.E = h->E; A.Q = h->Q; A.P = h->P; A.n_chains = h->C;
+    A.n_colors = (int)h->color_off.size() - 1;
+    A.rec = h->d_rec; A.color_off = h->d_color_off;
+    A.ev_q = h->d_ev_q; A.ev_p = h->d_ev_p; A.ev_pt = h->d_ev_pt;
+    A.q_events = h->d_q_events; A.q_off = h->d_q_off;
+    A.q_type = h->d_q_type; A.q_dist = h->d_q_dist; A.q_poff = h->d_q_poff;
+    A.state = h->d_state; A.theta = h->d_theta; A.stats = h->d_stats;
+    A.tr_theta = h->d_tr_theta; A.tr_wait = h->d_tr_wait; A.tr_logp = h->d_tr_logp;
+    A.seed = h->seed; A.chain_offset = h->chain_offset; A.sweep_base = h->sweep_counter;
+}
+
+extern "C" int bq_destroy(bq_handle *h) {
+    if (!h) return BQ_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void *ptrs[] = {h->d_rec, h->d_color_off, h->d_ev_q, h->d_ev_p, h->d_ev_pt, h->d_q_events, h->d_q_off,
+                    h->d_q_type, h->d_q_dist, h->d_q_poff, h->d_state, h->d_theta, h->d_stats,
+                    h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return BQ_OK;
+}
+
+extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *theta0, int32_t n_chains,
+                         int64_t chain_offset, uint64_t seed, int32_t device, bq_handle **out) {
+    if (!m || !a || !theta0 || !out) return fail(BQ_ERR_INVALID, "bq_create: null argument");
+    *out = nullptr;
+    if (n_chains < 1) return fail(BQ_ERR_INVALID, "bq_create: n_chains < 1");
+    if (m->n_queues < 1 || m->n_queues > 1024) return fail(BQ_ERR_INVALID, "bq_create: bad n_queues");
+    if (a->n_events < 1) return fail(BQ_ERR_INVALID, "bq_create: empty arrivals");
+    int ndev = bq_device_count();
+    if (ndev <= 0) return fail(BQ_ERR_NO_DEVICE, "bq_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(BQ_ERR_INVALID, "bq_create: bad device index");
+
+    bq_handle *h = new bq_handle();
+    h->device = device;
+    h->E = a->n_events; h->Q = m->n_queues; h->P = m->n_params; h->C = n_chains;
+    h->chain_offset = chain_offset; h->seed = seed;
+    const int E = h->E, Q = h->Q;
+    h->q_type.assign(m->q_type, m->q_type + Q);
+    h->q_k.assign(m->q_k, m->q_k + Q);
+    h->q_dist.assign(m->q_dist, m->q_dist + Q);
+    h->q_poff.assign(m->q_param_off, m->q_param_off + Q);
+    h->qid.assign(a->qid, a->qid + E);
+    h->tid.assign(a->tid, a->tid + E);
+    h->obs_a.assign(a->obs_a, a->obs_a + E);
+    h->obs_d.assign(a->obs_d, a->obs_d + E);
+    h->prev_byt.assign(a->prev_byt, a->prev_byt + E);
+    h->next_byt.assign(a->next_byt, a->next_byt + E);
+    h->prev_byq.assign(a->prev_byq, a->prev_byq + E);
+    h->next_byq.assign(a->next_byq, a->next_byq + E);
+
+    auto bail = [&](int code, const std::string &msg) { bq_destroy(h); return fail(code, msg); };
+    int pcount = 0;
+    for (int q = 0; q < Q; ++q) {
+        int t = h->q_type[q], dd = h->q_dist[q];
+        if (t != Q_GGK && t != Q_DELAY && t != Q_PS) return bail(BQ_ERR_INVALID, "unknown queue type");
+        if (dd != D_EXP && dd != D_GAMMA && dd != D_LOGNORMAL) return bail(BQ_ERR_INVALID, "unknown service family");
+        if (h->q_poff[q] != pcount) return bail(BQ_ERR_INVALID, "q_param_off is not the running parameter count");
+        pcount += (dd == D_EXP) ? 1 : 2;
+        if (t == Q_PS || (t == Q_GGK && h->q_k[q] != 1)) h->static_order = false;
+    }
+    if (pcount != h->P) return bail(BQ_ERR_INVALID, "n_params does not match the service families");
+    for (int e = 0; e < E; ++e) {
+        if (h->qid[e] < 0 || h->qid[e] >= Q) return bail(BQ_ERR_INVALID, "event with bad qid");
+        int lk[4] = {h->prev_byt[e], h->next_byt[e], h->prev_byq[e], h->next_byq[e]};
+        for (int k = 0; k < 4; ++k)
+            if (lk[k] < -1 || lk[k] >= E) return bail(BQ_ERR_INVALID, "event link out of range");
+        if (h->next_byt[e] >= 0 && h->prev_byt[h->next_byt[e]] != e) return bail(BQ_ERR_INVALID, "by-task links inconsistent");
+        if (h->next_byq[e] >= 0 && (h->prev_byq[h->next_byq[e]] != e || h->qid[h->next_byq[e]] != h->qid[e]))
+            return bail(BQ_ERR_INVALID, "by-queue links inconsistent");
+        if (h->next_byt[e] >= 0 && h->qid[h->next_byt[e]] == h->qid[e])
+            return bail(BQ_ERR_UNSUPPORTED, "a task visits the same queue twice in a row");
+    }
+    if (!h->static_order)
+        return bail(BQ_ERR_UNSUPPORTED, "multi-server (k>1) and PS queues are not in this build yet");
+
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) return bail(BQ_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+#define CKB(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return bail(BQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+    CKB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKB(cudaEventCreate(&h->ev0));
+    CKB(cudaEventCreate(&h->ev1));
+
+    build_schedule(h);
+
+    // per-event tables and events grouped by queue (in by-queue order)
+    std::vector<int> q_off(Q + 1, 0), q_events(E);
+    for (int e = 0; e < E; ++e) q_off[h->qid[e] + 1]++;
+    for (int q = 0; q < Q; ++q) q_off[q + 1] += q_off[q];
+    {
+        std::vector<int> fill(q_off.begin(), q_off.end() - 1);
+        for (int e = 0; e < E; ++e) q_events[fill[h->qid[e]]++] = e;
+    }
+    static_assert(sizeof(SchedRec) == 48, "SchedRec must be 3 x int4");
+    CKB(upload(&h->d_rec, h->recs.data(), h->recs.size() * 3));
+    CKB(upload(&h->d_color_off, h->color_off.data(), h->color_off.size()));
+    CKB(upload(&h->d_ev_q, h->qid.data(), E));
+    CKB(upload(&h->d_ev_p, h->prev_byq.data(), E));
+    CKB(upload(&h->d_ev_pt, h->prev_byt.data(), E));
+    CKB(upload(&h->d_q_events, q_events.data(), E));
+    CKB(upload(&h->d_q_off, q_off.data(), Q + 1));
+    CKB(upload(&h->d_q_type, h->q_type.data(), Q));
+    CKB(upload(&h->d_q_dist, h->q_dist.data(), Q));
+    CKB(upload(&h->d_q_poff, h->q_poff.data(), Q));
+
+    const size_t C = (size_t)n_chains;
+    CKB(cudaMalloc((void **)&h->d_state, C * E * sizeof(double)));
+    CKB(cudaMalloc((void **)&h->d_theta, C * h->P * sizeof(double)));
+    CKB(cudaMalloc((void **)&h->d_stats, C * 4 * sizeof(long long)));
+    CKB(cudaMemset(h->d_stats, 0, C * 4 * sizeof(long long)));
+    {
+        // replicate the initial state / parameters to every chain
+        std::vector<double> rep;
+        const size_t chunk = std::max<size_t>(1, std::min<size_t>(C, (64u << 20) / (E * sizeof(double))));
+        rep.resize(chunk * E);
+        for (size_t i = 0; i < chunk; ++i) memcpy(&rep[i * E], a->d, E * sizeof(double));
+        for (size_t c0 = 0; c0 < C; c0 += chunk) {
+            size_t nn = std::min(chunk, C - c0);
+            CKB(cudaMemcpy(h->d_state + c0 * E, rep.data(), nn * E * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        std::vector<double> th(C * h->P);
+        for (size_t c = 0; c < C; ++c) memcpy(&th[c * h->P], theta0, h->P * sizeof(double));
+        CKB(cudaMemcpy(h->d_theta, th.data(), th.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+
+    // shared-memory staging of the chain state when it fits (227 KB per CTA on sm_100a)
+    int max_optin = 0;
+    CKB(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    size_t need = static_smem_bytes(h, true);
+    h->use_smem = need + 1024 <= (size_t)max_optin;
+    h->smem_bytes = static_smem_bytes(h, h->use_smem);
+    if (const char *env = getenv("BQ_FORCE_GLOBAL"))
+        if (env[0] == '1') { h->use_smem = false; h->smem_bytes = static_smem_bytes(h, false); }
+    if (const char *env = getenv("BQ_THREADS")) {
+        int t = atoi(env);
+        if (t >= 32 && t <= BQ_MAX_THREADS && t % 32 == 0) h->threads = t;
+    }
+    CKB(cudaFuncSetAttribute(sweep_static_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    CKB(cudaFuncSetAttribute(sweep_static_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+#undef CKB
+    *out = h;
+    return BQ_OK;
+}
+
+static int check_range(bq_handle *h, int lo, int hi) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    if (lo < 0 || hi > h->C || lo >= hi) return fail(BQ_ERR_INVALID, "bad chain range");
+    return BQ_OK;
+}
+
+extern "C" int bq_set_params(bq_handle *h, int32_t lo, int32_t hi, const double *theta) {
+    if (int r = check_range(h, lo, hi)) return r;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_theta + (size_t)lo * h->P, theta, (size_t)(hi - lo) * h->P * sizeof(double),
+                       cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BQ_OK;
+}
+extern "C" int bq_get_params(bq_handle *h, int32_t lo, int32_t hi, double *theta) {
+    if (int r = check_range(h, lo, hi)) return r;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(theta, h->d_theta + (size_t)lo * h->P, (size_t)(hi - lo) * h->P * sizeof(double),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BQ_OK;
+}
+extern "C" int bq_set_state(bq_handle *h, int32_t lo, int32_t hi, const double *d) {
+    if (int r = check_range(h, lo, hi)) return r;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_state + (size_t)lo * h->E, d, (size_t)(hi - lo) * h->E * sizeof(double),
+                       cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BQ_OK;
+}
+
+extern "C" int bq_get_state(bq_handle *h, int32_t lo, int32_t hi, double *d, double *a, double *s,
+                            int32_t *proc, int32_t *prev_byq, int32_t *next_byq) {
+    if (int r = check_range(h, lo, hi)) return r;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)(hi - lo), E = h->E;
+    std::vector<double> tmp;
+    double *dd = d;
+    if (!dd) { tmp.resize(n * E); dd = tmp.data(); }
+    CK(cudaMemcpyAsync(dd, h->d_state + (size_t)lo * E, n * E * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t c = 0; c < n; ++c) {
+        const double *dc = dd + c * E;
+        for (size_t e = 0; e < E; ++e) {
+            int pt = h->prev_byt[e], p = h->prev_byq[e];
+            double ae = (pt >= 0) ? dc[pt] : 0.0;
+            if (a) a[c * E + e] = ae;
+            if (s) {
+                double cm = ae;
+                if (h->q_type[h->qid[e]] == Q_GGK && p >= 0) cm = std::max(ae, dc[p]);
+                s[c * E + e] = dc[e] - cm;
+            }
+            if (proc) proc[c * E + e] = 0;
+            if (prev_byq) prev_byq[c * E + e] = h->prev_byq[e];
+            if (next_byq) next_byq[c * E + e] = h->next_byq[e];
+        }
+    }
+    return BQ_OK;
+}
+
+extern "C" int bq_state_dev(bq_handle *h, double **d_dev, int64_t *chain_stride) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    if (d_dev) *d_dev = h->d_state;
+    if (chain_stride) *chain_stride = h->E;
+    return BQ_OK;
+}
+
+static int ensure_trace(bq_handle *h, int extra) {
+    int need = h->trace_len + extra;
+    if (need <= h->trace_cap) return BQ_OK;
+    int cap = std::max(need, h->trace_cap * 2);
+    const size_t C = h->C;
+    double *nt = nullptr, *nw = nullptr, *nl = nullptr;
+    CK(cudaMalloc((void **)&nt, (size_t)cap * C * h->P * sizeof(double)));
+    CK(cudaMalloc((void **)&nw, (size_t)cap * C * h->Q * sizeof(double)));
+    CK(cudaMalloc((void **)&nl, (size_t)cap * C * sizeof(double)));
+    if (h->trace_len) {
+        CK(cudaMemcpyAsync(nt, h->d_tr_theta, (size_t)h->trace_len * C * h->P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(nw, h->d_tr_wait, (size_t)h->trace_len * C * h->Q * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(nl, h->d_tr_logp, (size_t)h->trace_len * C * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (h->d_tr_theta) cudaFree(h->d_tr_theta);
+    if (h->d_tr_wait) cudaFree(h->d_tr_wait);
+    if (h->d_tr_logp) cudaFree(h->d_tr_logp);
+    h->d_tr_theta = nt; h->d_tr_wait = nw; h->d_tr_logp = nl;
+    h->trace_cap = cap;
+    return BQ_OK;
+}
+
+static int launch_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t update, uint32_t flags) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    if (n_sweeps < 0) return fail(BQ_ERR_INVALID, "n_sweeps < 0");
+    if (mode != BQ_MODE_SLICE) return fail(BQ_ERR_UNSUPPORTED, "only BQ_MODE_SLICE is built yet");
+    if (update < 0 || update > 2) return fail(BQ_ERR_INVALID, "bad param_update");
+    if (n_sweeps == 0) return BQ_OK;
+    CK(cudaSetDevice(h->device));
+    if (flags & BQ_FLAG_TRACE)
+        if (int r = ensure_trace(h, n_sweeps)) return r;
+    SweepArgs A;
+    fill_args(h, A);
+    A.n_sweeps = n_sweeps; A.update = update; A.flags = (int)flags; A.trace_base = h->trace_len;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    if (h->use_smem)
+        sweep_static_kernel<true><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
+    else
+        sweep_static_kernel<false><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->n_launches += 1;
+    if (!(flags & FLAG_PARAMS_ONLY)) h->n_sweeps += n_sweeps;
+    h->sweep_counter += (unsigned int)n_sweeps;
+    if (flags & BQ_FLAG_TRACE) h->trace_len += n_sweeps;
+    return BQ_OK;
+}
+
+extern "C" int bq_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t update, uint32_t flags) {
+    return launch_sweep(h, n_sweeps, mode, update, flags & 0xFFFFu);
+}
+
+extern "C" int bq_update_params(bq_handle *h, int32_t update) {
+    if (update != BQ_UPD_BAYES && update != BQ_UPD_STEM) return fail(BQ_ERR_INVALID, "bad param_update");
+    return launch_sweep(h, 1, BQ_MODE_SLICE, update, FLAG_PARAMS_ONLY);
+}
+
+extern "C" int bq_synchronize(bq_handle *h) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return BQ_OK;
+}
+
+extern "C" int bq_last_sweep_ms(bq_handle *h, float *ms) {
+    if (!h || !ms) return fail(BQ_ERR_INVALID, "null argument");
+    if (!h->timed) return fail(BQ_ERR_INVALID, "no sweep has been launched");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return BQ_OK;
+}
+
+extern "C" int bq_stream(bq_handle *h, void **stream) {
+    if (!h || !stream) return fail(BQ_ERR_INVALID, "null argument");
+    *stream = (void *)h->stream;
+    return BQ_OK;
+}
+
+extern "C" int bq_logcond(bq_handle *h, int32_t chain, int32_t eid, const double *x, int32_t n, double *out) {
+    if (int r = check_range(h, chain, chain + 1)) return r;
+    if (eid < 0 || eid >= h->E || n < 0) return fail(BQ_ERR_INVALID, "bad event id / n");
+    if (n == 0) return BQ_OK;
+    CK(cudaSetDevice(h->device));
+    if (h->scratch_n < 2 * n) {
+        if (h->d_scratch) cudaFree(h->d_scratch);
+        h->d_scratch = nullptr;
+        CK(cudaMalloc((void **)&h->d_scratch, (size_t)2 * n * sizeof(double)));
+        h->scratch_n = 2 * n;
+    }
+    CK(cudaMemcpyAsync(h->d_scratch, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SweepArgs A;
+    fill_args(h, A);
+    SchedRec r = make_rec(h, eid);
+    logcond_static_kernel<<<1, 128, 0, h->stream>>>(A, chain, r, h->d_scratch, n, h->d_scratch + n);
+    CK(cudaGetLastError());
+    h->n_launches += 1;
+    CK(cudaMemcpyAsync(out, h->d_scratch + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BQ_OK;
+}
+
+static int run_report(bq_handle *h, double *logp_host, double *ss_host) {
+    CK(cudaSetDevice(h->device));
+    const size_t C = h->C;
+    double *d_lp = nullptr, *d_ss = nullptr;
+    CK(cudaMalloc((void **)&d_lp, C * sizeof(double)));
+    cudaError_t e = cudaMalloc((void **)&d_ss, C * h->Q * 8 * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(d_lp); return fail(BQ_ERR_CUDA, cudaGetErrorString(e)); }
+    SweepArgs A;
+    fill_args(h, A);
+    size_t sm = static_smem_bytes(h, false);
+    report_static_kernel<<<h->C, 256, sm, h->stream>>>(A, d_lp, d_ss);
+    e = cudaGetLastError();
+    h->n_launches += 1;
+    if (e == cudaSuccess && logp_host)
+        e = cudaMemcpyAsync(logp_host, d_lp, C * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && ss_host)
+        e = cudaMemcpyAsync(ss_host, d_ss, C * h->Q * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_lp);
+    cudaFree(d_ss);
+    if (e != cudaSuccess) return fail(BQ_ERR_CUDA, cudaGetErrorString(e));
+    return BQ_OK;
+}
+
+extern "C" int bq_log_prob(bq_handle *h, double *out) {
+    if (!h || !out) return fail(BQ_ERR_INVALID, "null argument");
+    return run_report(h, out, nullptr);
+}
+extern "C" int bq_suffstats(bq_handle *h, double *out) {
+    if (!h || !out) return fail(BQ_ERR_INVALID, "null argument");
+    return run_report(h, nullptr, out);
+}
+
+extern "C" int bq_stats(bq_handle *h, bq_stats_t *out) {
+    if (!h || !out) return fail(BQ_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    std::vector<long long> st((size_t)h->C * 4);
+    CK(cudaMemcpyAsync(st.data(), h->d_stats, st.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memset(out, 0, sizeof(*out));
+    for (int c = 0; c < h->C; ++c) {
+        out->nevents += st[(size_t)c * 4 + 0];
+        out->slice_evals += st[(size_t)c * 4 + 1];
+        out->param_evals += st[(size_t)c * 4 + 2];
+        out->n_stuck += st[(size_t)c * 4 + 3];
+    }
+    out->slice_calls = out->nevents;
+    out->num_diff = out->slice_evals;
+    out->n_sweeps = h->n_sweeps;
+    out->n_launches = h->n_launches;
+    return BQ_OK;
+}
+extern "C" int bq_reset_stats(bq_handle *h) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_stats, 0, (size_t)h->C * 4 * sizeof(long long), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_sweeps = 0;
+    return BQ_OK;
+}
+
+extern "C" int bq_trace_len(bq_handle *h, int32_t *n_rec) {
+    if (!h || !n_rec) return fail(BQ_ERR_INVALID, "null argument");
+    *n_rec = h->trace_len;
+    return BQ_OK;
+}
+extern "C" int bq_get_trace(bq_handle *h, double *theta, double *mean_wait, double *logp) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    if (!h->trace_len) return BQ_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->trace_len * h->C;
+    if (theta) CK(cudaMemcpyAsync(theta, h->d_tr_theta, n * h->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (mean_wait) CK(cudaMemcpyAsync(mean_wait, h->d_tr_wait, n * h->Q * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (logp) CK(cudaMemcpyAsync(logp, h->d_tr_logp, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BQ_OK;
+}
+extern "C" int bq_clear_trace(bq_handle *h) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    h->trace_len = 0;
+    return BQ_OK;
+}
+extern "C" int bq_trace_dev(bq_handle *h, double **theta_dev, double **mean_wait_dev, double **logp_dev) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    if (theta_dev) *theta_dev = h->d_tr_theta;
+    if (mean_wait_dev) *mean_wait_dev = h->d_tr_wait;
+    if (logp_dev) *logp_dev = h->d_tr_logp;
+    return BQ_OK;
+}
+
+extern "C" int bq_get_schedule(bq_handle *h, int32_t *n_colors, int32_t *n_eligible, int32_t *color_off,
+                               int32_t *order) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    if (n_colors) *n_colors = (int)h->color_off.size() - 1;
+    if (n_eligible) *n_eligible = (int)h->order.size();
+    if (color_off) memcpy(color_off, h->color_off.data(), h->color_off.size() * sizeof(int));
+    if (order) memcpy(order, h->order.data(), h->order.size() * sizeof(int));
+    return BQ_OK;
+}
+
+// Pure host function (no device needed): the uniforms exactly as the kernels draw them.
+extern "C" int bq_rng_uniforms(uint64_t seed, int64_t chain, uint32_t sweep, uint32_t id, uint32_t tag,
+                               int32_t n, double *out) {
+    if (!out || n < 0) return fail(BQ_ERR_INVALID, "bad argument");
+    Rng r;
+    r.init(seed, (uint64_t)chain, sweep, id, tag);
+    for (int i = 0; i < n; ++i) out[i] = r.uniform();
+    return BQ_OK;
+}
+
+extern "C" int bq_kernel_info(bq_handle *h, int32_t *threads, int32_t *smem_bytes, int32_t *state_in_smem) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    if (threads) *threads = h->threads;
+    if (smem_bytes) *smem_bytes = (int)h->smem_bytes;
+    if (state_in_smem) *state_in_smem = h->use_smem ? 1 : 0;
+    return BQ_OK;
+}

@@ -1,0 +1,85 @@
+// Counter-based per-chain RNG (Philox4x32-10) shared by the device kernels and the host test hook.
+//
+// Replaces the reference's global MT19937 stream (randomkit.c:185-269, cdist.c:107-121).  Stream parity
+// with MT19937 is not a goal; what matters is that every (chain, sweep, event,
+// purpose) owns an independent stream, so the result does not depend on how chains are sharded over
+// GPUs or on the order the kernel visits events.
+//
+//   counter = (block index, event id or queue id, sweep index, global chain id low 32)
+//   key     = (seed low 32 ^ tag * 0x9E3779B9, seed high 32 ^ global chain id high 32)
+//
+// One Philox call yields 4 x 32 bits = two 53-bit uniforms in [0,1).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BQ_HD __host__ __device__ __forceinline__
+#else
+#define BQ_HD inline
+#endif
+
+namespace bq {
+
+enum : uint32_t {
+    TAG_SLICE = 1,   // hidden-time slice updates (qnet.pyx:701)
+    TAG_PARAM = 2,   // service-parameter draws (qnet.pyx:882)
+    TAG_MH = 3,      // MH-within-Gibbs proposal + accept (qnet.pyx:337)
+    TAG_TEST = 7
+};
+
+BQ_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+BQ_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                         uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+BQ_HD double u53(uint32_t lo, uint32_t hi) {
+    uint64_t v = ((uint64_t)hi << 32) | (uint64_t)lo;
+    return (double)(v >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct Rng {
+    uint32_t k0, k1, c1, c2, c3, blk;
+    double spare;
+    int has_spare;
+
+    BQ_HD void init(uint64_t seed, uint64_t chain, uint32_t sweep, uint32_t id, uint32_t tag) {
+        k0 = (uint32_t)seed ^ (tag * 0x9E3779B9u);
+        k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(chain >> 32);
+        c1 = id; c2 = sweep; c3 = (uint32_t)chain;
+        blk = 0; has_spare = 0; spare = 0.0;
+    }
+    // uniform in [0,1), 53 bits
+    BQ_HD double uniform() {
+        if (has_spare) { has_spare = 0; return spare; }
+        uint32_t o[4];
+        philox4x32_10(blk++, c1, c2, c3, k0, k1, o);
+        spare = u53(o[2], o[3]);
+        has_spare = 1;
+        return u53(o[0], o[1]);
+    }
+    // raw 32-bit word (consumes half a uniform's worth; used for rk_interval-style integers)
+    BQ_HD uint32_t word() {
+        uint32_t o[4];
+        philox4x32_10(blk++, c1, c2, c3, k0, k1, o);
+        return o[0];
+    }
+};
+
+}  // namespace bq

@@ -1,0 +1,427 @@
+// Sweep kernels for networks whose queue order is invariant under the sampler: every queue is a
+// single-server FIFO queue (QueueGGk with k = 1 -- what YAML `GG1` and the default produce,
+// qnetu.py:103-110 -- including the source queue, arrivals.pyx:256) or a DelayStation (queues.pyx:745).
+// For these the diff lists of queues.pyx:470-591 collapse to the closed form of SURVEY.md A.2/A.4, the
+// by-queue links never change and the only per-chain mutable state is d[E].
+//
+// Execution model (B200): one CTA owns one chain.  The chain's departure times are staged in shared
+// memory (E * 8 B; 160 KB for the 5k-task 3-tier benchmark) for the whole launch, all n_sweeps sweeps
+// run inside one launch, and within a sweep the resample-eligible events are visited colour class by
+// colour class: events of one class have disjoint Markov blankets (no event of the class is read by
+// another event's conditional), so the threads of the CTA update them concurrently and the result is
+// the same as visiting them one after another -- a fixed-scan Gibbs sweep, just in an order chosen for
+// the hardware.  The structure tables are identical for all chains and are
+// served from L2.  Sufficient statistics, the service-parameter update and the per-sweep summaries
+// are fused into the same kernel.
+#pragma once
+#include "bq_dist.cuh"
+
+namespace bq {
+
+#define BQ_MAX_THREADS 512
+#define BQ_SLICE_MAX_ITERS 1000
+
+enum { UPD_NONE = 0, UPD_BAYES = 1, UPD_STEM = 2 };
+enum { FLAG_TMAX_PER_SWEEP = 1, FLAG_NO_FINAL = 2, FLAG_TRACE = 4, FLAG_TIGHT = 8, FLAG_PARAMS_ONLY = 1 << 16 };
+
+// Static neighbourhood of one resample-eligible event e (12 x int32 = 3 x int4, stored in schedule
+// order so a colour class is one contiguous, coalesced read).  -1 = absent.
+struct SchedRec {
+    int e;      // the event whose departure is resampled
+    int pt_e;   // previous event of e's task: a_e = d[pt_e] (0 when absent: source queue)
+    int p;      // previous event in e's queue
+    int n;      // next event in e's queue
+    int pt_n;   // previous-by-task of n: a_n = d[pt_n]
+    int e1;     // next event of e's task (its arrival is d_e)
+    int p1;     // previous event in e1's queue
+    int pt_p1;  // previous-by-task of p1: a_{p1} (arrival order must be kept)
+    int pt_n1;  // previous-by-task of e1's queue successor: a_{n1}
+    int q0;     // queue of e
+    int q1;     // queue of e1
+    int pad;
+};
+
+struct SweepArgs {
+    int E, Q, P, n_colors, n_sweeps, update, flags, trace_base, n_chains;
+    const int4 *rec;
+    const int *color_off;
+    const int *ev_q, *ev_p, *ev_pt;  // per event: queue, prev-by-queue, prev-by-task
+    const int *q_events, *q_off;     // events grouped by queue
+    const int *q_type, *q_dist, *q_poff;
+    double *state;      // [C][E]
+    double *theta;      // [C][P]
+    long long *stats;   // [C][4]: nevents, slice_evals, param_evals, stuck
+    double *tr_theta;   // [rec][C][P]
+    double *tr_wait;    // [rec][C][Q]
+    double *tr_logp;    // [rec][C]
+    unsigned long long seed;
+    long long chain_offset;
+    unsigned int sweep_base;
+};
+
+// Local conditional of d_e given its Markov blanket (GGkGibbs.inner_dfun, qnet.pyx:1340-1357, in the
+// closed form of SURVEY.md A.2): G(d) = sum of the new-service log-densities; -inf outside the support.
+struct Cond {
+    double b;            // max(a_e, d_p): when e enters service        (queues.pyx:610-612)
+    double a_n, d_n;     // queue successor of e
+    double d_e1, d_p1;   // next-by-task event and its queue predecessor's departure
+    double flo, fhi;     // feasible interval (all services >= 0, arrival order kept)
+    int has_n, has_e1, e1_fifo;
+    const QConst *c0, *c1;
+
+    __device__ __forceinline__ double eval(double d) const {
+        if (d < flo || d > fhi) return BQ_NEG_INF;
+        double v = lpdf(*c0, d - b);
+        if (has_n) v += lpdf(*c0, d_n - fmax(a_n, d));
+        if (has_e1) v += lpdf(*c1, d_e1 - (e1_fifo ? fmax(d, d_p1) : d));
+        return v;
+    }
+};
+
+__device__ __forceinline__ void cond_load(Cond &c, const SchedRec &r, const double *d, const int *q_type,
+                                          const QConst *qc, double &x0, double &lower, double &upper,
+                                          double tmax) {
+    x0 = d[r.e];
+    double a_e = (r.pt_e >= 0) ? d[r.pt_e] : 0.0;
+    int fifo0 = (q_type[r.q0] == Q_GGK);
+    c.b = a_e;
+    c.c0 = &qc[r.q0];
+    c.c1 = c.c0;
+    double flo = a_e, fhi = INFINITY;
+    if (fifo0 && r.p >= 0) { c.b = fmax(a_e, d[r.p]); flo = c.b; }
+    c.has_n = (fifo0 && r.n >= 0);
+    c.a_n = 0.0; c.d_n = 0.0;
+    if (c.has_n) {
+        c.d_n = d[r.n];
+        c.a_n = (r.pt_n >= 0) ? d[r.pt_n] : 0.0;
+        fhi = c.d_n;
+    }
+    c.has_e1 = (r.e1 >= 0);
+    c.e1_fifo = 0; c.d_e1 = 0.0; c.d_p1 = 0.0;
+    lower = a_e;
+    upper = tmax;
+    if (c.has_e1) {
+        c.d_e1 = d[r.e1];
+        c.c1 = &qc[r.q1];
+        upper = fmin(c.d_e1, tmax);
+        fhi = fmin(fhi, c.d_e1);
+        c.e1_fifo = (q_type[r.q1] == Q_GGK);
+        if (c.e1_fifo) {
+            if (r.p1 >= 0) {
+                c.d_p1 = d[r.p1];
+                flo = fmax(flo, (r.pt_p1 >= 0) ? d[r.pt_p1] : 0.0);
+            }
+            if (r.pt_n1 >= 0) fhi = fmin(fhi, d[r.pt_n1]);
+        }
+    }
+    c.flo = flo; c.fhi = fhi;
+}
+
+// sampling._slice with finite bounds (sampling.pyx:283-298, 344-366): no stepping out, shrink on
+// rejection.  Deviation, documented in DESIGN.md: when the bracket collapses below 1e-10 the reference
+// returns L (sampling.pyx:360-362), which may lie outside the support and poison the chain; we keep x0.
+__device__ __forceinline__ double slice_update(const Cond &c, double x0, double L, double R, Rng &rng,
+                                               int &evals, int &stuck) {
+    double g0 = c.eval(x0);
+    ++evals;
+    double logy = g0 - (-log(1.0 - rng.uniform()));  // rk_exponential: -log(1 - U)   (cdist.c:107-110)
+    if (!(logy > BQ_NEG_INF)) { ++stuck; return x0; }  // point mass guard (sampling.pyx:289-291)
+    for (int it = 0; it < BQ_SLICE_MAX_ITERS; ++it) {
+        double x1 = L + (R - L) * rng.uniform();
+        ++evals;
+        if (c.eval(x1) >= logy) return x1;
+        if (x1 > x0) R = x1; else L = x1;
+        if (R - L < 1e-10) { ++stuck; return x0; }
+    }
+    ++stuck;
+    return x0;
+}
+
+template <int N>
+__device__ __forceinline__ void block_reduce_sum(double (&v)[N], double *scratch, double *out) {
+    // deterministic: warp shuffle tree, then warp 0 adds the per-warp partials in warp order
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) scratch[warp * N + i] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double x = 0.0;
+        for (int w = 0; w < nwarps; ++w) x += scratch[w * N + threadIdx.x];
+        out[threadIdx.x] = x;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double block_reduce_max(double v, double *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = scratch[0];
+        for (int w = 1; w < nwarps; ++w) m = fmax(m, scratch[w]);
+        scratch[32] = m;
+    }
+    __syncthreads();
+    double m = scratch[32];
+    __syncthreads();
+    return m;
+}
+
+// service time of event i under the static order (queues.pyx:610-612 with k = 1; queues.pyx:771)
+__device__ __forceinline__ void event_service(const double *d, int i, int fifo, int p, int pt, double &a,
+                                              double &s) {
+    double di = d[i];
+    a = (pt >= 0) ? d[pt] : 0.0;
+    double c = a;
+    if (fifo && p >= 0) c = fmax(a, d[p]);
+    s = di - c;
+}
+
+// Per-queue sufficient statistics for the whole chain; result in ss[Q] (shared), logp in *logp_out.
+// Two passes for LogNormal queues (distributions.pyx:276-299 is two-pass).
+__device__ inline void chain_suffstats(const SweepArgs &A, const double *d, const int *q_type,
+                                       const int *q_dist, const QConst *qc, SuffStat *ss, double *scratch,
+                                       double *red_out, bool want_logp, double *logp_out) {
+    double logp_acc = 0.0;
+    for (int q = 0; q < A.Q; ++q) {
+        const int lo = A.q_off[q], hi = A.q_off[q + 1];
+        const int fifo = (q_type[q] == Q_GGK), dist = q_dist[q];
+        const bool need_log = (dist != D_EXP);
+        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // n, sum, sumlog, nlog, wait, nzero, logp, bad
+        for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+            int i = A.q_events[j];
+            double a, s;
+            event_service(d, i, fifo, A.ev_p[i], A.ev_pt[i], a, s);
+            double w = d[i] - a - s;
+            v[4] += (w > 0.0) ? w : 0.0;
+            if (s > 0.0) {
+                v[0] += 1.0; v[1] += s;
+                if (need_log) {
+                    double ls = log(s);
+                    if (dist == D_GAMMA) { v[2] += ls; v[3] += 1.0; }
+                    else if (s >= 1e-50) { v[2] += ls; v[3] += 1.0; }
+                }
+            } else if (s == 0.0) v[5] += 1.0;
+            if (want_logp) {
+                if (s < 0.0) v[7] += 1.0; else v[6] += lpdf(qc[q], s);
+            }
+        }
+        block_reduce_sum<8>(v, scratch, red_out);
+        double mean_log = (red_out[3] > 0.0) ? red_out[2] / red_out[3] : 0.0;
+        double sq[1] = {0.0};
+        if (dist == D_LOGNORMAL) {
+            for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+                int i = A.q_events[j];
+                double a, s;
+                event_service(d, i, fifo, A.ev_p[i], A.ev_pt[i], a, s);
+                if (s >= 1e-50) { double z = log(s) - mean_log; sq[0] += z * z; }
+            }
+        }
+        if (threadIdx.x == 0) {
+            SuffStat &t = ss[q];
+            t.n = red_out[0]; t.sum = red_out[1]; t.sumlog = red_out[2]; t.nlog = red_out[3];
+            t.wait = red_out[4]; t.nzero = red_out[5]; t.nall = (double)(hi - lo); t.sumsq = 0.0;
+            logp_acc += (red_out[7] > 0.0) ? BQ_NEG_INF : red_out[6];
+        }
+        __syncthreads();
+        if (dist == D_LOGNORMAL) {
+            block_reduce_sum<1>(sq, scratch, red_out);
+            if (threadIdx.x == 0) ss[q].sumsq = red_out[0];
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0 && logp_out) *logp_out = logp_acc;
+    __syncthreads();
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const SweepArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int chain = blockIdx.x;
+    const int E = A.E, Q = A.Q, P = A.P;
+    double *dg = A.state + (size_t)chain * E;
+    // shared layout: [d (E padded to even)] [scratch 34*8] [red_out 8] [theta P] [qc Q] [ss Q] [ints 3Q]
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    const int Epad = SMEM ? ((E + 1) & ~1) : 0;
+    double *d = SMEM ? sm : dg;
+    double *scratch = sm + Epad;            // 16 warps * 8 + 2 slack -> 34*8 is ample
+    double *red_out = scratch + 34 * 8;
+    double *th = red_out + 8;
+    QConst *qc = reinterpret_cast<QConst *>(th + ((P + 1) & ~1));
+    SuffStat *ss = reinterpret_cast<SuffStat *>(qc + Q);
+    int *q_type = reinterpret_cast<int *>(ss + Q);
+    int *q_dist = q_type + Q;
+    int *q_poff = q_dist + Q;
+    __shared__ unsigned long long cnt[4];
+    __shared__ double logp_sh;
+
+    for (int i = threadIdx.x; i < P; i += blockDim.x) th[i] = A.theta[(size_t)chain * P + i];
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+        q_type[i] = A.q_type[i]; q_dist[i] = A.q_dist[i]; q_poff[i] = A.q_poff[i];
+    }
+    if (threadIdx.x < 4) cnt[threadIdx.x] = 0ull;
+    if (SMEM) {
+        // coalesced 16-byte loads; each chain's row is 16 B aligned when E is even, else fall back
+        if ((E & 1) == 0) {
+            const double2 *src = reinterpret_cast<const double2 *>(dg);
+            double2 *dst = reinterpret_cast<double2 *>(d);
+            for (int i = threadIdx.x; i < E / 2; i += blockDim.x) dst[i] = src[i];
+        } else {
+            for (int i = threadIdx.x; i < E; i += blockDim.x) d[i] = dg[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < Q) {
+        int q = threadIdx.x, o = q_poff[q];
+        qconst_set(qc[q], q_dist[q], th[o], (q_dist[q] == D_EXP) ? 0.0 : th[o + 1]);
+    }
+    __syncthreads();
+
+    const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain);
+    long long n_ev = 0, n_evals = 0, n_stuck = 0, n_pevals = 0;
+    double tmax = 0.0;
+
+    for (int sw = 0; sw < A.n_sweeps; ++sw) {
+        const unsigned int gsw = A.sweep_base + (unsigned int)sw;
+        if (sw == 0 || (A.flags & FLAG_TMAX_PER_SWEEP)) {  // Tmax = 2 max d   (qnet.pyx:672)
+            double m = 0.0;
+            for (int i = threadIdx.x; i < E; i += blockDim.x) m = fmax(m, d[i]);
+            tmax = 2.0 * block_reduce_max(m, scratch);
+        }
+        const int n_colors = (A.flags & FLAG_PARAMS_ONLY) ? 0 : A.n_colors;
+        for (int c = 0; c < n_colors; ++c) {
+            const int lo = A.color_off[c], hi = A.color_off[c + 1];
+            for (int idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
+                union { int4 v[3]; SchedRec r; } u;
+                u.v[0] = __ldg(&A.rec[3 * idx]);
+                u.v[1] = __ldg(&A.rec[3 * idx + 1]);
+                u.v[2] = __ldg(&A.rec[3 * idx + 2]);
+                Cond cd;
+                double x0, lower, upper;
+                cond_load(cd, u.r, d, q_type, qc, x0, lower, upper, tmax);
+                if (A.flags & FLAG_TIGHT) { lower = fmax(lower, cd.flo); upper = fmin(upper, cd.fhi); }
+                Rng rng;
+                rng.init(A.seed, gchain, gsw, (unsigned int)u.r.e, TAG_SLICE);
+                int ev = 0, st = 0;
+                double x1 = slice_update(cd, x0, lower, upper, rng, ev, st);
+                d[u.r.e] = x1;
+                n_ev += 1; n_evals += ev; n_stuck += st;
+            }
+            __syncthreads();
+        }
+        const bool trace = (A.flags & FLAG_TRACE) != 0;
+        if (A.update != UPD_NONE || trace) {
+            chain_suffstats(A, d, q_type, q_dist, qc, ss, scratch, red_out, trace, &logp_sh);
+            const size_t recno = (size_t)(A.trace_base + sw);
+            if (trace && threadIdx.x < Q) {
+                int q = threadIdx.x;
+                A.tr_wait[(recno * A.n_chains + chain) * Q + q] = (ss[q].nall > 0.0) ? ss[q].wait / ss[q].nall : 0.0;
+            }
+            if (trace && threadIdx.x == 0) A.tr_logp[recno * A.n_chains + chain] = logp_sh;
+            if (A.update != UPD_NONE && threadIdx.x < Q) {
+                int q = threadIdx.x, o = q_poff[q], dist = q_dist[q];
+                double p0 = th[o], p1 = (dist == D_EXP) ? 0.0 : th[o + 1];
+                if (A.update == UPD_BAYES) {
+                    Rng rng;
+                    rng.init(A.seed, gchain, gsw, (unsigned int)q, TAG_PARAM);
+                    sample_params(dist, ss[q], rng, p0, p1, &n_pevals);
+                } else {
+                    estimate_params(dist, ss[q], p0, p1);
+                }
+                th[o] = p0;
+                if (dist != D_EXP) th[o + 1] = p1;
+                qconst_set(qc[q], dist, p0, p1);
+            }
+            __syncthreads();
+            if (trace)
+                for (int i = threadIdx.x; i < P; i += blockDim.x)
+                    A.tr_theta[(recno * A.n_chains + chain) * P + i] = th[i];
+        }
+    }
+
+    if (SMEM) {
+        __syncthreads();
+        if ((E & 1) == 0) {
+            double2 *dst = reinterpret_cast<double2 *>(dg);
+            const double2 *src = reinterpret_cast<const double2 *>(d);
+            for (int i = threadIdx.x; i < E / 2; i += blockDim.x) dst[i] = src[i];
+        } else {
+            for (int i = threadIdx.x; i < E; i += blockDim.x) dg[i] = d[i];
+        }
+    }
+    for (int i = threadIdx.x; i < P; i += blockDim.x) A.theta[(size_t)chain * P + i] = th[i];
+    atomicAdd(&cnt[0], (unsigned long long)n_ev);
+    atomicAdd(&cnt[1], (unsigned long long)n_evals);
+    atomicAdd(&cnt[2], (unsigned long long)n_pevals);
+    atomicAdd(&cnt[3], (unsigned long long)n_stuck);
+    __syncthreads();
+    if (threadIdx.x < 4) A.stats[(size_t)chain * 4 + threadIdx.x] += (long long)cnt[threadIdx.x];
+}
+
+// ---- parity / reporting kernels ---------------------------------------------------------------
+
+// out[j] = inner_dfun(x[j]) - lik0 for event described by `r` on chain `chain` (qnet.pyx:1340-1357).
+__global__ void logcond_static_kernel(const SweepArgs A, int chain, SchedRec r, const double *x, int n,
+                                      double *out) {
+    __shared__ QConst qc[2];
+    __shared__ int qt[64];
+    const double *d = A.state + (size_t)chain * A.E;
+    const double *th = A.theta + (size_t)chain * A.P;
+    // only the two queues involved are needed; map them to slots 0/1
+    if (threadIdx.x == 0) {
+        int q = r.q0, o = A.q_poff[q], dist = A.q_dist[q];
+        qconst_set(qc[0], dist, th[o], dist == D_EXP ? 0.0 : th[o + 1]);
+        qt[0] = A.q_type[q];
+        if (r.e1 >= 0) {
+            q = r.q1; o = A.q_poff[q]; dist = A.q_dist[q];
+            qconst_set(qc[1], dist, th[o], dist == D_EXP ? 0.0 : th[o + 1]);
+            qt[1] = A.q_type[q];
+        }
+    }
+    __syncthreads();
+    SchedRec rr = r;
+    rr.q0 = 0; rr.q1 = 1;
+    double tmax = INFINITY;
+    Cond cd;
+    double x0, lower, upper;
+    cond_load(cd, rr, d, qt, qc, x0, lower, upper, tmax);
+    double g0 = cd.eval(x0);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) out[j] = cd.eval(x[j]) - g0;
+}
+
+// Qnet.log_prob (qnet.pyx:1032) and the fused sufficient statistics, one CTA per chain.
+__global__ void __launch_bounds__(256) report_static_kernel(const SweepArgs A, double *logp_out,
+                                                             double *ss_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int chain = blockIdx.x, Q = A.Q;
+    const double *d = A.state + (size_t)chain * A.E;
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    double *scratch = sm;
+    double *red_out = scratch + 34 * 8;
+    QConst *qc = reinterpret_cast<QConst *>(red_out + 8);
+    SuffStat *ss = reinterpret_cast<SuffStat *>(qc + Q);
+    int *q_type = reinterpret_cast<int *>(ss + Q);
+    int *q_dist = q_type + Q;
+    __shared__ double logp_sh;
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+        q_type[q] = A.q_type[q]; q_dist[q] = A.q_dist[q];
+        int o = A.q_poff[q];
+        const double *th = A.theta + (size_t)chain * A.P;
+        qconst_set(qc[q], q_dist[q], th[o], q_dist[q] == D_EXP ? 0.0 : th[o + 1]);
+    }
+    __syncthreads();
+    chain_suffstats(A, d, q_type, q_dist, qc, ss, scratch, red_out, true, &logp_sh);
+    if (threadIdx.x == 0 && logp_out) logp_out[chain] = logp_sh;
+    if (ss_out)
+        for (int i = threadIdx.x; i < Q * 8; i += blockDim.x)
+            ss_out[(size_t)chain * Q * 8 + i] = reinterpret_cast<double *>(ss)[i];
+}
+
+}  // namespace bq

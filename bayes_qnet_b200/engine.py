@@ -1,0 +1,235 @@
+"""GibbsEngine: many independent chains of the reference's sampler on one GPU.
+
+One engine = one ``bq_handle`` = one CUDA device + stream.  It is created from a ``Qnet`` (the model) and an
+initialised ``Arrivals`` (the data and the starting state, replicated to every chain); chains differ only in
+their RNG counters.  ``sweep`` runs the reference's per-iteration work for all chains in one launch:
+``Qnet.slice_resample`` (qnet.pyx:659) followed by ``Qnet.sample_parameters`` (qnet.pyx:882, "BAYES"),
+``Qnet.estimate`` (qnet.pyx:844, "STEM") or nothing ("NONE", ``estimation.sample_departures``).
+"""
+import ctypes
+
+import numpy
+
+from . import capi
+from . import sampling
+
+_UPD = {"NONE": capi.BQ_UPD_NONE, "BAYES": capi.BQ_UPD_BAYES, "STEM": capi.BQ_UPD_STEM}
+_MODE = {"SLICE": capi.BQ_MODE_SLICE, "MH": capi.BQ_MODE_MH}
+SUFFSTAT_FIELDS = ("n", "sum", "sumlog", "sumsq", "nlog", "wait", "nall", "nzero")
+
+
+def flatten_model(net):
+    q_type = capi.as_i32([q.code for q in net.queues])
+    q_k = capi.as_i32([q.k for q in net.queues])
+    q_dist = capi.as_i32([q.service.code for q in net.queues])
+    npar = [q.service.numParameters() for q in net.queues]
+    q_poff = capi.as_i32(numpy.concatenate(([0], numpy.cumsum(npar)[:-1])))
+    return q_type, q_k, q_dist, q_poff, int(sum(npar))
+
+
+class GibbsEngine(object):
+    def __init__(self, net, arrv, n_chains=1, seed=None, device=0, chain_offset=0):
+        self.net = net
+        self.arrv = arrv
+        self.n_chains = int(n_chains)
+        self.chain_offset = int(chain_offset)
+        self.seed = sampling.next_engine_seed() if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
+        L = capi.lib()
+        soa = arrv.soa()
+        self.E = len(soa["d"])
+        self.Q = len(net.queues)
+        q_type, q_k, q_dist, q_poff, self.P = flatten_model(net)
+        self._keep = [q_type, q_k, q_dist, q_poff]
+        m = capi.BqModel(self.Q, self.P, capi.ptr(q_type, capi.c_i32p), capi.ptr(q_k, capi.c_i32p),
+                         capi.ptr(q_dist, capi.c_i32p), capi.ptr(q_poff, capi.c_i32p))
+        arrs = dict((k, capi.as_i32(soa[k])) for k in ("qid", "tid", "prev_byt", "next_byt", "prev_byq", "next_byq"))
+        oa = numpy.ascontiguousarray(soa["obs_a"], dtype=numpy.uint8)
+        od = numpy.ascontiguousarray(soa["obs_d"], dtype=numpy.uint8)
+        d0 = capi.as_f64(soa["d"])
+        a = capi.BqArrivals(self.E, capi.ptr(arrs["qid"], capi.c_i32p), capi.ptr(arrs["tid"], capi.c_i32p),
+                            capi.ptr(oa, capi.c_u8p), capi.ptr(od, capi.c_u8p),
+                            capi.ptr(arrs["prev_byt"], capi.c_i32p), capi.ptr(arrs["next_byt"], capi.c_i32p),
+                            capi.ptr(arrs["prev_byq"], capi.c_i32p), capi.ptr(arrs["next_byq"], capi.c_i32p),
+                            capi.ptr(d0, capi.c_f64p))
+        theta0 = capi.as_f64(net.parameters)
+        h = ctypes.c_void_p()
+        capi.check(L.bq_create(ctypes.byref(m), ctypes.byref(a), capi.ptr(theta0, capi.c_f64p), self.n_chains,
+                               self.chain_offset, self.seed, int(device), ctypes.byref(h)))
+        self._h = h
+        self._L = L
+
+    # ---- lifetime -----------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.bq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- sampling -----------------------------------------------------------------------------------
+    def sweep(self, n_sweeps=1, mode="SLICE", update="NONE", trace=False, tmax_per_sweep=True, tight=False,
+              sample_final=True, sync=True):
+        """n_sweeps Gibbs sweeps of every chain, each followed by the parameter update."""
+        flags = 0
+        if tmax_per_sweep:
+            flags |= capi.BQ_FLAG_TMAX_PER_SWEEP
+        if trace:
+            flags |= capi.BQ_FLAG_TRACE
+        if tight:
+            flags |= capi.BQ_FLAG_TIGHT
+        if not sample_final:
+            flags |= capi.BQ_FLAG_NO_FINAL
+        capi.check(self._L.bq_sweep(self._h, int(n_sweeps), _MODE[mode], _UPD[update], flags))
+        if sync:
+            self.synchronize()
+
+    def synchronize(self):
+        capi.check(self._L.bq_synchronize(self._h))
+
+    def last_sweep_ms(self):
+        ms = ctypes.c_float()
+        capi.check(self._L.bq_last_sweep_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    # ---- parameters and state -------------------------------------------------------------------------
+    def params(self, lo=0, hi=None):
+        hi = self.n_chains if hi is None else hi
+        out = numpy.empty((hi - lo, self.P), dtype=numpy.float64)
+        capi.check(self._L.bq_get_params(self._h, lo, hi, capi.ptr(out, capi.c_f64p)))
+        return out
+
+    def set_params(self, theta, lo=0, hi=None):
+        hi = self.n_chains if hi is None else hi
+        th = numpy.ascontiguousarray(numpy.broadcast_to(numpy.asarray(theta, dtype=numpy.float64),
+                                                        (hi - lo, self.P)))
+        capi.check(self._L.bq_set_params(self._h, lo, hi, capi.ptr(th, capi.c_f64p)))
+
+    def state(self, lo=0, hi=None, full=False):
+        """Departure times [hi-lo, E]; with full=True a dict with a, s, proc and the by-queue links too."""
+        hi = self.n_chains if hi is None else hi
+        n = hi - lo
+        d = numpy.empty((n, self.E), dtype=numpy.float64)
+        if not full:
+            capi.check(self._L.bq_get_state(self._h, lo, hi, capi.ptr(d, capi.c_f64p), None, None, None, None, None))
+            return d
+        a = numpy.empty_like(d)
+        s = numpy.empty_like(d)
+        proc = numpy.empty((n, self.E), dtype=numpy.int32)
+        pq = numpy.empty((n, self.E), dtype=numpy.int32)
+        nq = numpy.empty((n, self.E), dtype=numpy.int32)
+        capi.check(self._L.bq_get_state(self._h, lo, hi, capi.ptr(d, capi.c_f64p), capi.ptr(a, capi.c_f64p),
+                                        capi.ptr(s, capi.c_f64p), capi.ptr(proc, capi.c_i32p),
+                                        capi.ptr(pq, capi.c_i32p), capi.ptr(nq, capi.c_i32p)))
+        return dict(d=d, a=a, s=s, proc=proc, prev_byq=pq, next_byq=nq)
+
+    def set_state(self, d, lo=0, hi=None):
+        hi = self.n_chains if hi is None else hi
+        dd = numpy.ascontiguousarray(numpy.broadcast_to(numpy.asarray(d, dtype=numpy.float64), (hi - lo, self.E)))
+        capi.check(self._L.bq_set_state(self._h, lo, hi, capi.ptr(dd, capi.c_f64p)))
+
+    def to_arrivals(self, chain=0):
+        """A host ``Arrivals`` holding the current state of one chain."""
+        st = self.state(chain, chain + 1, full=True)
+        out = self.arrv.duplicate()
+        out._d[:] = st["d"][0]
+        out._a[:] = st["a"][0]
+        out._s[:] = st["s"][0]
+        out._proc[:] = st["proc"][0]
+        out._prev_byq[:] = st["prev_byq"][0]
+        out._next_byq[:] = st["next_byq"][0]
+        has = out._prev_byq >= 0
+        return out
+
+    def write_back(self, arrv, chain=0):
+        """Copy one chain's state into an existing Arrivals (the reference's samplers mutate in place)."""
+        st = self.state(chain, chain + 1, full=True)
+        arrv._d[:] = st["d"][0]
+        arrv._a[:] = st["a"][0]
+        arrv._s[:] = st["s"][0]
+        arrv._proc[:] = st["proc"][0]
+        arrv._prev_byq[:] = st["prev_byq"][0]
+        arrv._next_byq[:] = st["next_byq"][0]
+
+    # ---- parity hooks and reporting ---------------------------------------------------------------------
+    def logcond(self, chain, row, xs):
+        """GGkGibbs.inner_dfun(x) - lik0 (qnet.pyx:1340-1357) for event `row` of `chain` at the points xs."""
+        xs = capi.as_f64(xs)
+        out = numpy.empty(len(xs), dtype=numpy.float64)
+        capi.check(self._L.bq_logcond(self._h, int(chain), int(row), capi.ptr(xs, capi.c_f64p), len(xs),
+                                      capi.ptr(out, capi.c_f64p)))
+        return out
+
+    def log_prob(self):
+        out = numpy.empty(self.n_chains, dtype=numpy.float64)
+        capi.check(self._L.bq_log_prob(self._h, capi.ptr(out, capi.c_f64p)))
+        return out
+
+    def suffstats(self):
+        """[n_chains, n_queues, 8]: see SUFFSTAT_FIELDS."""
+        out = numpy.empty((self.n_chains, self.Q, 8), dtype=numpy.float64)
+        capi.check(self._L.bq_suffstats(self._h, capi.ptr(out, capi.c_f64p)))
+        return out
+
+    def mean_wait(self):
+        ss = self.suffstats()
+        return ss[:, :, 5] / numpy.maximum(ss[:, :, 6], 1.0)
+
+    def stats(self):
+        st = capi.BqStats()
+        capi.check(self._L.bq_stats(self._h, ctypes.byref(st)))
+        return dict((k, int(getattr(st, k))) for k, _ in capi.BqStats._fields_)
+
+    def reset_stats(self):
+        capi.check(self._L.bq_reset_stats(self._h))
+
+    def trace_len(self):
+        n = ctypes.c_int32()
+        capi.check(self._L.bq_trace_len(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def traces(self):
+        """(theta [n_rec, C, P], mean_wait [n_rec, C, Q], logp [n_rec, C]) recorded by sweep(trace=True)."""
+        n = self.trace_len()
+        th = numpy.empty((n, self.n_chains, self.P))
+        mw = numpy.empty((n, self.n_chains, self.Q))
+        lp = numpy.empty((n, self.n_chains))
+        if n:
+            capi.check(self._L.bq_get_trace(self._h, capi.ptr(th, capi.c_f64p), capi.ptr(mw, capi.c_f64p),
+                                            capi.ptr(lp, capi.c_f64p)))
+        return th, mw, lp
+
+    def clear_traces(self):
+        capi.check(self._L.bq_clear_trace(self._h))
+
+    def schedule(self):
+        """(color_off [n_colors+1], order [n_eligible]): the conflict-free sweep schedule."""
+        nc, ne = ctypes.c_int32(), ctypes.c_int32()
+        capi.check(self._L.bq_get_schedule(self._h, ctypes.byref(nc), ctypes.byref(ne), None, None))
+        off = numpy.empty(nc.value + 1, dtype=numpy.int32)
+        order = numpy.empty(ne.value, dtype=numpy.int32)
+        capi.check(self._L.bq_get_schedule(self._h, None, None, capi.ptr(off, capi.c_i32p), capi.ptr(order, capi.c_i32p)))
+        return off, order
+
+    def kernel_info(self):
+        t, s, m = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        capi.check(self._L.bq_kernel_info(self._h, ctypes.byref(t), ctypes.byref(s), ctypes.byref(m)))
+        return dict(threads=int(t.value), smem_bytes=int(s.value), state_in_smem=bool(m.value))
+
+    def device_pointers(self):
+        """Raw device addresses (state, trace arrays) for zero-copy wrapping by torch / NCCL code."""
+        p = ctypes.c_void_p()
+        stride = ctypes.c_int64()
+        capi.check(self._L.bq_state_dev(self._h, ctypes.byref(p), ctypes.byref(stride)))
+        t, w, l = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        capi.check(self._L.bq_trace_dev(self._h, ctypes.byref(t), ctypes.byref(w), ctypes.byref(l)))
+        return dict(state=p.value, chain_stride=int(stride.value), tr_theta=t.value, tr_wait=w.value, tr_logp=l.value)

@@ -1,0 +1,118 @@
+"""Estimation drivers with the reference's signatures (estimation.py:29-257): ``bayes``, ``sem``,
+``sample_departures``.  Each outer iteration of the reference -- one sweep over the hidden times, then one
+parameter update -- is one fused step of the GPU engine, and all iterations of a call run in a single
+kernel launch.  ``n_chains > 1`` runs that many independent chains from the same initial state (new; the
+reference is single-chain): the return value stays ``(mus, arrvl)`` for chain 0, and the whole ensemble is
+available from ``last_run()``.
+"""
+import time
+
+import numpy
+
+from . import qnet as _qnet
+from . import diagnostics
+from .engine import GibbsEngine
+
+MH, SLICE = 0, 1
+_sampling_type = SLICE
+_last = None
+
+
+def set_sampler(name):
+    """sampling_type: SLICE (default) or MH (estimation.py:20-25)."""
+    global _sampling_type
+    if name == "SLICE":
+        _sampling_type = SLICE
+    elif name == "MH":
+        _sampling_type = MH
+    else:
+        raise Exception("Could not understand estimator %s" % name)
+
+
+def _mode():
+    return "SLICE" if _sampling_type == SLICE else "MH"
+
+
+class Run(object):
+    """Everything one estimation call produced, for all chains."""
+
+    def __init__(self, engine, theta, mean_wait, logp, seconds):
+        self.engine = engine
+        self.theta = theta          # [n_iter, n_chains, n_params]
+        self.mean_wait = mean_wait  # [n_iter, n_chains, n_queues]
+        self.logp = logp            # [n_iter, n_chains]
+        self.seconds = seconds
+        self.stats = engine.stats()
+
+    def rhat(self):
+        return diagnostics.rhat(self.theta)
+
+    def ess(self):
+        return diagnostics.ess(self.theta)
+
+    def posterior_mean(self):
+        return self.theta.mean(axis=(0, 1))
+
+
+def last_run():
+    return _last
+
+
+def _run(net, arrv, num_iter, update, n_chains, seed, device, report_fn, return_arrv, gibbs_iter=1):
+    global _last
+    eng = GibbsEngine(net, arrv, n_chains=n_chains, seed=seed, device=device)
+    t0 = time.time()
+    all_sampled = []
+    if report_fn or return_arrv or gibbs_iter != 1:
+        for i in range(num_iter):
+            if gibbs_iter > 1:
+                eng.sweep(gibbs_iter - 1, _mode(), "NONE", tmax_per_sweep=False)
+            eng.sweep(1, _mode(), update, trace=True)
+            if report_fn or return_arrv:
+                snap = eng.to_arrivals(0)
+                if report_fn:
+                    report_fn(net, snap, i, float(eng.traces()[2][-1, 0]))
+                if return_arrv:
+                    all_sampled.append(snap)
+    else:
+        eng.sweep(num_iter, _mode(), update, trace=True)
+    theta, mw, lp = eng.traces()
+    secs = time.time() - t0
+    eng.write_back(arrv, 0)
+    net.parameters = list(eng.params(0, 1)[0])
+    st = eng.stats()
+    _qnet._absorb(dict(nevents=0, nreject=0, num_diff=0, diff_len=0), st)
+    _last = Run(eng, theta, mw, lp, secs)
+    mus = [list(theta[i, 0, :]) for i in range(theta.shape[0])]
+    if not return_arrv:
+        all_sampled = [arrv]
+    return mus, all_sampled
+
+
+def bayes(net, arrv, num_iter, report_fn=None, return_arrv=False, reverse=False, sweeten=0, tag="MU",
+          n_chains=1, seed=None, device=0):
+    """Gibbs sampling of hidden times and service parameters (estimation.py:104-169)."""
+    if reverse:
+        raise NotImplementedError("reverse scan: the kernels use their own conflict-free scan order")
+    _qnet.reset_stats()
+    if sweeten:
+        net.slice_resample(arrv, sweeten)
+    net.estimate(arrv)  # initialise the parameters from the Gibbs initialisation (estimation.py:124)
+    return _run(net, arrv, num_iter, "BAYES", n_chains, seed, device, report_fn, return_arrv)
+
+
+def sem(net, arrv, burn, num_iter, gibbs_iter=1, momentum=0, return_arrv=False, report_fn=None,
+        burn_report_fn=None, debug=False, n_chains=1, seed=None, device=0):
+    """Stochastic EM (estimation.py:29-100)."""
+    if momentum:
+        raise NotImplementedError("momentum in sem()")
+    _qnet.reset_stats()
+    net.estimate(arrv)
+    mus, arrvl = _run(net, arrv, burn + num_iter, "STEM", n_chains, seed, device, None, return_arrv, gibbs_iter)
+    return mus[burn:], (arrvl[burn:] if return_arrv else arrvl)
+
+
+def sample_departures(net, arrv, num_iter, report_fn=None, debug=False, n_chains=1, seed=None, device=0):
+    """Sweeps with the parameters held fixed (estimation.py:171-224)."""
+    _qnet.reset_stats()
+    return _run(net, arrv, num_iter, "NONE", n_chains, seed, device, report_fn, True)

@@ -1,0 +1,341 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by running the REFERENCE ITSELF (oracle/_ref, built by oracle/build_ref.py from
+/root/reference/src with a mechanical Py2->Py3 patch).  TEST INFRASTRUCTURE ONLY.
+
+The reference cannot travel to the GPU box, so its outputs are committed as small fixtures:
+
+  lpdf_kat.npz        Distribution.lpdf values (distributions.pyx) at fixed points, incl. the reference's own
+                      known answers (test_distributions.py:44-46, 62-75).
+  cond_<net>.npz      for each network: a state produced by the reference (sample -> subset_by_task ->
+                      gibbs_initialize [-> a few slice sweeps]), flat fp64 arrays + links, Qnet.log_prob, and
+                      for a set of hidden events the values of GGkGibbs.inner_dfun (qnet.pyx:1340-1357) on a grid
+                      -- the test_likdelta.py:43-75 identity turned into fixed vectors.
+  post_<net>.npz      traces of estimation.bayes (estimation.py:104) run long by the reference from a saved
+                      initial state: service parameters per iteration and per-queue mean waiting time -- the
+                      statistical pin for posterior agreement.
+
+Usage: python oracle/make_golden.py [--only NAME] [--skip-post]
+"""
+import argparse
+import contextlib
+import io
+import os
+import sys
+import time
+
+import numpy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, "_ref")
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+sys.path.insert(0, REF)
+
+_sink = io.StringIO()
+with contextlib.redirect_stdout(_sink):
+    import qnetu, qnet, sampling, estimation, arrivals, qstats, distributions  # noqa: E402
+sampling.DEBUG = 0
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+NETS = {
+    # config 1 of BASELINE.json: source M(1.0) -> single-server M(0.7)
+    "mm1": """
+states:
+  - name: INITIAL
+    queues: [ INITIAL ]
+    successors: [ TIER1 ]
+    initial: TRUE
+  - name: TIER1
+    queues: [ WEB1 ]
+queues:
+  - { name: INITIAL, service: [M, 1.0] }
+  - { name: WEB1, service: [M, 0.7] }
+""",
+    # the paper's 3-tier model (test_qnet.py:1056-1078) with the parameters of test_qnet.py:589
+    "qnet3": """
+states:
+  - name: INITIAL
+    queues: [ INITIAL ]
+    successors: [ TIER1 ]
+    initial: TRUE
+  - name: TIER1
+    queues: [ WEB1, WEB2, WEB3 ]
+    successors: [ TIER2 ]
+  - name: TIER2
+    queues: [ APP1, APP2 ]
+    successors: [ TIER3 ]
+  - name: TIER3
+    queues: [ DB ]
+queues:
+  - { name: INITIAL, service: [M, 1.0] }
+  - { name: WEB1, service: [M, 0.2] }
+  - { name: WEB2, service: [M, 0.2] }
+  - { name: WEB3, service: [M, 0.2] }
+  - { name: APP1, service: [M, 0.05] }
+  - { name: APP2, service: [M, 0.05] }
+  - { name: DB, service: [M, 0.3] }
+""",
+    # delay station (test_delay_station.py:116-126) behind a FIFO stage
+    "delay": """
+states:
+  - name: I0
+    queues: [ I0 ]
+    successors: [ S1 ]
+  - name: S1
+    queues: [ Q1 ]
+    successors: [ S2 ]
+  - name: S2
+    queues: [ Q2 ]
+queues:
+  - { name: I0, service: [M, 1.0] }
+  - { name: Q1, service: [M, 0.5] }
+  - { name: Q2, service: [M, 2.0], type: DELAY }
+""",
+    # lognormal / gamma single-server tandem (test_mh_ggk.py ln1a shape; gamma3 of test_qnet.py)
+    "lng1": """
+states:
+  - name: INITIAL
+    queues: [ INITIAL ]
+    successors: [ TIER1 ]
+    initial: TRUE
+  - name: TIER1
+    queues: [ WEB1 ]
+    successors: [ TIER2 ]
+  - name: TIER2
+    queues: [ APP1 ]
+queues:
+  - { name: INITIAL, service: [M, 10.0] }
+  - { name: WEB1, processors: 1, type: GG1, service: [LN, 0.75, 0.8] }
+  - { name: APP1, processors: 1, type: GG1, service: [G, 2.0, 1.5] }
+""",
+    # multi-server FIFO (examples/models/mm3.yml)
+    "mm3": """
+states:
+  - name: INITIAL
+    queues: [ INITIAL ]
+    successors: [ TIER1 ]
+    initial: TRUE
+  - name: TIER1
+    queues: [ WEB1 ]
+    successors: [ TIER2 ]
+  - name: TIER2
+    queues: [ APP1 ]
+queues:
+  - { name: INITIAL, service: [M, 10.0]  }
+  - { name: WEB1, processors: 3, service: [M, 30.0] }
+  - { name: APP1, processors: 4, service: [M, 30.0] }
+""",
+    # lognormal G/G/3 tandem (test_mh_ggk.py:924-939), source scaled so the stations are stable
+    "lnk": """
+states:
+  - name: INITIAL
+    queues: [ INITIAL ]
+    successors: [ TIER1 ]
+    initial: TRUE
+  - name: TIER1
+    queues: [ WEB1 ]
+    successors: [ TIER2 ]
+  - name: TIER2
+    queues: [ APP1 ]
+queues:
+  - { name: INITIAL, service: [M, 5.0]  }
+  - { name: WEB1, processors: 3, type: GGk, service: [LN, 1.75, 1.0] }
+  - { name: APP1, processors: 3, type: GGk, service: [LN, 0.1, 2.0] }
+""",
+    # processor sharing + delay station (test_ps.py:266-292 + test_delay_station.py:116-126): config 4's shape
+    "psdelay": """
+states:
+  - name: I0
+    queues: [ I0 ]
+    successors: [ S1 ]
+  - name: S1
+    queues: [ Q1 ]
+    successors: [ S2 ]
+  - name: S2
+    queues: [ Q2 ]
+queues:
+  - { name: I0, service: [M, 1.0] }
+  - { name: Q1, service: [M, 0.5], type: PS }
+  - { name: Q2, service: [M, 2.0], type: DELAY }
+""",
+}
+
+# name -> (tasks, pct observed, initializer, seed, sweeps before the second snapshot)
+COND = {
+    "mm1": (60, 0.5, "DFN2", 13, 3),
+    "qnet3": (80, 0.2, "DFN2", 14, 3),
+    "delay": (60, 0.3, "NONE", 15, 3),   # DelayStation has no departure_of_service: DFN cannot initialise it
+    "lng1": (60, 0.3, "DFN2", 16, 3),
+    "mm3": (80, 0.2, "DFN2", 17, 5),
+    "lnk": (60, 0.2, "DFN2", 18, 5),
+    "psdelay": (50, 0.2, "PS", 19, 3),
+}
+
+# name -> (tasks, pct, initializer, seed, iterations, replicas)
+POST = {
+    "mm1": (200, 0.5, "DFN2", 13, 1500, 4),      # BASELINE.json configs[0]
+    "qnet3": (150, 0.2, "DFN2", 21, 1200, 3),
+    "lng1": (100, 0.3, "DFN2", 22, 1000, 3),
+    "mm3": (100, 0.3, "DFN2", 23, 800, 2),
+    "psdelay": (80, 0.3, "PS", 24, 800, 2),
+}
+
+
+def flatten(arrv):
+    """Rows = events, each task's events contiguous and in visit order; links as row indices."""
+    evts = []
+    for tid in sorted(arrv.all_tasks()):
+        evts.extend(arrv.events_of_task(tid))
+    row = dict((e.eid, i) for i, e in enumerate(evts))
+    lk = lambda e: row[e.eid] if e is not None else -1
+    out = dict(
+        eid=numpy.array([e.eid for e in evts], dtype=numpy.int32),
+        tid=numpy.array([e.tid for e in evts], dtype=numpy.int32),
+        qid=numpy.array([e.qid for e in evts], dtype=numpy.int32),
+        state=numpy.array([e.state for e in evts], dtype=numpy.int32),
+        a=numpy.array([e.a for e in evts], dtype=numpy.float64),
+        d=numpy.array([e.d for e in evts], dtype=numpy.float64),
+        s=numpy.array([e.s for e in evts], dtype=numpy.float64),
+        proc=numpy.array([e.proc for e in evts], dtype=numpy.int32),
+        obs_a=numpy.array([e.obs_a for e in evts], dtype=numpy.uint8),
+        obs_d=numpy.array([e.obs_d for e in evts], dtype=numpy.uint8),
+        prev_byt=numpy.array([lk(e.previous_by_task()) for e in evts], dtype=numpy.int32),
+        next_byt=numpy.array([lk(e.next_by_task()) for e in evts], dtype=numpy.int32),
+        prev_byq=numpy.array([lk(e.previous_by_queue()) for e in evts], dtype=numpy.int32),
+        next_byq=numpy.array([lk(e.next_by_queue()) for e in evts], dtype=numpy.int32),
+    )
+    return out, evts
+
+
+def make_state(name, ntasks, pct, init, seed):
+    net = qnetu.qnet_from_text(NETS[name])
+    qnetu.set_seed(seed)
+    with quiet():
+        qnet.set_initialization_type(init)
+        smp = net.sample(ntasks)
+        sub = smp.subset_by_task(pct)
+        ini = net.gibbs_initialize(sub)
+        qnet.set_initialization_type("DFN2")
+    ini.validate()
+    return net, ini
+
+
+def cond_grid(net, arrv, max_events, rng):
+    """inner_dfun on a grid for up to max_events resample-eligible events (qnet.pyx:688)."""
+    flat, evts = flatten(arrv)
+    elig = [i for i, e in enumerate(evts)
+            if not e.obs_d and (e.next_by_task() is None or not e.next_by_task().obs_a)]
+    rng.shuffle(elig)
+    elig = sorted(elig[:max_events])
+    tmax = 2 * max(e.d for e in evts)
+    rows, xs, vals = [], [], []
+    for i in elig:
+        e = evts[i]
+        nxt = e.next_by_task()
+        lo, hi = e.a, (nxt.d if nxt is not None else min(tmax, e.d + 3 * (e.d - e.a) + 1.0))
+        g = numpy.concatenate(([e.d], lo + (hi - lo) * numpy.array([0.03, 0.2, 0.4, 0.5, 0.6, 0.8, 0.97]),
+                               lo + (hi - lo) * rng.rand(4), [lo - 0.1, hi + 0.1]))
+        if any(type(q).__name__ == "QueuePS" for q in net.queues):
+            g = g[:-2]  # QueuePS asserts (queues.pyx:1068) when evaluated outside [a_e, upper]
+        dfn = qnet.GGkGibbs(net, arrv, e, 0.0).dfn()
+        with quiet():
+            v = numpy.array([dfn(float(x)) for x in g])
+        rows.append(i); xs.append(g); vals.append(v)
+    return flat, numpy.array(rows, dtype=numpy.int32), numpy.array(xs), numpy.array(vals)
+
+
+def do_cond(name):
+    ntasks, pct, init, seed, nsweeps = COND[name]
+    net, arrv = make_state(name, ntasks, pct, init, seed)
+    rng = numpy.random.RandomState(seed + 1000)
+    out = dict(yaml=NETS[name], theta=numpy.array(net.parameters, dtype=numpy.float64))
+    flat, rows, xs, vals = cond_grid(net, arrv, 40, rng)
+    for k, v in flat.items():
+        out["s0_" + k] = v
+    out.update(s0_rows=rows, s0_x=xs, s0_g=vals, s0_logprob=net.log_prob(arrv))
+    with quiet():
+        net.slice_resample(arrv, nsweeps)
+    arrv.validate()
+    flat, rows, xs, vals = cond_grid(net, arrv, 40, rng)
+    for k, v in flat.items():
+        out["s1_" + k] = v
+    out.update(s1_rows=rows, s1_x=xs, s1_g=vals, s1_logprob=net.log_prob(arrv))
+    # the same state under different parameters (exercises the lpdf constants)
+    theta2 = [p * 1.3 + 0.05 for p in net.parameters]
+    net.parameters = theta2
+    flat, rows, xs, vals = cond_grid(net, arrv, 15, rng)
+    out.update(s2_theta=numpy.array(theta2), s2_rows=rows, s2_x=xs, s2_g=vals, s2_logprob=net.log_prob(arrv))
+    numpy.savez_compressed(os.path.join(OUT, "cond_%s.npz" % name), **out)
+    print("cond_%s: E=%d, %d+%d+%d events on grids" % (name, len(flat["d"]), len(out["s0_rows"]), len(out["s1_rows"]), len(rows)))
+
+
+def do_post(name):
+    ntasks, pct, init, seed, niter, nrep = POST[name]
+    net, ini = make_state(name, ntasks, pct, init, seed)
+    theta0 = list(net.parameters)
+    flat, _ = flatten(ini)
+    thetas, waits, rate = [], [], []
+    for r in range(nrep):
+        net.parameters = theta0[:]
+        arrv = ini.duplicate()
+        qnetu.set_seed(1000 * seed + r)
+        w = []
+        t0 = time.time()
+        with quiet():
+            mus, _ = estimation.bayes(net, arrv, niter, report_fn=lambda n, a, i, lp: w.append(qstats.mean_wait(a)))
+        dt = time.time() - t0
+        thetas.append(numpy.array(mus))
+        waits.append(numpy.array(w))
+        rate.append(qnet.stats()["nevents"] / dt)
+    out = dict(yaml=NETS[name], theta0=numpy.array(theta0), theta=numpy.array(thetas), mean_wait=numpy.array(waits),
+               ref_resamples_per_s=numpy.array(rate))
+    for k, v in flat.items():
+        out["s0_" + k] = v
+    numpy.savez_compressed(os.path.join(OUT, "post_%s.npz" % name), **out)
+    print("post_%s: E=%d iters=%d reps=%d  ref %.0f resamples/s  theta mean %s" % (
+        name, len(flat["d"]), niter, nrep, numpy.mean(rate), numpy.array(thetas)[:, niter // 5:].mean(axis=(0, 1))))
+
+
+def do_lpdf():
+    pts = numpy.array([1e-6, 0.01, 0.1, 0.5, 1.0, 2.0, 3.7, 10.0, 55.0])
+    cases = []
+    for p in (0.05, 0.7, 1.0, 30.0):
+        f = distributions.Exponential(p)
+        cases.append((0, p, 0.0, [f.lpdf(x) for x in pts]))
+    for sh, sc in ((3.0, 0.5), (1.0, 2.0), (0.7, 1.5), (12.0, 0.1)):
+        f = distributions.Gamma(sh, sc)
+        cases.append((1, sh, sc, [f.lpdf(x) for x in pts]))
+    for mu, sd in ((0.0, 1.0), (1.75, 1.0), (0.1, 2.0), (-1.0, 0.3)):
+        f = distributions.LogNormal(mu, sd)
+        cases.append((2, mu, sd, [f.lpdf(x) for x in pts]))
+    numpy.savez_compressed(os.path.join(OUT, "lpdf_kat.npz"), x=pts,
+                           dist=numpy.array([c[0] for c in cases], dtype=numpy.int32),
+                           p0=numpy.array([c[1] for c in cases]), p1=numpy.array([c[2] for c in cases]),
+                           lpdf=numpy.array([c[3] for c in cases]),
+                           ln_at_zero=distributions.LogNormal(0.0, 1.0).lpdf(0.0))
+    print("lpdf_kat: %d cases; Gamma(3,0.5).lpdf(2) = %.6f (reference test pins -1.227411)" % (
+        len(cases), distributions.Gamma(3.0, 0.5).lpdf(2.0)))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--skip-post", action="store_true")
+    ap.add_argument("--skip-cond", action="store_true")
+    args = ap.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    if args.only in (None, "lpdf"):
+        do_lpdf()
+    if not args.skip_cond:
+        for n in COND:
+            if args.only in (None, n):
+                do_cond(n)
+    if not args.skip_post:
+        for n in POST:
+            if args.only in (None, n):
+                do_post(n)

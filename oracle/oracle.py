@@ -1,0 +1,156 @@
+"""ctypes wrapper of oracle/libbq_oracle.so (bq_oracle.c).  TEST INFRASTRUCTURE ONLY: imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline leg; never by bayes_qnet_b200/."""
+import ctypes
+import os
+import subprocess
+
+import numpy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libbq_oracle.so")
+SRC = os.path.join(HERE, "bq_oracle.c")
+
+i32p = ctypes.POINTER(ctypes.c_int32)
+u8p = ctypes.POINTER(ctypes.c_uint8)
+f64p = ctypes.POINTER(ctypes.c_double)
+
+
+class _State(ctypes.Structure):
+    _fields_ = [("E", ctypes.c_int), ("Q", ctypes.c_int), ("q_type", i32p), ("q_k", i32p), ("q_dist", i32p),
+                ("q_poff", i32p), ("theta", f64p), ("qid", i32p), ("prev_byt", i32p), ("next_byt", i32p),
+                ("obs_a", u8p), ("obs_d", u8p), ("a", f64p), ("d", f64p), ("s", f64p), ("proc", i32p),
+                ("prev_byq", i32p), ("next_byq", i32p)]
+
+
+def build(force=False):
+    if force or not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", SO, SRC, "-lm"])
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build())
+        L.bqo_lpdf.restype = ctypes.c_double
+        L.bqo_lpdf.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+        L.bqo_recompute.argtypes = [ctypes.POINTER(_State)]
+        L.bqo_log_prob.restype = ctypes.c_double
+        L.bqo_log_prob.argtypes = [ctypes.POINTER(_State)]
+        L.bqo_logcond.argtypes = [ctypes.POINTER(_State), ctypes.c_int, f64p, ctypes.c_int, f64p]
+        L.bqo_apply.argtypes = [ctypes.POINTER(_State), ctypes.c_int, ctypes.c_double]
+        L.bqo_eligible.restype = ctypes.c_int
+        L.bqo_eligible.argtypes = [ctypes.POINTER(_State), ctypes.c_int]
+        L.bqo_slice_sweep.restype = ctypes.c_long
+        L.bqo_slice_sweep.argtypes = [ctypes.POINTER(_State), i32p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64,
+                                      ctypes.c_uint32, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_long)]
+        L.bqo_suffstats.argtypes = [ctypes.POINTER(_State), f64p]
+        L.bqo_estimate.argtypes = [ctypes.c_int, f64p, f64p, f64p]
+        L.bqo_sample_params.argtypes = [ctypes.c_int, f64p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32,
+                                        ctypes.c_uint32, f64p, f64p]
+        L.bqo_rng_uniforms.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint32,
+                                       ctypes.c_uint32, ctypes.c_int, f64p]
+        _lib = L
+    return _lib
+
+
+def lpdf(dist, p0, p1, x):
+    return lib().bqo_lpdf(int(dist), float(p0), float(p1), float(x))
+
+
+def rng_uniforms(seed, chain, sweep, ident, tag, n):
+    out = numpy.empty(n)
+    lib().bqo_rng_uniforms(seed, chain, sweep, ident, tag, n, out.ctypes.data_as(f64p))
+    return out
+
+
+class OracleChain(object):
+    """One chain of the CPU oracle.  Built from flat arrays (row indices as event ids)."""
+
+    def __init__(self, q_type, q_k, q_dist, theta, qid, prev_byt, next_byt, obs_a, obs_d, d, prev_byq, next_byq):
+        I = lambda x: numpy.ascontiguousarray(x, dtype=numpy.int32).copy()
+        self.q_type, self.q_k, self.q_dist = I(q_type), I(q_k), I(q_dist)
+        npar = numpy.where(self.q_dist == 0, 1, 2)
+        self.q_poff = I(numpy.concatenate(([0], numpy.cumsum(npar)[:-1])))
+        self.theta = numpy.ascontiguousarray(theta, dtype=numpy.float64).copy()
+        self.qid, self.prev_byt, self.next_byt = I(qid), I(prev_byt), I(next_byt)
+        self.obs_a = numpy.ascontiguousarray(obs_a, dtype=numpy.uint8).copy()
+        self.obs_d = numpy.ascontiguousarray(obs_d, dtype=numpy.uint8).copy()
+        self.d = numpy.ascontiguousarray(d, dtype=numpy.float64).copy()
+        self.E, self.Q = len(self.d), len(self.q_type)
+        self.a = numpy.zeros(self.E)
+        self.s = numpy.zeros(self.E)
+        self.proc = numpy.zeros(self.E, dtype=numpy.int32)
+        self.prev_byq, self.next_byq = I(prev_byq), I(next_byq)
+        self._st = _State(self.E, self.Q, self.q_type.ctypes.data_as(i32p), self.q_k.ctypes.data_as(i32p),
+                          self.q_dist.ctypes.data_as(i32p), self.q_poff.ctypes.data_as(i32p),
+                          self.theta.ctypes.data_as(f64p), self.qid.ctypes.data_as(i32p),
+                          self.prev_byt.ctypes.data_as(i32p), self.next_byt.ctypes.data_as(i32p),
+                          self.obs_a.ctypes.data_as(u8p), self.obs_d.ctypes.data_as(u8p),
+                          self.a.ctypes.data_as(f64p), self.d.ctypes.data_as(f64p), self.s.ctypes.data_as(f64p),
+                          self.proc.ctypes.data_as(i32p), self.prev_byq.ctypes.data_as(i32p),
+                          self.next_byq.ctypes.data_as(i32p))
+        self.recompute()
+
+    @classmethod
+    def from_arrivals(cls, net, arrv, theta=None):
+        soa = arrv.soa()
+        return cls([q.code for q in net.queues], [q.k for q in net.queues], [q.service.code for q in net.queues],
+                   net.parameters if theta is None else theta, soa["qid"], soa["prev_byt"], soa["next_byt"],
+                   soa["obs_a"], soa["obs_d"], soa["d"], soa["prev_byq"], soa["next_byq"])
+
+    def set_theta(self, theta):
+        self.theta[:] = theta
+
+    def recompute(self):
+        lib().bqo_recompute(ctypes.byref(self._st))
+
+    def log_prob(self):
+        return lib().bqo_log_prob(ctypes.byref(self._st))
+
+    def logcond(self, e, xs):
+        xs = numpy.ascontiguousarray(xs, dtype=numpy.float64)
+        out = numpy.empty(len(xs))
+        lib().bqo_logcond(ctypes.byref(self._st), int(e), xs.ctypes.data_as(f64p), len(xs), out.ctypes.data_as(f64p))
+        return out
+
+    def apply(self, e, x):
+        lib().bqo_apply(ctypes.byref(self._st), int(e), float(x))
+
+    def eligible(self):
+        return numpy.array([e for e in range(self.E) if lib().bqo_eligible(ctypes.byref(self._st), e)], dtype=numpy.int32)
+
+    def slice_sweep(self, order, seed, chain, sweep, tmax=None):
+        order = numpy.ascontiguousarray(order, dtype=numpy.int32)
+        if tmax is None:
+            tmax = 2.0 * self.d.max()  # qnet.pyx:672
+        ev = ctypes.c_long(0)
+        ne = lib().bqo_slice_sweep(ctypes.byref(self._st), order.ctypes.data_as(i32p), len(order), seed, chain, sweep,
+                                   float(tmax), 0, ctypes.byref(ev))
+        return int(ne), int(ev.value)
+
+    def suffstats(self):
+        out = numpy.zeros((self.Q, 8))
+        lib().bqo_suffstats(ctypes.byref(self._st), out.ctypes.data_as(f64p))
+        return out
+
+    def update_params(self, update, seed=0, chain=0, sweep=0):
+        """update in {'BAYES','STEM'}: applies Qnet.sample_parameters / Qnet.estimate to self.theta."""
+        ss = self.suffstats()
+        for q in range(self.Q):
+            o = int(self.q_poff[q])
+            p0 = ctypes.c_double(self.theta[o])
+            p1 = ctypes.c_double(self.theta[o + 1] if self.q_dist[q] != 0 else 0.0)
+            row = numpy.ascontiguousarray(ss[q])
+            if update == "STEM":
+                lib().bqo_estimate(int(self.q_dist[q]), row.ctypes.data_as(f64p), ctypes.byref(p0), ctypes.byref(p1))
+            else:
+                lib().bqo_sample_params(int(self.q_dist[q]), row.ctypes.data_as(f64p), seed, chain, sweep, q,
+                                        ctypes.byref(p0), ctypes.byref(p1))
+            self.theta[o] = p0.value
+            if self.q_dist[q] != 0:
+                self.theta[o + 1] = p1.value
+        return self.theta.copy()
