@@ -150,8 +150,9 @@ class Arrivals(object):
     # ---- construction -------------------------------------------------------------------------
     @classmethod
     def from_arrays(cls, net, tid, qid, state, a, d, obs_a=None, obs_d=None, eid=None, proc=None, s=None,
-                    recompute=True):
-        """Rows must list each task's events in visit order (any interleaving between tasks)."""
+                    recompute=True, prev_byq=None, next_byq=None):
+        """Rows must list each task's events in visit order (any interleaving between tasks).  The by-queue
+        order is derived from the times unless explicit prev_byq/next_byq links are given."""
         self = cls(net)
         n = len(tid)
         self._n = n
@@ -166,6 +167,9 @@ class Arrivals(object):
         self._eid = numpy.arange(n, dtype=numpy.int32) if eid is None else numpy.asarray(eid, dtype=numpy.int32).copy()
         self._proc = numpy.zeros(n, dtype=numpy.int32) if proc is None else numpy.asarray(proc, dtype=numpy.int32).copy()
         self._relink()
+        if prev_byq is not None:
+            self._prev_byq = numpy.asarray(prev_byq, dtype=numpy.int32).copy()
+            self._next_byq = numpy.asarray(next_byq, dtype=numpy.int32).copy()
         if recompute:
             self.recompute_all_service()
         return self

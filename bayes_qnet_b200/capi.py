@@ -56,6 +56,7 @@ SYMBOLS = {
     "bq_set_params": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p]),
     "bq_get_params": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p]),
     "bq_set_state": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p]),
+    "bq_broadcast_state": (ctypes.c_int, [_H, c_f64p]),
     "bq_get_state": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p, c_f64p, c_f64p, c_i32p, c_i32p, c_i32p]),
     "bq_state_dev": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64)]),
     "bq_sweep": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32]),

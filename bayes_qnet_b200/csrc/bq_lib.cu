@@ -375,6 +375,21 @@ extern "C" int bq_set_state(bq_handle *h, int32_t lo, int32_t hi, const double *
     return BQ_OK;
 }
 
+// One chain's departure times from the host, replicated to every chain on the device (E*8 bytes cross PCIe).
+extern "C" int bq_broadcast_state(bq_handle *h, const double *d) {
+    if (!h || !d) return fail(BQ_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    const size_t E = h->E, C = h->C;
+    CK(cudaMemcpyAsync(h->d_state, d, E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    for (size_t have = 1; have < C; have *= 2) {
+        size_t n = std::min(have, C - have);
+        CK(cudaMemcpyAsync(h->d_state + have * E, h->d_state, n * E * sizeof(double), cudaMemcpyDeviceToDevice,
+                           h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return BQ_OK;
+}
+
 extern "C" int bq_get_state(bq_handle *h, int32_t lo, int32_t hi, double *d, double *a, double *s,
                             int32_t *proc, int32_t *prev_byq, int32_t *next_byq) {
     if (int r = check_range(h, lo, hi)) return r;

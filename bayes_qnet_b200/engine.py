@@ -137,6 +137,12 @@ class GibbsEngine(object):
         dd = numpy.ascontiguousarray(numpy.broadcast_to(numpy.asarray(d, dtype=numpy.float64), (hi - lo, self.E)))
         capi.check(self._L.bq_set_state(self._h, lo, hi, capi.ptr(dd, capi.c_f64p)))
 
+    def broadcast_state(self, d):
+        """One chain's departure times [E] replicated to every chain (only E*8 bytes cross PCIe)."""
+        dd = capi.as_f64(d)
+        assert dd.shape == (self.E,)
+        capi.check(self._L.bq_broadcast_state(self._h, capi.ptr(dd, capi.c_f64p)))
+
     def to_arrivals(self, chain=0):
         """A host ``Arrivals`` holding the current state of one chain."""
         st = self.state(chain, chain + 1, full=True)

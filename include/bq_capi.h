@@ -114,6 +114,8 @@ int bq_get_params(bq_handle *h, int32_t chain_lo, int32_t chain_hi, double *thet
 /* Chain state in/out (Arrivals.duplicate / Event fields).  Any output pointer may be NULL.
  * d,a,s: [(chain_hi-chain_lo) * E] fp64; proc, prev_byq, next_byq: same shape int32. */
 int bq_set_state(bq_handle *h, int32_t chain_lo, int32_t chain_hi, const double *d);
+/* Arrivals.duplicate for every chain: one state d[E] from the host, replicated on the device. */
+int bq_broadcast_state(bq_handle *h, const double *d);
 int bq_get_state(bq_handle *h, int32_t chain_lo, int32_t chain_hi, double *d, double *a, double *s,
                  int32_t *proc, int32_t *prev_byq, int32_t *next_byq);
 /* Same, but d is DEVICE memory laid out [n_chains][E] (zero-copy access for torch callers). */

@@ -239,7 +239,10 @@ def cond_grid(net, arrv, max_events, rng):
         nxt = e.next_by_task()
         lo, hi = e.a, (nxt.d if nxt is not None else min(tmax, e.d + 3 * (e.d - e.a) + 1.0))
         g = numpy.concatenate(([e.d], lo + (hi - lo) * numpy.array([0.03, 0.2, 0.4, 0.5, 0.6, 0.8, 0.97]),
-                               lo + (hi - lo) * rng.rand(4), [lo - 0.1, hi + 0.1]))
+                               lo + (hi - lo) * rng.rand(4),
+                               e.d + 0.02 * min(e.d - lo, hi - e.d) * numpy.array([-1.0, -0.3, 0.3, 1.0]),
+                               e.d + 0.3 * min(e.d - lo, hi - e.d) * numpy.array([-1.0, 1.0]),
+                               [lo - 0.1, hi + 0.1]))
         if any(type(q).__name__ == "QueuePS" for q in net.queues):
             g = g[:-2]  # QueuePS asserts (queues.pyx:1068) when evaluated outside [a_e, upper]
         dfn = qnet.GGkGibbs(net, arrv, e, 0.0).dfn()

@@ -1,0 +1,85 @@
+"""Shared test helpers: golden fixtures -> host objects / oracle chains; synthetic inputs."""
+import os
+
+import numpy
+
+import oracle as orc
+from bayes_qnet_b200 import qnetu
+from bayes_qnet_b200.arrivals import Arrivals
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+COND_NETS = ["mm1", "qnet3", "delay", "lng1", "mm3", "lnk", "psdelay"]
+STATIC_NETS = ["mm1", "qnet3", "delay", "lng1"]  # single-server FIFO + delay stations: queue order is static
+
+QNET3 = """
+states:
+  - name: INITIAL
+    queues: [ INITIAL ]
+    successors: [ TIER1 ]
+    initial: TRUE
+  - name: TIER1
+    queues: [ WEB1, WEB2, WEB3 ]
+    successors: [ TIER2 ]
+  - name: TIER2
+    queues: [ APP1, APP2 ]
+    successors: [ TIER3 ]
+  - name: TIER3
+    queues: [ DB ]
+queues:
+  - { name: INITIAL, service: [M, 1.0] }
+  - { name: WEB1, service: [M, 0.2] }
+  - { name: WEB2, service: [M, 0.2] }
+  - { name: WEB3, service: [M, 0.2] }
+  - { name: APP1, service: [M, 0.05] }
+  - { name: APP2, service: [M, 0.05] }
+  - { name: DB, service: [M, 0.3] }
+"""
+
+MM1 = """
+states:
+  - name: INITIAL
+    queues: [ INITIAL ]
+    successors: [ TIER1 ]
+    initial: TRUE
+  - name: TIER1
+    queues: [ WEB1 ]
+queues:
+  - { name: INITIAL, service: [M, 1.0] }
+  - { name: WEB1, service: [M, 0.7] }
+"""
+
+
+def golden(name):
+    return numpy.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+
+
+def golden_state(g, prefix, theta=None):
+    """(net, arrv) in the product's host API from a state the reference produced."""
+    net = qnetu.qnet_from_text(str(g["yaml"]))
+    net.parameters = list(g["theta"] if theta is None else theta)
+    p = prefix + "_"
+    arrv = Arrivals.from_arrays(net, g[p + "tid"], g[p + "qid"], g[p + "state"], g[p + "a"], g[p + "d"],
+                                g[p + "obs_a"], g[p + "obs_d"], eid=g[p + "eid"],
+                                prev_byq=g[p + "prev_byq"], next_byq=g[p + "next_byq"])
+    return net, arrv
+
+
+def oracle_chain(net, arrv, theta=None):
+    return orc.OracleChain.from_arrivals(net, arrv, theta)
+
+
+def relerr(x, ref):
+    x, ref = numpy.asarray(x, dtype=numpy.float64), numpy.asarray(ref, dtype=numpy.float64)
+    return numpy.abs(x - ref) / numpy.maximum(1.0, numpy.abs(ref))
+
+
+def synthetic(yaml_text, ntasks, pct, seed, theta=None):
+    """simulate -> hide tasks -> initialise, all with the product's host code."""
+    net = qnetu.qnet_from_text(yaml_text)
+    if theta is not None:
+        net.parameters = list(theta)
+    qnetu.set_seed(seed)
+    smp = net.sample(ntasks)
+    sub = smp.subset_by_task(pct)
+    ini = net.gibbs_initialize(sub)
+    return net, smp, sub, ini

@@ -1,0 +1,245 @@
+"""Parity of the CUDA path, called through the C-ABI, against (i) vectors produced by the reference's own code
+(tests/golden), (ii) the CPU oracle on the same seeded inputs, (iii) size-independent properties at the
+benchmark's full size, (iv) long reference runs (posterior agreement within Monte-Carlo error).
+
+Tolerances: conditional log-densities, log_prob, sufficient statistics and whole-sweep trajectories 1e-9
+relative in fp64 (BASELINE.json north_star); posterior means within 4 combined Monte-Carlo standard errors."""
+import numpy
+import pytest
+
+import helpers
+from bayes_qnet_b200 import GibbsEngine, capi, diagnostics, estimation, qnetu
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.mark.parametrize("name", helpers.STATIC_NETS)
+def test_logcond_matches_reference_vectors(name):
+    """bq_logcond == GGkGibbs.inner_dfun - lik0 (qnet.pyx:1340-1357) on states the reference produced."""
+    g = helpers.golden("cond_" + name)
+    total = 0
+    for st, pre, theta in (("s0", "s0", g["theta"]), ("s1", "s1", g["theta"]), ("s2", "s1", g["s2_theta"])):
+        net, arrv = helpers.golden_state(g, pre, theta)
+        with GibbsEngine(net, arrv, n_chains=2, seed=1) as eng:
+            ref_lp = float(g[st + "_logprob"])
+            lp = eng.log_prob()
+            assert numpy.all(numpy.abs(lp - ref_lp) < TOL * max(1.0, abs(ref_lp)))
+            for r, xs, ref in zip(g[st + "_rows"], g[st + "_x"], g[st + "_g"]):
+                v = eng.logcond(1, int(r), xs)
+                assert numpy.array_equal(numpy.isfinite(v), numpy.isfinite(ref)), "support differs at row %d" % r
+                m = numpy.isfinite(ref)
+                if m.any():
+                    assert helpers.relerr(v[m], ref[m]).max() < TOL
+                    total += int(m.sum())
+    assert total > 200
+
+
+@pytest.mark.parametrize("name", helpers.STATIC_NETS)
+def test_sweep_trajectory_matches_oracle(name):
+    """Same seed, same schedule -> the kernel and the CPU oracle walk the same path (5 sweeps, 3 chains)."""
+    g = helpers.golden("cond_" + name)
+    net, arrv = helpers.golden_state(g, "s0")
+    with GibbsEngine(net, arrv, n_chains=3, seed=4242, chain_offset=5) as eng:
+        off, order = eng.schedule()
+        eng.sweep(5, "SLICE", "NONE")
+        d = eng.state()
+        st = eng.stats()
+        lp = eng.log_prob()
+        ss = eng.suffstats()
+        for c in range(3):
+            oc = helpers.oracle_chain(net, arrv)
+            evals = 0
+            for s in range(5):
+                ne, ev = oc.slice_sweep(order, eng.seed, 5 + c, s)
+                evals += ev
+            assert helpers.relerr(d[c], oc.d).max() < TOL
+            assert abs(lp[c] - oc.log_prob()) < TOL * max(1.0, abs(oc.log_prob()))
+            oss = oc.suffstats()
+            assert helpers.relerr(ss[c], oss).max() < 1e-8
+        assert st["nevents"] == 3 * 5 * len(order)
+        assert not numpy.array_equal(d[0], d[1])  # chains differ only by their RNG counters
+
+
+def test_bayes_and_stem_updates_match_oracle():
+    """Fused sufficient statistics + parameter update after every sweep (qnet.pyx:882 / :844)."""
+    for name, upd in (("qnet3", "BAYES"), ("lng1", "BAYES"), ("lng1", "STEM"), ("delay", "STEM")):
+        g = helpers.golden("cond_" + name)
+        net, arrv = helpers.golden_state(g, "s0")
+        with GibbsEngine(net, arrv, n_chains=2, seed=99) as eng:
+            off, order = eng.schedule()
+            eng.sweep(4, "SLICE", upd, trace=True)
+            th, mw, lp = eng.traces()
+            assert th.shape == (4, 2, len(net.parameters))
+            oc = helpers.oracle_chain(net, arrv)
+            for s in range(4):
+                oc.slice_sweep(order, eng.seed, 1, s)
+                ss = oc.suffstats()
+                assert helpers.relerr(mw[s, 1], ss[:, 5] / ss[:, 6]).max() < 1e-8
+                assert abs(lp[s, 1] - oc.log_prob()) < 1e-8 * max(1.0, abs(oc.log_prob()))
+                oc.update_params(upd, eng.seed, 1, s)
+                assert helpers.relerr(th[s, 1], oc.theta).max() < 1e-7, (name, upd, s, th[s, 1], oc.theta)
+            assert helpers.relerr(eng.params()[1], oc.theta).max() < 1e-7
+            assert helpers.relerr(eng.state()[1], oc.d).max() < 1e-7
+
+
+def test_schedule_is_conflict_free_and_complete():
+    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 400, 0.2, seed=2)
+    with GibbsEngine(net, ini, n_chains=1, seed=1) as eng:
+        off, order = eng.schedule()
+    oc = helpers.oracle_chain(net, ini)
+    assert sorted(order) == sorted(oc.eligible())  # every eligible event exactly once (qnet.pyx:688)
+    soa = ini.soa()
+    pb, nb, pq, nq = soa["prev_byt"], soa["next_byt"], soa["prev_byq"], soa["next_byq"]
+
+    def blanket(e):
+        out = {pb[e], pq[e], nq[e], nb[e]}
+        if nq[e] >= 0:
+            out.add(pb[nq[e]])
+        e1 = nb[e]
+        if e1 >= 0:
+            out.add(pq[e1])
+            if pq[e1] >= 0:
+                out.add(pb[pq[e1]])
+            if nq[e1] >= 0:
+                out.add(pb[nq[e1]])
+        out.discard(-1)
+        return out
+
+    for c in range(len(off) - 1):
+        members = set(int(x) for x in order[off[c]:off[c + 1]])
+        for e in members:
+            assert not (blanket(e) & members), "colour class %d is not conflict free" % c
+
+
+def test_sharding_is_invisible():
+    """Chains are addressed by GLOBAL id: 8 chains in one handle == 2 handles of 4 with chain_offset."""
+    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 120, 0.3, seed=8)
+    with GibbsEngine(net, ini, n_chains=8, seed=31337) as whole:
+        whole.sweep(3, "SLICE", "BAYES")
+        d, th = whole.state(), whole.params()
+    for k in range(2):
+        with GibbsEngine(net, ini, n_chains=4, seed=31337, chain_offset=4 * k) as part:
+            part.sweep(3, "SLICE", "BAYES")
+            assert numpy.array_equal(part.state(), d[4 * k:4 * k + 4])
+            assert numpy.array_equal(part.params(), th[4 * k:4 * k + 4])
+
+
+def test_global_memory_path_equals_shared_memory_path(monkeypatch):
+    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 150, 0.3, seed=9)
+    with GibbsEngine(net, ini, n_chains=4, seed=5) as a:
+        assert a.kernel_info()["state_in_smem"]
+        a.sweep(3, "SLICE", "BAYES")
+        da, ta = a.state(), a.params()
+    monkeypatch.setenv("BQ_FORCE_GLOBAL", "1")
+    with GibbsEngine(net, ini, n_chains=4, seed=5) as b:
+        assert not b.kernel_info()["state_in_smem"]
+        b.sweep(3, "SLICE", "BAYES")
+        assert numpy.array_equal(b.state(), da) and numpy.array_equal(b.params(), ta)
+
+
+def test_edge_cases():
+    # nothing hidden: a sweep is a no-op and counts nothing
+    net, smp, sub, ini = helpers.synthetic(helpers.MM1, 30, 1.1, seed=3)
+    with GibbsEngine(net, ini, n_chains=2, seed=1) as eng:
+        d0 = eng.state()
+        eng.sweep(2, "SLICE", "BAYES")
+        assert numpy.array_equal(eng.state(), d0) and eng.stats()["nevents"] == 0
+        assert eng.schedule()[1].size == 0
+    # everything hidden, odd event count, single task
+    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 1, -1.0, seed=3)
+    with GibbsEngine(net, ini, n_chains=3, seed=1) as eng:
+        eng.sweep(10, "SLICE", "NONE")
+        full = eng.state(full=True)
+        assert numpy.all(full["s"] >= 0) and eng.stats()["nevents"] == 3 * 10 * 4
+    # bad arguments come back as error codes, not crashes
+    with GibbsEngine(net, ini, n_chains=1, seed=1) as eng:
+        with pytest.raises(capi.BqError):
+            eng.logcond(5, 0, [1.0])
+        with pytest.raises(capi.BqError):
+            eng.logcond(0, 10 ** 6, [1.0])
+        with pytest.raises(capi.BqError):
+            eng.params(0, 7)
+
+
+def test_reference_api_in_place_semantics():
+    """Qnet.slice_resample mutates arrv in place and returns [arrv] (qnet.pyx:659-730); qnet.stats() counts."""
+    from bayes_qnet_b200 import qnet
+    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 60, 0.3, seed=12)
+    d_before = ini.soa()["d"].copy()
+    qnet.reset_stats()
+    out, lp = net.slice_resample(ini, 4, return_lp=True)
+    assert out[0] is ini and numpy.isfinite(lp)
+    ini.validate()
+    hidden = ini.soa()["obs_d"] == 0
+    assert numpy.array_equal(ini.soa()["d"][~hidden], d_before[~hidden])
+    assert numpy.mean(ini.soa()["d"][hidden] != d_before[hidden]) > 0.9
+    assert qnet.stats()["nevents"] == 4 * ini.num_hidden_events()
+    assert abs(net.log_prob(ini) - lp) < 1e-9 * abs(lp)
+    theta = net.estimate(ini)
+    ms = [float(numpy.mean(ini.soa()["s"][(ini.soa()["qid"] == q) & (ini.soa()["s"] > 0)])) for q in range(7)]
+    assert numpy.allclose(theta, ms, rtol=1e-12)
+    mus, arrvl = estimation.bayes(net, ini, 20)
+    assert len(mus) == 20 and len(mus[0]) == 7 and arrvl[0] is ini
+    ini.validate()
+
+
+def test_full_size_invariants_config2():
+    """BASELINE.json configs[1] at full size (5k tasks, 20% observed, 1024 chains): properties that do not need
+    the oracle -- observed times untouched, every service >= 0, FIFO order kept, arrivals chained to departures,
+    counters consistent, log_prob finite and equal to a host recomputation, chains distinct."""
+    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 5000, 0.2, seed=13)
+    soa = ini.soa()
+    C = 1024
+    with GibbsEngine(net, ini, n_chains=C, seed=2024) as eng:
+        off, order = eng.schedule()
+        eng.sweep(5, "SLICE", "BAYES", trace=True)
+        st = eng.stats()
+        assert st["nevents"] == C * 5 * len(order) and st["n_stuck"] < 1e-4 * st["nevents"]
+        assert 3.0 < st["slice_evals"] / st["nevents"] < 12.0
+        lp = eng.log_prob()
+        assert numpy.all(numpy.isfinite(lp))
+        th = eng.params()
+        assert numpy.all(th > 0) and numpy.all(numpy.std(th, axis=0) > 0)
+        for lo in (0, 500, C - 4):
+            full = eng.state(lo, lo + 4, full=True)
+            d, a, s = full["d"], full["a"], full["s"]
+            obs = soa["obs_d"] == 1
+            assert numpy.array_equal(d[:, obs], numpy.broadcast_to(soa["d"][obs], (4, obs.sum())))
+            assert numpy.all(s >= 0)
+            has = soa["prev_byt"] >= 0
+            assert numpy.array_equal(a[:, has], d[:, soa["prev_byt"][has]])
+            nq = soa["next_byq"]
+            hasn = nq >= 0
+            assert numpy.all(d[:, nq[hasn]] >= d[:, hasn]) and numpy.all(a[:, nq[hasn]] >= a[:, hasn])
+            for c in range(4):
+                scale = th[lo + c][soa["qid"]]
+                host_lp = float(numpy.sum(-numpy.log(scale) - s[c] / scale))
+                assert abs(host_lp - lp[lo + c]) < 1e-9 * abs(host_lp)
+        d_all = eng.state(0, 8)
+        assert len(set(d_all[:, order[0]].tolist())) == 8
+
+
+@pytest.mark.parametrize("name", ["mm1", "qnet3", "lng1"])
+def test_posterior_agrees_with_long_reference_runs(name):
+    """estimation.bayes from the same initial state: posterior means of the service parameters and of the
+    per-queue mean waiting time vs the reference's own long runs (tests/golden/post_*.npz), within 4 combined
+    Monte-Carlo standard errors (ESS-based)."""
+    g = helpers.golden("post_" + name)
+    net, arrv = helpers.golden_state(dict((k, g[k]) for k in g.files if k != "theta") | {"theta": g["theta0"]}, "s0")
+    ref_th, ref_mw = g["theta"], g["mean_wait"]  # [R, n, P], [R, n, Q]
+    n = ref_th.shape[1]
+    burn = n // 5
+    C = 32
+    with GibbsEngine(net, arrv, n_chains=C, seed=777) as eng:
+        eng.sweep(n, "SLICE", "BAYES", trace=True)
+        th, mw, lp = eng.traces()
+    ref_th = numpy.swapaxes(ref_th[:, burn:], 0, 1)
+    ref_mw = numpy.swapaxes(ref_mw[:, burn:], 0, 1)
+    th, mw = th[burn:], mw[burn:]
+    for ours, ref, what in ((th, ref_th, "theta"), (mw[:, :, 1:], ref_mw[:, :, 1:], "mean wait")):
+        m1, m2 = ours.mean(axis=(0, 1)), ref.mean(axis=(0, 1))
+        se = numpy.sqrt(diagnostics.mcse(ours) ** 2 + diagnostics.mcse(ref) ** 2)
+        z = numpy.abs(m1 - m2) / numpy.maximum(se, 1e-12)
+        assert numpy.all(z < 4.0), "%s %s: ours %s ref %s z %s" % (name, what, m1, m2, z)
+    assert numpy.all(diagnostics.rhat(th) < 1.1)

@@ -1,0 +1,204 @@
+"""Host-side logic (no GPU): YAML loading, the SoA Arrivals, forward simulation, subsetting, the initialiser,
+diagnostics, and the C-ABI library's exported surface."""
+import io
+import os
+import re
+
+import numpy
+import pytest
+
+import helpers
+from bayes_qnet_b200 import capi, diagnostics, qnet, qnetu, qstats
+from bayes_qnet_b200.arrivals import Arrivals, Event, ps_service
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_yaml_model_loading_matches_reference_conventions():
+    net = qnetu.qnet_from_text(helpers.QNET3)
+    assert net.num_queues() == 7 and net.num_states() == 4
+    assert [q.name for q in net.queues] == ["INITIAL", "WEB1", "WEB2", "WEB3", "APP1", "APP2", "DB"]
+    assert all(q.code == 0 and q.k == 1 for q in net.queues)  # default type is GG1 -> QueueGGk(k=1), qnetu.py:103-110
+    assert net.parameters == [1.0, 0.2, 0.2, 0.2, 0.05, 0.05, 0.3]
+    net.parameters = [0.25, 0.5, 0.5, 0.5, 1.2, 1.2, 0.05]  # test_qnet.py:577-579
+    assert net.parameters == [0.25, 0.5, 0.5, 0.5, 1.2, 1.2, 0.05]
+    assert net.fsm.possible_observations(1) == {1, 2, 3} and net.fsm.successors(2) == {3}
+    assert net.queue_by_name("DB") is net.queues[6] and net.queue_by_name("nope") is None
+    net2 = qnetu.qnet_from_text(net.as_yaml())  # round trip through as_yaml
+    assert [q.name for q in net2.queues] == [q.name for q in net.queues] and net2.parameters == net.parameters
+    mm3 = qnetu.qnet_from_text("""
+states:
+  - {name: I, queues: [I], successors: [A]}
+  - {name: A, queues: [Q1], successors: [B]}
+  - {name: B, queues: [Q2], successors: [C]}
+  - {name: C, queues: [Q3]}
+queues:
+  - { name: I, service: [M, 10.0] }
+  - { name: Q1, processors: 3, service: [LN, 1.75, 1.0] }
+  - { name: Q2, type: DELAY, service: [G, 2.0, 0.5] }
+  - { name: Q3, type: PS, service: [M, 0.5] }
+""")
+    assert [(q.code, q.k, q.service.code) for q in mm3.queues] == [(0, 1, 0), (0, 3, 2), (1, 1, 1), (2, 1, 0)]
+    assert mm3.parameters == [10.0, 1.75, 1.0, 2.0, 0.5, 0.5]
+    with pytest.raises(NotImplementedError):
+        qnetu.qnet_from_text(helpers.MM1.replace("[M, 0.7]", "[M, 0.7], type: GG1R"))
+    with pytest.raises(Exception):
+        qnetu.qnet_from_text("- 1\n- 2\n")
+
+
+def test_configuration_keys():
+    qnetu.read_configuration(io.StringIO("sampling_type: SLICE\none_d_sampler: SLICE\ninitializer: DFN2\nuse_rtp: 0\n"))
+    with pytest.raises(NotImplementedError):
+        qnetu.read_configuration(io.StringIO("one_d_sampler: ARS_PWFUN\n"))
+    with pytest.raises(Exception):
+        qnetu.read_configuration(io.StringIO("bogus: 1\n"))
+
+
+def test_forward_simulation_is_a_valid_fifo_network():
+    net = qnetu.qnet_from_text(helpers.QNET3)
+    qnetu.set_seed(3)
+    arrv = net.sample(600)
+    arrv.validate()
+    assert arrv.num_events() == 2400 and arrv.num_tasks() == 600
+    ms = qstats.mean_service(arrv)
+    for m, p in zip(ms, net.parameters):
+        assert abs(m - p) < 5 * p / numpy.sqrt(150)
+    # every task walks INITIAL -> TIER1 -> TIER2 -> TIER3, arrivals chained to departures
+    evts = arrv.events_of_task(17)
+    assert [e.state for e in evts] == [0, 1, 2, 3] and evts[0].a == 0.0
+    assert all(x.d == y.a for x, y in zip(evts, evts[1:]))
+    # the oracle agrees with the host's service computation
+    oc = helpers.oracle_chain(net, arrv)
+    assert numpy.abs(oc.s - arrv.soa()["s"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("yaml_text", [helpers.QNET3, None, "mm3", "psdelay", "delay"])
+def test_subset_and_initializer_give_a_feasible_state(yaml_text):
+    if yaml_text is None:
+        yaml_text = helpers.MM1
+    elif yaml_text in ("mm3", "psdelay", "delay"):
+        yaml_text = str(helpers.golden("cond_" + yaml_text)["yaml"])
+    net, smp, sub, ini = helpers.synthetic(yaml_text, 300, 0.3, seed=11)
+    soa, ssoa = ini.soa(), sub.soa()
+    n_hidden_tasks = len(numpy.unique(ssoa["tid"][ssoa["obs_d"] == 0]))
+    assert 0.55 * 300 < n_hidden_tasks < 0.85 * 300
+    ini.validate()
+    assert ini.num_tasks() == 300
+    # observed events keep their data exactly
+    obs = ssoa["obs_d"] == 1
+    got = dict((int(e), (a, d)) for e, a, d, o in zip(soa["eid"], soa["a"], soa["d"], soa["obs_d"]) if o)
+    for e, a, d in zip(ssoa["eid"][obs], ssoa["a"][obs], ssoa["d"][obs]):
+        assert got[int(e)] == (a, d)
+    # hidden times were re-drawn (they do not leak the simulated truth)
+    hid = dict((int(e), d) for e, d, o in zip(soa["eid"], soa["d"], soa["obs_d"]) if not o)
+    truth = dict((int(e), d) for e, d in zip(ssoa["eid"][~obs], ssoa["d"][~obs]))
+    same = sum(1 for e in hid if e in truth and hid[e] == truth[e])
+    assert same == 0
+    oc = helpers.oracle_chain(net, ini)
+    assert numpy.all(oc.s >= 0) and numpy.isfinite(oc.log_prob())
+    assert numpy.abs(oc.s - soa["s"]).max() < 1e-9 and numpy.array_equal(oc.proc, soa["proc"])
+
+
+def test_event_facade_and_detached_events():
+    net = qnetu.qnet_from_text(helpers.MM1)
+    arrv = Arrivals(net)
+    q0, q1 = net.queues
+    arrv.append(Event(0, 0, 0, q0, 0.0, 0.0, 1.0, 0, obs_a=1, obs_d=1))
+    arrv.append(Event(1, 0, 1, q1, 1.0, 0.0, 1.5, 1, obs_a=1, obs_d=1))
+    arrv.append(Event(2, 1, 0, q0, 0.0, 0.0, 2.0, 0, obs_a=1, obs_d=1))
+    arrv.append(Event(3, 1, 1, q1, 2.0, 0.0, 4.0, 1, obs_a=1, obs_d=1))
+    arrv.recompute_all_service()
+    arrv.validate()
+    e = arrv.event(3)
+    assert (e.a, e.d, e.s, e.tid, e.qid) == (2.0, 4.0, 2.0, 1, 1) and e.q is q1 and e.queue().name == "WEB1"
+    assert e.previous_by_queue().eid == 1 and e.previous_by_task().eid == 2 and e.next_by_task() is None
+    assert arrv.event(2).s == 1.0 and arrv.event(2).wait() == 1.0  # source: waits for task 0
+    assert [x.eid for x in arrv.events_of_qid(1)] == [1, 3] and arrv.num_hidden_events() == 0
+    assert arrv.as_csv().splitlines()[0].startswith("EID TID QID A D S W")
+    dup = arrv.duplicate()
+    dup.event(3).d = 5.0
+    assert arrv.event(3).d == 4.0
+    rt = qnetu.read_table_from_string(net, arrv.as_csv())
+    assert numpy.allclose(sorted(rt.soa()["d"]), sorted(arrv.soa()["d"])) and rt.num_tasks() == 2
+
+
+def test_arrivals_yaml_and_multifile_formats():
+    net = qnetu.qnet_from_text(helpers.MM1)
+    text = """!Arrivals
+events:
+- !Event {arrival: 0.0, departure: 1.0, obs: 1, queue: INITIAL, state: 0, task: 0}
+- !Event {arrival: 0.0, departure: 2.5, obs: 1, queue: INITIAL, state: 0, task: 1}
+- !Event {arrival: 1.0, departure: 1.75, obs: 1, queue: WEB1, state: 1, task: 0}
+- !Event {arrival: 2.5, departure: 3.0, obs: 1, queue: WEB1, state: 1, task: 1}
+"""
+    arrv = qnetu.load_arrivals(net, io.StringIO(text))
+    assert arrv.num_events() == 4 and arrv.num_tasks() == 2
+    assert numpy.allclose(sorted(arrv.soa()["s"]), [0.5, 0.75, 1.0, 1.5])
+    sf, af, df = io.StringIO(), io.StringIO(), io.StringIO()
+    qnetu.write_multifile_arrv(arrv, sf, af, df, obs_only=False)
+    back = qnetu.read_multifile_arrv(net, io.StringIO(sf.getvalue()), io.StringIO(af.getvalue()), io.StringIO(df.getvalue()))
+    assert numpy.allclose(sorted(back.soa()["d"]), sorted(arrv.soa()["d"])) and back.num_tasks() == 2
+    back.validate()
+
+
+def test_ps_service_integral():
+    """Brute-force check of s = integral dt/N(t) and the test_ps.py:189-212 style zero-length case."""
+    rng = numpy.random.RandomState(0)
+    a = numpy.sort(rng.uniform(0, 20, 40))
+    d = a + rng.exponential(1.0, 40)
+    s = ps_service(a, d)
+    grid = numpy.linspace(0, d.max(), 400001)
+    N = (a[:, None] <= grid[None, ::]).sum(0) - (d[:, None] <= grid[None, :]).sum(0)
+    for i in (0, 7, 23, 39):
+        m = (grid >= a[i]) & (grid < d[i])
+        assert abs(s[i] - numpy.sum(1.0 / N[m]) * (grid[1] - grid[0])) < 2e-3
+    assert numpy.all(s <= d - a + 1e-12) and numpy.all(s > 0)
+
+
+def test_diagnostics():
+    rng = numpy.random.RandomState(1)
+    x = rng.normal(size=(2000, 8, 2))
+    assert numpy.all(numpy.abs(diagnostics.rhat(x) - 1.0) < 0.01)
+    e = diagnostics.ess(x)
+    assert numpy.all(e > 0.8 * 16000) and numpy.all(e < 1.25 * 16000)
+    y = numpy.zeros((4000, 4))  # AR(1) with rho = 0.9 -> ESS ~ n (1-rho)/(1+rho)
+    eps = rng.normal(size=y.shape)
+    for t in range(1, len(y)):
+        y[t] = 0.9 * y[t - 1] + eps[t]
+    assert 0.5 * 16000 / 19 < diagnostics.ess(y[:, :, None])[0] < 2.0 * 16000 / 19
+    z = x.copy()
+    z[:, 0] += 3.0  # one chain somewhere else
+    assert numpy.all(diagnostics.rhat(z) > 1.2)
+
+
+def test_capi_exports_every_declared_symbol():
+    """include/bq_capi.h is the boundary: each function it declares is exported by the library and bound by
+    capi.SYMBOLS (and vice versa).  No compute call is made -- there is no GPU here."""
+    header = open(os.path.join(ROOT, "include", "bq_capi.h")).read()
+    declared = set(re.findall(r"\b(bq_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(capi.SYMBOLS), declared.symmetric_difference(capi.SYMBOLS)
+    L = capi.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.bq_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to run instead of silently computing on the host."""
+    if capi.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    net, smp, sub, ini = helpers.synthetic(helpers.MM1, 20, 0.5, seed=1)
+    with pytest.raises(capi.BqError) as ei:
+        net.engine(ini, n_chains=2)
+    assert ei.value.code == capi.BQ_ERR_NO_DEVICE
+    with pytest.raises(capi.BqError):
+        net.slice_resample(ini, 1)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "bayes_qnet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("Py3 oracle", ""), "%s mentions the oracle" % f
