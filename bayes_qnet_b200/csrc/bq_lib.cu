@@ -40,7 +40,9 @@ struct bq_handle {
     unsigned long long seed = 0;
     unsigned int sweep_counter = 0;
     bool static_order = true;
+    bool all_exp = true;  // every service family exponential: branch-free conditional
     int threads = 512;
+    int refill = BQ_REFILL_THRESH;  // idle lanes per warp that trigger a refill from the class work counter
     bool use_smem = true;
     size_t smem_bytes = 0;
     // host copies
@@ -200,6 +202,7 @@ static void fill_args(const bq_handle *h, SweepArgs &A) {
     A.state = h->d_state; A.theta = h->d_theta; A.stats = h->d_stats;
     A.tr_theta = h->d_tr_theta; A.tr_wait = h->d_tr_wait; A.tr_logp = h->d_tr_logp;
     A.seed = h->seed; A.chain_offset = h->chain_offset; A.sweep_base = h->sweep_counter;
+    A.refill = h->refill;
 }
 
 extern "C" int bq_destroy(bq_handle *h) {
@@ -256,6 +259,7 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         if (h->q_poff[q] != pcount) return bail(BQ_ERR_INVALID, "q_param_off is not the running parameter count");
         pcount += (dd == D_EXP) ? 1 : 2;
         if (t == Q_PS || (t == Q_GGK && h->q_k[q] != 1)) h->static_order = false;
+        if (dd != D_EXP) h->all_exp = false;
     }
     if (pcount != h->P) return bail(BQ_ERR_INVALID, "n_params does not match the service families");
     for (int e = 0; e < E; ++e) {
@@ -337,8 +341,23 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         int t = atoi(env);
         if (t >= 32 && t <= BQ_MAX_THREADS && t % 32 == 0) h->threads = t;
     }
-    CKB(cudaFuncSetAttribute(sweep_static_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-    CKB(cudaFuncSetAttribute(sweep_static_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    {
+        auto set_max = [&](const void *fn) -> cudaError_t {
+            cudaFuncAttributes fa;
+            cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+            if (e != cudaSuccess) return e;
+            return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - (int)fa.sharedSizeBytes);
+        };
+        CKB(set_max((const void *)sweep_static_kernel<true, true>));
+        CKB(set_max((const void *)sweep_static_kernel<true, false>));
+        CKB(set_max((const void *)sweep_static_kernel<false, true>));
+        CKB(set_max((const void *)sweep_static_kernel<false, false>));
+    }
+    if (getenv("BQ_NO_EXP_FASTPATH")) h->all_exp = false;
+    if (const char *env = getenv("BQ_REFILL")) {
+        int t = atoi(env);
+        if (t >= 1 && t <= 32) h->refill = t;
+    }
 #undef CKB
     *out = h;
     return BQ_OK;
@@ -462,10 +481,13 @@ static int launch_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t up
     fill_args(h, A);
     A.n_sweeps = n_sweeps; A.update = update; A.flags = (int)flags; A.trace_base = h->trace_len;
     CK(cudaEventRecord(h->ev0, h->stream));
-    if (h->use_smem)
-        sweep_static_kernel<true><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
-    else
-        sweep_static_kernel<false><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
+    if (h->use_smem) {
+        if (h->all_exp) sweep_static_kernel<true, true><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
+        else sweep_static_kernel<true, false><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
+    } else {
+        if (h->all_exp) sweep_static_kernel<false, true><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
+        else sweep_static_kernel<false, false><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;

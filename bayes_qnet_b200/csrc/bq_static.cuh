@@ -42,7 +42,7 @@ struct SchedRec {
 };
 
 struct SweepArgs {
-    int E, Q, P, n_colors, n_sweeps, update, flags, trace_base, n_chains;
+    int E, Q, P, n_colors, n_sweeps, update, flags, trace_base, n_chains, refill;
     const int4 *rec;
     const int *color_off;
     const int *ev_q, *ev_p, *ev_pt;  // per event: queue, prev-by-queue, prev-by-task
@@ -135,6 +135,151 @@ __device__ __forceinline__ double slice_update(const Cond &c, double x0, double 
     }
     ++stuck;
     return x0;
+}
+
+// All-exponential networks (the paper's M/M/1 tiers): lpdf(s) = -log(mu) - s/mu, so up to a constant
+// that cancels in every slice comparison G(d) is a sum of three linear pieces -- evaluated branch-free.
+struct CondExp {
+    double b, a_n, d_n, d_e1, d_p1, flo, fhi, inv0, invn, inv1;
+
+    __device__ __forceinline__ void idle(const QConst *) {
+        b = a_n = d_n = d_e1 = d_p1 = inv0 = invn = inv1 = 0.0; flo = 1.0; fhi = 0.0;
+    }
+
+    __device__ __forceinline__ double eval(double d) const {
+        double v = -(d - b) * inv0 - (d_n - fmax(a_n, d)) * invn - (d_e1 - fmax(d, d_p1)) * inv1;
+        return (d >= flo && d <= fhi) ? v : BQ_NEG_INF;
+    }
+    __device__ __forceinline__ void load(const SchedRec &r, const double *d, const int *q_type, const QConst *qc,
+                                         double &x0, double &lower, double &upper, double tmax) {
+        Cond c;
+        cond_load(c, r, d, q_type, qc, x0, lower, upper, tmax);
+        b = c.b; flo = c.flo; fhi = c.fhi;
+        inv0 = c.c0->inv;
+        invn = c.has_n ? inv0 : 0.0;
+        a_n = c.a_n; d_n = c.d_n;                    // both 0 when absent: the term vanishes
+        inv1 = c.has_e1 ? c.c1->inv : 0.0;
+        d_e1 = c.d_e1;
+        d_p1 = c.e1_fifo ? c.d_p1 : -INFINITY;        // delay station: max(d, -inf) = d
+        if (!c.has_e1) d_p1 = 0.0;
+    }
+};
+
+struct CondGen : Cond {
+    // lanes that hold no event still run the branch-free shrink step: give them something harmless to evaluate
+    __device__ __forceinline__ void idle(const QConst *qc) {
+        b = a_n = d_n = d_e1 = d_p1 = 0.0; flo = 1.0; fhi = 0.0; has_n = has_e1 = e1_fifo = 0; c0 = c1 = qc;
+    }
+    __device__ __forceinline__ void load(const SchedRec &r, const double *d, const int *q_type, const QConst *qc,
+                                         double &x0, double &lower, double &upper, double tmax) {
+        cond_load(*this, r, d, q_type, qc, x0, lower, upper, tmax);
+    }
+};
+
+#ifndef BQ_REFILL_THRESH
+#define BQ_REFILL_THRESH 24
+#endif
+
+// One colour class, one warp's share of it.  Each lane runs the slice sampler of one event at a time as a
+// state machine: every trip of the loop evaluates exactly one candidate per active lane; lanes whose
+// sampler has finished are refilled from the class's shared work counter as soon as BQ_REFILL_THRESH of
+// them are idle, so the data-dependent trip count of sampling._slice (1..~20 shrink steps) costs neither
+// idle lanes inside the warp nor idle warps at the class barrier.  The result does not depend on which
+// lane handles which event: the RNG stream is keyed by (chain, sweep, event).
+// Two 53-bit uniforms of block `blk` of the (chain, sweep, event) stream.
+__device__ __forceinline__ void stream_pair(const Rng &r, unsigned int blk, double &ua, double &ub) {
+    uint32_t o[4];
+    philox4x32_10(blk, r.c1, r.c2, r.c3, r.k0, r.k1, o);
+    ua = u53(o[0], o[1]);
+    ub = u53(o[2], o[3]);
+}
+
+template <class CondT>
+__device__ __forceinline__ void run_class(const SweepArgs &A, double *d, const int *q_type, const QConst *qc,
+                                          int hi, int *ctr, double tmax, unsigned long long gchain,
+                                          unsigned int gsw, long long &n_ev, long long &n_evals,
+                                          long long &n_stuck) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    bool active = false, exhausted = false;
+    CondT cd;
+    cd.idle(qc);
+    Rng rng;
+    rng.init(0ull, 0ull, 0u, 0u, 0u);
+    double x0 = 0.0, L = 0.0, R = 0.0, logy = 0.0;
+    int e = -1, it = 0;
+    unsigned int blk = 0;
+    int ev = 0, stuck = 0, nev = 0;
+    for (;;) {
+        const unsigned need = __ballot_sync(FULL, !active);
+        if (!exhausted && (__popc(need) >= A.refill)) {
+            const int cnt = __popc(need);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(ctr, cnt);
+            base = __shfl_sync(FULL, base, 0);
+            const int my = base + __popc(need & ((1u << lane) - 1u));
+            if (base + cnt >= hi) exhausted = true;
+            if (!active && my < hi) {
+                union { int4 v[3]; SchedRec r; } u;
+                u.v[0] = __ldg(&A.rec[3 * my]);
+                u.v[1] = __ldg(&A.rec[3 * my + 1]);
+                u.v[2] = __ldg(&A.rec[3 * my + 2]);
+                double lower, upper, ua, ub;
+                cd.load(u.r, d, q_type, qc, x0, lower, upper, tmax);
+                if (A.flags & FLAG_TIGHT) { lower = fmax(lower, cd.flo); upper = fmin(upper, cd.fhi); }
+                e = u.r.e;
+                rng.init(A.seed, gchain, gsw, (unsigned int)e, TAG_SLICE);
+                stream_pair(rng, 0u, ua, ub);
+                blk = 1u;
+                const double g0 = cd.eval(x0);
+                logy = g0 - (-log(1.0 - ua));  // rk_exponential = -log(1 - U)   (cdist.c:107-110)
+                nev += 1; ev += 1;
+                if (logy > BQ_NEG_INF) {
+                    // first candidate comes from the same Philox block as the slice level
+                    L = lower; R = upper; it = 0;
+                    const double x1 = L + (R - L) * ub;
+                    ev += 1;
+                    if (cd.eval(x1) >= logy) d[e] = x1;
+                    else {
+                        if (x1 > x0) R = x1; else L = x1;
+                        if (R - L < 1e-10) stuck += 1; else active = true;
+                    }
+                } else stuck += 1;  // point-mass guard (sampling.pyx:289-291): keep x0
+            }
+        }
+        if (!__any_sync(FULL, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        // Two shrink steps of sampling._slice (sampling.pyx:344-364) per trip, one Philox block.  The second
+        // candidate only depends on where the first one fell (not on its density), so both densities are
+        // evaluated side by side; the outcome is exactly that of the sequential loop.  Branch-free:
+        // inactive lanes compute harmlessly and only the final store is predicated.
+        double ua, ub;
+        stream_pair(rng, blk, ua, ub);
+        const double xa = L + (R - L) * ua;
+        const bool upa = xa > x0;
+        const double La = upa ? L : xa, Ra = upa ? xa : R;
+        const double xb = La + (Ra - La) * ub;
+        const bool upb = xb > x0;
+        const double Lb = upb ? La : xb, Rb = upb ? xb : Ra;
+        const bool acc_a = cd.eval(xa) >= logy;
+        const bool acc_b = cd.eval(xb) >= logy;
+        const bool stuck_a = !acc_a && (Ra - La < 1e-10);
+        const bool try_b = !acc_a && !stuck_a;
+        it += 2;
+        const bool stuck_b = try_b && !acc_b && ((Rb - Lb < 1e-10) || it >= BQ_SLICE_MAX_ITERS);
+        const bool done = acc_a || (try_b && acc_b);
+        if (active) {
+            ev += try_b ? 2 : 1;
+            if (done) d[e] = acc_a ? xa : xb;
+            if (stuck_a || stuck_b) stuck += 1;
+            if (done || stuck_a || stuck_b) active = false;
+        }
+        L = Lb; R = Rb;
+        blk += 1u;
+    }
+    n_ev += nev; n_evals += ev; n_stuck += stuck;
 }
 
 template <int N>
@@ -241,7 +386,7 @@ __device__ inline void chain_suffstats(const SweepArgs &A, const double *d, cons
     __syncthreads();
 }
 
-template <bool SMEM>
+template <bool SMEM, bool ALL_EXP>
 __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const SweepArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int chain = blockIdx.x;
@@ -261,6 +406,7 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
     int *q_poff = q_dist + Q;
     __shared__ unsigned long long cnt[4];
     __shared__ double logp_sh;
+    __shared__ int work_ctr[2];
 
     for (int i = threadIdx.x; i < P; i += blockDim.x) th[i] = A.theta[(size_t)chain * P + i];
     for (int i = threadIdx.x; i < Q; i += blockDim.x) {
@@ -296,24 +442,15 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
             tmax = 2.0 * block_reduce_max(m, scratch);
         }
         const int n_colors = (A.flags & FLAG_PARAMS_ONLY) ? 0 : A.n_colors;
+        if (threadIdx.x == 0) work_ctr[0] = A.color_off[0];
+        __syncthreads();
         for (int c = 0; c < n_colors; ++c) {
-            const int lo = A.color_off[c], hi = A.color_off[c + 1];
-            for (int idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
-                union { int4 v[3]; SchedRec r; } u;
-                u.v[0] = __ldg(&A.rec[3 * idx]);
-                u.v[1] = __ldg(&A.rec[3 * idx + 1]);
-                u.v[2] = __ldg(&A.rec[3 * idx + 2]);
-                Cond cd;
-                double x0, lower, upper;
-                cond_load(cd, u.r, d, q_type, qc, x0, lower, upper, tmax);
-                if (A.flags & FLAG_TIGHT) { lower = fmax(lower, cd.flo); upper = fmin(upper, cd.fhi); }
-                Rng rng;
-                rng.init(A.seed, gchain, gsw, (unsigned int)u.r.e, TAG_SLICE);
-                int ev = 0, st = 0;
-                double x1 = slice_update(cd, x0, lower, upper, rng, ev, st);
-                d[u.r.e] = x1;
-                n_ev += 1; n_evals += ev; n_stuck += st;
-            }
+            const int hi = A.color_off[c + 1];
+            if (threadIdx.x == 0) work_ctr[(c + 1) & 1] = hi;  // next class starts where this one ends
+            if (ALL_EXP)
+                run_class<CondExp>(A, d, q_type, qc, hi, &work_ctr[c & 1], tmax, gchain, gsw, n_ev, n_evals, n_stuck);
+            else
+                run_class<CondGen>(A, d, q_type, qc, hi, &work_ctr[c & 1], tmax, gchain, gsw, n_ev, n_evals, n_stuck);
             __syncthreads();
         }
         const bool trace = (A.flags & FLAG_TRACE) != 0;
