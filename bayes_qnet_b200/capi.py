@@ -9,7 +9,7 @@ import os
 import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbq_b200.so")
+LIB_PATH = os.environ.get("BQ_LIB", os.path.join(_HERE, "libbq_b200.so"))  # BQ_LIB: tuning builds only
 
 BQ_OK = 0
 BQ_ERR_INVALID, BQ_ERR_CUDA, BQ_ERR_UNSUPPORTED, BQ_ERR_NO_DEVICE, BQ_ERR_STATE = -1, -2, -3, -4, -5

@@ -18,7 +18,9 @@
 
 namespace bq {
 
+#ifndef BQ_MAX_THREADS
 #define BQ_MAX_THREADS 512
+#endif
 #define BQ_SLICE_MAX_ITERS 1000
 
 enum { UPD_NONE = 0, UPD_BAYES = 1, UPD_STEM = 2 };
@@ -146,8 +148,11 @@ struct CondExp {
         b = a_n = d_n = d_e1 = d_p1 = inv0 = invn = inv1 = 0.0; flo = 1.0; fhi = 0.0;
     }
 
+    // G(d) - const = -d/mu0 + max(a_n, d)/mu0 [successor] + max(d, d_p1)/mu1 [next-by-task]: the terms of
+    // -(d-b)/mu0 - (d_n - max(a_n,d))/mu0 - (d_e1 - max(d,d_p1))/mu1 that do not depend on d are dropped,
+    // they cancel in g(x1) >= g(x0) - Exp(1).
     __device__ __forceinline__ double eval(double d) const {
-        double v = -(d - b) * inv0 - (d_n - fmax(a_n, d)) * invn - (d_e1 - fmax(d, d_p1)) * inv1;
+        double v = fma(invn, fmax(a_n, d), fma(inv1, fmax(d, d_p1), -inv0 * d));
         return (d >= flo && d <= fhi) ? v : BQ_NEG_INF;
     }
     __device__ __forceinline__ void load(const SchedRec &r, const double *d, const int *q_type, const QConst *qc,
@@ -176,6 +181,9 @@ struct CondGen : Cond {
     }
 };
 
+#ifndef BQ_CAND
+#define BQ_CAND 4  // candidates per trip (even)
+#endif
 #ifndef BQ_REFILL_THRESH
 #define BQ_REFILL_THRESH 24
 #endif
@@ -251,33 +259,52 @@ __device__ __forceinline__ void run_class(const SweepArgs &A, double *d, const i
             if (exhausted) break;
             continue;
         }
-        // Two shrink steps of sampling._slice (sampling.pyx:344-364) per trip, one Philox block.  The second
-        // candidate only depends on where the first one fell (not on its density), so both densities are
-        // evaluated side by side; the outcome is exactly that of the sequential loop.  Branch-free:
-        // inactive lanes compute harmlessly and only the final store is predicated.
-        double ua, ub;
-        stream_pair(rng, blk, ua, ub);
-        const double xa = L + (R - L) * ua;
-        const bool upa = xa > x0;
-        const double La = upa ? L : xa, Ra = upa ? xa : R;
-        const double xb = La + (Ra - La) * ub;
-        const bool upb = xb > x0;
-        const double Lb = upb ? La : xb, Rb = upb ? xb : Ra;
-        const bool acc_a = cd.eval(xa) >= logy;
-        const bool acc_b = cd.eval(xb) >= logy;
-        const bool stuck_a = !acc_a && (Ra - La < 1e-10);
-        const bool try_b = !acc_a && !stuck_a;
-        it += 2;
-        const bool stuck_b = try_b && !acc_b && ((Rb - Lb < 1e-10) || it >= BQ_SLICE_MAX_ITERS);
-        const bool done = acc_a || (try_b && acc_b);
-        if (active) {
-            ev += try_b ? 2 : 1;
-            if (done) d[e] = acc_a ? xa : xb;
-            if (stuck_a || stuck_b) stuck += 1;
-            if (done || stuck_a || stuck_b) active = false;
+        // BQ_CAND shrink steps of sampling._slice (sampling.pyx:344-364) per trip, BQ_CAND/2 Philox blocks.
+        // A candidate's position depends on where the earlier ones fell, never on their densities, so all
+        // positions are known up front and the densities are evaluated side by side (instruction-level
+        // parallelism for a latency-bound loop); the first accepted one in order wins, which is exactly the
+        // outcome of the sequential loop.  Branch-free: idle lanes compute harmlessly, only the store is
+        // predicated.
+        double u[BQ_CAND], x[BQ_CAND], La[BQ_CAND], Ra[BQ_CAND];
+#pragma unroll
+        for (int b = 0; b < BQ_CAND / 2; ++b) stream_pair(rng, blk + (unsigned)b, u[2 * b], u[2 * b + 1]);
+        {
+            double Lk = L, Rk = R;
+#pragma unroll
+            for (int k = 0; k < BQ_CAND; ++k) {
+                x[k] = Lk + (Rk - Lk) * u[k];
+                const bool up = x[k] > x0;
+                Lk = up ? Lk : x[k];
+                Rk = up ? x[k] : Rk;
+                La[k] = Lk; Ra[k] = Rk;
+            }
         }
-        L = Lb; R = Rb;
-        blk += 1u;
+        bool acc[BQ_CAND];
+#pragma unroll
+        for (int k = 0; k < BQ_CAND; ++k) acc[k] = cd.eval(x[k]) >= logy;
+        bool going = active, done = false, stk = false;
+        double xnew = x0;
+        int nev_trip = 0;
+#pragma unroll
+        for (int k = 0; k < BQ_CAND; ++k) {
+            nev_trip += going ? 1 : 0;
+            const bool a = going && acc[k];
+            const bool c = going && !acc[k] && (Ra[k] - La[k] < 1e-10);
+            xnew = a ? x[k] : xnew;
+            done = done || a;
+            stk = stk || c;
+            going = going && !a && !c;
+        }
+        it += BQ_CAND;
+        if (going && it >= BQ_SLICE_MAX_ITERS) { stk = true; going = false; }
+        if (active) {
+            ev += nev_trip;
+            if (done) d[e] = xnew;
+            if (stk) stuck += 1;
+            active = going;
+        }
+        L = La[BQ_CAND - 1]; R = Ra[BQ_CAND - 1];
+        blk += BQ_CAND / 2;
     }
     n_ev += nev; n_evals += ev; n_stuck += stuck;
 }

@@ -27,7 +27,7 @@
  *
  * Random numbers: the reference draws from a global MT19937 (randomkit.c); stream parity is not a goal
  * (SURVEY.md section 8a).  So that whole sweeps can be compared with the kernels, this file restates the
- * product's documented stream convention (Philox4x32-10, Salmon et al. 2011; counter = (block, id, sweep,
+ * product's documented stream convention (Philox4x32-7, Salmon et al. 2011; counter = (block, id, sweep,
  * chain lo), key = (seed lo ^ tag*0x9E3779B9, seed hi ^ chain hi); two 53-bit uniforms per block) -- the
  * convention is part of the C-ABI contract (include/bq_capi.h: bq_rng_uniforms).
  *
@@ -281,7 +281,7 @@ typedef struct { uint32_t k0, k1, c1, c2, c3, blk; double spare; int has; } bqo_
 
 static void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
     int r;
-    for (r = 0; r < 10; ++r) {
+    for (r = 0; r < 7; ++r) { /* Philox4x32-7 */
         uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
         c[0] = n0; c[1] = (uint32_t)p1; c[2] = n2; c[3] = (uint32_t)p0;

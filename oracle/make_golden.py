@@ -180,7 +180,7 @@ COND = {
 POST = {
     "mm1": (200, 0.5, "DFN2", 13, 1500, 4),      # BASELINE.json configs[0]
     "qnet3": (150, 0.2, "DFN2", 21, 1200, 3),
-    "lng1": (100, 0.3, "DFN2", 22, 1000, 3),
+    "lng1": (100, 0.3, "DFN2", 22, 3000, 8),     # slow-mixing Gamma scale: needs long runs for a usable MCSE
     "mm3": (100, 0.3, "DFN2", 23, 800, 2),
     "psdelay": (80, 0.3, "PS", 24, 800, 2),
 }
