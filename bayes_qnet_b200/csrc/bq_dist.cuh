@@ -23,7 +23,7 @@ struct QConst {
     int pad;
 };
 
-__device__ __forceinline__ void qconst_set(QConst &qc, int dist, double p0, double p1) {
+__host__ __device__ __forceinline__ void qconst_set(QConst &qc, int dist, double p0, double p1) {
     qc.dist = dist;
     qc.pad = 0;
     if (dist == D_EXP) {  // -log(scale) - x/scale                      (distributions.pyx:59)
@@ -40,7 +40,7 @@ __device__ __forceinline__ void qconst_set(QConst &qc, int dist, double p0, doub
 }
 
 // log-density of service time s >= 0
-__device__ __forceinline__ double lpdf(const QConst &qc, double s) {
+__host__ __device__ __forceinline__ double lpdf(const QConst &qc, double s) {
     if (qc.dist == D_EXP) return qc.c0 - s * qc.inv;
     if (qc.dist == D_GAMMA) {
         if (qc.c1 == 0.0) return qc.c0 - s * qc.inv;  // shape == 1 special case handles s == 0

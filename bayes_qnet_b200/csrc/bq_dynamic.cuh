@@ -1,0 +1,588 @@
+// Sweep kernels for networks whose queue order is per-chain state: multi-server FIFO queues (QueueGGk
+// with k > 1, queues.pyx:444-723) and processor-sharing queues (QueuePS, queues.pyx:1032-1232), mixed
+// freely with single-server FIFO queues and delay stations.
+//
+// What the reference does per evaluation of the conditional (GGkGibbs.inner_dfun, qnet.pyx:1340-1357) is
+// build two diff lists -- diffListForDeparture(e, x) in e's queue and diffListForArrival(e', x) in the
+// queue of the task's next event -- and sum lpdf(s_new) - lpdf(s_old) over them (queues.pyx:83-95).  Here
+// the same sums are produced by forward walks over per-chain arrays:
+//
+//   d[E]        departure times                                   (fp64, the chain state proper)
+//   ord[E]      events of every queue in arrival order, queue after queue (queue 0: departure order,
+//               arrivals.pyx:256); pos[E] is the inverse permutation
+//   F[e][k]     for every event of a k-server FIFO queue: the k server-free times seen at its arrival,
+//               ascending (the reference's Event.d_proc_prev, arrivals.pxd:30, as a sorted multiset:
+//               services depend only on min F, and replacing the minimum by the event's own departure
+//               is the whole recursion of queues.pyx:654-680)
+//   dord/dpos, svc   PS queues only: events in departure order, and the stored service times
+//
+// A walk starts from the stored vector of the first event whose predecessors are unchanged, replays the
+// recursion with the modified time, and stops as soon as the running vector equals the stored one of the
+// next event (nothing further can change) or a service time goes negative (-inf).  Moving an arrival
+// re-inserts the event at its new rank (stable sort by arrival, queues.pyx:537) on the fly.
+//
+// Execution model: a GROUP of W lanes (W = 8, 16 or 32; 32/W chains per warp) owns one chain and visits
+// its resample-eligible events one after another in a fixed order.  The lanes of the group evaluate W
+// consecutive shrink candidates of sampling._slice side by side: a candidate's position depends only on
+// where the earlier candidates fell, never on their densities, so the first accepted candidate in order
+// is exactly the outcome of the sequential loop.  All lanes of a group read the same addresses (broadcast
+// loads); the accepted move is committed cooperatively (order shift across lanes, vector refresh).
+// Sufficient statistics, parameter updates and traces are fused, as in the static kernel.
+#pragma once
+#include "bq_static.cuh"
+
+// The walk and commit routines are __host__ __device__ so that the test harness under tests/emul can run the
+// very same code on the CPU (test infrastructure only: the library itself has no host execution path).
+#if defined(__CUDA_ARCH__)
+#define BQ_LDG(p) __ldg(p)
+#define BQ_SYNCG(m) __syncwarp(m)
+#else
+#define BQ_LDG(p) (*(p))
+#define BQ_SYNCG(m) ((void)(m))
+#endif
+#define BQ_HDF __host__ __device__ __forceinline__
+#define BQ_HDI __host__ __device__ inline
+
+namespace bq {
+
+struct DynArgs {
+    int E, Q, P, n_order, n_sweeps, update, flags, trace_base, n_chains, EF;
+    const int *order;                        // [n_order] resample-eligible events in sweep order
+    const int *ev_q, *ev_pt, *ev_nt, *ev_f;  // per event: queue, prev/next by task, offset of F[e] (-1: none)
+    const int *q_off;                        // [Q+1] position range of each queue inside ord
+    const int *q_type, *q_k, *q_dist, *q_poff;
+    double *state;                           // [C][E]
+    int *ord, *pos;                          // [C][E]
+    double *F;                               // [C][EF]
+    int *dord, *dpos;                        // [C][E]  (PS queues)
+    double *svc;                             // [C][E]  (PS queues)
+    double *theta;                           // [C][P]
+    long long *stats;                        // [C][BQ_NSTAT]
+    double *tr_theta, *tr_wait, *tr_logp;
+    unsigned long long seed;
+    long long chain_offset;
+    unsigned int sweep_base;
+};
+
+// ascending multiset of the k server-free times, +inf padded to KMAX so every loop is fully unrolled
+template <int KMAX>
+struct FreeVec {
+    double v[KMAX];
+    BQ_HDF void load(const double *f, int k) {
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) v[j] = (j < k) ? f[j] : INFINITY;
+    }
+    // the arriving event takes the server that frees first and holds it until x  (queues.pyx:610-612, 654-680)
+    BQ_HDF void replace_min(double x) {
+        v[0] = x;
+#pragma unroll
+        for (int j = 0; j + 1 < KMAX; ++j) {
+            const double lo = fmin(v[j], v[j + 1]), hi = fmax(v[j], v[j + 1]);
+            v[j] = lo; v[j + 1] = hi;
+        }
+    }
+    BQ_HDF bool equals(const double *f, int k) const {
+        bool eq = true;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < k) eq = eq && (v[j] == f[j]);
+        return eq;
+    }
+    BQ_HDF void store(double *f, int k) const {
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < k) f[j] = v[j];
+    }
+};
+
+// one chain's arrays + the tables shared by all chains
+struct Chain {
+    const DynArgs *A;
+    double *d;
+    int *ord, *pos;
+    double *F;
+    int *dord, *dpos;
+    double *svc;
+    const QConst *qc;
+
+    BQ_HDF void bind(const DynArgs &a, int chain, const QConst *qc_) {
+        A = &a;
+        const size_t c = (size_t)chain;
+        d = a.state + c * a.E;
+        ord = a.ord + c * a.E;
+        pos = a.pos + c * a.E;
+        F = a.F + c * a.EF;
+        dord = a.dord ? a.dord + c * a.E : nullptr;
+        dpos = a.dpos ? a.dpos + c * a.E : nullptr;
+        svc = a.svc ? a.svc + c * a.E : nullptr;
+        qc = qc_;
+    }
+    // a_e = departure of the task's previous event, 0 for the task's first event (arrivals.pyx:848)
+    BQ_HDF double arr(int i) const {
+        const int pt = BQ_LDG(&A->ev_pt[i]);
+        return (pt >= 0) ? d[pt] : 0.0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// FIFO queue with k servers: likelihoodDelta(diffListForDeparture(e, x))   (queues.pyx:470-511, 83-95)
+// ---------------------------------------------------------------------------------------------
+template <int KMAX>
+BQ_HDI double ggk_dep_delta(const Chain &c, int e, int q, double x, double a_e, double d_e, int &steps) {
+    const int k = BQ_LDG(&c.A->q_k[q]);
+    const QConst &qc = c.qc[q];
+    FreeVec<KMAX> M;
+    M.load(c.F + BQ_LDG(&c.A->ev_f[e]), k);
+    const double st = dmax(a_e, M.v[0]);
+    const double s_new = x - st;
+    if (s_new < 0.0) return BQ_NEG_INF;
+    const double s_old = d_e - st;
+    double acc = 0.0;
+    if (s_new != s_old) acc = lpdf(qc, s_new) - lpdf(qc, s_old);
+    M.replace_min(x);
+    const int end = BQ_LDG(&c.A->q_off[q + 1]);
+    for (int p = c.pos[e] + 1; p < end; ++p) {
+        const int i = c.ord[p];
+        const double *fi = c.F + BQ_LDG(&c.A->ev_f[i]);
+        if (M.equals(fi, k)) break;  // same free times as before: nothing after i changes
+        ++steps;
+        const double bn = M.v[0], bo = fi[0], di = c.d[i];
+        if (bn != bo) {
+            const double ai = c.arr(i);
+            const double sn = di - dmax(ai, bn);
+            if (sn < 0.0) return BQ_NEG_INF;
+            const double so = di - dmax(ai, bo);
+            if (sn != so) acc += lpdf(qc, sn) - lpdf(qc, so);
+        }
+        M.replace_min(di);
+    }
+    return acc;
+}
+
+// rank of e1 among the OTHER events of its queue once its arrival is x: before the first event whose
+// arrival is > x (stable sort by arrival, queues.pyx:537).  Returned as the index e1 will occupy.
+BQ_HDF int ggk_new_rank(const Chain &c, int e1, int lo, int end, int p1, double x, double a_old) {
+    int j = p1;
+    if (x >= a_old) {
+        while (j + 1 < end && c.arr(c.ord[j + 1]) <= x) ++j;
+    } else {
+        int l = lo, r = p1;
+        while (l < r) {
+            const int m = (l + r) >> 1;
+            if (c.arr(c.ord[m]) > x) r = m; else l = m + 1;
+        }
+        j = l;
+    }
+    return j;
+}
+
+// event at index t of the queue's order after e1 moved from index p1 to index j
+BQ_HDF int ggk_moved_at(const Chain &c, int t, int j, int p1, int e1) {
+    if (t == j) return e1;
+    if (j >= p1) return (t >= p1 && t < j) ? c.ord[t + 1] : c.ord[t];
+    return (t > j && t <= p1) ? c.ord[t - 1] : c.ord[t];
+}
+
+// likelihoodDelta(diffListForArrival(e1, x))   (queues.pyx:514-591, 83-95)
+template <int KMAX>
+BQ_HDI double ggk_arr_delta(const Chain &c, int e1, int q, double x, double a_old, int &steps) {
+    const int k = BQ_LDG(&c.A->q_k[q]);
+    const QConst &qc = c.qc[q];
+    const int lo = BQ_LDG(&c.A->q_off[q]), end = BQ_LDG(&c.A->q_off[q + 1]);
+    const int p1 = c.pos[e1];
+    const int j = ggk_new_rank(c, e1, lo, end, p1, x, a_old);
+    const int ps = (j < p1) ? j : p1, pe = (j < p1) ? p1 : j;
+    FreeVec<KMAX> M;
+    M.load(c.F + BQ_LDG(&c.A->ev_f[c.ord[ps]]), k);  // predecessors of index ps are untouched
+    double acc = 0.0;
+    for (int t = ps; t < end; ++t) {
+        const int i = ggk_moved_at(c, t, j, p1, e1);
+        const double *fi = c.F + BQ_LDG(&c.A->ev_f[i]);
+        if (t > pe && M.equals(fi, k)) break;
+        ++steps;
+        const double ai_old = (i == e1) ? a_old : c.arr(i);
+        const double ai = (i == e1) ? x : ai_old;
+        const double di = c.d[i];
+        const double sn = di - dmax(ai, M.v[0]);
+        if (sn < 0.0) return BQ_NEG_INF;
+        const double so = di - dmax(ai_old, fi[0]);
+        if (sn != so) acc += lpdf(qc, sn) - lpdf(qc, so);
+        M.replace_min(di);
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the conditional of d_e: inner_dfun(x) - lik0   (qnet.pyx:1340-1357)
+// ---------------------------------------------------------------------------------------------
+struct EventCtx {
+    int e, e1, q0, q1, t0, t1;
+    double x0, a_e, d1;
+};
+
+BQ_HDF void event_load(const Chain &c, int e, EventCtx &ev) {
+    const DynArgs &A = *c.A;
+    ev.e = e;
+    ev.q0 = BQ_LDG(&A.ev_q[e]);
+    ev.e1 = BQ_LDG(&A.ev_nt[e]);
+    ev.t0 = BQ_LDG(&A.q_type[ev.q0]);
+    ev.x0 = c.d[e];
+    ev.a_e = c.arr(e);
+    ev.q1 = -1; ev.t1 = -1; ev.d1 = 0.0;
+    if (ev.e1 >= 0) {
+        ev.q1 = BQ_LDG(&A.ev_q[ev.e1]);
+        ev.t1 = BQ_LDG(&A.q_type[ev.q1]);
+        ev.d1 = c.d[ev.e1];
+    }
+}
+
+template <int KMAX>
+BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, int &steps) {
+    double g;
+    if (ev.t0 == Q_GGK) {
+        g = ggk_dep_delta<KMAX>(c, ev.e, ev.q0, x, ev.a_e, ev.x0, steps);
+    } else {  // DelayStation: s = d - a, single-event diff list (queues.pyx:745-784)
+        const double sn = x - ev.a_e, so = ev.x0 - ev.a_e;
+        if (sn < 0.0) return BQ_NEG_INF;
+        g = (sn != so) ? lpdf(c.qc[ev.q0], sn) - lpdf(c.qc[ev.q0], so) : 0.0;
+    }
+    if (!(g > BQ_NEG_INF) || ev.e1 < 0) return g;
+    double g1;
+    if (ev.t1 == Q_GGK) {
+        g1 = ggk_arr_delta<KMAX>(c, ev.e1, ev.q1, x, ev.x0, steps);
+    } else {
+        const double sn = ev.d1 - x, so = ev.d1 - ev.x0;
+        if (sn < 0.0) return BQ_NEG_INF;
+        g1 = (sn != so) ? lpdf(c.qc[ev.q1], sn) - lpdf(c.qc[ev.q1], so) : 0.0;
+    }
+    return g + g1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// commit d_e := x   (apply_departure, qnet.pyx:2166-2178 -> applyDiffList, arrivals.pyx:542-604)
+// Executed by every lane of the group with identical control flow; lane 0 stores.
+// ---------------------------------------------------------------------------------------------
+template <int W, int KMAX>
+BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, unsigned gmask) {
+    const DynArgs &A = *c.A;
+    // where e1 goes is decided on the old state (its own arrival is still x0 in memory)
+    int j1 = 0, p1 = 0, lo1 = 0, end1 = 0, k1 = 0;
+    if (ev.e1 >= 0 && ev.t1 == Q_GGK) {
+        lo1 = BQ_LDG(&A.q_off[ev.q1]); end1 = BQ_LDG(&A.q_off[ev.q1 + 1]); k1 = BQ_LDG(&A.q_k[ev.q1]);
+        p1 = c.pos[ev.e1];
+        j1 = ggk_new_rank(c, ev.e1, lo1, end1, p1, x, ev.x0);
+    }
+    // ---- departure side: refresh the free-time vectors downstream of e ----------------------------------
+    if (ev.t0 == Q_GGK) {
+        const int k = BQ_LDG(&A.q_k[ev.q0]);
+        FreeVec<KMAX> M;
+        M.load(c.F + BQ_LDG(&A.ev_f[ev.e]), k);
+        M.replace_min(x);
+        const int end = BQ_LDG(&A.q_off[ev.q0 + 1]);
+        for (int p = c.pos[ev.e] + 1; p < end; ++p) {
+            const int i = c.ord[p];
+            double *fi = c.F + BQ_LDG(&A.ev_f[i]);
+            if (M.equals(fi, k)) break;
+            const double di = c.d[i];
+            BQ_SYNCG(gmask);
+            if (lane == 0) M.store(fi, k);
+            M.replace_min(di);
+        }
+    }
+    BQ_SYNCG(gmask);
+    if (lane == 0) c.d[ev.e] = x;
+    BQ_SYNCG(gmask);
+    // ---- arrival side: re-rank e1, refresh the vectors from the first changed index ------------------------
+    if (ev.e1 >= 0 && ev.t1 == Q_GGK) {
+        const int ps = (j1 < p1) ? j1 : p1, pe = (j1 < p1) ? p1 : j1;
+        FreeVec<KMAX> M;
+        M.load(c.F + BQ_LDG(&A.ev_f[c.ord[ps]]), k1);
+        for (int t = ps; t < end1; ++t) {
+            const int i = ggk_moved_at(c, t, j1, p1, ev.e1);
+            double *fi = c.F + BQ_LDG(&A.ev_f[i]);
+            if (t > pe && M.equals(fi, k1)) break;
+            const double di = c.d[i];
+            BQ_SYNCG(gmask);
+            if (lane == 0) M.store(fi, k1);
+            M.replace_min(di);
+        }
+        BQ_SYNCG(gmask);
+        if (j1 > p1) {  // later: events p1+1..j1 move one slot towards the head
+            for (int base = p1 + 1; base <= j1; base += W) {
+                const int t = base + lane;
+                int i = -1;
+                if (t <= j1) i = c.ord[t];
+                BQ_SYNCG(gmask);
+                if (i >= 0) { c.ord[t - 1] = i; c.pos[i] = t - 1; }
+                BQ_SYNCG(gmask);
+            }
+        } else if (j1 < p1) {  // earlier: events j1..p1-1 move one slot towards the tail
+            for (int top = p1 - 1; top >= j1; top -= W) {
+                const int t = top - lane;
+                int i = -1;
+                if (t >= j1) i = c.ord[t];
+                BQ_SYNCG(gmask);
+                if (i >= 0) { c.ord[t + 1] = i; c.pos[i] = t + 1; }
+                BQ_SYNCG(gmask);
+            }
+        }
+        if (j1 != p1 && lane == 0) { c.ord[j1] = ev.e1; c.pos[ev.e1] = j1; }
+        BQ_SYNCG(gmask);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// group-wide helpers
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ double group_sum(double x, unsigned gmask) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) x += __shfl_xor_sync(gmask, x, o, W);
+    return x;
+}
+template <int W>
+__device__ __forceinline__ double group_max(double x, unsigned gmask) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(gmask, x, o, W));
+    return x;
+}
+
+// service time of event i of queue q (type t) in the current state
+BQ_HDF double dyn_service(const Chain &c, int i, int t, double ai) {
+    if (t == Q_GGK) return c.d[i] - dmax(ai, c.F[BQ_LDG(&c.A->ev_f[i])]);
+    if (t == Q_DELAY) return c.d[i] - ai;
+    return c.svc[i];
+}
+
+// per-queue sufficient statistics of one chain (queues.pyx:1316-1336), every lane returns with ss[] filled
+template <int W>
+__device__ void dyn_suffstats(const Chain &c, SuffStat *ss, int lane, unsigned gmask, bool want_logp, double *logp_out) {
+    const DynArgs &A = *c.A;
+    double logp_acc = 0.0;
+    for (int q = 0; q < A.Q; ++q) {
+        const int lo = __ldg(&A.q_off[q]), hi = __ldg(&A.q_off[q + 1]);
+        const int t = __ldg(&A.q_type[q]), dist = __ldg(&A.q_dist[q]);
+        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // n, sum, sumlog, nlog, wait, nzero, logp, bad
+        for (int p = lo + lane; p < hi; p += W) {
+            const int i = c.ord[p];
+            const double ai = c.arr(i), s = dyn_service(c, i, t, ai);
+            const double w = c.d[i] - ai - s;
+            v[4] += (w > 0.0) ? w : 0.0;
+            if (s > 0.0) {
+                v[0] += 1.0; v[1] += s;
+                if (dist != D_EXP) {
+                    if (dist == D_GAMMA || s >= 1e-50) { v[2] += log(s); v[3] += 1.0; }
+                }
+            } else if (s == 0.0) v[5] += 1.0;
+            if (want_logp) {
+                if (s < 0.0) v[7] += 1.0; else v[6] += lpdf(c.qc[q], s);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = group_sum<W>(v[i], gmask);
+        double sq = 0.0;
+        if (dist == D_LOGNORMAL) {  // second pass, as distributions.pyx:276-299
+            const double mean_log = (v[3] > 0.0) ? v[2] / v[3] : 0.0;
+            for (int p = lo + lane; p < hi; p += W) {
+                const int i = c.ord[p];
+                const double s = dyn_service(c, i, t, c.arr(i));
+                if (s >= 1e-50) { const double z = log(s) - mean_log; sq += z * z; }
+            }
+            sq = group_sum<W>(sq, gmask);
+        }
+        if (lane == 0) {
+            SuffStat &o = ss[q];
+            o.n = v[0]; o.sum = v[1]; o.sumlog = v[2]; o.nlog = v[3]; o.wait = v[4]; o.nzero = v[5];
+            o.nall = (double)(hi - lo); o.sumsq = sq;
+        }
+        logp_acc += (v[7] > 0.0) ? BQ_NEG_INF : v[6];
+    }
+    __syncwarp(gmask);
+    if (logp_out) *logp_out = logp_acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the sweep kernel
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t dyn_group_smem(int Q, int P) {
+    size_t b = (size_t)Q * (sizeof(QConst) + sizeof(SuffStat)) + (size_t)((P + 1) & ~1) * sizeof(double);
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int W, int KMAX>
+__global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int G = blockDim.x / W;
+    const int gib = threadIdx.x / W, lane = threadIdx.x % W;
+    const int chain = blockIdx.x * G + gib;
+    if (chain >= A.n_chains) return;  // whole groups leave together; no block-wide barrier below
+    const unsigned gshift = (threadIdx.x & 31) & ~(W - 1);
+    const unsigned gbits = (W == 32) ? 0xffffffffu : ((1u << W) - 1u);
+    const unsigned gmask = gbits << gshift;
+    unsigned char *base = smem_raw + (size_t)gib * dyn_group_smem(A.Q, A.P);
+    QConst *qc = reinterpret_cast<QConst *>(base);
+    SuffStat *ss = reinterpret_cast<SuffStat *>(qc + A.Q);
+    double *th = reinterpret_cast<double *>(ss + A.Q);
+    const int Q = A.Q, P = A.P, E = A.E;
+
+    Chain c;
+    c.bind(A, chain, qc);
+    for (int i = lane; i < P; i += W) th[i] = A.theta[(size_t)chain * P + i];
+    __syncwarp(gmask);
+    for (int q = lane; q < Q; q += W) {
+        const int o = __ldg(&A.q_poff[q]), dist = __ldg(&A.q_dist[q]);
+        qconst_set(qc[q], dist, th[o], (dist == D_EXP) ? 0.0 : th[o + 1]);
+    }
+    __syncwarp(gmask);
+
+    const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain);
+    long long n_ev = 0, n_evals = 0, n_stuck = 0, n_pevals = 0, n_steps = 0;
+    double tmax = 0.0;
+
+    for (int sw = 0; sw < A.n_sweeps; ++sw) {
+        const unsigned int gsw = A.sweep_base + (unsigned int)sw;
+        if (sw == 0 || (A.flags & FLAG_TMAX_PER_SWEEP)) {  // Tmax = 2 max d   (qnet.pyx:672)
+            double m = 0.0;
+            for (int i = lane; i < E; i += W) m = fmax(m, c.d[i]);
+            tmax = 2.0 * group_max<W>(m, gmask);
+        }
+        const int n_order = (A.flags & FLAG_PARAMS_ONLY) ? 0 : A.n_order;
+        for (int idx = 0; idx < n_order; ++idx) {
+            EventCtx ev;
+            event_load(c, __ldg(&A.order[idx]), ev);
+            const double lower = ev.a_e;
+            const double upper = (ev.e1 >= 0) ? fmin(ev.d1, tmax) : tmax;  // qnet.pyx:698-701, 732-734
+            Rng rng;
+            rng.init(A.seed, gchain, gsw, (unsigned int)ev.e, TAG_SLICE);
+            double L = lower, R = upper, logy = 0.0, xacc = ev.x0;
+            bool accepted = false;
+            int steps = 0;
+            n_ev += 1;
+            for (int cbase = 0;; cbase += W) {
+                // candidate cbase + lane (candidate 0 is x0 itself); uniform number c of the event's stream
+                const unsigned int cidx = (unsigned int)(cbase + lane);
+                double ua, ub;
+                stream_pair(rng, cidx >> 1, ua, ub);
+                const double u = (cidx & 1u) ? ub : ua;
+                double myx = ev.x0, myL = L, myR = R;
+#pragma unroll 4
+                for (int jj = (cbase == 0) ? 1 : 0; jj < W; ++jj) {
+                    const double uj = __shfl_sync(gmask, u, jj, W);
+                    const double xj = L + (R - L) * uj;
+                    if (xj > ev.x0) R = xj; else L = xj;
+                    if (lane == jj) { myx = xj; myL = L; myR = R; }
+                }
+                const double g = dyn_logcond<KMAX>(c, ev, myx, steps);
+                if (cbase == 0) {
+                    const double g0 = __shfl_sync(gmask, g, 0, W);
+                    double u0a, u0b;
+                    stream_pair(rng, 0u, u0a, u0b);
+                    logy = g0 - (-log(1.0 - u0a));  // rk_exponential = -log(1 - U)   (cdist.c:107-110)
+                    if (!(logy > BQ_NEG_INF)) { n_stuck += 1; n_evals += 1; break; }  // sampling.pyx:289-291
+                }
+                const bool cand = (cidx != 0u);
+                const bool ok = cand && (g >= logy);
+                const bool dead = cand && !ok && (myR - myL < 1e-10);  // sampling.pyx:360-362 (we keep x0)
+                const unsigned okm = (__ballot_sync(gmask, ok) >> gshift) & gbits;
+                const unsigned deadm = (__ballot_sync(gmask, dead) >> gshift) & gbits;
+                const int fo = okm ? (__ffs(okm) - 1) : 64, fd = deadm ? (__ffs(deadm) - 1) : 64;
+                if (fo < fd) {
+                    xacc = __shfl_sync(gmask, myx, fo, W);
+                    accepted = true;
+                    n_evals += cbase + fo + 1;
+                    break;
+                }
+                if (fd < 64) { n_stuck += 1; n_evals += cbase + fd + 1; break; }
+                if (cbase + W >= BQ_SLICE_MAX_ITERS) { n_stuck += 1; n_evals += cbase + W; break; }
+            }
+            n_steps += steps;
+            if (accepted && xacc != ev.x0) dyn_commit<W, KMAX>(c, ev, xacc, lane, gmask);
+            __syncwarp(gmask);
+        }
+        const bool trace = (A.flags & FLAG_TRACE) != 0;
+        if (A.update != UPD_NONE || trace) {
+            double logp = 0.0;
+            dyn_suffstats<W>(c, ss, lane, gmask, trace, &logp);
+            const size_t recno = (size_t)(A.trace_base + sw);
+            if (trace) {
+                for (int q = lane; q < Q; q += W)
+                    A.tr_wait[(recno * A.n_chains + chain) * Q + q] = (ss[q].nall > 0.0) ? ss[q].wait / ss[q].nall : 0.0;
+                if (lane == 0) A.tr_logp[recno * A.n_chains + chain] = logp;
+            }
+            if (A.update != UPD_NONE) {
+                for (int q = lane; q < Q; q += W) {
+                    const int o = __ldg(&A.q_poff[q]), dist = __ldg(&A.q_dist[q]);
+                    double p0 = th[o], p1 = (dist == D_EXP) ? 0.0 : th[o + 1];
+                    if (A.update == UPD_BAYES) {
+                        Rng prng;
+                        prng.init(A.seed, gchain, gsw, (unsigned int)q, TAG_PARAM);
+                        sample_params(dist, ss[q], prng, p0, p1, &n_pevals);
+                    } else {
+                        estimate_params(dist, ss[q], p0, p1);
+                    }
+                    th[o] = p0;
+                    if (dist != D_EXP) th[o + 1] = p1;
+                    qconst_set(qc[q], dist, p0, p1);
+                }
+            }
+            __syncwarp(gmask);
+            if (trace)
+                for (int i = lane; i < P; i += W) A.tr_theta[(recno * A.n_chains + chain) * P + i] = th[i];
+        }
+    }
+    for (int i = lane; i < P; i += W) A.theta[(size_t)chain * P + i] = th[i];
+    n_pevals = (long long)group_sum<W>((double)n_pevals, gmask);
+    if (lane == 0) {
+        long long *st = A.stats + (size_t)chain * BQ_NSTAT;
+        st[0] += n_ev; st[1] += n_evals; st[2] += n_pevals; st[3] += n_stuck; st[5] += n_steps;
+    }
+}
+
+// ---- parity / reporting kernels ---------------------------------------------------------------
+
+// out[j] = inner_dfun(x[j]) - lik0 for event e of one chain (qnet.pyx:1340-1357); one warp
+template <int KMAX>
+__global__ void logcond_dynamic_kernel(const DynArgs A, int chain, int e, const double *x, int n, double *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QConst *qc = reinterpret_cast<QConst *>(smem_raw);
+    const double *th = A.theta + (size_t)chain * A.P;
+    for (int q = threadIdx.x; q < A.Q; q += blockDim.x) {
+        const int o = A.q_poff[q], dist = A.q_dist[q];
+        qconst_set(qc[q], dist, th[o], dist == D_EXP ? 0.0 : th[o + 1]);
+    }
+    __syncthreads();
+    Chain c;
+    c.bind(A, chain, qc);
+    EventCtx ev;
+    event_load(c, e, ev);
+    int steps = 0;
+    const double g0 = dyn_logcond<KMAX>(c, ev, ev.x0, steps);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) out[j] = dyn_logcond<KMAX>(c, ev, x[j], steps) - g0;
+}
+
+// Qnet.log_prob (qnet.pyx:1032) and the sufficient statistics, one warp per chain
+__global__ void __launch_bounds__(128) report_dynamic_kernel(const DynArgs A, double *logp_out, double *ss_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chain = blockIdx.x * (blockDim.x >> 5) + gib;
+    if (chain >= A.n_chains) return;
+    unsigned char *base = smem_raw + (size_t)gib * dyn_group_smem(A.Q, A.P);
+    QConst *qc = reinterpret_cast<QConst *>(base);
+    SuffStat *ss = reinterpret_cast<SuffStat *>(qc + A.Q);
+    const double *th = A.theta + (size_t)chain * A.P;
+    for (int q = lane; q < A.Q; q += 32) {
+        const int o = A.q_poff[q], dist = A.q_dist[q];
+        qconst_set(qc[q], dist, th[o], dist == D_EXP ? 0.0 : th[o + 1]);
+    }
+    __syncwarp();
+    Chain c;
+    c.bind(A, chain, qc);
+    double logp = 0.0;
+    dyn_suffstats<32>(c, ss, lane, 0xffffffffu, true, &logp);
+    if (lane == 0 && logp_out) logp_out[chain] = logp;
+    if (ss_out)
+        for (int i = lane; i < A.Q * 8; i += 32)
+            ss_out[(size_t)chain * A.Q * 8 + i] = reinterpret_cast<double *>(ss)[i];
+}
+
+}  // namespace bq

@@ -16,6 +16,8 @@
 
 #include "../../include/bq_capi.h"
 #include "bq_static.cuh"
+#include "bq_dynamic.cuh"
+#include "bq_host.h"
 
 using namespace bq;
 
@@ -65,6 +67,20 @@ struct bq_handle {
     long long n_sweeps = 0, n_launches = 0;
     float last_ms = 0.f;
     bool timed = false;
+    // ---- dynamic-order networks (k > 1, PS): per-chain queue order and free-time vectors ----
+    bool has_ps = false;
+    int EF = 0, kmax = 1, dyn_w = 32, dyn_threads = 128;
+    std::vector<int> ev_f, q_off, ord0;  // F offset per event, queue ranges, initial order
+    int *d_order = nullptr, *d_ev_nt = nullptr, *d_ev_f = nullptr, *d_q_k = nullptr;
+    int *d_ord = nullptr, *d_pos = nullptr, *d_dord = nullptr, *d_dpos = nullptr;
+    double *d_F = nullptr, *d_svc = nullptr;
+    HostNet net() const {
+        HostNet n;
+        n.E = E; n.Q = Q;
+        n.q_type = q_type.data(); n.q_k = q_k.data(); n.q_off = q_off.data();
+        n.ev_f = ev_f.data(); n.prev_byt = prev_byt.data();
+        return n;
+    }
 };
 
 extern "C" const char *bq_last_error(void) { return g_err.c_str(); }
@@ -205,13 +221,144 @@ static void fill_args(const bq_handle *h, SweepArgs &A) {
     A.refill = h->refill;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// dynamic-order networks (k > 1, PS): host-side construction of one chain's derived arrays
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t replicate_rows(T *base, size_t row, size_t C, cudaStream_t st) {  // row 0 -> rows 1..C-1
+    for (size_t have = 1; have < C; have *= 2) {
+        const size_t n = std::min(have, C - have);
+        cudaError_t e = cudaMemcpyAsync(base + have * row, base, n * row * sizeof(T), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+static void fill_dyn_args(const bq_handle *h, DynArgs &A) {
+    memset(&A, 0, sizeof(A));
+    A.E = h->E; A.Q = h->Q; A.P = h->P; A.n_chains = h->C; A.EF = h->EF;
+    A.n_order = (int)h->order.size();
+    A.order = h->d_order;
+    A.ev_q = h->d_ev_q; A.ev_pt = h->d_ev_pt; A.ev_nt = h->d_ev_nt; A.ev_f = h->d_ev_f;
+    A.q_off = h->d_q_off; A.q_type = h->d_q_type; A.q_k = h->d_q_k; A.q_dist = h->d_q_dist; A.q_poff = h->d_q_poff;
+    A.state = h->d_state; A.ord = h->d_ord; A.pos = h->d_pos; A.F = h->d_F;
+    A.dord = h->d_dord; A.dpos = h->d_dpos; A.svc = h->d_svc;
+    A.theta = h->d_theta; A.stats = h->d_stats;
+    A.tr_theta = h->d_tr_theta; A.tr_wait = h->d_tr_wait; A.tr_logp = h->d_tr_logp;
+    A.seed = h->seed; A.chain_offset = h->chain_offset; A.sweep_base = h->sweep_counter;
+}
+
+// per-handle tables of the dynamic kernels + the derived arrays of the initial state, replicated to all chains
+static int setup_dynamic(bq_handle *h, const double *d0) {
+    const int E = h->E, Q = h->Q;
+    // initial queue orders from the caller's by-queue links
+    h->ord0.assign(E, -1);
+    std::vector<int> head(Q, -1), cnt(Q, 0);
+    for (int e = 0; e < E; ++e)
+        if (h->prev_byq[e] < 0) {
+            if (head[h->qid[e]] >= 0) return fail(BQ_ERR_INVALID, "a queue has two head events (prev_byq < 0)");
+            head[h->qid[e]] = e;
+        }
+    for (int q = 0; q < Q; ++q) {
+        int p = h->q_off[q];
+        for (int e = head[q]; e >= 0; e = h->next_byq[e]) {
+            if (p >= h->q_off[q + 1]) return fail(BQ_ERR_INVALID, "by-queue links do not form one list per queue");
+            h->ord0[p++] = e;
+        }
+        if (p != h->q_off[q + 1]) return fail(BQ_ERR_INVALID, "by-queue links do not cover the queue");
+    }
+    h->ev_f.assign(E, -1);
+    h->EF = 0; h->kmax = 1;
+    for (int q = 0; q < Q; ++q)
+        if (h->q_type[q] == Q_GGK) {
+            h->kmax = std::max(h->kmax, h->q_k[q]);
+            for (int p = h->q_off[q]; p < h->q_off[q + 1]; ++p) { h->ev_f[h->ord0[p]] = h->EF; h->EF += h->q_k[q]; }
+        }
+    if (h->kmax > 8) return fail(BQ_ERR_UNSUPPORTED, "more than 8 processors per queue");
+    std::vector<int> pos0(E);
+    std::vector<double> F0(std::max(h->EF, 1));
+    { HostNet hn = h->net(); host_rebuild(&hn, d0, h->ord0.data(), pos0.data(), F0.data(), false); }
+    // sweep order: queue after queue, each in its initial arrival order (any fixed scan is a valid Gibbs sweep)
+    h->order.clear();
+    for (int p = 0; p < E; ++p)
+        if (eligible(h, h->ord0[p])) h->order.push_back(h->ord0[p]);
+    h->color_off.resize(h->order.size() + 1);
+    for (size_t i = 0; i <= h->order.size(); ++i) h->color_off[i] = (int)i;
+
+    const size_t C = h->C;
+    CK(upload(&h->d_order, h->order.data(), h->order.size()));
+    CK(upload(&h->d_ev_nt, h->next_byt.data(), E));
+    CK(upload(&h->d_ev_f, h->ev_f.data(), E));
+    CK(upload(&h->d_q_k, h->q_k.data(), Q));
+    CK(cudaMalloc((void **)&h->d_ord, C * E * sizeof(int)));
+    CK(cudaMalloc((void **)&h->d_pos, C * E * sizeof(int)));
+    CK(cudaMalloc((void **)&h->d_F, std::max<size_t>(C * h->EF, 1) * sizeof(double)));
+    CK(cudaMemcpyAsync(h->d_ord, h->ord0.data(), E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_pos, pos0.data(), E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_F, F0.data(), h->EF * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(replicate_rows(h->d_ord, E, C, h->stream));
+    CK(replicate_rows(h->d_pos, E, C, h->stream));
+    if (h->EF) CK(replicate_rows(h->d_F, h->EF, C, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (const char *env = getenv("BQ_DYN_W")) {
+        int w = atoi(env);
+        if (w == 8 || w == 16 || w == 32) h->dyn_w = w;
+    }
+    if (const char *env = getenv("BQ_DYN_THREADS")) {
+        int t = atoi(env);
+        if (t == 32 || t == 64 || t == 128) h->dyn_threads = t;
+    }
+    return BQ_OK;
+}
+
+// new departure times for chains [lo, hi) of a dynamic-order handle: every queue is re-ranked by arrival and
+// the derived arrays are rebuilt on the host
+static int dynamic_set_rows(bq_handle *h, int lo, int hi, const double *d, bool same_for_all) {
+    const size_t E = h->E, EF = h->EF, n = (size_t)(hi - lo);
+    const size_t rows = same_for_all ? 1 : n;
+    std::vector<int> ord(rows * E), pos(rows * E);
+    std::vector<double> F(std::max<size_t>(rows * EF, 1));
+    const HostNet hn = h->net();
+    for (size_t r = 0; r < rows; ++r) {
+        memcpy(&ord[r * E], h->ord0.data(), E * sizeof(int));
+        host_rebuild(&hn, d + r * E, &ord[r * E], &pos[r * E], &F[r * EF], true);
+    }
+    CK(cudaMemcpyAsync(h->d_state + (size_t)lo * E, d, rows * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_ord + (size_t)lo * E, ord.data(), rows * E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_pos + (size_t)lo * E, pos.data(), rows * E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (EF) CK(cudaMemcpyAsync(h->d_F + (size_t)lo * EF, F.data(), rows * EF * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (same_for_all) {
+        CK(replicate_rows(h->d_state + (size_t)lo * E, E, n, h->stream));
+        CK(replicate_rows(h->d_ord + (size_t)lo * E, E, n, h->stream));
+        CK(replicate_rows(h->d_pos + (size_t)lo * E, E, n, h->stream));
+        if (EF) CK(replicate_rows(h->d_F + (size_t)lo * EF, EF, n, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return BQ_OK;
+}
+
+template <int W>
+static void launch_dynamic_w(bq_handle *h, const DynArgs &A) {
+    const int G = h->dyn_threads / W, blocks = (h->C + G - 1) / G;
+    const size_t sm = (size_t)G * dyn_group_smem(h->Q, h->P);
+    if (h->kmax <= 4) sweep_dynamic_kernel<W, 4><<<blocks, h->dyn_threads, sm, h->stream>>>(A);
+    else sweep_dynamic_kernel<W, 8><<<blocks, h->dyn_threads, sm, h->stream>>>(A);
+}
+static void launch_dynamic(bq_handle *h, const DynArgs &A) {
+    if (h->dyn_w == 8) launch_dynamic_w<8>(h, A);
+    else if (h->dyn_w == 16) launch_dynamic_w<16>(h, A);
+    else launch_dynamic_w<32>(h, A);
+}
+
 extern "C" int bq_destroy(bq_handle *h) {
     if (!h) return BQ_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->d_rec, h->d_color_off, h->d_ev_q, h->d_ev_p, h->d_ev_pt, h->d_q_events, h->d_q_off,
                     h->d_q_type, h->d_q_dist, h->d_q_poff, h->d_state, h->d_theta, h->d_stats,
-                    h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch};
+                    h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch, h->d_order, h->d_ev_nt, h->d_ev_f,
+                    h->d_q_k, h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_F, h->d_svc};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -273,8 +420,13 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         if (h->next_byt[e] >= 0 && h->qid[h->next_byt[e]] == h->qid[e])
             return bail(BQ_ERR_UNSUPPORTED, "a task visits the same queue twice in a row");
     }
-    if (!h->static_order)
-        return bail(BQ_ERR_UNSUPPORTED, "multi-server (k>1) and PS queues are not in this build yet");
+    for (int q = 0; q < Q; ++q) {
+        if (h->q_type[q] == Q_PS) h->has_ps = true;
+        if (h->q_k[q] < 1) return bail(BQ_ERR_INVALID, "queue with fewer than one processor");
+    }
+    if (h->has_ps) return bail(BQ_ERR_UNSUPPORTED, "PS queues are not in this build yet");
+    if (const char *env = getenv("BQ_FORCE_DYNAMIC"))
+        if (env[0] == '1') h->static_order = false;  // run a static-order network through the dynamic kernels
 
     cudaError_t ce = cudaSetDevice(device);
     if (ce != cudaSuccess) return bail(BQ_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
@@ -298,6 +450,7 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
     std::vector<int> q_off(Q + 1, 0), q_events(E);
     for (int e = 0; e < E; ++e) q_off[h->qid[e] + 1]++;
     for (int q = 0; q < Q; ++q) q_off[q + 1] += q_off[q];
+    h->q_off = q_off;
     {
         std::vector<int> fill(q_off.begin(), q_off.end() - 1);
         for (int e = 0; e < E; ++e) q_events[fill[h->qid[e]]++] = e;
@@ -317,8 +470,8 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
     const size_t C = (size_t)n_chains;
     CKB(cudaMalloc((void **)&h->d_state, C * E * sizeof(double)));
     CKB(cudaMalloc((void **)&h->d_theta, C * h->P * sizeof(double)));
-    CKB(cudaMalloc((void **)&h->d_stats, C * 4 * sizeof(long long)));
-    CKB(cudaMemset(h->d_stats, 0, C * 4 * sizeof(long long)));
+    CKB(cudaMalloc((void **)&h->d_stats, C * BQ_NSTAT * sizeof(long long)));
+    CKB(cudaMemset(h->d_stats, 0, C * BQ_NSTAT * sizeof(long long)));
     {
         // replicate the initial state / parameters to every chain
         std::vector<double> rep;
@@ -333,6 +486,9 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         for (size_t c = 0; c < C; ++c) memcpy(&th[c * h->P], theta0, h->P * sizeof(double));
         CKB(cudaMemcpy(h->d_theta, th.data(), th.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+
+    if (!h->static_order)
+        if (int rc = setup_dynamic(h, a->d)) { std::string msg = g_err; bq_destroy(h); return fail(rc, msg); }
 
     // shared-memory staging of the chain state when it fits (227 KB per CTA on sm_100a)
     int max_optin = 0;
@@ -393,6 +549,7 @@ extern "C" int bq_get_params(bq_handle *h, int32_t lo, int32_t hi, double *theta
 extern "C" int bq_set_state(bq_handle *h, int32_t lo, int32_t hi, const double *d) {
     if (int r = check_range(h, lo, hi)) return r;
     CK(cudaSetDevice(h->device));
+    if (!h->static_order) return dynamic_set_rows(h, lo, hi, d, false);
     CK(cudaMemcpyAsync(h->d_state + (size_t)lo * h->E, d, (size_t)(hi - lo) * h->E * sizeof(double),
                        cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -403,6 +560,7 @@ extern "C" int bq_set_state(bq_handle *h, int32_t lo, int32_t hi, const double *
 extern "C" int bq_broadcast_state(bq_handle *h, const double *d) {
     if (!h || !d) return fail(BQ_ERR_INVALID, "null argument");
     CK(cudaSetDevice(h->device));
+    if (!h->static_order) return dynamic_set_rows(h, 0, h->C, d, true);
     const size_t E = h->E, C = h->C;
     CK(cudaMemcpyAsync(h->d_state, d, E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     for (size_t have = 1; have < C; have *= 2) {
@@ -423,6 +581,18 @@ extern "C" int bq_get_state(bq_handle *h, int32_t lo, int32_t hi, double *d, dou
     double *dd = d;
     if (!dd) { tmp.resize(n * E); dd = tmp.data(); }
     CK(cudaMemcpyAsync(dd, h->d_state + (size_t)lo * E, n * E * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (!h->static_order) {
+        if (!(a || s || proc || prev_byq || next_byq)) { CK(cudaStreamSynchronize(h->stream)); return BQ_OK; }
+        std::vector<int> ord(n * E);
+        CK(cudaMemcpyAsync(ord.data(), h->d_ord + (size_t)lo * E, n * E * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const HostNet hn = h->net();
+        for (size_t c = 0; c < n; ++c)
+            host_derive(&hn, dd + c * E, &ord[c * E], a ? a + c * E : nullptr, s ? s + c * E : nullptr,
+                        proc ? proc + c * E : nullptr, prev_byq ? prev_byq + c * E : nullptr,
+                        next_byq ? next_byq + c * E : nullptr);
+        return BQ_OK;
+    }
     CK(cudaStreamSynchronize(h->stream));
     for (size_t c = 0; c < n; ++c) {
         const double *dc = dd + c * E;
@@ -486,7 +656,12 @@ static int launch_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t up
     fill_args(h, A);
     A.n_sweeps = n_sweeps; A.update = update; A.flags = (int)flags; A.trace_base = h->trace_len;
     CK(cudaEventRecord(h->ev0, h->stream));
-    if (h->use_smem) {
+    if (!h->static_order) {
+        DynArgs D;
+        fill_dyn_args(h, D);
+        D.n_sweeps = n_sweeps; D.update = update; D.flags = (int)flags; D.trace_base = h->trace_len;
+        launch_dynamic(h, D);
+    } else if (h->use_smem) {
         if (h->all_exp) sweep_static_kernel<true, true><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
         else sweep_static_kernel<true, false><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
     } else {
@@ -546,10 +721,18 @@ extern "C" int bq_logcond(bq_handle *h, int32_t chain, int32_t eid, const double
         h->scratch_n = 2 * n;
     }
     CK(cudaMemcpyAsync(h->d_scratch, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    SweepArgs A;
-    fill_args(h, A);
-    SchedRec r = make_rec(h, eid);
-    logcond_static_kernel<<<1, 128, 0, h->stream>>>(A, chain, r, h->d_scratch, n, h->d_scratch + n);
+    if (!h->static_order) {
+        DynArgs D;
+        fill_dyn_args(h, D);
+        const size_t sm = dyn_group_smem(h->Q, h->P);
+        if (h->kmax <= 4) logcond_dynamic_kernel<4><<<1, 32, sm, h->stream>>>(D, chain, eid, h->d_scratch, n, h->d_scratch + n);
+        else logcond_dynamic_kernel<8><<<1, 32, sm, h->stream>>>(D, chain, eid, h->d_scratch, n, h->d_scratch + n);
+    } else {
+        SweepArgs A;
+        fill_args(h, A);
+        SchedRec r = make_rec(h, eid);
+        logcond_static_kernel<<<1, 128, 0, h->stream>>>(A, chain, r, h->d_scratch, n, h->d_scratch + n);
+    }
     CK(cudaGetLastError());
     h->n_launches += 1;
     CK(cudaMemcpyAsync(out, h->d_scratch + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -564,10 +747,16 @@ static int run_report(bq_handle *h, double *logp_host, double *ss_host) {
     CK(cudaMalloc((void **)&d_lp, C * sizeof(double)));
     cudaError_t e = cudaMalloc((void **)&d_ss, C * h->Q * 8 * sizeof(double));
     if (e != cudaSuccess) { cudaFree(d_lp); return fail(BQ_ERR_CUDA, cudaGetErrorString(e)); }
-    SweepArgs A;
-    fill_args(h, A);
-    size_t sm = static_smem_bytes(h, false);
-    report_static_kernel<<<h->C, 256, sm, h->stream>>>(A, d_lp, d_ss);
+    if (!h->static_order) {
+        DynArgs D;
+        fill_dyn_args(h, D);
+        report_dynamic_kernel<<<(h->C + 3) / 4, 128, 4 * dyn_group_smem(h->Q, h->P), h->stream>>>(D, d_lp, d_ss);
+    } else {
+        SweepArgs A;
+        fill_args(h, A);
+        size_t sm = static_smem_bytes(h, false);
+        report_static_kernel<<<h->C, 256, sm, h->stream>>>(A, d_lp, d_ss);
+    }
     e = cudaGetLastError();
     h->n_launches += 1;
     if (e == cudaSuccess && logp_host)
@@ -593,15 +782,18 @@ extern "C" int bq_suffstats(bq_handle *h, double *out) {
 extern "C" int bq_stats(bq_handle *h, bq_stats_t *out) {
     if (!h || !out) return fail(BQ_ERR_INVALID, "null argument");
     CK(cudaSetDevice(h->device));
-    std::vector<long long> st((size_t)h->C * 4);
+    std::vector<long long> st((size_t)h->C * BQ_NSTAT);
     CK(cudaMemcpyAsync(st.data(), h->d_stats, st.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     memset(out, 0, sizeof(*out));
     for (int c = 0; c < h->C; ++c) {
-        out->nevents += st[(size_t)c * 4 + 0];
-        out->slice_evals += st[(size_t)c * 4 + 1];
-        out->param_evals += st[(size_t)c * 4 + 2];
-        out->n_stuck += st[(size_t)c * 4 + 3];
+        const long long *r = &st[(size_t)c * BQ_NSTAT];
+        out->nevents += r[0];
+        out->slice_evals += r[1];
+        out->param_evals += r[2];
+        out->n_stuck += r[3];
+        out->nreject += r[4];
+        out->diff_len += r[5];
     }
     out->slice_calls = out->nevents;
     out->num_diff = out->slice_evals;
@@ -612,7 +804,7 @@ extern "C" int bq_stats(bq_handle *h, bq_stats_t *out) {
 extern "C" int bq_reset_stats(bq_handle *h) {
     if (!h) return fail(BQ_ERR_INVALID, "null handle");
     CK(cudaSetDevice(h->device));
-    CK(cudaMemsetAsync(h->d_stats, 0, (size_t)h->C * 4 * sizeof(long long), h->stream));
+    CK(cudaMemsetAsync(h->d_stats, 0, (size_t)h->C * BQ_NSTAT * sizeof(long long), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->n_sweeps = 0;
     return BQ_OK;

@@ -22,6 +22,7 @@ namespace bq {
 #define BQ_MAX_THREADS 512
 #endif
 #define BQ_SLICE_MAX_ITERS 1000
+#define BQ_NSTAT 8  // per-chain counters: nevents, slice_evals, param_evals, stuck, nreject, walk steps, 2 spare
 
 enum { UPD_NONE = 0, UPD_BAYES = 1, UPD_STEM = 2 };
 enum { FLAG_TMAX_PER_SWEEP = 1, FLAG_NO_FINAL = 2, FLAG_TRACE = 4, FLAG_TIGHT = 8, FLAG_PARAMS_ONLY = 1 << 16 };
@@ -52,7 +53,7 @@ struct SweepArgs {
     const int *q_type, *q_dist, *q_poff;
     double *state;      // [C][E]
     double *theta;      // [C][P]
-    long long *stats;   // [C][4]: nevents, slice_evals, param_evals, stuck
+    long long *stats;   // [C][BQ_NSTAT]: nevents, slice_evals, param_evals, stuck, ...
     double *tr_theta;   // [rec][C][P]
     double *tr_wait;    // [rec][C][Q]
     double *tr_logp;    // [rec][C]
@@ -62,7 +63,7 @@ struct SweepArgs {
 };
 
 // max without fmax()'s NaN handling: DSETP + 2 selects instead of ~8 instructions (the hot loop has no NaNs)
-__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__host__ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 
 // Local conditional of d_e given its Markov blanket (GGkGibbs.inner_dfun, qnet.pyx:1340-1357, in the
 // closed form of SURVEY.md A.2): G(d) = sum of the new-service log-densities; -inf outside the support.
@@ -529,7 +530,7 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
     atomicAdd(&cnt[2], (unsigned long long)n_pevals);
     atomicAdd(&cnt[3], (unsigned long long)n_stuck);
     __syncthreads();
-    if (threadIdx.x < 4) A.stats[(size_t)chain * 4 + threadIdx.x] += (long long)cnt[threadIdx.x];
+    if (threadIdx.x < 4) A.stats[(size_t)chain * BQ_NSTAT + threadIdx.x] += (long long)cnt[threadIdx.x];
 }
 
 // ---- parity / reporting kernels ---------------------------------------------------------------

@@ -1,0 +1,177 @@
+// TEST INFRASTRUCTURE ONLY.  Runs the __host__ __device__ walk / commit routines of the product's dynamic-order
+// kernels (bayes_qnet_b200/csrc/bq_dynamic.cuh) on the CPU for ONE chain, so that the CPU test-suite can check the
+// kernel logic against oracle/ without a GPU.  Nothing under bayes_qnet_b200/ links or loads this file; the
+// product has no host execution path.  The slice loop below restates, sequentially (group width 1), what
+// sweep_dynamic_kernel does with W lanes.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../bayes_qnet_b200/csrc/bq_dynamic.cuh"
+#include "../../bayes_qnet_b200/csrc/bq_host.h"
+
+using namespace bq;
+
+struct Emul {
+    int E, Q, P;
+    std::vector<int> q_type, q_k, q_dist, q_poff, q_off;
+    std::vector<int> qid, prev_byt, next_byt, ev_f, ord, pos, dord, dpos;
+    std::vector<uint8_t> obs_a, obs_d;
+    std::vector<double> d, F, svc, theta;
+    std::vector<QConst> qc;
+    int EF;
+    DynArgs A;
+    Chain c;
+    long evals, steps;
+
+    void refresh_qc() {
+        for (int q = 0; q < Q; ++q) {
+            int o = q_poff[q];
+            qconst_set(qc[q], q_dist[q], theta[o], q_dist[q] == D_EXP ? 0.0 : theta[o + 1]);
+        }
+    }
+    void bind() {
+        memset(&A, 0, sizeof(A));
+        A.E = E; A.Q = Q; A.P = P; A.n_chains = 1; A.EF = EF;
+        A.ev_q = qid.data(); A.ev_pt = prev_byt.data(); A.ev_nt = next_byt.data(); A.ev_f = ev_f.data();
+        A.q_off = q_off.data(); A.q_type = q_type.data(); A.q_k = q_k.data(); A.q_dist = q_dist.data();
+        A.q_poff = q_poff.data();
+        A.state = d.data(); A.ord = ord.data(); A.pos = pos.data(); A.F = F.data();
+        A.dord = dord.data(); A.dpos = dpos.data(); A.svc = svc.data();
+        A.theta = theta.data();
+        c.bind(A, 0, qc.data());
+    }
+};
+
+extern "C" {
+
+void *bqe_create(int E, int Q, int P, const int *q_type, const int *q_k, const int *q_dist, const int *q_poff,
+                 const double *theta, const int *qid, const int *prev_byt, const int *next_byt, const int *prev_byq,
+                 const int *next_byq, const uint8_t *obs_a, const uint8_t *obs_d, const double *d) {
+    Emul *m = new Emul();
+    m->E = E; m->Q = Q; m->P = P;
+    m->q_type.assign(q_type, q_type + Q); m->q_k.assign(q_k, q_k + Q); m->q_dist.assign(q_dist, q_dist + Q);
+    m->q_poff.assign(q_poff, q_poff + Q);
+    m->theta.assign(theta, theta + P);
+    m->qid.assign(qid, qid + E); m->prev_byt.assign(prev_byt, prev_byt + E); m->next_byt.assign(next_byt, next_byt + E);
+    m->obs_a.assign(obs_a, obs_a + E); m->obs_d.assign(obs_d, obs_d + E);
+    m->d.assign(d, d + E);
+    m->q_off.assign(Q + 1, 0);
+    for (int e = 0; e < E; ++e) m->q_off[qid[e] + 1]++;
+    for (int q = 0; q < Q; ++q) m->q_off[q + 1] += m->q_off[q];
+    m->ord.assign(E, -1); m->pos.assign(E, -1); m->dord.assign(E, -1); m->dpos.assign(E, -1); m->svc.assign(E, 0.0);
+    for (int q = 0; q < Q; ++q) {
+        int p = m->q_off[q];
+        for (int e = 0; e < E; ++e)
+            if (qid[e] == q && prev_byq[e] < 0)
+                for (int x = e; x >= 0; x = next_byq[x]) m->ord[p++] = x;
+    }
+    m->ev_f.assign(E, -1);
+    m->EF = 0;
+    for (int q = 0; q < Q; ++q)
+        if (q_type[q] == Q_GGK)
+            for (int p = m->q_off[q]; p < m->q_off[q + 1]; ++p) { m->ev_f[m->ord[p]] = m->EF; m->EF += q_k[q]; }
+    m->F.assign(m->EF + 1, 0.0);
+    m->qc.resize(Q);
+    HostNet hn{E, Q, m->q_type.data(), m->q_k.data(), m->q_off.data(), m->ev_f.data(), m->prev_byt.data()};
+    host_rebuild(&hn, m->d.data(), m->ord.data(), m->pos.data(), m->F.data(), false);
+    m->refresh_qc();
+    m->bind();
+    m->evals = m->steps = 0;
+    return m;
+}
+
+void bqe_destroy(void *h) { delete (Emul *)h; }
+
+void bqe_set_theta(void *h, const double *theta) {
+    Emul *m = (Emul *)h;
+    m->theta.assign(theta, theta + m->P);
+    m->refresh_qc();
+}
+
+void bqe_logcond(void *h, int e, const double *x, int n, double *out) {
+    Emul *m = (Emul *)h;
+    EventCtx ev;
+    event_load(m->c, e, ev);
+    int steps = 0;
+    const double g0 = dyn_logcond<8>(m->c, ev, ev.x0, steps);
+    for (int j = 0; j < n; ++j) out[j] = dyn_logcond<8>(m->c, ev, x[j], steps) - g0;
+}
+
+void bqe_apply(void *h, int e, double x) {
+    Emul *m = (Emul *)h;
+    EventCtx ev;
+    event_load(m->c, e, ev);
+    dyn_commit<1, 8>(m->c, ev, x, 0, 1u);
+}
+
+// one sweep over `order`, same stream convention as the kernels: uniform 0 of (chain, sweep, event) is the slice
+// level, uniform c >= 1 the c-th shrink candidate
+long bqe_slice_sweep(void *h, const int *order, int n_order, uint64_t seed, int64_t chain, uint32_t sweep, double tmax) {
+    Emul *m = (Emul *)h;
+    long ne = 0;
+    for (int idx = 0; idx < n_order; ++idx) {
+        EventCtx ev;
+        event_load(m->c, order[idx], ev);
+        const double lower = ev.a_e, upper = (ev.e1 >= 0) ? fmin(ev.d1, tmax) : tmax;
+        Rng rng;
+        rng.init(seed, (uint64_t)chain, sweep, (uint32_t)ev.e, TAG_SLICE);
+        int steps = 0;
+        const double g0 = dyn_logcond<8>(m->c, ev, ev.x0, steps);
+        m->evals++;
+        ++ne;
+        const double logy = g0 - (-log(1.0 - rng.uniform()));
+        if (!(logy > BQ_NEG_INF)) continue;
+        double L = lower, R = upper, x1 = ev.x0;
+        for (int it = 0; it < BQ_SLICE_MAX_ITERS; ++it) {
+            x1 = L + (R - L) * rng.uniform();
+            m->evals++;
+            if (dyn_logcond<8>(m->c, ev, x1, steps) >= logy) break;
+            if (x1 > ev.x0) R = x1; else L = x1;
+            if (R - L < 1e-10) { x1 = ev.x0; break; }
+        }
+        m->steps += steps;
+        if (x1 != ev.x0) dyn_commit<1, 8>(m->c, ev, x1, 0, 1u);
+    }
+    return ne;
+}
+
+void bqe_get(void *h, double *d, int *ord, double *F, double *svc) {
+    Emul *m = (Emul *)h;
+    if (d) memcpy(d, m->d.data(), m->E * sizeof(double));
+    if (ord) memcpy(ord, m->ord.data(), m->E * sizeof(int));
+    if (F) memcpy(F, m->F.data(), m->EF * sizeof(double));
+    if (svc) memcpy(svc, m->svc.data(), m->E * sizeof(double));
+}
+
+// a, s, proc, links recomputed from (d, ord) by the library's host code
+void bqe_derive(void *h, double *a, double *s, int32_t *proc, int32_t *prev_byq, int32_t *next_byq) {
+    Emul *m = (Emul *)h;
+    HostNet hn{m->E, m->Q, m->q_type.data(), m->q_k.data(), m->q_off.data(), m->ev_f.data(), m->prev_byt.data()};
+    host_derive(&hn, m->d.data(), m->ord.data(), a, s, proc, prev_byq, next_byq);
+}
+
+// consistency of the incrementally maintained arrays with a from-scratch rebuild: 0 = consistent
+int bqe_check(void *h) {
+    Emul *m = (Emul *)h;
+    std::vector<int> ord(m->ord), pos(m->E);
+    std::vector<double> F(m->EF + 1, 0.0);
+    HostNet hn{m->E, m->Q, m->q_type.data(), m->q_k.data(), m->q_off.data(), m->ev_f.data(), m->prev_byt.data()};
+    host_rebuild(&hn, m->d.data(), ord.data(), pos.data(), F.data(), false);
+    for (int e = 0; e < m->E; ++e)
+        if (pos[e] != m->pos[e]) return 1;
+    for (int i = 0; i < m->EF; ++i)
+        if (F[i] != m->F[i]) return 2;
+    // every non-delay queue must be sorted by arrival
+    for (int q = 0; q < m->Q; ++q) {
+        if (m->q_type[q] == Q_DELAY) continue;
+        for (int p = m->q_off[q] + 1; p < m->q_off[q + 1]; ++p)
+            if (m->c.arr(m->ord[p]) < m->c.arr(m->ord[p - 1])) return 3;
+    }
+    return 0;
+}
+
+long bqe_evals(void *h) { return ((Emul *)h)->evals; }
+}

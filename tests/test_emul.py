@@ -1,0 +1,47 @@
+"""The dynamic-order walk / commit routines of the CUDA kernels (bq_dynamic.cuh), compiled for the host by
+tests/emul and run against (i) the reference's own inner_dfun vectors and (ii) the CPU oracle's trajectories.
+This is the no-GPU check of the kernel logic; the kernels themselves are checked by test_gpu_parity.py."""
+import numpy
+import pytest
+
+import emul_helper
+import helpers
+
+TOL = 1e-9
+
+
+@pytest.mark.parametrize("name", helpers.STATIC_NETS + helpers.DYNAMIC_NETS)
+def test_emulated_logcond_matches_reference_vectors(name):
+    g = helpers.golden("cond_" + name)
+    total = 0
+    for st, pre, theta in (("s0", "s0", g["theta"]), ("s1", "s1", g["theta"]), ("s2", "s1", g["s2_theta"])):
+        net, arrv = helpers.golden_state(g, pre, theta)
+        ec = emul_helper.EmulChain(net, arrv, theta)
+        for r, xs, ref in zip(g[st + "_rows"], g[st + "_x"], g[st + "_g"]):
+            v = ec.logcond(int(r), xs)
+            assert numpy.array_equal(numpy.isfinite(v), numpy.isfinite(ref)), "support differs at row %d" % r
+            m = numpy.isfinite(ref)
+            if m.any():
+                assert helpers.relerr(v[m], ref[m]).max() < TOL
+                total += int(m.sum())
+    assert total > 200
+
+
+@pytest.mark.parametrize("name", helpers.STATIC_NETS + helpers.DYNAMIC_NETS)
+def test_emulated_sweeps_match_oracle(name):
+    """Same stream, same scan order: identical trajectories, and the incrementally maintained queue order and
+    free-time vectors stay consistent with a from-scratch rebuild after every sweep."""
+    g = helpers.golden("cond_" + name)
+    net, arrv = helpers.golden_state(g, "s0")
+    oc = helpers.oracle_chain(net, arrv)
+    ec = emul_helper.EmulChain(net, arrv)
+    order = oc.eligible()
+    for s in range(6):
+        oc.slice_sweep(order, 4242, 3, s)
+        ec.slice_sweep(order, 4242, 3, s)
+        assert ec.check() == 0
+    dv = ec.derive()
+    assert helpers.relerr(ec.d, oc.d).max() < TOL
+    assert helpers.relerr(dv["s"], oc.s).max() < TOL
+    assert numpy.array_equal(dv["proc"], oc.proc)
+    assert numpy.array_equal(dv["next_byq"], oc.next_byq) and numpy.array_equal(dv["prev_byq"], oc.prev_byq)

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 
-@pytest.mark.parametrize("name", helpers.STATIC_NETS)
+@pytest.mark.parametrize("name", helpers.STATIC_NETS + helpers.DYNAMIC_NETS)
 def test_logcond_matches_reference_vectors(name):
     """bq_logcond == GGkGibbs.inner_dfun - lik0 (qnet.pyx:1340-1357) on states the reference produced."""
     g = helpers.golden("cond_" + name)
@@ -35,7 +35,7 @@ def test_logcond_matches_reference_vectors(name):
     assert total > 200
 
 
-@pytest.mark.parametrize("name", helpers.STATIC_NETS)
+@pytest.mark.parametrize("name", helpers.STATIC_NETS + helpers.DYNAMIC_NETS)
 def test_sweep_trajectory_matches_oracle(name):
     """Same seed, same schedule -> the kernel and the CPU oracle walk the same path (5 sweeps, 3 chains)."""
     g = helpers.golden("cond_" + name)
@@ -57,6 +57,11 @@ def test_sweep_trajectory_matches_oracle(name):
             assert abs(lp[c] - oc.log_prob()) < TOL * max(1.0, abs(oc.log_prob()))
             oss = oc.suffstats()
             assert helpers.relerr(ss[c], oss).max() < 1e-8
+            full = eng.state(c, c + 1, full=True)
+            assert helpers.relerr(full["s"][0], oc.s).max() < TOL and helpers.relerr(full["a"][0], oc.a).max() < TOL
+            assert numpy.array_equal(full["proc"][0], oc.proc)
+            assert numpy.array_equal(full["next_byq"][0], oc.next_byq)
+            assert numpy.array_equal(full["prev_byq"][0], oc.prev_byq)
         assert st["nevents"] == 3 * 5 * len(order)
         assert not numpy.array_equal(d[0], d[1])  # chains differ only by their RNG counters
 
@@ -245,3 +250,57 @@ def test_posterior_agrees_with_long_reference_runs(name):
     # the sampler mixes slowly on heavily loaded, mostly hidden queues (same algorithm as the reference), so
     # R-hat is a sanity bound here, not a convergence claim; the MCSEs above already account for autocorrelation
     assert numpy.all(diagnostics.rhat(th) < 2.0)
+
+
+@pytest.mark.parametrize("width", ["8", "16", "32"])
+@pytest.mark.parametrize("name", ["qnet3", "lng1", "mm3", "lnk"])
+def test_dynamic_kernel_group_widths(name, width, monkeypatch):
+    """The dynamic-order kernel (per-chain queue order, free-time vectors) with W = 8 / 16 / 32 lanes per chain:
+    the speculative candidates of a group reproduce the sequential slice sampler, so every width walks the
+    oracle's path; static-order networks are forced through the same kernel as a cross-check."""
+    monkeypatch.setenv("BQ_DYN_W", width)
+    monkeypatch.setenv("BQ_FORCE_DYNAMIC", "1")
+    g = helpers.golden("cond_" + name)
+    net, arrv = helpers.golden_state(g, "s0")
+    with GibbsEngine(net, arrv, n_chains=5, seed=911, chain_offset=2) as eng:
+        off, order = eng.schedule()
+        assert len(off) == len(order) + 1  # sequential scan: one event per class
+        eng.sweep(4, "SLICE", "BAYES", trace=True)
+        d, th = eng.state(), eng.params()
+        tr_th, tr_mw, tr_lp = eng.traces()
+        for c in (0, 4):
+            oc = helpers.oracle_chain(net, arrv)
+            for s in range(4):
+                oc.slice_sweep(order, eng.seed, 2 + c, s)
+                assert abs(tr_lp[s, c] - oc.log_prob()) < 1e-8 * max(1.0, abs(oc.log_prob()))
+                oc.update_params("BAYES", eng.seed, 2 + c, s)
+                assert helpers.relerr(tr_th[s, c], oc.theta).max() < 1e-7
+            assert helpers.relerr(d[c], oc.d).max() < 1e-7
+        assert eng.stats()["nevents"] == 5 * 4 * len(order)
+
+
+def test_dynamic_set_state_and_sharding():
+    """set_state / broadcast_state re-rank the queues and rebuild the free-time vectors; chains are addressed by
+    global id, so shards reproduce the unsharded run."""
+    g = helpers.golden("cond_mm3")
+    net, arrv = helpers.golden_state(g, "s0")
+    with GibbsEngine(net, arrv, n_chains=6, seed=5150) as whole:
+        whole.sweep(3, "SLICE", "BAYES")
+        d, th = whole.state(), whole.params()
+        full = whole.state(full=True)
+    for k in range(2):
+        with GibbsEngine(net, arrv, n_chains=3, seed=5150, chain_offset=3 * k) as part:
+            part.sweep(3, "SLICE", "BAYES")
+            assert numpy.array_equal(part.state(), d[3 * k:3 * k + 3])
+            assert numpy.array_equal(part.params(), th[3 * k:3 * k + 3])
+    # feed chain 4's state to a fresh engine: same derived quantities, and it keeps sampling validly
+    with GibbsEngine(net, arrv, n_chains=2, seed=1) as eng:
+        eng.set_state(d[4])
+        f2 = eng.state(full=True)
+        for k in ("s", "a", "proc", "next_byq"):
+            assert numpy.array_equal(f2[k][1], full[k][4]), k
+        eng.broadcast_state(d[2])
+        f3 = eng.state(full=True)
+        assert numpy.array_equal(f3["s"][0], full["s"][2]) and numpy.array_equal(f3["s"][1], full["s"][2])
+        eng.sweep(2, "SLICE", "NONE")
+        assert numpy.all(eng.state(full=True)["s"] >= 0) and numpy.all(numpy.isfinite(eng.log_prob()))
