@@ -14,7 +14,8 @@
 //               ascending (the reference's Event.d_proc_prev, arrivals.pxd:30, as a sorted multiset:
 //               services depend only on min F, and replacing the minimum by the event's own departure
 //               is the whole recursion of queues.pyx:654-680)
-//   dord/dpos, svc   PS queues only: events in departure order, and the stored service times
+//   at/dt, dord/dpos, svc   PS queues only: sorted arrival and departure times, the events in departure
+//               order, and the stored service times
 //
 // A walk starts from the stored vector of the first event whose predecessors are unchanged, replays the
 // recursion with the modified time, and stops as soon as the running vector equals the stored one of the
@@ -54,8 +55,8 @@ struct DynArgs {
     double *state;                           // [C][E]
     int *ord, *pos;                          // [C][E]
     double *F;                               // [C][EF]
-    int *dord, *dpos;                        // [C][E]  (PS queues)
-    double *svc;                             // [C][E]  (PS queues)
+    int *dord, *dpos;                        // [C][E]  (PS queues) events in departure order / inverse
+    double *at, *dt, *svc;                   // [C][E]  (PS queues) sorted arrival / departure times, services
     double *theta;                           // [C][P]
     long long *stats;                        // [C][BQ_NSTAT]
     double *tr_theta, *tr_wait, *tr_logp;
@@ -77,7 +78,8 @@ struct FreeVec {
         v[0] = x;
 #pragma unroll
         for (int j = 0; j + 1 < KMAX; ++j) {
-            const double lo = fmin(v[j], v[j + 1]), hi = fmax(v[j], v[j + 1]);
+            const bool sw = v[j] > v[j + 1];  // no NaNs here: one DSETP + selects instead of fmin/fmax
+            const double lo = sw ? v[j + 1] : v[j], hi = sw ? v[j] : v[j + 1];
             v[j] = lo; v[j + 1] = hi;
         }
     }
@@ -102,7 +104,7 @@ struct Chain {
     int *ord, *pos;
     double *F;
     int *dord, *dpos;
-    double *svc;
+    double *at, *dt, *svc;
     const QConst *qc;
 
     BQ_HDF void bind(const DynArgs &a, int chain, const QConst *qc_) {
@@ -115,6 +117,8 @@ struct Chain {
         dord = a.dord ? a.dord + c * a.E : nullptr;
         dpos = a.dpos ? a.dpos + c * a.E : nullptr;
         svc = a.svc ? a.svc + c * a.E : nullptr;
+        at = a.at ? a.at + c * a.E : nullptr;
+        dt = a.dt ? a.dt + c * a.E : nullptr;
         qc = qc_;
     }
     // a_e = departure of the task's previous event, 0 for the task's first event (arrivals.pyx:848)
@@ -213,6 +217,202 @@ BQ_HDI double ggk_arr_delta(const Chain &c, int e1, int q, double x, double a_ol
 }
 
 // ---------------------------------------------------------------------------------------------
+// Processor sharing (QueuePS, queues.pyx:1032-1232): s_i = integral over [a_i, d_i] of dt / N(t), with
+// N(t) = #{a <= t} - #{d <= t} over the queue (cninq.pyx:55-58).  Per chain and PS queue the arrival times are
+// kept sorted in at[] (event ids: ord[]) and the departure times in dt[] (event ids: dord[]), the service
+// times in svc[].  Moving one arrival or departure of event m from t_old to t_new changes N(t) by sgn = +-1 on
+// I = (lo, hi) = (min, max) only, so (diffListForDeparture / diffListForArrival, queues.pyx:1149-1183):
+//   * m itself gains or loses   sgn * integral over I of dt / max(N_old, N_old + sgn),
+//   * every other event i that is in the queue during part of I changes by the integral over I ^ [a_i, d_i] of
+//     (1 / (N_old + sgn) - 1 / N_old) dt,
+//   * likelihoodDelta adds log(N_old(d_i) + 1) - log(N_new(d_i) + 1) for the events that depart inside I and for
+//     m's own departure (queues.pyx:1220-1232).
+// The breakpoints inside I are a merge of two contiguous ranges of at[] and dt[]; ranks are found by galloping
+// from the moved event's own slots, so no search starts cold.
+// ---------------------------------------------------------------------------------------------
+
+// first index in [lo, hi) whose value is > t, galloping from `hint`
+BQ_HDI int ps_upper(const double *v, int lo, int hi, int hint, double t) {
+    if (hint < lo) hint = lo;
+    if (hint > hi) hint = hi;
+    int l, r;  // invariant: v[l] <= t (or l == lo - 1), v[r] > t (or r == hi)
+    if (hint < hi && v[hint] <= t) {
+        l = hint;
+        int step = 1;
+        r = l + step;
+        while (r < hi && v[r] <= t) { l = r; step <<= 1; r = l + step; }
+        if (r > hi) r = hi;
+    } else {
+        r = hint;
+        int step = 1;
+        l = r - step;
+        while (l >= lo && v[l] > t) { r = l; step <<= 1; l = r - step; }
+        if (l < lo - 1) l = lo - 1;
+    }
+    while (r - l > 1) {
+        const int m = (l + r) >> 1;
+        if (v[m] <= t) l = m; else r = m;
+    }
+    return r;
+}
+
+struct PsMove {
+    int q, m, lo_q, hi_q, sgn;
+    int ia, id;     // first arrival / departure strictly after lo
+    int n0;         // N_old just after lo
+    double lo, hi;  // the interval on which N(t) changes
+    bool is_dep;
+};
+
+// merge cursor over the breakpoints strictly inside (lo, hi)
+struct PsCursor {
+    int ia, id, n;
+    double t0;
+    BQ_HDF void start(const PsMove &mv) { ia = mv.ia; id = mv.id; n = mv.n0; t0 = mv.lo; }
+    // next piece [t0, t1) with constant N_old = n; returns false after the last piece.  kind: +1 arrival,
+    // -1 departure, 0 end of I at t1; `slot` = index of the breakpoint in its array
+    BQ_HDF bool piece(const Chain &c, const PsMove &mv, double &t1, int &kind, int &slot) const {
+        const double ta = (ia < mv.hi_q) ? c.at[ia] : INFINITY, td = (id < mv.hi_q) ? c.dt[id] : INFINITY;
+        if (ta <= td) { t1 = ta; kind = 1; slot = ia; } else { t1 = td; kind = -1; slot = id; }
+        if (!(t1 < mv.hi)) { t1 = mv.hi; kind = 0; slot = -1; }
+        return true;
+    }
+    BQ_HDF void advance(double t1, int kind) {
+        if (kind > 0) { ++n; ++ia; } else if (kind < 0) { --n; ++id; }
+        t0 = t1;
+    }
+};
+
+BQ_HDI void ps_move_setup(const Chain &c, int q, int m, bool is_dep, double t_old, double t_new, PsMove &mv) {
+    mv.q = q; mv.m = m; mv.is_dep = is_dep;
+    mv.lo_q = BQ_LDG(&c.A->q_off[q]); mv.hi_q = BQ_LDG(&c.A->q_off[q + 1]);
+    mv.lo = (t_new < t_old) ? t_new : t_old;
+    mv.hi = (t_new < t_old) ? t_old : t_new;
+    // departure later / arrival earlier: m is in the queue longer
+    mv.sgn = is_dep ? ((t_new > t_old) ? 1 : -1) : ((t_new < t_old) ? 1 : -1);
+    const int pa = c.pos[m], pd = c.dpos[m];
+    // arrivals <= lo: a_m <= lo always (departure moves stay right of a_m; arrival moves: lo = min(a_old, x));
+    // departures <= lo: d_m >= lo always, so the rank is at or before m's own departure slot
+    mv.ia = ps_upper(c.at, mv.lo_q, mv.hi_q, pa, mv.lo);
+    mv.id = ps_upper(c.dt, mv.lo_q, mv.hi_q, pd, mv.lo);
+    mv.n0 = (mv.ia - mv.lo_q) - (mv.id - mv.lo_q);
+}
+
+// change of event i's service: it is in the queue on [b_i, e_i] ^ I; MINE = i is the moved event itself
+template <bool MINE>
+BQ_HDI double ps_delta_service(const Chain &c, const PsMove &mv, double b_i, double e_i) {
+    PsCursor cu;
+    cu.start(mv);
+    double acc = 0.0;
+    for (;;) {
+        double t1; int kind, slot;
+        cu.piece(c, mv, t1, kind, slot);
+        const double a = (cu.t0 > b_i) ? cu.t0 : b_i, b = (t1 < e_i) ? t1 : e_i;
+        if (b > a) {
+            const double n = (double)cu.n;
+            if (MINE) acc += (b - a) / ((mv.sgn > 0) ? n + 1.0 : n);
+            else acc += (b - a) * (1.0 / (n + (double)mv.sgn) - 1.0 / n);
+        }
+        if (kind == 0 || !(t1 < e_i)) break;
+        cu.advance(t1, kind);
+    }
+    return MINE ? (double)mv.sgn * acc : acc;
+}
+
+// Visits every event of the queue whose service changes.  COMMIT = false: returns
+// likelihoodDelta (sum of lpdf(s_new) - lpdf(s_old) plus the log N terms).  COMMIT = true: stores the new
+// service times (lane 0) and returns 0.
+template <bool COMMIT>
+BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, int &steps) {
+    const QConst &qc = c.qc[mv.q];
+    double acc = 0.0;
+    // the moved event
+    {
+        const double ds = ps_delta_service<true>(c, mv, mv.lo, mv.hi);
+        const double so = c.svc[mv.m];
+        double sn = so + ds;
+        if (sn < 0.0) sn = 0.0;
+        if (COMMIT) { if (lane == 0) c.svc[mv.m] = sn; }
+        else acc += lpdf(qc, sn) - lpdf(qc, so);
+    }
+    // events in the queue just after lo (other than m): scan back over the arrivals <= lo
+    int need = mv.n0 - ((mv.sgn < 0) ? 1 : 0);
+    for (int p = mv.ia - 1; p >= mv.lo_q && need > 0; --p) {
+        const int i = c.ord[p];
+        if (i == mv.m) continue;
+        const double di = c.d[i];
+        if (!(di > mv.lo)) continue;
+        --need; ++steps;
+        const double ds = ps_delta_service<false>(c, mv, mv.lo, di);
+        const double so = c.svc[i];
+        double sn = so + ds;
+        if (sn < 0.0) sn = 0.0;
+        if (COMMIT) { if (lane == 0) c.svc[i] = sn; }
+        else acc += lpdf(qc, sn) - lpdf(qc, so);
+    }
+    // events that arrive inside I
+    for (int p = mv.ia; p < mv.hi_q && c.at[p] < mv.hi; ++p) {
+        const int i = c.ord[p];
+        if (i == mv.m) continue;
+        ++steps;
+        const double ds = ps_delta_service<false>(c, mv, c.at[p], c.d[i]);
+        const double so = c.svc[i];
+        double sn = so + ds;
+        if (sn < 0.0) sn = 0.0;
+        if (COMMIT) { if (lane == 0) c.svc[i] = sn; }
+        else acc += lpdf(qc, sn) - lpdf(qc, so);
+    }
+    if (COMMIT) return 0.0;
+    // log N terms: departures strictly inside I see one job more (sgn > 0) or less; plus m's own departure
+    PsCursor cu;
+    cu.start(mv);
+    for (;;) {
+        double t1; int kind, slot;
+        cu.piece(c, mv, t1, kind, slot);
+        if (kind == 0) break;
+        if (kind < 0 && c.dord[slot] != mv.m) acc += log((double)cu.n) - log((double)(cu.n + mv.sgn));
+        cu.advance(t1, kind);
+    }
+    if (mv.is_dep) {
+        // N_old(d_old) + 1 and N_new(x) + 1, m counted (queues.pyx:1225-1230)
+        if (mv.sgn > 0) acc += log((double)(mv.n0 + 1)) - log((double)(cu.n + 1));
+        else acc += log((double)cu.n) - log((double)mv.n0);
+    }
+    return acc;
+}
+
+// commit: slide m's entry of the sorted array (times v, ids ev, inverse inv) from slot p to its new rank
+template <int W>
+BQ_HDI void ps_reslot(double *v, int *ev, int *inv, int lo_q, int hi_q, int p, int m, double t_new, int lane,
+                      unsigned gmask) {
+    // rank among the other entries: before the first one > t_new
+    int j = ps_upper(v, lo_q, hi_q, p, t_new);  // counts m's own old entry if it is <= t_new
+    if (v[p] <= t_new) --j;                      // ... remove it from the count: j = final slot of m
+    BQ_SYNCG(gmask);
+    if (j > p) {
+        for (int base = p + 1; base <= j; base += W) {
+            const int t = base + lane;
+            int i = -1; double x = 0.0;
+            if (t <= j) { i = ev[t]; x = v[t]; }
+            BQ_SYNCG(gmask);
+            if (i >= 0) { ev[t - 1] = i; v[t - 1] = x; inv[i] = t - 1; }
+            BQ_SYNCG(gmask);
+        }
+    } else if (j < p) {
+        for (int top = p - 1; top >= j; top -= W) {
+            const int t = top - lane;
+            int i = -1; double x = 0.0;
+            if (t >= j) { i = ev[t]; x = v[t]; }
+            BQ_SYNCG(gmask);
+            if (i >= 0) { ev[t + 1] = i; v[t + 1] = x; inv[i] = t + 1; }
+            BQ_SYNCG(gmask);
+        }
+    }
+    if (lane == 0) { ev[j] = m; v[j] = t_new; inv[m] = j; }
+    BQ_SYNCG(gmask);
+}
+
+// ---------------------------------------------------------------------------------------------
 // the conditional of d_e: inner_dfun(x) - lik0   (qnet.pyx:1340-1357)
 // ---------------------------------------------------------------------------------------------
 struct EventCtx {
@@ -241,6 +441,14 @@ BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, int &ste
     double g;
     if (ev.t0 == Q_GGK) {
         g = ggk_dep_delta<KMAX>(c, ev.e, ev.q0, x, ev.a_e, ev.x0, steps);
+    } else if (ev.t0 == Q_PS) {
+        if (x < ev.a_e) return BQ_NEG_INF;
+        g = 0.0;
+        if (x != ev.x0) {
+            PsMove mv;
+            ps_move_setup(c, ev.q0, ev.e, true, ev.x0, x, mv);
+            g = ps_apply_move<false>(c, mv, 0, steps);
+        }
     } else {  // DelayStation: s = d - a, single-event diff list (queues.pyx:745-784)
         const double sn = x - ev.a_e, so = ev.x0 - ev.a_e;
         if (sn < 0.0) return BQ_NEG_INF;
@@ -250,6 +458,14 @@ BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, int &ste
     double g1;
     if (ev.t1 == Q_GGK) {
         g1 = ggk_arr_delta<KMAX>(c, ev.e1, ev.q1, x, ev.x0, steps);
+    } else if (ev.t1 == Q_PS) {
+        if (x > ev.d1) return BQ_NEG_INF;
+        g1 = 0.0;
+        if (x != ev.x0) {
+            PsMove mv;
+            ps_move_setup(c, ev.q1, ev.e1, false, ev.x0, x, mv);
+            g1 = ps_apply_move<false>(c, mv, 0, steps);
+        }
     } else {
         const double sn = ev.d1 - x, so = ev.d1 - ev.x0;
         if (sn < 0.0) return BQ_NEG_INF;
@@ -289,6 +505,25 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
             M.replace_min(di);
         }
     }
+    // PS: new service times of everything that overlaps the moved interval, computed on the old arrays
+    int dummy = 0;
+    if (ev.t0 == Q_PS) {
+        PsMove mv;
+        ps_move_setup(c, ev.q0, ev.e, true, ev.x0, x, mv);
+        ps_apply_move<true>(c, mv, lane, dummy);
+    }
+    if (ev.e1 >= 0 && ev.t1 == Q_PS) {
+        PsMove mv;
+        ps_move_setup(c, ev.q1, ev.e1, false, ev.x0, x, mv);
+        ps_apply_move<true>(c, mv, lane, dummy);
+    }
+    BQ_SYNCG(gmask);
+    if (ev.t0 == Q_PS)
+        ps_reslot<W>(c.dt, c.dord, c.dpos, BQ_LDG(&A.q_off[ev.q0]), BQ_LDG(&A.q_off[ev.q0 + 1]), c.dpos[ev.e], ev.e, x,
+                     lane, gmask);
+    if (ev.e1 >= 0 && ev.t1 == Q_PS)
+        ps_reslot<W>(c.at, c.ord, c.pos, BQ_LDG(&A.q_off[ev.q1]), BQ_LDG(&A.q_off[ev.q1 + 1]), c.pos[ev.e1], ev.e1, x,
+                     lane, gmask);
     BQ_SYNCG(gmask);
     if (lane == 0) c.d[ev.e] = x;
     BQ_SYNCG(gmask);

@@ -3,6 +3,7 @@
 // the library at create / set_state / get_state time and by the test harness under tests/emul.
 #pragma once
 #include <stdint.h>
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -25,7 +26,30 @@ static inline void fv_replace_min(double *v, int k, double x) {
 // ord: the events of each queue (ranges h->q_off) in queue order.  With `resort`, FIFO and PS queues are first
 // re-ranked by (arrival, departure) -- queue 0, whose arrivals are all 0, thereby by departure
 // (arrivals.pyx:256).  Fills pos and the free-time vectors F (queues.pyx:654-680 as a sorted multiset).
-static void host_rebuild(const HostNet *h, const double *d, int *ord, int *pos, double *F, bool resort) {
+// PS queues additionally get their sorted arrival / departure times (at, dt), the departure order (dord, dpos)
+// and the service times from the definition (queues.pyx:1049-1070); those pointers may be null otherwise.
+struct HostPs { double *at, *dt, *svc; int *dord, *dpos; };
+
+// s = integral over [a, d] of dt / N(t) on the queue's sorted arrival / departure times (n of each)
+static double host_ps_service(const double *at, const double *dt, int n, double a, double d) {
+    int ia = (int)(std::upper_bound(at, at + n, a) - at), id = (int)(std::upper_bound(dt, dt + n, a) - dt);
+    int cnt = ia - id;
+    if (d - a < 1e-15) return (d - a) / (1.0 + cnt);
+    double t0 = a, s = 0.0;
+    for (;;) {
+        const double ta = ia < n ? at[ia] : INFINITY, td = id < n ? dt[id] : INFINITY;
+        const bool arr = ta <= td;
+        const double t1 = arr ? ta : td;
+        if (!(t1 < d)) { if (cnt > 0) s += (d - t0) / cnt; break; }
+        if (t1 > t0 && cnt > 0) s += (t1 - t0) / cnt;
+        if (arr) { ++cnt; ++ia; } else { --cnt; ++id; }
+        t0 = t1;
+    }
+    return s;
+}
+
+static void host_rebuild(const HostNet *h, const double *d, int *ord, int *pos, double *F, bool resort,
+                         const HostPs *ps = nullptr) {
     auto arr = [&](int i) { int pt = h->prev_byt[i]; return pt >= 0 ? d[pt] : 0.0; };
     std::vector<double> M;
     for (int q = 0; q < h->Q; ++q) {
@@ -46,13 +70,21 @@ static void host_rebuild(const HostNet *h, const double *d, int *ord, int *pos, 
                 fv_replace_min(M.data(), k, d[i]);
             }
         }
+        if (h->q_type[q] == 2 /* Q_PS */ && ps) {
+            for (int p = lo; p < hi; ++p) { ps->at[p] = arr(ord[p]); ps->dord[p] = ord[p]; }
+            std::stable_sort(ps->dord + lo, ps->dord + hi, [&](int x, int y) { return d[x] < d[y]; });
+            for (int p = lo; p < hi; ++p) { ps->dt[p] = d[ps->dord[p]]; ps->dpos[ps->dord[p]] = p; }
+            for (int p = lo; p < hi; ++p)
+                ps->svc[ord[p]] = host_ps_service(ps->at + lo, ps->dt + lo, hi - lo, ps->at[p], d[ord[p]]);
+        }
     }
 }
 
 // a, s, proc and the by-queue links of one chain from d and its queue order (what Event carries in the
 // reference: arrivals.pxd:11-37; proc = first arg-min of the processor-indexed vector, queues.pyx:1518-1527)
 static void host_derive(const HostNet *h, const double *d, const int *ord, double *a, double *s, int32_t *proc,
-                        int32_t *prev_byq, int32_t *next_byq) {
+                        int32_t *prev_byq, int32_t *next_byq, const double *svc = nullptr,
+                        const int *ord0 = nullptr) {
     const int E = h->E;
     std::vector<double> av(E);
     for (int e = 0; e < E; ++e) { int pt = h->prev_byt[e]; av[e] = pt >= 0 ? d[pt] : 0.0; }
@@ -61,10 +93,14 @@ static void host_derive(const HostNet *h, const double *d, const int *ord, doubl
     for (int q = 0; q < h->Q; ++q) {
         const int lo = h->q_off[q], hi = h->q_off[q + 1], k = h->q_k[q], t = h->q_type[q];
         fr.assign(std::max(k, 1), 0.0);
+        // the reference never relinks a PS queue (queues.pyx:1149-1183 touch only a, d, s): report the initial links
+        const int *lk = (t == 2 /* Q_PS */ && ord0) ? ord0 : ord;
+        for (int p = lo; p < hi; ++p) {
+            if (prev_byq) prev_byq[lk[p]] = p > lo ? lk[p - 1] : -1;
+            if (next_byq) next_byq[lk[p]] = p + 1 < hi ? lk[p + 1] : -1;
+        }
         for (int p = lo; p < hi; ++p) {
             const int i = ord[p];
-            if (prev_byq) prev_byq[i] = p > lo ? ord[p - 1] : -1;
-            if (next_byq) next_byq[i] = p + 1 < hi ? ord[p + 1] : -1;
             int pr = 0;
             double sv = d[i] - av[i];
             if (t == 0 /* Q_GGK */) {
@@ -73,6 +109,7 @@ static void host_derive(const HostNet *h, const double *d, const int *ord, doubl
                 sv = d[i] - std::max(av[i], fr[pr]);
                 fr[pr] = d[i];
             }
+            if (t == 2 /* Q_PS */ && svc) sv = svc[i];
             if (proc) proc[i] = pr;
             if (s) s[i] = sv;
         }

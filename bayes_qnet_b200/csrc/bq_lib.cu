@@ -73,7 +73,7 @@ struct bq_handle {
     std::vector<int> ev_f, q_off, ord0;  // F offset per event, queue ranges, initial order
     int *d_order = nullptr, *d_ev_nt = nullptr, *d_ev_f = nullptr, *d_q_k = nullptr;
     int *d_ord = nullptr, *d_pos = nullptr, *d_dord = nullptr, *d_dpos = nullptr;
-    double *d_F = nullptr, *d_svc = nullptr;
+    double *d_F = nullptr, *d_svc = nullptr, *d_at = nullptr, *d_dt = nullptr;
     HostNet net() const {
         HostNet n;
         n.E = E; n.Q = Q;
@@ -243,7 +243,7 @@ static void fill_dyn_args(const bq_handle *h, DynArgs &A) {
     A.ev_q = h->d_ev_q; A.ev_pt = h->d_ev_pt; A.ev_nt = h->d_ev_nt; A.ev_f = h->d_ev_f;
     A.q_off = h->d_q_off; A.q_type = h->d_q_type; A.q_k = h->d_q_k; A.q_dist = h->d_q_dist; A.q_poff = h->d_q_poff;
     A.state = h->d_state; A.ord = h->d_ord; A.pos = h->d_pos; A.F = h->d_F;
-    A.dord = h->d_dord; A.dpos = h->d_dpos; A.svc = h->d_svc;
+    A.dord = h->d_dord; A.dpos = h->d_dpos; A.svc = h->d_svc; A.at = h->d_at; A.dt = h->d_dt;
     A.theta = h->d_theta; A.stats = h->d_stats;
     A.tr_theta = h->d_tr_theta; A.tr_wait = h->d_tr_wait; A.tr_logp = h->d_tr_logp;
     A.seed = h->seed; A.chain_offset = h->chain_offset; A.sweep_base = h->sweep_counter;
@@ -276,9 +276,14 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
             for (int p = h->q_off[q]; p < h->q_off[q + 1]; ++p) { h->ev_f[h->ord0[p]] = h->EF; h->EF += h->q_k[q]; }
         }
     if (h->kmax > 8) return fail(BQ_ERR_UNSUPPORTED, "more than 8 processors per queue");
-    std::vector<int> pos0(E);
-    std::vector<double> F0(std::max(h->EF, 1));
-    { HostNet hn = h->net(); host_rebuild(&hn, d0, h->ord0.data(), pos0.data(), F0.data(), false); }
+    std::vector<int> pos0(E), dord0, dpos0;
+    std::vector<double> F0(std::max(h->EF, 1)), at0, dt0, svc0;
+    if (h->has_ps) { dord0.assign(E, 0); dpos0.assign(E, 0); at0.assign(E, 0.0); dt0.assign(E, 0.0); svc0.assign(E, 0.0); }
+    {
+        HostNet hn = h->net();
+        HostPs ps{at0.data(), dt0.data(), svc0.data(), dord0.data(), dpos0.data()};
+        host_rebuild(&hn, d0, h->ord0.data(), pos0.data(), F0.data(), false, h->has_ps ? &ps : nullptr);
+    }
     // sweep order: queue after queue, each in its initial arrival order (any fixed scan is a valid Gibbs sweep)
     h->order.clear();
     for (int p = 0; p < E; ++p)
@@ -300,7 +305,27 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
     CK(replicate_rows(h->d_ord, E, C, h->stream));
     CK(replicate_rows(h->d_pos, E, C, h->stream));
     if (h->EF) CK(replicate_rows(h->d_F, h->EF, C, h->stream));
+    if (h->has_ps) {
+        CK(cudaMalloc((void **)&h->d_dord, C * E * sizeof(int)));
+        CK(cudaMalloc((void **)&h->d_dpos, C * E * sizeof(int)));
+        CK(cudaMalloc((void **)&h->d_at, C * E * sizeof(double)));
+        CK(cudaMalloc((void **)&h->d_dt, C * E * sizeof(double)));
+        CK(cudaMalloc((void **)&h->d_svc, C * E * sizeof(double)));
+        CK(cudaMemcpyAsync(h->d_dord, dord0.data(), E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_dpos, dpos0.data(), E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_at, at0.data(), E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_dt, dt0.data(), E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_svc, svc0.data(), E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(replicate_rows(h->d_dord, E, C, h->stream));
+        CK(replicate_rows(h->d_dpos, E, C, h->stream));
+        CK(replicate_rows(h->d_at, E, C, h->stream));
+        CK(replicate_rows(h->d_dt, E, C, h->stream));
+        CK(replicate_rows(h->d_svc, E, C, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
+    // lanes per chain: wide groups hide the latency of a single chain's serial walk when chains are few; with many
+    // chains narrower groups waste fewer lanes on speculative candidates (measured on B200, tools/probe_dyn.py)
+    h->dyn_w = (h->C >= 3072) ? 8 : (h->C >= 1536 ? 16 : 32);
     if (const char *env = getenv("BQ_DYN_W")) {
         int w = atoi(env);
         if (w == 8 || w == 16 || w == 32) h->dyn_w = w;
@@ -317,12 +342,32 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
 static int dynamic_set_rows(bq_handle *h, int lo, int hi, const double *d, bool same_for_all) {
     const size_t E = h->E, EF = h->EF, n = (size_t)(hi - lo);
     const size_t rows = same_for_all ? 1 : n;
-    std::vector<int> ord(rows * E), pos(rows * E);
-    std::vector<double> F(std::max<size_t>(rows * EF, 1));
+    std::vector<int> ord(rows * E), pos(rows * E), dord, dpos;
+    std::vector<double> F(std::max<size_t>(rows * EF, 1)), at, dt, svc;
+    if (h->has_ps) {
+        dord.assign(rows * E, 0); dpos.assign(rows * E, 0);
+        at.assign(rows * E, 0.0); dt.assign(rows * E, 0.0); svc.assign(rows * E, 0.0);
+    }
     const HostNet hn = h->net();
     for (size_t r = 0; r < rows; ++r) {
         memcpy(&ord[r * E], h->ord0.data(), E * sizeof(int));
-        host_rebuild(&hn, d + r * E, &ord[r * E], &pos[r * E], &F[r * EF], true);
+        HostPs ps{at.data() + r * E, dt.data() + r * E, svc.data() + r * E, dord.data() + r * E, dpos.data() + r * E};
+        host_rebuild(&hn, d + r * E, &ord[r * E], &pos[r * E], &F[r * EF], true, h->has_ps ? &ps : nullptr);
+    }
+    if (h->has_ps) {
+        const size_t o = (size_t)lo * E;
+        CK(cudaMemcpyAsync(h->d_dord + o, dord.data(), rows * E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_dpos + o, dpos.data(), rows * E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_at + o, at.data(), rows * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_dt + o, dt.data(), rows * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_svc + o, svc.data(), rows * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (same_for_all) {
+            CK(replicate_rows(h->d_dord + o, E, n, h->stream));
+            CK(replicate_rows(h->d_dpos + o, E, n, h->stream));
+            CK(replicate_rows(h->d_at + o, E, n, h->stream));
+            CK(replicate_rows(h->d_dt + o, E, n, h->stream));
+            CK(replicate_rows(h->d_svc + o, E, n, h->stream));
+        }
     }
     CK(cudaMemcpyAsync(h->d_state + (size_t)lo * E, d, rows * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_ord + (size_t)lo * E, ord.data(), rows * E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -358,7 +403,7 @@ extern "C" int bq_destroy(bq_handle *h) {
     void *ptrs[] = {h->d_rec, h->d_color_off, h->d_ev_q, h->d_ev_p, h->d_ev_pt, h->d_q_events, h->d_q_off,
                     h->d_q_type, h->d_q_dist, h->d_q_poff, h->d_state, h->d_theta, h->d_stats,
                     h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch, h->d_order, h->d_ev_nt, h->d_ev_f,
-                    h->d_q_k, h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_F, h->d_svc};
+                    h->d_q_k, h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_F, h->d_svc, h->d_at, h->d_dt};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -424,7 +469,6 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         if (h->q_type[q] == Q_PS) h->has_ps = true;
         if (h->q_k[q] < 1) return bail(BQ_ERR_INVALID, "queue with fewer than one processor");
     }
-    if (h->has_ps) return bail(BQ_ERR_UNSUPPORTED, "PS queues are not in this build yet");
     if (const char *env = getenv("BQ_FORCE_DYNAMIC"))
         if (env[0] == '1') h->static_order = false;  // run a static-order network through the dynamic kernels
 
@@ -584,13 +628,18 @@ extern "C" int bq_get_state(bq_handle *h, int32_t lo, int32_t hi, double *d, dou
     if (!h->static_order) {
         if (!(a || s || proc || prev_byq || next_byq)) { CK(cudaStreamSynchronize(h->stream)); return BQ_OK; }
         std::vector<int> ord(n * E);
+        std::vector<double> svc;
         CK(cudaMemcpyAsync(ord.data(), h->d_ord + (size_t)lo * E, n * E * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        if (h->has_ps) {
+            svc.resize(n * E);
+            CK(cudaMemcpyAsync(svc.data(), h->d_svc + (size_t)lo * E, n * E * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
         CK(cudaStreamSynchronize(h->stream));
         const HostNet hn = h->net();
         for (size_t c = 0; c < n; ++c)
             host_derive(&hn, dd + c * E, &ord[c * E], a ? a + c * E : nullptr, s ? s + c * E : nullptr,
                         proc ? proc + c * E : nullptr, prev_byq ? prev_byq + c * E : nullptr,
-                        next_byq ? next_byq + c * E : nullptr);
+                        next_byq ? next_byq + c * E : nullptr, h->has_ps ? &svc[c * E] : nullptr, h->ord0.data());
         return BQ_OK;
     }
     CK(cudaStreamSynchronize(h->stream));

@@ -17,9 +17,9 @@ using namespace bq;
 struct Emul {
     int E, Q, P;
     std::vector<int> q_type, q_k, q_dist, q_poff, q_off;
-    std::vector<int> qid, prev_byt, next_byt, ev_f, ord, pos, dord, dpos;
+    std::vector<int> qid, prev_byt, next_byt, ev_f, ord, ord0, pos, dord, dpos;
     std::vector<uint8_t> obs_a, obs_d;
-    std::vector<double> d, F, svc, theta;
+    std::vector<double> d, F, svc, at, dt, theta;
     std::vector<QConst> qc;
     int EF;
     DynArgs A;
@@ -39,7 +39,7 @@ struct Emul {
         A.q_off = q_off.data(); A.q_type = q_type.data(); A.q_k = q_k.data(); A.q_dist = q_dist.data();
         A.q_poff = q_poff.data();
         A.state = d.data(); A.ord = ord.data(); A.pos = pos.data(); A.F = F.data();
-        A.dord = dord.data(); A.dpos = dpos.data(); A.svc = svc.data();
+        A.dord = dord.data(); A.dpos = dpos.data(); A.svc = svc.data(); A.at = at.data(); A.dt = dt.data();
         A.theta = theta.data();
         c.bind(A, 0, qc.data());
     }
@@ -61,13 +61,14 @@ void *bqe_create(int E, int Q, int P, const int *q_type, const int *q_k, const i
     m->q_off.assign(Q + 1, 0);
     for (int e = 0; e < E; ++e) m->q_off[qid[e] + 1]++;
     for (int q = 0; q < Q; ++q) m->q_off[q + 1] += m->q_off[q];
-    m->ord.assign(E, -1); m->pos.assign(E, -1); m->dord.assign(E, -1); m->dpos.assign(E, -1); m->svc.assign(E, 0.0);
+    m->ord.assign(E, -1); m->pos.assign(E, -1); m->dord.assign(E, -1); m->dpos.assign(E, -1); m->svc.assign(E, 0.0); m->at.assign(E, 0.0); m->dt.assign(E, 0.0);
     for (int q = 0; q < Q; ++q) {
         int p = m->q_off[q];
         for (int e = 0; e < E; ++e)
             if (qid[e] == q && prev_byq[e] < 0)
                 for (int x = e; x >= 0; x = next_byq[x]) m->ord[p++] = x;
     }
+    m->ord0 = m->ord;
     m->ev_f.assign(E, -1);
     m->EF = 0;
     for (int q = 0; q < Q; ++q)
@@ -76,7 +77,8 @@ void *bqe_create(int E, int Q, int P, const int *q_type, const int *q_k, const i
     m->F.assign(m->EF + 1, 0.0);
     m->qc.resize(Q);
     HostNet hn{E, Q, m->q_type.data(), m->q_k.data(), m->q_off.data(), m->ev_f.data(), m->prev_byt.data()};
-    host_rebuild(&hn, m->d.data(), m->ord.data(), m->pos.data(), m->F.data(), false);
+    HostPs ps{m->at.data(), m->dt.data(), m->svc.data(), m->dord.data(), m->dpos.data()};
+    host_rebuild(&hn, m->d.data(), m->ord.data(), m->pos.data(), m->F.data(), false, &ps);
     m->refresh_qc();
     m->bind();
     m->evals = m->steps = 0;
@@ -150,20 +152,31 @@ void bqe_get(void *h, double *d, int *ord, double *F, double *svc) {
 void bqe_derive(void *h, double *a, double *s, int32_t *proc, int32_t *prev_byq, int32_t *next_byq) {
     Emul *m = (Emul *)h;
     HostNet hn{m->E, m->Q, m->q_type.data(), m->q_k.data(), m->q_off.data(), m->ev_f.data(), m->prev_byt.data()};
-    host_derive(&hn, m->d.data(), m->ord.data(), a, s, proc, prev_byq, next_byq);
+    host_derive(&hn, m->d.data(), m->ord.data(), a, s, proc, prev_byq, next_byq, m->svc.data(), m->ord0.data());
 }
 
 // consistency of the incrementally maintained arrays with a from-scratch rebuild: 0 = consistent
 int bqe_check(void *h) {
     Emul *m = (Emul *)h;
-    std::vector<int> ord(m->ord), pos(m->E);
-    std::vector<double> F(m->EF + 1, 0.0);
+    std::vector<int> ord(m->ord), pos(m->E), dord(m->E, -1), dpos(m->E, -1);
+    std::vector<double> F(m->EF + 1, 0.0), at(m->E, 0.0), dt(m->E, 0.0), svc(m->E, 0.0);
     HostNet hn{m->E, m->Q, m->q_type.data(), m->q_k.data(), m->q_off.data(), m->ev_f.data(), m->prev_byt.data()};
-    host_rebuild(&hn, m->d.data(), ord.data(), pos.data(), F.data(), false);
+    HostPs ps{at.data(), dt.data(), svc.data(), dord.data(), dpos.data()};
+    host_rebuild(&hn, m->d.data(), ord.data(), pos.data(), F.data(), false, &ps);
     for (int e = 0; e < m->E; ++e)
         if (pos[e] != m->pos[e]) return 1;
     for (int i = 0; i < m->EF; ++i)
         if (F[i] != m->F[i]) return 2;
+    for (int q = 0; q < m->Q; ++q) {
+        if (m->q_type[q] != Q_PS) continue;
+        for (int p = m->q_off[q]; p < m->q_off[q + 1]; ++p) {
+            if (at[p] != m->at[p]) return 4;
+            if (dt[p] != m->dt[p]) return 5;
+            if (dt[p] != m->d[m->dord[p]] || m->dpos[m->dord[p]] != p) return 6;
+            const int i = m->ord[p];
+            if (fabs(svc[i] - m->svc[i]) > 1e-9 * fmax(1.0, fabs(svc[i]))) return 7;
+        }
+    }
     // every non-delay queue must be sorted by arrival
     for (int q = 0; q < m->Q; ++q) {
         if (m->q_type[q] == Q_DELAY) continue;

@@ -10,7 +10,7 @@ from bayes_qnet_b200.arrivals import Arrivals
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 COND_NETS = ["mm1", "qnet3", "delay", "lng1", "mm3", "lnk", "psdelay"]
 STATIC_NETS = ["mm1", "qnet3", "delay", "lng1"]  # single-server FIFO + delay stations: queue order is static
-DYNAMIC_NETS = ["mm3", "lnk"]  # multi-server FIFO (k = 3, 4): per-chain queue order
+DYNAMIC_NETS = ["mm3", "lnk", "psdelay"]  # multi-server FIFO (k = 3, 4) and processor sharing: per-chain order
 
 QNET3 = """
 states:
@@ -84,3 +84,53 @@ def synthetic(yaml_text, ntasks, pct, seed, theta=None):
     sub = smp.subset_by_task(pct)
     ini = net.gibbs_initialize(sub)
     return net, smp, sub, ini
+
+
+# networks without a reference fixture, checked against the oracle only: every pairing of disciplines
+MIXED = {
+    "ps_ln_to_gg3": """
+states:
+  - {name: INITIAL, queues: [INITIAL], successors: [A], initial: TRUE}
+  - {name: A, queues: [QA], successors: [B]}
+  - {name: B, queues: [QB]}
+queues:
+  - { name: INITIAL, service: [M, 1.0] }
+  - { name: QA, type: PS, service: [LN, -1.0, 0.8] }
+  - { name: QB, type: GGk, processors: 3, service: [G, 2.0, 0.6] }
+""",
+    "gg2_to_ps_to_ps": """
+states:
+  - {name: INITIAL, queues: [INITIAL], successors: [A], initial: TRUE}
+  - {name: A, queues: [QA], successors: [B]}
+  - {name: B, queues: [QB], successors: [C]}
+  - {name: C, queues: [QC]}
+queues:
+  - { name: INITIAL, service: [M, 1.0] }
+  - { name: QA, type: GGk, processors: 2, service: [M, 1.2] }
+  - { name: QB, type: PS, service: [G, 1.5, 0.3] }
+  - { name: QC, type: PS, service: [M, 0.6] }
+""",
+    "delay_gg1_gg4": """
+states:
+  - {name: INITIAL, queues: [INITIAL], successors: [A], initial: TRUE}
+  - {name: A, queues: [QA1, QA2], successors: [B]}
+  - {name: B, queues: [QB], successors: [C]}
+  - {name: C, queues: [QC]}
+queues:
+  - { name: INITIAL, service: [M, 0.5] }
+  - { name: QA1, type: DELAY, service: [LN, 0.0, 0.5] }
+  - { name: QA2, service: [M, 0.6] }
+  - { name: QB, type: GGk, processors: 4, service: [LN, 0.3, 0.7] }
+  - { name: QC, service: [G, 3.0, 0.1] }
+""",
+}
+
+
+def mixed(name, ntasks=80, pct=0.25, seed=21):
+    from bayes_qnet_b200 import qnet
+    old = qnet.get_initializer()
+    qnet.set_initialization_type("PS" if "PS" in MIXED[name] else "DFN2")
+    try:
+        return synthetic(MIXED[name], ntasks, pct, seed)
+    finally:
+        qnet.set_initialization_type(old)

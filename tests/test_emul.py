@@ -10,7 +10,7 @@ import helpers
 TOL = 1e-9
 
 
-@pytest.mark.parametrize("name", helpers.STATIC_NETS + helpers.DYNAMIC_NETS)
+@pytest.mark.parametrize("name", helpers.COND_NETS)
 def test_emulated_logcond_matches_reference_vectors(name):
     g = helpers.golden("cond_" + name)
     total = 0
@@ -27,7 +27,7 @@ def test_emulated_logcond_matches_reference_vectors(name):
     assert total > 200
 
 
-@pytest.mark.parametrize("name", helpers.STATIC_NETS + helpers.DYNAMIC_NETS)
+@pytest.mark.parametrize("name", helpers.COND_NETS)
 def test_emulated_sweeps_match_oracle(name):
     """Same stream, same scan order: identical trajectories, and the incrementally maintained queue order and
     free-time vectors stay consistent with a from-scratch rebuild after every sweep."""
@@ -45,3 +45,31 @@ def test_emulated_sweeps_match_oracle(name):
     assert helpers.relerr(dv["s"], oc.s).max() < TOL
     assert numpy.array_equal(dv["proc"], oc.proc)
     assert numpy.array_equal(dv["next_byq"], oc.next_byq) and numpy.array_equal(dv["prev_byq"], oc.prev_byq)
+
+
+@pytest.mark.parametrize("name", sorted(helpers.MIXED))
+def test_emulated_mixed_networks_match_oracle(name):
+    """Every pairing of disciplines (PS with LogNormal / Gamma service next to multi-server FIFO, PS -> PS,
+    delay stations, parallel queues): conditional on random grids and whole sweeps against the oracle."""
+    net, smp, sub, ini = helpers.mixed(name)
+    oc = helpers.oracle_chain(net, ini)
+    ec = emul_helper.EmulChain(net, ini)
+    assert helpers.relerr(ec.derive()["s"], oc.s).max() < 1e-12
+    order = oc.eligible()
+    rs = numpy.random.RandomState(5)
+    for sweep in range(4):
+        for e in rs.choice(order, size=25, replace=False):
+            e1 = oc.next_byt[e]
+            hi = oc.d[e1] if e1 >= 0 else oc.d[e] + 3.0
+            xs = numpy.concatenate((rs.uniform(oc.a[e] - 0.2, hi + 0.2, size=6), [oc.d[e]]))
+            v, r = ec.logcond(int(e), xs), oc.logcond(int(e), xs)
+            assert numpy.array_equal(numpy.isfinite(v), numpy.isfinite(r)), (name, e, xs, v, r)
+            m = numpy.isfinite(r)
+            assert helpers.relerr(v[m], r[m]).max() < TOL, (name, e, xs, v, r)
+        oc.slice_sweep(order, 99, 1, sweep)
+        ec.slice_sweep(order, 99, 1, sweep)
+        assert ec.check() == 0
+        assert helpers.relerr(ec.d, oc.d).max() < TOL
+    dv = ec.derive()
+    assert helpers.relerr(dv["s"], oc.s).max() < TOL
+    assert numpy.array_equal(dv["next_byq"], oc.next_byq)

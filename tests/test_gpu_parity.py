@@ -225,7 +225,7 @@ def test_full_size_invariants_config2():
         assert len(set(d_all[:, order[0]].tolist())) == 8
 
 
-@pytest.mark.parametrize("name", ["mm1", "qnet3", "lng1"])
+@pytest.mark.parametrize("name", ["mm1", "qnet3", "lng1", "mm3", "psdelay"])
 def test_posterior_agrees_with_long_reference_runs(name):
     """estimation.bayes from the same initial state: posterior means of the service parameters and of the
     per-queue mean waiting time vs the reference's own long runs (tests/golden/post_*.npz), within 4 combined
@@ -253,7 +253,7 @@ def test_posterior_agrees_with_long_reference_runs(name):
 
 
 @pytest.mark.parametrize("width", ["8", "16", "32"])
-@pytest.mark.parametrize("name", ["qnet3", "lng1", "mm3", "lnk"])
+@pytest.mark.parametrize("name", ["qnet3", "lng1", "mm3", "lnk", "psdelay"])
 def test_dynamic_kernel_group_widths(name, width, monkeypatch):
     """The dynamic-order kernel (per-chain queue order, free-time vectors) with W = 8 / 16 / 32 lanes per chain:
     the speculative candidates of a group reproduce the sequential slice sampler, so every width walks the
@@ -304,3 +304,33 @@ def test_dynamic_set_state_and_sharding():
         assert numpy.array_equal(f3["s"][0], full["s"][2]) and numpy.array_equal(f3["s"][1], full["s"][2])
         eng.sweep(2, "SLICE", "NONE")
         assert numpy.all(eng.state(full=True)["s"] >= 0) and numpy.all(numpy.isfinite(eng.log_prob()))
+
+
+@pytest.mark.parametrize("name", sorted(helpers.MIXED))
+def test_mixed_disciplines_match_oracle(name):
+    """PS with LogNormal / Gamma service, PS -> PS, multi-server FIFO next to PS, delay stations in parallel with
+    FIFO queues: conditional, sweeps with STEM updates, and the derived state against the oracle."""
+    net, smp, sub, ini = helpers.mixed(name)
+    with GibbsEngine(net, ini, n_chains=3, seed=2718) as eng:
+        off, order = eng.schedule()
+        oc = helpers.oracle_chain(net, ini)
+        rs = numpy.random.RandomState(1)
+        for e in rs.choice(order, size=40, replace=False):
+            e1 = oc.next_byt[e]
+            hi = oc.d[e1] if e1 >= 0 else oc.d[e] + 3.0
+            xs = rs.uniform(oc.a[e] - 0.2, hi + 0.2, size=8)
+            v, r = eng.logcond(2, int(e), xs), oc.logcond(int(e), xs)
+            assert numpy.array_equal(numpy.isfinite(v), numpy.isfinite(r)), (name, e)
+            m = numpy.isfinite(r)
+            if m.any():
+                assert helpers.relerr(v[m], r[m]).max() < TOL, (name, e, v, r)
+        eng.sweep(4, "SLICE", "STEM", trace=True)
+        th = eng.traces()[0]
+        for s in range(4):
+            oc.slice_sweep(order, eng.seed, 2, s)
+            oc.update_params("STEM", eng.seed, 2, s)
+            assert helpers.relerr(th[s, 2], oc.theta).max() < 1e-7, (name, s, th[s, 2], oc.theta)
+        full = eng.state(2, 3, full=True)
+        assert helpers.relerr(full["d"][0], oc.d).max() < 1e-7
+        assert helpers.relerr(full["s"][0], oc.s).max() < 1e-7
+        assert numpy.array_equal(full["proc"][0], oc.proc) and numpy.array_equal(full["next_byq"][0], oc.next_byq)
