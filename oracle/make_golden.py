@@ -181,8 +181,8 @@ POST = {
     "mm1": (200, 0.5, "DFN2", 13, 1500, 4),      # BASELINE.json configs[0]
     "qnet3": (150, 0.2, "DFN2", 21, 1200, 3),
     "lng1": (100, 0.3, "DFN2", 22, 3000, 8),     # slow-mixing Gamma scale: needs long runs for a usable MCSE
-    "mm3": (100, 0.3, "DFN2", 23, 800, 2),
-    "psdelay": (80, 0.3, "PS", 24, 800, 2),
+    "mm3": (100, 0.3, "DFN2", 23, 2500, 8),       # heavily loaded 3-server queue: waits mix slowly
+    "psdelay": (80, 0.3, "PS", 24, 1500, 8),
 }
 
 
@@ -277,24 +277,32 @@ def do_cond(name):
     print("cond_%s: E=%d, %d+%d+%d events on grids" % (name, len(flat["d"]), len(out["s0_rows"]), len(out["s1_rows"]), len(rows)))
 
 
+def _post_rep(args):
+    """One replica of the reference's estimation.bayes from the common initial state (own process: the reference
+    keeps its sampler state in module globals)."""
+    name, r = args
+    ntasks, pct, init, seed, niter, nrep = POST[name]
+    net, ini = make_state(name, ntasks, pct, init, seed)
+    arrv = ini.duplicate()
+    qnetu.set_seed(1000 * seed + r)
+    w = []
+    qnet.reset_stats()
+    t0 = time.time()
+    with quiet():
+        mus, _ = estimation.bayes(net, arrv, niter, report_fn=lambda n, a, i, lp: w.append(qstats.mean_wait(a)))
+    dt = time.time() - t0
+    return numpy.array(mus), numpy.array(w), qnet.stats()["nevents"] / dt
+
+
 def do_post(name):
+    import multiprocessing
     ntasks, pct, init, seed, niter, nrep = POST[name]
     net, ini = make_state(name, ntasks, pct, init, seed)
     theta0 = list(net.parameters)
     flat, _ = flatten(ini)
-    thetas, waits, rate = [], [], []
-    for r in range(nrep):
-        net.parameters = theta0[:]
-        arrv = ini.duplicate()
-        qnetu.set_seed(1000 * seed + r)
-        w = []
-        t0 = time.time()
-        with quiet():
-            mus, _ = estimation.bayes(net, arrv, niter, report_fn=lambda n, a, i, lp: w.append(qstats.mean_wait(a)))
-        dt = time.time() - t0
-        thetas.append(numpy.array(mus))
-        waits.append(numpy.array(w))
-        rate.append(qnet.stats()["nevents"] / dt)
+    with multiprocessing.Pool(min(nrep, os.cpu_count() or 1)) as pool:
+        res = pool.map(_post_rep, [(name, r) for r in range(nrep)])
+    thetas, waits, rate = [x[0] for x in res], [x[1] for x in res], [x[2] for x in res]
     out = dict(yaml=NETS[name], theta0=numpy.array(theta0), theta=numpy.array(thetas), mean_wait=numpy.array(waits),
                ref_resamples_per_s=numpy.array(rate))
     for k, v in flat.items():
