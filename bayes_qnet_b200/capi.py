@@ -63,6 +63,7 @@ SYMBOLS = {
     "bq_synchronize": (ctypes.c_int, [_H]),
     "bq_update_params": (ctypes.c_int, [_H, ctypes.c_int32]),
     "bq_logcond": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p, ctypes.c_int32, c_f64p]),
+    "bq_mh_proposal": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p, ctypes.c_int32, c_f64p]),
     "bq_log_prob": (ctypes.c_int, [_H, c_f64p]),
     "bq_suffstats": (ctypes.c_int, [_H, c_f64p]),
     "bq_stats": (ctypes.c_int, [_H, ctypes.POINTER(BqStats)]),
@@ -73,6 +74,7 @@ SYMBOLS = {
     "bq_trace_dev": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
                                     ctypes.POINTER(ctypes.c_void_p)]),
     "bq_get_schedule": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), c_i32p, c_i32p]),
+    "bq_get_sequential_order": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), c_i32p]),
     "bq_rng_uniforms": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint32,
                                        ctypes.c_uint32, ctypes.c_int32, c_f64p]),
     "bq_kernel_info": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),

@@ -47,7 +47,7 @@
 namespace bq {
 
 struct DynArgs {
-    int E, Q, P, n_order, n_sweeps, update, flags, trace_base, n_chains, EF;
+    int E, Q, P, n_order, n_sweeps, update, flags, trace_base, n_chains, EF, mode;
     const int *order;                        // [n_order] resample-eligible events in sweep order
     const int *ev_q, *ev_pt, *ev_nt, *ev_f;  // per event: queue, prev/next by task, offset of F[e] (-1: none)
     const int *q_off;                        // [Q+1] position range of each queue inside ord
@@ -475,6 +475,85 @@ BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, int &ste
 }
 
 // ---------------------------------------------------------------------------------------------
+// MH-within-Gibbs (Qnet.gibbs_resample, qnet.pyx:337-514): the proposal is one draw (two slice steps,
+// call_sampler thin = 2, qnet.pyx:1292-1300) from h(x) = departureLik(e)(x) + arrivalLik(e')(x)
+// (queues.pyx:1239-1256, pwfun.pyx:183-202):
+//   FIFO queue:    h_dep(x) = lpdf(x - max(a_e, d_prev)) on [max(a_e, d_prev), inf)      (queues.pyx:414-430, 464-468)
+//                  h_arr(x) = lpdf(d_e' - max(x, d_prev'))  on [0, d_e']                  (queues.pyx:394-412, 458-462)
+//                  d_prev = last departure of the server the event occupies = min F
+//   delay station: h_dep(x) = lpdf(x - a_e) on [a_e, inf),  h_arr(x) = lpdf(d_e' - x) on [0, d_e']   (queues.pyx:750-756)
+//   PS has no arrivalLik (queues.pyx:1140: "use slice-only"): MH sweeps are refused for networks with PS queues.
+// ---------------------------------------------------------------------------------------------
+struct MhProp {
+    double b0, d1, dp1, Lh, Uh;
+    const QConst *c0, *c1;
+    int has1, fifo1;
+    BQ_HDF double eval(double x) const {
+        if (x < Lh || x > Uh) return BQ_NEG_INF;
+        double v = lpdf(*c0, x - b0);
+        if (has1) v += lpdf(*c1, d1 - (fifo1 ? dmax(x, dp1) : x));
+        return v;
+    }
+};
+
+BQ_HDI void mh_setup(const Chain &c, const EventCtx &ev, MhProp &pr) {
+    pr.c0 = &c.qc[ev.q0];
+    pr.c1 = pr.c0;
+    pr.b0 = ev.a_e;
+    if (ev.t0 == Q_GGK) pr.b0 = dmax(ev.a_e, c.F[BQ_LDG(&c.A->ev_f[ev.e])]);
+    pr.Lh = pr.b0;
+    pr.Uh = INFINITY;
+    pr.has1 = (ev.e1 >= 0);
+    pr.fifo1 = 0; pr.d1 = 0.0; pr.dp1 = 0.0;
+    if (pr.has1) {
+        pr.c1 = &c.qc[ev.q1];
+        pr.d1 = ev.d1;
+        pr.Uh = ev.d1;
+        if (pr.Lh < 0.0) pr.Lh = 0.0;
+        if (ev.t1 == Q_GGK) { pr.fifo1 = 1; pr.dp1 = c.F[BQ_LDG(&c.A->ev_f[ev.e1])]; }
+    }
+}
+
+// sampling._slice when a bound is infinite: stepping out with w0 = 1, doubling, m = 1024 (sampling.pyx:299-341),
+// then shrinkage.  Sequential; used for final events of MH sweeps (upper = inf).  On a collapsed bracket we keep x0
+// (the documented deviation from sampling.pyx:360-362).
+template <class G>
+BQ_HDI double slice_stepout_seq(const G &g, double x0, double lower, double upper, Rng &rng, long long &evals) {
+    double w = 1.0;
+    const double gx0 = g(x0);
+    ++evals;
+    const double logy = gx0 - (-log(1.0 - rng.uniform()));
+    if (!(logy > BQ_NEG_INF)) return x0;
+    const double u = w * rng.uniform();
+    double L = x0 - u, R = x0 + (w - u);
+    unsigned long long J = (unsigned long long)(rng.word() % 1025u);  // rk_interval(m): uniform on [0, m]
+    unsigned long long K = 1023ull - J;
+    while (J > 0) {
+        if (L <= lower) break;
+        ++evals;
+        if (g(L) <= logy) break;
+        L -= w; --J; w *= 2.0;
+    }
+    int guard = 0;
+    while (K > 0 && guard < 1100) {
+        if (R >= upper) break;
+        ++evals;
+        if (g(R) <= logy) break;
+        R += w; --K; w *= 2.0; ++guard;
+    }
+    if (L < lower) L = lower;
+    if (R > upper) R = upper;
+    for (int it = 0; it < 100000; ++it) {
+        const double x1 = L + (R - L) * rng.uniform();
+        ++evals;
+        if (g(x1) >= logy) return x1;
+        if (x1 > x0) R = x1; else L = x1;
+        if (R - L < 1e-10) return x0;
+    }
+    return x0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // commit d_e := x   (apply_departure, qnet.pyx:2166-2178 -> applyDiffList, arrivals.pyx:542-604)
 // Executed by every lane of the group with identical control flow; lane 0 stores.
 // ---------------------------------------------------------------------------------------------
@@ -637,6 +716,109 @@ __device__ void dyn_suffstats(const Chain &c, SuffStat *ss, int lane, unsigned g
 }
 
 // ---------------------------------------------------------------------------------------------
+// One step of sampling._slice with finite bounds (sampling.pyx:283-298, 344-366), by the W lanes of a group.
+// Lane l of round r evaluates candidate c = r W + l (candidate 0 is x0 itself); candidate c uses uniform number c
+// of the stream `rng`, uniform 0 draws the slice level.  A candidate's position depends only on where the earlier
+// ones fell, so the first accepted candidate in order is the outcome of the sequential loop.
+// ---------------------------------------------------------------------------------------------
+struct GroupLane {
+    int lane;
+    unsigned gmask, gshift, gbits;
+};
+
+template <int W, class G>
+__device__ __forceinline__ bool group_slice(const G &g, double x0, double lower, double upper, const Rng &rng,
+                                            const GroupLane &gl, double &xacc, long long &n_evals, long long &n_stuck) {
+    double L = lower, R = upper, logy = 0.0;
+    for (int cbase = 0;; cbase += W) {
+        const unsigned int cidx = (unsigned int)(cbase + gl.lane);
+        double ua, ub;
+        stream_pair(rng, cidx >> 1, ua, ub);
+        const double u = (cidx & 1u) ? ub : ua;
+        double myx = x0, myL = L, myR = R;
+#pragma unroll 4
+        for (int jj = (cbase == 0) ? 1 : 0; jj < W; ++jj) {
+            const double uj = __shfl_sync(gl.gmask, u, jj, W);
+            const double xj = L + (R - L) * uj;
+            if (xj > x0) R = xj; else L = xj;
+            if (gl.lane == jj) { myx = xj; myL = L; myR = R; }
+        }
+        const double gv = g(myx);
+        if (cbase == 0) {
+            const double g0 = __shfl_sync(gl.gmask, gv, 0, W);
+            double u0a, u0b;
+            stream_pair(rng, 0u, u0a, u0b);
+            logy = g0 - (-log(1.0 - u0a));  // rk_exponential = -log(1 - U)   (cdist.c:107-110)
+            if (!(logy > BQ_NEG_INF)) { n_stuck += 1; n_evals += 1; return false; }  // sampling.pyx:289-291
+        }
+        const bool cand = (cidx != 0u);
+        const bool ok = cand && (gv >= logy);
+        const bool dead = cand && !ok && (myR - myL < 1e-10);  // sampling.pyx:360-362 (we keep x0)
+        const unsigned okm = (__ballot_sync(gl.gmask, ok) >> gl.gshift) & gl.gbits;
+        const unsigned deadm = (__ballot_sync(gl.gmask, dead) >> gl.gshift) & gl.gbits;
+        const int fo = okm ? (__ffs(okm) - 1) : 64, fd = deadm ? (__ffs(deadm) - 1) : 64;
+        if (fo < fd) {
+            xacc = __shfl_sync(gl.gmask, myx, fo, W);
+            n_evals += cbase + fo + 1;
+            return true;
+        }
+        if (fd < 64) { n_stuck += 1; n_evals += cbase + fd + 1; return false; }
+        if (cbase + W >= BQ_SLICE_MAX_ITERS) { n_stuck += 1; n_evals += cbase + W; return false; }
+    }
+}
+
+// One MH-within-Gibbs update of d_e (gibbs_resample_pair / gibbs_resample_final, qnet.pyx:382-498).
+// Streams of (chain, sweep, event): TAG_MH and TAG_MH2 feed the two slice steps on the proposal, TAG_MH_AUX holds the
+// accept uniform (number 0) and the re-initialisation draws (numbers 1..25).
+template <int W, int KMAX>
+__device__ void mh_update(const Chain &c, const EventCtx &ev, const DynArgs &A, unsigned long long gchain,
+                          unsigned int gsw, const GroupLane &gl, long long &n_ev, long long &n_evals, long long &n_stuck,
+                          long long &n_reject, int &steps) {
+    const bool final_evt = (ev.e1 < 0);
+    if (final_evt && (A.flags & FLAG_NO_FINAL)) return;  // sample_final = False (qnet.pyx:361)
+    MhProp pr;
+    mh_setup(c, ev, pr);
+    if (pr.Uh - pr.Lh < 1e-10) return;                      // qnet.pyx:385, 440: don't sample small intervals
+    if (!final_evt && ev.d1 - ev.a_e < 1e-10) return;
+    Rng aux;
+    aux.init(A.seed, gchain, gsw, (unsigned int)ev.e, TAG_MH_AUX);
+    const double u_acc = aux.uniform();
+    (void)aux.uniform();  // the spare of block 0 is not used: re-initialisation draws start at block 1
+    const double h0 = pr.eval(ev.x0);
+    double x_init = ev.x0;
+    if (!(h0 > BQ_NEG_INF)) {  // qnet.pyx:389-397, 444-451
+        int tries = 0;
+        for (; tries < 25; ++tries) {
+            const double u = aux.uniform();
+            x_init = final_evt ? pr.b0 + (-log(1.0 - u)) : ev.a_e + (ev.d1 - ev.a_e) * u;
+            if (pr.eval(x_init) > BQ_NEG_INF) break;
+        }
+        if (tries >= 25) return;
+    }
+    double x_new = x_init;
+    for (int step = 0; step < 2; ++step) {
+        Rng rng;
+        rng.init(A.seed, gchain, gsw, (unsigned int)ev.e, step == 0 ? TAG_MH : TAG_MH2);
+        if (final_evt) {
+            x_new = slice_stepout_seq([&](double x) { return pr.eval(x); }, x_new, pr.Lh, pr.Uh, rng, n_evals);
+        } else {
+            double xa = x_new;
+            if (group_slice<W>([&](double x) { return pr.eval(x); }, x_new, pr.Lh, pr.Uh, rng, gl, xa, n_evals, n_stuck))
+                x_new = xa;
+        }
+    }
+    n_ev += 1;
+    // ratio = exp(h(d_e) - h(d_new)) * prod over the diff lists of exp(lpdf(s_new) - lpdf(s_old))   (qnet.pyx:425-431)
+    const double g_new = dyn_logcond<KMAX>(c, ev, x_new, steps);
+    const double ratio = exp(h0 - pr.eval(x_new) + g_new);
+    if (u_acc < ratio) {
+        if (x_new != ev.x0) dyn_commit<W, KMAX>(c, ev, x_new, gl.lane, gl.gmask);
+    } else {
+        n_reject += 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the sweep kernel
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t dyn_group_smem(int Q, int P) {
@@ -654,6 +836,7 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
     const unsigned gshift = (threadIdx.x & 31) & ~(W - 1);
     const unsigned gbits = (W == 32) ? 0xffffffffu : ((1u << W) - 1u);
     const unsigned gmask = gbits << gshift;
+    const GroupLane gl = {lane, gmask, gshift, gbits};
     unsigned char *base = smem_raw + (size_t)gib * dyn_group_smem(A.Q, A.P);
     QConst *qc = reinterpret_cast<QConst *>(base);
     SuffStat *ss = reinterpret_cast<SuffStat *>(qc + A.Q);
@@ -671,7 +854,7 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
     __syncwarp(gmask);
 
     const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain);
-    long long n_ev = 0, n_evals = 0, n_stuck = 0, n_pevals = 0, n_steps = 0;
+    long long n_ev = 0, n_evals = 0, n_stuck = 0, n_pevals = 0, n_steps = 0, n_reject = 0;
     double tmax = 0.0;
 
     for (int sw = 0; sw < A.n_sweeps; ++sw) {
@@ -685,51 +868,21 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
         for (int idx = 0; idx < n_order; ++idx) {
             EventCtx ev;
             event_load(c, __ldg(&A.order[idx]), ev);
+            int steps = 0;
+            if (A.mode == MODE_MH) {
+                mh_update<W, KMAX>(c, ev, A, gchain, gsw, gl, n_ev, n_evals, n_stuck, n_reject, steps);
+                n_steps += steps;
+                __syncwarp(gmask);
+                continue;
+            }
             const double lower = ev.a_e;
             const double upper = (ev.e1 >= 0) ? fmin(ev.d1, tmax) : tmax;  // qnet.pyx:698-701, 732-734
             Rng rng;
             rng.init(A.seed, gchain, gsw, (unsigned int)ev.e, TAG_SLICE);
-            double L = lower, R = upper, logy = 0.0, xacc = ev.x0;
-            bool accepted = false;
-            int steps = 0;
             n_ev += 1;
-            for (int cbase = 0;; cbase += W) {
-                // candidate cbase + lane (candidate 0 is x0 itself); uniform number c of the event's stream
-                const unsigned int cidx = (unsigned int)(cbase + lane);
-                double ua, ub;
-                stream_pair(rng, cidx >> 1, ua, ub);
-                const double u = (cidx & 1u) ? ub : ua;
-                double myx = ev.x0, myL = L, myR = R;
-#pragma unroll 4
-                for (int jj = (cbase == 0) ? 1 : 0; jj < W; ++jj) {
-                    const double uj = __shfl_sync(gmask, u, jj, W);
-                    const double xj = L + (R - L) * uj;
-                    if (xj > ev.x0) R = xj; else L = xj;
-                    if (lane == jj) { myx = xj; myL = L; myR = R; }
-                }
-                const double g = dyn_logcond<KMAX>(c, ev, myx, steps);
-                if (cbase == 0) {
-                    const double g0 = __shfl_sync(gmask, g, 0, W);
-                    double u0a, u0b;
-                    stream_pair(rng, 0u, u0a, u0b);
-                    logy = g0 - (-log(1.0 - u0a));  // rk_exponential = -log(1 - U)   (cdist.c:107-110)
-                    if (!(logy > BQ_NEG_INF)) { n_stuck += 1; n_evals += 1; break; }  // sampling.pyx:289-291
-                }
-                const bool cand = (cidx != 0u);
-                const bool ok = cand && (g >= logy);
-                const bool dead = cand && !ok && (myR - myL < 1e-10);  // sampling.pyx:360-362 (we keep x0)
-                const unsigned okm = (__ballot_sync(gmask, ok) >> gshift) & gbits;
-                const unsigned deadm = (__ballot_sync(gmask, dead) >> gshift) & gbits;
-                const int fo = okm ? (__ffs(okm) - 1) : 64, fd = deadm ? (__ffs(deadm) - 1) : 64;
-                if (fo < fd) {
-                    xacc = __shfl_sync(gmask, myx, fo, W);
-                    accepted = true;
-                    n_evals += cbase + fo + 1;
-                    break;
-                }
-                if (fd < 64) { n_stuck += 1; n_evals += cbase + fd + 1; break; }
-                if (cbase + W >= BQ_SLICE_MAX_ITERS) { n_stuck += 1; n_evals += cbase + W; break; }
-            }
+            double xacc = ev.x0;
+            const bool accepted = group_slice<W>([&](double x) { return dyn_logcond<KMAX>(c, ev, x, steps); }, ev.x0, lower,
+                                                 upper, rng, gl, xacc, n_evals, n_stuck);
             n_steps += steps;
             if (accepted && xacc != ev.x0) dyn_commit<W, KMAX>(c, ev, xacc, lane, gmask);
             __syncwarp(gmask);
@@ -769,15 +922,16 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
     n_pevals = (long long)group_sum<W>((double)n_pevals, gmask);
     if (lane == 0) {
         long long *st = A.stats + (size_t)chain * BQ_NSTAT;
-        st[0] += n_ev; st[1] += n_evals; st[2] += n_pevals; st[3] += n_stuck; st[5] += n_steps;
+        st[0] += n_ev; st[1] += n_evals; st[2] += n_pevals; st[3] += n_stuck; st[4] += n_reject; st[5] += n_steps;
     }
 }
 
 // ---- parity / reporting kernels ---------------------------------------------------------------
 
 // out[j] = inner_dfun(x[j]) - lik0 for event e of one chain (qnet.pyx:1340-1357); one warp
+// what = 1: the MH proposal log-density h(x[j]) instead (queues.pyx:1239-1256)
 template <int KMAX>
-__global__ void logcond_dynamic_kernel(const DynArgs A, int chain, int e, const double *x, int n, double *out) {
+__global__ void logcond_dynamic_kernel(const DynArgs A, int chain, int e, const double *x, int n, double *out, int what) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     QConst *qc = reinterpret_cast<QConst *>(smem_raw);
     const double *th = A.theta + (size_t)chain * A.P;
@@ -791,6 +945,12 @@ __global__ void logcond_dynamic_kernel(const DynArgs A, int chain, int e, const 
     EventCtx ev;
     event_load(c, e, ev);
     int steps = 0;
+    if (what == 1) {
+        MhProp pr;
+        mh_setup(c, ev, pr);
+        for (int j = threadIdx.x; j < n; j += blockDim.x) out[j] = pr.eval(x[j]);
+        return;
+    }
     const double g0 = dyn_logcond<KMAX>(c, ev, ev.x0, steps);
     for (int j = threadIdx.x; j < n; j += blockDim.x) out[j] = dyn_logcond<KMAX>(c, ev, x[j], steps) - g0;
 }
@@ -818,6 +978,29 @@ __global__ void __launch_bounds__(128) report_dynamic_kernel(const DynArgs A, do
     if (ss_out)
         for (int i = lane; i < A.Q * 8; i += 32)
             ss_out[(size_t)chain * A.Q * 8 + i] = reinterpret_cast<double *>(ss)[i];
+}
+
+// Free-time vectors of every FIFO queue from the departure times and the current queue order; one thread per
+// (chain, queue), sequential along the queue (queues.pyx:654-680).  Used when a static-order handle switches to the
+// dynamic-order kernels (MH sweeps) after slice sweeps have moved the departure times.
+template <int KMAX>
+__global__ void rebuild_free_times_kernel(const DynArgs A) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)A.n_chains * A.Q) return;
+    const int chain = (int)(t / A.Q), q = (int)(t % A.Q);
+    if (A.q_type[q] != Q_GGK) return;
+    const int k = A.q_k[q];
+    const double *d = A.state + (size_t)chain * A.E;
+    const int *ord = A.ord + (size_t)chain * A.E;
+    double *F = A.F + (size_t)chain * A.EF;
+    FreeVec<KMAX> M;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) M.v[j] = (j < k) ? 0.0 : INFINITY;
+    for (int p = A.q_off[q]; p < A.q_off[q + 1]; ++p) {
+        const int i = ord[p];
+        M.store(F + A.ev_f[i], k);
+        M.replace_min(d[i]);
+    }
 }
 
 }  // namespace bq

@@ -71,6 +71,9 @@ struct bq_handle {
     bool has_ps = false;
     int EF = 0, kmax = 1, dyn_w = 32, dyn_threads = 128;
     std::vector<int> ev_f, q_off, ord0;  // F offset per event, queue ranges, initial order
+    std::vector<int> dyn_order;          // sweep order of the dynamic-order kernels
+    bool dyn_ready = false;              // dynamic arrays allocated
+    bool dyn_stale = false;              // ... but the static kernel has moved d since they were built
     int *d_order = nullptr, *d_ev_nt = nullptr, *d_ev_f = nullptr, *d_q_k = nullptr;
     int *d_ord = nullptr, *d_pos = nullptr, *d_dord = nullptr, *d_dpos = nullptr;
     double *d_F = nullptr, *d_svc = nullptr, *d_at = nullptr, *d_dt = nullptr;
@@ -238,7 +241,7 @@ static cudaError_t replicate_rows(T *base, size_t row, size_t C, cudaStream_t st
 static void fill_dyn_args(const bq_handle *h, DynArgs &A) {
     memset(&A, 0, sizeof(A));
     A.E = h->E; A.Q = h->Q; A.P = h->P; A.n_chains = h->C; A.EF = h->EF;
-    A.n_order = (int)h->order.size();
+    A.n_order = (int)h->dyn_order.size();
     A.order = h->d_order;
     A.ev_q = h->d_ev_q; A.ev_pt = h->d_ev_pt; A.ev_nt = h->d_ev_nt; A.ev_f = h->d_ev_f;
     A.q_off = h->d_q_off; A.q_type = h->d_q_type; A.q_k = h->d_q_k; A.q_dist = h->d_q_dist; A.q_poff = h->d_q_poff;
@@ -249,12 +252,12 @@ static void fill_dyn_args(const bq_handle *h, DynArgs &A) {
     A.seed = h->seed; A.chain_offset = h->chain_offset; A.sweep_base = h->sweep_counter;
 }
 
-// per-handle tables of the dynamic kernels + the derived arrays of the initial state, replicated to all chains
-static int setup_dynamic(bq_handle *h, const double *d0) {
+// initial queue orders from the caller's by-queue links, and the sequential scan order of the dynamic-order kernels:
+// queue after queue, each in its initial arrival order (any fixed scan is a valid Gibbs sweep)
+static int build_sequential_order(bq_handle *h) {
     const int E = h->E, Q = h->Q;
-    // initial queue orders from the caller's by-queue links
     h->ord0.assign(E, -1);
-    std::vector<int> head(Q, -1), cnt(Q, 0);
+    std::vector<int> head(Q, -1);
     for (int e = 0; e < E; ++e)
         if (h->prev_byq[e] < 0) {
             if (head[h->qid[e]] >= 0) return fail(BQ_ERR_INVALID, "a queue has two head events (prev_byq < 0)");
@@ -268,6 +271,15 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
         }
         if (p != h->q_off[q + 1]) return fail(BQ_ERR_INVALID, "by-queue links do not cover the queue");
     }
+    h->dyn_order.clear();
+    for (int p = 0; p < E; ++p)
+        if (eligible(h, h->ord0[p])) h->dyn_order.push_back(h->ord0[p]);
+    return BQ_OK;
+}
+
+// per-handle tables of the dynamic kernels + the derived arrays of the initial state, replicated to all chains
+static int setup_dynamic(bq_handle *h, const double *d0) {
+    const int E = h->E, Q = h->Q;
     h->ev_f.assign(E, -1);
     h->EF = 0; h->kmax = 1;
     for (int q = 0; q < Q; ++q)
@@ -284,15 +296,14 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
         HostPs ps{at0.data(), dt0.data(), svc0.data(), dord0.data(), dpos0.data()};
         host_rebuild(&hn, d0, h->ord0.data(), pos0.data(), F0.data(), false, h->has_ps ? &ps : nullptr);
     }
-    // sweep order: queue after queue, each in its initial arrival order (any fixed scan is a valid Gibbs sweep)
-    h->order.clear();
-    for (int p = 0; p < E; ++p)
-        if (eligible(h, h->ord0[p])) h->order.push_back(h->ord0[p]);
-    h->color_off.resize(h->order.size() + 1);
-    for (size_t i = 0; i <= h->order.size(); ++i) h->color_off[i] = (int)i;
+    if (!h->static_order) {  // the handle's schedule is the sequential scan: one event per class
+        h->order = h->dyn_order;
+        h->color_off.resize(h->order.size() + 1);
+        for (size_t i = 0; i <= h->order.size(); ++i) h->color_off[i] = (int)i;
+    }
 
     const size_t C = h->C;
-    CK(upload(&h->d_order, h->order.data(), h->order.size()));
+    CK(upload(&h->d_order, h->dyn_order.data(), h->dyn_order.size()));
     CK(upload(&h->d_ev_nt, h->next_byt.data(), E));
     CK(upload(&h->d_ev_f, h->ev_f.data(), E));
     CK(upload(&h->d_q_k, h->q_k.data(), Q));
@@ -334,6 +345,8 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
         int t = atoi(env);
         if (t == 32 || t == 64 || t == 128) h->dyn_threads = t;
     }
+    h->dyn_ready = true;
+    h->dyn_stale = false;
     return BQ_OK;
 }
 
@@ -531,6 +544,7 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         CKB(cudaMemcpy(h->d_theta, th.data(), th.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
 
+    if (int rc = build_sequential_order(h)) { std::string msg = g_err; bq_destroy(h); return fail(rc, msg); }
     if (!h->static_order)
         if (int rc = setup_dynamic(h, a->d)) { std::string msg = g_err; bq_destroy(h); return fail(rc, msg); }
 
@@ -594,6 +608,7 @@ extern "C" int bq_set_state(bq_handle *h, int32_t lo, int32_t hi, const double *
     if (int r = check_range(h, lo, hi)) return r;
     CK(cudaSetDevice(h->device));
     if (!h->static_order) return dynamic_set_rows(h, lo, hi, d, false);
+    h->dyn_stale = true;
     CK(cudaMemcpyAsync(h->d_state + (size_t)lo * h->E, d, (size_t)(hi - lo) * h->E * sizeof(double),
                        cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -605,6 +620,7 @@ extern "C" int bq_broadcast_state(bq_handle *h, const double *d) {
     if (!h || !d) return fail(BQ_ERR_INVALID, "null argument");
     CK(cudaSetDevice(h->device));
     if (!h->static_order) return dynamic_set_rows(h, 0, h->C, d, true);
+    h->dyn_stale = true;
     const size_t E = h->E, C = h->C;
     CK(cudaMemcpyAsync(h->d_state, d, E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     for (size_t have = 1; have < C; have *= 2) {
@@ -692,10 +708,35 @@ static int ensure_trace(bq_handle *h, int extra) {
     return BQ_OK;
 }
 
+// A static-order handle entering the dynamic-order kernels (MH sweeps, proposal hook): build their arrays once, and
+// refresh the free-time vectors whenever the static kernel has moved the departure times since.
+static int ensure_dynamic(bq_handle *h) {
+    if (!h->dyn_ready) {
+        std::vector<double> d0(h->E);
+        CK(cudaMemcpyAsync(d0.data(), h->d_state, h->E * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (int rc = setup_dynamic(h, d0.data())) return rc;
+        h->dyn_stale = true;
+    }
+    if (h->dyn_stale) {
+        DynArgs D;
+        fill_dyn_args(h, D);
+        const long long n = (long long)h->C * h->Q;
+        if (h->kmax <= 4) rebuild_free_times_kernel<4><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(D);
+        else rebuild_free_times_kernel<8><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(D);
+        CK(cudaGetLastError());
+        h->n_launches += 1;
+        h->dyn_stale = false;
+    }
+    return BQ_OK;
+}
+
 static int launch_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t update, uint32_t flags) {
     if (!h) return fail(BQ_ERR_INVALID, "null handle");
     if (n_sweeps < 0) return fail(BQ_ERR_INVALID, "n_sweeps < 0");
-    if (mode != BQ_MODE_SLICE) return fail(BQ_ERR_UNSUPPORTED, "only BQ_MODE_SLICE is built yet");
+    if (mode != BQ_MODE_SLICE && mode != BQ_MODE_MH) return fail(BQ_ERR_INVALID, "bad sweep mode");
+    if (mode == BQ_MODE_MH && h->has_ps)
+        return fail(BQ_ERR_UNSUPPORTED, "MH sweeps need arrivalLik, which PS queues do not have (queues.pyx:1140): use BQ_MODE_SLICE");
     if (update < 0 || update > 2) return fail(BQ_ERR_INVALID, "bad param_update");
     if (n_sweeps == 0) return BQ_OK;
     CK(cudaSetDevice(h->device));
@@ -704,16 +745,21 @@ static int launch_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t up
     SweepArgs A;
     fill_args(h, A);
     A.n_sweeps = n_sweeps; A.update = update; A.flags = (int)flags; A.trace_base = h->trace_len;
+    const bool use_dynamic = !h->static_order || (mode == BQ_MODE_MH && !(flags & FLAG_PARAMS_ONLY));
+    if (use_dynamic && h->static_order)
+        if (int rc = ensure_dynamic(h)) return rc;
     CK(cudaEventRecord(h->ev0, h->stream));
-    if (!h->static_order) {
+    if (use_dynamic) {
         DynArgs D;
         fill_dyn_args(h, D);
-        D.n_sweeps = n_sweeps; D.update = update; D.flags = (int)flags; D.trace_base = h->trace_len;
+        D.n_sweeps = n_sweeps; D.update = update; D.flags = (int)flags; D.trace_base = h->trace_len; D.mode = mode;
         launch_dynamic(h, D);
     } else if (h->use_smem) {
+        h->dyn_stale = true;
         if (h->all_exp) sweep_static_kernel<true, true><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
         else sweep_static_kernel<true, false><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
     } else {
+        h->dyn_stale = true;
         if (h->all_exp) sweep_static_kernel<false, true><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
         else sweep_static_kernel<false, false><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
     }
@@ -758,8 +804,10 @@ extern "C" int bq_stream(bq_handle *h, void **stream) {
     return BQ_OK;
 }
 
-extern "C" int bq_logcond(bq_handle *h, int32_t chain, int32_t eid, const double *x, int32_t n, double *out) {
+static int eval_hook(bq_handle *h, int32_t chain, int32_t eid, const double *x, int32_t n, double *out, int what) {
     if (int r = check_range(h, chain, chain + 1)) return r;
+    if (what == 1 && h->has_ps)
+        return fail(BQ_ERR_UNSUPPORTED, "PS queues have no arrivalLik (queues.pyx:1140): no MH proposal");
     if (eid < 0 || eid >= h->E || n < 0) return fail(BQ_ERR_INVALID, "bad event id / n");
     if (n == 0) return BQ_OK;
     CK(cudaSetDevice(h->device));
@@ -770,12 +818,16 @@ extern "C" int bq_logcond(bq_handle *h, int32_t chain, int32_t eid, const double
         h->scratch_n = 2 * n;
     }
     CK(cudaMemcpyAsync(h->d_scratch, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (!h->static_order) {
+    if (what == 1 && h->static_order)
+        if (int rc = ensure_dynamic(h)) return rc;
+    if (!h->static_order || what == 1) {
         DynArgs D;
         fill_dyn_args(h, D);
         const size_t sm = dyn_group_smem(h->Q, h->P);
-        if (h->kmax <= 4) logcond_dynamic_kernel<4><<<1, 32, sm, h->stream>>>(D, chain, eid, h->d_scratch, n, h->d_scratch + n);
-        else logcond_dynamic_kernel<8><<<1, 32, sm, h->stream>>>(D, chain, eid, h->d_scratch, n, h->d_scratch + n);
+        if (h->kmax <= 4)
+            logcond_dynamic_kernel<4><<<1, 32, sm, h->stream>>>(D, chain, eid, h->d_scratch, n, h->d_scratch + n, what);
+        else
+            logcond_dynamic_kernel<8><<<1, 32, sm, h->stream>>>(D, chain, eid, h->d_scratch, n, h->d_scratch + n, what);
     } else {
         SweepArgs A;
         fill_args(h, A);
@@ -787,6 +839,13 @@ extern "C" int bq_logcond(bq_handle *h, int32_t chain, int32_t eid, const double
     CK(cudaMemcpyAsync(out, h->d_scratch + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return BQ_OK;
+}
+
+extern "C" int bq_logcond(bq_handle *h, int32_t chain, int32_t eid, const double *x, int32_t n, double *out) {
+    return eval_hook(h, chain, eid, x, n, out, 0);
+}
+extern "C" int bq_mh_proposal(bq_handle *h, int32_t chain, int32_t eid, const double *x, int32_t n, double *out) {
+    return eval_hook(h, chain, eid, x, n, out, 1);
 }
 
 static int run_report(bq_handle *h, double *logp_host, double *ss_host) {
@@ -895,6 +954,13 @@ extern "C" int bq_get_schedule(bq_handle *h, int32_t *n_colors, int32_t *n_eligi
     if (n_eligible) *n_eligible = (int)h->order.size();
     if (color_off) memcpy(color_off, h->color_off.data(), h->color_off.size() * sizeof(int));
     if (order) memcpy(order, h->order.data(), h->order.size() * sizeof(int));
+    return BQ_OK;
+}
+
+extern "C" int bq_get_sequential_order(bq_handle *h, int32_t *n_eligible, int32_t *order) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    if (n_eligible) *n_eligible = (int)h->dyn_order.size();
+    if (order) memcpy(order, h->dyn_order.data(), h->dyn_order.size() * sizeof(int));
     return BQ_OK;
 }
 

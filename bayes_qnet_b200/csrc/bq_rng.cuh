@@ -29,7 +29,9 @@ namespace bq {
 enum : uint32_t {
     TAG_SLICE = 1,   // hidden-time slice updates (qnet.pyx:701)
     TAG_PARAM = 2,   // service-parameter draws (qnet.pyx:882)
-    TAG_MH = 3,      // MH-within-Gibbs proposal + accept (qnet.pyx:337)
+    TAG_MH = 3,      // MH-within-Gibbs: first slice step on the proposal (qnet.pyx:337, 1292-1300)
+    TAG_MH2 = 4,     //   second slice step (thin = 2)
+    TAG_MH_AUX = 5,  //   accept uniform (number 0) and re-initialisation draws (qnet.pyx:389-397, 444-451)
     TAG_TEST = 7
 };
 

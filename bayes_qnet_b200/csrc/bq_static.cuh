@@ -25,6 +25,7 @@ namespace bq {
 #define BQ_NSTAT 8  // per-chain counters: nevents, slice_evals, param_evals, stuck, nreject, walk steps, 2 spare
 
 enum { UPD_NONE = 0, UPD_BAYES = 1, UPD_STEM = 2 };
+enum { MODE_SLICE = 0, MODE_MH = 1 };
 enum { FLAG_TMAX_PER_SWEEP = 1, FLAG_NO_FINAL = 2, FLAG_TRACE = 4, FLAG_TIGHT = 8, FLAG_PARAMS_ONLY = 1 << 16 };
 
 // Static neighbourhood of one resample-eligible event e (12 x int32 = 3 x int4, stored in schedule

@@ -175,6 +175,14 @@ class GibbsEngine(object):
                                       capi.ptr(out, capi.c_f64p)))
         return out
 
+    def mh_proposal(self, chain, row, xs):
+        """The MH proposal log-density of event `row` (queues.pair_proposal / departure_proposal, queues.pyx:1279)."""
+        xs = capi.as_f64(xs)
+        out = numpy.empty(len(xs), dtype=numpy.float64)
+        capi.check(self._L.bq_mh_proposal(self._h, int(chain), int(row), capi.ptr(xs, capi.c_f64p), len(xs),
+                                          capi.ptr(out, capi.c_f64p)))
+        return out
+
     def log_prob(self):
         out = numpy.empty(self.n_chains, dtype=numpy.float64)
         capi.check(self._L.bq_log_prob(self._h, capi.ptr(out, capi.c_f64p)))
@@ -225,6 +233,14 @@ class GibbsEngine(object):
         order = numpy.empty(ne.value, dtype=numpy.int32)
         capi.check(self._L.bq_get_schedule(self._h, None, None, capi.ptr(off, capi.c_i32p), capi.ptr(order, capi.c_i32p)))
         return off, order
+
+    def sequential_order(self):
+        """Scan order of MH sweeps (and of slice sweeps on networks with multi-server or PS queues)."""
+        ne = ctypes.c_int32()
+        capi.check(self._L.bq_get_sequential_order(self._h, ctypes.byref(ne), None))
+        order = numpy.empty(ne.value, dtype=numpy.int32)
+        capi.check(self._L.bq_get_sequential_order(self._h, None, capi.ptr(order, capi.c_i32p)))
+        return order
 
     def kernel_info(self):
         t, s, m = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()

@@ -134,6 +134,9 @@ int bq_update_params(bq_handle *h, int32_t param_update);
 /* Parity hook: GGkGibbs.inner_dfun(x) - lik0 (qnet.pyx:1340-1357) for event `eid` of chain `chain`
  * at n points. */
 int bq_logcond(bq_handle *h, int32_t chain, int32_t eid, const double *x, int32_t n, double *out);
+/* Parity hook for the MH path: the TWOS proposal log-density departureLik(e) + arrivalLik(e') at n points
+ * (queues.pair_proposal / departure_proposal, queues.pyx:1239-1283; -inf outside its support). */
+int bq_mh_proposal(bq_handle *h, int32_t chain, int32_t eid, const double *x, int32_t n, double *out);
 /* Qnet.log_prob (qnet.pyx:1032): out[n_chains] */
 int bq_log_prob(bq_handle *h, double *out);
 /* Per chain per queue sufficient statistics over events with s>0 (queues.pyx:1317):
@@ -158,8 +161,14 @@ int bq_trace_dev(bq_handle *h, double **theta_dev, double **mean_wait_dev, doubl
 int bq_get_schedule(bq_handle *h, int32_t *n_colors, int32_t *n_eligible, int32_t *color_off,
                     int32_t *order);
 
+/* The scan order of the sequential kernels (MH sweeps on any network, slice sweeps on networks with multi-server
+ * or PS queues): the resample-eligible events queue after queue, each queue in its initial arrival order.  MH
+ * visits them as Qnet.gibbs_resample does (qnet.pyx:354-368). */
+int bq_get_sequential_order(bq_handle *h, int32_t *n_eligible, int32_t *order);
+
 /* Raw counter-based RNG stream (Philox4x32-10) exactly as the kernels consume it: n uniforms in [0,1)
- * for (seed, global chain id, sweep index, event or queue id, stream tag: 1 slice, 2 parameters, 3 MH).
+ * for (seed, global chain id, sweep index, event or queue id, stream tag: 1 slice, 2 parameters, 3/4 the two slice
+ * steps of an MH proposal, 5 MH accept + re-initialisation).
  * Pure host function, needs no device.  Replaces rk_double (randomkit.c:264). */
 int bq_rng_uniforms(uint64_t seed, int64_t chain, uint32_t sweep, uint32_t id, uint32_t tag, int32_t n,
                     double *out);

@@ -17,6 +17,8 @@
  *     (queues.pyx:514-556), -inf when any new service is negative, and PS's log N terms;
  *   - one slice update, sampling._slice with finite bounds (sampling.pyx:283-298, 344-366), eligibility and
  *     bounds of Qnet.slice_resample (qnet.pyx:672, 686-702), commit = apply_departure (qnet.pyx:2166-2178);
+ *   - one MH-within-Gibbs update, Qnet.gibbs_resample_pair / _final with the TWOS proposal (qnet.pyx:337-498;
+ *     queues.pyx:394-430, 458-468, 750-756, 1239-1256);
  *   - Qnet.log_prob (qnet.pyx:1032; queues.pyx:97-117), the log-densities (distributions.pyx:59, 129-133,
  *     266-270), the sufficient statistics and the parameter updates (distributions.pyx:65-74, 92-96,
  *     142-160, 276-320; netutils.py:19-42; queues.pyx:1316-1336).
@@ -362,6 +364,131 @@ long bqo_slice_sweep(bqo_state *st, const int *order, int n_order, uint64_t seed
         if (x1 != x0) bqo_apply(st, e, x1);
     }
     return ne;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* MH-within-Gibbs sweep: Qnet.gibbs_resample (qnet.pyx:337-498)                                     */
+/* ---------------------------------------------------------------------------------------------- */
+/* departure of the previous event served by the same processor (QueueGGk.prev_by_proc, queues.pyx:619-624) */
+static double prev_by_proc_d(const bqo_state *st, int e) {
+    int p = st->prev_byq[e];
+    while (p >= 0) {
+        if (st->proc[p] == st->proc[e]) return st->d[p];
+        p = st->prev_byq[p];
+    }
+    return 0.0;
+}
+
+/* TWOS proposal (queues.pyx:1239-1256): departureLik(e) + arrivalLik(e1) on the intersection of their supports
+ * (pwfun.pyx:183-202).  GGk: queues.pyx:394-430, 458-468; DelayStation: queues.pyx:750-756.  -inf outside. */
+typedef struct { double b0, d1, dp1, L, U; int q0, q1, has1, fifo1; } mhprop;
+
+static void mh_setup(const bqo_state *st, int e, mhprop *pr) {
+    int e1 = st->next_byt[e];
+    pr->q0 = st->qid[e]; pr->q1 = -1; pr->has1 = 0; pr->fifo1 = 0; pr->d1 = 0.0; pr->dp1 = 0.0;
+    pr->b0 = st->a[e];
+    if (st->q_type[pr->q0] == Q_GGK) { double dp = prev_by_proc_d(st, e); if (dp > pr->b0) pr->b0 = dp; }
+    pr->L = pr->b0; pr->U = INFINITY;
+    if (e1 >= 0) {
+        pr->has1 = 1; pr->q1 = st->qid[e1]; pr->d1 = st->d[e1]; pr->U = st->d[e1];
+        if (pr->L < 0.0) pr->L = 0.0;
+        if (st->q_type[pr->q1] == Q_GGK) { pr->fifo1 = 1; pr->dp1 = prev_by_proc_d(st, e1); }
+    }
+}
+static double mh_eval(const bqo_state *st, const mhprop *pr, double x) {
+    double v;
+    if (x < pr->L || x > pr->U) return -INFINITY;
+    v = q_lpdf(st, pr->q0, x - pr->b0);
+    if (pr->has1) {
+        double m = x;
+        if (pr->fifo1 && pr->dp1 > m) m = pr->dp1;
+        v += q_lpdf(st, pr->q1, pr->d1 - m);
+    }
+    return v;
+}
+
+/* one step of sampling._slice on the proposal (sampling.pyx:267-366); keeps x0 on a collapsed bracket */
+static double mh_slice(const bqo_state *st, const mhprop *pr, double x0, bqo_rng *rng, long *evals) {
+    double gx0 = mh_eval(st, pr, x0), logy, L, R;
+    int it;
+    ++*evals;
+    logy = gx0 - (-log(1.0 - rng_uniform(rng)));
+    if (!(logy > -INFINITY)) return x0;
+    if (pr->U < INFINITY) { L = pr->L; R = pr->U; }
+    else {
+        double w = 1.0, u = w * rng_uniform(rng);
+        unsigned long long J, K;
+        int guard = 0;
+        L = x0 - u; R = x0 + (w - u);
+        J = (unsigned long long)(rng_word(rng) % 1025u);
+        K = 1023ull - J;
+        while (J > 0) { if (L <= pr->L) break; ++*evals; if (mh_eval(st, pr, L) <= logy) break; L -= w; --J; w *= 2.0; }
+        while (K > 0 && guard < 1100) { if (R >= pr->U) break; ++*evals; if (mh_eval(st, pr, R) <= logy) break; R += w; --K; w *= 2.0; ++guard; }
+        if (L < pr->L) L = pr->L;
+        if (R > pr->U) R = pr->U;
+    }
+    for (it = 0; it < 100000; ++it) {
+        double x1 = L + (R - L) * rng_uniform(rng);
+        ++*evals;
+        if (mh_eval(st, pr, x1) >= logy) return x1;
+        if (x1 > x0) R = x1; else L = x1;
+        if (R - L < 1e-10) return x0;
+    }
+    return x0;
+}
+
+/* Streams of (chain, sweep, event): tag 3 and 4 = the two slice steps of call_sampler(thin = 2) (qnet.pyx:1292-1300),
+ * tag 5 = accept uniform (number 0; number 1 unused) and the re-initialisation draws (numbers 2..).
+ * Returns the number of proposals made (the reference's nevents); *nreject counts rejections. */
+long bqo_mh_sweep(bqo_state *st, const int *order, int n_order, uint64_t seed, int64_t chain, uint32_t sweep,
+                  int sample_final, long *nreject, long *evals) {
+    long ne = 0, dummy = 0;
+    int i;
+    if (!evals) evals = &dummy;
+    for (i = 0; i < n_order; ++i) {
+        int e = order[i], e1 = st->next_byt[e], fin = (e1 < 0), step;
+        mhprop pr;
+        bqo_rng aux, rng;
+        double u_acc, h0, x_init, x_new, g_new, ratio;
+        if (!bqo_eligible(st, e)) continue;
+        if (fin && !sample_final) continue;
+        mh_setup(st, e, &pr);
+        if (pr.U - pr.L < 1e-10) continue;                       /* qnet.pyx:385, 440 */
+        if (!fin && st->d[e1] - st->a[e] < 1e-10) continue;
+        rng_init(&aux, seed, (uint64_t)chain, sweep, (uint32_t)e, 5u);
+        u_acc = rng_uniform(&aux);
+        (void)rng_uniform(&aux);
+        h0 = mh_eval(st, &pr, st->d[e]);
+        x_init = st->d[e];
+        if (!(h0 > -INFINITY)) {                                  /* qnet.pyx:389-397, 444-451 */
+            int tries = 0;
+            for (; tries < 25; ++tries) {
+                double u = rng_uniform(&aux);
+                x_init = fin ? pr.b0 + (-log(1.0 - u)) : st->a[e] + (st->d[e1] - st->a[e]) * u;
+                if (mh_eval(st, &pr, x_init) > -INFINITY) break;
+            }
+            if (tries >= 25) continue;
+        }
+        x_new = x_init;
+        for (step = 0; step < 2; ++step) {
+            rng_init(&rng, seed, (uint64_t)chain, sweep, (uint32_t)e, step == 0 ? 3u : 4u);
+            x_new = mh_slice(st, &pr, x_new, &rng, evals);
+        }
+        ++ne;
+        g_new = bqo_logcond1(st, e, x_new);                       /* product over both diff lists, qnet.pyx:425-431 */
+        ratio = exp(h0 - mh_eval(st, &pr, x_new) + g_new);
+        if (u_acc < ratio) { if (x_new != st->d[e]) bqo_apply(st, e, x_new); }
+        else if (nreject) ++*nreject;
+    }
+    return ne;
+}
+
+/* the proposal log-density on a grid (parity hook for queues.pyx:1239-1256) */
+void bqo_mh_proposal(const bqo_state *st, int e, const double *x, int n, double *out) {
+    mhprop pr;
+    int i;
+    mh_setup(st, e, &pr);
+    for (i = 0; i < n; ++i) out[i] = mh_eval(st, &pr, x[i]);
 }
 
 /* ---------------------------------------------------------------------------------------------- */

@@ -10,6 +10,9 @@ The reference cannot travel to the GPU box, so its outputs are committed as smal
                       gibbs_initialize [-> a few slice sweeps]), flat fp64 arrays + links, Qnet.log_prob, and
                       for a set of hidden events the values of GGkGibbs.inner_dfun (qnet.pyx:1340-1357) on a grid
                       -- the test_likdelta.py:43-75 identity turned into fixed vectors.
+  mh_<net>.npz        the MH proposal log-density (queues.pair_proposal / departure_proposal, queues.pyx:1239-1283) on
+                      grids for the same initial states; postmh_<net>.npz: long estimation.bayes runs with
+                      sampling_type MH (Qnet.gibbs_resample, qnet.pyx:337)
   post_<net>.npz      traces of estimation.bayes (estimation.py:104) run long by the reference from a saved
                       initial state: service parameters per iteration and per-queue mean waiting time -- the
                       statistical pin for posterior agreement.
@@ -277,39 +280,90 @@ def do_cond(name):
     print("cond_%s: E=%d, %d+%d+%d events on grids" % (name, len(flat["d"]), len(out["s0_rows"]), len(out["s1_rows"]), len(rows)))
 
 
+def do_mh(name):
+    """MH-within-Gibbs pins: the TWOS proposal log-density (queues.pair_proposal / departure_proposal,
+    queues.pyx:1239-1283) on grids for resample-eligible events of the cond_<name> initial state."""
+    import queues
+    ntasks, pct, init, seed, nsweeps = COND[name]
+    net, arrv = make_state(name, ntasks, pct, init, seed)
+    rng = numpy.random.RandomState(seed + 2000)
+    flat, evts = flatten(arrv)
+    elig = [i for i, e in enumerate(evts)
+            if not e.obs_d and (e.next_by_task() is None or not e.next_by_task().obs_a)]
+    rng.shuffle(elig)
+    elig = sorted(elig[:40])
+    rows, xs, vals, lo_hi = [], [], [], []
+    for i in elig:
+        e = evts[i]
+        nxt = e.next_by_task()
+        with quiet():
+            fn = queues.pair_proposal(arrv, e, nxt) if nxt is not None else queues.departure_proposal(arrv, e)
+        L, U = fn.range()
+        hi = U if numpy.isfinite(U) else L + 3.0 * (e.d - L) + 1.0
+        g = numpy.concatenate(([e.d], L + (hi - L) * numpy.array([0.001, 0.05, 0.3, 0.5, 0.7, 0.95, 0.999]),
+                               L + (hi - L) * rng.rand(4), [L - 0.1, hi + 0.1]))
+        with quiet():
+            v = numpy.array([float(fn(float(x))) for x in g])
+        rows.append(i); xs.append(g); vals.append(v); lo_hi.append((L, U))
+    out = dict(yaml=NETS[name], theta=numpy.array(net.parameters, dtype=numpy.float64),
+               rows=numpy.array(rows, dtype=numpy.int32), x=numpy.array(xs), h=numpy.array(vals), range=numpy.array(lo_hi))
+    for k, v in flat.items():
+        out["s0_" + k] = v
+    numpy.savez_compressed(os.path.join(OUT, "mh_%s.npz" % name), **out)
+    print("mh_%s: %d events on grids" % (name, len(rows)))
+
+
 def _post_rep(args):
     """One replica of the reference's estimation.bayes from the common initial state (own process: the reference
     keeps its sampler state in module globals)."""
     name, r = args
+    sampler = "SLICE"
+    if name.endswith("@MH"):
+        name, sampler = name[:-3], "MH"
     ntasks, pct, init, seed, niter, nrep = POST[name]
     net, ini = make_state(name, ntasks, pct, init, seed)
+    with quiet():
+        estimation.set_sampler(sampler)
     arrv = ini.duplicate()
     qnetu.set_seed(1000 * seed + r)
     w = []
     qnet.reset_stats()
     t0 = time.time()
     with quiet():
-        mus, _ = estimation.bayes(net, arrv, niter, report_fn=lambda n, a, i, lp: w.append(qstats.mean_wait(a)))
+        if sampler == "SLICE":
+            mus, _ = estimation.bayes(net, arrv, niter, report_fn=lambda n, a, i, lp: w.append(qstats.mean_wait(a)))
+        else:
+            # estimation.bayes with sampling_type MH cannot take a report_fn (estimation.py:141 passes `lp`, which
+            # only the slice branch defines), so its loop (estimation.py:123-151) is spelled out here
+            net.estimate(arrv)
+            mus = []
+            for i in range(niter):
+                arrv = net.gibbs_resample(arrv, burn=0, num_iter=1, return_arrv=False)[-1]
+                w.append(qstats.mean_wait(arrv))
+                net.sample_parameters(arrv)
+                mus.append(net.parameters[:])
     dt = time.time() - t0
     return numpy.array(mus), numpy.array(w), qnet.stats()["nevents"] / dt
 
 
-def do_post(name):
+def do_post(name, sampler="SLICE"):
     import multiprocessing
+    key = name + ("@MH" if sampler == "MH" else "")
     ntasks, pct, init, seed, niter, nrep = POST[name]
     net, ini = make_state(name, ntasks, pct, init, seed)
     theta0 = list(net.parameters)
     flat, _ = flatten(ini)
     with multiprocessing.Pool(min(nrep, os.cpu_count() or 1)) as pool:
-        res = pool.map(_post_rep, [(name, r) for r in range(nrep)])
+        res = pool.map(_post_rep, [(key, r) for r in range(nrep)])
     thetas, waits, rate = [x[0] for x in res], [x[1] for x in res], [x[2] for x in res]
     out = dict(yaml=NETS[name], theta0=numpy.array(theta0), theta=numpy.array(thetas), mean_wait=numpy.array(waits),
                ref_resamples_per_s=numpy.array(rate))
     for k, v in flat.items():
         out["s0_" + k] = v
-    numpy.savez_compressed(os.path.join(OUT, "post_%s.npz" % name), **out)
-    print("post_%s: E=%d iters=%d reps=%d  ref %.0f resamples/s  theta mean %s" % (
-        name, len(flat["d"]), niter, nrep, numpy.mean(rate), numpy.array(thetas)[:, niter // 5:].mean(axis=(0, 1))))
+    fname = "post_%s.npz" % name if sampler == "SLICE" else "postmh_%s.npz" % name
+    numpy.savez_compressed(os.path.join(OUT, fname), **out)
+    print("%s: E=%d iters=%d reps=%d  ref %.0f resamples/s  theta mean %s" % (
+        fname, len(flat["d"]), niter, nrep, numpy.mean(rate), numpy.array(thetas)[:, niter // 5:].mean(axis=(0, 1))))
 
 
 def do_lpdf():
@@ -338,6 +392,7 @@ if __name__ == "__main__":
     ap.add_argument("--only", default=None)
     ap.add_argument("--skip-post", action="store_true")
     ap.add_argument("--skip-cond", action="store_true")
+    ap.add_argument("--skip-mh", action="store_true")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     if args.only in (None, "lpdf"):
@@ -346,6 +401,13 @@ if __name__ == "__main__":
         for n in COND:
             if args.only in (None, n):
                 do_cond(n)
+    if not args.skip_mh:  # MH-within-Gibbs (gibbs_resample): proposal grids and long reference runs; no PS (queues.pyx:1140)
+        for n in COND:
+            if n != "psdelay" and args.only in (None, n):
+                do_mh(n)
+        for n in ("mm1", "qnet3", "mm3"):
+            if args.only in (None, n) and not args.skip_post:
+                do_post(n, "MH")
     if not args.skip_post:
         for n in POST:
             if args.only in (None, n):

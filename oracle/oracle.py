@@ -47,6 +47,11 @@ def lib():
         L.bqo_slice_sweep.restype = ctypes.c_long
         L.bqo_slice_sweep.argtypes = [ctypes.POINTER(_State), i32p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64,
                                       ctypes.c_uint32, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_long)]
+        L.bqo_mh_sweep.restype = ctypes.c_long
+        L.bqo_mh_sweep.argtypes = [ctypes.POINTER(_State), i32p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64,
+                                   ctypes.c_uint32, ctypes.c_int, ctypes.POINTER(ctypes.c_long),
+                                   ctypes.POINTER(ctypes.c_long)]
+        L.bqo_mh_proposal.argtypes = [ctypes.POINTER(_State), ctypes.c_int, f64p, ctypes.c_int, f64p]
         L.bqo_suffstats.argtypes = [ctypes.POINTER(_State), f64p]
         L.bqo_estimate.argtypes = [ctypes.c_int, f64p, f64p, f64p]
         L.bqo_sample_params.argtypes = [ctypes.c_int, f64p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32,
@@ -131,6 +136,20 @@ class OracleChain(object):
         ne = lib().bqo_slice_sweep(ctypes.byref(self._st), order.ctypes.data_as(i32p), len(order), seed, chain, sweep,
                                    float(tmax), 0, ctypes.byref(ev))
         return int(ne), int(ev.value)
+
+    def mh_sweep(self, order, seed, chain, sweep, sample_final=True):
+        """One sweep of Qnet.gibbs_resample; returns (proposals, rejections)."""
+        order = numpy.ascontiguousarray(order, dtype=numpy.int32)
+        rej, ev = ctypes.c_long(0), ctypes.c_long(0)
+        ne = lib().bqo_mh_sweep(ctypes.byref(self._st), order.ctypes.data_as(i32p), len(order), seed, chain, sweep,
+                                1 if sample_final else 0, ctypes.byref(rej), ctypes.byref(ev))
+        return int(ne), int(rej.value)
+
+    def mh_proposal(self, e, xs):
+        xs = numpy.ascontiguousarray(xs, dtype=numpy.float64)
+        out = numpy.empty(len(xs))
+        lib().bqo_mh_proposal(ctypes.byref(self._st), int(e), xs.ctypes.data_as(f64p), len(xs), out.ctypes.data_as(f64p))
+        return out
 
     def suffstats(self):
         out = numpy.zeros((self.Q, 8))

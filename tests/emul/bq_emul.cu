@@ -140,6 +140,74 @@ long bqe_slice_sweep(void *h, const int *order, int n_order, uint64_t seed, int6
     return ne;
 }
 
+// one MH-within-Gibbs sweep with the product's proposal / accept routines, sequentially (group width 1)
+long bqe_mh_sweep(void *h, const int *order, int n_order, uint64_t seed, int64_t chain, uint32_t sweep, int sample_final,
+                  long *nreject) {
+    Emul *m = (Emul *)h;
+    long ne = 0;
+    for (int idx = 0; idx < n_order; ++idx) {
+        EventCtx ev;
+        event_load(m->c, order[idx], ev);
+        const bool fin = ev.e1 < 0;
+        if (fin && !sample_final) continue;
+        MhProp pr;
+        mh_setup(m->c, ev, pr);
+        if (pr.Uh - pr.Lh < 1e-10) continue;
+        if (!fin && ev.d1 - ev.a_e < 1e-10) continue;
+        Rng aux;
+        aux.init(seed, (uint64_t)chain, sweep, (uint32_t)ev.e, TAG_MH_AUX);
+        const double u_acc = aux.uniform();
+        (void)aux.uniform();
+        const double h0 = pr.eval(ev.x0);
+        double x_init = ev.x0;
+        if (!(h0 > BQ_NEG_INF)) {
+            int tries = 0;
+            for (; tries < 25; ++tries) {
+                const double u = aux.uniform();
+                x_init = fin ? pr.b0 + (-log(1.0 - u)) : ev.a_e + (ev.d1 - ev.a_e) * u;
+                if (pr.eval(x_init) > BQ_NEG_INF) break;
+            }
+            if (tries >= 25) continue;
+        }
+        double x_new = x_init;
+        long long evals = 0;
+        for (int step = 0; step < 2; ++step) {
+            Rng rng;
+            rng.init(seed, (uint64_t)chain, sweep, (uint32_t)ev.e, step == 0 ? TAG_MH : TAG_MH2);
+            if (fin) {
+                x_new = slice_stepout_seq([&](double x) { return pr.eval(x); }, x_new, pr.Lh, pr.Uh, rng, evals);
+            } else {  // finite bounds: what group_slice does with W lanes, one candidate at a time
+                const double x0 = x_new;
+                const double logy = pr.eval(x0) - (-log(1.0 - rng.uniform()));
+                if (!(logy > BQ_NEG_INF)) continue;
+                double L = pr.Lh, R = pr.Uh;
+                for (int it = 0; it < BQ_SLICE_MAX_ITERS; ++it) {
+                    const double x1 = L + (R - L) * rng.uniform();
+                    if (pr.eval(x1) >= logy) { x_new = x1; break; }
+                    if (x1 > x0) R = x1; else L = x1;
+                    if (R - L < 1e-10) break;
+                }
+            }
+        }
+        ++ne;
+        int steps = 0;
+        const double g_new = dyn_logcond<8>(m->c, ev, x_new, steps);
+        const double ratio = exp(h0 - pr.eval(x_new) + g_new);
+        if (u_acc < ratio) { if (x_new != ev.x0) dyn_commit<1, 8>(m->c, ev, x_new, 0, 1u); }
+        else if (nreject) ++*nreject;
+    }
+    return ne;
+}
+
+void bqe_mh_proposal(void *h, int e, const double *x, int n, double *out) {
+    Emul *m = (Emul *)h;
+    EventCtx ev;
+    event_load(m->c, e, ev);
+    MhProp pr;
+    mh_setup(m->c, ev, pr);
+    for (int j = 0; j < n; ++j) out[j] = pr.eval(x[j]);
+}
+
 void bqe_get(void *h, double *d, int *ord, double *F, double *svc) {
     Emul *m = (Emul *)h;
     if (d) memcpy(d, m->d.data(), m->E * sizeof(double));

@@ -20,7 +20,7 @@ f64p = ctypes.POINTER(ctypes.c_double)
 def build():
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     if not os.path.exists(SO) or any(os.path.getmtime(f) > os.path.getmtime(SO) for f in deps):
-        subprocess.check_call([NVCC, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC",
+        subprocess.check_call([NVCC, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
                                "-shared", "-o", SO, SRC])
     return SO
 
@@ -42,6 +42,10 @@ def lib():
         L.bqe_slice_sweep.restype = ctypes.c_long
         L.bqe_slice_sweep.argtypes = [ctypes.c_void_p, i32p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64,
                                       ctypes.c_uint32, ctypes.c_double]
+        L.bqe_mh_sweep.restype = ctypes.c_long
+        L.bqe_mh_sweep.argtypes = [ctypes.c_void_p, i32p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32,
+                                   ctypes.c_int, ctypes.POINTER(ctypes.c_long)]
+        L.bqe_mh_proposal.argtypes = [ctypes.c_void_p, ctypes.c_int, f64p, ctypes.c_int, f64p]
         L.bqe_get.argtypes = [ctypes.c_void_p, f64p, i32p, f64p, f64p]
         L.bqe_derive.argtypes = [ctypes.c_void_p, f64p, f64p, i32p, i32p, i32p]
         L.bqe_check.restype = ctypes.c_int
@@ -96,6 +100,19 @@ class EmulChain(object):
             tmax = 2.0 * self.d.max()
         return int(lib().bqe_slice_sweep(self._h, order.ctypes.data_as(i32p), len(order), seed, chain, sweep,
                                          float(tmax)))
+
+    def mh_sweep(self, order, seed, chain, sweep, sample_final=True):
+        order = numpy.ascontiguousarray(order, dtype=numpy.int32)
+        rej = ctypes.c_long(0)
+        ne = lib().bqe_mh_sweep(self._h, order.ctypes.data_as(i32p), len(order), seed, chain, sweep,
+                                1 if sample_final else 0, ctypes.byref(rej))
+        return int(ne), int(rej.value)
+
+    def mh_proposal(self, e, xs):
+        xs = numpy.ascontiguousarray(xs, dtype=numpy.float64)
+        out = numpy.empty(len(xs))
+        lib().bqe_mh_proposal(self._h, int(e), xs.ctypes.data_as(f64p), len(xs), out.ctypes.data_as(f64p))
+        return out
 
     @property
     def d(self):

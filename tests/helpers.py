@@ -9,6 +9,7 @@ from bayes_qnet_b200.arrivals import Arrivals
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 COND_NETS = ["mm1", "qnet3", "delay", "lng1", "mm3", "lnk", "psdelay"]
+MH_NETS = ["mm1", "qnet3", "delay", "lng1", "mm3", "lnk"]  # PS has no arrivalLik (queues.pyx:1140): slice only
 STATIC_NETS = ["mm1", "qnet3", "delay", "lng1"]  # single-server FIFO + delay stations: queue order is static
 DYNAMIC_NETS = ["mm3", "lnk", "psdelay"]  # multi-server FIFO (k = 3, 4) and processor sharing: per-chain order
 

@@ -73,3 +73,31 @@ def test_emulated_mixed_networks_match_oracle(name):
     dv = ec.derive()
     assert helpers.relerr(dv["s"], oc.s).max() < TOL
     assert numpy.array_equal(dv["next_byq"], oc.next_byq)
+
+
+@pytest.mark.parametrize("name", helpers.MH_NETS)
+def test_emulated_mh_matches_reference_and_oracle(name):
+    """MH-within-Gibbs (Qnet.gibbs_resample): the product's proposal log-density against the reference's Pwfun
+    values, and whole MH sweeps (proposal draws, accept / reject, commits) against the oracle."""
+    g = helpers.golden("mh_" + name)
+    net, arrv = helpers.golden_state(g, "s0")
+    ec = emul_helper.EmulChain(net, arrv)
+    for r, xs, ref in zip(g["rows"], g["x"], g["h"]):
+        v = ec.mh_proposal(int(r), xs)
+        assert numpy.array_equal(numpy.isfinite(v), numpy.isfinite(ref)), "support differs at row %d" % r
+        m = numpy.isfinite(ref)
+        assert helpers.relerr(v[m], ref[m]).max() < 1e-12
+    oc = helpers.oracle_chain(net, arrv)
+    order = oc.eligible()
+    props = rejects = 0
+    for s in range(6):
+        a, b = oc.mh_sweep(order, 77, 2, s), ec.mh_sweep(order, 77, 2, s)
+        assert a == b
+        props, rejects = props + a[0], rejects + a[1]
+        assert ec.check() == 0
+    assert helpers.relerr(ec.d, oc.d).max() < TOL
+    assert 0 < rejects < props
+    # sample_final = False skips the tasks' last events (qnet.pyx:361)
+    n_final = int(sum(1 for e in order if oc.next_byt[e] < 0))
+    a = oc.mh_sweep(order, 77, 2, 9, sample_final=False)
+    assert a == ec.mh_sweep(order, 77, 2, 9, sample_final=False) and a[0] <= len(order) - n_final

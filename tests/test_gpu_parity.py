@@ -334,3 +334,119 @@ def test_mixed_disciplines_match_oracle(name):
         assert helpers.relerr(full["d"][0], oc.d).max() < 1e-7
         assert helpers.relerr(full["s"][0], oc.s).max() < 1e-7
         assert numpy.array_equal(full["proc"][0], oc.proc) and numpy.array_equal(full["next_byq"][0], oc.next_byq)
+
+
+@pytest.mark.parametrize("name", helpers.MH_NETS)
+def test_mh_proposal_and_sweeps(name):
+    """MH-within-Gibbs (Qnet.gibbs_resample, qnet.pyx:337): bq_mh_proposal against the reference's Pwfun values
+    (tests/golden/mh_*.npz); MH sweeps -- two slice steps on the proposal, exact-conditional accept ratio, commit --
+    against the oracle, interleaved with slice sweeps (static-order handles switch kernels in between)."""
+    g = helpers.golden("mh_" + name)
+    net, arrv = helpers.golden_state(g, "s0")
+    with GibbsEngine(net, arrv, n_chains=4, seed=606, chain_offset=1) as eng:
+        for r, xs, ref in zip(g["rows"], g["x"], g["h"]):
+            v = eng.mh_proposal(3, int(r), xs)
+            assert numpy.array_equal(numpy.isfinite(v), numpy.isfinite(ref)), "support differs at row %d" % r
+            m = numpy.isfinite(ref)
+            assert helpers.relerr(v[m], ref[m]).max() < TOL
+        seq = eng.sequential_order()
+        off, order = eng.schedule()
+        assert sorted(seq) == sorted(order)
+        ocs = [helpers.oracle_chain(net, arrv) for _ in range(2)]
+        chains = (0, 3)
+        props = rejects = 0
+        sweep = 0
+        for mode, n in (("MH", 3), ("SLICE", 2), ("MH", 2)):
+            eng.sweep(n, mode, "NONE")
+            for s in range(n):
+                for oc, c in zip(ocs, chains):
+                    if mode == "MH":
+                        a = oc.mh_sweep(seq, eng.seed, 1 + c, sweep)
+                        props, rejects = props + a[0], rejects + a[1]
+                    else:
+                        oc.slice_sweep(order, eng.seed, 1 + c, sweep)
+                sweep += 1
+        d = eng.state()
+        for oc, c in zip(ocs, chains):
+            assert helpers.relerr(d[c], oc.d).max() < 1e-7
+        st = eng.stats()
+        assert st["nreject"] > 0 and st["nevents"] > st["nreject"]
+        lp = eng.log_prob()
+        assert abs(lp[3] - ocs[1].log_prob()) < 1e-7 * max(1.0, abs(ocs[1].log_prob()))
+
+
+def test_mh_counts_and_group_widths(monkeypatch):
+    """nevents / nreject of one chain equal the oracle's; every group width walks the same path."""
+    g = helpers.golden("mh_mm3")
+    net, arrv = helpers.golden_state(g, "s0")
+    ref = None
+    for width in ("8", "16", "32"):
+        monkeypatch.setenv("BQ_DYN_W", width)
+        with GibbsEngine(net, arrv, n_chains=1, seed=31) as eng:
+            seq = eng.sequential_order()
+            eng.sweep(5, "MH", "BAYES")
+            st, d, th = eng.stats(), eng.state(), eng.params()
+        if ref is None:
+            oc = helpers.oracle_chain(net, arrv)
+            props = rejects = 0
+            for s in range(5):
+                a = oc.mh_sweep(seq, 31, 0, s)
+                props, rejects = props + a[0], rejects + a[1]
+                oc.update_params("BAYES", 31, 0, s)
+            assert (st["nevents"], st["nreject"]) == (props, rejects)
+            assert helpers.relerr(d[0], oc.d).max() < 1e-7 and helpers.relerr(th[0], oc.theta).max() < 1e-7
+            ref = (d, th)
+        else:
+            assert numpy.array_equal(d, ref[0]) and numpy.array_equal(th, ref[1])
+
+
+def test_mh_refused_for_ps():
+    g = helpers.golden("cond_psdelay")
+    net, arrv = helpers.golden_state(g, "s0")
+    with GibbsEngine(net, arrv, n_chains=1, seed=1) as eng:
+        with pytest.raises(capi.BqError):
+            eng.sweep(1, "MH", "NONE")
+        with pytest.raises(capi.BqError):
+            eng.mh_proposal(0, 0, [1.0])
+
+
+def test_reference_api_gibbs_resample():
+    """Qnet.gibbs_resample(arrv, burn, num_iter) mutates arrv, returns the per-iteration copies, counts rejects;
+    estimation.bayes honours set_sampler("MH") (estimation.py:20-25, 131-132)."""
+    from bayes_qnet_b200 import qnet
+    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 60, 0.3, seed=12)
+    qnet.reset_stats()
+    out = net.gibbs_resample(ini, 2, 3)
+    assert len(out) == 3
+    ini.validate()
+    st = qnet.stats()
+    assert 0 < st["nreject"] < st["nevents"] <= 5 * ini.num_hidden_events()
+    estimation.set_sampler("MH")
+    try:
+        mus, arrvl = estimation.bayes(net, ini, 15)
+    finally:
+        estimation.set_sampler("SLICE")
+    assert len(mus) == 15 and estimation.last_run().stats["nreject"] > 0
+    ini.validate()
+
+
+@pytest.mark.parametrize("name", ["mm1", "qnet3", "mm3"])
+def test_mh_posterior_agrees_with_long_reference_mh_runs(name):
+    """estimation.bayes with sampling_type MH from the same initial state vs the reference's own long MH runs
+    (tests/golden/postmh_*.npz), within 4 combined Monte-Carlo standard errors."""
+    g = helpers.golden("postmh_" + name)
+    net, arrv = helpers.golden_state(dict((k, g[k]) for k in g.files if k != "theta") | {"theta": g["theta0"]}, "s0")
+    ref_th, ref_mw = g["theta"], g["mean_wait"]
+    n = ref_th.shape[1]
+    burn = n // 5
+    with GibbsEngine(net, arrv, n_chains=32, seed=4711) as eng:
+        eng.sweep(n, "MH", "BAYES", trace=True)
+        th, mw, lp = eng.traces()
+    ref_th = numpy.swapaxes(ref_th[:, burn:], 0, 1)
+    ref_mw = numpy.swapaxes(ref_mw[:, burn:], 0, 1)
+    th, mw = th[burn:], mw[burn:]
+    for ours, ref, what in ((th, ref_th, "theta"), (mw[:, :, 1:], ref_mw[:, :, 1:], "mean wait")):
+        m1, m2 = ours.mean(axis=(0, 1)), ref.mean(axis=(0, 1))
+        se = numpy.sqrt(diagnostics.mcse(ours) ** 2 + diagnostics.mcse(ref) ** 2)
+        z = numpy.abs(m1 - m2) / numpy.maximum(se, 1e-12)
+        assert numpy.all(z < 4.0), "%s %s: ours %s ref %s z %s" % (name, what, m1, m2, z)
