@@ -21,68 +21,64 @@ from . import queues as _queues
 MAX_TRIES = 20
 
 
+def _replace_min(free, x):
+    """The arriving job takes the server that frees first and holds it until x: sorted tuple in, sorted tuple out."""
+    out = list(free[1:])
+    bisect.insort(out, x)
+    return tuple(out)
+
+
 class _QueueState(object):
-    """Events of one queue in arrival order (source queue: departure order), as parallel python lists."""
+    """Events of one queue in arrival order (source queue: departure order), as parallel python lists.  For a
+    multi-server queue F[j] is the sorted tuple of server-free times seen by the event at position j (the reference's
+    d_proc_prev, queues.pyx:654-680, as a multiset: services only depend on its minimum); F[n] is the state after
+    the last event."""
 
     def __init__(self, queue):
         self.queue = queue
         self.key = []   # sort key: arrival (source: departure)
         self.a = []
         self.d = []
-        self.proc = []
+        self.F = []
 
     def load(self, a, d):
         k = self.queue.k
         self.a = list(a)
         self.d = list(d)
         self.key = list(a)
-        self.proc = [0] * len(self.a)
+        self.F = []
         if self.queue.code == _queues.Q_GGK and k > 1:
-            free = [0.0] * k
+            free = (0.0,) * k
             for j in range(len(self.a)):
-                p = min(range(k), key=free.__getitem__)
-                self.proc[j] = p
-                free[p] = self.d[j]
-
-    def free_vector(self, j):
-        """Per-server last departure among events before position j (queues.pyx:654-680)."""
-        k = self.queue.k
-        free = [None] * k
-        left = k
-        i = j - 1
-        while i >= 0 and left > 0:
-            p = self.proc[i]
-            if free[p] is None:
-                free[p] = self.d[i]
-                left -= 1
-            i -= 1
-        return [0.0 if f is None else f for f in free]
+                self.F.append(free)
+                free = _replace_min(free, self.d[j])
+            self.F.append(free)
 
     def feasible_after(self, j, free):
-        """Would every successor of position j keep s >= 0 given the server vector `free` after j?
-        Walk forward until the vector matches what the successors already imply."""
-        k = self.queue.k
+        """Would every event from position j on keep s >= 0 if the server-free times it sees became `free`?  Walks
+        forward until the times match what that event already sees (nothing further changes).  Returns the new
+        tuples for positions j, j+1, ... or None."""
         n = len(self.a)
+        out = []
         i = j
-        newproc = []
-        while i < n:
-            p = min(range(k), key=free.__getitem__)
-            if self.d[i] - max(self.a[i], free[p]) < 0:
+        while True:
+            if free == self.F[i]:
+                return out
+            out.append(free)
+            if i == n:
+                return out
+            if self.d[i] - max(self.a[i], free[0]) < 0:
                 return None
-            newproc.append(p)
-            free[p] = self.d[i]
+            free = _replace_min(free, self.d[i])
             i += 1
-            if free == self.free_vector(i):  # same server vector as before the insertion: nothing changes further
-                break
-        return newproc
 
-    def insert(self, j, a, d, proc=0, newproc=None):
+    def insert(self, j, a, d, newF=None):
         self.key.insert(j, a)
         self.a.insert(j, a)
         self.d.insert(j, d)
-        self.proc.insert(j, proc)
-        if newproc:
-            self.proc[j + 1:j + 1 + len(newproc)] = newproc
+        if newF is not None:  # multi-server: the new event sees what position j saw; its successors see newF
+            self.F.insert(j, self.F[j])
+            self.F[j + 1:j + 1 + len(newF)] = newF
 
 
 def _draw_departure_fifo1(qs, a, mean):
@@ -102,24 +98,18 @@ def _draw_departure_fifo1(qs, a, mean):
 
 
 def _draw_departure_ggk(qs, a, mean):
-    k = qs.queue.k
     j = bisect.bisect_right(qs.key, a)
-    free = qs.free_vector(j)
-    p = min(range(k), key=free.__getitem__)
-    c = max(a, free[p])
+    free = qs.F[j]
+    c = max(a, free[0])
     s = numpy.random.exponential(mean)
     for _ in range(60):
-        f2 = list(free)
-        f2[p] = c + s
-        newproc = qs.feasible_after(j, f2)
-        if newproc is not None:
-            qs.insert(j, a, c + s, p, newproc)
+        newF = qs.feasible_after(j, _replace_min(free, c + s))
+        if newF is not None:
+            qs.insert(j, a, c + s, newF)
             return c + s
         s *= 0.5
-    f2 = list(free)
-    f2[p] = c
-    newproc = qs.feasible_after(j, f2) or []
-    qs.insert(j, a, c, p, newproc)
+    newF = qs.feasible_after(j, _replace_min(free, c)) or []
+    qs.insert(j, a, c, newF)
     return c
 
 
@@ -211,7 +201,8 @@ def initialize(net, arrv, kind="DFN2", sample_paths=True):
             path = [(int(soa["state"][i]), int(soa["qid"][i])) for i in chain[1:]]
         d = src_d[t]
         j = bisect.bisect_right(qstate[0].key, d)
-        qstate[0].key.insert(j, d); qstate[0].a.insert(j, 0.0); qstate[0].d.insert(j, d); qstate[0].proc.insert(j, 0)
+        qstate[0].insert(j, 0.0, d)
+        qstate[0].key[j] = d
         new["tid"].append(t); new["qid"].append(0); new["state"].append(s0); new["a"].append(0.0); new["d"].append(d)
         new["eid"].append(int(soa["eid"][first]))
         for step, (sid, qid) in enumerate(path):
