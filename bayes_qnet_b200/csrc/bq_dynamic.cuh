@@ -1,25 +1,28 @@
 // Sweep kernels for networks whose queue order is per-chain state: multi-server FIFO queues (QueueGGk
 // with k > 1, queues.pyx:444-723) and processor-sharing queues (QueuePS, queues.pyx:1032-1232), mixed
-// freely with single-server FIFO queues and delay stations.
+// freely with single-server FIFO queues and delay stations.  MH-within-Gibbs sweeps (Qnet.gibbs_resample,
+// qnet.pyx:337) of any network also run here.
 //
 // What the reference does per evaluation of the conditional (GGkGibbs.inner_dfun, qnet.pyx:1340-1357) is
 // build two diff lists -- diffListForDeparture(e, x) in e's queue and diffListForArrival(e', x) in the
 // queue of the task's next event -- and sum lpdf(s_new) - lpdf(s_old) over them (queues.pyx:83-95).  Here
-// the same sums are produced by forward walks over per-chain arrays:
+// the same sums are produced by forward walks over per-chain arrays that are indexed by POSITION in the
+// queue (queue after queue, each in arrival order; queue 0 in departure order, arrivals.pyx:256), so that a
+// walk is a stream of consecutive loads with no pointer chasing:
 //
-//   d[E]        departure times                                   (fp64, the chain state proper)
-//   ord[E]      events of every queue in arrival order, queue after queue (queue 0: departure order,
-//               arrivals.pyx:256); pos[E] is the inverse permutation
-//   F[e][k]     for every event of a k-server FIFO queue: the k server-free times seen at its arrival,
-//               ascending (the reference's Event.d_proc_prev, arrivals.pxd:30, as a sorted multiset:
-//               services depend only on min F, and replacing the minimum by the event's own departure
-//               is the whole recursion of queues.pyx:654-680)
-//   at/dt, dord/dpos, svc   PS queues only: sorted arrival and departure times, the events in departure
-//               order, and the stored service times
+//   ord[p], pos[e]   the event at position p / the position of event e
+//   at[p], dq[p]     arrival and departure time of the event at position p
+//   F[p][k]          k-server FIFO queues: the k server-free times seen by the event at position p, ascending
+//                    (the reference's Event.d_proc_prev, arrivals.pxd:30, as a sorted multiset: services
+//                    depend only on min F, and replacing the minimum by the event's own departure is the
+//                    whole recursion of queues.pyx:654-680)
+//   dt[p], dord[p], dpos[e], sq[p]   PS queues: departure times sorted (with their events and the inverse
+//                    map), and the service time of the event at arrival-position p
+//   d[e]             departure times by event: the chain state as the C-ABI exposes it, kept in step
 //
-// A walk starts from the stored vector of the first event whose predecessors are unchanged, replays the
+// A walk starts from the stored vector of the first position whose predecessors are unchanged, replays the
 // recursion with the modified time, and stops as soon as the running vector equals the stored one of the
-// next event (nothing further can change) or a service time goes negative (-inf).  Moving an arrival
+// next position (nothing further can change) or a service time goes negative (-inf).  Moving an arrival
 // re-inserts the event at its new rank (stable sort by arrival, queues.pyx:537) on the fly.
 //
 // Execution model: a GROUP of W lanes (W = 8, 16 or 32; 32/W chains per warp) owns one chain and visits
@@ -35,10 +38,8 @@
 // The walk and commit routines are __host__ __device__ so that the test harness under tests/emul can run the
 // very same code on the CPU (test infrastructure only: the library itself has no host execution path).
 #if defined(__CUDA_ARCH__)
-#define BQ_LDG(p) __ldg(p)
 #define BQ_SYNCG(m) __syncwarp(m)
 #else
-#define BQ_LDG(p) (*(p))
 #define BQ_SYNCG(m) ((void)(m))
 #endif
 #define BQ_HDF __host__ __device__ __forceinline__
@@ -46,19 +47,29 @@
 
 namespace bq {
 
+// per queue, identical for all chains: discipline, servers, position range [lo, hi), offset of its F block
+struct QInfo {
+    int type, k, lo, hi, foff, dist;
+};
+
+// one resample-eligible event of the sweep order: the event, the next event of its task, their queues
+struct DynRec {
+    int e, e1, q0, q1;
+};
+
 struct DynArgs {
     int E, Q, P, n_order, n_sweeps, update, flags, trace_base, n_chains, EF, mode;
-    const int *order;                        // [n_order] resample-eligible events in sweep order
-    const int *ev_q, *ev_pt, *ev_nt, *ev_f;  // per event: queue, prev/next by task, offset of F[e] (-1: none)
-    const int *q_off;                        // [Q+1] position range of each queue inside ord
-    const int *q_type, *q_k, *q_dist, *q_poff;
-    double *state;                           // [C][E]
-    int *ord, *pos;                          // [C][E]
-    double *F;                               // [C][EF]
-    int *dord, *dpos;                        // [C][E]  (PS queues) events in departure order / inverse
-    double *at, *dt, *svc;                   // [C][E]  (PS queues) sorted arrival / departure times, services
-    double *theta;                           // [C][P]
-    long long *stats;                        // [C][BQ_NSTAT]
+    const DynRec *order;  // [n_order]
+    const QInfo *qinfo;   // [Q]
+    const int *q_poff;    // [Q] offset of the queue's first parameter
+    double *state;        // [C][E]  d by event
+    int *ord, *pos;       // [C][E]
+    double *at, *dq;      // [C][E]  by position
+    double *F;            // [C][EF] by position
+    int *dord, *dpos;     // [C][E]  PS
+    double *dt, *sq;      // [C][E]  PS
+    double *theta;        // [C][P]
+    long long *stats;     // [C][BQ_NSTAT]
     double *tr_theta, *tr_wait, *tr_logp;
     unsigned long long seed;
     long long chain_offset;
@@ -99,140 +110,54 @@ struct FreeVec {
 
 // one chain's arrays + the tables shared by all chains
 struct Chain {
-    const DynArgs *A;
     double *d;
     int *ord, *pos;
-    double *F;
+    double *at, *dq, *F;
     int *dord, *dpos;
-    double *at, *dt, *svc;
+    double *dt, *sq;
+    const QInfo *qi;
     const QConst *qc;
 
-    BQ_HDF void bind(const DynArgs &a, int chain, const QConst *qc_) {
-        A = &a;
+    BQ_HDF void bind(const DynArgs &a, int chain, const QInfo *qi_, const QConst *qc_) {
         const size_t c = (size_t)chain;
         d = a.state + c * a.E;
         ord = a.ord + c * a.E;
         pos = a.pos + c * a.E;
+        at = a.at + c * a.E;
+        dq = a.dq + c * a.E;
         F = a.F + c * a.EF;
         dord = a.dord ? a.dord + c * a.E : nullptr;
         dpos = a.dpos ? a.dpos + c * a.E : nullptr;
-        svc = a.svc ? a.svc + c * a.E : nullptr;
-        at = a.at ? a.at + c * a.E : nullptr;
         dt = a.dt ? a.dt + c * a.E : nullptr;
+        sq = a.sq ? a.sq + c * a.E : nullptr;
+        qi = qi_;
         qc = qc_;
     }
-    // a_e = departure of the task's previous event, 0 for the task's first event (arrivals.pyx:848)
-    BQ_HDF double arr(int i) const {
-        const int pt = BQ_LDG(&A->ev_pt[i]);
-        return (pt >= 0) ? d[pt] : 0.0;
-    }
+    BQ_HDF double *fvec(const QInfo &q, int p) const { return F + q.foff + (size_t)(p - q.lo) * q.k; }
 };
 
-// ---------------------------------------------------------------------------------------------
-// FIFO queue with k servers: likelihoodDelta(diffListForDeparture(e, x))   (queues.pyx:470-511, 83-95)
-// ---------------------------------------------------------------------------------------------
-template <int KMAX>
-BQ_HDI double ggk_dep_delta(const Chain &c, int e, int q, double x, double a_e, double d_e, int &steps) {
-    const int k = BQ_LDG(&c.A->q_k[q]);
-    const QConst &qc = c.qc[q];
-    FreeVec<KMAX> M;
-    M.load(c.F + BQ_LDG(&c.A->ev_f[e]), k);
-    const double st = dmax(a_e, M.v[0]);
-    const double s_new = x - st;
-    if (s_new < 0.0) return BQ_NEG_INF;
-    const double s_old = d_e - st;
-    double acc = 0.0;
-    if (s_new != s_old) acc = lpdf(qc, s_new) - lpdf(qc, s_old);
-    M.replace_min(x);
-    const int end = BQ_LDG(&c.A->q_off[q + 1]);
-    for (int p = c.pos[e] + 1; p < end; ++p) {
-        const int i = c.ord[p];
-        const double *fi = c.F + BQ_LDG(&c.A->ev_f[i]);
-        if (M.equals(fi, k)) break;  // same free times as before: nothing after i changes
-        ++steps;
-        const double bn = M.v[0], bo = fi[0], di = c.d[i];
-        if (bn != bo) {
-            const double ai = c.arr(i);
-            const double sn = di - dmax(ai, bn);
-            if (sn < 0.0) return BQ_NEG_INF;
-            const double so = di - dmax(ai, bo);
-            if (sn != so) acc += lpdf(qc, sn) - lpdf(qc, so);
-        }
-        M.replace_min(di);
+// the event being resampled and its task successor, with their positions and current times
+struct EventCtx {
+    int e, e1, q0, q1, t0, t1, p0, p1;
+    double x0, a_e, d1;
+};
+
+BQ_HDF void event_load(const Chain &c, const DynRec &rec, EventCtx &ev) {
+    ev.e = rec.e; ev.e1 = rec.e1; ev.q0 = rec.q0; ev.q1 = rec.q1;
+    ev.t0 = c.qi[ev.q0].type;
+    ev.p0 = c.pos[ev.e];
+    ev.x0 = c.dq[ev.p0];
+    ev.a_e = c.at[ev.p0];
+    ev.t1 = -1; ev.p1 = -1; ev.d1 = 0.0;
+    if (ev.e1 >= 0) {
+        ev.t1 = c.qi[ev.q1].type;
+        ev.p1 = c.pos[ev.e1];
+        ev.d1 = c.dq[ev.p1];
     }
-    return acc;
 }
-
-// rank of e1 among the OTHER events of its queue once its arrival is x: before the first event whose
-// arrival is > x (stable sort by arrival, queues.pyx:537).  Returned as the index e1 will occupy.
-BQ_HDF int ggk_new_rank(const Chain &c, int e1, int lo, int end, int p1, double x, double a_old) {
-    int j = p1;
-    if (x >= a_old) {
-        while (j + 1 < end && c.arr(c.ord[j + 1]) <= x) ++j;
-    } else {
-        int l = lo, r = p1;
-        while (l < r) {
-            const int m = (l + r) >> 1;
-            if (c.arr(c.ord[m]) > x) r = m; else l = m + 1;
-        }
-        j = l;
-    }
-    return j;
-}
-
-// event at index t of the queue's order after e1 moved from index p1 to index j
-BQ_HDF int ggk_moved_at(const Chain &c, int t, int j, int p1, int e1) {
-    if (t == j) return e1;
-    if (j >= p1) return (t >= p1 && t < j) ? c.ord[t + 1] : c.ord[t];
-    return (t > j && t <= p1) ? c.ord[t - 1] : c.ord[t];
-}
-
-// likelihoodDelta(diffListForArrival(e1, x))   (queues.pyx:514-591, 83-95)
-template <int KMAX>
-BQ_HDI double ggk_arr_delta(const Chain &c, int e1, int q, double x, double a_old, int &steps) {
-    const int k = BQ_LDG(&c.A->q_k[q]);
-    const QConst &qc = c.qc[q];
-    const int lo = BQ_LDG(&c.A->q_off[q]), end = BQ_LDG(&c.A->q_off[q + 1]);
-    const int p1 = c.pos[e1];
-    const int j = ggk_new_rank(c, e1, lo, end, p1, x, a_old);
-    const int ps = (j < p1) ? j : p1, pe = (j < p1) ? p1 : j;
-    FreeVec<KMAX> M;
-    M.load(c.F + BQ_LDG(&c.A->ev_f[c.ord[ps]]), k);  // predecessors of index ps are untouched
-    double acc = 0.0;
-    for (int t = ps; t < end; ++t) {
-        const int i = ggk_moved_at(c, t, j, p1, e1);
-        const double *fi = c.F + BQ_LDG(&c.A->ev_f[i]);
-        if (t > pe && M.equals(fi, k)) break;
-        ++steps;
-        const double ai_old = (i == e1) ? a_old : c.arr(i);
-        const double ai = (i == e1) ? x : ai_old;
-        const double di = c.d[i];
-        const double sn = di - dmax(ai, M.v[0]);
-        if (sn < 0.0) return BQ_NEG_INF;
-        const double so = di - dmax(ai_old, fi[0]);
-        if (sn != so) acc += lpdf(qc, sn) - lpdf(qc, so);
-        M.replace_min(di);
-    }
-    return acc;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Processor sharing (QueuePS, queues.pyx:1032-1232): s_i = integral over [a_i, d_i] of dt / N(t), with
-// N(t) = #{a <= t} - #{d <= t} over the queue (cninq.pyx:55-58).  Per chain and PS queue the arrival times are
-// kept sorted in at[] (event ids: ord[]) and the departure times in dt[] (event ids: dord[]), the service
-// times in svc[].  Moving one arrival or departure of event m from t_old to t_new changes N(t) by sgn = +-1 on
-// I = (lo, hi) = (min, max) only, so (diffListForDeparture / diffListForArrival, queues.pyx:1149-1183):
-//   * m itself gains or loses   sgn * integral over I of dt / max(N_old, N_old + sgn),
-//   * every other event i that is in the queue during part of I changes by the integral over I ^ [a_i, d_i] of
-//     (1 / (N_old + sgn) - 1 / N_old) dt,
-//   * likelihoodDelta adds log(N_old(d_i) + 1) - log(N_new(d_i) + 1) for the events that depart inside I and for
-//     m's own departure (queues.pyx:1220-1232).
-// The breakpoints inside I are a merge of two contiguous ranges of at[] and dt[]; ranks are found by galloping
-// from the moved event's own slots, so no search starts cold.
-// ---------------------------------------------------------------------------------------------
 
 // first index in [lo, hi) whose value is > t, galloping from `hint`
-BQ_HDI int ps_upper(const double *v, int lo, int hi, int hint, double t) {
+BQ_HDI int upper_from(const double *v, int lo, int hi, int hint, double t) {
     if (hint < lo) hint = lo;
     if (hint > hi) hint = hi;
     int l, r;  // invariant: v[l] <= t (or l == lo - 1), v[r] > t (or r == hi)
@@ -256,11 +181,107 @@ BQ_HDI int ps_upper(const double *v, int lo, int hi, int hint, double t) {
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// FIFO queue with k servers: likelihoodDelta(diffListForDeparture(e, x))   (queues.pyx:470-511, 83-95)
+// ---------------------------------------------------------------------------------------------
+template <int KMAX>
+BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, int &steps) {
+    const QInfo &q = c.qi[ev.q0];
+    const QConst &qc = c.qc[ev.q0];
+    const int k = q.k;
+    const double *fi = c.fvec(q, ev.p0);
+    FreeVec<KMAX> M;
+    M.load(fi, k);
+    const double st = dmax(ev.a_e, M.v[0]);
+    const double s_new = x - st;
+    if (s_new < 0.0) return BQ_NEG_INF;
+    const double s_old = ev.x0 - st;
+    double acc = 0.0;
+    if (s_new != s_old) acc = lpdf(qc, s_new) - lpdf(qc, s_old);
+    M.replace_min(x);
+    fi += k;
+    for (int p = ev.p0 + 1; p < q.hi; ++p, fi += k) {
+        if (M.equals(fi, k)) break;  // same free times as before: nothing after p changes
+        ++steps;
+        const double bn = M.v[0], bo = fi[0], di = c.dq[p];
+        if (bn != bo) {
+            const double ai = c.at[p];
+            const double sn = di - dmax(ai, bn);
+            if (sn < 0.0) return BQ_NEG_INF;
+            const double so = di - dmax(ai, bo);
+            if (sn != so) acc += lpdf(qc, sn) - lpdf(qc, so);
+        }
+        M.replace_min(di);
+    }
+    return acc;
+}
+
+// Position e1 (now at p1) will occupy once its arrival is x: before the first OTHER event whose arrival is > x
+// (stable sort by arrival, queues.pyx:537).
+BQ_HDF int new_rank(const Chain &c, const QInfo &q, int p1, double x, double a_old) {
+    if (x >= a_old) {
+        int j = p1;
+        while (j + 1 < q.hi && c.at[j + 1] <= x) ++j;
+        return j;
+    }
+    return upper_from(c.at, q.lo, p1, p1 - 1, x);
+}
+
+// old position of the event that sits at position t once e1 has moved from p1 to j (t != j)
+BQ_HDF int moved_src(int t, int j, int p1) {
+    if (j >= p1) return (t >= p1 && t < j) ? t + 1 : t;
+    return (t > j && t <= p1) ? t - 1 : t;
+}
+
+// likelihoodDelta(diffListForArrival(e1, x))   (queues.pyx:514-591, 83-95)
+template <int KMAX>
+BQ_HDI double ggk_arr_delta(const Chain &c, const EventCtx &ev, double x, int &steps) {
+    const QInfo &q = c.qi[ev.q1];
+    const QConst &qc = c.qc[ev.q1];
+    const int k = q.k, p1 = ev.p1;
+    const double a_old = ev.x0;
+    const int j = new_rank(c, q, p1, x, a_old);
+    const int ps = (j < p1) ? j : p1, pe = (j < p1) ? p1 : j;
+    FreeVec<KMAX> M;
+    M.load(c.fvec(q, ps), k);  // predecessors of position ps are untouched
+    double acc = 0.0;
+    for (int t = ps; t < q.hi; ++t) {
+        double ai, ai_old, di;
+        const double *fo;  // the vector this event saw before the move
+        if (t == j) { ai = x; ai_old = a_old; di = ev.d1; fo = c.fvec(q, p1); }
+        else {
+            const int sp = moved_src(t, j, p1);
+            ai = ai_old = c.at[sp]; di = c.dq[sp]; fo = c.fvec(q, sp);
+            if (t > pe && M.equals(fo, k)) break;
+        }
+        ++steps;
+        const double sn = di - dmax(ai, M.v[0]);
+        if (sn < 0.0) return BQ_NEG_INF;
+        const double so = di - dmax(ai_old, fo[0]);
+        if (sn != so) acc += lpdf(qc, sn) - lpdf(qc, so);
+        M.replace_min(di);
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Processor sharing (QueuePS, queues.pyx:1032-1232): s_i = integral over [a_i, d_i] of dt / N(t), with
+// N(t) = #{a <= t} - #{d <= t} over the queue (cninq.pyx:55-58).  Moving one arrival or departure of event m from
+// t_old to t_new changes N(t) by sgn = +-1 on I = (lo, hi) = (min, max) only, so (diffListForDeparture /
+// diffListForArrival, queues.pyx:1149-1183):
+//   * m itself gains or loses   sgn * integral over I of dt / max(N_old, N_old + sgn),
+//   * every other event i that is in the queue during part of I changes by the integral over I ^ [a_i, d_i] of
+//     (1 / (N_old + sgn) - 1 / N_old) dt,
+//   * likelihoodDelta adds log(N_old(d_i) + 1) - log(N_new(d_i) + 1) for the events that depart inside I and for
+//     m's own departure (queues.pyx:1220-1232).
+// The breakpoints inside I are a merge of two contiguous ranges of at[] and dt[]; ranks are found by galloping
+// from the moved event's own slots, so no search starts cold.
+// ---------------------------------------------------------------------------------------------
 struct PsMove {
-    int q, m, lo_q, hi_q, sgn;
-    int ia, id;     // first arrival / departure strictly after lo
-    int n0;         // N_old just after lo
-    double lo, hi;  // the interval on which N(t) changes
+    int q, pm, dm, lo_q, hi_q, sgn;  // queue, m's arrival position and departure slot
+    int ia, id;                      // first arrival / departure strictly after lo
+    int n0;                          // N_old just after lo
+    double lo, hi;                   // the interval on which N(t) changes
     bool is_dep;
 };
 
@@ -269,13 +290,12 @@ struct PsCursor {
     int ia, id, n;
     double t0;
     BQ_HDF void start(const PsMove &mv) { ia = mv.ia; id = mv.id; n = mv.n0; t0 = mv.lo; }
-    // next piece [t0, t1) with constant N_old = n; returns false after the last piece.  kind: +1 arrival,
-    // -1 departure, 0 end of I at t1; `slot` = index of the breakpoint in its array
-    BQ_HDF bool piece(const Chain &c, const PsMove &mv, double &t1, int &kind, int &slot) const {
+    // next piece [t0, t1) with constant N_old = n.  kind: +1 arrival, -1 departure, 0 end of I at t1;
+    // `slot` = index of the breakpoint in its array
+    BQ_HDF void piece(const Chain &c, const PsMove &mv, double &t1, int &kind, int &slot) const {
         const double ta = (ia < mv.hi_q) ? c.at[ia] : INFINITY, td = (id < mv.hi_q) ? c.dt[id] : INFINITY;
         if (ta <= td) { t1 = ta; kind = 1; slot = ia; } else { t1 = td; kind = -1; slot = id; }
         if (!(t1 < mv.hi)) { t1 = mv.hi; kind = 0; slot = -1; }
-        return true;
     }
     BQ_HDF void advance(double t1, int kind) {
         if (kind > 0) { ++n; ++ia; } else if (kind < 0) { --n; ++id; }
@@ -283,22 +303,22 @@ struct PsCursor {
     }
 };
 
-BQ_HDI void ps_move_setup(const Chain &c, int q, int m, bool is_dep, double t_old, double t_new, PsMove &mv) {
-    mv.q = q; mv.m = m; mv.is_dep = is_dep;
-    mv.lo_q = BQ_LDG(&c.A->q_off[q]); mv.hi_q = BQ_LDG(&c.A->q_off[q + 1]);
+BQ_HDI void ps_move_setup(const Chain &c, int q, int pm, int m, bool is_dep, double t_old, double t_new, PsMove &mv) {
+    const QInfo &qi = c.qi[q];
+    mv.q = q; mv.pm = pm; mv.dm = c.dpos[m]; mv.is_dep = is_dep;
+    mv.lo_q = qi.lo; mv.hi_q = qi.hi;
     mv.lo = (t_new < t_old) ? t_new : t_old;
     mv.hi = (t_new < t_old) ? t_old : t_new;
     // departure later / arrival earlier: m is in the queue longer
     mv.sgn = is_dep ? ((t_new > t_old) ? 1 : -1) : ((t_new < t_old) ? 1 : -1);
-    const int pa = c.pos[m], pd = c.dpos[m];
     // arrivals <= lo: a_m <= lo always (departure moves stay right of a_m; arrival moves: lo = min(a_old, x));
     // departures <= lo: d_m >= lo always, so the rank is at or before m's own departure slot
-    mv.ia = ps_upper(c.at, mv.lo_q, mv.hi_q, pa, mv.lo);
-    mv.id = ps_upper(c.dt, mv.lo_q, mv.hi_q, pd, mv.lo);
+    mv.ia = upper_from(c.at, mv.lo_q, mv.hi_q, pm, mv.lo);
+    mv.id = upper_from(c.dt, mv.lo_q, mv.hi_q, mv.dm, mv.lo);
     mv.n0 = (mv.ia - mv.lo_q) - (mv.id - mv.lo_q);
 }
 
-// change of event i's service: it is in the queue on [b_i, e_i] ^ I; MINE = i is the moved event itself
+// change of an event's service: it is in the queue on [b_i, e_i] ^ I; MINE = it is the moved event itself
 template <bool MINE>
 BQ_HDI double ps_delta_service(const Chain &c, const PsMove &mv, double b_i, double e_i) {
     PsCursor cu;
@@ -319,47 +339,43 @@ BQ_HDI double ps_delta_service(const Chain &c, const PsMove &mv, double b_i, dou
     return MINE ? (double)mv.sgn * acc : acc;
 }
 
-// Visits every event of the queue whose service changes.  COMMIT = false: returns
-// likelihoodDelta (sum of lpdf(s_new) - lpdf(s_old) plus the log N terms).  COMMIT = true: stores the new
-// service times (lane 0) and returns 0.
+// Visits every event of the queue whose service changes.  COMMIT = false: returns likelihoodDelta (sum of
+// lpdf(s_new) - lpdf(s_old) plus the log N terms).  COMMIT = true: stores the new service times (lane 0), returns 0.
 template <bool COMMIT>
 BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, int &steps) {
     const QConst &qc = c.qc[mv.q];
     double acc = 0.0;
-    // the moved event
-    {
+    {   // the moved event
         const double ds = ps_delta_service<true>(c, mv, mv.lo, mv.hi);
-        const double so = c.svc[mv.m];
+        const double so = c.sq[mv.pm];
         double sn = so + ds;
         if (sn < 0.0) sn = 0.0;
-        if (COMMIT) { if (lane == 0) c.svc[mv.m] = sn; }
+        if (COMMIT) { if (lane == 0) c.sq[mv.pm] = sn; }
         else acc += lpdf(qc, sn) - lpdf(qc, so);
     }
     // events in the queue just after lo (other than m): scan back over the arrivals <= lo
     int need = mv.n0 - ((mv.sgn < 0) ? 1 : 0);
     for (int p = mv.ia - 1; p >= mv.lo_q && need > 0; --p) {
-        const int i = c.ord[p];
-        if (i == mv.m) continue;
-        const double di = c.d[i];
+        if (p == mv.pm) continue;
+        const double di = c.dq[p];
         if (!(di > mv.lo)) continue;
         --need; ++steps;
         const double ds = ps_delta_service<false>(c, mv, mv.lo, di);
-        const double so = c.svc[i];
+        const double so = c.sq[p];
         double sn = so + ds;
         if (sn < 0.0) sn = 0.0;
-        if (COMMIT) { if (lane == 0) c.svc[i] = sn; }
+        if (COMMIT) { if (lane == 0) c.sq[p] = sn; }
         else acc += lpdf(qc, sn) - lpdf(qc, so);
     }
     // events that arrive inside I
     for (int p = mv.ia; p < mv.hi_q && c.at[p] < mv.hi; ++p) {
-        const int i = c.ord[p];
-        if (i == mv.m) continue;
+        if (p == mv.pm) continue;
         ++steps;
-        const double ds = ps_delta_service<false>(c, mv, c.at[p], c.d[i]);
-        const double so = c.svc[i];
+        const double ds = ps_delta_service<false>(c, mv, c.at[p], c.dq[p]);
+        const double so = c.sq[p];
         double sn = so + ds;
         if (sn < 0.0) sn = 0.0;
-        if (COMMIT) { if (lane == 0) c.svc[i] = sn; }
+        if (COMMIT) { if (lane == 0) c.sq[p] = sn; }
         else acc += lpdf(qc, sn) - lpdf(qc, so);
     }
     if (COMMIT) return 0.0;
@@ -370,7 +386,7 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, int &ste
         double t1; int kind, slot;
         cu.piece(c, mv, t1, kind, slot);
         if (kind == 0) break;
-        if (kind < 0 && c.dord[slot] != mv.m) acc += log((double)cu.n) - log((double)(cu.n + mv.sgn));
+        if (kind < 0 && slot != mv.dm) acc += log((double)cu.n) - log((double)(cu.n + mv.sgn));
         cu.advance(t1, kind);
     }
     if (mv.is_dep) {
@@ -381,72 +397,20 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, int &ste
     return acc;
 }
 
-// commit: slide m's entry of the sorted array (times v, ids ev, inverse inv) from slot p to its new rank
-template <int W>
-BQ_HDI void ps_reslot(double *v, int *ev, int *inv, int lo_q, int hi_q, int p, int m, double t_new, int lane,
-                      unsigned gmask) {
-    // rank among the other entries: before the first one > t_new
-    int j = ps_upper(v, lo_q, hi_q, p, t_new);  // counts m's own old entry if it is <= t_new
-    if (v[p] <= t_new) --j;                      // ... remove it from the count: j = final slot of m
-    BQ_SYNCG(gmask);
-    if (j > p) {
-        for (int base = p + 1; base <= j; base += W) {
-            const int t = base + lane;
-            int i = -1; double x = 0.0;
-            if (t <= j) { i = ev[t]; x = v[t]; }
-            BQ_SYNCG(gmask);
-            if (i >= 0) { ev[t - 1] = i; v[t - 1] = x; inv[i] = t - 1; }
-            BQ_SYNCG(gmask);
-        }
-    } else if (j < p) {
-        for (int top = p - 1; top >= j; top -= W) {
-            const int t = top - lane;
-            int i = -1; double x = 0.0;
-            if (t >= j) { i = ev[t]; x = v[t]; }
-            BQ_SYNCG(gmask);
-            if (i >= 0) { ev[t + 1] = i; v[t + 1] = x; inv[i] = t + 1; }
-            BQ_SYNCG(gmask);
-        }
-    }
-    if (lane == 0) { ev[j] = m; v[j] = t_new; inv[m] = j; }
-    BQ_SYNCG(gmask);
-}
-
 // ---------------------------------------------------------------------------------------------
 // the conditional of d_e: inner_dfun(x) - lik0   (qnet.pyx:1340-1357)
 // ---------------------------------------------------------------------------------------------
-struct EventCtx {
-    int e, e1, q0, q1, t0, t1;
-    double x0, a_e, d1;
-};
-
-BQ_HDF void event_load(const Chain &c, int e, EventCtx &ev) {
-    const DynArgs &A = *c.A;
-    ev.e = e;
-    ev.q0 = BQ_LDG(&A.ev_q[e]);
-    ev.e1 = BQ_LDG(&A.ev_nt[e]);
-    ev.t0 = BQ_LDG(&A.q_type[ev.q0]);
-    ev.x0 = c.d[e];
-    ev.a_e = c.arr(e);
-    ev.q1 = -1; ev.t1 = -1; ev.d1 = 0.0;
-    if (ev.e1 >= 0) {
-        ev.q1 = BQ_LDG(&A.ev_q[ev.e1]);
-        ev.t1 = BQ_LDG(&A.q_type[ev.q1]);
-        ev.d1 = c.d[ev.e1];
-    }
-}
-
 template <int KMAX>
 BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, int &steps) {
     double g;
     if (ev.t0 == Q_GGK) {
-        g = ggk_dep_delta<KMAX>(c, ev.e, ev.q0, x, ev.a_e, ev.x0, steps);
+        g = ggk_dep_delta<KMAX>(c, ev, x, steps);
     } else if (ev.t0 == Q_PS) {
         if (x < ev.a_e) return BQ_NEG_INF;
         g = 0.0;
         if (x != ev.x0) {
             PsMove mv;
-            ps_move_setup(c, ev.q0, ev.e, true, ev.x0, x, mv);
+            ps_move_setup(c, ev.q0, ev.p0, ev.e, true, ev.x0, x, mv);
             g = ps_apply_move<false>(c, mv, 0, steps);
         }
     } else {  // DelayStation: s = d - a, single-event diff list (queues.pyx:745-784)
@@ -457,13 +421,13 @@ BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, int &ste
     if (!(g > BQ_NEG_INF) || ev.e1 < 0) return g;
     double g1;
     if (ev.t1 == Q_GGK) {
-        g1 = ggk_arr_delta<KMAX>(c, ev.e1, ev.q1, x, ev.x0, steps);
+        g1 = ggk_arr_delta<KMAX>(c, ev, x, steps);
     } else if (ev.t1 == Q_PS) {
         if (x > ev.d1) return BQ_NEG_INF;
         g1 = 0.0;
         if (x != ev.x0) {
             PsMove mv;
-            ps_move_setup(c, ev.q1, ev.e1, false, ev.x0, x, mv);
+            ps_move_setup(c, ev.q1, ev.p1, ev.e1, false, ev.x0, x, mv);
             g1 = ps_apply_move<false>(c, mv, 0, steps);
         }
     } else {
@@ -500,7 +464,7 @@ BQ_HDI void mh_setup(const Chain &c, const EventCtx &ev, MhProp &pr) {
     pr.c0 = &c.qc[ev.q0];
     pr.c1 = pr.c0;
     pr.b0 = ev.a_e;
-    if (ev.t0 == Q_GGK) pr.b0 = dmax(ev.a_e, c.F[BQ_LDG(&c.A->ev_f[ev.e])]);
+    if (ev.t0 == Q_GGK) pr.b0 = dmax(ev.a_e, c.fvec(c.qi[ev.q0], ev.p0)[0]);
     pr.Lh = pr.b0;
     pr.Uh = INFINITY;
     pr.has1 = (ev.e1 >= 0);
@@ -510,7 +474,7 @@ BQ_HDI void mh_setup(const Chain &c, const EventCtx &ev, MhProp &pr) {
         pr.d1 = ev.d1;
         pr.Uh = ev.d1;
         if (pr.Lh < 0.0) pr.Lh = 0.0;
-        if (ev.t1 == Q_GGK) { pr.fifo1 = 1; pr.dp1 = c.F[BQ_LDG(&c.A->ev_f[ev.e1])]; }
+        if (ev.t1 == Q_GGK) { pr.fifo1 = 1; pr.dp1 = c.fvec(c.qi[ev.q1], ev.p1)[0]; }
     }
 }
 
@@ -555,96 +519,128 @@ BQ_HDI double slice_stepout_seq(const G &g, double x0, double lower, double uppe
 
 // ---------------------------------------------------------------------------------------------
 // commit d_e := x   (apply_departure, qnet.pyx:2166-2178 -> applyDiffList, arrivals.pyx:542-604)
-// Executed by every lane of the group with identical control flow; lane 0 stores.
+// Executed by every lane of the group with identical control flow; lane 0 stores, the shifts are spread over lanes.
 // ---------------------------------------------------------------------------------------------
+
+// Slide the entry at slot p of a sorted time array to slot j (its rank under the new time), carrying the parallel
+// arrays along: ids ev[] with inverse inv[], and up to two payload arrays (may be null).
+template <int W>
+BQ_HDI void reslot(double *v, int *ev, int *inv, double *pay0, double *pay1, int p, int j, double t_new, int lane,
+                   unsigned gmask) {
+    const int m = ev[p];
+    const double m0 = pay0 ? pay0[p] : 0.0, m1 = pay1 ? pay1[p] : 0.0;
+    BQ_SYNCG(gmask);
+    if (j > p) {  // later: entries p+1..j move one slot towards the head
+        for (int base = p + 1; base <= j; base += W) {
+            const int t = base + lane;
+            int i = -1; double x = 0.0, y0 = 0.0, y1 = 0.0;
+            if (t <= j) { i = ev[t]; x = v[t]; if (pay0) y0 = pay0[t]; if (pay1) y1 = pay1[t]; }
+            BQ_SYNCG(gmask);
+            if (i >= 0) { ev[t - 1] = i; v[t - 1] = x; inv[i] = t - 1; if (pay0) pay0[t - 1] = y0; if (pay1) pay1[t - 1] = y1; }
+            BQ_SYNCG(gmask);
+        }
+    } else if (j < p) {  // earlier: entries j..p-1 move one slot towards the tail
+        for (int top = p - 1; top >= j; top -= W) {
+            const int t = top - lane;
+            int i = -1; double x = 0.0, y0 = 0.0, y1 = 0.0;
+            if (t >= j) { i = ev[t]; x = v[t]; if (pay0) y0 = pay0[t]; if (pay1) y1 = pay1[t]; }
+            BQ_SYNCG(gmask);
+            if (i >= 0) { ev[t + 1] = i; v[t + 1] = x; inv[i] = t + 1; if (pay0) pay0[t + 1] = y0; if (pay1) pay1[t + 1] = y1; }
+            BQ_SYNCG(gmask);
+        }
+    }
+    if (lane == 0) { ev[j] = m; v[j] = t_new; inv[m] = j; if (pay0) pay0[j] = m0; if (pay1) pay1[j] = m1; }
+    BQ_SYNCG(gmask);
+}
+
 template <int W, int KMAX>
 BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, unsigned gmask) {
-    const DynArgs &A = *c.A;
-    // where e1 goes is decided on the old state (its own arrival is still x0 in memory)
-    int j1 = 0, p1 = 0, lo1 = 0, end1 = 0, k1 = 0;
-    if (ev.e1 >= 0 && ev.t1 == Q_GGK) {
-        lo1 = BQ_LDG(&A.q_off[ev.q1]); end1 = BQ_LDG(&A.q_off[ev.q1 + 1]); k1 = BQ_LDG(&A.q_k[ev.q1]);
-        p1 = c.pos[ev.e1];
-        j1 = ggk_new_rank(c, ev.e1, lo1, end1, p1, x, ev.x0);
+    // ---- everything that is computed on the old state first ------------------------------------------------
+    int j1 = ev.p1;
+    if (ev.e1 >= 0 && ev.t1 != Q_DELAY) {
+        const QInfo &q1 = c.qi[ev.q1];
+        if (ev.t1 == Q_GGK) j1 = new_rank(c, q1, ev.p1, x, ev.x0);
+        else {  // PS: rank among the other arrivals
+            j1 = upper_from(c.at, q1.lo, q1.hi, ev.p1, x);
+            if (c.at[ev.p1] <= x) --j1;
+        }
     }
-    // ---- departure side: refresh the free-time vectors downstream of e ----------------------------------
-    if (ev.t0 == Q_GGK) {
-        const int k = BQ_LDG(&A.q_k[ev.q0]);
+    int dummy = 0;
+    if (ev.t0 == Q_PS) {  // new service times of everything that overlaps the moved interval
+        PsMove mv;
+        ps_move_setup(c, ev.q0, ev.p0, ev.e, true, ev.x0, x, mv);
+        ps_apply_move<true>(c, mv, lane, dummy);
+    }
+    if (ev.e1 >= 0 && ev.t1 == Q_PS) {
+        PsMove mv;
+        ps_move_setup(c, ev.q1, ev.p1, ev.e1, false, ev.x0, x, mv);
+        ps_apply_move<true>(c, mv, lane, dummy);
+    }
+    // ---- departure side --------------------------------------------------------------------------------------
+    if (ev.t0 == Q_GGK) {  // refresh the free-time vectors downstream of e
+        const QInfo &q = c.qi[ev.q0];
+        const int k = q.k;
+        double *fi = c.fvec(q, ev.p0);
         FreeVec<KMAX> M;
-        M.load(c.F + BQ_LDG(&A.ev_f[ev.e]), k);
+        M.load(fi, k);
         M.replace_min(x);
-        const int end = BQ_LDG(&A.q_off[ev.q0 + 1]);
-        for (int p = c.pos[ev.e] + 1; p < end; ++p) {
-            const int i = c.ord[p];
-            double *fi = c.F + BQ_LDG(&A.ev_f[i]);
+        fi += k;
+        for (int p = ev.p0 + 1; p < q.hi; ++p, fi += k) {
             if (M.equals(fi, k)) break;
-            const double di = c.d[i];
+            const double di = c.dq[p];
             BQ_SYNCG(gmask);
             if (lane == 0) M.store(fi, k);
             M.replace_min(di);
         }
     }
-    // PS: new service times of everything that overlaps the moved interval, computed on the old arrays
-    int dummy = 0;
-    if (ev.t0 == Q_PS) {
-        PsMove mv;
-        ps_move_setup(c, ev.q0, ev.e, true, ev.x0, x, mv);
-        ps_apply_move<true>(c, mv, lane, dummy);
+    BQ_SYNCG(gmask);
+    if (ev.t0 == Q_PS) {  // the departure changes rank among the queue's sorted departures
+        const QInfo &q = c.qi[ev.q0];
+        const int pd = c.dpos[ev.e];
+        int j = upper_from(c.dt, q.lo, q.hi, pd, x);
+        if (c.dt[pd] <= x) --j;
+        reslot<W>(c.dt, c.dord, c.dpos, nullptr, nullptr, pd, j, x, lane, gmask);
     }
-    if (ev.e1 >= 0 && ev.t1 == Q_PS) {
-        PsMove mv;
-        ps_move_setup(c, ev.q1, ev.e1, false, ev.x0, x, mv);
-        ps_apply_move<true>(c, mv, lane, dummy);
-    }
+    if (lane == 0) { c.d[ev.e] = x; c.dq[ev.p0] = x; }
     BQ_SYNCG(gmask);
-    if (ev.t0 == Q_PS)
-        ps_reslot<W>(c.dt, c.dord, c.dpos, BQ_LDG(&A.q_off[ev.q0]), BQ_LDG(&A.q_off[ev.q0 + 1]), c.dpos[ev.e], ev.e, x,
-                     lane, gmask);
-    if (ev.e1 >= 0 && ev.t1 == Q_PS)
-        ps_reslot<W>(c.at, c.ord, c.pos, BQ_LDG(&A.q_off[ev.q1]), BQ_LDG(&A.q_off[ev.q1 + 1]), c.pos[ev.e1], ev.e1, x,
-                     lane, gmask);
-    BQ_SYNCG(gmask);
-    if (lane == 0) c.d[ev.e] = x;
-    BQ_SYNCG(gmask);
-    // ---- arrival side: re-rank e1, refresh the vectors from the first changed index ------------------------
-    if (ev.e1 >= 0 && ev.t1 == Q_GGK) {
+    // ---- arrival side ------------------------------------------------------------------------------------------
+    if (ev.e1 < 0) return;
+    if (ev.t1 == Q_GGK) {  // refresh the vectors from the first changed position, then re-rank e1
+        const QInfo &q = c.qi[ev.q1];
+        const int k = q.k, p1 = ev.p1;
         const int ps = (j1 < p1) ? j1 : p1, pe = (j1 < p1) ? p1 : j1;
         FreeVec<KMAX> M;
-        M.load(c.F + BQ_LDG(&A.ev_f[c.ord[ps]]), k1);
-        for (int t = ps; t < end1; ++t) {
-            const int i = ggk_moved_at(c, t, j1, p1, ev.e1);
-            double *fi = c.F + BQ_LDG(&A.ev_f[i]);
-            if (t > pe && M.equals(fi, k1)) break;
-            const double di = c.d[i];
+        M.load(c.fvec(q, ps), k);
+        for (int t = ps; t < q.hi; ++t) {
+            double di;
+            if (t == j1) di = ev.d1;
+            else {
+                const int sp = moved_src(t, j1, p1);
+                di = c.dq[sp];
+                if (t > pe && M.equals(c.fvec(q, sp), k)) break;
+            }
             BQ_SYNCG(gmask);
-            if (lane == 0) M.store(fi, k1);
+            if (lane == 0) M.store(c.fvec(q, t), k);
             M.replace_min(di);
         }
         BQ_SYNCG(gmask);
-        if (j1 > p1) {  // later: events p1+1..j1 move one slot towards the head
-            for (int base = p1 + 1; base <= j1; base += W) {
-                const int t = base + lane;
-                int i = -1;
-                if (t <= j1) i = c.ord[t];
-                BQ_SYNCG(gmask);
-                if (i >= 0) { c.ord[t - 1] = i; c.pos[i] = t - 1; }
-                BQ_SYNCG(gmask);
-            }
-        } else if (j1 < p1) {  // earlier: events j1..p1-1 move one slot towards the tail
-            for (int top = p1 - 1; top >= j1; top -= W) {
-                const int t = top - lane;
-                int i = -1;
-                if (t >= j1) i = c.ord[t];
-                BQ_SYNCG(gmask);
-                if (i >= 0) { c.ord[t + 1] = i; c.pos[i] = t + 1; }
-                BQ_SYNCG(gmask);
-            }
-        }
-        if (j1 != p1 && lane == 0) { c.ord[j1] = ev.e1; c.pos[ev.e1] = j1; }
+        reslot<W>(c.at, c.ord, c.pos, c.dq, nullptr, p1, j1, x, lane, gmask);
+    } else if (ev.t1 == Q_PS) {
+        reslot<W>(c.at, c.ord, c.pos, c.dq, c.sq, ev.p1, j1, x, lane, gmask);
+    } else {
+        if (lane == 0) c.at[ev.p1] = x;
         BQ_SYNCG(gmask);
     }
 }
 
+// service time of the event at position p of queue q in the current state
+BQ_HDF double dyn_service(const Chain &c, const QInfo &q, int p) {
+    if (q.type == Q_GGK) return c.dq[p] - dmax(c.at[p], c.fvec(q, p)[0]);
+    if (q.type == Q_DELAY) return c.dq[p] - c.at[p];
+    return c.sq[p];
+}
+
+#if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------------
 // group-wide helpers
 // ---------------------------------------------------------------------------------------------
@@ -661,26 +657,18 @@ __device__ __forceinline__ double group_max(double x, unsigned gmask) {
     return x;
 }
 
-// service time of event i of queue q (type t) in the current state
-BQ_HDF double dyn_service(const Chain &c, int i, int t, double ai) {
-    if (t == Q_GGK) return c.d[i] - dmax(ai, c.F[BQ_LDG(&c.A->ev_f[i])]);
-    if (t == Q_DELAY) return c.d[i] - ai;
-    return c.svc[i];
-}
-
 // per-queue sufficient statistics of one chain (queues.pyx:1316-1336), every lane returns with ss[] filled
 template <int W>
-__device__ void dyn_suffstats(const Chain &c, SuffStat *ss, int lane, unsigned gmask, bool want_logp, double *logp_out) {
-    const DynArgs &A = *c.A;
+__device__ void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, int lane, unsigned gmask, bool want_logp,
+                              double *logp_out) {
     double logp_acc = 0.0;
-    for (int q = 0; q < A.Q; ++q) {
-        const int lo = __ldg(&A.q_off[q]), hi = __ldg(&A.q_off[q + 1]);
-        const int t = __ldg(&A.q_type[q]), dist = __ldg(&A.q_dist[q]);
+    for (int q = 0; q < Q; ++q) {
+        const QInfo &qi = c.qi[q];
+        const int dist = qi.dist;
         double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // n, sum, sumlog, nlog, wait, nzero, logp, bad
-        for (int p = lo + lane; p < hi; p += W) {
-            const int i = c.ord[p];
-            const double ai = c.arr(i), s = dyn_service(c, i, t, ai);
-            const double w = c.d[i] - ai - s;
+        for (int p = qi.lo + lane; p < qi.hi; p += W) {
+            const double s = dyn_service(c, qi, p);
+            const double w = c.dq[p] - c.at[p] - s;
             v[4] += (w > 0.0) ? w : 0.0;
             if (s > 0.0) {
                 v[0] += 1.0; v[1] += s;
@@ -697,9 +685,8 @@ __device__ void dyn_suffstats(const Chain &c, SuffStat *ss, int lane, unsigned g
         double sq = 0.0;
         if (dist == D_LOGNORMAL) {  // second pass, as distributions.pyx:276-299
             const double mean_log = (v[3] > 0.0) ? v[2] / v[3] : 0.0;
-            for (int p = lo + lane; p < hi; p += W) {
-                const int i = c.ord[p];
-                const double s = dyn_service(c, i, t, c.arr(i));
+            for (int p = qi.lo + lane; p < qi.hi; p += W) {
+                const double s = dyn_service(c, qi, p);
                 if (s >= 1e-50) { const double z = log(s) - mean_log; sq += z * z; }
             }
             sq = group_sum<W>(sq, gmask);
@@ -707,7 +694,7 @@ __device__ void dyn_suffstats(const Chain &c, SuffStat *ss, int lane, unsigned g
         if (lane == 0) {
             SuffStat &o = ss[q];
             o.n = v[0]; o.sum = v[1]; o.sumlog = v[2]; o.nlog = v[3]; o.wait = v[4]; o.nzero = v[5];
-            o.nall = (double)(hi - lo); o.sumsq = sq;
+            o.nall = (double)(qi.hi - qi.lo); o.sumsq = sq;
         }
         logp_acc += (v[7] > 0.0) ? BQ_NEG_INF : v[6];
     }
@@ -769,7 +756,7 @@ __device__ __forceinline__ bool group_slice(const G &g, double x0, double lower,
 
 // One MH-within-Gibbs update of d_e (gibbs_resample_pair / gibbs_resample_final, qnet.pyx:382-498).
 // Streams of (chain, sweep, event): TAG_MH and TAG_MH2 feed the two slice steps on the proposal, TAG_MH_AUX holds the
-// accept uniform (number 0) and the re-initialisation draws (numbers 1..25).
+// accept uniform (number 0) and the re-initialisation draws (numbers 2..).
 template <int W, int KMAX>
 __device__ void mh_update(const Chain &c, const EventCtx &ev, const DynArgs &A, unsigned long long gchain,
                           unsigned int gsw, const GroupLane &gl, long long &n_ev, long long &n_evals, long long &n_stuck,
@@ -822,9 +809,23 @@ __device__ void mh_update(const Chain &c, const EventCtx &ev, const DynArgs &A, 
 // the sweep kernel
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t dyn_group_smem(int Q, int P) {
-    size_t b = (size_t)Q * (sizeof(QConst) + sizeof(SuffStat)) + (size_t)((P + 1) & ~1) * sizeof(double);
+    size_t b = (size_t)Q * (sizeof(QConst) + sizeof(SuffStat) + sizeof(QInfo)) + (size_t)((P + 1) & ~1) * sizeof(double);
     return (b + 15) & ~(size_t)15;
 }
+
+// the group's slice of shared memory: [QConst Q][SuffStat Q][theta P (padded to even)][QInfo Q]
+struct GroupSmem {
+    QConst *qc;
+    SuffStat *ss;
+    double *th;
+    QInfo *qi;
+    __device__ __forceinline__ void carve(unsigned char *base, int Q, int P) {
+        qc = reinterpret_cast<QConst *>(base);
+        ss = reinterpret_cast<SuffStat *>(qc + Q);
+        th = reinterpret_cast<double *>(ss + Q);
+        qi = reinterpret_cast<QInfo *>(th + ((P + 1) & ~1));
+    }
+};
 
 template <int W, int KMAX>
 __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
@@ -837,37 +838,45 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
     const unsigned gbits = (W == 32) ? 0xffffffffu : ((1u << W) - 1u);
     const unsigned gmask = gbits << gshift;
     const GroupLane gl = {lane, gmask, gshift, gbits};
-    unsigned char *base = smem_raw + (size_t)gib * dyn_group_smem(A.Q, A.P);
-    QConst *qc = reinterpret_cast<QConst *>(base);
-    SuffStat *ss = reinterpret_cast<SuffStat *>(qc + A.Q);
-    double *th = reinterpret_cast<double *>(ss + A.Q);
+    GroupSmem sm;
+    sm.carve(smem_raw + (size_t)gib * dyn_group_smem(A.Q, A.P), A.Q, A.P);
+    QConst *qc = sm.qc;
+    SuffStat *ss = sm.ss;
+    double *th = sm.th;
     const int Q = A.Q, P = A.P, E = A.E;
 
-    Chain c;
-    c.bind(A, chain, qc);
     for (int i = lane; i < P; i += W) th[i] = A.theta[(size_t)chain * P + i];
+    for (int q = lane; q < Q; q += W) sm.qi[q] = A.qinfo[q];
     __syncwarp(gmask);
     for (int q = lane; q < Q; q += W) {
-        const int o = __ldg(&A.q_poff[q]), dist = __ldg(&A.q_dist[q]);
+        const int o = __ldg(&A.q_poff[q]), dist = sm.qi[q].dist;
         qconst_set(qc[q], dist, th[o], (dist == D_EXP) ? 0.0 : th[o + 1]);
     }
     __syncwarp(gmask);
+    Chain c;
+    c.bind(A, chain, sm.qi, qc);
 
     const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain);
     long long n_ev = 0, n_evals = 0, n_stuck = 0, n_pevals = 0, n_steps = 0, n_reject = 0;
     double tmax = 0.0;
+    const int4 *order4 = reinterpret_cast<const int4 *>(A.order);
 
     for (int sw = 0; sw < A.n_sweeps; ++sw) {
         const unsigned int gsw = A.sweep_base + (unsigned int)sw;
         if (sw == 0 || (A.flags & FLAG_TMAX_PER_SWEEP)) {  // Tmax = 2 max d   (qnet.pyx:672)
             double m = 0.0;
-            for (int i = lane; i < E; i += W) m = fmax(m, c.d[i]);
+            for (int i = lane; i < E; i += W) m = fmax(m, c.dq[i]);
             tmax = 2.0 * group_max<W>(m, gmask);
         }
         const int n_order = (A.flags & FLAG_PARAMS_ONLY) ? 0 : A.n_order;
+        int4 rec_next = make_int4(0, -1, 0, 0);
+        if (n_order > 0) rec_next = __ldg(&order4[0]);
         for (int idx = 0; idx < n_order; ++idx) {
+            const int4 r4 = rec_next;
+            if (idx + 1 < n_order) rec_next = __ldg(&order4[idx + 1]);  // the next record is in flight during this event
+            const DynRec rec = {r4.x, r4.y, r4.z, r4.w};
             EventCtx ev;
-            event_load(c, __ldg(&A.order[idx]), ev);
+            event_load(c, rec, ev);
             int steps = 0;
             if (A.mode == MODE_MH) {
                 mh_update<W, KMAX>(c, ev, A, gchain, gsw, gl, n_ev, n_evals, n_stuck, n_reject, steps);
@@ -890,7 +899,7 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
         const bool trace = (A.flags & FLAG_TRACE) != 0;
         if (A.update != UPD_NONE || trace) {
             double logp = 0.0;
-            dyn_suffstats<W>(c, ss, lane, gmask, trace, &logp);
+            dyn_suffstats<W>(c, Q, ss, lane, gmask, trace, &logp);
             const size_t recno = (size_t)(A.trace_base + sw);
             if (trace) {
                 for (int q = lane; q < Q; q += W)
@@ -899,7 +908,7 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
             }
             if (A.update != UPD_NONE) {
                 for (int q = lane; q < Q; q += W) {
-                    const int o = __ldg(&A.q_poff[q]), dist = __ldg(&A.q_dist[q]);
+                    const int o = __ldg(&A.q_poff[q]), dist = sm.qi[q].dist;
                     double p0 = th[o], p1 = (dist == D_EXP) ? 0.0 : th[o + 1];
                     if (A.update == UPD_BAYES) {
                         Rng prng;
@@ -928,22 +937,25 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
 
 // ---- parity / reporting kernels ---------------------------------------------------------------
 
-// out[j] = inner_dfun(x[j]) - lik0 for event e of one chain (qnet.pyx:1340-1357); one warp
+// out[j] = inner_dfun(x[j]) - lik0 for the event of `rec` on one chain (qnet.pyx:1340-1357); one warp.
 // what = 1: the MH proposal log-density h(x[j]) instead (queues.pyx:1239-1256)
 template <int KMAX>
-__global__ void logcond_dynamic_kernel(const DynArgs A, int chain, int e, const double *x, int n, double *out, int what) {
+__global__ void logcond_dynamic_kernel(const DynArgs A, int chain, DynRec rec, const double *x, int n, double *out,
+                                       int what) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    QConst *qc = reinterpret_cast<QConst *>(smem_raw);
+    GroupSmem sm;
+    sm.carve(smem_raw, A.Q, A.P);
     const double *th = A.theta + (size_t)chain * A.P;
     for (int q = threadIdx.x; q < A.Q; q += blockDim.x) {
-        const int o = A.q_poff[q], dist = A.q_dist[q];
-        qconst_set(qc[q], dist, th[o], dist == D_EXP ? 0.0 : th[o + 1]);
+        sm.qi[q] = A.qinfo[q];
+        const int o = A.q_poff[q], dist = A.qinfo[q].dist;
+        qconst_set(sm.qc[q], dist, th[o], dist == D_EXP ? 0.0 : th[o + 1]);
     }
     __syncthreads();
     Chain c;
-    c.bind(A, chain, qc);
+    c.bind(A, chain, sm.qi, sm.qc);
     EventCtx ev;
-    event_load(c, e, ev);
+    event_load(c, rec, ev);
     int steps = 0;
     if (what == 1) {
         MhProp pr;
@@ -961,46 +973,52 @@ __global__ void __launch_bounds__(128) report_dynamic_kernel(const DynArgs A, do
     const int gib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chain = blockIdx.x * (blockDim.x >> 5) + gib;
     if (chain >= A.n_chains) return;
-    unsigned char *base = smem_raw + (size_t)gib * dyn_group_smem(A.Q, A.P);
-    QConst *qc = reinterpret_cast<QConst *>(base);
-    SuffStat *ss = reinterpret_cast<SuffStat *>(qc + A.Q);
+    GroupSmem sm;
+    sm.carve(smem_raw + (size_t)gib * dyn_group_smem(A.Q, A.P), A.Q, A.P);
     const double *th = A.theta + (size_t)chain * A.P;
     for (int q = lane; q < A.Q; q += 32) {
-        const int o = A.q_poff[q], dist = A.q_dist[q];
-        qconst_set(qc[q], dist, th[o], dist == D_EXP ? 0.0 : th[o + 1]);
+        sm.qi[q] = A.qinfo[q];
+        const int o = A.q_poff[q], dist = A.qinfo[q].dist;
+        qconst_set(sm.qc[q], dist, th[o], dist == D_EXP ? 0.0 : th[o + 1]);
     }
     __syncwarp();
     Chain c;
-    c.bind(A, chain, qc);
+    c.bind(A, chain, sm.qi, sm.qc);
     double logp = 0.0;
-    dyn_suffstats<32>(c, ss, lane, 0xffffffffu, true, &logp);
+    dyn_suffstats<32>(c, A.Q, sm.ss, lane, 0xffffffffu, true, &logp);
     if (lane == 0 && logp_out) logp_out[chain] = logp;
     if (ss_out)
         for (int i = lane; i < A.Q * 8; i += 32)
-            ss_out[(size_t)chain * A.Q * 8 + i] = reinterpret_cast<double *>(ss)[i];
+            ss_out[(size_t)chain * A.Q * 8 + i] = reinterpret_cast<double *>(sm.ss)[i];
 }
 
-// Free-time vectors of every FIFO queue from the departure times and the current queue order; one thread per
-// (chain, queue), sequential along the queue (queues.pyx:654-680).  Used when a static-order handle switches to the
-// dynamic-order kernels (MH sweeps) after slice sweeps have moved the departure times.
+// Position-indexed times and free-time vectors of every queue from the departure times by event and the current
+// queue order; one thread per (chain, queue), sequential along the queue (queues.pyx:654-680).  Used when a
+// static-order handle enters the dynamic-order kernels (MH sweeps) after slice sweeps have moved the departures.
 template <int KMAX>
-__global__ void rebuild_free_times_kernel(const DynArgs A) {
+__global__ void rebuild_positions_kernel(const DynArgs A, const int *ev_pt) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)A.n_chains * A.Q) return;
     const int chain = (int)(t / A.Q), q = (int)(t % A.Q);
-    if (A.q_type[q] != Q_GGK) return;
-    const int k = A.q_k[q];
+    const QInfo qi = A.qinfo[q];
     const double *d = A.state + (size_t)chain * A.E;
     const int *ord = A.ord + (size_t)chain * A.E;
-    double *F = A.F + (size_t)chain * A.EF;
+    double *at = A.at + (size_t)chain * A.E, *dq = A.dq + (size_t)chain * A.E;
+    double *F = A.F + (size_t)chain * A.EF + qi.foff;
     FreeVec<KMAX> M;
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j) M.v[j] = (j < k) ? 0.0 : INFINITY;
-    for (int p = A.q_off[q]; p < A.q_off[q + 1]; ++p) {
-        const int i = ord[p];
-        M.store(F + A.ev_f[i], k);
-        M.replace_min(d[i]);
+    for (int j = 0; j < KMAX; ++j) M.v[j] = (j < qi.k) ? 0.0 : INFINITY;
+    for (int p = qi.lo; p < qi.hi; ++p) {
+        const int i = ord[p], pt = ev_pt[i];
+        const double di = d[i];
+        dq[p] = di;
+        at[p] = (pt >= 0) ? d[pt] : 0.0;
+        if (qi.type == Q_GGK) {
+            M.store(F + (size_t)(p - qi.lo) * qi.k, qi.k);
+            M.replace_min(di);
+        }
     }
 }
+#endif  // __CUDACC__
 
 }  // namespace bq

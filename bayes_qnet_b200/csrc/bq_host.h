@@ -1,9 +1,10 @@
 // Host-side construction of one chain's derived arrays for the dynamic-order kernels (bq_dynamic.cuh): queue
-// orders, free-time vectors, and the Event fields the reference carries (a, s, proc, by-queue links).  Used by
-// the library at create / set_state / get_state time and by the test harness under tests/emul.
+// orders, position-indexed times and free-time vectors, and the Event fields the reference carries (a, s, proc,
+// by-queue links).  Used by the library at create / set_state / get_state time and by the test harness under
+// tests/emul.
 #pragma once
-#include <stdint.h>
 #include <math.h>
+#include <stdint.h>
 #include <string.h>
 
 #include <algorithm>
@@ -13,8 +14,16 @@ namespace bq {
 
 struct HostNet {
     int E, Q;
-    const int *q_type, *q_k, *q_off;  // [Q], [Q], [Q+1]
-    const int *ev_f, *prev_byt;       // [E]
+    const int *q_type, *q_k, *q_off, *q_foff;  // [Q], [Q], [Q+1], [Q]: discipline, servers, position ranges, F offsets
+    const int *prev_byt;                       // [E]
+};
+
+// one chain's position-indexed arrays (at, dq: all queues; F: FIFO queues; dt, sq, dord, dpos: PS queues, may be null)
+struct HostChain {
+    int *ord, *pos;
+    double *at, *dq, *F;
+    double *dt, *sq;
+    int *dord, *dpos;
 };
 
 static inline void fv_replace_min(double *v, int k, double x) {
@@ -23,14 +32,8 @@ static inline void fv_replace_min(double *v, int k, double x) {
         if (v[j] > v[j + 1]) std::swap(v[j], v[j + 1]);
 }
 
-// ord: the events of each queue (ranges h->q_off) in queue order.  With `resort`, FIFO and PS queues are first
-// re-ranked by (arrival, departure) -- queue 0, whose arrivals are all 0, thereby by departure
-// (arrivals.pyx:256).  Fills pos and the free-time vectors F (queues.pyx:654-680 as a sorted multiset).
-// PS queues additionally get their sorted arrival / departure times (at, dt), the departure order (dord, dpos)
-// and the service times from the definition (queues.pyx:1049-1070); those pointers may be null otherwise.
-struct HostPs { double *at, *dt, *svc; int *dord, *dpos; };
-
-// s = integral over [a, d] of dt / N(t) on the queue's sorted arrival / departure times (n of each)
+// s = integral over [a, d] of dt / N(t) on a PS queue's sorted arrival / departure times (n of each;
+// queues.pyx:1049-1070)
 static double host_ps_service(const double *at, const double *dt, int n, double a, double d) {
     int ia = (int)(std::upper_bound(at, at + n, a) - at), id = (int)(std::upper_bound(dt, dt + n, a) - dt);
     int cnt = ia - id;
@@ -48,43 +51,48 @@ static double host_ps_service(const double *at, const double *dt, int n, double 
     return s;
 }
 
-static void host_rebuild(const HostNet *h, const double *d, int *ord, int *pos, double *F, bool resort,
-                         const HostPs *ps = nullptr) {
+// c.ord holds the events of each queue (ranges h->q_off) in queue order.  With `resort`, FIFO and PS queues are
+// first re-ranked by (arrival, departure) -- queue 0, whose arrivals are all 0, thereby by departure
+// (arrivals.pyx:256).  Fills every other array of the chain.
+static void host_rebuild(const HostNet *h, const double *d, const HostChain &c, bool resort) {
     auto arr = [&](int i) { int pt = h->prev_byt[i]; return pt >= 0 ? d[pt] : 0.0; };
     std::vector<double> M;
     for (int q = 0; q < h->Q; ++q) {
-        const int lo = h->q_off[q], hi = h->q_off[q + 1];
-        if (resort && h->q_type[q] != 1 /* Q_DELAY */)
-            std::stable_sort(ord + lo, ord + hi, [&](int x, int y) {
+        const int lo = h->q_off[q], hi = h->q_off[q + 1], type = h->q_type[q];
+        if (resort && type != 1 /* Q_DELAY */)
+            std::stable_sort(c.ord + lo, c.ord + hi, [&](int x, int y) {
                 const double ax = arr(x), ay = arr(y);
                 if (ax != ay) return ax < ay;
                 return d[x] < d[y];
             });
-        for (int p = lo; p < hi; ++p) pos[ord[p]] = p;
-        if (h->q_type[q] == 0 /* Q_GGK */) {
+        for (int p = lo; p < hi; ++p) {
+            const int i = c.ord[p];
+            c.pos[i] = p;
+            c.at[p] = arr(i);
+            c.dq[p] = d[i];
+        }
+        if (type == 0 /* Q_GGK */) {  // free-time vectors (queues.pyx:654-680 as a sorted multiset)
             const int k = h->q_k[q];
             M.assign(k, 0.0);
             for (int p = lo; p < hi; ++p) {
-                const int i = ord[p];
-                memcpy(F + h->ev_f[i], M.data(), k * sizeof(double));
-                fv_replace_min(M.data(), k, d[i]);
+                memcpy(c.F + h->q_foff[q] + (size_t)(p - lo) * k, M.data(), k * sizeof(double));
+                fv_replace_min(M.data(), k, c.dq[p]);
             }
         }
-        if (h->q_type[q] == 2 /* Q_PS */ && ps) {
-            for (int p = lo; p < hi; ++p) { ps->at[p] = arr(ord[p]); ps->dord[p] = ord[p]; }
-            std::stable_sort(ps->dord + lo, ps->dord + hi, [&](int x, int y) { return d[x] < d[y]; });
-            for (int p = lo; p < hi; ++p) { ps->dt[p] = d[ps->dord[p]]; ps->dpos[ps->dord[p]] = p; }
-            for (int p = lo; p < hi; ++p)
-                ps->svc[ord[p]] = host_ps_service(ps->at + lo, ps->dt + lo, hi - lo, ps->at[p], d[ord[p]]);
+        if (type == 2 /* Q_PS */ && c.dt) {
+            for (int p = lo; p < hi; ++p) c.dord[p] = c.ord[p];
+            std::stable_sort(c.dord + lo, c.dord + hi, [&](int x, int y) { return d[x] < d[y]; });
+            for (int p = lo; p < hi; ++p) { c.dt[p] = d[c.dord[p]]; c.dpos[c.dord[p]] = p; }
+            for (int p = lo; p < hi; ++p) c.sq[p] = host_ps_service(c.at + lo, c.dt + lo, hi - lo, c.at[p], c.dq[p]);
         }
     }
 }
 
 // a, s, proc and the by-queue links of one chain from d and its queue order (what Event carries in the
-// reference: arrivals.pxd:11-37; proc = first arg-min of the processor-indexed vector, queues.pyx:1518-1527)
+// reference: arrivals.pxd:11-37; proc = first arg-min of the processor-indexed vector, queues.pyx:1518-1527).
+// sq: the PS service times by position; ord0: the initial order, whose links PS queues keep.
 static void host_derive(const HostNet *h, const double *d, const int *ord, double *a, double *s, int32_t *proc,
-                        int32_t *prev_byq, int32_t *next_byq, const double *svc = nullptr,
-                        const int *ord0 = nullptr) {
+                        int32_t *prev_byq, int32_t *next_byq, const double *sq = nullptr, const int *ord0 = nullptr) {
     const int E = h->E;
     std::vector<double> av(E);
     for (int e = 0; e < E; ++e) { int pt = h->prev_byt[e]; av[e] = pt >= 0 ? d[pt] : 0.0; }
@@ -109,12 +117,11 @@ static void host_derive(const HostNet *h, const double *d, const int *ord, doubl
                 sv = d[i] - std::max(av[i], fr[pr]);
                 fr[pr] = d[i];
             }
-            if (t == 2 /* Q_PS */ && svc) sv = svc[i];
+            if (t == 2 /* Q_PS */ && sq) sv = sq[p];
             if (proc) proc[i] = pr;
             if (s) s[i] = sv;
         }
     }
 }
-
 
 }  // namespace bq

@@ -70,18 +70,19 @@ struct bq_handle {
     // ---- dynamic-order networks (k > 1, PS): per-chain queue order and free-time vectors ----
     bool has_ps = false;
     int EF = 0, kmax = 1, dyn_w = 32, dyn_threads = 128;
-    std::vector<int> ev_f, q_off, ord0;  // F offset per event, queue ranges, initial order
+    std::vector<int> q_off, q_foff, ord0;  // queue position ranges, F offsets, initial order
     std::vector<int> dyn_order;          // sweep order of the dynamic-order kernels
     bool dyn_ready = false;              // dynamic arrays allocated
     bool dyn_stale = false;              // ... but the static kernel has moved d since they were built
-    int *d_order = nullptr, *d_ev_nt = nullptr, *d_ev_f = nullptr, *d_q_k = nullptr;
+    DynRec *d_order = nullptr;
+    QInfo *d_qinfo = nullptr;
     int *d_ord = nullptr, *d_pos = nullptr, *d_dord = nullptr, *d_dpos = nullptr;
-    double *d_F = nullptr, *d_svc = nullptr, *d_at = nullptr, *d_dt = nullptr;
+    double *d_F = nullptr, *d_sq = nullptr, *d_at = nullptr, *d_dq = nullptr, *d_dt = nullptr;
     HostNet net() const {
         HostNet n;
         n.E = E; n.Q = Q;
-        n.q_type = q_type.data(); n.q_k = q_k.data(); n.q_off = q_off.data();
-        n.ev_f = ev_f.data(); n.prev_byt = prev_byt.data();
+        n.q_type = q_type.data(); n.q_k = q_k.data(); n.q_off = q_off.data(); n.q_foff = q_foff.data();
+        n.prev_byt = prev_byt.data();
         return n;
     }
 };
@@ -243,13 +244,56 @@ static void fill_dyn_args(const bq_handle *h, DynArgs &A) {
     A.E = h->E; A.Q = h->Q; A.P = h->P; A.n_chains = h->C; A.EF = h->EF;
     A.n_order = (int)h->dyn_order.size();
     A.order = h->d_order;
-    A.ev_q = h->d_ev_q; A.ev_pt = h->d_ev_pt; A.ev_nt = h->d_ev_nt; A.ev_f = h->d_ev_f;
-    A.q_off = h->d_q_off; A.q_type = h->d_q_type; A.q_k = h->d_q_k; A.q_dist = h->d_q_dist; A.q_poff = h->d_q_poff;
-    A.state = h->d_state; A.ord = h->d_ord; A.pos = h->d_pos; A.F = h->d_F;
-    A.dord = h->d_dord; A.dpos = h->d_dpos; A.svc = h->d_svc; A.at = h->d_at; A.dt = h->d_dt;
+    A.qinfo = h->d_qinfo; A.q_poff = h->d_q_poff;
+    A.state = h->d_state; A.ord = h->d_ord; A.pos = h->d_pos; A.at = h->d_at; A.dq = h->d_dq; A.F = h->d_F;
+    A.dord = h->d_dord; A.dpos = h->d_dpos; A.dt = h->d_dt; A.sq = h->d_sq;
     A.theta = h->d_theta; A.stats = h->d_stats;
     A.tr_theta = h->d_tr_theta; A.tr_wait = h->d_tr_wait; A.tr_logp = h->d_tr_logp;
     A.seed = h->seed; A.chain_offset = h->chain_offset; A.sweep_base = h->sweep_counter;
+}
+
+// host staging of the per-chain derived arrays for `rows` chains
+struct HostRows {
+    std::vector<int> ord, pos, dord, dpos;
+    std::vector<double> at, dq, F, dt, sq;
+    void alloc(size_t rows, size_t E, size_t EF, bool ps) {
+        ord.assign(rows * E, 0); pos.assign(rows * E, 0);
+        at.assign(rows * E, 0.0); dq.assign(rows * E, 0.0);
+        F.assign(std::max<size_t>(rows * EF, 1), 0.0);
+        if (ps) { dord.assign(rows * E, 0); dpos.assign(rows * E, 0); dt.assign(rows * E, 0.0); sq.assign(rows * E, 0.0); }
+    }
+    HostChain chain(size_t i, size_t E, size_t EF) {
+        HostChain c;
+        c.ord = &ord[i * E]; c.pos = &pos[i * E]; c.at = &at[i * E]; c.dq = &dq[i * E]; c.F = &F[i * EF];
+        const bool ps = !dt.empty();
+        c.dt = ps ? &dt[i * E] : nullptr; c.sq = ps ? &sq[i * E] : nullptr;
+        c.dord = ps ? &dord[i * E] : nullptr; c.dpos = ps ? &dpos[i * E] : nullptr;
+        return c;
+    }
+};
+
+// rows staged on the host -> chains [lo, lo + rows); when rows == 1 < n the row is replicated to n chains
+static int upload_rows(bq_handle *h, const HostRows &r, int lo, size_t rows, size_t n, bool sync) {
+    const size_t E = h->E, EF = h->EF, o = (size_t)lo * E, of = (size_t)lo * EF;
+    auto put = [&](auto *dst, const auto &src, size_t row) -> cudaError_t {
+        if (!row) return cudaSuccess;
+        cudaError_t e = cudaMemcpyAsync(dst, src.data(), rows * row * sizeof(*dst), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess && rows == 1 && n > 1) e = replicate_rows(dst, row, n, h->stream);
+        return e;
+    };
+    CK(put(h->d_ord + o, r.ord, E));
+    CK(put(h->d_pos + o, r.pos, E));
+    CK(put(h->d_at + o, r.at, E));
+    CK(put(h->d_dq + o, r.dq, E));
+    CK(put(h->d_F + of, r.F, EF));
+    if (h->has_ps) {
+        CK(put(h->d_dord + o, r.dord, E));
+        CK(put(h->d_dpos + o, r.dpos, E));
+        CK(put(h->d_dt + o, r.dt, E));
+        CK(put(h->d_sq + o, r.sq, E));
+    }
+    if (sync) CK(cudaStreamSynchronize(h->stream));
+    return BQ_OK;
 }
 
 // initial queue orders from the caller's by-queue links, and the sequential scan order of the dynamic-order kernels:
@@ -280,59 +324,54 @@ static int build_sequential_order(bq_handle *h) {
 // per-handle tables of the dynamic kernels + the derived arrays of the initial state, replicated to all chains
 static int setup_dynamic(bq_handle *h, const double *d0) {
     const int E = h->E, Q = h->Q;
-    h->ev_f.assign(E, -1);
+    h->q_foff.assign(Q, 0);
     h->EF = 0; h->kmax = 1;
     for (int q = 0; q < Q; ++q)
         if (h->q_type[q] == Q_GGK) {
             h->kmax = std::max(h->kmax, h->q_k[q]);
-            for (int p = h->q_off[q]; p < h->q_off[q + 1]; ++p) { h->ev_f[h->ord0[p]] = h->EF; h->EF += h->q_k[q]; }
+            h->q_foff[q] = h->EF;
+            h->EF += h->q_k[q] * (h->q_off[q + 1] - h->q_off[q]);
         }
     if (h->kmax > 8) return fail(BQ_ERR_UNSUPPORTED, "more than 8 processors per queue");
-    std::vector<int> pos0(E), dord0, dpos0;
-    std::vector<double> F0(std::max(h->EF, 1)), at0, dt0, svc0;
-    if (h->has_ps) { dord0.assign(E, 0); dpos0.assign(E, 0); at0.assign(E, 0.0); dt0.assign(E, 0.0); svc0.assign(E, 0.0); }
+    HostRows r0;
+    r0.alloc(1, E, h->EF, h->has_ps);
+    memcpy(r0.ord.data(), h->ord0.data(), E * sizeof(int));
     {
         HostNet hn = h->net();
-        HostPs ps{at0.data(), dt0.data(), svc0.data(), dord0.data(), dpos0.data()};
-        host_rebuild(&hn, d0, h->ord0.data(), pos0.data(), F0.data(), false, h->has_ps ? &ps : nullptr);
+        host_rebuild(&hn, d0, r0.chain(0, E, h->EF), false);
     }
     if (!h->static_order) {  // the handle's schedule is the sequential scan: one event per class
         h->order = h->dyn_order;
         h->color_off.resize(h->order.size() + 1);
         for (size_t i = 0; i <= h->order.size(); ++i) h->color_off[i] = (int)i;
     }
+    std::vector<DynRec> recs(h->dyn_order.size());
+    for (size_t i = 0; i < recs.size(); ++i) {
+        const int e = h->dyn_order[i], e1 = h->next_byt[e];
+        recs[i].e = e; recs[i].e1 = e1; recs[i].q0 = h->qid[e]; recs[i].q1 = e1 >= 0 ? h->qid[e1] : -1;
+    }
+    std::vector<QInfo> qinfo(Q);
+    for (int q = 0; q < Q; ++q) {
+        qinfo[q].type = h->q_type[q]; qinfo[q].k = h->q_k[q]; qinfo[q].lo = h->q_off[q]; qinfo[q].hi = h->q_off[q + 1];
+        qinfo[q].foff = h->q_foff[q]; qinfo[q].dist = h->q_dist[q];
+    }
+    static_assert(sizeof(DynRec) == 16, "DynRec is loaded as one int4");
 
     const size_t C = h->C;
-    CK(upload(&h->d_order, h->dyn_order.data(), h->dyn_order.size()));
-    CK(upload(&h->d_ev_nt, h->next_byt.data(), E));
-    CK(upload(&h->d_ev_f, h->ev_f.data(), E));
-    CK(upload(&h->d_q_k, h->q_k.data(), Q));
+    CK(upload(&h->d_order, recs.data(), recs.size()));
+    CK(upload(&h->d_qinfo, qinfo.data(), qinfo.size()));
     CK(cudaMalloc((void **)&h->d_ord, C * E * sizeof(int)));
     CK(cudaMalloc((void **)&h->d_pos, C * E * sizeof(int)));
+    CK(cudaMalloc((void **)&h->d_at, C * E * sizeof(double)));
+    CK(cudaMalloc((void **)&h->d_dq, C * E * sizeof(double)));
     CK(cudaMalloc((void **)&h->d_F, std::max<size_t>(C * h->EF, 1) * sizeof(double)));
-    CK(cudaMemcpyAsync(h->d_ord, h->ord0.data(), E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_pos, pos0.data(), E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_F, F0.data(), h->EF * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(replicate_rows(h->d_ord, E, C, h->stream));
-    CK(replicate_rows(h->d_pos, E, C, h->stream));
-    if (h->EF) CK(replicate_rows(h->d_F, h->EF, C, h->stream));
     if (h->has_ps) {
         CK(cudaMalloc((void **)&h->d_dord, C * E * sizeof(int)));
         CK(cudaMalloc((void **)&h->d_dpos, C * E * sizeof(int)));
-        CK(cudaMalloc((void **)&h->d_at, C * E * sizeof(double)));
         CK(cudaMalloc((void **)&h->d_dt, C * E * sizeof(double)));
-        CK(cudaMalloc((void **)&h->d_svc, C * E * sizeof(double)));
-        CK(cudaMemcpyAsync(h->d_dord, dord0.data(), E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_dpos, dpos0.data(), E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_at, at0.data(), E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_dt, dt0.data(), E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_svc, svc0.data(), E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        CK(replicate_rows(h->d_dord, E, C, h->stream));
-        CK(replicate_rows(h->d_dpos, E, C, h->stream));
-        CK(replicate_rows(h->d_at, E, C, h->stream));
-        CK(replicate_rows(h->d_dt, E, C, h->stream));
-        CK(replicate_rows(h->d_svc, E, C, h->stream));
+        CK(cudaMalloc((void **)&h->d_sq, C * E * sizeof(double)));
     }
+    if (int rc = upload_rows(h, r0, 0, 1, C, false)) return rc;
     CK(cudaStreamSynchronize(h->stream));
     // lanes per chain: wide groups hide the latency of a single chain's serial walk when chains are few; with many
     // chains narrower groups waste fewer lanes on speculative candidates (measured on B200, tools/probe_dyn.py)
@@ -353,47 +392,18 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
 // new departure times for chains [lo, hi) of a dynamic-order handle: every queue is re-ranked by arrival and
 // the derived arrays are rebuilt on the host
 static int dynamic_set_rows(bq_handle *h, int lo, int hi, const double *d, bool same_for_all) {
-    const size_t E = h->E, EF = h->EF, n = (size_t)(hi - lo);
+    const size_t E = h->E, n = (size_t)(hi - lo);
     const size_t rows = same_for_all ? 1 : n;
-    std::vector<int> ord(rows * E), pos(rows * E), dord, dpos;
-    std::vector<double> F(std::max<size_t>(rows * EF, 1)), at, dt, svc;
-    if (h->has_ps) {
-        dord.assign(rows * E, 0); dpos.assign(rows * E, 0);
-        at.assign(rows * E, 0.0); dt.assign(rows * E, 0.0); svc.assign(rows * E, 0.0);
-    }
+    HostRows r;
+    r.alloc(rows, E, h->EF, h->has_ps);
     const HostNet hn = h->net();
-    for (size_t r = 0; r < rows; ++r) {
-        memcpy(&ord[r * E], h->ord0.data(), E * sizeof(int));
-        HostPs ps{at.data() + r * E, dt.data() + r * E, svc.data() + r * E, dord.data() + r * E, dpos.data() + r * E};
-        host_rebuild(&hn, d + r * E, &ord[r * E], &pos[r * E], &F[r * EF], true, h->has_ps ? &ps : nullptr);
-    }
-    if (h->has_ps) {
-        const size_t o = (size_t)lo * E;
-        CK(cudaMemcpyAsync(h->d_dord + o, dord.data(), rows * E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_dpos + o, dpos.data(), rows * E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_at + o, at.data(), rows * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_dt + o, dt.data(), rows * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_svc + o, svc.data(), rows * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        if (same_for_all) {
-            CK(replicate_rows(h->d_dord + o, E, n, h->stream));
-            CK(replicate_rows(h->d_dpos + o, E, n, h->stream));
-            CK(replicate_rows(h->d_at + o, E, n, h->stream));
-            CK(replicate_rows(h->d_dt + o, E, n, h->stream));
-            CK(replicate_rows(h->d_svc + o, E, n, h->stream));
-        }
+    for (size_t i = 0; i < rows; ++i) {
+        memcpy(&r.ord[i * E], h->ord0.data(), E * sizeof(int));
+        host_rebuild(&hn, d + i * E, r.chain(i, E, h->EF), true);
     }
     CK(cudaMemcpyAsync(h->d_state + (size_t)lo * E, d, rows * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_ord + (size_t)lo * E, ord.data(), rows * E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_pos + (size_t)lo * E, pos.data(), rows * E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    if (EF) CK(cudaMemcpyAsync(h->d_F + (size_t)lo * EF, F.data(), rows * EF * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (same_for_all) {
-        CK(replicate_rows(h->d_state + (size_t)lo * E, E, n, h->stream));
-        CK(replicate_rows(h->d_ord + (size_t)lo * E, E, n, h->stream));
-        CK(replicate_rows(h->d_pos + (size_t)lo * E, E, n, h->stream));
-        if (EF) CK(replicate_rows(h->d_F + (size_t)lo * EF, EF, n, h->stream));
-    }
-    CK(cudaStreamSynchronize(h->stream));
-    return BQ_OK;
+    if (same_for_all) CK(replicate_rows(h->d_state + (size_t)lo * E, E, n, h->stream));
+    return upload_rows(h, r, lo, rows, n, true);
 }
 
 template <int W>
@@ -415,8 +425,8 @@ extern "C" int bq_destroy(bq_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->d_rec, h->d_color_off, h->d_ev_q, h->d_ev_p, h->d_ev_pt, h->d_q_events, h->d_q_off,
                     h->d_q_type, h->d_q_dist, h->d_q_poff, h->d_state, h->d_theta, h->d_stats,
-                    h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch, h->d_order, h->d_ev_nt, h->d_ev_f,
-                    h->d_q_k, h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_F, h->d_svc, h->d_at, h->d_dt};
+                    h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch, h->d_order, h->d_qinfo,
+                    h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_F, h->d_sq, h->d_at, h->d_dq, h->d_dt};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -648,7 +658,7 @@ extern "C" int bq_get_state(bq_handle *h, int32_t lo, int32_t hi, double *d, dou
         CK(cudaMemcpyAsync(ord.data(), h->d_ord + (size_t)lo * E, n * E * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         if (h->has_ps) {
             svc.resize(n * E);
-            CK(cudaMemcpyAsync(svc.data(), h->d_svc + (size_t)lo * E, n * E * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(svc.data(), h->d_sq + (size_t)lo * E, n * E * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         }
         CK(cudaStreamSynchronize(h->stream));
         const HostNet hn = h->net();
@@ -722,8 +732,8 @@ static int ensure_dynamic(bq_handle *h) {
         DynArgs D;
         fill_dyn_args(h, D);
         const long long n = (long long)h->C * h->Q;
-        if (h->kmax <= 4) rebuild_free_times_kernel<4><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(D);
-        else rebuild_free_times_kernel<8><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(D);
+        if (h->kmax <= 4) rebuild_positions_kernel<4><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(D, h->d_ev_pt);
+        else rebuild_positions_kernel<8><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(D, h->d_ev_pt);
         CK(cudaGetLastError());
         h->n_launches += 1;
         h->dyn_stale = false;
@@ -824,10 +834,12 @@ static int eval_hook(bq_handle *h, int32_t chain, int32_t eid, const double *x, 
         DynArgs D;
         fill_dyn_args(h, D);
         const size_t sm = dyn_group_smem(h->Q, h->P);
+        const int e1 = h->next_byt[eid];
+        const DynRec rec = {eid, e1, h->qid[eid], e1 >= 0 ? h->qid[e1] : -1};
         if (h->kmax <= 4)
-            logcond_dynamic_kernel<4><<<1, 32, sm, h->stream>>>(D, chain, eid, h->d_scratch, n, h->d_scratch + n, what);
+            logcond_dynamic_kernel<4><<<1, 32, sm, h->stream>>>(D, chain, rec, h->d_scratch, n, h->d_scratch + n, what);
         else
-            logcond_dynamic_kernel<8><<<1, 32, sm, h->stream>>>(D, chain, eid, h->d_scratch, n, h->d_scratch + n, what);
+            logcond_dynamic_kernel<8><<<1, 32, sm, h->stream>>>(D, chain, rec, h->d_scratch, n, h->d_scratch + n, what);
     } else {
         SweepArgs A;
         fill_args(h, A);

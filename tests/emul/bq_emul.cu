@@ -16,11 +16,12 @@ using namespace bq;
 
 struct Emul {
     int E, Q, P;
-    std::vector<int> q_type, q_k, q_dist, q_poff, q_off;
-    std::vector<int> qid, prev_byt, next_byt, ev_f, ord, ord0, pos, dord, dpos;
+    std::vector<int> q_type, q_k, q_dist, q_poff, q_off, q_foff;
+    std::vector<int> qid, prev_byt, next_byt, ord, ord0, pos, dord, dpos;
     std::vector<uint8_t> obs_a, obs_d;
-    std::vector<double> d, F, svc, at, dt, theta;
+    std::vector<double> d, F, sq, at, dq, dt, theta;
     std::vector<QConst> qc;
+    std::vector<QInfo> qinfo;
     int EF;
     DynArgs A;
     Chain c;
@@ -35,13 +36,18 @@ struct Emul {
     void bind() {
         memset(&A, 0, sizeof(A));
         A.E = E; A.Q = Q; A.P = P; A.n_chains = 1; A.EF = EF;
-        A.ev_q = qid.data(); A.ev_pt = prev_byt.data(); A.ev_nt = next_byt.data(); A.ev_f = ev_f.data();
-        A.q_off = q_off.data(); A.q_type = q_type.data(); A.q_k = q_k.data(); A.q_dist = q_dist.data();
-        A.q_poff = q_poff.data();
-        A.state = d.data(); A.ord = ord.data(); A.pos = pos.data(); A.F = F.data();
-        A.dord = dord.data(); A.dpos = dpos.data(); A.svc = svc.data(); A.at = at.data(); A.dt = dt.data();
+        A.qinfo = qinfo.data(); A.q_poff = q_poff.data();
+        A.state = d.data(); A.ord = ord.data(); A.pos = pos.data(); A.at = at.data(); A.dq = dq.data(); A.F = F.data();
+        A.dord = dord.data(); A.dpos = dpos.data(); A.dt = dt.data(); A.sq = sq.data();
         A.theta = theta.data();
-        c.bind(A, 0, qc.data());
+        c.bind(A, 0, qinfo.data(), qc.data());
+    }
+    HostNet net() const {
+        return HostNet{E, Q, q_type.data(), q_k.data(), q_off.data(), q_foff.data(), prev_byt.data()};
+    }
+    DynRec rec(int e) const {
+        const int e1 = next_byt[e];
+        return DynRec{e, e1, qid[e], e1 >= 0 ? qid[e1] : -1};
     }
 };
 
@@ -61,7 +67,8 @@ void *bqe_create(int E, int Q, int P, const int *q_type, const int *q_k, const i
     m->q_off.assign(Q + 1, 0);
     for (int e = 0; e < E; ++e) m->q_off[qid[e] + 1]++;
     for (int q = 0; q < Q; ++q) m->q_off[q + 1] += m->q_off[q];
-    m->ord.assign(E, -1); m->pos.assign(E, -1); m->dord.assign(E, -1); m->dpos.assign(E, -1); m->svc.assign(E, 0.0); m->at.assign(E, 0.0); m->dt.assign(E, 0.0);
+    m->ord.assign(E, -1); m->pos.assign(E, -1); m->dord.assign(E, -1); m->dpos.assign(E, -1);
+    m->sq.assign(E, 0.0); m->at.assign(E, 0.0); m->dq.assign(E, 0.0); m->dt.assign(E, 0.0);
     for (int q = 0; q < Q; ++q) {
         int p = m->q_off[q];
         for (int e = 0; e < E; ++e)
@@ -69,16 +76,21 @@ void *bqe_create(int E, int Q, int P, const int *q_type, const int *q_k, const i
                 for (int x = e; x >= 0; x = next_byq[x]) m->ord[p++] = x;
     }
     m->ord0 = m->ord;
-    m->ev_f.assign(E, -1);
+    m->q_foff.assign(Q, 0);
     m->EF = 0;
-    for (int q = 0; q < Q; ++q)
-        if (q_type[q] == Q_GGK)
-            for (int p = m->q_off[q]; p < m->q_off[q + 1]; ++p) { m->ev_f[m->ord[p]] = m->EF; m->EF += q_k[q]; }
+    m->qinfo.resize(Q);
+    for (int q = 0; q < Q; ++q) {
+        if (q_type[q] == Q_GGK) { m->q_foff[q] = m->EF; m->EF += q_k[q] * (m->q_off[q + 1] - m->q_off[q]); }
+        m->qinfo[q] = QInfo{q_type[q], q_k[q], m->q_off[q], m->q_off[q + 1], m->q_foff[q], q_dist[q]};
+    }
     m->F.assign(m->EF + 1, 0.0);
     m->qc.resize(Q);
-    HostNet hn{E, Q, m->q_type.data(), m->q_k.data(), m->q_off.data(), m->ev_f.data(), m->prev_byt.data()};
-    HostPs ps{m->at.data(), m->dt.data(), m->svc.data(), m->dord.data(), m->dpos.data()};
-    host_rebuild(&hn, m->d.data(), m->ord.data(), m->pos.data(), m->F.data(), false, &ps);
+    {
+        HostNet hn = m->net();
+        HostChain hc{m->ord.data(), m->pos.data(), m->at.data(), m->dq.data(), m->F.data(), m->dt.data(), m->sq.data(),
+                     m->dord.data(), m->dpos.data()};
+        host_rebuild(&hn, m->d.data(), hc, false);
+    }
     m->refresh_qc();
     m->bind();
     m->evals = m->steps = 0;
@@ -96,7 +108,7 @@ void bqe_set_theta(void *h, const double *theta) {
 void bqe_logcond(void *h, int e, const double *x, int n, double *out) {
     Emul *m = (Emul *)h;
     EventCtx ev;
-    event_load(m->c, e, ev);
+    event_load(m->c, m->rec(e), ev);
     int steps = 0;
     const double g0 = dyn_logcond<8>(m->c, ev, ev.x0, steps);
     for (int j = 0; j < n; ++j) out[j] = dyn_logcond<8>(m->c, ev, x[j], steps) - g0;
@@ -105,7 +117,7 @@ void bqe_logcond(void *h, int e, const double *x, int n, double *out) {
 void bqe_apply(void *h, int e, double x) {
     Emul *m = (Emul *)h;
     EventCtx ev;
-    event_load(m->c, e, ev);
+    event_load(m->c, m->rec(e), ev);
     dyn_commit<1, 8>(m->c, ev, x, 0, 1u);
 }
 
@@ -116,7 +128,7 @@ long bqe_slice_sweep(void *h, const int *order, int n_order, uint64_t seed, int6
     long ne = 0;
     for (int idx = 0; idx < n_order; ++idx) {
         EventCtx ev;
-        event_load(m->c, order[idx], ev);
+        event_load(m->c, m->rec(order[idx]), ev);
         const double lower = ev.a_e, upper = (ev.e1 >= 0) ? fmin(ev.d1, tmax) : tmax;
         Rng rng;
         rng.init(seed, (uint64_t)chain, sweep, (uint32_t)ev.e, TAG_SLICE);
@@ -147,7 +159,7 @@ long bqe_mh_sweep(void *h, const int *order, int n_order, uint64_t seed, int64_t
     long ne = 0;
     for (int idx = 0; idx < n_order; ++idx) {
         EventCtx ev;
-        event_load(m->c, order[idx], ev);
+        event_load(m->c, m->rec(order[idx]), ev);
         const bool fin = ev.e1 < 0;
         if (fin && !sample_final) continue;
         MhProp pr;
@@ -202,7 +214,7 @@ long bqe_mh_sweep(void *h, const int *order, int n_order, uint64_t seed, int64_t
 void bqe_mh_proposal(void *h, int e, const double *x, int n, double *out) {
     Emul *m = (Emul *)h;
     EventCtx ev;
-    event_load(m->c, e, ev);
+    event_load(m->c, m->rec(e), ev);
     MhProp pr;
     mh_setup(m->c, ev, pr);
     for (int j = 0; j < n; ++j) out[j] = pr.eval(x[j]);
@@ -213,43 +225,45 @@ void bqe_get(void *h, double *d, int *ord, double *F, double *svc) {
     if (d) memcpy(d, m->d.data(), m->E * sizeof(double));
     if (ord) memcpy(ord, m->ord.data(), m->E * sizeof(int));
     if (F) memcpy(F, m->F.data(), m->EF * sizeof(double));
-    if (svc) memcpy(svc, m->svc.data(), m->E * sizeof(double));
+    if (svc) memcpy(svc, m->sq.data(), m->E * sizeof(double));
 }
 
 // a, s, proc, links recomputed from (d, ord) by the library's host code
 void bqe_derive(void *h, double *a, double *s, int32_t *proc, int32_t *prev_byq, int32_t *next_byq) {
     Emul *m = (Emul *)h;
-    HostNet hn{m->E, m->Q, m->q_type.data(), m->q_k.data(), m->q_off.data(), m->ev_f.data(), m->prev_byt.data()};
-    host_derive(&hn, m->d.data(), m->ord.data(), a, s, proc, prev_byq, next_byq, m->svc.data(), m->ord0.data());
+    HostNet hn = m->net();
+    host_derive(&hn, m->d.data(), m->ord.data(), a, s, proc, prev_byq, next_byq, m->sq.data(), m->ord0.data());
 }
 
 // consistency of the incrementally maintained arrays with a from-scratch rebuild: 0 = consistent
 int bqe_check(void *h) {
     Emul *m = (Emul *)h;
     std::vector<int> ord(m->ord), pos(m->E), dord(m->E, -1), dpos(m->E, -1);
-    std::vector<double> F(m->EF + 1, 0.0), at(m->E, 0.0), dt(m->E, 0.0), svc(m->E, 0.0);
-    HostNet hn{m->E, m->Q, m->q_type.data(), m->q_k.data(), m->q_off.data(), m->ev_f.data(), m->prev_byt.data()};
-    HostPs ps{at.data(), dt.data(), svc.data(), dord.data(), dpos.data()};
-    host_rebuild(&hn, m->d.data(), ord.data(), pos.data(), F.data(), false, &ps);
+    std::vector<double> F(m->EF + 1, 0.0), at(m->E, 0.0), dq(m->E, 0.0), dt(m->E, 0.0), sq(m->E, 0.0);
+    HostNet hn = m->net();
+    HostChain hc{ord.data(), pos.data(), at.data(), dq.data(), F.data(), dt.data(), sq.data(), dord.data(), dpos.data()};
+    host_rebuild(&hn, m->d.data(), hc, false);
     for (int e = 0; e < m->E; ++e)
         if (pos[e] != m->pos[e]) return 1;
     for (int i = 0; i < m->EF; ++i)
         if (F[i] != m->F[i]) return 2;
+    for (int p = 0; p < m->E; ++p) {
+        if (at[p] != m->at[p]) return 8;
+        if (dq[p] != m->dq[p]) return 9;
+    }
     for (int q = 0; q < m->Q; ++q) {
         if (m->q_type[q] != Q_PS) continue;
         for (int p = m->q_off[q]; p < m->q_off[q + 1]; ++p) {
-            if (at[p] != m->at[p]) return 4;
             if (dt[p] != m->dt[p]) return 5;
             if (dt[p] != m->d[m->dord[p]] || m->dpos[m->dord[p]] != p) return 6;
-            const int i = m->ord[p];
-            if (fabs(svc[i] - m->svc[i]) > 1e-9 * fmax(1.0, fabs(svc[i]))) return 7;
+            if (fabs(sq[p] - m->sq[p]) > 1e-9 * fmax(1.0, fabs(sq[p]))) return 7;
         }
     }
     // every non-delay queue must be sorted by arrival
     for (int q = 0; q < m->Q; ++q) {
         if (m->q_type[q] == Q_DELAY) continue;
         for (int p = m->q_off[q] + 1; p < m->q_off[q + 1]; ++p)
-            if (m->c.arr(m->ord[p]) < m->c.arr(m->ord[p - 1])) return 3;
+            if (m->at[p] < m->at[p - 1]) return 3;
     }
     return 0;
 }
