@@ -7,7 +7,20 @@
 #include <math.h>
 #include "bq_rng.cuh"
 
+// Heavy routines are kept out of line in device code: the sweep kernels call lpdf (an fp64 log) from a dozen places,
+// and inlining every copy grows the kernel past the instruction cache.
+#if defined(__CUDA_ARCH__)
+#define BQ_NOINLINE __noinline__
+#else
+#define BQ_NOINLINE
+#endif
+
 namespace bq {
+
+// libdevice's fp64 log / lgamma are 100+ / 1000+ instructions and get inlined at every call site: one out-of-line
+// copy each keeps the sweep kernels inside the instruction cache
+__host__ __device__ BQ_NOINLINE inline double log_d(double x) { return log(x); }
+__host__ __device__ BQ_NOINLINE inline double lgamma_d(double x) { return lgamma(x); }
 
 enum { Q_GGK = 0, Q_DELAY = 1, Q_PS = 2 };
 enum { D_EXP = 0, D_GAMMA = 1, D_LOGNORMAL = 2 };
@@ -27,28 +40,32 @@ __host__ __device__ __forceinline__ void qconst_set(QConst &qc, int dist, double
     qc.dist = dist;
     qc.pad = 0;
     if (dist == D_EXP) {  // -log(scale) - x/scale                      (distributions.pyx:59)
-        qc.c0 = -log(p0); qc.c1 = 0.0; qc.inv = 1.0 / p0;
+        qc.c0 = -log_d(p0); qc.c1 = 0.0; qc.inv = 1.0 / p0;
     } else if (dist == D_GAMMA) {  // shape p0, scale p1                 (distributions.pyx:129-133)
         qc.c1 = p0 - 1.0;
         qc.inv = 1.0 / p1;
-        qc.c0 = (p0 == 1.0) ? -p0 * log(p1) : -lgamma(p0) - p0 * log(p1);
+        qc.c0 = (p0 == 1.0) ? -p0 * log_d(p1) : -lgamma_d(p0) - p0 * log_d(p1);
     } else {  // LogNormal meanlog p0, sdlog p1                          (distributions.pyx:266-270)
-        qc.c0 = BQ_HALF_LOG_2PI - log(p1);
+        qc.c0 = BQ_HALF_LOG_2PI - log_d(p1);
         qc.c1 = p0;
         qc.inv = 1.0 / (2.0 * p1 * p1);
     }
 }
 
-// log-density of service time s >= 0
+// log-density of service time s >= 0; the Gamma / LogNormal part (one fp64 log) is a real call
+__host__ __device__ BQ_NOINLINE inline double lpdf_log(const QConst &qc, double s) {
+    if (qc.dist == D_GAMMA) return qc.c1 * log_d(s) - s * qc.inv + qc.c0;
+    const double ls = log_d(s), z = ls - qc.c1;
+    return qc.c0 - ls - z * z * qc.inv;
+}
 __host__ __device__ __forceinline__ double lpdf(const QConst &qc, double s) {
     if (qc.dist == D_EXP) return qc.c0 - s * qc.inv;
     if (qc.dist == D_GAMMA) {
         if (qc.c1 == 0.0) return qc.c0 - s * qc.inv;  // shape == 1 special case handles s == 0
-        return qc.c1 * log(s) - s * qc.inv + qc.c0;
+        return lpdf_log(qc, s);
     }
     if (s == 0.0) return BQ_NEG_INF;
-    double ls = log(s), z = ls - qc.c1;
-    return qc.c0 - ls - z * z * qc.inv;
+    return lpdf_log(qc, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -57,7 +74,7 @@ __host__ __device__ __forceinline__ double lpdf(const QConst &qc, double s) {
 __device__ inline double draw_normal(Rng &r) {  // Box-Muller
     double u1 = 1.0 - r.uniform();         // (0,1]
     double u2 = r.uniform();
-    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    return sqrt(-2.0 * log_d(u1)) * cospi(2.0 * u2);
 }
 
 __device__ inline double draw_gamma(Rng &r, double shape) {  // Marsaglia-Tsang, scale 1
@@ -73,7 +90,7 @@ __device__ inline double draw_gamma(Rng &r, double shape) {  // Marsaglia-Tsang,
         if (v <= 0.0) continue;
         v = v * v * v;
         double u = 1.0 - r.uniform();
-        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v;
+        if (log_d(u) < 0.5 * x * x + d - d * v + d * log_d(v)) return boost * d * v;
     }
     return boost * d;
 }
@@ -83,7 +100,7 @@ __device__ inline double digamma_d(double x) {
     double r = 0.0;
     while (x < 6.0) { r -= 1.0 / x; x += 1.0; }
     double f = 1.0 / (x * x);
-    return r + log(x) - 0.5 / x -
+    return r + log_d(x) - 0.5 / x -
            f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f * (1.0 / 132.0)))));
 }
 __device__ inline double trigamma_d(double x) {
@@ -98,10 +115,10 @@ __device__ inline double trigamma_d(double x) {
 struct GammaPost {
     double logP, q, r, s;  // 1+sum log x, 1+sum x, 1+N, 1+N
     __device__ double shape_lnf(double al, double scale0) const {
-        return (al - 1.0) * logP - q / scale0 - r * lgamma(al) - (al * s) * log(scale0);
+        return (al - 1.0) * logP - q / scale0 - r * lgamma_d(al) - (al * s) * log_d(scale0);
     }
     __device__ double scale_lnf(double beta, double shape) const {
-        return (shape - 1.0) * logP - q / beta - r * lgamma(shape) - (shape * s) * log(beta);
+        return (shape - 1.0) * logP - q / beta - r * lgamma_d(shape) - (shape * s) * log_d(beta);
     }
 };
 
@@ -114,7 +131,7 @@ __device__ inline double slice_stepout(Rng &rng, const GammaPost &gp, int which,
 #define BQ_GP(x) ((which == 0) ? gp.shape_lnf((x), fixed) : gp.scale_lnf((x), fixed))
     double gx0 = BQ_GP(x0);
     ++*evals;
-    double logy = gx0 - (-log(1.0 - rng.uniform()));
+    double logy = gx0 - (-log_d(1.0 - rng.uniform()));
     if (logy == BQ_NEG_INF || logy != logy) return x0;
     double u = w * rng.uniform();
     double L = x0 - u, R = x0 + (w - u);
@@ -159,7 +176,7 @@ struct SuffStat {
 };
 
 // Posterior draw of one queue's parameters (DistributionTemplate.sample_parameters, queues.pyx:1316).
-__device__ inline void sample_params(int dist, const SuffStat &st, Rng &rng, double &p0, double &p1,
+__device__ BQ_NOINLINE void sample_params(int dist, const SuffStat &st, Rng &rng, double &p0, double &p1,
                                      long long *evals) {
     if (dist == D_EXP) {  // distributions.pyx:92-96: scale = 1 / Gamma(N, 1/sum)
         if (st.n < 1.0 || !(st.sum > 0.0)) return;
@@ -193,7 +210,7 @@ __device__ inline void sample_params(int dist, const SuffStat &st, Rng &rng, dou
 }
 
 // ML update of one queue's parameters (DistributionTemplate.estimate, queues.pyx:1324).
-__device__ inline void estimate_params(int dist, const SuffStat &st, double &p0, double &p1) {
+__device__ BQ_NOINLINE void estimate_params(int dist, const SuffStat &st, double &p0, double &p1) {
     if (dist == D_EXP) {  // distributions.pyx:65-74
         if (st.n < 1.0) { p0 = 1.0; return; }
         double mu = st.sum / st.n;
@@ -206,10 +223,10 @@ __device__ inline void estimate_params(int dist, const SuffStat &st, double &p0,
     } else {  // Minka fixed point, distributions.pyx:142-160
         if (st.n < 1.0) return;
         double mu = st.sum / st.n, mu_log = st.sumlog / st.n;
-        double a = 0.5 / (log(mu) - mu_log), a_old = -INFINITY;
+        double a = 0.5 / (log_d(mu) - mu_log), a_old = -INFINITY;
         for (int it = 0; it < 200 && fabs(a - a_old) >= 0.01; ++it) {
             a_old = a;
-            a = 1.0 / (1.0 / a_old + (mu_log - log(mu) + log(a_old) - digamma_d(a_old)) /
+            a = 1.0 / (1.0 / a_old + (mu_log - log_d(mu) + log_d(a_old) - digamma_d(a_old)) /
                                          (a_old * a_old * (1.0 / a_old - trigamma_d(a_old))));
         }
         p0 = a; p1 = mu / a;

@@ -44,6 +44,7 @@
 #endif
 #define BQ_HDF __host__ __device__ __forceinline__
 #define BQ_HDI __host__ __device__ inline
+#define BQ_HDN __host__ __device__ BQ_NOINLINE inline  // one copy in device code
 
 namespace bq {
 
@@ -386,13 +387,13 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, int &ste
         double t1; int kind, slot;
         cu.piece(c, mv, t1, kind, slot);
         if (kind == 0) break;
-        if (kind < 0 && slot != mv.dm) acc += log((double)cu.n) - log((double)(cu.n + mv.sgn));
+        if (kind < 0 && slot != mv.dm) acc += log_d((double)cu.n) - log_d((double)(cu.n + mv.sgn));
         cu.advance(t1, kind);
     }
     if (mv.is_dep) {
         // N_old(d_old) + 1 and N_new(x) + 1, m counted (queues.pyx:1225-1230)
-        if (mv.sgn > 0) acc += log((double)(mv.n0 + 1)) - log((double)(cu.n + 1));
-        else acc += log((double)cu.n) - log((double)mv.n0);
+        if (mv.sgn > 0) acc += log_d((double)(mv.n0 + 1)) - log_d((double)(cu.n + 1));
+        else acc += log_d((double)cu.n) - log_d((double)mv.n0);
     }
     return acc;
 }
@@ -486,7 +487,7 @@ BQ_HDI double slice_stepout_seq(const G &g, double x0, double lower, double uppe
     double w = 1.0;
     const double gx0 = g(x0);
     ++evals;
-    const double logy = gx0 - (-log(1.0 - rng.uniform()));
+    const double logy = gx0 - (-log_d(1.0 - rng.uniform()));
     if (!(logy > BQ_NEG_INF)) return x0;
     const double u = w * rng.uniform();
     double L = x0 - u, R = x0 + (w - u);
@@ -659,7 +660,7 @@ __device__ __forceinline__ double group_max(double x, unsigned gmask) {
 
 // per-queue sufficient statistics of one chain (queues.pyx:1316-1336), every lane returns with ss[] filled
 template <int W>
-__device__ void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, int lane, unsigned gmask, bool want_logp,
+__device__ BQ_NOINLINE void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, int lane, unsigned gmask, bool want_logp,
                               double *logp_out) {
     double logp_acc = 0.0;
     for (int q = 0; q < Q; ++q) {
@@ -673,7 +674,7 @@ __device__ void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, int lane, uns
             if (s > 0.0) {
                 v[0] += 1.0; v[1] += s;
                 if (dist != D_EXP) {
-                    if (dist == D_GAMMA || s >= 1e-50) { v[2] += log(s); v[3] += 1.0; }
+                    if (dist == D_GAMMA || s >= 1e-50) { v[2] += log_d(s); v[3] += 1.0; }
                 }
             } else if (s == 0.0) v[5] += 1.0;
             if (want_logp) {
@@ -687,7 +688,7 @@ __device__ void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, int lane, uns
             const double mean_log = (v[3] > 0.0) ? v[2] / v[3] : 0.0;
             for (int p = qi.lo + lane; p < qi.hi; p += W) {
                 const double s = dyn_service(c, qi, p);
-                if (s >= 1e-50) { const double z = log(s) - mean_log; sq += z * z; }
+                if (s >= 1e-50) { const double z = log_d(s) - mean_log; sq += z * z; }
             }
             sq = group_sum<W>(sq, gmask);
         }
@@ -735,7 +736,7 @@ __device__ __forceinline__ bool group_slice(const G &g, double x0, double lower,
             const double g0 = __shfl_sync(gl.gmask, gv, 0, W);
             double u0a, u0b;
             stream_pair(rng, 0u, u0a, u0b);
-            logy = g0 - (-log(1.0 - u0a));  // rk_exponential = -log(1 - U)   (cdist.c:107-110)
+            logy = g0 - (-log_d(1.0 - u0a));  // rk_exponential = -log(1 - U)   (cdist.c:107-110)
             if (!(logy > BQ_NEG_INF)) { n_stuck += 1; n_evals += 1; return false; }  // sampling.pyx:289-291
         }
         const bool cand = (cidx != 0u);
@@ -758,7 +759,7 @@ __device__ __forceinline__ bool group_slice(const G &g, double x0, double lower,
 // Streams of (chain, sweep, event): TAG_MH and TAG_MH2 feed the two slice steps on the proposal, TAG_MH_AUX holds the
 // accept uniform (number 0) and the re-initialisation draws (numbers 2..).
 template <int W, int KMAX>
-__device__ void mh_update(const Chain &c, const EventCtx &ev, const DynArgs &A, unsigned long long gchain,
+__device__ BQ_NOINLINE void mh_update(const Chain &c, const EventCtx &ev, const DynArgs &A, unsigned long long gchain,
                           unsigned int gsw, const GroupLane &gl, long long &n_ev, long long &n_evals, long long &n_stuck,
                           long long &n_reject, int &steps) {
     const bool final_evt = (ev.e1 < 0);
@@ -777,7 +778,7 @@ __device__ void mh_update(const Chain &c, const EventCtx &ev, const DynArgs &A, 
         int tries = 0;
         for (; tries < 25; ++tries) {
             const double u = aux.uniform();
-            x_init = final_evt ? pr.b0 + (-log(1.0 - u)) : ev.a_e + (ev.d1 - ev.a_e) * u;
+            x_init = final_evt ? pr.b0 + (-log_d(1.0 - u)) : ev.a_e + (ev.d1 - ev.a_e) * u;
             if (pr.eval(x_init) > BQ_NEG_INF) break;
         }
         if (tries >= 25) return;

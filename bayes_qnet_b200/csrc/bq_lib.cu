@@ -375,10 +375,10 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
     CK(cudaStreamSynchronize(h->stream));
     // lanes per chain: wide groups hide the latency of a single chain's serial walk when chains are few; with many
     // chains narrower groups waste fewer lanes on speculative candidates (measured on B200, tools/probe_dyn.py)
-    h->dyn_w = (h->C >= 3072) ? 8 : (h->C >= 1536 ? 16 : 32);
+    h->dyn_w = (h->C >= 12288) ? 4 : (h->C >= 6144 ? 8 : (h->C >= 1536 ? 16 : 32));
     if (const char *env = getenv("BQ_DYN_W")) {
         int w = atoi(env);
-        if (w == 8 || w == 16 || w == 32) h->dyn_w = w;
+        if (w == 1 || w == 2 || w == 4 || w == 8 || w == 16 || w == 32) h->dyn_w = w;
     }
     if (const char *env = getenv("BQ_DYN_THREADS")) {
         int t = atoi(env);
@@ -410,11 +410,18 @@ template <int W>
 static void launch_dynamic_w(bq_handle *h, const DynArgs &A) {
     const int G = h->dyn_threads / W, blocks = (h->C + G - 1) / G;
     const size_t sm = (size_t)G * dyn_group_smem(h->Q, h->P);
+    if (sm > 48 * 1024) {  // many narrow groups per CTA: opt in to the large shared-memory carve-out
+        cudaFuncSetAttribute((const void *)sweep_dynamic_kernel<W, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaFuncSetAttribute((const void *)sweep_dynamic_kernel<W, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    }
     if (h->kmax <= 4) sweep_dynamic_kernel<W, 4><<<blocks, h->dyn_threads, sm, h->stream>>>(A);
     else sweep_dynamic_kernel<W, 8><<<blocks, h->dyn_threads, sm, h->stream>>>(A);
 }
 static void launch_dynamic(bq_handle *h, const DynArgs &A) {
-    if (h->dyn_w == 8) launch_dynamic_w<8>(h, A);
+    if (h->dyn_w == 1) launch_dynamic_w<1>(h, A);
+    else if (h->dyn_w == 2) launch_dynamic_w<2>(h, A);
+    else if (h->dyn_w == 4) launch_dynamic_w<4>(h, A);
+    else if (h->dyn_w == 8) launch_dynamic_w<8>(h, A);
     else if (h->dyn_w == 16) launch_dynamic_w<16>(h, A);
     else launch_dynamic_w<32>(h, A);
 }

@@ -252,7 +252,7 @@ def test_posterior_agrees_with_long_reference_runs(name):
     assert numpy.all(diagnostics.rhat(th) < 2.0)
 
 
-@pytest.mark.parametrize("width", ["8", "16", "32"])
+@pytest.mark.parametrize("width", ["1", "2", "4", "8", "16", "32"])
 @pytest.mark.parametrize("name", ["qnet3", "lng1", "mm3", "lnk", "psdelay"])
 def test_dynamic_kernel_group_widths(name, width, monkeypatch):
     """The dynamic-order kernel (per-chain queue order, free-time vectors) with W = 8 / 16 / 32 lanes per chain:
@@ -380,7 +380,7 @@ def test_mh_counts_and_group_widths(monkeypatch):
     g = helpers.golden("mh_mm3")
     net, arrv = helpers.golden_state(g, "s0")
     ref = None
-    for width in ("8", "16", "32"):
+    for width in ("1", "4", "8", "16", "32"):
         monkeypatch.setenv("BQ_DYN_W", width)
         with GibbsEngine(net, arrv, n_chains=1, seed=31) as eng:
             seq = eng.sequential_order()
@@ -396,8 +396,8 @@ def test_mh_counts_and_group_widths(monkeypatch):
             assert (st["nevents"], st["nreject"]) == (props, rejects)
             assert helpers.relerr(d[0], oc.d).max() < 1e-7 and helpers.relerr(th[0], oc.theta).max() < 1e-7
             ref = (d, th)
-        else:
-            assert numpy.array_equal(d, ref[0]) and numpy.array_equal(th, ref[1])
+        else:  # the sufficient statistics are summed in a width-dependent order: equal up to rounding
+            assert helpers.relerr(d, ref[0]).max() < 1e-9 and helpers.relerr(th, ref[1]).max() < 1e-9
 
 
 def test_mh_refused_for_ps():
