@@ -52,6 +52,9 @@ queues:
   - { name: DB, service: [M, 0.3] }
 """
 BYTES_PER_RESAMPLE = 16.0  # SURVEY.md 8d: source / GGk k=1 / DELAY visits
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the default configuration, from the ncu --set full
+# capture summarised in profiles/r1_static_final_ncu_full.txt (166.0 MB + 108.0 MB)
+NCU_TRAFFIC_DEFAULT = 273.98e6
 WORKLOAD = "3-tier web-service network (qnet3), %d tasks, 20%% observed, %d chains/GPU x %d sweeps per step"
 
 
@@ -304,7 +307,12 @@ def main():
                     "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / hbm_peak,
+                         "traffic": NCU_TRAFFIC_DEFAULT if (args.tasks, C, S) == (5000, 1024, 20) else None,
+                         "traffic_note": "bytes per launch from profiles/r1_static_final_ncu_full.txt; far BELOW the "
+                                         "algorithmic 16 B x resamples because the chain state stays in shared memory "
+                                         "for all sweeps of a launch",
+                         "peak_kind": peak_kind,
                          "kernel": "sweep_static_kernel<true>", "bytes_per_resample": BYTES_PER_RESAMPLE,
                          "resamples_per_launch": resamples_per_step, "launch_ms_mean": mean_ms, "launch_ms_max": worst_ms},
             "clocks": sampler.summary(),

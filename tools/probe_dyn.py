@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Timing probe for the dynamic-order sweep kernel (GPU): tandem source -> G/G/3 -> G/G/3 with LogNormal service
-(BASELINE.json configs[2] shape) at a chosen size, for each group width."""
+"""Timing probe for the dynamic-order sweep kernels (GPU): tandem source -> G/G/3 -> G/G/3 with LogNormal service
+(BASELINE.json configs[2] shape) or source -> PS -> delay station (configs[3] shape) at a chosen size, slice or MH
+sweeps, for each group width."""
 import argparse
 import json
 import os
@@ -28,6 +29,25 @@ queues:
 """
 
 
+PSDELAY = """
+states:
+  - name: INITIAL
+    queues: [ INITIAL ]
+    successors: [ TIER1 ]
+    initial: TRUE
+  - name: TIER1
+    queues: [ QPS ]
+    successors: [ TIER2 ]
+  - name: TIER2
+    queues: [ QDELAY ]
+queues:
+  - { name: INITIAL, service: [M, 1.0] }
+  - { name: QPS, type: PS, service: [M, 0.5] }
+  - { name: QDELAY, type: DELAY, service: [M, 2.0] }
+"""
+NETS = {"tandem": (TANDEM, "DFN2", 32.0), "ps": (PSDELAY, "PS", 80.0 / 3.0)}  # yaml, initializer, SURVEY 8d bytes / resample
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tasks", type=int, default=2000)
@@ -35,9 +55,17 @@ def main():
     ap.add_argument("--sweeps", type=int, default=5)
     ap.add_argument("--widths", default="8,16,32")
     ap.add_argument("--threads", default="128")
-    ap.add_argument("--yaml", default=None)
+    ap.add_argument("--net", default="tandem", choices=sorted(NETS) + ["qnet3"])
+    ap.add_argument("--mode", default="SLICE", choices=["SLICE", "MH"])
     args = ap.parse_args()
-    text = open(args.yaml).read() if args.yaml else TANDEM
+    from bayes_qnet_b200 import qnet
+    if args.net == "qnet3":
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+        import helpers
+        text, init, nbytes = helpers.QNET3, "DFN2", 16.0
+    else:
+        text, init, nbytes = NETS[args.net]
+    qnet.set_initialization_type(init)
     net = qnetu.qnet_from_text(text)
     qnetu.set_seed(13)
     t0 = time.time()
@@ -51,12 +79,16 @@ def main():
             os.environ["BQ_DYN_THREADS"] = th
             with GibbsEngine(net, ini, n_chains=args.chains, seed=7) as eng:
                 n = len(eng.schedule()[1])
-                eng.sweep(1, "SLICE", "BAYES")
-                eng.sweep(args.sweeps, "SLICE", "BAYES")
+                n = len(eng.sequential_order())
+                eng.sweep(1, args.mode, "BAYES")
+                eng.reset_stats()
+                eng.sweep(args.sweeps, args.mode, "BAYES")
                 ms = eng.last_sweep_ms()
                 st = eng.stats()
-                print(json.dumps({"W": int(w), "threads": int(th), "chains": args.chains, "events": eng.E, "eligible": n,
-                                  "ms": ms, "resamples_per_s": args.chains * args.sweeps * n / (ms / 1e3),
+                rate = st["nevents"] / (ms / 1e3)
+                print(json.dumps({"net": args.net, "mode": args.mode, "W": int(w), "threads": int(th), "chains": args.chains,
+                                  "events": eng.E, "eligible": n, "ms": ms, "resamples_per_s": rate,
+                                  "algorithmic_GBps": rate * nbytes / 1e9, "reject_frac": st["nreject"] / max(st["nevents"], 1),
                                   "evals_per_resample": st["slice_evals"] / st["nevents"],
                                   "walk_steps_per_resample": st["diff_len"] / st["nevents"],
                                   "stuck": st["n_stuck"]}), flush=True)
