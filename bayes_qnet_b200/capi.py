@@ -75,6 +75,7 @@ SYMBOLS = {
                                     ctypes.POINTER(ctypes.c_void_p)]),
     "bq_get_schedule": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), c_i32p, c_i32p]),
     "bq_get_sequential_order": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), c_i32p]),
+    "bq_get_mh_order": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), c_i32p]),
     "bq_rng_uniforms": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint32,
                                        ctypes.c_uint32, ctypes.c_int32, c_f64p]),
     "bq_kernel_info": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),

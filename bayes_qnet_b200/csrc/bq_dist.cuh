@@ -15,6 +15,10 @@
 #define BQ_NOINLINE
 #endif
 
+#define BQ_HDF __host__ __device__ __forceinline__
+#define BQ_HDI __host__ __device__ inline
+#define BQ_HDN __host__ __device__ BQ_NOINLINE inline  // one copy in device code
+
 namespace bq {
 
 // libdevice's fp64 log / lgamma are 100+ / 1000+ instructions and get inlined at every call site: one out-of-line
@@ -160,6 +164,66 @@ __device__ inline double slice_stepout(Rng &rng, const GammaPost &gp, int which,
         if (R - L < 1e-10) return L;
     }
 #undef BQ_GP
+    return x0;
+}
+
+// ---- one-lane slice sampling on an arbitrary log-density (the MH proposal) ------------------------------------
+// sampling._slice when a bound is infinite: stepping out with w0 = 1, doubling, m = 1024 (sampling.pyx:299-341),
+// then shrinkage.  Sequential; used for final events of MH sweeps (upper = inf).  On a collapsed bracket we keep x0
+// (the documented deviation from sampling.pyx:360-362).
+template <class G>
+BQ_HDI double slice_stepout_seq(const G &g, double x0, double lower, double upper, Rng &rng, long long &evals) {
+    double w = 1.0;
+    const double gx0 = g(x0);
+    ++evals;
+    const double logy = gx0 - (-log_d(1.0 - rng.uniform()));
+    if (!(logy > BQ_NEG_INF)) return x0;
+    const double u = w * rng.uniform();
+    double L = x0 - u, R = x0 + (w - u);
+    unsigned long long J = (unsigned long long)(rng.word() % 1025u);  // rk_interval(m): uniform on [0, m]
+    unsigned long long K = 1023ull - J;
+    while (J > 0) {
+        if (L <= lower) break;
+        ++evals;
+        if (g(L) <= logy) break;
+        L -= w; --J; w *= 2.0;
+    }
+    int guard = 0;
+    while (K > 0 && guard < 1100) {
+        if (R >= upper) break;
+        ++evals;
+        if (g(R) <= logy) break;
+        R += w; --K; w *= 2.0; ++guard;
+    }
+    if (L < lower) L = lower;
+    if (R > upper) R = upper;
+    for (int it = 0; it < 100000; ++it) {
+        const double x1 = L + (R - L) * rng.uniform();
+        ++evals;
+        if (g(x1) >= logy) return x1;
+        if (x1 > x0) R = x1; else L = x1;
+        if (R - L < 1e-10) return x0;
+    }
+    return x0;
+}
+
+// sampling._slice with finite bounds (sampling.pyx:283-298, 344-366), one lane, candidates in sequence: uniform 0 of
+// the stream draws the slice level, uniform c the c-th shrink candidate -- the same mapping the W-lane groups of the
+// dynamic-order kernel use.  Keeps x0 on a collapsed bracket.
+template <class G>
+BQ_HDI double slice_finite_seq(const G &g, double x0, double lower, double upper, Rng &rng, long long &evals) {
+    const double gx0 = g(x0);
+    ++evals;
+    const double logy = gx0 - (-log_d(1.0 - rng.uniform()));
+    if (!(logy > BQ_NEG_INF)) return x0;
+    double L = lower, R = upper;
+    for (int it = 0; it < 1000; ++it) {
+        const double x1 = L + (R - L) * rng.uniform();
+        ++evals;
+        if (g(x1) >= logy) return x1;
+        if (x1 > x0) R = x1; else L = x1;
+        if (R - L < 1e-10) return x0;
+    }
     return x0;
 }
 

@@ -42,9 +42,6 @@
 #else
 #define BQ_SYNCG(m) ((void)(m))
 #endif
-#define BQ_HDF __host__ __device__ __forceinline__
-#define BQ_HDI __host__ __device__ inline
-#define BQ_HDN __host__ __device__ BQ_NOINLINE inline  // one copy in device code
 
 namespace bq {
 
@@ -477,45 +474,6 @@ BQ_HDI void mh_setup(const Chain &c, const EventCtx &ev, MhProp &pr) {
         if (pr.Lh < 0.0) pr.Lh = 0.0;
         if (ev.t1 == Q_GGK) { pr.fifo1 = 1; pr.dp1 = c.fvec(c.qi[ev.q1], ev.p1)[0]; }
     }
-}
-
-// sampling._slice when a bound is infinite: stepping out with w0 = 1, doubling, m = 1024 (sampling.pyx:299-341),
-// then shrinkage.  Sequential; used for final events of MH sweeps (upper = inf).  On a collapsed bracket we keep x0
-// (the documented deviation from sampling.pyx:360-362).
-template <class G>
-BQ_HDI double slice_stepout_seq(const G &g, double x0, double lower, double upper, Rng &rng, long long &evals) {
-    double w = 1.0;
-    const double gx0 = g(x0);
-    ++evals;
-    const double logy = gx0 - (-log_d(1.0 - rng.uniform()));
-    if (!(logy > BQ_NEG_INF)) return x0;
-    const double u = w * rng.uniform();
-    double L = x0 - u, R = x0 + (w - u);
-    unsigned long long J = (unsigned long long)(rng.word() % 1025u);  // rk_interval(m): uniform on [0, m]
-    unsigned long long K = 1023ull - J;
-    while (J > 0) {
-        if (L <= lower) break;
-        ++evals;
-        if (g(L) <= logy) break;
-        L -= w; --J; w *= 2.0;
-    }
-    int guard = 0;
-    while (K > 0 && guard < 1100) {
-        if (R >= upper) break;
-        ++evals;
-        if (g(R) <= logy) break;
-        R += w; --K; w *= 2.0; ++guard;
-    }
-    if (L < lower) L = lower;
-    if (R > upper) R = upper;
-    for (int it = 0; it < 100000; ++it) {
-        const double x1 = L + (R - L) * rng.uniform();
-        ++evals;
-        if (g(x1) >= logy) return x1;
-        if (x1 > x0) R = x1; else L = x1;
-        if (R - L < 1e-10) return x0;
-    }
-    return x0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -72,6 +72,7 @@ struct bq_handle {
     int EF = 0, kmax = 1, dyn_w = 32, dyn_threads = 128;
     std::vector<int> q_off, q_foff, ord0;  // queue position ranges, F offsets, initial order
     std::vector<int> dyn_order;          // sweep order of the dynamic-order kernels
+    bool mh_dynamic = false;             // static-order handle: run MH sweeps in the dynamic-order kernel (BQ_MH_DYNAMIC)
     bool dyn_ready = false;              // dynamic arrays allocated
     bool dyn_stale = false;              // ... but the static kernel has moved d since they were built
     DynRec *d_order = nullptr;
@@ -590,6 +591,7 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         CKB(set_max((const void *)sweep_static_kernel<false, false>));
     }
     if (getenv("BQ_NO_EXP_FASTPATH")) h->all_exp = false;
+    if (const char *env = getenv("BQ_MH_DYNAMIC")) h->mh_dynamic = (env[0] == '1');
     if (const char *env = getenv("BQ_REFILL")) {
         int t = atoi(env);
         if (t >= 1 && t <= 32) h->refill = t;
@@ -761,8 +763,10 @@ static int launch_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t up
         if (int r = ensure_trace(h, n_sweeps)) return r;
     SweepArgs A;
     fill_args(h, A);
-    A.n_sweeps = n_sweeps; A.update = update; A.flags = (int)flags; A.trace_base = h->trace_len;
-    const bool use_dynamic = !h->static_order || (mode == BQ_MODE_MH && !(flags & FLAG_PARAMS_ONLY));
+    A.n_sweeps = n_sweeps; A.update = update; A.flags = (int)flags; A.trace_base = h->trace_len; A.mode = mode;
+    // MH sweeps of a static-order network run in the chromatic kernel too (closed-form proposal); BQ_MH_DYNAMIC=1
+    // sends them through the sequential dynamic-order kernel instead (cross-check of the two implementations)
+    const bool use_dynamic = !h->static_order || (mode == BQ_MODE_MH && !(flags & FLAG_PARAMS_ONLY) && h->mh_dynamic);
     if (use_dynamic && h->static_order)
         if (int rc = ensure_dynamic(h)) return rc;
     CK(cudaEventRecord(h->ev0, h->stream));
@@ -980,6 +984,14 @@ extern "C" int bq_get_sequential_order(bq_handle *h, int32_t *n_eligible, int32_
     if (!h) return fail(BQ_ERR_INVALID, "null handle");
     if (n_eligible) *n_eligible = (int)h->dyn_order.size();
     if (order) memcpy(order, h->dyn_order.data(), h->dyn_order.size() * sizeof(int));
+    return BQ_OK;
+}
+
+extern "C" int bq_get_mh_order(bq_handle *h, int32_t *n_eligible, int32_t *order) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    const std::vector<int> &o = (h->static_order && !h->mh_dynamic) ? h->order : h->dyn_order;
+    if (n_eligible) *n_eligible = (int)o.size();
+    if (order) memcpy(order, o.data(), o.size() * sizeof(int));
     return BQ_OK;
 }
 

@@ -46,7 +46,7 @@ struct SchedRec {
 };
 
 struct SweepArgs {
-    int E, Q, P, n_colors, n_sweeps, update, flags, trace_base, n_chains, refill;
+    int E, Q, P, n_colors, n_sweeps, update, flags, trace_base, n_chains, refill, mode;
     const int4 *rec;
     const int *color_off;
     const int *ev_q, *ev_p, *ev_pt;  // per event: queue, prev-by-queue, prev-by-task
@@ -314,6 +314,85 @@ __device__ __forceinline__ void run_class(const SweepArgs &A, double *d, const i
     n_ev += nev; n_evals += ev; n_stuck += stuck;
 }
 
+// One colour class of an MH-within-Gibbs sweep (Qnet.gibbs_resample, qnet.pyx:337-498) on a static-order network.
+// The TWOS proposal (queues.pyx:1239-1256) is closed form here:
+//   h(x) = lpdf_q0(x - b) + [e1] lpdf_q1(d_e1 - max(x, d_p1))   on [b, d_e1]  (b = max(a_e, d_p); no d_p1 for a delay
+// station), and so is the exact conditional used in the accept ratio (Cond::eval).  Each lane handles one event at a
+// time: two slice steps on h (call_sampler thin = 2, qnet.pyx:1292-1300; stepping out when the event is final and the
+// support unbounded), then u < exp(h(d_e) - h(d') + G(d') - G(d_e)) (qnet.pyx:425-431).  Same three counter streams
+// per (chain, sweep, event) as the dynamic-order kernel, so both implementations walk the same path.
+struct MhPropStatic {
+    const Cond *c;
+    double Lh, Uh;
+    __device__ __forceinline__ double operator()(double x) const {
+        if (x < Lh || x > Uh) return BQ_NEG_INF;
+        double v = lpdf(*c->c0, x - c->b);
+        if (c->has_e1) v += lpdf(*c->c1, c->d_e1 - (c->e1_fifo ? dmax(x, c->d_p1) : x));
+        return v;
+    }
+};
+
+__device__ __forceinline__ void run_class_mh(const SweepArgs &A, double *d, const int *q_type, const QConst *qc, int hi,
+                                             int *ctr, unsigned long long gchain, unsigned int gsw, long long &n_ev,
+                                             long long &n_evals, long long &n_reject) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(ctr, 32);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= hi) break;
+        const int my = base + lane;
+        if (my < hi) {
+            union { int4 v[3]; SchedRec r; } u;
+            u.v[0] = __ldg(&A.rec[3 * my]);
+            u.v[1] = __ldg(&A.rec[3 * my + 1]);
+            u.v[2] = __ldg(&A.rec[3 * my + 2]);
+            Cond cd;
+            double x0, a_e, upper;
+            cond_load(cd, u.r, d, q_type, qc, x0, a_e, upper, INFINITY);
+            const bool final_evt = !cd.has_e1;
+            MhPropStatic h;
+            h.c = &cd;
+            h.Lh = cd.has_e1 ? dmax(cd.b, 0.0) : cd.b;
+            h.Uh = cd.has_e1 ? cd.d_e1 : INFINITY;
+            const unsigned int e = (unsigned int)u.r.e;
+            bool skip = (final_evt && (A.flags & FLAG_NO_FINAL)) || (h.Uh - h.Lh < 1e-10) ||
+                        (!final_evt && cd.d_e1 - a_e < 1e-10);  // qnet.pyx:361, 385, 440
+            if (!skip) {
+                Rng aux;
+                aux.init(A.seed, gchain, gsw, e, TAG_MH_AUX);
+                const double u_acc = aux.uniform();
+                (void)aux.uniform();
+                const double h0 = h(x0);
+                double x_new = x0;
+                if (!(h0 > BQ_NEG_INF)) {  // qnet.pyx:389-397, 444-451
+                    int tries = 0;
+                    for (; tries < 25; ++tries) {
+                        const double uu = aux.uniform();
+                        x_new = final_evt ? cd.b + (-log_d(1.0 - uu)) : a_e + (cd.d_e1 - a_e) * uu;
+                        if (h(x_new) > BQ_NEG_INF) break;
+                    }
+                    skip = tries >= 25;
+                }
+                if (!skip) {
+#pragma unroll 1
+                    for (int step = 0; step < 2; ++step) {
+                        Rng rng;
+                        rng.init(A.seed, gchain, gsw, e, step == 0 ? TAG_MH : TAG_MH2);
+                        x_new = final_evt ? slice_stepout_seq(h, x_new, h.Lh, h.Uh, rng, n_evals)
+                                          : slice_finite_seq(h, x_new, h.Lh, h.Uh, rng, n_evals);
+                    }
+                    n_ev += 1;
+                    const double ratio = exp(h0 - h(x_new) + (cd.eval(x_new) - cd.eval(x0)));
+                    if (u_acc < ratio) d[u.r.e] = x_new;
+                    else n_reject += 1;
+                }
+            }
+        }
+    }
+}
+
 template <int N>
 __device__ __forceinline__ void block_reduce_sum(double (&v)[N], double *scratch, double *out) {
     // deterministic: warp shuffle tree, then warp 0 adds the per-warp partials in warp order
@@ -436,7 +515,7 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
     int *q_type = reinterpret_cast<int *>(ss + Q);
     int *q_dist = q_type + Q;
     int *q_poff = q_dist + Q;
-    __shared__ unsigned long long cnt[4];
+    __shared__ unsigned long long cnt[5];
     __shared__ double logp_sh;
     __shared__ int work_ctr[2];
 
@@ -444,7 +523,7 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
     for (int i = threadIdx.x; i < Q; i += blockDim.x) {
         q_type[i] = A.q_type[i]; q_dist[i] = A.q_dist[i]; q_poff[i] = A.q_poff[i];
     }
-    if (threadIdx.x < 4) cnt[threadIdx.x] = 0ull;
+    if (threadIdx.x < 5) cnt[threadIdx.x] = 0ull;
     if (SMEM) {
         // coalesced 16-byte loads; each chain's row is 16 B aligned when E is even, else fall back
         if ((E & 1) == 0) {
@@ -463,7 +542,7 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
     __syncthreads();
 
     const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain);
-    long long n_ev = 0, n_evals = 0, n_stuck = 0, n_pevals = 0;
+    long long n_ev = 0, n_evals = 0, n_stuck = 0, n_pevals = 0, n_reject = 0;
     double tmax = 0.0;
 
     for (int sw = 0; sw < A.n_sweeps; ++sw) {
@@ -479,7 +558,9 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
         for (int c = 0; c < n_colors; ++c) {
             const int hi = A.color_off[c + 1];
             if (threadIdx.x == 0) work_ctr[(c + 1) & 1] = hi;  // next class starts where this one ends
-            if (ALL_EXP)
+            if (A.mode == MODE_MH)
+                run_class_mh(A, d, q_type, qc, hi, &work_ctr[c & 1], gchain, gsw, n_ev, n_evals, n_reject);
+            else if (ALL_EXP)
                 run_class<CondExp>(A, d, q_type, qc, hi, &work_ctr[c & 1], tmax, gchain, gsw, n_ev, n_evals, n_stuck);
             else
                 run_class<CondGen>(A, d, q_type, qc, hi, &work_ctr[c & 1], tmax, gchain, gsw, n_ev, n_evals, n_stuck);
@@ -530,8 +611,9 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
     atomicAdd(&cnt[1], (unsigned long long)n_evals);
     atomicAdd(&cnt[2], (unsigned long long)n_pevals);
     atomicAdd(&cnt[3], (unsigned long long)n_stuck);
+    atomicAdd(&cnt[4], (unsigned long long)n_reject);
     __syncthreads();
-    if (threadIdx.x < 4) A.stats[(size_t)chain * BQ_NSTAT + threadIdx.x] += (long long)cnt[threadIdx.x];
+    if (threadIdx.x < 5) A.stats[(size_t)chain * BQ_NSTAT + threadIdx.x] += (long long)cnt[threadIdx.x];
 }
 
 // ---- parity / reporting kernels ---------------------------------------------------------------

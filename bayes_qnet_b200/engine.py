@@ -242,6 +242,14 @@ class GibbsEngine(object):
         capi.check(self._L.bq_get_sequential_order(self._h, None, capi.ptr(order, capi.c_i32p)))
         return order
 
+    def mh_order(self):
+        """The order in which MH sweeps visit the events (chromatic schedule for static-order networks)."""
+        ne = ctypes.c_int32()
+        capi.check(self._L.bq_get_mh_order(self._h, ctypes.byref(ne), None))
+        order = numpy.empty(ne.value, dtype=numpy.int32)
+        capi.check(self._L.bq_get_mh_order(self._h, None, capi.ptr(order, capi.c_i32p)))
+        return order
+
     def kernel_info(self):
         t, s, m = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         capi.check(self._L.bq_kernel_info(self._h, ctypes.byref(t), ctypes.byref(s), ctypes.byref(m)))

@@ -161,10 +161,12 @@ int bq_trace_dev(bq_handle *h, double **theta_dev, double **mean_wait_dev, doubl
 int bq_get_schedule(bq_handle *h, int32_t *n_colors, int32_t *n_eligible, int32_t *color_off,
                     int32_t *order);
 
-/* The scan order of the sequential kernels (MH sweeps on any network, slice sweeps on networks with multi-server
- * or PS queues): the resample-eligible events queue after queue, each queue in its initial arrival order.  MH
- * visits them as Qnet.gibbs_resample does (qnet.pyx:354-368). */
+/* The scan order of the sequential (dynamic-order) kernels: the resample-eligible events queue after queue, each
+ * queue in its initial arrival order. */
 int bq_get_sequential_order(bq_handle *h, int32_t *n_eligible, int32_t *order);
+/* The order in which BQ_MODE_MH sweeps visit the events (Qnet.gibbs_resample, qnet.pyx:354-368): the schedule of
+ * bq_get_schedule for static-order networks, the sequential order otherwise. */
+int bq_get_mh_order(bq_handle *h, int32_t *n_eligible, int32_t *order);
 
 /* Raw counter-based RNG stream (Philox4x32-10) exactly as the kernels consume it: n uniforms in [0,1)
  * for (seed, global chain id, sweep index, event or queue id, stream tag: 1 slice, 2 parameters, 3/4 the two slice

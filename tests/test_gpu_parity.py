@@ -336,11 +336,16 @@ def test_mixed_disciplines_match_oracle(name):
         assert numpy.array_equal(full["proc"][0], oc.proc) and numpy.array_equal(full["next_byq"][0], oc.next_byq)
 
 
+@pytest.mark.parametrize("impl", ["native", "dynamic"])
 @pytest.mark.parametrize("name", helpers.MH_NETS)
-def test_mh_proposal_and_sweeps(name):
+def test_mh_proposal_and_sweeps(name, impl, monkeypatch):
     """MH-within-Gibbs (Qnet.gibbs_resample, qnet.pyx:337): bq_mh_proposal against the reference's Pwfun values
     (tests/golden/mh_*.npz); MH sweeps -- two slice steps on the proposal, exact-conditional accept ratio, commit --
     against the oracle, interleaved with slice sweeps (static-order handles switch kernels in between)."""
+    if impl == "dynamic":  # static-order networks: the MH update of the sequential dynamic-order kernel instead of
+        if name in helpers.DYNAMIC_NETS:  # the chromatic kernel's (two implementations of one algorithm)
+            pytest.skip("dynamic-order networks have one implementation")
+        monkeypatch.setenv("BQ_MH_DYNAMIC", "1")
     g = helpers.golden("mh_" + name)
     net, arrv = helpers.golden_state(g, "s0")
     with GibbsEngine(net, arrv, n_chains=4, seed=606, chain_offset=1) as eng:
@@ -349,9 +354,9 @@ def test_mh_proposal_and_sweeps(name):
             assert numpy.array_equal(numpy.isfinite(v), numpy.isfinite(ref)), "support differs at row %d" % r
             m = numpy.isfinite(ref)
             assert helpers.relerr(v[m], ref[m]).max() < TOL
-        seq = eng.sequential_order()
+        seq = eng.mh_order()
         off, order = eng.schedule()
-        assert sorted(seq) == sorted(order)
+        assert sorted(seq) == sorted(order) == sorted(eng.sequential_order())
         ocs = [helpers.oracle_chain(net, arrv) for _ in range(2)]
         chains = (0, 3)
         props = rejects = 0
@@ -383,7 +388,7 @@ def test_mh_counts_and_group_widths(monkeypatch):
     for width in ("1", "4", "8", "16", "32"):
         monkeypatch.setenv("BQ_DYN_W", width)
         with GibbsEngine(net, arrv, n_chains=1, seed=31) as eng:
-            seq = eng.sequential_order()
+            seq = eng.mh_order()
             eng.sweep(5, "MH", "BAYES")
             st, d, th = eng.stats(), eng.state(), eng.params()
         if ref is None:

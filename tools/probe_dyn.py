@@ -80,6 +80,7 @@ def main():
             with GibbsEngine(net, ini, n_chains=args.chains, seed=7) as eng:
                 n = len(eng.schedule()[1])
                 n = len(eng.sequential_order())
+                impl = eng.kernel_info()
                 eng.sweep(1, args.mode, "BAYES")
                 eng.reset_stats()
                 eng.sweep(args.sweeps, args.mode, "BAYES")
