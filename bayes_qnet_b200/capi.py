@@ -35,7 +35,8 @@ class BqArrivals(ctypes.Structure):
 
 class BqStats(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int64) for k in ("nevents", "nreject", "num_diff", "diff_len", "slice_calls",
-                                              "slice_evals", "n_sweeps", "n_launches", "param_evals", "n_stuck")]
+                                              "slice_evals", "n_sweeps", "n_launches", "param_evals", "n_stuck",
+                                              "n_redone")]
 
 
 class BqError(RuntimeError):

@@ -26,6 +26,19 @@ namespace bq {
 __host__ __device__ BQ_NOINLINE inline double log_d(double x) { return log(x); }
 __host__ __device__ BQ_NOINLINE inline double lgamma_d(double x) { return lgamma(x); }
 
+// log of a small positive integer (the N(t) + 1 of processor sharing, queues.pyx:1225-1230): table in constant
+// memory on the device, filled by the library with the host's log(); plain log() on the host
+#if defined(__CUDACC__)
+__constant__ double c_log_count[256];
+#endif
+__host__ __device__ __forceinline__ double log_count(int n) {
+#if defined(__CUDA_ARCH__)
+    return (n >= 0 && n < 256) ? c_log_count[n] : log_d((double)n);
+#else
+    return log((double)n);
+#endif
+}
+
 enum { Q_GGK = 0, Q_DELAY = 1, Q_PS = 2 };
 enum { D_EXP = 0, D_GAMMA = 1, D_LOGNORMAL = 2 };
 
@@ -60,6 +73,17 @@ __host__ __device__ __forceinline__ void qconst_set(QConst &qc, int dist, double
 __host__ __device__ BQ_NOINLINE inline double lpdf_log(const QConst &qc, double s) {
     if (qc.dist == D_GAMMA) return qc.c1 * log_d(s) - s * qc.inv + qc.c0;
     const double ls = log_d(s), z = ls - qc.c1;
+    return qc.c0 - ls - z * z * qc.inv;
+}
+// the same with log(s) supplied by the caller (the dynamic-order kernels cache it per position): no transcendental
+__host__ __device__ __forceinline__ double lpdf_ls(const QConst &qc, double s, double ls) {
+    if (qc.dist == D_EXP) return qc.c0 - s * qc.inv;
+    if (qc.dist == D_GAMMA) {
+        if (qc.c1 == 0.0) return qc.c0 - s * qc.inv;
+        return qc.c1 * ls - s * qc.inv + qc.c0;
+    }
+    if (s == 0.0) return BQ_NEG_INF;
+    const double z = ls - qc.c1;
     return qc.c0 - ls - z * z * qc.inv;
 }
 __host__ __device__ __forceinline__ double lpdf(const QConst &qc, double s) {

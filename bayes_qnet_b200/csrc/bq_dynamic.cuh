@@ -12,6 +12,8 @@
 //
 //   ord[p], pos[e]   the event at position p / the position of event e
 //   at[p], dq[p]     arrival and departure time of the event at position p
+//   ls[p]            log of its service time, for FIFO queues and delay stations with Gamma / LogNormal service:
+//                    the "old" half of every lpdf(s_new) - lpdf(s_old) then costs no transcendental
 //   F[p][k]          k-server FIFO queues: the k server-free times seen by the event at position p, ascending
 //                    (the reference's Event.d_proc_prev, arrivals.pxd:30, as a sorted multiset: services
 //                    depend only on min F, and replacing the minimum by the event's own departure is the
@@ -63,6 +65,7 @@ struct DynArgs {
     double *state;        // [C][E]  d by event
     int *ord, *pos;       // [C][E]
     double *at, *dq;      // [C][E]  by position
+    double *ls;           // [C][E]  by position: log of the service time (queues with Gamma / LogNormal service)
     double *F;            // [C][EF] by position
     int *dord, *dpos;     // [C][E]  PS
     double *dt, *sq;      // [C][E]  PS
@@ -110,7 +113,7 @@ struct FreeVec {
 struct Chain {
     double *d;
     int *ord, *pos;
-    double *at, *dq, *F;
+    double *at, *dq, *ls, *F;
     int *dord, *dpos;
     double *dt, *sq;
     const QInfo *qi;
@@ -123,6 +126,7 @@ struct Chain {
         pos = a.pos + c * a.E;
         at = a.at + c * a.E;
         dq = a.dq + c * a.E;
+        ls = a.ls + c * a.E;
         F = a.F + c * a.EF;
         dord = a.dord ? a.dord + c * a.E : nullptr;
         dpos = a.dpos ? a.dpos + c * a.E : nullptr;
@@ -154,6 +158,25 @@ BQ_HDF void event_load(const Chain &c, const DynRec &rec, EventCtx &ev) {
     }
 }
 
+// What one evaluation of the conditional read: walk steps, and the closed ranges of positions it touched in the
+// queue of e (lo0..hi0), in the queue of the task's next event (lo1..hi1) and, for PS queues, of slots of the
+// sorted-departure arrays (dlo..dhi).  The batch kernel commits an update only if no earlier update of the same
+// batch wrote into these ranges.  Ranges are conservative (a superset is always safe).
+struct Touch {
+    int steps, lo0, hi0, lo1, hi1, dlo, dhi;
+    BQ_HDF void reset() { steps = 0; lo0 = lo1 = dlo = 0x7fffffff; hi0 = hi1 = dhi = -1; }
+    BQ_HDF void p0(int p) { lo0 = p < lo0 ? p : lo0; hi0 = p > hi0 ? p : hi0; }
+    BQ_HDF void p1(int p) { lo1 = p < lo1 ? p : lo1; hi1 = p > hi1 ? p : hi1; }
+    BQ_HDF void pa(bool first, int p) { if (first) p0(p); else p1(p); }
+    BQ_HDF void pd(int p) { dlo = p < dlo ? p : dlo; dhi = p > dhi ? p : dhi; }
+    BQ_HDF void merge(const Touch &o) {
+        steps += o.steps;
+        lo0 = o.lo0 < lo0 ? o.lo0 : lo0; hi0 = o.hi0 > hi0 ? o.hi0 : hi0;
+        lo1 = o.lo1 < lo1 ? o.lo1 : lo1; hi1 = o.hi1 > hi1 ? o.hi1 : hi1;
+        dlo = o.dlo < dlo ? o.dlo : dlo; dhi = o.dhi > dhi ? o.dhi : dhi;
+    }
+};
+
 // first index in [lo, hi) whose value is > t, galloping from `hint`
 BQ_HDI int upper_from(const double *v, int lo, int hi, int hint, double t) {
     if (hint < lo) hint = lo;
@@ -183,7 +206,7 @@ BQ_HDI int upper_from(const double *v, int lo, int hi, int hint, double t) {
 // FIFO queue with k servers: likelihoodDelta(diffListForDeparture(e, x))   (queues.pyx:470-511, 83-95)
 // ---------------------------------------------------------------------------------------------
 template <int KMAX>
-BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, int &steps) {
+BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, Touch &tc) {
     const QInfo &q = c.qi[ev.q0];
     const QConst &qc = c.qc[ev.q0];
     const int k = q.k;
@@ -195,19 +218,21 @@ BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, int &s
     if (s_new < 0.0) return BQ_NEG_INF;
     const double s_old = ev.x0 - st;
     double acc = 0.0;
-    if (s_new != s_old) acc = lpdf(qc, s_new) - lpdf(qc, s_old);
+    if (s_new != s_old) acc = lpdf(qc, s_new) - lpdf_ls(qc, s_old, c.ls[ev.p0]);
     M.replace_min(x);
     fi += k;
+    tc.p0(ev.p0);
     for (int p = ev.p0 + 1; p < q.hi; ++p, fi += k) {
+        tc.p0(p);
         if (M.equals(fi, k)) break;  // same free times as before: nothing after p changes
-        ++steps;
+        ++tc.steps;
         const double bn = M.v[0], bo = fi[0], di = c.dq[p];
         if (bn != bo) {
             const double ai = c.at[p];
             const double sn = di - dmax(ai, bn);
             if (sn < 0.0) return BQ_NEG_INF;
             const double so = di - dmax(ai, bo);
-            if (sn != so) acc += lpdf(qc, sn) - lpdf(qc, so);
+            if (sn != so) acc += lpdf(qc, sn) - lpdf_ls(qc, so, c.ls[p]);
         }
         M.replace_min(di);
     }
@@ -216,13 +241,18 @@ BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, int &s
 
 // Position e1 (now at p1) will occupy once its arrival is x: before the first OTHER event whose arrival is > x
 // (stable sort by arrival, queues.pyx:537).
-BQ_HDF int new_rank(const Chain &c, const QInfo &q, int p1, double x, double a_old) {
+BQ_HDF int new_rank(const Chain &c, const QInfo &q, int p1, double x, double a_old, Touch &tc) {
+    tc.p1(p1);
     if (x >= a_old) {
         int j = p1;
         while (j + 1 < q.hi && c.at[j + 1] <= x) ++j;
+        tc.p1(j + 1 < q.hi ? j + 1 : j);
         return j;
     }
-    return upper_from(c.at, q.lo, p1, p1 - 1, x);
+    const int j = upper_from(c.at, q.lo, p1, p1 - 1, x);
+    const int far = j - (p1 - j) - 1;  // the backward gallop overshoots by at most the distance covered
+    tc.p1(far > q.lo ? far : q.lo);
+    return j;
 }
 
 // old position of the event that sits at position t once e1 has moved from p1 to j (t != j)
@@ -233,30 +263,33 @@ BQ_HDF int moved_src(int t, int j, int p1) {
 
 // likelihoodDelta(diffListForArrival(e1, x))   (queues.pyx:514-591, 83-95)
 template <int KMAX>
-BQ_HDI double ggk_arr_delta(const Chain &c, const EventCtx &ev, double x, int &steps) {
+BQ_HDI double ggk_arr_delta(const Chain &c, const EventCtx &ev, double x, Touch &tc) {
     const QInfo &q = c.qi[ev.q1];
     const QConst &qc = c.qc[ev.q1];
     const int k = q.k, p1 = ev.p1;
     const double a_old = ev.x0;
-    const int j = new_rank(c, q, p1, x, a_old);
+    const int j = new_rank(c, q, p1, x, a_old, tc);
     const int ps = (j < p1) ? j : p1, pe = (j < p1) ? p1 : j;
     FreeVec<KMAX> M;
     M.load(c.fvec(q, ps), k);  // predecessors of position ps are untouched
+    tc.p1(ps);
     double acc = 0.0;
     for (int t = ps; t < q.hi; ++t) {
         double ai, ai_old, di;
         const double *fo;  // the vector this event saw before the move
+        int sp = p1;       // ... and its position then
         if (t == j) { ai = x; ai_old = a_old; di = ev.d1; fo = c.fvec(q, p1); }
         else {
-            const int sp = moved_src(t, j, p1);
+            sp = moved_src(t, j, p1);
+            tc.p1(sp);
             ai = ai_old = c.at[sp]; di = c.dq[sp]; fo = c.fvec(q, sp);
             if (t > pe && M.equals(fo, k)) break;
         }
-        ++steps;
+        ++tc.steps;
         const double sn = di - dmax(ai, M.v[0]);
         if (sn < 0.0) return BQ_NEG_INF;
         const double so = di - dmax(ai_old, fo[0]);
-        if (sn != so) acc += lpdf(qc, sn) - lpdf(qc, so);
+        if (sn != so) acc += lpdf(qc, sn) - lpdf_ls(qc, so, c.ls[sp]);
         M.replace_min(di);
     }
     return acc;
@@ -301,7 +334,8 @@ struct PsCursor {
     }
 };
 
-BQ_HDI void ps_move_setup(const Chain &c, int q, int pm, int m, bool is_dep, double t_old, double t_new, PsMove &mv) {
+BQ_HDI void ps_move_setup(const Chain &c, int q, int pm, int m, bool is_dep, double t_old, double t_new, PsMove &mv,
+                          Touch &tc) {
     const QInfo &qi = c.qi[q];
     mv.q = q; mv.pm = pm; mv.dm = c.dpos[m]; mv.is_dep = is_dep;
     mv.lo_q = qi.lo; mv.hi_q = qi.hi;
@@ -314,6 +348,16 @@ BQ_HDI void ps_move_setup(const Chain &c, int q, int pm, int m, bool is_dep, dou
     mv.ia = upper_from(c.at, mv.lo_q, mv.hi_q, pm, mv.lo);
     mv.id = upper_from(c.dt, mv.lo_q, mv.hi_q, mv.dm, mv.lo);
     mv.n0 = (mv.ia - mv.lo_q) - (mv.id - mv.lo_q);
+    // the gallops probe between the hint and about twice the distance to the answer
+    const bool first = is_dep;  // a departure move happens in the queue of e, an arrival move in the queue of e1
+    int far = 2 * mv.ia - pm;
+    far = far < mv.lo_q ? mv.lo_q : (far >= mv.hi_q ? mv.hi_q - 1 : far);
+    tc.pa(first, pm); tc.pa(first, far); tc.pa(first, mv.ia < mv.hi_q ? mv.ia : mv.hi_q - 1);
+    if (mv.ia > mv.lo_q) tc.pa(first, mv.ia - 1);
+    far = 2 * mv.id - mv.dm;
+    far = far < mv.lo_q ? mv.lo_q : (far >= mv.hi_q ? mv.hi_q - 1 : far);
+    tc.pd(mv.dm); tc.pd(far); tc.pd(mv.id < mv.hi_q ? mv.id : mv.hi_q - 1);
+    if (mv.id > mv.lo_q) tc.pd(mv.id - 1);
 }
 
 // change of an event's service: it is in the queue on [b_i, e_i] ^ I; MINE = it is the moved event itself
@@ -322,7 +366,7 @@ BQ_HDI double ps_delta_service(const Chain &c, const PsMove &mv, double b_i, dou
     PsCursor cu;
     cu.start(mv);
     double acc = 0.0;
-    for (;;) {
+    for (;;) {  // reads at[] / dt[] only inside the ranges ps_apply_move reports
         double t1; int kind, slot;
         cu.piece(c, mv, t1, kind, slot);
         const double a = (cu.t0 > b_i) ? cu.t0 : b_i, b = (t1 < e_i) ? t1 : e_i;
@@ -340,7 +384,7 @@ BQ_HDI double ps_delta_service(const Chain &c, const PsMove &mv, double b_i, dou
 // Visits every event of the queue whose service changes.  COMMIT = false: returns likelihoodDelta (sum of
 // lpdf(s_new) - lpdf(s_old) plus the log N terms).  COMMIT = true: stores the new service times (lane 0), returns 0.
 template <bool COMMIT>
-BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, int &steps) {
+BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, Touch &tc) {
     const QConst &qc = c.qc[mv.q];
     double acc = 0.0;
     {   // the moved event
@@ -352,12 +396,14 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, int &ste
         else acc += lpdf(qc, sn) - lpdf(qc, so);
     }
     // events in the queue just after lo (other than m): scan back over the arrivals <= lo
+    const bool first = mv.is_dep;
     int need = mv.n0 - ((mv.sgn < 0) ? 1 : 0);
     for (int p = mv.ia - 1; p >= mv.lo_q && need > 0; --p) {
+        tc.pa(first, p);
         if (p == mv.pm) continue;
         const double di = c.dq[p];
         if (!(di > mv.lo)) continue;
-        --need; ++steps;
+        --need; ++tc.steps;
         const double ds = ps_delta_service<false>(c, mv, mv.lo, di);
         const double so = c.sq[p];
         double sn = so + ds;
@@ -366,9 +412,21 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, int &ste
         else acc += lpdf(qc, sn) - lpdf(qc, so);
     }
     // events that arrive inside I
+    {   // every merge over I reads at[] up to the first arrival >= hi and dt[] up to the first departure >= hi
+        PsCursor cu;
+        cu.start(mv);
+        for (;;) {
+            double t1; int kind, slot;
+            cu.piece(c, mv, t1, kind, slot);
+            if (kind == 0) break;
+            cu.advance(t1, kind);
+        }
+        tc.pa(first, cu.ia < mv.hi_q ? cu.ia : mv.hi_q - 1);
+        tc.pd(cu.id < mv.hi_q ? cu.id : mv.hi_q - 1);
+    }
     for (int p = mv.ia; p < mv.hi_q && c.at[p] < mv.hi; ++p) {
         if (p == mv.pm) continue;
-        ++steps;
+        ++tc.steps;
         const double ds = ps_delta_service<false>(c, mv, c.at[p], c.dq[p]);
         const double so = c.sq[p];
         double sn = so + ds;
@@ -384,13 +442,13 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, int &ste
         double t1; int kind, slot;
         cu.piece(c, mv, t1, kind, slot);
         if (kind == 0) break;
-        if (kind < 0 && slot != mv.dm) acc += log_d((double)cu.n) - log_d((double)(cu.n + mv.sgn));
+        if (kind < 0 && slot != mv.dm) acc += log_count(cu.n) - log_count(cu.n + mv.sgn);
         cu.advance(t1, kind);
     }
     if (mv.is_dep) {
         // N_old(d_old) + 1 and N_new(x) + 1, m counted (queues.pyx:1225-1230)
-        if (mv.sgn > 0) acc += log_d((double)(mv.n0 + 1)) - log_d((double)(cu.n + 1));
-        else acc += log_d((double)cu.n) - log_d((double)mv.n0);
+        if (mv.sgn > 0) acc += log_count(mv.n0 + 1) - log_count(cu.n + 1);
+        else acc += log_count(cu.n) - log_count(mv.n0);
     }
     return acc;
 }
@@ -399,39 +457,41 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, int &ste
 // the conditional of d_e: inner_dfun(x) - lik0   (qnet.pyx:1340-1357)
 // ---------------------------------------------------------------------------------------------
 template <int KMAX>
-BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, int &steps) {
+BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, Touch &tc) {
     double g;
+    tc.p0(ev.p0);
+    if (ev.e1 >= 0) tc.p1(ev.p1);
     if (ev.t0 == Q_GGK) {
-        g = ggk_dep_delta<KMAX>(c, ev, x, steps);
+        g = ggk_dep_delta<KMAX>(c, ev, x, tc);
     } else if (ev.t0 == Q_PS) {
         if (x < ev.a_e) return BQ_NEG_INF;
         g = 0.0;
         if (x != ev.x0) {
             PsMove mv;
-            ps_move_setup(c, ev.q0, ev.p0, ev.e, true, ev.x0, x, mv);
-            g = ps_apply_move<false>(c, mv, 0, steps);
+            ps_move_setup(c, ev.q0, ev.p0, ev.e, true, ev.x0, x, mv, tc);
+            g = ps_apply_move<false>(c, mv, 0, tc);
         }
     } else {  // DelayStation: s = d - a, single-event diff list (queues.pyx:745-784)
         const double sn = x - ev.a_e, so = ev.x0 - ev.a_e;
         if (sn < 0.0) return BQ_NEG_INF;
-        g = (sn != so) ? lpdf(c.qc[ev.q0], sn) - lpdf(c.qc[ev.q0], so) : 0.0;
+        g = (sn != so) ? lpdf(c.qc[ev.q0], sn) - lpdf_ls(c.qc[ev.q0], so, c.ls[ev.p0]) : 0.0;
     }
     if (!(g > BQ_NEG_INF) || ev.e1 < 0) return g;
     double g1;
     if (ev.t1 == Q_GGK) {
-        g1 = ggk_arr_delta<KMAX>(c, ev, x, steps);
+        g1 = ggk_arr_delta<KMAX>(c, ev, x, tc);
     } else if (ev.t1 == Q_PS) {
         if (x > ev.d1) return BQ_NEG_INF;
         g1 = 0.0;
         if (x != ev.x0) {
             PsMove mv;
-            ps_move_setup(c, ev.q1, ev.p1, ev.e1, false, ev.x0, x, mv);
-            g1 = ps_apply_move<false>(c, mv, 0, steps);
+            ps_move_setup(c, ev.q1, ev.p1, ev.e1, false, ev.x0, x, mv, tc);
+            g1 = ps_apply_move<false>(c, mv, 0, tc);
         }
     } else {
         const double sn = ev.d1 - x, so = ev.d1 - ev.x0;
         if (sn < 0.0) return BQ_NEG_INF;
-        g1 = (sn != so) ? lpdf(c.qc[ev.q1], sn) - lpdf(c.qc[ev.q1], so) : 0.0;
+        g1 = (sn != so) ? lpdf(c.qc[ev.q1], sn) - lpdf_ls(c.qc[ev.q1], so, c.ls[ev.p1]) : 0.0;
     }
     return g + g1;
 }
@@ -518,39 +578,49 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
     int j1 = ev.p1;
     if (ev.e1 >= 0 && ev.t1 != Q_DELAY) {
         const QInfo &q1 = c.qi[ev.q1];
-        if (ev.t1 == Q_GGK) j1 = new_rank(c, q1, ev.p1, x, ev.x0);
+        Touch tmp;
+        tmp.reset();
+        if (ev.t1 == Q_GGK) j1 = new_rank(c, q1, ev.p1, x, ev.x0, tmp);
         else {  // PS: rank among the other arrivals
             j1 = upper_from(c.at, q1.lo, q1.hi, ev.p1, x);
             if (c.at[ev.p1] <= x) --j1;
         }
     }
-    int dummy = 0;
+    Touch dummy;
+    dummy.reset();
     if (ev.t0 == Q_PS) {  // new service times of everything that overlaps the moved interval
         PsMove mv;
-        ps_move_setup(c, ev.q0, ev.p0, ev.e, true, ev.x0, x, mv);
+        ps_move_setup(c, ev.q0, ev.p0, ev.e, true, ev.x0, x, mv, dummy);
         ps_apply_move<true>(c, mv, lane, dummy);
     }
     if (ev.e1 >= 0 && ev.t1 == Q_PS) {
         PsMove mv;
-        ps_move_setup(c, ev.q1, ev.p1, ev.e1, false, ev.x0, x, mv);
+        ps_move_setup(c, ev.q1, ev.p1, ev.e1, false, ev.x0, x, mv, dummy);
         ps_apply_move<true>(c, mv, lane, dummy);
     }
     // ---- departure side --------------------------------------------------------------------------------------
-    if (ev.t0 == Q_GGK) {  // refresh the free-time vectors downstream of e
+    const bool log0 = (c.qi[ev.q0].dist != D_EXP);
+    if (ev.t0 == Q_GGK) {  // e's own service, then the free-time vectors (and services) downstream of e
         const QInfo &q = c.qi[ev.q0];
         const int k = q.k;
         double *fi = c.fvec(q, ev.p0);
         FreeVec<KMAX> M;
         M.load(fi, k);
+        if (log0 && lane == 0) c.ls[ev.p0] = log_d(x - dmax(ev.a_e, M.v[0]));
         M.replace_min(x);
         fi += k;
         for (int p = ev.p0 + 1; p < q.hi; ++p, fi += k) {
             if (M.equals(fi, k)) break;
             const double di = c.dq[p];
             BQ_SYNCG(gmask);
-            if (lane == 0) M.store(fi, k);
+            if (lane == 0) {
+                if (log0 && M.v[0] != fi[0]) c.ls[p] = log_d(di - dmax(c.at[p], M.v[0]));
+                M.store(fi, k);
+            }
             M.replace_min(di);
         }
+    } else if (ev.t0 == Q_DELAY) {
+        if (log0 && lane == 0) c.ls[ev.p0] = log_d(x - ev.a_e);
     }
     BQ_SYNCG(gmask);
     if (ev.t0 == Q_PS) {  // the departure changes rank among the queue's sorted departures
@@ -564,32 +634,126 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
     BQ_SYNCG(gmask);
     // ---- arrival side ------------------------------------------------------------------------------------------
     if (ev.e1 < 0) return;
-    if (ev.t1 == Q_GGK) {  // refresh the vectors from the first changed position, then re-rank e1
+    const bool log1 = (c.qi[ev.q1].dist != D_EXP);
+    if (ev.t1 == Q_GGK) {  // re-rank e1, then refresh vectors and services from the first changed position
         const QInfo &q = c.qi[ev.q1];
         const int k = q.k, p1 = ev.p1;
         const int ps = (j1 < p1) ? j1 : p1, pe = (j1 < p1) ? p1 : j1;
+        reslot<W>(c.at, c.ord, c.pos, c.dq, log1 ? c.ls : nullptr, p1, j1, x, lane, gmask);
         FreeVec<KMAX> M;
-        M.load(c.fvec(q, ps), k);
-        for (int t = ps; t < q.hi; ++t) {
-            double di;
-            if (t == j1) di = ev.d1;
-            else {
-                const int sp = moved_src(t, j1, p1);
-                di = c.dq[sp];
-                if (t > pe && M.equals(c.fvec(q, sp), k)) break;
-            }
+        double *fi = c.fvec(q, ps);
+        M.load(fi, k);  // predecessors of position ps are untouched
+        for (int t = ps; t < q.hi; ++t, fi += k) {
+            if (t > pe && M.equals(fi, k)) break;
+            const double di = c.dq[t];
             BQ_SYNCG(gmask);
-            if (lane == 0) M.store(c.fvec(q, t), k);
+            if (lane == 0) {
+                if (log1 && (t <= pe || M.v[0] != fi[0])) c.ls[t] = log_d(di - dmax(c.at[t], M.v[0]));
+                M.store(fi, k);
+            }
             M.replace_min(di);
         }
         BQ_SYNCG(gmask);
-        reslot<W>(c.at, c.ord, c.pos, c.dq, nullptr, p1, j1, x, lane, gmask);
     } else if (ev.t1 == Q_PS) {
         reslot<W>(c.at, c.ord, c.pos, c.dq, c.sq, ev.p1, j1, x, lane, gmask);
     } else {
-        if (lane == 0) c.at[ev.p1] = x;
+        if (lane == 0) {
+            c.at[ev.p1] = x;
+            if (log1) c.ls[ev.p1] = log_d(ev.d1 - x);
+        }
         BQ_SYNCG(gmask);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One lane, one event: the whole update computed WITHOUT writing anything -- one step of sampling._slice on the exact
+// conditional (sequential candidates) or one MH-within-Gibbs proposal + accept decision -- together with the ranges
+// it read (R) and the ranges the accepted move will write (Wt = what the accepted candidate's evaluation touched).
+// Used by sweep_batch_kernel, where the 32 lanes of a warp update 32 different events of one chain at once.
+// ---------------------------------------------------------------------------------------------
+struct LaneUpdate {
+    double x_new;
+    int changed, counted, rejected, stuck;
+    long long evals;
+    Touch R, Wt;
+};
+
+struct LaneParams {
+    unsigned long long seed, gchain;
+    unsigned int gsw;
+    int mode, flags;
+    double tmax;
+};
+
+template <int KMAX>
+BQ_HDI void lane_update(const Chain &c, const EventCtx &ev, const LaneParams &P, LaneUpdate &out) {
+    out.x_new = ev.x0; out.changed = 0; out.counted = 0; out.rejected = 0; out.stuck = 0; out.evals = 0;
+    out.R.reset(); out.Wt.reset();
+    out.R.p0(ev.p0);
+    if (ev.e1 >= 0) out.R.p1(ev.p1);
+    Touch last;
+    last.reset();
+    auto g = [&](double x) {
+        last.reset();
+        const double v = dyn_logcond<KMAX>(c, ev, x, last);
+        out.R.merge(last);
+        return v;
+    };
+    if (P.mode != MODE_MH) {
+        const double lower = ev.a_e, upper = (ev.e1 >= 0) ? fmin(ev.d1, P.tmax) : P.tmax;  // qnet.pyx:698-701, 732-734
+        Rng rng;
+        rng.init(P.seed, P.gchain, P.gsw, (unsigned int)ev.e, TAG_SLICE);
+        out.counted = 1;
+        const double x1 = slice_finite_seq(g, ev.x0, lower, upper, rng, out.evals);
+        if (x1 != ev.x0) { out.changed = 1; out.x_new = x1; out.Wt = last; }
+        else out.stuck = 1;
+        return;
+    }
+    // MH-within-Gibbs (gibbs_resample_pair / gibbs_resample_final, qnet.pyx:382-498); see mh_update for the streams
+    const bool final_evt = (ev.e1 < 0);
+    if (final_evt && (P.flags & FLAG_NO_FINAL)) return;
+    MhProp pr;
+    mh_setup(c, ev, pr);
+    if (pr.Uh - pr.Lh < 1e-10) return;
+    if (!final_evt && ev.d1 - ev.a_e < 1e-10) return;
+    Rng aux;
+    aux.init(P.seed, P.gchain, P.gsw, (unsigned int)ev.e, TAG_MH_AUX);
+    const double u_acc = aux.uniform();
+    (void)aux.uniform();
+    const double h0 = pr.eval(ev.x0);
+    double x1 = ev.x0;
+    if (!(h0 > BQ_NEG_INF)) {
+        int tries = 0;
+        for (; tries < 25; ++tries) {
+            const double u = aux.uniform();
+            x1 = final_evt ? pr.b0 + (-log_d(1.0 - u)) : ev.a_e + (ev.d1 - ev.a_e) * u;
+            if (pr.eval(x1) > BQ_NEG_INF) break;
+        }
+        if (tries >= 25) return;
+    }
+    auto hp = [&](double x) { return pr.eval(x); };
+    for (int step = 0; step < 2; ++step) {
+        Rng rng;
+        rng.init(P.seed, P.gchain, P.gsw, (unsigned int)ev.e, step == 0 ? TAG_MH : TAG_MH2);
+        x1 = final_evt ? slice_stepout_seq(hp, x1, pr.Lh, pr.Uh, rng, out.evals)
+                       : slice_finite_seq(hp, x1, pr.Lh, pr.Uh, rng, out.evals);
+    }
+    out.counted = 1;
+    const double g_new = g(x1);
+    const double ratio = exp(h0 - pr.eval(x1) + g_new);
+    if (u_acc < ratio) {
+        if (x1 != ev.x0) { out.changed = 1; out.x_new = x1; out.Wt = last; }
+    } else {
+        out.rejected = 1;
+    }
+}
+
+// does a lane that read R depend on a lane that writes W?
+BQ_HDF bool ranges_overlap(int alo, int ahi, int blo, int bhi) { return alo <= bhi && blo <= ahi; }
+BQ_HDF bool touch_conflict(const Touch &r, const Touch &w) {
+    return ranges_overlap(r.lo0, r.hi0, w.lo0, w.hi0) || ranges_overlap(r.lo0, r.hi0, w.lo1, w.hi1) ||
+           ranges_overlap(r.lo1, r.hi1, w.lo0, w.hi0) || ranges_overlap(r.lo1, r.hi1, w.lo1, w.hi1) ||
+           ranges_overlap(r.dlo, r.dhi, w.dlo, w.dhi);
 }
 
 // service time of the event at position p of queue q in the current state
@@ -632,11 +796,12 @@ __device__ BQ_NOINLINE void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, i
             if (s > 0.0) {
                 v[0] += 1.0; v[1] += s;
                 if (dist != D_EXP) {
-                    if (dist == D_GAMMA || s >= 1e-50) { v[2] += log_d(s); v[3] += 1.0; }
+                    if (dist == D_GAMMA || s >= 1e-50) { v[2] += (qi.type == Q_PS) ? log_d(s) : c.ls[p]; v[3] += 1.0; }
                 }
             } else if (s == 0.0) v[5] += 1.0;
             if (want_logp) {
-                if (s < 0.0) v[7] += 1.0; else v[6] += lpdf(c.qc[q], s);
+                if (s < 0.0) v[7] += 1.0;
+                else v[6] += (qi.type == Q_PS) ? lpdf(c.qc[q], s) : lpdf_ls(c.qc[q], s, c.ls[p]);
             }
         }
 #pragma unroll
@@ -646,7 +811,7 @@ __device__ BQ_NOINLINE void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, i
             const double mean_log = (v[3] > 0.0) ? v[2] / v[3] : 0.0;
             for (int p = qi.lo + lane; p < qi.hi; p += W) {
                 const double s = dyn_service(c, qi, p);
-                if (s >= 1e-50) { const double z = log_d(s) - mean_log; sq += z * z; }
+                if (s >= 1e-50) { const double z = ((qi.type == Q_PS) ? log_d(s) : c.ls[p]) - mean_log; sq += z * z; }
             }
             sq = group_sum<W>(sq, gmask);
         }
@@ -719,7 +884,7 @@ __device__ __forceinline__ bool group_slice(const G &g, double x0, double lower,
 template <int W, int KMAX>
 __device__ BQ_NOINLINE void mh_update(const Chain &c, const EventCtx &ev, const DynArgs &A, unsigned long long gchain,
                           unsigned int gsw, const GroupLane &gl, long long &n_ev, long long &n_evals, long long &n_stuck,
-                          long long &n_reject, int &steps) {
+                          long long &n_reject, Touch &tc) {
     const bool final_evt = (ev.e1 < 0);
     if (final_evt && (A.flags & FLAG_NO_FINAL)) return;  // sample_final = False (qnet.pyx:361)
     MhProp pr;
@@ -755,7 +920,7 @@ __device__ BQ_NOINLINE void mh_update(const Chain &c, const EventCtx &ev, const 
     }
     n_ev += 1;
     // ratio = exp(h(d_e) - h(d_new)) * prod over the diff lists of exp(lpdf(s_new) - lpdf(s_old))   (qnet.pyx:425-431)
-    const double g_new = dyn_logcond<KMAX>(c, ev, x_new, steps);
+    const double g_new = dyn_logcond<KMAX>(c, ev, x_new, tc);
     const double ratio = exp(h0 - pr.eval(x_new) + g_new);
     if (u_acc < ratio) {
         if (x_new != ev.x0) dyn_commit<W, KMAX>(c, ev, x_new, gl.lane, gl.gmask);
@@ -836,10 +1001,11 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
             const DynRec rec = {r4.x, r4.y, r4.z, r4.w};
             EventCtx ev;
             event_load(c, rec, ev);
-            int steps = 0;
+            Touch tc;
+            tc.reset();
             if (A.mode == MODE_MH) {
-                mh_update<W, KMAX>(c, ev, A, gchain, gsw, gl, n_ev, n_evals, n_stuck, n_reject, steps);
-                n_steps += steps;
+                mh_update<W, KMAX>(c, ev, A, gchain, gsw, gl, n_ev, n_evals, n_stuck, n_reject, tc);
+                n_steps += tc.steps;
                 __syncwarp(gmask);
                 continue;
             }
@@ -849,9 +1015,9 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
             rng.init(A.seed, gchain, gsw, (unsigned int)ev.e, TAG_SLICE);
             n_ev += 1;
             double xacc = ev.x0;
-            const bool accepted = group_slice<W>([&](double x) { return dyn_logcond<KMAX>(c, ev, x, steps); }, ev.x0, lower,
+            const bool accepted = group_slice<W>([&](double x) { return dyn_logcond<KMAX>(c, ev, x, tc); }, ev.x0, lower,
                                                  upper, rng, gl, xacc, n_evals, n_stuck);
-            n_steps += steps;
+            n_steps += tc.steps;
             if (accepted && xacc != ev.x0) dyn_commit<W, KMAX>(c, ev, xacc, lane, gmask);
             __syncwarp(gmask);
         }
@@ -894,6 +1060,157 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The batch kernel: one WARP owns a chain and its 32 lanes update 32 consecutive events of the sweep order at once.
+// The order (built on the host) interleaves each queue's events with a stride of 1/32 of the queue, so the events of a
+// batch are far apart.  Every lane computes its update on the unchanged state (lane_update) and the ranges it read and
+// would write; writers publish their ranges in a per-chain claim array; the longest prefix of the batch in which no
+// lane read a range claimed by an earlier lane is committed, the rest is redone in the next round.  The outcome is
+// therefore EXACTLY the sequential sweep in the fixed order -- whatever the batch boundaries -- with 32 updates of a
+// chain in flight per warp instead of one.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void claim_range(int *claim, int lo, int hi, int stamp) {
+    for (int p = lo; p <= hi; ++p) atomicMax(&claim[p], stamp);
+}
+__device__ __forceinline__ bool claimed_before(const int *claim, int lo, int hi, int round_base, int lane) {
+    for (int p = lo; p <= hi; ++p) {
+        const int v = __ldcg(&claim[p]);
+        if (v >= round_base && 31 - (v - round_base) < lane) return true;
+    }
+    return false;
+}
+
+#ifndef BQ_BATCH_MINBLOCKS
+#define BQ_BATCH_MINBLOCKS 4
+#endif
+template <int KMAX>
+__global__ void __launch_bounds__(128, BQ_BATCH_MINBLOCKS) sweep_batch_kernel(const DynArgs A, int *claim_all, int *claimd_all) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int W = 32;
+    const unsigned FULL = 0xffffffffu;
+    const int gib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chain = blockIdx.x * (blockDim.x >> 5) + gib;
+    if (chain >= A.n_chains) return;
+    GroupSmem sm;
+    sm.carve(smem_raw + (size_t)gib * dyn_group_smem(A.Q, A.P), A.Q, A.P);
+    QConst *qc = sm.qc;
+    SuffStat *ss = sm.ss;
+    double *th = sm.th;
+    const int Q = A.Q, P = A.P, E = A.E;
+    int *claim = claim_all + (size_t)chain * E;
+    int *claimd = claimd_all ? claimd_all + (size_t)chain * E : nullptr;
+
+    for (int i = lane; i < P; i += W) th[i] = A.theta[(size_t)chain * P + i];
+    for (int q = lane; q < Q; q += W) sm.qi[q] = A.qinfo[q];
+    for (int i = lane; i < E; i += W) { claim[i] = 0; if (claimd) claimd[i] = 0; }
+    __syncwarp();
+    for (int q = lane; q < Q; q += W) {
+        const int o = __ldg(&A.q_poff[q]), dist = sm.qi[q].dist;
+        qconst_set(qc[q], dist, th[o], (dist == D_EXP) ? 0.0 : th[o + 1]);
+    }
+    __syncwarp();
+    Chain c;
+    c.bind(A, chain, sm.qi, qc);
+
+    LaneParams LP;
+    LP.seed = A.seed; LP.gchain = (unsigned long long)(A.chain_offset + chain); LP.mode = A.mode; LP.flags = A.flags;
+    long long n_ev = 0, n_evals = 0, n_stuck = 0, n_pevals = 0, n_steps = 0, n_reject = 0, n_redo = 0;
+    const int4 *order4 = reinterpret_cast<const int4 *>(A.order);
+    int round = 0;
+
+    for (int sw = 0; sw < A.n_sweeps; ++sw) {
+        LP.gsw = A.sweep_base + (unsigned int)sw;
+        if (sw == 0 || (A.flags & FLAG_TMAX_PER_SWEEP)) {  // Tmax = 2 max d   (qnet.pyx:672)
+            double m = 0.0;
+            for (int i = lane; i < E; i += W) m = fmax(m, c.dq[i]);
+            LP.tmax = 2.0 * group_max<W>(m, FULL);
+        }
+        const int n_order = (A.flags & FLAG_PARAMS_ONLY) ? 0 : A.n_order;
+        for (int s = 0; s < n_order;) {
+            ++round;
+            const int round_base = round * 32;
+            const int idx = s + lane;
+            const bool active = idx < n_order;
+            EventCtx ev;
+            LaneUpdate up;
+            up.changed = 0; up.counted = 0; up.rejected = 0; up.stuck = 0; up.evals = 0;
+            up.R.reset(); up.Wt.reset();
+            if (active) {
+                const int4 r4 = __ldg(&order4[idx]);
+                const DynRec rec = {r4.x, r4.y, r4.z, r4.w};
+                event_load(c, rec, ev);
+                lane_update<KMAX>(c, ev, LP, up);
+            }
+            __syncwarp();
+            if (active && up.changed) {  // publish what this lane will write
+                const int stamp = round_base + 31 - lane;
+                claim_range(claim, up.Wt.lo0, up.Wt.hi0, stamp);
+                claim_range(claim, up.Wt.lo1, up.Wt.hi1, stamp);
+                if (claimd) claim_range(claimd, up.Wt.dlo, up.Wt.dhi, stamp);
+            }
+            __syncwarp();
+            bool conflict = false;
+            if (active && lane > 0) {
+                conflict = claimed_before(claim, up.R.lo0, up.R.hi0, round_base, lane) ||
+                           claimed_before(claim, up.R.lo1, up.R.hi1, round_base, lane) ||
+                           (claimd && claimed_before(claimd, up.R.dlo, up.R.dhi, round_base, lane));
+            }
+            const unsigned cm = __ballot_sync(FULL, conflict);
+            const int nact = (n_order - s < 32) ? n_order - s : 32;
+            const int fc = cm ? (__ffs(cm) - 1) : nact;
+            if (active && lane < fc) {
+                n_ev += up.counted; n_evals += up.evals; n_reject += up.rejected; n_steps += up.R.steps;
+                if (LP.mode != MODE_MH) n_stuck += up.stuck;
+                if (up.changed) dyn_commit<1, KMAX>(c, ev, up.x_new, 0, 1u << lane);
+            }
+            n_redo += (lane == 0) ? (nact - fc) : 0;
+            __syncwarp();
+            s += fc;
+        }
+        const bool trace = (A.flags & FLAG_TRACE) != 0;
+        if (A.update != UPD_NONE || trace) {
+            double logp = 0.0;
+            dyn_suffstats<W>(c, Q, ss, lane, FULL, trace, &logp);
+            const size_t recno = (size_t)(A.trace_base + sw);
+            if (trace) {
+                for (int q = lane; q < Q; q += W)
+                    A.tr_wait[(recno * A.n_chains + chain) * Q + q] = (ss[q].nall > 0.0) ? ss[q].wait / ss[q].nall : 0.0;
+                if (lane == 0) A.tr_logp[recno * A.n_chains + chain] = logp;
+            }
+            if (A.update != UPD_NONE) {
+                for (int q = lane; q < Q; q += W) {
+                    const int o = __ldg(&A.q_poff[q]), dist = sm.qi[q].dist;
+                    double p0 = th[o], p1 = (dist == D_EXP) ? 0.0 : th[o + 1];
+                    if (A.update == UPD_BAYES) {
+                        Rng prng;
+                        prng.init(A.seed, LP.gchain, LP.gsw, (unsigned int)q, TAG_PARAM);
+                        sample_params(dist, ss[q], prng, p0, p1, &n_pevals);
+                    } else {
+                        estimate_params(dist, ss[q], p0, p1);
+                    }
+                    th[o] = p0;
+                    if (dist != D_EXP) th[o + 1] = p1;
+                    qconst_set(qc[q], dist, p0, p1);
+                }
+            }
+            __syncwarp();
+            if (trace)
+                for (int i = lane; i < P; i += W) A.tr_theta[(recno * A.n_chains + chain) * P + i] = th[i];
+        }
+    }
+    for (int i = lane; i < P; i += W) A.theta[(size_t)chain * P + i] = th[i];
+    // per-lane counters -> the chain's totals
+    double tot[7] = {(double)n_ev, (double)n_evals, (double)n_pevals, (double)n_stuck, (double)n_reject, (double)n_steps,
+                     (double)n_redo};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) tot[i] = group_sum<W>(tot[i], FULL);
+    if (lane == 0) {
+        long long *st = A.stats + (size_t)chain * BQ_NSTAT;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) st[i] += (long long)tot[i];
+    }
+}
+
 // ---- parity / reporting kernels ---------------------------------------------------------------
 
 // out[j] = inner_dfun(x[j]) - lik0 for the event of `rec` on one chain (qnet.pyx:1340-1357); one warp.
@@ -915,15 +1232,16 @@ __global__ void logcond_dynamic_kernel(const DynArgs A, int chain, DynRec rec, c
     c.bind(A, chain, sm.qi, sm.qc);
     EventCtx ev;
     event_load(c, rec, ev);
-    int steps = 0;
+    Touch tc;
+    tc.reset();
     if (what == 1) {
         MhProp pr;
         mh_setup(c, ev, pr);
         for (int j = threadIdx.x; j < n; j += blockDim.x) out[j] = pr.eval(x[j]);
         return;
     }
-    const double g0 = dyn_logcond<KMAX>(c, ev, ev.x0, steps);
-    for (int j = threadIdx.x; j < n; j += blockDim.x) out[j] = dyn_logcond<KMAX>(c, ev, x[j], steps) - g0;
+    const double g0 = dyn_logcond<KMAX>(c, ev, ev.x0, tc);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) out[j] = dyn_logcond<KMAX>(c, ev, x[j], tc) - g0;
 }
 
 // Qnet.log_prob (qnet.pyx:1032) and the sufficient statistics, one warp per chain
@@ -962,7 +1280,7 @@ __global__ void rebuild_positions_kernel(const DynArgs A, const int *ev_pt) {
     const QInfo qi = A.qinfo[q];
     const double *d = A.state + (size_t)chain * A.E;
     const int *ord = A.ord + (size_t)chain * A.E;
-    double *at = A.at + (size_t)chain * A.E, *dq = A.dq + (size_t)chain * A.E;
+    double *at = A.at + (size_t)chain * A.E, *dq = A.dq + (size_t)chain * A.E, *ls = A.ls + (size_t)chain * A.E;
     double *F = A.F + (size_t)chain * A.EF + qi.foff;
     FreeVec<KMAX> M;
 #pragma unroll
@@ -970,11 +1288,15 @@ __global__ void rebuild_positions_kernel(const DynArgs A, const int *ev_pt) {
     for (int p = qi.lo; p < qi.hi; ++p) {
         const int i = ord[p], pt = ev_pt[i];
         const double di = d[i];
+        const double ai = (pt >= 0) ? d[pt] : 0.0;
         dq[p] = di;
-        at[p] = (pt >= 0) ? d[pt] : 0.0;
+        at[p] = ai;
         if (qi.type == Q_GGK) {
             M.store(F + (size_t)(p - qi.lo) * qi.k, qi.k);
+            if (qi.dist != D_EXP) ls[p] = log_d(di - dmax(ai, M.v[0]));
             M.replace_min(di);
+        } else if (qi.type == Q_DELAY && qi.dist != D_EXP) {
+            ls[p] = log_d(di - ai);
         }
     }
 }

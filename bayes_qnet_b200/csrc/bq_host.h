@@ -15,13 +15,14 @@ namespace bq {
 struct HostNet {
     int E, Q;
     const int *q_type, *q_k, *q_off, *q_foff;  // [Q], [Q], [Q+1], [Q]: discipline, servers, position ranges, F offsets
+    const int *q_dist;                         // [Q] service family (0 = exponential: no log-service cache)
     const int *prev_byt;                       // [E]
 };
 
 // one chain's position-indexed arrays (at, dq: all queues; F: FIFO queues; dt, sq, dord, dpos: PS queues, may be null)
 struct HostChain {
     int *ord, *pos;
-    double *at, *dq, *F;
+    double *at, *dq, *ls, *F;
     double *dt, *sq;
     int *dord, *dpos;
 };
@@ -71,14 +72,18 @@ static void host_rebuild(const HostNet *h, const double *d, const HostChain &c, 
             c.at[p] = arr(i);
             c.dq[p] = d[i];
         }
-        if (type == 0 /* Q_GGK */) {  // free-time vectors (queues.pyx:654-680 as a sorted multiset)
+        const bool logs = h->q_dist[q] != 0;
+        if (type == 0 /* Q_GGK */) {  // free-time vectors (queues.pyx:654-680 as a sorted multiset), log services
             const int k = h->q_k[q];
             M.assign(k, 0.0);
             for (int p = lo; p < hi; ++p) {
                 memcpy(c.F + h->q_foff[q] + (size_t)(p - lo) * k, M.data(), k * sizeof(double));
+                if (logs) c.ls[p] = log(c.dq[p] - std::max(c.at[p], M[0]));
                 fv_replace_min(M.data(), k, c.dq[p]);
             }
         }
+        if (type == 1 /* Q_DELAY */ && logs)
+            for (int p = lo; p < hi; ++p) c.ls[p] = log(c.dq[p] - c.at[p]);
         if (type == 2 /* Q_PS */ && c.dt) {
             for (int p = lo; p < hi; ++p) c.dord[p] = c.ord[p];
             std::stable_sort(c.dord + lo, c.dord + hi, [&](int x, int y) { return d[x] < d[y]; });

@@ -6,6 +6,7 @@
 // sharing).  No torch types, no exceptions across the boundary.  There is no CPU fallback: without a
 // CUDA device bq_create fails with BQ_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -72,18 +73,20 @@ struct bq_handle {
     int EF = 0, kmax = 1, dyn_w = 32, dyn_threads = 128;
     std::vector<int> q_off, q_foff, ord0;  // queue position ranges, F offsets, initial order
     std::vector<int> dyn_order;          // sweep order of the dynamic-order kernels
+    bool dyn_batch = true;               // dynamic-order kernels: warp-per-chain batches (else W-lane groups, BQ_DYN_BATCH=0)
+    int *d_claim = nullptr, *d_claimd = nullptr;
     bool mh_dynamic = false;             // static-order handle: run MH sweeps in the dynamic-order kernel (BQ_MH_DYNAMIC)
     bool dyn_ready = false;              // dynamic arrays allocated
     bool dyn_stale = false;              // ... but the static kernel has moved d since they were built
     DynRec *d_order = nullptr;
     QInfo *d_qinfo = nullptr;
     int *d_ord = nullptr, *d_pos = nullptr, *d_dord = nullptr, *d_dpos = nullptr;
-    double *d_F = nullptr, *d_sq = nullptr, *d_at = nullptr, *d_dq = nullptr, *d_dt = nullptr;
+    double *d_F = nullptr, *d_sq = nullptr, *d_at = nullptr, *d_dq = nullptr, *d_dt = nullptr, *d_ls = nullptr;
     HostNet net() const {
         HostNet n;
         n.E = E; n.Q = Q;
         n.q_type = q_type.data(); n.q_k = q_k.data(); n.q_off = q_off.data(); n.q_foff = q_foff.data();
-        n.prev_byt = prev_byt.data();
+        n.q_dist = q_dist.data(); n.prev_byt = prev_byt.data();
         return n;
     }
 };
@@ -246,7 +249,7 @@ static void fill_dyn_args(const bq_handle *h, DynArgs &A) {
     A.n_order = (int)h->dyn_order.size();
     A.order = h->d_order;
     A.qinfo = h->d_qinfo; A.q_poff = h->d_q_poff;
-    A.state = h->d_state; A.ord = h->d_ord; A.pos = h->d_pos; A.at = h->d_at; A.dq = h->d_dq; A.F = h->d_F;
+    A.state = h->d_state; A.ord = h->d_ord; A.pos = h->d_pos; A.at = h->d_at; A.dq = h->d_dq; A.ls = h->d_ls; A.F = h->d_F;
     A.dord = h->d_dord; A.dpos = h->d_dpos; A.dt = h->d_dt; A.sq = h->d_sq;
     A.theta = h->d_theta; A.stats = h->d_stats;
     A.tr_theta = h->d_tr_theta; A.tr_wait = h->d_tr_wait; A.tr_logp = h->d_tr_logp;
@@ -256,16 +259,17 @@ static void fill_dyn_args(const bq_handle *h, DynArgs &A) {
 // host staging of the per-chain derived arrays for `rows` chains
 struct HostRows {
     std::vector<int> ord, pos, dord, dpos;
-    std::vector<double> at, dq, F, dt, sq;
+    std::vector<double> at, dq, ls, F, dt, sq;
     void alloc(size_t rows, size_t E, size_t EF, bool ps) {
         ord.assign(rows * E, 0); pos.assign(rows * E, 0);
-        at.assign(rows * E, 0.0); dq.assign(rows * E, 0.0);
+        at.assign(rows * E, 0.0); dq.assign(rows * E, 0.0); ls.assign(rows * E, 0.0);
         F.assign(std::max<size_t>(rows * EF, 1), 0.0);
         if (ps) { dord.assign(rows * E, 0); dpos.assign(rows * E, 0); dt.assign(rows * E, 0.0); sq.assign(rows * E, 0.0); }
     }
     HostChain chain(size_t i, size_t E, size_t EF) {
         HostChain c;
-        c.ord = &ord[i * E]; c.pos = &pos[i * E]; c.at = &at[i * E]; c.dq = &dq[i * E]; c.F = &F[i * EF];
+        c.ord = &ord[i * E]; c.pos = &pos[i * E]; c.at = &at[i * E]; c.dq = &dq[i * E]; c.ls = &ls[i * E];
+        c.F = &F[i * EF];
         const bool ps = !dt.empty();
         c.dt = ps ? &dt[i * E] : nullptr; c.sq = ps ? &sq[i * E] : nullptr;
         c.dord = ps ? &dord[i * E] : nullptr; c.dpos = ps ? &dpos[i * E] : nullptr;
@@ -286,6 +290,7 @@ static int upload_rows(bq_handle *h, const HostRows &r, int lo, size_t rows, siz
     CK(put(h->d_pos + o, r.pos, E));
     CK(put(h->d_at + o, r.at, E));
     CK(put(h->d_dq + o, r.dq, E));
+    CK(put(h->d_ls + o, r.ls, E));
     CK(put(h->d_F + of, r.F, EF));
     if (h->has_ps) {
         CK(put(h->d_dord + o, r.dord, E));
@@ -317,8 +322,23 @@ static int build_sequential_order(bq_handle *h) {
         if (p != h->q_off[q + 1]) return fail(BQ_ERR_INVALID, "by-queue links do not cover the queue");
     }
     h->dyn_order.clear();
-    for (int p = 0; p < E; ++p)
-        if (eligible(h, h->ord0[p])) h->dyn_order.push_back(h->ord0[p]);
+    if (const char *env = getenv("BQ_DYN_BATCH")) h->dyn_batch = (env[0] != '0');
+    if (!h->dyn_batch) {
+        for (int p = 0; p < E; ++p)
+            if (eligible(h, h->ord0[p])) h->dyn_order.push_back(h->ord0[p]);
+        return BQ_OK;
+    }
+    // batch kernel: each queue's eligible events interleaved with a stride of 1/32 of the queue, so that any 32
+    // consecutive events of the order are far apart in their queue (and rarely touch each other's neighbourhoods)
+    std::vector<int> lst;
+    for (int q = 0; q < Q; ++q) {
+        lst.clear();
+        for (int p = h->q_off[q]; p < h->q_off[q + 1]; ++p)
+            if (eligible(h, h->ord0[p])) lst.push_back(h->ord0[p]);
+        const int n = (int)lst.size(), st = (n + 31) / 32;
+        for (int r = 0; r < st; ++r)
+            for (int i = r; i < n; i += st) h->dyn_order.push_back(lst[i]);
+    }
     return BQ_OK;
 }
 
@@ -365,12 +385,23 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
     CK(cudaMalloc((void **)&h->d_pos, C * E * sizeof(int)));
     CK(cudaMalloc((void **)&h->d_at, C * E * sizeof(double)));
     CK(cudaMalloc((void **)&h->d_dq, C * E * sizeof(double)));
+    CK(cudaMalloc((void **)&h->d_ls, C * E * sizeof(double)));
+    {   // log of small counts for the PS terms, computed with the host's log()
+        double tab[256];
+        tab[0] = -INFINITY;
+        for (int i = 1; i < 256; ++i) tab[i] = log((double)i);
+        CK(cudaMemcpyToSymbol(c_log_count, tab, sizeof(tab)));
+    }
     CK(cudaMalloc((void **)&h->d_F, std::max<size_t>(C * h->EF, 1) * sizeof(double)));
     if (h->has_ps) {
         CK(cudaMalloc((void **)&h->d_dord, C * E * sizeof(int)));
         CK(cudaMalloc((void **)&h->d_dpos, C * E * sizeof(int)));
         CK(cudaMalloc((void **)&h->d_dt, C * E * sizeof(double)));
         CK(cudaMalloc((void **)&h->d_sq, C * E * sizeof(double)));
+    }
+    if (h->dyn_batch) {
+        CK(cudaMalloc((void **)&h->d_claim, C * E * sizeof(int)));
+        if (h->has_ps) CK(cudaMalloc((void **)&h->d_claimd, C * E * sizeof(int)));
     }
     if (int rc = upload_rows(h, r0, 0, 1, C, false)) return rc;
     CK(cudaStreamSynchronize(h->stream));
@@ -419,6 +450,13 @@ static void launch_dynamic_w(bq_handle *h, const DynArgs &A) {
     else sweep_dynamic_kernel<W, 8><<<blocks, h->dyn_threads, sm, h->stream>>>(A);
 }
 static void launch_dynamic(bq_handle *h, const DynArgs &A) {
+    if (h->dyn_batch) {  // one warp per chain, 32 events of the chain in flight
+        const int G = 4, blocks = (h->C + G - 1) / G;
+        const size_t sm = (size_t)G * dyn_group_smem(h->Q, h->P);
+        if (h->kmax <= 4) sweep_batch_kernel<4><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
+        else sweep_batch_kernel<8><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
+        return;
+    }
     if (h->dyn_w == 1) launch_dynamic_w<1>(h, A);
     else if (h->dyn_w == 2) launch_dynamic_w<2>(h, A);
     else if (h->dyn_w == 4) launch_dynamic_w<4>(h, A);
@@ -434,7 +472,8 @@ extern "C" int bq_destroy(bq_handle *h) {
     void *ptrs[] = {h->d_rec, h->d_color_off, h->d_ev_q, h->d_ev_p, h->d_ev_pt, h->d_q_events, h->d_q_off,
                     h->d_q_type, h->d_q_dist, h->d_q_poff, h->d_state, h->d_theta, h->d_stats,
                     h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch, h->d_order, h->d_qinfo,
-                    h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_F, h->d_sq, h->d_at, h->d_dq, h->d_dt};
+                    h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_F, h->d_sq, h->d_at, h->d_dq, h->d_dt, h->d_ls, h->d_claim,
+                    h->d_claimd};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -925,6 +964,7 @@ extern "C" int bq_stats(bq_handle *h, bq_stats_t *out) {
         out->n_stuck += r[3];
         out->nreject += r[4];
         out->diff_len += r[5];
+        out->n_redone += r[6];
     }
     out->slice_calls = out->nevents;
     out->num_diff = out->slice_evals;

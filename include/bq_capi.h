@@ -93,6 +93,8 @@ typedef struct {
     int64_t n_launches;  /* CUDA kernels launched by this handle */
     int64_t param_evals; /* log-target evaluations inside the Gamma posterior slice sampler (netutils.py:19) */
     int64_t n_stuck;     /* slice updates that kept x0: point mass / bracket < 1e-10 (sampling.pyx:289,360) */
+    int64_t n_redone;    /* batch kernel: updates recomputed because an earlier update of the batch wrote what
+                            they had read (the result is the sequential sweep either way)                 */
 } bq_stats_t;
 
 const char *bq_last_error(void);

@@ -19,7 +19,7 @@ struct Emul {
     std::vector<int> q_type, q_k, q_dist, q_poff, q_off, q_foff;
     std::vector<int> qid, prev_byt, next_byt, ord, ord0, pos, dord, dpos;
     std::vector<uint8_t> obs_a, obs_d;
-    std::vector<double> d, F, sq, at, dq, dt, theta;
+    std::vector<double> d, F, sq, at, dq, ls, dt, theta;
     std::vector<QConst> qc;
     std::vector<QInfo> qinfo;
     int EF;
@@ -37,13 +37,13 @@ struct Emul {
         memset(&A, 0, sizeof(A));
         A.E = E; A.Q = Q; A.P = P; A.n_chains = 1; A.EF = EF;
         A.qinfo = qinfo.data(); A.q_poff = q_poff.data();
-        A.state = d.data(); A.ord = ord.data(); A.pos = pos.data(); A.at = at.data(); A.dq = dq.data(); A.F = F.data();
+        A.state = d.data(); A.ord = ord.data(); A.pos = pos.data(); A.at = at.data(); A.dq = dq.data(); A.ls = ls.data(); A.F = F.data();
         A.dord = dord.data(); A.dpos = dpos.data(); A.dt = dt.data(); A.sq = sq.data();
         A.theta = theta.data();
         c.bind(A, 0, qinfo.data(), qc.data());
     }
     HostNet net() const {
-        return HostNet{E, Q, q_type.data(), q_k.data(), q_off.data(), q_foff.data(), prev_byt.data()};
+        return HostNet{E, Q, q_type.data(), q_k.data(), q_off.data(), q_foff.data(), q_dist.data(), prev_byt.data()};
     }
     DynRec rec(int e) const {
         const int e1 = next_byt[e];
@@ -68,7 +68,7 @@ void *bqe_create(int E, int Q, int P, const int *q_type, const int *q_k, const i
     for (int e = 0; e < E; ++e) m->q_off[qid[e] + 1]++;
     for (int q = 0; q < Q; ++q) m->q_off[q + 1] += m->q_off[q];
     m->ord.assign(E, -1); m->pos.assign(E, -1); m->dord.assign(E, -1); m->dpos.assign(E, -1);
-    m->sq.assign(E, 0.0); m->at.assign(E, 0.0); m->dq.assign(E, 0.0); m->dt.assign(E, 0.0);
+    m->sq.assign(E, 0.0); m->at.assign(E, 0.0); m->dq.assign(E, 0.0); m->ls.assign(E, 0.0); m->dt.assign(E, 0.0);
     for (int q = 0; q < Q; ++q) {
         int p = m->q_off[q];
         for (int e = 0; e < E; ++e)
@@ -87,8 +87,8 @@ void *bqe_create(int E, int Q, int P, const int *q_type, const int *q_k, const i
     m->qc.resize(Q);
     {
         HostNet hn = m->net();
-        HostChain hc{m->ord.data(), m->pos.data(), m->at.data(), m->dq.data(), m->F.data(), m->dt.data(), m->sq.data(),
-                     m->dord.data(), m->dpos.data()};
+        HostChain hc{m->ord.data(), m->pos.data(), m->at.data(), m->dq.data(), m->ls.data(), m->F.data(), m->dt.data(),
+                     m->sq.data(), m->dord.data(), m->dpos.data()};
         host_rebuild(&hn, m->d.data(), hc, false);
     }
     m->refresh_qc();
@@ -109,9 +109,10 @@ void bqe_logcond(void *h, int e, const double *x, int n, double *out) {
     Emul *m = (Emul *)h;
     EventCtx ev;
     event_load(m->c, m->rec(e), ev);
-    int steps = 0;
-    const double g0 = dyn_logcond<8>(m->c, ev, ev.x0, steps);
-    for (int j = 0; j < n; ++j) out[j] = dyn_logcond<8>(m->c, ev, x[j], steps) - g0;
+    Touch tc;
+    tc.reset();
+    const double g0 = dyn_logcond<8>(m->c, ev, ev.x0, tc);
+    for (int j = 0; j < n; ++j) out[j] = dyn_logcond<8>(m->c, ev, x[j], tc) - g0;
 }
 
 void bqe_apply(void *h, int e, double x) {
@@ -132,8 +133,9 @@ long bqe_slice_sweep(void *h, const int *order, int n_order, uint64_t seed, int6
         const double lower = ev.a_e, upper = (ev.e1 >= 0) ? fmin(ev.d1, tmax) : tmax;
         Rng rng;
         rng.init(seed, (uint64_t)chain, sweep, (uint32_t)ev.e, TAG_SLICE);
-        int steps = 0;
-        const double g0 = dyn_logcond<8>(m->c, ev, ev.x0, steps);
+        Touch tc;
+        tc.reset();
+        const double g0 = dyn_logcond<8>(m->c, ev, ev.x0, tc);
         m->evals++;
         ++ne;
         const double logy = g0 - (-log(1.0 - rng.uniform()));
@@ -142,11 +144,11 @@ long bqe_slice_sweep(void *h, const int *order, int n_order, uint64_t seed, int6
         for (int it = 0; it < BQ_SLICE_MAX_ITERS; ++it) {
             x1 = L + (R - L) * rng.uniform();
             m->evals++;
-            if (dyn_logcond<8>(m->c, ev, x1, steps) >= logy) break;
+            if (dyn_logcond<8>(m->c, ev, x1, tc) >= logy) break;
             if (x1 > ev.x0) R = x1; else L = x1;
             if (R - L < 1e-10) { x1 = ev.x0; break; }
         }
-        m->steps += steps;
+        m->steps += tc.steps;
         if (x1 != ev.x0) dyn_commit<1, 8>(m->c, ev, x1, 0, 1u);
     }
     return ne;
@@ -202,8 +204,9 @@ long bqe_mh_sweep(void *h, const int *order, int n_order, uint64_t seed, int64_t
             }
         }
         ++ne;
-        int steps = 0;
-        const double g_new = dyn_logcond<8>(m->c, ev, x_new, steps);
+        Touch tc;
+        tc.reset();
+        const double g_new = dyn_logcond<8>(m->c, ev, x_new, tc);
         const double ratio = exp(h0 - pr.eval(x_new) + g_new);
         if (u_acc < ratio) { if (x_new != ev.x0) dyn_commit<1, 8>(m->c, ev, x_new, 0, 1u); }
         else if (nreject) ++*nreject;
@@ -218,6 +221,39 @@ void bqe_mh_proposal(void *h, int e, const double *x, int n, double *out) {
     MhProp pr;
     mh_setup(m->c, ev, pr);
     for (int j = 0; j < n; ++j) out[j] = pr.eval(x[j]);
+}
+
+// ---- batch semantics of sweep_batch_kernel, emulated: B lanes evaluate B consecutive events of the order on the same
+// (unchanged) state; the longest prefix in which no lane read a range that an earlier lane writes is committed; the
+// rest is redone.  Must reproduce the sequential sweep exactly, for any B.
+long bqe_sweep_batch(void *h, const int *order, int n_order, uint64_t seed, int64_t chain, uint32_t sweep, double tmax,
+                     int B, int mh, int sample_final, long *nreject, long *nredo) {
+    Emul *m = (Emul *)h;
+    long ne = 0;
+    std::vector<EventCtx> evs(B);
+    std::vector<LaneUpdate> up(B);
+    LaneParams LP;
+    LP.seed = seed; LP.gchain = (unsigned long long)chain; LP.gsw = sweep; LP.mode = mh ? MODE_MH : MODE_SLICE;
+    LP.flags = sample_final ? 0 : FLAG_NO_FINAL; LP.tmax = tmax;
+    for (int s = 0; s < n_order;) {
+        const int nb = std::min(B, n_order - s);
+        for (int l = 0; l < nb; ++l) {
+            event_load(m->c, m->rec(order[s + l]), evs[l]);
+            lane_update<8>(m->c, evs[l], LP, up[l]);
+        }
+        int fc = nb;
+        for (int l = 1; l < nb && fc == nb; ++l)
+            for (int j = 0; j < l; ++j)
+                if (up[j].changed && touch_conflict(up[l].R, up[j].Wt)) { fc = l; break; }
+        for (int l = 0; l < fc; ++l) {
+            ne += up[l].counted;
+            if (up[l].rejected && nreject) ++*nreject;
+            if (up[l].changed) dyn_commit<1, 8>(m->c, evs[l], up[l].x_new, 0, 1u);
+        }
+        if (nredo) *nredo += nb - fc;
+        s += fc;
+    }
+    return ne;
 }
 
 void bqe_get(void *h, double *d, int *ord, double *F, double *svc) {
@@ -239,9 +275,10 @@ void bqe_derive(void *h, double *a, double *s, int32_t *proc, int32_t *prev_byq,
 int bqe_check(void *h) {
     Emul *m = (Emul *)h;
     std::vector<int> ord(m->ord), pos(m->E), dord(m->E, -1), dpos(m->E, -1);
-    std::vector<double> F(m->EF + 1, 0.0), at(m->E, 0.0), dq(m->E, 0.0), dt(m->E, 0.0), sq(m->E, 0.0);
+    std::vector<double> F(m->EF + 1, 0.0), at(m->E, 0.0), dq(m->E, 0.0), ls(m->E, 0.0), dt(m->E, 0.0), sq(m->E, 0.0);
     HostNet hn = m->net();
-    HostChain hc{ord.data(), pos.data(), at.data(), dq.data(), F.data(), dt.data(), sq.data(), dord.data(), dpos.data()};
+    HostChain hc{ord.data(), pos.data(), at.data(), dq.data(), ls.data(), F.data(), dt.data(), sq.data(), dord.data(),
+                 dpos.data()};
     host_rebuild(&hn, m->d.data(), hc, false);
     for (int e = 0; e < m->E; ++e)
         if (pos[e] != m->pos[e]) return 1;
@@ -251,6 +288,10 @@ int bqe_check(void *h) {
         if (at[p] != m->at[p]) return 8;
         if (dq[p] != m->dq[p]) return 9;
     }
+    for (int q = 0; q < m->Q; ++q)  // the cached log services of non-exponential FIFO / delay queues
+        if (m->q_dist[q] != D_EXP && m->q_type[q] != Q_PS)
+            for (int p = m->q_off[q]; p < m->q_off[q + 1]; ++p)
+                if (ls[p] != m->ls[p] && !(ls[p] != ls[p] && m->ls[p] != m->ls[p])) return 10;
     for (int q = 0; q < m->Q; ++q) {
         if (m->q_type[q] != Q_PS) continue;
         for (int p = m->q_off[q]; p < m->q_off[q + 1]; ++p) {

@@ -46,6 +46,10 @@ def lib():
         L.bqe_mh_sweep.argtypes = [ctypes.c_void_p, i32p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32,
                                    ctypes.c_int, ctypes.POINTER(ctypes.c_long)]
         L.bqe_mh_proposal.argtypes = [ctypes.c_void_p, ctypes.c_int, f64p, ctypes.c_int, f64p]
+        L.bqe_sweep_batch.restype = ctypes.c_long
+        L.bqe_sweep_batch.argtypes = [ctypes.c_void_p, i32p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32,
+                                      ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_long), ctypes.POINTER(ctypes.c_long)]
         L.bqe_get.argtypes = [ctypes.c_void_p, f64p, i32p, f64p, f64p]
         L.bqe_derive.argtypes = [ctypes.c_void_p, f64p, f64p, i32p, i32p, i32p]
         L.bqe_check.restype = ctypes.c_int
@@ -107,6 +111,16 @@ class EmulChain(object):
         ne = lib().bqe_mh_sweep(self._h, order.ctypes.data_as(i32p), len(order), seed, chain, sweep,
                                 1 if sample_final else 0, ctypes.byref(rej))
         return int(ne), int(rej.value)
+
+    def sweep_batch(self, order, seed, chain, sweep, B, mh=False, sample_final=True, tmax=None):
+        """One sweep with the batch semantics of sweep_batch_kernel; returns (resamples, rejections, redone)."""
+        order = numpy.ascontiguousarray(order, dtype=numpy.int32)
+        if tmax is None:
+            tmax = 2.0 * self.d.max()
+        rej, redo = ctypes.c_long(0), ctypes.c_long(0)
+        ne = lib().bqe_sweep_batch(self._h, order.ctypes.data_as(i32p), len(order), seed, chain, sweep, float(tmax),
+                                   int(B), 1 if mh else 0, 1 if sample_final else 0, ctypes.byref(rej), ctypes.byref(redo))
+        return int(ne), int(rej.value), int(redo.value)
 
     def mh_proposal(self, e, xs):
         xs = numpy.ascontiguousarray(xs, dtype=numpy.float64)

@@ -101,3 +101,31 @@ def test_emulated_mh_matches_reference_and_oracle(name):
     n_final = int(sum(1 for e in order if oc.next_byt[e] < 0))
     a = oc.mh_sweep(order, 77, 2, 9, sample_final=False)
     assert a == ec.mh_sweep(order, 77, 2, 9, sample_final=False) and a[0] <= len(order) - n_final
+
+
+@pytest.mark.parametrize("name", helpers.COND_NETS + sorted(helpers.MIXED))
+def test_emulated_batches_are_the_sequential_sweep(name):
+    """lane_update + range claims (what sweep_batch_kernel does with 32 lanes), emulated for several batch sizes: the
+    committed result must be the oracle's sequential sweep whatever the batch boundaries, for slice and MH updates."""
+    if name in helpers.MIXED:
+        net, smp, sub, arrv = helpers.mixed(name)
+    else:
+        net, arrv = helpers.golden_state(helpers.golden("cond_" + name), "s0")
+    has_ps = any(q.code == 2 for q in net.queues)
+    for B in (2, 7, 32):
+        for mh in ((False,) if has_ps else (False, True)):
+            oc = helpers.oracle_chain(net, arrv)
+            ec = emul_helper.EmulChain(net, arrv)
+            order = oc.eligible()
+            redone = 0
+            for s in range(3):
+                if mh:
+                    a, b = oc.mh_sweep(order, 5, 1, s), ec.sweep_batch(order, 5, 1, s, B, mh=True)
+                else:
+                    tmax = 2.0 * oc.d.max()
+                    a, b = (oc.slice_sweep(order, 5, 1, s, tmax=tmax)[0], 0), ec.sweep_batch(order, 5, 1, s, B, tmax=tmax)
+                assert a == b[:2]
+                redone += b[2]
+                assert ec.check() == 0
+            assert redone > 0  # task-major order: neighbours in a batch do conflict
+            assert helpers.relerr(ec.d, oc.d).max() < TOL

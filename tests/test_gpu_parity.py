@@ -258,6 +258,7 @@ def test_dynamic_kernel_group_widths(name, width, monkeypatch):
     """The dynamic-order kernel (per-chain queue order, free-time vectors) with W = 8 / 16 / 32 lanes per chain:
     the speculative candidates of a group reproduce the sequential slice sampler, so every width walks the
     oracle's path; static-order networks are forced through the same kernel as a cross-check."""
+    monkeypatch.setenv("BQ_DYN_BATCH", "0")
     monkeypatch.setenv("BQ_DYN_W", width)
     monkeypatch.setenv("BQ_FORCE_DYNAMIC", "1")
     g = helpers.golden("cond_" + name)
@@ -385,6 +386,7 @@ def test_mh_counts_and_group_widths(monkeypatch):
     g = helpers.golden("mh_mm3")
     net, arrv = helpers.golden_state(g, "s0")
     ref = None
+    monkeypatch.setenv("BQ_DYN_BATCH", "0")
     for width in ("1", "4", "8", "16", "32"):
         monkeypatch.setenv("BQ_DYN_W", width)
         with GibbsEngine(net, arrv, n_chains=1, seed=31) as eng:
@@ -455,3 +457,36 @@ def test_mh_posterior_agrees_with_long_reference_mh_runs(name):
         se = numpy.sqrt(diagnostics.mcse(ours) ** 2 + diagnostics.mcse(ref) ** 2)
         z = numpy.abs(m1 - m2) / numpy.maximum(se, 1e-12)
         assert numpy.all(z < 4.0), "%s %s: ours %s ref %s z %s" % (name, what, m1, m2, z)
+
+
+@pytest.mark.parametrize("mode", ["SLICE", "MH"])
+@pytest.mark.parametrize("name", ["qnet3", "lng1", "mm3", "lnk", "psdelay"])
+def test_batch_kernel_is_the_sequential_sweep(name, mode, monkeypatch):
+    """The batch kernel (a warp per chain, 32 events of the chain updated at once, conflicting updates redone) must
+    give exactly the sequential sweep in its fixed order.  On these small networks the events of a batch are close
+    together, so a large share of the updates conflicts and is redone -- the path under test."""
+    if mode == "MH" and name == "psdelay":
+        pytest.skip("PS has no MH proposal")
+    monkeypatch.setenv("BQ_FORCE_DYNAMIC", "1")
+    monkeypatch.setenv("BQ_MH_DYNAMIC", "1")
+    g = helpers.golden("cond_" + name)
+    net, arrv = helpers.golden_state(g, "s0")
+    with GibbsEngine(net, arrv, n_chains=3, seed=8086, chain_offset=4) as eng:
+        order = eng.mh_order() if mode == "MH" else eng.schedule()[1]
+        assert numpy.array_equal(order, eng.sequential_order())
+        eng.sweep(4, mode, "BAYES", trace=True)
+        d, th, st = eng.state(), eng.params(), eng.stats()
+        assert st["n_redone"] > 0
+        for c in (0, 2):
+            oc = helpers.oracle_chain(net, arrv)
+            props = 0
+            for s in range(4):
+                if mode == "MH":
+                    props += oc.mh_sweep(order, eng.seed, 4 + c, s)[0]
+                else:
+                    props += oc.slice_sweep(order, eng.seed, 4 + c, s)[0]
+                oc.update_params("BAYES", eng.seed, 4 + c, s)
+            assert helpers.relerr(d[c], oc.d).max() < 1e-7
+            assert helpers.relerr(th[c], oc.theta).max() < 1e-7
+        full = eng.state(2, 3, full=True)
+        assert helpers.relerr(full["s"][0], oc.s).max() < 1e-7 and numpy.array_equal(full["proc"][0], oc.proc)
