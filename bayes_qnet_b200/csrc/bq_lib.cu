@@ -554,11 +554,6 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
     CKB(cudaEventCreate(&h->ev1));
 
     build_schedule(h);
-    if (getenv("BQ_DEBUG_ONE_CLASS")) {  // timing experiment only: INVALID sampler (no conflict-freedom)
-        int n = h->color_off.back();
-        h->color_off.assign(2, 0);
-        h->color_off[1] = n;
-    }
 
     // per-event tables and events grouped by queue (in by-queue order)
     std::vector<int> q_off(Q + 1, 0), q_events(E);

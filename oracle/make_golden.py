@@ -313,6 +313,23 @@ def do_mh(name):
     print("mh_%s: %d events on grids" % (name, len(rows)))
 
 
+def do_qstats(name):
+    """Every exported statistic of the reference's qstats.py (qstats.py:174-184, plus the task-level ones) on the
+    cond_<name> initial state."""
+    ntasks, pct, init, seed, nsweeps = COND[name]
+    net, arrv = make_state(name, ntasks, pct, init, seed)
+    flat, _ = flatten(arrv)
+    out = dict(yaml=NETS[name], theta=numpy.array(net.parameters, dtype=numpy.float64))
+    for k, v in flat.items():
+        out["s0_" + k] = v
+    names = [fn.__name__ for fn in qstats.STATS] + ["max_service", "mean_task_service", "mean_task_length", "total_service"]
+    for n in names:
+        out["stat_" + n] = numpy.atleast_1d(numpy.array(getattr(qstats, n)(arrv), dtype=numpy.float64))
+    out["stat_names"] = numpy.array(names)
+    numpy.savez_compressed(os.path.join(OUT, "qstats_%s.npz" % name), **out)
+    print("qstats_%s: %d statistics" % (name, len(names)))
+
+
 def _post_rep(args):
     """One replica of the reference's estimation.bayes from the common initial state (own process: the reference
     keeps its sampler state in module globals)."""
@@ -401,6 +418,9 @@ if __name__ == "__main__":
         for n in COND:
             if args.only in (None, n):
                 do_cond(n)
+    for n in ("qnet3", "mm3", "psdelay"):
+        if args.only in (None, n) and not args.skip_cond:
+            do_qstats(n)
     if not args.skip_mh:  # MH-within-Gibbs (gibbs_resample): proposal grids and long reference runs; no PS (queues.pyx:1140)
         for n in COND:
             if n != "psdelay" and args.only in (None, n):

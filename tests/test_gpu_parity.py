@@ -490,3 +490,34 @@ def test_batch_kernel_is_the_sequential_sweep(name, mode, monkeypatch):
             assert helpers.relerr(th[c], oc.theta).max() < 1e-7
         full = eng.state(2, 3, full=True)
         assert helpers.relerr(full["s"][0], oc.s).max() < 1e-7 and numpy.array_equal(full["proc"][0], oc.proc)
+
+
+def test_gibbs_front_end(tmp_path, monkeypatch, capsys):
+    """The gibbs.py front end (gibbs.py:41-248): same options, same output files -- parameter series, per-iteration
+    statistics, arrivals snapshots, LOG_PROB / AIC / BIC -- here with 8 chains on the GPU."""
+    from bayes_qnet_b200 import gibbs
+    monkeypatch.chdir(tmp_path)
+    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 60, 0.3, seed=12)
+    with open("net.yml", "w") as f:
+        f.write(helpers.QNET3)
+    qnetu.write_multif_to_prefix("obs_", sub, obs_only=False)
+    rc = gibbs.main(["--network", "net.yml", "--multiarr", "obs_", "--bayes", "1", "--gibbs-iter", "12", "--seed", "5",
+                     "--chains", "8", "--output-mu", "mu.txt", "--statistics", "mean_wait, mean_service",
+                     "--output-arrv", "arrv_", "--arrv-iter", "5", "--stats-iter", "3"])
+    assert rc == 0
+    out = capsys.readouterr().out
+    assert "LOG_PROB" in out and "AIC" in out and "BIC" in out and "RHAT" in out
+    mu = numpy.loadtxt("mu.txt")
+    assert mu.shape == (12, 7) and numpy.all(mu > 0)
+    tw = numpy.loadtxt("train_mean_wait.txt")
+    assert tw.shape == (12, 8) and numpy.array_equal(tw[:, 0], numpy.arange(12))
+    assert numpy.loadtxt("mean_service.txt").shape == (3, 7)
+    for name in ("initial.txt", "arrv_0.txt", "arrv_5.txt", "arrv_10.txt"):
+        with open(name) as f:
+            back = qnetu.read_csv_from_lines(net, f.readlines())
+        assert back.num_events() == ini.num_events()
+    # StEM through the same front end, MH sampler, single chain
+    rc = gibbs.main(["-n", "net.yml", "-A", "obs_", "--burn", "3", "--gibbs-iter", "5", "--thin", "2", "--sampler", "MH",
+                     "--output-mu", "mu2.txt"])
+    estimation.set_sampler("SLICE")
+    assert rc == 0 and numpy.loadtxt("mu2.txt").shape == (5, 7)

@@ -202,3 +202,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("Py3 oracle", ""), "%s mentions the oracle" % f
+
+
+@pytest.mark.parametrize("name", ["qnet3", "mm3", "psdelay"])
+def test_qstats_match_reference(name):
+    """Every exported statistic of qstats.py (qstats.py:174-184) on a state the reference produced, against the values
+    the reference's own qstats computed for it (tests/golden/qstats_*.npz)."""
+    import helpers
+    from bayes_qnet_b200 import qstats
+    g = helpers.golden("qstats_" + name)
+    net, arrv = helpers.golden_state(g, "s0")
+    for n in g["stat_names"]:
+        ours = numpy.atleast_1d(numpy.array(getattr(qstats, str(n))(arrv), dtype=numpy.float64))
+        ref = g["stat_" + str(n)]
+        assert ours.shape == ref.shape, n
+        m = numpy.isfinite(ref)
+        assert numpy.array_equal(numpy.isfinite(ours), m), n
+        assert numpy.allclose(ours[m], ref[m], rtol=1e-9, atol=1e-12), (n, ours, ref)
+    assert qstats.all_stats_string().split() == [str(n) for n in g["stat_names"]][:len(qstats.STATS)]
