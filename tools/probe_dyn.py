@@ -92,6 +92,7 @@ def main():
                                   "algorithmic_GBps": rate * nbytes / 1e9, "reject_frac": st["nreject"] / max(st["nevents"], 1),
                                   "evals_per_resample": st["slice_evals"] / st["nevents"],
                                   "walk_steps_per_resample": st["diff_len"] / st["nevents"],
+                                  "redone_frac": st["n_redone"] / max(st["nevents"], 1),
                                   "stuck": st["n_stuck"]}), flush=True)
 
 
