@@ -410,7 +410,7 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
     h->dyn_w = (h->C >= 12288) ? 4 : (h->C >= 6144 ? 8 : (h->C >= 1536 ? 16 : 32));
     if (const char *env = getenv("BQ_DYN_W")) {
         int w = atoi(env);
-        if (w == 1 || w == 2 || w == 4 || w == 8 || w == 16 || w == 32) h->dyn_w = w;
+        if (w == 4 || w == 8 || w == 16 || w == 32) h->dyn_w = w;
     }
     if (const char *env = getenv("BQ_DYN_THREADS")) {
         int t = atoi(env);
@@ -457,9 +457,7 @@ static void launch_dynamic(bq_handle *h, const DynArgs &A) {
         else sweep_batch_kernel<8><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
         return;
     }
-    if (h->dyn_w == 1) launch_dynamic_w<1>(h, A);
-    else if (h->dyn_w == 2) launch_dynamic_w<2>(h, A);
-    else if (h->dyn_w == 4) launch_dynamic_w<4>(h, A);
+    if (h->dyn_w == 4) launch_dynamic_w<4>(h, A);
     else if (h->dyn_w == 8) launch_dynamic_w<8>(h, A);
     else if (h->dyn_w == 16) launch_dynamic_w<16>(h, A);
     else launch_dynamic_w<32>(h, A);

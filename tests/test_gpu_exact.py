@@ -1,0 +1,89 @@
+"""Distributional checks of the samplers against closed-form answers, in the style of the reference's own
+test_qnet.py:222-298 (sum of exponential services is hypo-exponential; with equal rates the conditional of the
+intermediate time is uniform).  Thousands of chains on the GPU stand in for the reference's repeated runs, a
+Kolmogorov-Smirnov test for its decile comparison (netutils.py:183-201).  Independent of the oracle and of the
+reference build: every kernel -- chromatic slice, chromatic MH, batch, group -- must reproduce the exact law."""
+import numpy
+import pytest
+import scipy.stats
+
+from bayes_qnet_b200 import GibbsEngine, qnetu
+from bayes_qnet_b200.arrivals import Arrivals
+
+pytestmark = pytest.mark.gpu
+
+TANDEM2 = """
+states:
+  - {name: INITIAL, queues: [INITIAL], successors: [S1], initial: TRUE}
+  - {name: S1, queues: [Q1], successors: [S2]}
+  - {name: S2, queues: [Q2]}
+queues:
+  - { name: INITIAL, service: [M, 10.0] }
+  - { name: Q1, service: [M, %s] }
+  - { name: Q2, service: [M, %s] }
+"""
+
+
+def _tasks(net, nt, mu1, mu2, final_observed, rs):
+    """nt tasks 10 time units apart (no queueing to speak of), source departures observed, the time between Q1 and
+    Q2 hidden; the final departure observed or not."""
+    tid, qid, state, a, d, oa, od = [], [], [], [], [], [], []
+    for t in range(nt):
+        t0 = 10.0 * (t + 1)
+        d1 = t0 + rs.exponential(mu1)
+        d2 = d1 + rs.exponential(mu2)
+        for q, (aa, dd, o_a, o_d) in enumerate(((0.0, t0, 1, 1), (t0, d1, 1, 0), (d1, d2, 0, 1 if final_observed else 0))):
+            tid.append(t); qid.append(q); state.append(q); a.append(aa); d.append(dd); oa.append(o_a); od.append(o_d)
+    return Arrivals.from_arrays(net, tid, qid, state, a, d, oa, od)
+
+
+def _kernels(monkeypatch, which):
+    if which in ("batch", "group"):
+        monkeypatch.setenv("BQ_FORCE_DYNAMIC", "1")
+        monkeypatch.setenv("BQ_MH_DYNAMIC", "1")
+        monkeypatch.setenv("BQ_DYN_BATCH", "1" if which == "batch" else "0")
+
+
+@pytest.mark.parametrize("which", ["chromatic", "batch", "group"])
+@pytest.mark.parametrize("mode", ["SLICE", "MH"])
+def test_conditional_is_uniform_with_equal_rates(mode, which, monkeypatch):
+    """test_qnet.py:256-298 (test_m2b_via_uniform): a_e and d_e' fixed, both services Exp(0.5): d_e ~ U[a_e, d_e']."""
+    _kernels(monkeypatch, which)
+    net = qnetu.qnet_from_text(TANDEM2 % (0.5, 0.5))
+    arrv = _tasks(net, 5, 0.5, 0.5, True, numpy.random.RandomState(1))
+    soa = arrv.soa()
+    C = 4096
+    with GibbsEngine(net, arrv, n_chains=C, seed=17) as eng:
+        eng.sweep(12, mode, "NONE")
+        d = eng.state()
+    for t in range(5):
+        e = 3 * t + 1
+        lo, hi = soa["d"][e - 1], soa["d"][e + 1]
+        u = (d[:, e] - lo) / (hi - lo)
+        assert numpy.all((u >= 0) & (u <= 1))
+        assert scipy.stats.kstest(u, "uniform").pvalue > 1e-4, (mode, which, t)
+    # the observed times never move
+    fixed = numpy.array([e for e in range(15) if e % 3 != 1])
+    assert numpy.array_equal(d[:, fixed], numpy.broadcast_to(soa["d"][fixed], (C, len(fixed))))
+
+
+@pytest.mark.parametrize("which", ["chromatic", "batch", "group"])
+@pytest.mark.parametrize("mode", ["SLICE", "MH"])
+def test_unobserved_services_follow_the_prior(mode, which, monkeypatch):
+    """test_qnet.py:222-253 (test_m2_via_gamma): only the source departures observed, so the sampler draws the two
+    services from their prior: s1 + s2 ~ Exp(mean 0.5) + Exp(mean 0.25), each marginal exponential."""
+    _kernels(monkeypatch, which)
+    net = qnetu.qnet_from_text(TANDEM2 % (0.5, 0.25))
+    arrv = _tasks(net, 5, 0.5, 0.25, False, numpy.random.RandomState(2))
+    soa = arrv.soa()
+    C = 4096
+    with GibbsEngine(net, arrv, n_chains=C, seed=23) as eng:
+        eng.sweep(40, mode, "NONE")
+        full = eng.state(full=True)
+    l1, l2 = 2.0, 4.0
+    hypo = lambda t: 1.0 - (l2 * numpy.exp(-l1 * t) - l1 * numpy.exp(-l2 * t)) / (l2 - l1)
+    for t in (0, 2, 4):
+        s1, s2 = full["s"][:, 3 * t + 1], full["s"][:, 3 * t + 2]
+        assert scipy.stats.kstest(s1 + s2, hypo).pvalue > 1e-4, (mode, which, t)
+        assert scipy.stats.kstest(s1, "expon", args=(0, 0.5)).pvalue > 1e-4
+        assert scipy.stats.kstest(s2, "expon", args=(0, 0.25)).pvalue > 1e-4

@@ -252,7 +252,7 @@ def test_posterior_agrees_with_long_reference_runs(name):
     assert numpy.all(diagnostics.rhat(th) < 2.0)
 
 
-@pytest.mark.parametrize("width", ["1", "2", "4", "8", "16", "32"])
+@pytest.mark.parametrize("width", ["4", "8", "16", "32"])
 @pytest.mark.parametrize("name", ["qnet3", "lng1", "mm3", "lnk", "psdelay"])
 def test_dynamic_kernel_group_widths(name, width, monkeypatch):
     """The dynamic-order kernel (per-chain queue order, free-time vectors) with W = 8 / 16 / 32 lanes per chain:
@@ -387,7 +387,7 @@ def test_mh_counts_and_group_widths(monkeypatch):
     net, arrv = helpers.golden_state(g, "s0")
     ref = None
     monkeypatch.setenv("BQ_DYN_BATCH", "0")
-    for width in ("1", "4", "8", "16", "32"):
+    for width in ("4", "8", "16", "32"):
         monkeypatch.setenv("BQ_DYN_W", width)
         with GibbsEngine(net, arrv, n_chains=1, seed=31) as eng:
             seq = eng.mh_order()
@@ -521,3 +521,45 @@ def test_gibbs_front_end(tmp_path, monkeypatch, capsys):
                      "--output-mu", "mu2.txt"])
     estimation.set_sampler("SLICE")
     assert rc == 0 and numpy.loadtxt("mu2.txt").shape == (5, 7)
+
+
+@pytest.mark.parametrize("name", ["qnet3", "lng1", "mm3", "lnk", "delay_gg1_gg4"])
+def test_incremental_conditional_equals_log_prob_difference(name):
+    """The identity the reference checks in test_likdelta.py:43-75: for hidden events and several offsets, the
+    incrementally evaluated conditional inner_dfun(d1) - lik0 equals log_prob after physically moving the departure
+    (queues re-ranked by arrival, services recomputed from scratch) minus log_prob before.  Here at a few hundred
+    tasks, on static- and dynamic-order networks, without the oracle."""
+    if name in helpers.MIXED:
+        net, smp, sub, ini = helpers.mixed(name, ntasks=300, pct=0.2, seed=33)
+    else:
+        g = helpers.golden("cond_" + name)
+        net = qnetu.qnet_from_text(str(g["yaml"]))
+        net.parameters = list(g["theta"])
+        qnetu.set_seed(44)
+        ini = net.gibbs_initialize(net.sample(300).subset_by_task(0.2))
+    rs = numpy.random.RandomState(9)
+    # only feasible moves are compared: where the conditional is -inf (a service would go negative in the current
+    # order) "the state after the move" is not defined -- re-ranking the queue from scratch can make it feasible again
+    with GibbsEngine(net, ini, n_chains=2, seed=3) as eng:
+        eng.sweep(3, "SLICE", "NONE")       # move away from the initialiser's state
+        base = eng.state(0, 1, full=True)
+        d0 = base["d"][0].copy()
+        eng.set_state(d0, 1, 2)              # chain 1 = scratch copy of chain 0
+        lp0 = eng.log_prob()[1]
+        order = eng.schedule()[1]
+        soa = ini.soa()
+        checked = 0
+        for e in rs.choice(order, size=40, replace=False):
+            e1 = soa["next_byt"][e]
+            lo, hi = base["a"][0][e], (d0[e1] if e1 >= 0 else d0[e] + 2.0)
+            xs = numpy.concatenate((d0[e] + numpy.array([-0.3, 0.3]) * min(d0[e] - lo, hi - d0[e]), rs.uniform(lo, hi, 3)))
+            inc = eng.logcond(0, int(e), xs)
+            for x, v in zip(xs, inc):
+                d1 = d0.copy()
+                d1[e] = x
+                eng.set_state(d1, 1, 2)
+                lp1 = eng.log_prob()[1]
+                if numpy.isfinite(v):
+                    assert abs((lp1 - lp0) - v) < 1e-8 * max(1.0, abs(lp0)), (name, e, x, v, lp1 - lp0)
+                    checked += 1
+        assert checked > 60
