@@ -129,3 +129,23 @@ def test_emulated_batches_are_the_sequential_sweep(name):
                 assert ec.check() == 0
             assert redone > 0  # task-major order: neighbours in a batch do conflict
             assert helpers.relerr(ec.d, oc.d).max() < TOL
+
+
+def test_emulated_code_is_clean_under_address_sanitizer(tmp_path):
+    """The same routines, compiled with -fsanitize=address, driven over every fixture network with probes outside
+    the support, slice / MH / batch sweeps (tests/emul/asan_check.py)."""
+    import os
+    import subprocess
+    import sys
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    so = str(tmp_path / "libbq_emul_asan.so")
+    subprocess.check_call([emul_helper.NVCC, "-O1", "-g", "-std=c++17", "-Wno-deprecated-gpu-targets",
+                           "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fsanitize=address,-fno-omit-frame-pointer",
+                           "-shared", "-o", so, emul_helper.SRC])
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", BQ_EMUL_SO=so)
+    r = subprocess.run([sys.executable, os.path.join(emul_helper.HERE, "emul", "asan_check.py")], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ERROR: AddressSanitizer" not in r.stderr, r.stderr[-3000:]
+    assert r.stdout.count(" ok") == 10
