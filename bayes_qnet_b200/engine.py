@@ -93,6 +93,25 @@ class GibbsEngine(object):
         if sync:
             self.synchronize()
 
+    def disperse(self, sweeps=20, scale=0.7, seed=0, mode="SLICE"):
+        """Over-dispersed starting points for convergence diagnostics (new; the reference is single-chain): every
+        chain runs `sweeps` sweeps under its own perturbed parameters theta * exp(scale * N(0, 1)) -- held fixed --
+        then gets its parameters back.  Chains that started from one state are then spread wider than the posterior,
+        which is what R-hat assumes.  Queue membership and, for static-order networks, the queue order stay those
+        of the initial state (they are shared by all chains of a handle)."""
+        th = self.params()
+        rs = numpy.random.RandomState(seed)
+        pert = th * numpy.exp(scale * rs.standard_normal(th.shape))
+        # location parameters (LogNormal meanlog) are shifted, not scaled
+        col = 0
+        for q in self.net.queues:
+            if q.service.code == 2:
+                pert[:, col] = th[:, col] + scale * rs.standard_normal(self.n_chains)
+            col += q.service.numParameters()
+        self.set_params(pert)
+        self.sweep(sweeps, mode, "NONE")
+        self.set_params(th)
+
     def synchronize(self):
         capi.check(self._L.bq_synchronize(self._h))
 

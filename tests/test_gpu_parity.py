@@ -563,3 +563,20 @@ def test_incremental_conditional_equals_log_prob_difference(name):
                     assert abs((lp1 - lp0) - v) < 1e-8 * max(1.0, abs(lp0)), (name, e, x, v, lp1 - lp0)
                     checked += 1
         assert checked > 60
+
+
+def test_disperse_spreads_the_chains():
+    """GibbsEngine.disperse: burn-in under per-chain perturbed parameters, parameters restored afterwards; the
+    chains' states end up more spread than after the same number of ordinary sweeps, and stay valid."""
+    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 200, 0.2, seed=4)
+    hidden = ini.soa()["obs_d"] == 0
+    with GibbsEngine(net, ini, n_chains=64, seed=9) as a, GibbsEngine(net, ini, n_chains=64, seed=9) as b:
+        th0 = a.params().copy()
+        a.disperse(sweeps=15, scale=0.7, seed=1)
+        b.sweep(15, "SLICE", "NONE")
+        assert numpy.array_equal(a.params(), th0)
+        sa, sb = a.state(full=True), b.state(full=True)
+        assert numpy.all(sa["s"] >= 0) and numpy.all(numpy.isfinite(a.log_prob()))
+        spread_a = numpy.std(sa["d"][:, hidden], axis=0).mean()
+        spread_b = numpy.std(sb["d"][:, hidden], axis=0).mean()
+        assert spread_a > 1.2 * spread_b
