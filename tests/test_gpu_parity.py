@@ -8,7 +8,7 @@ import numpy
 import pytest
 
 import helpers
-from bayes_qnet_b200 import GibbsEngine, capi, diagnostics, estimation, qnetu
+from bayes_qnet_b200 import GibbsEngine, capi, diagnostics, estimation, qnet, qnetu
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -580,3 +580,47 @@ def test_disperse_spreads_the_chains():
         spread_a = numpy.std(sa["d"][:, hidden], axis=0).mean()
         spread_b = numpy.std(sb["d"][:, hidden], axis=0).mean()
         assert spread_a > 1.2 * spread_b
+
+
+@pytest.mark.parametrize("batch", ["1", "0"])
+def test_dynamic_edge_cases(batch, monkeypatch):
+    """Dynamic-order kernels on degenerate inputs: nothing hidden, everything hidden, a single task, odd chain counts,
+    too many processors -- for a multi-server network and a PS network."""
+    monkeypatch.setenv("BQ_DYN_BATCH", batch)
+    for name, init in (("mm3", "DFN2"), ("psdelay", "PS")):
+        g = helpers.golden("cond_" + name)
+        yaml_text = str(g["yaml"])
+        old = qnet.get_initializer()
+        qnet.set_initialization_type(init)
+        try:
+            # nothing hidden: no eligible event, sweeps are no-ops, reporting still works
+            net, smp, sub, ini = helpers.synthetic(yaml_text, 30, 2.0, seed=3, theta=g["theta"])
+            with GibbsEngine(net, ini, n_chains=3, seed=1) as eng:
+                assert len(eng.schedule()[1]) == 0
+                d0 = eng.state()
+                eng.sweep(2, "SLICE", "BAYES", trace=True)
+                assert numpy.array_equal(eng.state(), d0) and eng.stats()["nevents"] == 0
+                assert numpy.all(numpy.isfinite(eng.log_prob()))
+            # everything hidden, odd chain count
+            net, smp, sub, ini = helpers.synthetic(yaml_text, 30, -1.0, seed=3, theta=g["theta"])
+            with GibbsEngine(net, ini, n_chains=5, seed=1) as eng:
+                n = len(eng.schedule()[1])
+                assert n == ini.num_events()
+                eng.sweep(3, "SLICE", "NONE")
+                full = eng.state(full=True)
+                assert numpy.all(full["s"] >= 0) and eng.stats()["nevents"] == 5 * 3 * n
+                oc = helpers.oracle_chain(net, ini)
+                for s in range(3):
+                    oc.slice_sweep(eng.schedule()[1], eng.seed, 4, s)
+                assert helpers.relerr(full["d"][4], oc.d).max() < 1e-7
+            # a single hidden task
+            net, smp, sub, ini = helpers.synthetic(yaml_text, 1, -1.0, seed=3, theta=g["theta"])
+            with GibbsEngine(net, ini, n_chains=2, seed=1) as eng:
+                eng.sweep(5, "SLICE", "NONE")
+                assert numpy.all(eng.state(full=True)["s"] >= 0)
+        finally:
+            qnet.set_initialization_type(old)
+    wide = str(helpers.golden("cond_mm3")["yaml"]).replace("processors: 3", "processors: 9")
+    net, smp, sub, ini = helpers.synthetic(wide, 20, 0.5, seed=1)
+    with pytest.raises(capi.BqError):
+        GibbsEngine(net, ini, n_chains=1, seed=1)
