@@ -87,3 +87,34 @@ def test_unobserved_services_follow_the_prior(mode, which, monkeypatch):
         assert scipy.stats.kstest(s1 + s2, hypo).pvalue > 1e-4, (mode, which, t)
         assert scipy.stats.kstest(s1, "expon", args=(0, 0.5)).pvalue > 1e-4
         assert scipy.stats.kstest(s2, "expon", args=(0, 0.25)).pvalue > 1e-4
+
+
+def test_kernels_agree_at_scale(monkeypatch):
+    """The chromatic kernel and the batch kernel are different programs with different scan orders; at a size where
+    the batch kernel's conflicts are rare (500 tasks) their posteriors must agree within Monte-Carlo error, for the
+    slice and the MH sampler."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import helpers
+    from bayes_qnet_b200 import diagnostics
+    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 500, 0.2, seed=21)
+    runs = {}
+    for which in ("chromatic", "batch"):
+        if which == "batch":
+            monkeypatch.setenv("BQ_FORCE_DYNAMIC", "1")
+            monkeypatch.setenv("BQ_MH_DYNAMIC", "1")
+        for mode in ("SLICE", "MH"):
+            with GibbsEngine(net, ini, n_chains=64, seed=101) as eng:
+                eng.sweep(400, mode, "BAYES", trace=True)
+                th, mw, lp = eng.traces()
+                st = eng.stats()
+                if which == "batch":
+                    assert st["n_redone"] < 0.2 * st["nevents"]
+            runs[(which, mode)] = (th[100:], mw[100:, :, 1:])
+    ref = runs[("chromatic", "SLICE")]
+    for key, (th, mw) in runs.items():
+        for ours, other, what in ((th, ref[0], "theta"), (mw, ref[1], "mean wait")):
+            se = numpy.sqrt(diagnostics.mcse(ours) ** 2 + diagnostics.mcse(other) ** 2)
+            z = numpy.abs(ours.mean(axis=(0, 1)) - other.mean(axis=(0, 1))) / numpy.maximum(se, 1e-12)
+            assert numpy.all(z < 4.5), (key, what, z)
