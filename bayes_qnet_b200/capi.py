@@ -81,6 +81,8 @@ SYMBOLS = {
                                        ctypes.c_uint32, ctypes.c_int32, c_f64p]),
     "bq_kernel_info": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                       ctypes.POINTER(ctypes.c_int32)]),
+    "bq_get_sweep_counter": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint32)]),
+    "bq_set_sweep_counter": (ctypes.c_int, [_H, ctypes.c_uint32]),
     "bq_last_sweep_ms": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_float)]),
     "bq_stream": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_void_p)]),
 }

@@ -842,6 +842,19 @@ extern "C" int bq_synchronize(bq_handle *h) {
     return BQ_OK;
 }
 
+// The sweep index that the next bq_sweep call will use as its first counter value: together with the seed, the chain
+// ids, the departure times and the parameters it determines everything that follows (checkpoint / resume).
+extern "C" int bq_get_sweep_counter(bq_handle *h, uint32_t *counter) {
+    if (!h || !counter) return fail(BQ_ERR_INVALID, "null argument");
+    *counter = h->sweep_counter;
+    return BQ_OK;
+}
+extern "C" int bq_set_sweep_counter(bq_handle *h, uint32_t counter) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    h->sweep_counter = counter;
+    return BQ_OK;
+}
+
 extern "C" int bq_last_sweep_ms(bq_handle *h, float *ms) {
     if (!h || !ms) return fail(BQ_ERR_INVALID, "null argument");
     if (!h->timed) return fail(BQ_ERR_INVALID, "no sweep has been launched");

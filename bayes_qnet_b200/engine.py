@@ -112,6 +112,28 @@ class GibbsEngine(object):
         self.sweep(sweeps, mode, "NONE")
         self.set_params(th)
 
+    # ---- checkpoint / resume ----------------------------------------------------------------------------
+    def save(self, path):
+        """Lossless checkpoint (fp64 .npz): departure times and parameters of every chain, seed, chain offset and the
+        sweep counter.  `load` into an engine built from the same model and data continues the run exactly (the
+        reference restarts from 5-decimal CSV snapshots, gibbs.py:137-160)."""
+        ctr = ctypes.c_uint32()
+        capi.check(self._L.bq_get_sweep_counter(self._h, ctypes.byref(ctr)))
+        numpy.savez_compressed(path, d=self.state(), theta=self.params(), seed=numpy.uint64(self.seed),
+                               chain_offset=numpy.int64(self.chain_offset), sweep_counter=numpy.uint32(ctr.value),
+                               n_events=numpy.int64(self.E))
+
+    def load(self, path):
+        z = numpy.load(path)
+        if int(z["n_events"]) != self.E or z["d"].shape != (self.n_chains, self.E):
+            raise ValueError("checkpoint %s does not fit this engine (%s vs %d chains x %d events)" % (
+                path, z["d"].shape, self.n_chains, self.E))
+        if int(z["seed"]) != self.seed or int(z["chain_offset"]) != self.chain_offset:
+            raise ValueError("checkpoint was written with seed %d / chain offset %d" % (int(z["seed"]), int(z["chain_offset"])))
+        self.set_state(z["d"])
+        self.set_params(z["theta"])
+        capi.check(self._L.bq_set_sweep_counter(self._h, int(z["sweep_counter"])))
+
     def synchronize(self):
         capi.check(self._L.bq_synchronize(self._h))
 

@@ -181,6 +181,12 @@ int bq_rng_uniforms(uint64_t seed, int64_t chain, uint32_t sweep, uint32_t id, u
  * chain state is staged in shared memory for the whole launch. */
 int bq_kernel_info(bq_handle *h, int32_t *threads, int32_t *smem_bytes, int32_t *state_in_smem);
 
+/* Checkpoint / resume (the reference restarts from 5-decimal CSV snapshots, gibbs.py:137-160, arrivals.pyx:97 -- lossy;
+ * here a run resumes exactly): the index of the next sweep, which with the seed, the global chain ids, the departure
+ * times (bq_get_state / bq_set_state) and the parameters fixes every random number that follows. */
+int bq_get_sweep_counter(bq_handle *h, uint32_t *counter);
+int bq_set_sweep_counter(bq_handle *h, uint32_t counter);
+
 /* CUDA-event timing of the last bq_sweep call on the handle's stream, in milliseconds. */
 int bq_last_sweep_ms(bq_handle *h, float *ms);
 /* The handle's cudaStream_t (as void*) so callers can order their own work after the sweeps. */

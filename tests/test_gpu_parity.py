@@ -624,3 +624,28 @@ def test_dynamic_edge_cases(batch, monkeypatch):
     net, smp, sub, ini = helpers.synthetic(wide, 20, 0.5, seed=1)
     with pytest.raises(capi.BqError):
         GibbsEngine(net, ini, n_chains=1, seed=1)
+
+
+@pytest.mark.parametrize("name", ["qnet3", "lng1", "mm3", "lnk"])
+def test_checkpoint_resume_is_exact(name, tmp_path):
+    """GibbsEngine.save / load: 4 sweeps, checkpoint, 4 more sweeps in a NEW engine == 8 sweeps in one go, bit for bit
+    (departure times, parameters, traces) -- for static- and dynamic-order networks, slice and MH."""
+    g = helpers.golden("cond_" + name)
+    net, arrv = helpers.golden_state(g, "s0")
+    for mode in ("SLICE", "MH"):
+        with GibbsEngine(net, arrv, n_chains=3, seed=555, chain_offset=2) as whole:
+            whole.sweep(8, mode, "BAYES", trace=True)
+            d8, th8 = whole.state(), whole.params()
+            tr8 = whole.traces()[0]
+        ck = str(tmp_path / ("ck_%s_%s.npz" % (name, mode)))
+        with GibbsEngine(net, arrv, n_chains=3, seed=555, chain_offset=2) as first:
+            first.sweep(4, mode, "BAYES")
+            first.save(ck)
+        with GibbsEngine(net, arrv, n_chains=3, seed=555, chain_offset=2) as second:
+            second.load(ck)
+            second.sweep(4, mode, "BAYES", trace=True)
+            assert numpy.array_equal(second.state(), d8) and numpy.array_equal(second.params(), th8)
+            assert numpy.array_equal(second.traces()[0], tr8[4:])
+        with GibbsEngine(net, arrv, n_chains=3, seed=556, chain_offset=2) as other:
+            with pytest.raises(ValueError):
+                other.load(ck)
