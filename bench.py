@@ -51,11 +51,41 @@ queues:
   - { name: APP2, service: [M, 0.05] }
   - { name: DB, service: [M, 0.3] }
 """
+TANDEM3 = """
+states:
+  - {name: INITIAL, queues: [INITIAL], successors: [TIER1], initial: TRUE}
+  - {name: TIER1, queues: [Q1], successors: [TIER2]}
+  - {name: TIER2, queues: [Q2]}
+queues:
+  - { name: INITIAL, service: [M, 5.0] }
+  - { name: Q1, type: GGk, processors: 3, service: [LN, 1.75, 1.0] }
+  - { name: Q2, type: GGk, processors: 3, service: [LN, 0.1, 2.0] }
+"""
+PSDELAY = """
+states:
+  - {name: INITIAL, queues: [INITIAL], successors: [TIER1], initial: TRUE}
+  - {name: TIER1, queues: [QPS], successors: [TIER2]}
+  - {name: TIER2, queues: [QDELAY]}
+queues:
+  - { name: INITIAL, service: [M, 1.0] }
+  - { name: QPS, type: PS, service: [M, 0.5] }
+  - { name: QDELAY, type: DELAY, service: [M, 2.0] }
+"""
+# BASELINE.json configs[1..3] (the headline is configs[1]); algorithmic bytes per resample from SURVEY.md 8d
+WORKLOADS = {
+    "config2": dict(yaml=QNET3, init="DFN2", tasks=5000, chains=1024, sweeps=20, ref_tasks=5000, bytes=16.0,
+                    kernel="sweep_static_kernel<true>", name="3-tier web-service network (qnet3)"),
+    "config3": dict(yaml=TANDEM3, init="DFN2", tasks=20000, chains=4096, sweeps=2, ref_tasks=1000, bytes=32.0,
+                    kernel="sweep_batch_kernel<4>", name="tandem source -> G/G/3 -> G/G/3, LogNormal service"),
+    "config4": dict(yaml=PSDELAY, init="PS", tasks=50000, chains=2048, sweeps=2, ref_tasks=2000, bytes=80.0 / 3.0,
+                    kernel="sweep_batch_kernel<4>", name="source -> processor sharing -> delay station (one GPU's share "
+                                                         "of the 16384 chains)"),
+}
 BYTES_PER_RESAMPLE = 16.0  # SURVEY.md 8d: source / GGk k=1 / DELAY visits
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the default configuration, from the ncu --set full
 # capture summarised in profiles/r1_static_final_ncu_full.txt (166.0 MB + 108.0 MB)
 NCU_TRAFFIC_DEFAULT = 273.98e6
-WORKLOAD = "3-tier web-service network (qnet3), %d tasks, 20%% observed, %d chains/GPU x %d sweeps per step"
+WORKLOAD = "%s, %d tasks, 20%% observed, %d chains/GPU x %d sweeps per step"
 
 
 def peaks():
@@ -122,17 +152,21 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def make_input(tasks, seed=13):
-    from bayes_qnet_b200 import qnetu
-    net = qnetu.qnet_from_text(QNET3)
+def make_input(tasks, seed=13, yaml_text=QNET3, init="DFN2"):
+    from bayes_qnet_b200 import qnet, qnetu
+    net = qnetu.qnet_from_text(yaml_text)
     qnetu.set_seed(seed)
     smp = net.sample(tasks)
     sub = smp.subset_by_task(0.2)
-    ini = net.gibbs_initialize(sub)
+    qnet.set_initialization_type(init)
+    try:
+        ini = net.gibbs_initialize(sub)
+    finally:
+        qnet.set_initialization_type("DFN2")
     return net, ini
 
 
-def cpu_baseline_reference(tasks, sweeps, seed=13):
+def cpu_baseline_reference(tasks, sweeps, seed=13, yaml_text=QNET3, init="DFN2"):
     """The reference's own single-chain Cython path (oracle/_ref) on the same kind of input, one process per
     host core, each running `sweeps` iterations of estimation.bayes; returns resamples/s summed over cores."""
     ref = os.path.join(ROOT, "oracle", "_ref")
@@ -147,6 +181,7 @@ with contextlib.redirect_stdout(io.StringIO()):
     sampling.DEBUG = 0
     net = qnetu.qnet_from_text(%r)
     qnetu.set_seed(%d + int(sys.argv[1]))
+    qnet.set_initialization_type(%r)
     smp = net.sample(%d); sub = smp.subset_by_task(0.2); ini = net.gibbs_initialize(sub)
     qnet.reset_stats()
     t0 = time.time()
@@ -154,7 +189,7 @@ with contextlib.redirect_stdout(io.StringIO()):
     dt = time.time() - t0
     ne = qnet.stats()['nevents']
 print("RESULT %%d %%.6f" %% (ne, dt))
-""" % (ref, QNET3, seed, tasks, sweeps)
+""" % (ref, yaml_text, seed, init, tasks, sweeps)
     procs = []
     for c in range(ncores):
         cmd = [sys.executable, "-c", code, str(c)]
@@ -178,11 +213,12 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = WORKLOADS[args.workload]
     tasks = args.ref_tasks
     per_step = []
     for i in range(args.warmup + args.steps):
         t0 = time.time()
-        r = cpu_baseline_reference(tasks, args.ref_sweeps, seed=13 + i)
+        r = cpu_baseline_reference(tasks, args.ref_sweeps, seed=13 + i, yaml_text=wl["yaml"], init=wl["init"])
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built on this box"}))
             return
@@ -191,13 +227,13 @@ def run_reference_arm(args):
             per_step.append(r)
     v = sum(r["value"] for r in per_step) / len(per_step)
     cores = per_step[0]["cores"]
-    sample = ("reference Cython estimation.bayes (slice), one pinned single-chain process per core, %d-task qnet3, "
-              "%d iterations per step" % (tasks, args.ref_sweeps))
+    sample = ("reference Cython estimation.bayes (slice), one pinned single-chain process per core, %d-task %s, "
+              "%d iterations per step" % (tasks, args.workload, args.ref_sweeps))
     line = {"impl": "reference", "metric": "chain-task resamples/sec", "value": v, "unit": "resamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(r["sec"] for r in per_step) / len(per_step), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD % (args.tasks, args.chains, args.sweeps), "reference_sample": sample},
+            "config": {"workload": WORKLOAD % (wl["name"], args.tasks, args.chains, args.sweeps), "reference_sample": sample},
             "cpu_baseline": {"value": v, "unit": "resamples/s", "cores": cores, "kind": "reference", "sample": sample,
                              "per_core": v / cores},
             "e2e": {"value": v, "unit": "resamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -211,14 +247,20 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--chains", type=int, default=1024, help="chains per GPU")
-    ap.add_argument("--tasks", type=int, default=5000)
-    ap.add_argument("--sweeps", type=int, default=20, help="Gibbs sweeps per step")
-    ap.add_argument("--ref-tasks", type=int, default=5000)
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
+                    help="BASELINE.json configs[1] (default, the headline), configs[2] or configs[3]")
+    ap.add_argument("--chains", type=int, default=None, help="chains per GPU")
+    ap.add_argument("--tasks", type=int, default=None)
+    ap.add_argument("--sweeps", type=int, default=None, help="Gibbs sweeps per step")
+    ap.add_argument("--ref-tasks", type=int, default=None)
     ap.add_argument("--ref-sweeps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tight", action="store_true", help="BQ_FLAG_TIGHT bracket (not the default sampler)")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    for k in ("chains", "tasks", "sweeps", "ref_tasks"):
+        if getattr(args, k) is None:
+            setattr(args, k, wl[k])
 
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -240,7 +282,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
 
-    net, ini = make_input(args.tasks)  # same seed on every rank -> identical data everywhere
+    net, ini = make_input(args.tasks, yaml_text=wl["yaml"], init=wl["init"])  # same seed on every rank -> identical data
     C, S = args.chains, args.sweeps
     eng = GibbsEngine(net, ini, n_chains=C, seed=20261019, device=local, chain_offset=rank * C)
     n_elig = len(eng.schedule()[1])
@@ -314,7 +356,7 @@ def main():
         e2e = world * resamples_per_step * args.steps / t_e2e
         worst_ms = max(launch_ms)
         mean_ms = sum(launch_ms) / len(launch_ms)
-        achieved = resamples_per_step * BYTES_PER_RESAMPLE / (mean_ms / 1e3) / 1e9
+        achieved = resamples_per_step * wl["bytes"] / (mean_ms / 1e3) / 1e9
         ess = diagnostics.ess(summ)
         rhat = diagnostics.rhat(summ)
         info = eng.kernel_info()
@@ -322,7 +364,8 @@ def main():
             "metric": "chain-task resamples/sec", "value": value, "unit": "resamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD % (args.tasks, C, S), "events_per_chain": eng.E,
+            "config": {"workload": WORKLOAD % (wl["name"], args.tasks, C, S), "baseline_config": args.workload,
+                       "events_per_chain": eng.E,
                        "resampled_events_per_chain": n_elig, "chains_total": world * C, "sweeps_per_step": S,
                        "param_update": "BAYES (posterior draw every sweep)", "sampler": "slice" + (" tight" if args.tight else ""),
                        "l2": "256 MiB buffer written between timed steps (L2 flush); chain state 8*E*C = %.0f MB" % (8e-6 * eng.E * C),
@@ -333,12 +376,13 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak,
-                         "traffic": NCU_TRAFFIC_DEFAULT if (args.tasks, C, S) == (5000, 1024, 20) else None,
-                         "traffic_note": "bytes per launch from profiles/r1_static_final_ncu_full.txt; far BELOW the "
-                                         "algorithmic 16 B x resamples because the chain state stays in shared memory "
-                                         "for all sweeps of a launch",
+                         "traffic": NCU_TRAFFIC_DEFAULT if (args.workload, args.tasks, C, S) == ("config2", 5000, 1024, 20) else None,
+                         "traffic_note": ("bytes per launch from profiles/r1_static_final_ncu_full.txt; far BELOW the "
+                                          "algorithmic 16 B x resamples because the chain state stays in shared memory "
+                                          "for all sweeps of a launch") if args.workload == "config2" else
+                                         "see profiles/r1_batch_tandem_ncu_full.txt (61 GB per launch of 39 M resamples)",
                          "peak_kind": peak_kind,
-                         "kernel": "sweep_static_kernel<true>", "bytes_per_resample": BYTES_PER_RESAMPLE,
+                         "kernel": wl["kernel"], "bytes_per_resample": wl["bytes"],
                          "resamples_per_launch": resamples_per_step, "launch_ms_mean": mean_ms, "launch_ms_max": worst_ms},
             "clocks": sampler.summary(),
             "ess_per_s": float(numpy.min(ess)) / (ess_ms / 1e3) if numpy.all(numpy.isfinite(ess)) else None,
@@ -349,13 +393,13 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             t0 = time.time()
-            cb = cpu_baseline_reference(args.ref_tasks, args.ref_sweeps)
+            cb = cpu_baseline_reference(args.ref_tasks, args.ref_sweeps, yaml_text=wl["yaml"], init=wl["init"])
             if cb is not None:
                 line["cpu_baseline"] = {
                     "value": cb["value"], "unit": "resamples/s", "cores": cb["cores"], "kind": "reference",
                     "per_core": cb["per_core"],
                     "sample": "reference Cython estimation.bayes (slice), one pinned single-chain process per core, "
-                              "%d-task qnet3, %d iterations each (%.0f s wall)" % (args.ref_tasks, args.ref_sweeps, time.time() - t0)}
+                              "%d-task %s, %d iterations each (%.0f s wall)" % (args.ref_tasks, args.workload, args.ref_sweeps, time.time() - t0)}
         print(json.dumps(line))
     eng.close()
     if world > 1:
