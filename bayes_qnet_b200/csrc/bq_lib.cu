@@ -453,8 +453,16 @@ static void launch_dynamic(bq_handle *h, const DynArgs &A) {
     if (h->dyn_batch) {  // one warp per chain, 32 events of the chain in flight
         const int G = 4, blocks = (h->C + G - 1) / G;
         const size_t sm = (size_t)G * dyn_group_smem(h->Q, h->P);
-        if (h->kmax <= 4) sweep_batch_kernel<4><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
-        else sweep_batch_kernel<8><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        const bool dense = h->C > 16 * sms;  // more chains than 16 warps per SM can hold: use the 32-warp build
+        if (h->kmax <= 4) {
+            if (dense) sweep_batch_kernel<4, 8><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
+            else sweep_batch_kernel<4, 4><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
+        } else {
+            if (dense) sweep_batch_kernel<8, 8><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
+            else sweep_batch_kernel<8, 4><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
+        }
         return;
     }
     if (h->dyn_w == 4) launch_dynamic_w<4>(h, A);
