@@ -204,38 +204,91 @@ BQ_HDI int upper_from(const double *v, int lo, int hi, int hint, double t) {
 
 // ---------------------------------------------------------------------------------------------
 // FIFO queue with k servers: likelihoodDelta(diffListForDeparture(e, x))   (queues.pyx:470-511, 83-95)
+//
+// Every event replaces the smallest free time by its own departure, which is never smaller, so the free-time
+// vector F[p] seen at position p is the k largest departures among the positions before p (over k initial zeros),
+// F[p][0] is nondecreasing in p, and the value dropped at step p - 1, F[p-1][0], is the largest one outside F[p].
+// Moving the departure at p0 from x0 to x therefore changes the server-free time seen at a later position p,
+// b_old = F[p][0], independently of the other positions:
+//   x > x0:  b_new = min(F[p][1], x)     where x0 <= F[p][0] < x      (x takes the place of x0 or of the minimum)
+//   x < x0:  b_new = max(x, F[p-1][0])   where x  <  F[p][0] <= x0    (x0 leaves, x or the last dropped value enters)
+// and b_new = b_old everywhere else; past the range the vectors are equal again.  The range is found by galloping
+// over F[.][0]; the terms are the ones the reference's diff list holds, added in queue order.
 // ---------------------------------------------------------------------------------------------
+// first p in [lo, hi) with F[p][0] >= t (strict: > t); f = &F[lo][0], stride k.  *far = furthest position probed
+BQ_HDI int free_min_bound(const double *f, int k, int lo, int hi, double t, bool strict, int *far) {
+    int l = lo - 1, r = lo, step = 1;  // the predicate is false at l (or l = lo - 1)
+    while (r < hi) {
+        const double v = f[(size_t)(r - lo) * k];
+        if (strict ? (v > t) : (v >= t)) break;
+        l = r; step <<= 1; r = l + step;
+    }
+    if (r > hi) r = hi;
+    *far = (r < hi) ? r : hi - 1;
+    while (r - l > 1) {
+        const int m = (l + r) >> 1;
+        const double v = f[(size_t)(m - lo) * k];
+        if (strict ? (v > t) : (v >= t)) r = m; else l = m;
+    }
+    return r;
+}
+
+#ifndef BQ_WALK_U
+#define BQ_WALK_U 2
+#endif
 template <int KMAX>
 BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, Touch &tc) {
     const QInfo &q = c.qi[ev.q0];
     const QConst &qc = c.qc[ev.q0];
-    const int k = q.k;
-    const double *fi = c.fvec(q, ev.p0);
-    FreeVec<KMAX> M;
-    M.load(fi, k);
-    const double st = dmax(ev.a_e, M.v[0]);
+    const int k = q.k, p0 = ev.p0;
+    const double *f = c.fvec(q, p0);  // F[p0 + i][j] = f[i k + j]
+    const double x0 = ev.x0;
+    const double st = dmax(ev.a_e, f[0]);
     const double s_new = x - st;
     if (s_new < 0.0) return BQ_NEG_INF;
-    const double s_old = ev.x0 - st;
+    const double s_old = x0 - st;
     double acc = 0.0;
-    if (s_new != s_old) acc = lpdf(qc, s_new) - lpdf_ls(qc, s_old, c.ls[ev.p0]);
-    M.replace_min(x);
-    fi += k;
-    tc.p0(ev.p0);
-    for (int p = ev.p0 + 1; p < q.hi; ++p, fi += k) {
-        tc.p0(p);
-        if (M.equals(fi, k)) break;  // same free times as before: nothing after p changes
-        ++tc.steps;
-        const double bn = M.v[0], bo = fi[0], di = c.dq[p];
-        if (bn != bo) {
-            const double ai = c.at[p];
-            const double sn = di - dmax(ai, bn);
-            if (sn < 0.0) return BQ_NEG_INF;
-            const double so = di - dmax(ai, bo);
-            if (sn != so) acc += lpdf(qc, sn) - lpdf_ls(qc, so, c.ls[p]);
+    if (s_new != s_old) acc = lpdf(qc, s_new) - lpdf_ls(qc, s_old, c.ls[p0]);
+    tc.p0(p0);
+    if (x == x0 || p0 + 1 >= q.hi) return acc;
+    const bool later = x > x0;
+    int far;
+    int p = free_min_bound(f + k, k, p0 + 1, q.hi, later ? x0 : x, !later, &far);
+    tc.p0(far);
+    const double stop = later ? x : x0;
+    // the positions are independent: fetch BQ_WALK_U of them at once so their cache misses overlap
+    const int last = q.hi - 1;
+    bool done = false;
+    while (p <= last && !done) {
+        double bo_[BQ_WALK_U], bx_[BQ_WALK_U], ai_[BQ_WALK_U], di_[BQ_WALK_U];
+#pragma unroll
+        for (int u = 0; u < BQ_WALK_U; ++u) {
+            const int pu = (p + u < last) ? p + u : last;
+            const double *fp = f + (size_t)(pu - p0) * k;
+            bo_[u] = fp[0];
+            bx_[u] = later ? ((k > 1) ? fp[1] : INFINITY) : fp[-k];
+            ai_[u] = c.at[pu];
+            di_[u] = c.dq[pu];
         }
-        M.replace_min(di);
+#pragma unroll
+        for (int u = 0; u < BQ_WALK_U; ++u) {
+            if (done) break;
+            if (p > last) { done = true; break; }
+            const double bo = bo_[u];
+            if (later ? (bo >= stop) : (bo > stop)) { done = true; break; }  // same free times as before from here on
+            ++tc.steps;
+            const double bn = later ? ((bx_[u] < x) ? bx_[u] : x) : ((x > bx_[u]) ? x : bx_[u]);
+            if (bn != bo) {
+                const double ai = ai_[u], di = di_[u];
+                const double sn = di - dmax(ai, bn);
+                if (sn < 0.0) { tc.p0(p); return BQ_NEG_INF; }
+                const double so = di - dmax(ai, bo);
+                if (sn != so) acc += lpdf(qc, sn) - lpdf_ls(qc, so, c.ls[p]);
+            }
+            ++p;
+        }
     }
+    tc.p0(p < q.hi ? p : q.hi - 1);
     return acc;
 }
 
@@ -685,7 +738,7 @@ struct LaneParams {
     double tmax;
 };
 
-template <int KMAX>
+template <int KMAX, bool MH = true, bool SLICE = true>
 BQ_HDI void lane_update(const Chain &c, const EventCtx &ev, const LaneParams &P, LaneUpdate &out) {
     out.x_new = ev.x0; out.changed = 0; out.counted = 0; out.rejected = 0; out.stuck = 0; out.evals = 0;
     out.R.reset(); out.Wt.reset();
@@ -699,7 +752,7 @@ BQ_HDI void lane_update(const Chain &c, const EventCtx &ev, const LaneParams &P,
         out.R.merge(last);
         return v;
     };
-    if (P.mode != MODE_MH) {
+    if (SLICE && (!MH || P.mode != MODE_MH)) {
         const double lower = ev.a_e, upper = (ev.e1 >= 0) ? fmin(ev.d1, P.tmax) : P.tmax;  // qnet.pyx:698-701, 732-734
         Rng rng;
         rng.init(P.seed, P.gchain, P.gsw, (unsigned int)ev.e, TAG_SLICE);
@@ -709,6 +762,7 @@ BQ_HDI void lane_update(const Chain &c, const EventCtx &ev, const LaneParams &P,
         else out.stuck = 1;
         return;
     }
+    if (!MH) return;
     // MH-within-Gibbs (gibbs_resample_pair / gibbs_resample_final, qnet.pyx:382-498); see mh_update for the streams
     const bool final_evt = (ev.e1 < 0);
     if (final_evt && (P.flags & FLAG_NO_FINAL)) return;
@@ -1083,7 +1137,8 @@ __device__ __forceinline__ bool claimed_before(const int *claim, int lo, int hi,
 // MINB = CTAs of 128 threads resident per SM: 4 (128 registers per thread, 16 warps/SM) is fastest as long as all
 // chains are resident; with more than 16 x 148 chains the 8-CTA build (64 registers, some spilling, 32 warps/SM) avoids
 // a second, partly filled wave (measured: +12 % at 4096 chains, -17 % at 2048)
-template <int KMAX, int MINB>
+// MHK: the build for MH sweeps; the slice build carries no proposal code (fewer registers, less spilling).
+template <int KMAX, int MINB, bool MHK>
 __global__ void __launch_bounds__(128, MINB) sweep_batch_kernel(const DynArgs A, int *claim_all, int *claimd_all) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int W = 32;
@@ -1139,7 +1194,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_batch_kernel(const DynArgs A,
                 const int4 r4 = __ldg(&order4[idx]);
                 const DynRec rec = {r4.x, r4.y, r4.z, r4.w};
                 event_load(c, rec, ev);
-                lane_update<KMAX>(c, ev, LP, up);
+                lane_update<KMAX, MHK, !MHK>(c, ev, LP, up);
             }
             __syncwarp();
             if (active && up.changed) {  // publish what this lane will write

@@ -456,13 +456,20 @@ static void launch_dynamic(bq_handle *h, const DynArgs &A) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         const bool dense = h->C > 16 * sms;  // more chains than 16 warps per SM can hold: use the 32-warp build
+#ifndef BQ_DENSE_MINB
+#define BQ_DENSE_MINB 8
+#endif
+#define BQ_LAUNCH_BATCH(K, MINB, MHK) \
+    sweep_batch_kernel<K, MINB, MHK><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd)
+        const bool mh = (A.mode == MODE_MH);
         if (h->kmax <= 4) {
-            if (dense) sweep_batch_kernel<4, 8><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
-            else sweep_batch_kernel<4, 4><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
+            if (dense) { if (mh) BQ_LAUNCH_BATCH(4, BQ_DENSE_MINB, true); else BQ_LAUNCH_BATCH(4, BQ_DENSE_MINB, false); }
+            else { if (mh) BQ_LAUNCH_BATCH(4, 4, true); else BQ_LAUNCH_BATCH(4, 4, false); }
         } else {
-            if (dense) sweep_batch_kernel<8, 8><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
-            else sweep_batch_kernel<8, 4><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
+            if (dense) { if (mh) BQ_LAUNCH_BATCH(8, BQ_DENSE_MINB, true); else BQ_LAUNCH_BATCH(8, BQ_DENSE_MINB, false); }
+            else { if (mh) BQ_LAUNCH_BATCH(8, 4, true); else BQ_LAUNCH_BATCH(8, 4, false); }
         }
+#undef BQ_LAUNCH_BATCH
         return;
     }
     if (h->dyn_w == 4) launch_dynamic_w<4>(h, A);
