@@ -48,6 +48,15 @@
 namespace bq {
 
 // per queue, identical for all chains: discipline, servers, position range [lo, hi), offset of its F block
+// record of one queue position (DynArgs::rec)
+#define BQ_REC_AT 0
+#define BQ_REC_DQ 1
+#define BQ_REC_LS 2
+#define BQ_REC_F 3
+// doubles per record for queues with up to kmax servers: a multiple of 4, so a record never straddles more 32-byte
+// sectors than it must (kmax <= 5: 64 bytes, two positions per 128-byte line)
+BQ_HDF int rec_stride(int kmax) { return (BQ_REC_F + kmax + 3) & ~3; }
+
 struct QInfo {
     int type, k, lo, hi, foff, dist;
 };
@@ -58,15 +67,13 @@ struct DynRec {
 };
 
 struct DynArgs {
-    int E, Q, P, n_order, n_sweeps, update, flags, trace_base, n_chains, EF, mode;
+    int E, Q, P, n_order, n_sweeps, update, flags, trace_base, n_chains, S, mode;
     const DynRec *order;  // [n_order]
     const QInfo *qinfo;   // [Q]
     const int *q_poff;    // [Q] offset of the queue's first parameter
     double *state;        // [C][E]  d by event
     int *ord, *pos;       // [C][E]
-    double *at, *dq;      // [C][E]  by position
-    double *ls;           // [C][E]  by position: log of the service time (queues with Gamma / LogNormal service)
-    double *F;            // [C][EF] by position
+    double *rec;          // [C][E][S] by position: {arrival, departure, log service, free-time vector F[0..k), pad}
     int *dord, *dpos;     // [C][E]  PS
     double *dt, *sq;      // [C][E]  PS
     double *theta;        // [C][P]
@@ -113,7 +120,8 @@ struct FreeVec {
 struct Chain {
     double *d;
     int *ord, *pos;
-    double *at, *dq, *ls, *F;
+    double *rec;  // one record of S doubles per position: the neighbourhood of an event is one or two cache lines
+    int S;
     int *dord, *dpos;
     double *dt, *sq;
     const QInfo *qi;
@@ -124,10 +132,8 @@ struct Chain {
         d = a.state + c * a.E;
         ord = a.ord + c * a.E;
         pos = a.pos + c * a.E;
-        at = a.at + c * a.E;
-        dq = a.dq + c * a.E;
-        ls = a.ls + c * a.E;
-        F = a.F + c * a.EF;
+        rec = a.rec + c * a.E * a.S;
+        S = a.S;
         dord = a.dord ? a.dord + c * a.E : nullptr;
         dpos = a.dpos ? a.dpos + c * a.E : nullptr;
         dt = a.dt ? a.dt + c * a.E : nullptr;
@@ -135,7 +141,11 @@ struct Chain {
         qi = qi_;
         qc = qc_;
     }
-    BQ_HDF double *fvec(const QInfo &q, int p) const { return F + q.foff + (size_t)(p - q.lo) * q.k; }
+    BQ_HDF double &at(int p) const { return rec[(size_t)p * S + BQ_REC_AT]; }  // arrival of the event at position p
+    BQ_HDF double &dq(int p) const { return rec[(size_t)p * S + BQ_REC_DQ]; }  // its departure
+    BQ_HDF double &ls(int p) const { return rec[(size_t)p * S + BQ_REC_LS]; }  // log of its service time (Gamma / LogNormal)
+    // server-free times seen by position p of a FIFO queue; the next position's vector is S doubles further
+    BQ_HDF double *fvec(const QInfo &, int p) const { return rec + (size_t)p * S + BQ_REC_F; }
 };
 
 // the event being resampled and its task successor, with their positions and current times
@@ -148,13 +158,13 @@ BQ_HDF void event_load(const Chain &c, const DynRec &rec, EventCtx &ev) {
     ev.e = rec.e; ev.e1 = rec.e1; ev.q0 = rec.q0; ev.q1 = rec.q1;
     ev.t0 = c.qi[ev.q0].type;
     ev.p0 = c.pos[ev.e];
-    ev.x0 = c.dq[ev.p0];
-    ev.a_e = c.at[ev.p0];
+    ev.x0 = c.dq(ev.p0);
+    ev.a_e = c.at(ev.p0);
     ev.t1 = -1; ev.p1 = -1; ev.d1 = 0.0;
     if (ev.e1 >= 0) {
         ev.t1 = c.qi[ev.q1].type;
         ev.p1 = c.pos[ev.e1];
-        ev.d1 = c.dq[ev.p1];
+        ev.d1 = c.dq(ev.p1);
     }
 }
 
@@ -177,27 +187,27 @@ struct Touch {
     }
 };
 
-// first index in [lo, hi) whose value is > t, galloping from `hint`
-BQ_HDI int upper_from(const double *v, int lo, int hi, int hint, double t) {
+// first index in [lo, hi) whose value v[i stride] is > t, galloping from `hint`
+BQ_HDI int upper_from(const double *v, int lo, int hi, int hint, double t, int stride = 1) {
     if (hint < lo) hint = lo;
     if (hint > hi) hint = hi;
-    int l, r;  // invariant: v[l] <= t (or l == lo - 1), v[r] > t (or r == hi)
-    if (hint < hi && v[hint] <= t) {
+    int l, r;  // invariant: v[(size_t)l * stride] <= t (or l == lo - 1), v[(size_t)r * stride] > t (or r == hi)
+    if (hint < hi && v[(size_t)hint * stride] <= t) {
         l = hint;
         int step = 1;
         r = l + step;
-        while (r < hi && v[r] <= t) { l = r; step <<= 1; r = l + step; }
+        while (r < hi && v[(size_t)r * stride] <= t) { l = r; step <<= 1; r = l + step; }
         if (r > hi) r = hi;
     } else {
         r = hint;
         int step = 1;
         l = r - step;
-        while (l >= lo && v[l] > t) { r = l; step <<= 1; l = r - step; }
+        while (l >= lo && v[(size_t)l * stride] > t) { r = l; step <<= 1; l = r - step; }
         if (l < lo - 1) l = lo - 1;
     }
     while (r - l > 1) {
         const int m = (l + r) >> 1;
-        if (v[m] <= t) l = m; else r = m;
+        if (v[(size_t)m * stride] <= t) l = m; else r = m;
     }
     return r;
 }
@@ -215,7 +225,7 @@ BQ_HDI int upper_from(const double *v, int lo, int hi, int hint, double t) {
 // and b_new = b_old everywhere else; past the range the vectors are equal again.  The range is found by galloping
 // over F[.][0]; the terms are the ones the reference's diff list holds, added in queue order.
 // ---------------------------------------------------------------------------------------------
-// first p in [lo, hi) with F[p][0] >= t (strict: > t); f = &F[lo][0], stride k.  *far = furthest position probed
+// first p in [lo, hi) with F[p][0] >= t (strict: > t); f = &F[lo][0], stride k doubles.  *far = furthest position probed
 BQ_HDI int free_min_bound(const double *f, int k, int lo, int hi, double t, bool strict, int *far) {
     int l = lo - 1, r = lo, step = 1;  // the predicate is false at l (or l = lo - 1)
     while (r < hi) {
@@ -241,19 +251,20 @@ BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, Touch 
     const QInfo &q = c.qi[ev.q0];
     const QConst &qc = c.qc[ev.q0];
     const int k = q.k, p0 = ev.p0;
-    const double *f = c.fvec(q, p0);  // F[p0 + i][j] = f[i k + j]
+    const double *f = c.fvec(q, p0);  // F[p0 + i][j] = f[i S + j]
+    const int S = c.S;
     const double x0 = ev.x0;
     const double st = dmax(ev.a_e, f[0]);
     const double s_new = x - st;
     if (s_new < 0.0) return BQ_NEG_INF;
     const double s_old = x0 - st;
     double acc = 0.0;
-    if (s_new != s_old) acc = lpdf(qc, s_new) - lpdf_ls(qc, s_old, c.ls[p0]);
+    if (s_new != s_old) acc = lpdf(qc, s_new) - lpdf_ls(qc, s_old, c.ls(p0));
     tc.p0(p0);
     if (x == x0 || p0 + 1 >= q.hi) return acc;
     const bool later = x > x0;
     int far;
-    int p = free_min_bound(f + k, k, p0 + 1, q.hi, later ? x0 : x, !later, &far);
+    int p = free_min_bound(f + S, S, p0 + 1, q.hi, later ? x0 : x, !later, &far);
     tc.p0(far);
     const double stop = later ? x : x0;
     // the positions are independent: fetch BQ_WALK_U of them at once so their cache misses overlap
@@ -264,11 +275,11 @@ BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, Touch 
 #pragma unroll
         for (int u = 0; u < BQ_WALK_U; ++u) {
             const int pu = (p + u < last) ? p + u : last;
-            const double *fp = f + (size_t)(pu - p0) * k;
+            const double *fp = f + (size_t)(pu - p0) * S;
             bo_[u] = fp[0];
-            bx_[u] = later ? ((k > 1) ? fp[1] : INFINITY) : fp[-k];
-            ai_[u] = c.at[pu];
-            di_[u] = c.dq[pu];
+            bx_[u] = later ? ((k > 1) ? fp[1] : INFINITY) : fp[-S];
+            ai_[u] = c.at(pu);
+            di_[u] = c.dq(pu);
         }
 #pragma unroll
         for (int u = 0; u < BQ_WALK_U; ++u) {
@@ -283,7 +294,7 @@ BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, Touch 
                 const double sn = di - dmax(ai, bn);
                 if (sn < 0.0) { tc.p0(p); return BQ_NEG_INF; }
                 const double so = di - dmax(ai, bo);
-                if (sn != so) acc += lpdf(qc, sn) - lpdf_ls(qc, so, c.ls[p]);
+                if (sn != so) acc += lpdf(qc, sn) - lpdf_ls(qc, so, c.ls(p));
             }
             ++p;
         }
@@ -298,11 +309,11 @@ BQ_HDF int new_rank(const Chain &c, const QInfo &q, int p1, double x, double a_o
     tc.p1(p1);
     if (x >= a_old) {
         int j = p1;
-        while (j + 1 < q.hi && c.at[j + 1] <= x) ++j;
+        while (j + 1 < q.hi && c.at(j + 1) <= x) ++j;
         tc.p1(j + 1 < q.hi ? j + 1 : j);
         return j;
     }
-    const int j = upper_from(c.at, q.lo, p1, p1 - 1, x);
+    const int j = upper_from(c.rec + BQ_REC_AT, q.lo, p1, p1 - 1, x, c.S);
     const int far = j - (p1 - j) - 1;  // the backward gallop overshoots by at most the distance covered
     tc.p1(far > q.lo ? far : q.lo);
     return j;
@@ -335,14 +346,14 @@ BQ_HDI double ggk_arr_delta(const Chain &c, const EventCtx &ev, double x, Touch 
         else {
             sp = moved_src(t, j, p1);
             tc.p1(sp);
-            ai = ai_old = c.at[sp]; di = c.dq[sp]; fo = c.fvec(q, sp);
+            ai = ai_old = c.at(sp); di = c.dq(sp); fo = c.fvec(q, sp);
             if (t > pe && M.equals(fo, k)) break;
         }
         ++tc.steps;
         const double sn = di - dmax(ai, M.v[0]);
         if (sn < 0.0) return BQ_NEG_INF;
         const double so = di - dmax(ai_old, fo[0]);
-        if (sn != so) acc += lpdf(qc, sn) - lpdf_ls(qc, so, c.ls[sp]);
+        if (sn != so) acc += lpdf(qc, sn) - lpdf_ls(qc, so, c.ls(sp));
         M.replace_min(di);
     }
     return acc;
@@ -377,7 +388,7 @@ struct PsCursor {
     // next piece [t0, t1) with constant N_old = n.  kind: +1 arrival, -1 departure, 0 end of I at t1;
     // `slot` = index of the breakpoint in its array
     BQ_HDF void piece(const Chain &c, const PsMove &mv, double &t1, int &kind, int &slot) const {
-        const double ta = (ia < mv.hi_q) ? c.at[ia] : INFINITY, td = (id < mv.hi_q) ? c.dt[id] : INFINITY;
+        const double ta = (ia < mv.hi_q) ? c.at(ia) : INFINITY, td = (id < mv.hi_q) ? c.dt[id] : INFINITY;
         if (ta <= td) { t1 = ta; kind = 1; slot = ia; } else { t1 = td; kind = -1; slot = id; }
         if (!(t1 < mv.hi)) { t1 = mv.hi; kind = 0; slot = -1; }
     }
@@ -398,7 +409,7 @@ BQ_HDI void ps_move_setup(const Chain &c, int q, int pm, int m, bool is_dep, dou
     mv.sgn = is_dep ? ((t_new > t_old) ? 1 : -1) : ((t_new < t_old) ? 1 : -1);
     // arrivals <= lo: a_m <= lo always (departure moves stay right of a_m; arrival moves: lo = min(a_old, x));
     // departures <= lo: d_m >= lo always, so the rank is at or before m's own departure slot
-    mv.ia = upper_from(c.at, mv.lo_q, mv.hi_q, pm, mv.lo);
+    mv.ia = upper_from(c.rec + BQ_REC_AT, mv.lo_q, mv.hi_q, pm, mv.lo, c.S);
     mv.id = upper_from(c.dt, mv.lo_q, mv.hi_q, mv.dm, mv.lo);
     mv.n0 = (mv.ia - mv.lo_q) - (mv.id - mv.lo_q);
     // the gallops probe between the hint and about twice the distance to the answer
@@ -454,7 +465,7 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, Touch &t
     for (int p = mv.ia - 1; p >= mv.lo_q && need > 0; --p) {
         tc.pa(first, p);
         if (p == mv.pm) continue;
-        const double di = c.dq[p];
+        const double di = c.dq(p);
         if (!(di > mv.lo)) continue;
         --need; ++tc.steps;
         const double ds = ps_delta_service<false>(c, mv, mv.lo, di);
@@ -477,10 +488,10 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, Touch &t
         tc.pa(first, cu.ia < mv.hi_q ? cu.ia : mv.hi_q - 1);
         tc.pd(cu.id < mv.hi_q ? cu.id : mv.hi_q - 1);
     }
-    for (int p = mv.ia; p < mv.hi_q && c.at[p] < mv.hi; ++p) {
+    for (int p = mv.ia; p < mv.hi_q && c.at(p) < mv.hi; ++p) {
         if (p == mv.pm) continue;
         ++tc.steps;
-        const double ds = ps_delta_service<false>(c, mv, c.at[p], c.dq[p]);
+        const double ds = ps_delta_service<false>(c, mv, c.at(p), c.dq(p));
         const double so = c.sq[p];
         double sn = so + ds;
         if (sn < 0.0) sn = 0.0;
@@ -527,7 +538,7 @@ BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, Touch &t
     } else {  // DelayStation: s = d - a, single-event diff list (queues.pyx:745-784)
         const double sn = x - ev.a_e, so = ev.x0 - ev.a_e;
         if (sn < 0.0) return BQ_NEG_INF;
-        g = (sn != so) ? lpdf(c.qc[ev.q0], sn) - lpdf_ls(c.qc[ev.q0], so, c.ls[ev.p0]) : 0.0;
+        g = (sn != so) ? lpdf(c.qc[ev.q0], sn) - lpdf_ls(c.qc[ev.q0], so, c.ls(ev.p0)) : 0.0;
     }
     if (!(g > BQ_NEG_INF) || ev.e1 < 0) return g;
     double g1;
@@ -544,7 +555,7 @@ BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, Touch &t
     } else {
         const double sn = ev.d1 - x, so = ev.d1 - ev.x0;
         if (sn < 0.0) return BQ_NEG_INF;
-        g1 = (sn != so) ? lpdf(c.qc[ev.q1], sn) - lpdf_ls(c.qc[ev.q1], so, c.ls[ev.p1]) : 0.0;
+        g1 = (sn != so) ? lpdf(c.qc[ev.q1], sn) - lpdf_ls(c.qc[ev.q1], so, c.ls(ev.p1)) : 0.0;
     }
     return g + g1;
 }
@@ -597,32 +608,38 @@ BQ_HDI void mh_setup(const Chain &c, const EventCtx &ev, MhProp &pr) {
 // Slide the entry at slot p of a sorted time array to slot j (its rank under the new time), carrying the parallel
 // arrays along: ids ev[] with inverse inv[], and up to two payload arrays (may be null).
 template <int W>
-BQ_HDI void reslot(double *v, int *ev, int *inv, double *pay0, double *pay1, int p, int j, double t_new, int lane,
-                   unsigned gmask) {
+BQ_HDI void reslot(double *v, int sv, int *ev, int *inv, double *pay0, int s0, double *pay1, int s1, int p, int j,
+                   double t_new, int lane, unsigned gmask) {
+#define V_(t) v[(size_t)(t) * sv]
+#define P0_(t) pay0[(size_t)(t) * s0]
+#define P1_(t) pay1[(size_t)(t) * s1]
     const int m = ev[p];
-    const double m0 = pay0 ? pay0[p] : 0.0, m1 = pay1 ? pay1[p] : 0.0;
+    const double m0 = pay0 ? P0_(p) : 0.0, m1 = pay1 ? P1_(p) : 0.0;
     BQ_SYNCG(gmask);
     if (j > p) {  // later: entries p+1..j move one slot towards the head
         for (int base = p + 1; base <= j; base += W) {
             const int t = base + lane;
             int i = -1; double x = 0.0, y0 = 0.0, y1 = 0.0;
-            if (t <= j) { i = ev[t]; x = v[t]; if (pay0) y0 = pay0[t]; if (pay1) y1 = pay1[t]; }
+            if (t <= j) { i = ev[t]; x = V_(t); if (pay0) y0 = P0_(t); if (pay1) y1 = P1_(t); }
             BQ_SYNCG(gmask);
-            if (i >= 0) { ev[t - 1] = i; v[t - 1] = x; inv[i] = t - 1; if (pay0) pay0[t - 1] = y0; if (pay1) pay1[t - 1] = y1; }
+            if (i >= 0) { ev[t - 1] = i; V_(t - 1) = x; inv[i] = t - 1; if (pay0) P0_(t - 1) = y0; if (pay1) P1_(t - 1) = y1; }
             BQ_SYNCG(gmask);
         }
     } else if (j < p) {  // earlier: entries j..p-1 move one slot towards the tail
         for (int top = p - 1; top >= j; top -= W) {
             const int t = top - lane;
             int i = -1; double x = 0.0, y0 = 0.0, y1 = 0.0;
-            if (t >= j) { i = ev[t]; x = v[t]; if (pay0) y0 = pay0[t]; if (pay1) y1 = pay1[t]; }
+            if (t >= j) { i = ev[t]; x = V_(t); if (pay0) y0 = P0_(t); if (pay1) y1 = P1_(t); }
             BQ_SYNCG(gmask);
-            if (i >= 0) { ev[t + 1] = i; v[t + 1] = x; inv[i] = t + 1; if (pay0) pay0[t + 1] = y0; if (pay1) pay1[t + 1] = y1; }
+            if (i >= 0) { ev[t + 1] = i; V_(t + 1) = x; inv[i] = t + 1; if (pay0) P0_(t + 1) = y0; if (pay1) P1_(t + 1) = y1; }
             BQ_SYNCG(gmask);
         }
     }
-    if (lane == 0) { ev[j] = m; v[j] = t_new; inv[m] = j; if (pay0) pay0[j] = m0; if (pay1) pay1[j] = m1; }
+    if (lane == 0) { ev[j] = m; V_(j) = t_new; inv[m] = j; if (pay0) P0_(j) = m0; if (pay1) P1_(j) = m1; }
     BQ_SYNCG(gmask);
+#undef V_
+#undef P0_
+#undef P1_
 }
 
 template <int W, int KMAX>
@@ -635,8 +652,8 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         tmp.reset();
         if (ev.t1 == Q_GGK) j1 = new_rank(c, q1, ev.p1, x, ev.x0, tmp);
         else {  // PS: rank among the other arrivals
-            j1 = upper_from(c.at, q1.lo, q1.hi, ev.p1, x);
-            if (c.at[ev.p1] <= x) --j1;
+            j1 = upper_from(c.rec + BQ_REC_AT, q1.lo, q1.hi, ev.p1, x, c.S);
+            if (c.at(ev.p1) <= x) --j1;
         }
     }
     Touch dummy;
@@ -659,21 +676,21 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         double *fi = c.fvec(q, ev.p0);
         FreeVec<KMAX> M;
         M.load(fi, k);
-        if (log0 && lane == 0) c.ls[ev.p0] = log_d(x - dmax(ev.a_e, M.v[0]));
+        if (log0 && lane == 0) c.ls(ev.p0) = log_d(x - dmax(ev.a_e, M.v[0]));
         M.replace_min(x);
-        fi += k;
-        for (int p = ev.p0 + 1; p < q.hi; ++p, fi += k) {
+        fi += c.S;
+        for (int p = ev.p0 + 1; p < q.hi; ++p, fi += c.S) {
             if (M.equals(fi, k)) break;
-            const double di = c.dq[p];
+            const double di = c.dq(p);
             BQ_SYNCG(gmask);
             if (lane == 0) {
-                if (log0 && M.v[0] != fi[0]) c.ls[p] = log_d(di - dmax(c.at[p], M.v[0]));
+                if (log0 && M.v[0] != fi[0]) c.ls(p) = log_d(di - dmax(c.at(p), M.v[0]));
                 M.store(fi, k);
             }
             M.replace_min(di);
         }
     } else if (ev.t0 == Q_DELAY) {
-        if (log0 && lane == 0) c.ls[ev.p0] = log_d(x - ev.a_e);
+        if (log0 && lane == 0) c.ls(ev.p0) = log_d(x - ev.a_e);
     }
     BQ_SYNCG(gmask);
     if (ev.t0 == Q_PS) {  // the departure changes rank among the queue's sorted departures
@@ -681,9 +698,9 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         const int pd = c.dpos[ev.e];
         int j = upper_from(c.dt, q.lo, q.hi, pd, x);
         if (c.dt[pd] <= x) --j;
-        reslot<W>(c.dt, c.dord, c.dpos, nullptr, nullptr, pd, j, x, lane, gmask);
+        reslot<W>(c.dt, 1, c.dord, c.dpos, nullptr, 1, nullptr, 1, pd, j, x, lane, gmask);
     }
-    if (lane == 0) { c.d[ev.e] = x; c.dq[ev.p0] = x; }
+    if (lane == 0) { c.d[ev.e] = x; c.dq(ev.p0) = x; }
     BQ_SYNCG(gmask);
     // ---- arrival side ------------------------------------------------------------------------------------------
     if (ev.e1 < 0) return;
@@ -692,27 +709,28 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         const QInfo &q = c.qi[ev.q1];
         const int k = q.k, p1 = ev.p1;
         const int ps = (j1 < p1) ? j1 : p1, pe = (j1 < p1) ? p1 : j1;
-        reslot<W>(c.at, c.ord, c.pos, c.dq, log1 ? c.ls : nullptr, p1, j1, x, lane, gmask);
+        reslot<W>(c.rec + BQ_REC_AT, c.S, c.ord, c.pos, c.rec + BQ_REC_DQ, c.S, log1 ? c.rec + BQ_REC_LS : nullptr, c.S, p1, j1, x,
+                  lane, gmask);
         FreeVec<KMAX> M;
         double *fi = c.fvec(q, ps);
         M.load(fi, k);  // predecessors of position ps are untouched
-        for (int t = ps; t < q.hi; ++t, fi += k) {
+        for (int t = ps; t < q.hi; ++t, fi += c.S) {
             if (t > pe && M.equals(fi, k)) break;
-            const double di = c.dq[t];
+            const double di = c.dq(t);
             BQ_SYNCG(gmask);
             if (lane == 0) {
-                if (log1 && (t <= pe || M.v[0] != fi[0])) c.ls[t] = log_d(di - dmax(c.at[t], M.v[0]));
+                if (log1 && (t <= pe || M.v[0] != fi[0])) c.ls(t) = log_d(di - dmax(c.at(t), M.v[0]));
                 M.store(fi, k);
             }
             M.replace_min(di);
         }
         BQ_SYNCG(gmask);
     } else if (ev.t1 == Q_PS) {
-        reslot<W>(c.at, c.ord, c.pos, c.dq, c.sq, ev.p1, j1, x, lane, gmask);
+        reslot<W>(c.rec + BQ_REC_AT, c.S, c.ord, c.pos, c.rec + BQ_REC_DQ, c.S, c.sq, 1, ev.p1, j1, x, lane, gmask);
     } else {
         if (lane == 0) {
-            c.at[ev.p1] = x;
-            if (log1) c.ls[ev.p1] = log_d(ev.d1 - x);
+            c.at(ev.p1) = x;
+            if (log1) c.ls(ev.p1) = log_d(ev.d1 - x);
         }
         BQ_SYNCG(gmask);
     }
@@ -812,8 +830,8 @@ BQ_HDF bool touch_conflict(const Touch &r, const Touch &w) {
 
 // service time of the event at position p of queue q in the current state
 BQ_HDF double dyn_service(const Chain &c, const QInfo &q, int p) {
-    if (q.type == Q_GGK) return c.dq[p] - dmax(c.at[p], c.fvec(q, p)[0]);
-    if (q.type == Q_DELAY) return c.dq[p] - c.at[p];
+    if (q.type == Q_GGK) return c.dq(p) - dmax(c.at(p), c.fvec(q, p)[0]);
+    if (q.type == Q_DELAY) return c.dq(p) - c.at(p);
     return c.sq[p];
 }
 
@@ -845,17 +863,17 @@ __device__ BQ_NOINLINE void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, i
         double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // n, sum, sumlog, nlog, wait, nzero, logp, bad
         for (int p = qi.lo + lane; p < qi.hi; p += W) {
             const double s = dyn_service(c, qi, p);
-            const double w = c.dq[p] - c.at[p] - s;
+            const double w = c.dq(p) - c.at(p) - s;
             v[4] += (w > 0.0) ? w : 0.0;
             if (s > 0.0) {
                 v[0] += 1.0; v[1] += s;
                 if (dist != D_EXP) {
-                    if (dist == D_GAMMA || s >= 1e-50) { v[2] += (qi.type == Q_PS) ? log_d(s) : c.ls[p]; v[3] += 1.0; }
+                    if (dist == D_GAMMA || s >= 1e-50) { v[2] += (qi.type == Q_PS) ? log_d(s) : c.ls(p); v[3] += 1.0; }
                 }
             } else if (s == 0.0) v[5] += 1.0;
             if (want_logp) {
                 if (s < 0.0) v[7] += 1.0;
-                else v[6] += (qi.type == Q_PS) ? lpdf(c.qc[q], s) : lpdf_ls(c.qc[q], s, c.ls[p]);
+                else v[6] += (qi.type == Q_PS) ? lpdf(c.qc[q], s) : lpdf_ls(c.qc[q], s, c.ls(p));
             }
         }
 #pragma unroll
@@ -865,7 +883,7 @@ __device__ BQ_NOINLINE void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, i
             const double mean_log = (v[3] > 0.0) ? v[2] / v[3] : 0.0;
             for (int p = qi.lo + lane; p < qi.hi; p += W) {
                 const double s = dyn_service(c, qi, p);
-                if (s >= 1e-50) { const double z = ((qi.type == Q_PS) ? log_d(s) : c.ls[p]) - mean_log; sq += z * z; }
+                if (s >= 1e-50) { const double z = ((qi.type == Q_PS) ? log_d(s) : c.ls(p)) - mean_log; sq += z * z; }
             }
             sq = group_sum<W>(sq, gmask);
         }
@@ -1043,7 +1061,7 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
         const unsigned int gsw = A.sweep_base + (unsigned int)sw;
         if (sw == 0 || (A.flags & FLAG_TMAX_PER_SWEEP)) {  // Tmax = 2 max d   (qnet.pyx:672)
             double m = 0.0;
-            for (int i = lane; i < E; i += W) m = fmax(m, c.dq[i]);
+            for (int i = lane; i < E; i += W) m = fmax(m, c.d[i]);
             tmax = 2.0 * group_max<W>(m, gmask);
         }
         const int n_order = (A.flags & FLAG_PARAMS_ONLY) ? 0 : A.n_order;
@@ -1177,7 +1195,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_batch_kernel(const DynArgs A,
         LP.gsw = A.sweep_base + (unsigned int)sw;
         if (sw == 0 || (A.flags & FLAG_TMAX_PER_SWEEP)) {  // Tmax = 2 max d   (qnet.pyx:672)
             double m = 0.0;
-            for (int i = lane; i < E; i += W) m = fmax(m, c.dq[i]);
+            for (int i = lane; i < E; i += W) m = fmax(m, c.d[i]);
             LP.tmax = 2.0 * group_max<W>(m, FULL);
         }
         const int n_order = (A.flags & FLAG_PARAMS_ONLY) ? 0 : A.n_order;
@@ -1335,8 +1353,7 @@ __global__ void rebuild_positions_kernel(const DynArgs A, const int *ev_pt) {
     const QInfo qi = A.qinfo[q];
     const double *d = A.state + (size_t)chain * A.E;
     const int *ord = A.ord + (size_t)chain * A.E;
-    double *at = A.at + (size_t)chain * A.E, *dq = A.dq + (size_t)chain * A.E, *ls = A.ls + (size_t)chain * A.E;
-    double *F = A.F + (size_t)chain * A.EF + qi.foff;
+    double *rec = A.rec + (size_t)chain * A.E * A.S;
     FreeVec<KMAX> M;
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) M.v[j] = (j < qi.k) ? 0.0 : INFINITY;
@@ -1344,14 +1361,15 @@ __global__ void rebuild_positions_kernel(const DynArgs A, const int *ev_pt) {
         const int i = ord[p], pt = ev_pt[i];
         const double di = d[i];
         const double ai = (pt >= 0) ? d[pt] : 0.0;
-        dq[p] = di;
-        at[p] = ai;
+        double *r = rec + (size_t)p * A.S;
+        r[BQ_REC_DQ] = di;
+        r[BQ_REC_AT] = ai;
         if (qi.type == Q_GGK) {
-            M.store(F + (size_t)(p - qi.lo) * qi.k, qi.k);
-            if (qi.dist != D_EXP) ls[p] = log_d(di - dmax(ai, M.v[0]));
+            M.store(r + BQ_REC_F, qi.k);
+            if (qi.dist != D_EXP) r[BQ_REC_LS] = log_d(di - dmax(ai, M.v[0]));
             M.replace_min(di);
         } else if (qi.type == Q_DELAY && qi.dist != D_EXP) {
-            ls[p] = log_d(di - ai);
+            r[BQ_REC_LS] = log_d(di - ai);
         }
     }
 }

@@ -81,7 +81,8 @@ struct bq_handle {
     DynRec *d_order = nullptr;
     QInfo *d_qinfo = nullptr;
     int *d_ord = nullptr, *d_pos = nullptr, *d_dord = nullptr, *d_dpos = nullptr;
-    double *d_F = nullptr, *d_sq = nullptr, *d_at = nullptr, *d_dq = nullptr, *d_dt = nullptr, *d_ls = nullptr;
+    double *d_prec = nullptr, *d_sq = nullptr, *d_dt = nullptr;  // position records (DynArgs::rec), PS arrays
+    int recS = 4;  // doubles per position record
     HostNet net() const {
         HostNet n;
         n.E = E; n.Q = Q;
@@ -245,11 +246,11 @@ static cudaError_t replicate_rows(T *base, size_t row, size_t C, cudaStream_t st
 
 static void fill_dyn_args(const bq_handle *h, DynArgs &A) {
     memset(&A, 0, sizeof(A));
-    A.E = h->E; A.Q = h->Q; A.P = h->P; A.n_chains = h->C; A.EF = h->EF;
+    A.E = h->E; A.Q = h->Q; A.P = h->P; A.n_chains = h->C; A.S = h->recS;
     A.n_order = (int)h->dyn_order.size();
     A.order = h->d_order;
     A.qinfo = h->d_qinfo; A.q_poff = h->d_q_poff;
-    A.state = h->d_state; A.ord = h->d_ord; A.pos = h->d_pos; A.at = h->d_at; A.dq = h->d_dq; A.ls = h->d_ls; A.F = h->d_F;
+    A.state = h->d_state; A.ord = h->d_ord; A.pos = h->d_pos; A.rec = h->d_prec;
     A.dord = h->d_dord; A.dpos = h->d_dpos; A.dt = h->d_dt; A.sq = h->d_sq;
     A.theta = h->d_theta; A.stats = h->d_stats;
     A.tr_theta = h->d_tr_theta; A.tr_wait = h->d_tr_wait; A.tr_logp = h->d_tr_logp;
@@ -260,6 +261,9 @@ static void fill_dyn_args(const bq_handle *h, DynArgs &A) {
 struct HostRows {
     std::vector<int> ord, pos, dord, dpos;
     std::vector<double> at, dq, ls, F, dt, sq;
+    std::vector<double> rec;  // at, dq, ls and F interleaved by position, as the device holds them
+    // one record per position: {at, dq, ls, F[0..k)} (bq_dynamic.cuh, BQ_REC_*)
+    void pack(const bq_handle *h, size_t rows);
     void alloc(size_t rows, size_t E, size_t EF, bool ps) {
         ord.assign(rows * E, 0); pos.assign(rows * E, 0);
         at.assign(rows * E, 0.0); dq.assign(rows * E, 0.0); ls.assign(rows * E, 0.0);
@@ -277,9 +281,24 @@ struct HostRows {
     }
 };
 
+void HostRows::pack(const bq_handle *h, size_t rows) {
+    const size_t E = h->E, S = h->recS, EF = h->EF;
+    rec.assign(rows * E * S, 0.0);
+    for (size_t i = 0; i < rows; ++i)
+        for (int q = 0; q < h->Q; ++q) {
+            const int lo = h->q_off[q], hi = h->q_off[q + 1], k = (h->q_type[q] == Q_GGK) ? h->q_k[q] : 0;
+            for (int p = lo; p < hi; ++p) {
+                double *r = &rec[(i * E + p) * S];
+                r[BQ_REC_AT] = at[i * E + p]; r[BQ_REC_DQ] = dq[i * E + p]; r[BQ_REC_LS] = ls[i * E + p];
+                for (int j = 0; j < k; ++j) r[BQ_REC_F + j] = F[i * EF + h->q_foff[q] + (size_t)(p - lo) * k + j];
+            }
+        }
+}
+
 // rows staged on the host -> chains [lo, lo + rows); when rows == 1 < n the row is replicated to n chains
-static int upload_rows(bq_handle *h, const HostRows &r, int lo, size_t rows, size_t n, bool sync) {
-    const size_t E = h->E, EF = h->EF, o = (size_t)lo * E, of = (size_t)lo * EF;
+static int upload_rows(bq_handle *h, HostRows &r, int lo, size_t rows, size_t n, bool sync) {
+    const size_t E = h->E, o = (size_t)lo * E;
+    r.pack(h, rows);
     auto put = [&](auto *dst, const auto &src, size_t row) -> cudaError_t {
         if (!row) return cudaSuccess;
         cudaError_t e = cudaMemcpyAsync(dst, src.data(), rows * row * sizeof(*dst), cudaMemcpyHostToDevice, h->stream);
@@ -288,10 +307,7 @@ static int upload_rows(bq_handle *h, const HostRows &r, int lo, size_t rows, siz
     };
     CK(put(h->d_ord + o, r.ord, E));
     CK(put(h->d_pos + o, r.pos, E));
-    CK(put(h->d_at + o, r.at, E));
-    CK(put(h->d_dq + o, r.dq, E));
-    CK(put(h->d_ls + o, r.ls, E));
-    CK(put(h->d_F + of, r.F, EF));
+    CK(put(h->d_prec + o * h->recS, r.rec, E * h->recS));
     if (h->has_ps) {
         CK(put(h->d_dord + o, r.dord, E));
         CK(put(h->d_dpos + o, r.dpos, E));
@@ -354,6 +370,7 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
             h->EF += h->q_k[q] * (h->q_off[q + 1] - h->q_off[q]);
         }
     if (h->kmax > 8) return fail(BQ_ERR_UNSUPPORTED, "more than 8 processors per queue");
+    h->recS = rec_stride(h->kmax);
     HostRows r0;
     r0.alloc(1, E, h->EF, h->has_ps);
     memcpy(r0.ord.data(), h->ord0.data(), E * sizeof(int));
@@ -383,16 +400,13 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
     CK(upload(&h->d_qinfo, qinfo.data(), qinfo.size()));
     CK(cudaMalloc((void **)&h->d_ord, C * E * sizeof(int)));
     CK(cudaMalloc((void **)&h->d_pos, C * E * sizeof(int)));
-    CK(cudaMalloc((void **)&h->d_at, C * E * sizeof(double)));
-    CK(cudaMalloc((void **)&h->d_dq, C * E * sizeof(double)));
-    CK(cudaMalloc((void **)&h->d_ls, C * E * sizeof(double)));
+    CK(cudaMalloc((void **)&h->d_prec, C * E * h->recS * sizeof(double)));
     {   // log of small counts for the PS terms, computed with the host's log()
         double tab[256];
         tab[0] = -INFINITY;
         for (int i = 1; i < 256; ++i) tab[i] = log((double)i);
         CK(cudaMemcpyToSymbol(c_log_count, tab, sizeof(tab)));
     }
-    CK(cudaMalloc((void **)&h->d_F, std::max<size_t>(C * h->EF, 1) * sizeof(double)));
     if (h->has_ps) {
         CK(cudaMalloc((void **)&h->d_dord, C * E * sizeof(int)));
         CK(cudaMalloc((void **)&h->d_dpos, C * E * sizeof(int)));
@@ -485,7 +499,7 @@ extern "C" int bq_destroy(bq_handle *h) {
     void *ptrs[] = {h->d_rec, h->d_color_off, h->d_ev_q, h->d_ev_p, h->d_ev_pt, h->d_q_events, h->d_q_off,
                     h->d_q_type, h->d_q_dist, h->d_q_poff, h->d_state, h->d_theta, h->d_stats,
                     h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch, h->d_order, h->d_qinfo,
-                    h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_F, h->d_sq, h->d_at, h->d_dq, h->d_dt, h->d_ls, h->d_claim,
+                    h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_prec, h->d_sq, h->d_dt, h->d_claim,
                     h->d_claimd};
     for (void *p : ptrs)
         if (p) cudaFree(p);

@@ -22,7 +22,8 @@ struct Emul {
     std::vector<double> d, F, sq, at, dq, ls, dt, theta;
     std::vector<QConst> qc;
     std::vector<QInfo> qinfo;
-    int EF;
+    std::vector<double> recs;  // at, dq, ls, F interleaved by position: what the kernels work on
+    int EF, S;
     DynArgs A;
     Chain c;
     long evals, steps;
@@ -33,11 +34,31 @@ struct Emul {
             qconst_set(qc[q], q_dist[q], theta[o], q_dist[q] == D_EXP ? 0.0 : theta[o + 1]);
         }
     }
+    // at / dq / ls / F (host_rebuild's separate arrays) <-> position records
+    void pack() {
+        recs.assign((size_t)E * S, 0.0);
+        for (int q = 0; q < Q; ++q)
+            for (int p = q_off[q]; p < q_off[q + 1]; ++p) {
+                double *r = &recs[(size_t)p * S];
+                r[BQ_REC_AT] = at[p]; r[BQ_REC_DQ] = dq[p]; r[BQ_REC_LS] = ls[p];
+                if (q_type[q] == Q_GGK)
+                    for (int j = 0; j < q_k[q]; ++j) r[BQ_REC_F + j] = F[q_foff[q] + (size_t)(p - q_off[q]) * q_k[q] + j];
+            }
+    }
+    void unpack() {
+        for (int q = 0; q < Q; ++q)
+            for (int p = q_off[q]; p < q_off[q + 1]; ++p) {
+                const double *r = &recs[(size_t)p * S];
+                at[p] = r[BQ_REC_AT]; dq[p] = r[BQ_REC_DQ]; ls[p] = r[BQ_REC_LS];
+                if (q_type[q] == Q_GGK)
+                    for (int j = 0; j < q_k[q]; ++j) F[q_foff[q] + (size_t)(p - q_off[q]) * q_k[q] + j] = r[BQ_REC_F + j];
+            }
+    }
     void bind() {
         memset(&A, 0, sizeof(A));
-        A.E = E; A.Q = Q; A.P = P; A.n_chains = 1; A.EF = EF;
+        A.E = E; A.Q = Q; A.P = P; A.n_chains = 1; A.S = S;
         A.qinfo = qinfo.data(); A.q_poff = q_poff.data();
-        A.state = d.data(); A.ord = ord.data(); A.pos = pos.data(); A.at = at.data(); A.dq = dq.data(); A.ls = ls.data(); A.F = F.data();
+        A.state = d.data(); A.ord = ord.data(); A.pos = pos.data(); A.rec = recs.data();
         A.dord = dord.data(); A.dpos = dpos.data(); A.dt = dt.data(); A.sq = sq.data();
         A.theta = theta.data();
         c.bind(A, 0, qinfo.data(), qc.data());
@@ -84,6 +105,11 @@ void *bqe_create(int E, int Q, int P, const int *q_type, const int *q_k, const i
         m->qinfo[q] = QInfo{q_type[q], q_k[q], m->q_off[q], m->q_off[q + 1], m->q_foff[q], q_dist[q]};
     }
     m->F.assign(m->EF + 1, 0.0);
+    {
+        int kmax = 1;
+        for (int q = 0; q < Q; ++q) if (q_type[q] == Q_GGK && q_k[q] > kmax) kmax = q_k[q];
+        m->S = rec_stride(kmax);
+    }
     m->qc.resize(Q);
     {
         HostNet hn = m->net();
@@ -91,6 +117,7 @@ void *bqe_create(int E, int Q, int P, const int *q_type, const int *q_k, const i
                      m->sq.data(), m->dord.data(), m->dpos.data()};
         host_rebuild(&hn, m->d.data(), hc, false);
     }
+    m->pack();
     m->refresh_qc();
     m->bind();
     m->evals = m->steps = 0;
@@ -260,6 +287,7 @@ void bqe_get(void *h, double *d, int *ord, double *F, double *svc) {
     Emul *m = (Emul *)h;
     if (d) memcpy(d, m->d.data(), m->E * sizeof(double));
     if (ord) memcpy(ord, m->ord.data(), m->E * sizeof(int));
+    m->unpack();
     if (F) memcpy(F, m->F.data(), m->EF * sizeof(double));
     if (svc) memcpy(svc, m->sq.data(), m->E * sizeof(double));
 }
@@ -274,6 +302,7 @@ void bqe_derive(void *h, double *a, double *s, int32_t *proc, int32_t *prev_byq,
 // consistency of the incrementally maintained arrays with a from-scratch rebuild: 0 = consistent
 int bqe_check(void *h) {
     Emul *m = (Emul *)h;
+    m->unpack();
     std::vector<int> ord(m->ord), pos(m->E), dord(m->E, -1), dpos(m->E, -1);
     std::vector<double> F(m->EF + 1, 0.0), at(m->E, 0.0), dq(m->E, 0.0), ls(m->E, 0.0), dt(m->E, 0.0), sq(m->E, 0.0);
     HostNet hn = m->net();
