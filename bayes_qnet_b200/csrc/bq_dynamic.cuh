@@ -48,14 +48,17 @@
 namespace bq {
 
 // per queue, identical for all chains: discipline, servers, position range [lo, hi), offset of its F block
-// record of one queue position (DynArgs::rec)
+// Record of one queue position (DynArgs::rec), S doubles:
+//   [0] arrival  [1] departure  [2] F[0]  [3] F[1]  |  [4] log service  [5..] F[2..k)
+// so the departure-side scan, which needs the two smallest free times and the event's own times, reads one
+// 32-byte sector per position.  Networks without multi-server queues keep the log service in slot 3 (S = 4).
 #define BQ_REC_AT 0
 #define BQ_REC_DQ 1
-#define BQ_REC_LS 2
-#define BQ_REC_F 3
-// doubles per record for queues with up to kmax servers: a multiple of 4, so a record never straddles more 32-byte
-// sectors than it must (kmax <= 5: 64 bytes, two positions per 128-byte line)
-BQ_HDF int rec_stride(int kmax) { return (BQ_REC_F + kmax + 3) & ~3; }
+#define BQ_REC_F 2
+// slot of F[j] relative to F[0]
+#define BQ_FSLOT(j) ((j) + ((j) >= 2 ? 1 : 0))
+BQ_HDF int rec_stride(int kmax) { return (kmax <= 1) ? 4 : ((5 + (kmax - 2) + 3) & ~3); }
+BQ_HDF int rec_ls_slot(int S) { return (S == 4) ? 3 : 4; }
 
 struct QInfo {
     int type, k, lo, hi, foff, dist;
@@ -84,13 +87,14 @@ struct DynArgs {
     unsigned int sweep_base;
 };
 
-// ascending multiset of the k server-free times, +inf padded to KMAX so every loop is fully unrolled
+// ascending multiset of the k server-free times, +inf padded to KMAX so every loop is fully unrolled;
+// `f` points at F[0] of a position record (element j at f[BQ_FSLOT(j)])
 template <int KMAX>
 struct FreeVec {
     double v[KMAX];
     BQ_HDF void load(const double *f, int k) {
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j) v[j] = (j < k) ? f[j] : INFINITY;
+        for (int j = 0; j < KMAX; ++j) v[j] = (j < k) ? f[BQ_FSLOT(j)] : INFINITY;
     }
     // the arriving event takes the server that frees first and holds it until x  (queues.pyx:610-612, 654-680)
     BQ_HDF void replace_min(double x) {
@@ -106,13 +110,13 @@ struct FreeVec {
         bool eq = true;
 #pragma unroll
         for (int j = 0; j < KMAX; ++j)
-            if (j < k) eq = eq && (v[j] == f[j]);
+            if (j < k) eq = eq && (v[j] == f[BQ_FSLOT(j)]);
         return eq;
     }
     BQ_HDF void store(double *f, int k) const {
 #pragma unroll
         for (int j = 0; j < KMAX; ++j)
-            if (j < k) f[j] = v[j];
+            if (j < k) f[BQ_FSLOT(j)] = v[j];
     }
 };
 
@@ -121,7 +125,7 @@ struct Chain {
     double *d;
     int *ord, *pos;
     double *rec;  // one record of S doubles per position: the neighbourhood of an event is one or two cache lines
-    int S;
+    int S, ols;   // ols: slot of the log service
     int *dord, *dpos;
     double *dt, *sq;
     const QInfo *qi;
@@ -134,6 +138,7 @@ struct Chain {
         pos = a.pos + c * a.E;
         rec = a.rec + c * a.E * a.S;
         S = a.S;
+        ols = rec_ls_slot(a.S);
         dord = a.dord ? a.dord + c * a.E : nullptr;
         dpos = a.dpos ? a.dpos + c * a.E : nullptr;
         dt = a.dt ? a.dt + c * a.E : nullptr;
@@ -143,7 +148,7 @@ struct Chain {
     }
     BQ_HDF double &at(int p) const { return rec[(size_t)p * S + BQ_REC_AT]; }  // arrival of the event at position p
     BQ_HDF double &dq(int p) const { return rec[(size_t)p * S + BQ_REC_DQ]; }  // its departure
-    BQ_HDF double &ls(int p) const { return rec[(size_t)p * S + BQ_REC_LS]; }  // log of its service time (Gamma / LogNormal)
+    BQ_HDF double &ls(int p) const { return rec[(size_t)p * S + ols]; }  // log of its service time (Gamma / LogNormal)
     // server-free times seen by position p of a FIFO queue; the next position's vector is S doubles further
     BQ_HDF double *fvec(const QInfo &, int p) const { return rec + (size_t)p * S + BQ_REC_F; }
 };
@@ -251,7 +256,7 @@ BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, Touch 
     const QInfo &q = c.qi[ev.q0];
     const QConst &qc = c.qc[ev.q0];
     const int k = q.k, p0 = ev.p0;
-    const double *f = c.fvec(q, p0);  // F[p0 + i][j] = f[i S + j]
+    const double *f = c.fvec(q, p0);  // F[p0 + i][j] = f[i S + BQ_FSLOT(j)]
     const int S = c.S;
     const double x0 = ev.x0;
     const double st = dmax(ev.a_e, f[0]);
@@ -278,8 +283,8 @@ BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, Touch 
             const double *fp = f + (size_t)(pu - p0) * S;
             bo_[u] = fp[0];
             bx_[u] = later ? ((k > 1) ? fp[1] : INFINITY) : fp[-S];
-            ai_[u] = c.at(pu);
-            di_[u] = c.dq(pu);
+            ai_[u] = fp[BQ_REC_AT - BQ_REC_F];
+            di_[u] = fp[BQ_REC_DQ - BQ_REC_F];
         }
 #pragma unroll
         for (int u = 0; u < BQ_WALK_U; ++u) {
@@ -709,7 +714,7 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         const QInfo &q = c.qi[ev.q1];
         const int k = q.k, p1 = ev.p1;
         const int ps = (j1 < p1) ? j1 : p1, pe = (j1 < p1) ? p1 : j1;
-        reslot<W>(c.rec + BQ_REC_AT, c.S, c.ord, c.pos, c.rec + BQ_REC_DQ, c.S, log1 ? c.rec + BQ_REC_LS : nullptr, c.S, p1, j1, x,
+        reslot<W>(c.rec + BQ_REC_AT, c.S, c.ord, c.pos, c.rec + BQ_REC_DQ, c.S, log1 ? c.rec + c.ols : nullptr, c.S, p1, j1, x,
                   lane, gmask);
         FreeVec<KMAX> M;
         double *fi = c.fvec(q, ps);
@@ -1366,10 +1371,10 @@ __global__ void rebuild_positions_kernel(const DynArgs A, const int *ev_pt) {
         r[BQ_REC_AT] = ai;
         if (qi.type == Q_GGK) {
             M.store(r + BQ_REC_F, qi.k);
-            if (qi.dist != D_EXP) r[BQ_REC_LS] = log_d(di - dmax(ai, M.v[0]));
+            if (qi.dist != D_EXP) r[rec_ls_slot(A.S)] = log_d(di - dmax(ai, M.v[0]));
             M.replace_min(di);
         } else if (qi.type == Q_DELAY && qi.dist != D_EXP) {
-            r[BQ_REC_LS] = log_d(di - ai);
+            r[rec_ls_slot(A.S)] = log_d(di - ai);
         }
     }
 }

@@ -262,7 +262,7 @@ struct HostRows {
     std::vector<int> ord, pos, dord, dpos;
     std::vector<double> at, dq, ls, F, dt, sq;
     std::vector<double> rec;  // at, dq, ls and F interleaved by position, as the device holds them
-    // one record per position: {at, dq, ls, F[0..k)} (bq_dynamic.cuh, BQ_REC_*)
+    // one record per position: {at, dq, F[0], F[1], ls, F[2..k)} (bq_dynamic.cuh, BQ_REC_*)
     void pack(const bq_handle *h, size_t rows);
     void alloc(size_t rows, size_t E, size_t EF, bool ps) {
         ord.assign(rows * E, 0); pos.assign(rows * E, 0);
@@ -289,8 +289,8 @@ void HostRows::pack(const bq_handle *h, size_t rows) {
             const int lo = h->q_off[q], hi = h->q_off[q + 1], k = (h->q_type[q] == Q_GGK) ? h->q_k[q] : 0;
             for (int p = lo; p < hi; ++p) {
                 double *r = &rec[(i * E + p) * S];
-                r[BQ_REC_AT] = at[i * E + p]; r[BQ_REC_DQ] = dq[i * E + p]; r[BQ_REC_LS] = ls[i * E + p];
-                for (int j = 0; j < k; ++j) r[BQ_REC_F + j] = F[i * EF + h->q_foff[q] + (size_t)(p - lo) * k + j];
+                r[BQ_REC_AT] = at[i * E + p]; r[BQ_REC_DQ] = dq[i * E + p]; r[rec_ls_slot((int)S)] = ls[i * E + p];
+                for (int j = 0; j < k; ++j) r[BQ_REC_F + BQ_FSLOT(j)] = F[i * EF + h->q_foff[q] + (size_t)(p - lo) * k + j];
             }
         }
 }

@@ -76,9 +76,9 @@ WORKLOADS = {
     "config2": dict(yaml=QNET3, init="DFN2", tasks=5000, chains=1024, sweeps=20, ref_tasks=5000, bytes=16.0,
                     kernel="sweep_static_kernel<true>", name="3-tier web-service network (qnet3)"),
     "config3": dict(yaml=TANDEM3, init="DFN2", tasks=20000, chains=4096, sweeps=2, ref_tasks=1000, bytes=32.0,
-                    kernel="sweep_batch_kernel<4>", name="tandem source -> G/G/3 -> G/G/3, LogNormal service"),
+                    kernel="sweep_batch_kernel<4, 8, false>", name="tandem source -> G/G/3 -> G/G/3, LogNormal service"),
     "config4": dict(yaml=PSDELAY, init="PS", tasks=50000, chains=2048, sweeps=2, ref_tasks=2000, bytes=80.0 / 3.0,
-                    kernel="sweep_batch_kernel<4>", name="source -> processor sharing -> delay station (one GPU's share "
+                    kernel="sweep_batch_kernel<4, 4, false>", name="source -> processor sharing -> delay station (one GPU's share "
                                                          "of the 16384 chains)"),
 }
 BYTES_PER_RESAMPLE = 16.0  # source / GGk k=1 / DELAY visits
@@ -380,7 +380,7 @@ def main():
                          "traffic_note": ("bytes per launch from profiles/r1_static_final_ncu_full.txt; far BELOW the "
                                           "algorithmic 16 B x resamples because the chain state stays in shared memory "
                                           "for all sweeps of a launch") if args.workload == "config2" else
-                                         "see profiles/r1_batch_tandem_ncu_full.txt (61 GB per launch of 39 M resamples)",
+                                         "see profiles/r1_batch_tandem_4096_ncu_full.txt (259 GB per launch of 98 M resamples on the 2000-task tandem)",
                          "peak_kind": peak_kind,
                          "kernel": wl["kernel"], "bytes_per_resample": wl["bytes"],
                          "resamples_per_launch": resamples_per_step, "launch_ms_mean": mean_ms, "launch_ms_max": worst_ms},

@@ -40,18 +40,18 @@ struct Emul {
         for (int q = 0; q < Q; ++q)
             for (int p = q_off[q]; p < q_off[q + 1]; ++p) {
                 double *r = &recs[(size_t)p * S];
-                r[BQ_REC_AT] = at[p]; r[BQ_REC_DQ] = dq[p]; r[BQ_REC_LS] = ls[p];
+                r[BQ_REC_AT] = at[p]; r[BQ_REC_DQ] = dq[p]; r[rec_ls_slot(S)] = ls[p];
                 if (q_type[q] == Q_GGK)
-                    for (int j = 0; j < q_k[q]; ++j) r[BQ_REC_F + j] = F[q_foff[q] + (size_t)(p - q_off[q]) * q_k[q] + j];
+                    for (int j = 0; j < q_k[q]; ++j) r[BQ_REC_F + BQ_FSLOT(j)] = F[q_foff[q] + (size_t)(p - q_off[q]) * q_k[q] + j];
             }
     }
     void unpack() {
         for (int q = 0; q < Q; ++q)
             for (int p = q_off[q]; p < q_off[q + 1]; ++p) {
                 const double *r = &recs[(size_t)p * S];
-                at[p] = r[BQ_REC_AT]; dq[p] = r[BQ_REC_DQ]; ls[p] = r[BQ_REC_LS];
+                at[p] = r[BQ_REC_AT]; dq[p] = r[BQ_REC_DQ]; ls[p] = r[rec_ls_slot(S)];
                 if (q_type[q] == Q_GGK)
-                    for (int j = 0; j < q_k[q]; ++j) F[q_foff[q] + (size_t)(p - q_off[q]) * q_k[q] + j] = r[BQ_REC_F + j];
+                    for (int j = 0; j < q_k[q]; ++j) F[q_foff[q] + (size_t)(p - q_off[q]) * q_k[q] + j] = r[BQ_REC_F + BQ_FSLOT(j)];
             }
     }
     void bind() {
