@@ -225,6 +225,62 @@ def test_full_size_invariants_config2():
         assert len(set(d_all[:, order[0]].tolist())) == 8
 
 
+@pytest.mark.parametrize("workload", ["config3", "config4"])
+def test_full_size_invariants_dynamic(workload):
+    """BASELINE.json configs[2] and [3] at their full event counts (fewer chains): after sweeps of the batch kernel
+    the state the device maintained incrementally -- queue order, free-time vectors, cached log services, sorted PS
+    times -- must agree with a from-scratch host recomputation: observed times untouched, services >= 0, arrivals
+    chained to departures, queues in arrival order, counters consistent, log_prob equal to the sum of the service
+    log-densities recomputed on the host."""
+    import bench
+    from bayes_qnet_b200 import qnet
+    wl = bench.WORKLOADS[workload]
+    tasks = 20000
+    net, ini = bench.make_input(tasks, yaml_text=wl["yaml"], init=wl["init"])
+    soa = ini.soa()
+    C = 64
+    with GibbsEngine(net, ini, n_chains=C, seed=77) as eng:
+        order = eng.sequential_order()
+        assert eng.kernel_info()["threads"] > 0
+        eng.sweep(3, "SLICE", "BAYES")
+        st = eng.stats()
+        assert st["nevents"] == C * 3 * len(order)
+        assert st["n_redone"] < 0.05 * st["nevents"] and st["n_stuck"] < 1e-3 * st["nevents"]
+        lp = eng.log_prob()
+        th = eng.params()
+        assert numpy.all(numpy.isfinite(lp)) and numpy.all(numpy.isfinite(th))  # a LogNormal mean-log may be < 0
+        full = eng.state(0, 4, full=True)
+        d, a, s, nq = full["d"], full["a"], full["s"], full["next_byq"]
+        obs = soa["obs_d"] == 1
+        assert numpy.array_equal(d[:, obs], numpy.broadcast_to(soa["d"][obs], (4, obs.sum())))
+        assert numpy.all(s >= 0)
+        has = soa["prev_byt"] >= 0
+        assert numpy.array_equal(a[:, has], d[:, soa["prev_byt"][has]])
+        qtype = numpy.array([q.code for q in net.queues])[soa["qid"]]
+        qdist = numpy.array([q.service.code for q in net.queues])
+        npar = numpy.where(qdist == 0, 1, 2)
+        poff = numpy.concatenate(([0], numpy.cumsum(npar)[:-1]))
+        for c in range(4):
+            hasn = (nq[c] >= 0) & (qtype == 0)  # FIFO queues stay in arrival order
+            assert numpy.all(a[c, nq[c, hasn]] >= a[c, hasn])
+            host_lp = 0.0
+            for q in range(len(qdist)):
+                sel = soa["qid"] == q
+                sq = s[c, sel]
+                p0 = th[c, poff[q]]
+                if qdist[q] == 0:
+                    host_lp += float(numpy.sum(-numpy.log(p0) - sq / p0))
+                else:  # LogNormal(mu, sd)   (distributions.pyx:266-270)
+                    assert qdist[q] == 2
+                    sd = th[c, poff[q] + 1]
+                    ls = numpy.log(sq)
+                    host_lp += float(numpy.sum(-0.5 * numpy.log(2 * numpy.pi) - numpy.log(sd) - ls
+                                               - (ls - p0) ** 2 / (2 * sd * sd)))
+            assert abs(host_lp - lp[c]) < 1e-9 * abs(host_lp), (host_lp, lp[c])
+        assert len(set(eng.state(0, 8)[:, order[0]].tolist())) == 8
+    qnet.set_initialization_type("DFN2")
+
+
 @pytest.mark.parametrize("name", ["mm1", "qnet3", "lng1", "mm3", "psdelay"])
 def test_posterior_agrees_with_long_reference_runs(name):
     """estimation.bayes from the same initial state: posterior means of the service parameters and of the
