@@ -15,7 +15,7 @@ BQ_OK = 0
 BQ_ERR_INVALID, BQ_ERR_CUDA, BQ_ERR_UNSUPPORTED, BQ_ERR_NO_DEVICE, BQ_ERR_STATE = -1, -2, -3, -4, -5
 BQ_MODE_SLICE, BQ_MODE_MH = 0, 1
 BQ_UPD_NONE, BQ_UPD_BAYES, BQ_UPD_STEM = 0, 1, 2
-BQ_FLAG_TMAX_PER_SWEEP, BQ_FLAG_NO_FINAL, BQ_FLAG_TRACE, BQ_FLAG_TIGHT = 1, 2, 4, 8
+BQ_FLAG_TMAX_PER_SWEEP, BQ_FLAG_NO_FINAL, BQ_FLAG_TRACE, BQ_FLAG_TIGHT, BQ_FLAG_REVERSE = 1, 2, 4, 8, 16
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_u8p = ctypes.POINTER(ctypes.c_uint8)

@@ -1071,10 +1071,11 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
         }
         const int n_order = (A.flags & FLAG_PARAMS_ONLY) ? 0 : A.n_order;
         int4 rec_next = make_int4(0, -1, 0, 0);
-        if (n_order > 0) rec_next = __ldg(&order4[0]);
+        const bool rev = (A.flags & FLAG_REVERSE) != 0;  // slice_resample(reverse=True): the scan order backwards
+        if (n_order > 0) rec_next = __ldg(&order4[rev ? n_order - 1 : 0]);
         for (int idx = 0; idx < n_order; ++idx) {
             const int4 r4 = rec_next;
-            if (idx + 1 < n_order) rec_next = __ldg(&order4[idx + 1]);  // the next record is in flight during this event
+            if (idx + 1 < n_order) rec_next = __ldg(&order4[rev ? n_order - 2 - idx : idx + 1]);  // in flight during this event
             const DynRec rec = {r4.x, r4.y, r4.z, r4.w};
             EventCtx ev;
             event_load(c, rec, ev);
@@ -1214,7 +1215,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_batch_kernel(const DynArgs A,
             up.changed = 0; up.counted = 0; up.rejected = 0; up.stuck = 0; up.evals = 0;
             up.R.reset(); up.Wt.reset();
             if (active) {
-                const int4 r4 = __ldg(&order4[idx]);
+                const int4 r4 = __ldg(&order4[(A.flags & FLAG_REVERSE) ? n_order - 1 - idx : idx]);
                 const DynRec rec = {r4.x, r4.y, r4.z, r4.w};
                 event_load(c, rec, ev);
                 lane_update<KMAX, MHK, !MHK>(c, ev, LP, up);

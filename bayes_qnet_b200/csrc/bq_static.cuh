@@ -26,7 +26,7 @@ namespace bq {
 
 enum { UPD_NONE = 0, UPD_BAYES = 1, UPD_STEM = 2 };
 enum { MODE_SLICE = 0, MODE_MH = 1 };
-enum { FLAG_TMAX_PER_SWEEP = 1, FLAG_NO_FINAL = 2, FLAG_TRACE = 4, FLAG_TIGHT = 8, FLAG_PARAMS_ONLY = 1 << 16 };
+enum { FLAG_TMAX_PER_SWEEP = 1, FLAG_NO_FINAL = 2, FLAG_TRACE = 4, FLAG_TIGHT = 8, FLAG_REVERSE = 16, FLAG_PARAMS_ONLY = 1 << 16 };
 
 // Static neighbourhood of one resample-eligible event e (12 x int32 = 3 x int4, stored in schedule
 // order so a colour class is one contiguous, coalesced read).  -1 = absent.
@@ -553,11 +553,16 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
             tmax = 2.0 * block_reduce_max(m, scratch);
         }
         const int n_colors = (A.flags & FLAG_PARAMS_ONLY) ? 0 : A.n_colors;
-        if (threadIdx.x == 0) work_ctr[0] = A.color_off[0];
+        // reverse scan (slice_resample(reverse=True), qnet.pyx:683-684): the classes in reverse order; the events of a
+        // class are conditionally independent, so the order inside a class is immaterial
+        const bool rev = (A.flags & FLAG_REVERSE) != 0;
+        if (threadIdx.x == 0 && n_colors > 0) work_ctr[0] = A.color_off[rev ? n_colors - 1 : 0];
         __syncthreads();
         for (int c = 0; c < n_colors; ++c) {
-            const int hi = A.color_off[c + 1];
-            if (threadIdx.x == 0) work_ctr[(c + 1) & 1] = hi;  // next class starts where this one ends
+            const int cc = rev ? n_colors - 1 - c : c;
+            const int hi = A.color_off[cc + 1];
+            if (threadIdx.x == 0 && c + 1 < n_colors)  // where the next class starts
+                work_ctr[(c + 1) & 1] = A.color_off[rev ? cc - 1 : cc + 1];
             if (A.mode == MODE_MH)
                 run_class_mh(A, d, q_type, qc, hi, &work_ctr[c & 1], gchain, gsw, n_ev, n_evals, n_reject);
             else if (ALL_EXP)

@@ -78,8 +78,9 @@ class GibbsEngine(object):
 
     # ---- sampling -----------------------------------------------------------------------------------
     def sweep(self, n_sweeps=1, mode="SLICE", update="NONE", trace=False, tmax_per_sweep=True, tight=False,
-              sample_final=True, sync=True):
-        """n_sweeps Gibbs sweeps of every chain, each followed by the parameter update."""
+              sample_final=True, sync=True, reverse=False):
+        """n_sweeps Gibbs sweeps of every chain, each followed by the parameter update.  reverse: visit the events in
+        the reverse of the scan order (slice_resample(reverse=True), qnet.pyx:683-684)."""
         flags = 0
         if tmax_per_sweep:
             flags |= capi.BQ_FLAG_TMAX_PER_SWEEP
@@ -89,6 +90,8 @@ class GibbsEngine(object):
             flags |= capi.BQ_FLAG_TIGHT
         if not sample_final:
             flags |= capi.BQ_FLAG_NO_FINAL
+        if reverse:
+            flags |= capi.BQ_FLAG_REVERSE
         capi.check(self._L.bq_sweep(self._h, int(n_sweeps), _MODE[mode], _UPD[update], flags))
         if sync:
             self.synchronize()

@@ -58,16 +58,17 @@ def last_run():
     return _last
 
 
-def _run(net, arrv, num_iter, update, n_chains, seed, device, report_fn, return_arrv, gibbs_iter=1):
+def _run(net, arrv, num_iter, update, n_chains, seed, device, report_fn, return_arrv, gibbs_iter=1, reverse=False):
     global _last
+    reverse = bool(reverse) and _mode() == "SLICE"  # the reference only reverses slice sweeps (estimation.py:135)
     eng = GibbsEngine(net, arrv, n_chains=n_chains, seed=seed, device=device)
     t0 = time.time()
     all_sampled = []
     if report_fn or return_arrv or gibbs_iter != 1:
         for i in range(num_iter):
             if gibbs_iter > 1:
-                eng.sweep(gibbs_iter - 1, _mode(), "NONE", tmax_per_sweep=False)
-            eng.sweep(1, _mode(), update, trace=True)
+                eng.sweep(gibbs_iter - 1, _mode(), "NONE", tmax_per_sweep=False, reverse=reverse)
+            eng.sweep(1, _mode(), update, trace=True, reverse=reverse)
             if report_fn or return_arrv:
                 snap = eng.to_arrivals(0)
                 if report_fn:
@@ -75,7 +76,7 @@ def _run(net, arrv, num_iter, update, n_chains, seed, device, report_fn, return_
                 if return_arrv:
                     all_sampled.append(snap)
     else:
-        eng.sweep(num_iter, _mode(), update, trace=True)
+        eng.sweep(num_iter, _mode(), update, trace=True, reverse=reverse)
     theta, mw, lp = eng.traces()
     secs = time.time() - t0
     eng.write_back(arrv, 0)
@@ -92,13 +93,11 @@ def _run(net, arrv, num_iter, update, n_chains, seed, device, report_fn, return_
 def bayes(net, arrv, num_iter, report_fn=None, return_arrv=False, reverse=False, sweeten=0, tag="MU",
           n_chains=1, seed=None, device=0):
     """Gibbs sampling of hidden times and service parameters (estimation.py:104-169)."""
-    if reverse:
-        raise NotImplementedError("reverse scan: the kernels use their own conflict-free scan order")
     _qnet.reset_stats()
     if sweeten:
-        net.slice_resample(arrv, sweeten)
+        net.slice_resample(arrv, sweeten, reverse=reverse)
     net.estimate(arrv)  # initialise the parameters from the Gibbs initialisation (estimation.py:124)
-    return _run(net, arrv, num_iter, "BAYES", n_chains, seed, device, report_fn, return_arrv)
+    return _run(net, arrv, num_iter, "BAYES", n_chains, seed, device, report_fn, return_arrv, reverse=reverse)
 
 
 def sem(net, arrv, burn, num_iter, gibbs_iter=1, momentum=0, return_arrv=False, report_fn=None,

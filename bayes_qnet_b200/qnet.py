@@ -192,9 +192,8 @@ class Qnet(object):
         return eng
 
     def slice_resample(self, arrv, num_iter, report_fn=None, return_arrv=False, reverse=False, return_lp=False):
-        """num_iter exact-conditional slice sweeps over the hidden times of arrv, in place (qnet.pyx:659)."""
-        if reverse:
-            raise NotImplementedError("reverse scan: the kernels use their own conflict-free scan order")
+        """num_iter exact-conditional slice sweeps over the hidden times of arrv, in place (qnet.pyx:659).
+        reverse: the kernel's scan order backwards (qnet.pyx:683-684)."""
         eng = self._engine_for(arrv)
         before = eng.stats()
         all_arrv = []
@@ -202,7 +201,7 @@ class Qnet(object):
         if report_fn or return_arrv:
             for gi in range(num_iter):
                 # Tmax is fixed for the whole call (qnet.pyx:672): only the first launch recomputes it
-                eng.sweep(1, "SLICE", "NONE", tmax_per_sweep=(gi == 0))
+                eng.sweep(1, "SLICE", "NONE", tmax_per_sweep=(gi == 0), reverse=reverse)
                 eng.write_back(arrv)
                 lik = float(eng.log_prob()[0])
                 if report_fn:
@@ -210,7 +209,7 @@ class Qnet(object):
                 if return_arrv:
                     all_arrv.append(arrv.duplicate())
         else:
-            eng.sweep(num_iter, "SLICE", "NONE", tmax_per_sweep=False)
+            eng.sweep(num_iter, "SLICE", "NONE", tmax_per_sweep=False, reverse=reverse)
             eng.write_back(arrv)
         _absorb(before, eng.stats())
         if not return_arrv:

@@ -48,9 +48,11 @@ enum {
                                    (qnet.pyx:672) */
     BQ_FLAG_NO_FINAL = 2,       /* MH only: sample_final=False (qnet.pyx:337)                              */
     BQ_FLAG_TRACE = 4,          /* record per-sweep theta / mean wait / log-prob traces                    */
-    BQ_FLAG_TIGHT = 8           /* start the slice bracket at the support of the conditional instead of
+    BQ_FLAG_TIGHT = 8,          /* start the slice bracket at the support of the conditional instead of
                                    [a_e, min(d_next, Tmax)] (qnet.pyx:698-701): same stationary law, fewer
                                    rejected candidates; off by default (reference-faithful bracket)        */
+    BQ_FLAG_REVERSE = 16        /* visit the events in the reverse of the scan order: slice_resample(reverse=True)
+                                   (qnet.pyx:683-684), the backward kernel of estimation.chib_evidence        */
 };
 
 /* Flattened network: replaces the Queue vtable (queues.pxd:19-37), FactorTemplate (queues.pxd:12-17)

@@ -66,6 +66,32 @@ def test_sweep_trajectory_matches_oracle(name):
         assert not numpy.array_equal(d[0], d[1])  # chains differ only by their RNG counters
 
 
+@pytest.mark.parametrize("batch", ["1", "0"])
+@pytest.mark.parametrize("name", ["qnet3", "lng1", "mm3", "psdelay"])
+def test_reverse_scan_matches_oracle(name, batch, monkeypatch):
+    """slice_resample(reverse=True) (qnet.pyx:683-684): the scan order backwards, alternating with forward sweeps as
+    estimation.chib_evidence does; chromatic, batch and group kernels against the oracle run over the reversed list."""
+    monkeypatch.setenv("BQ_DYN_BATCH", batch)
+    g = helpers.golden("cond_" + name)
+    net, arrv = helpers.golden_state(g, "s0")
+    with GibbsEngine(net, arrv, n_chains=2, seed=99) as eng:
+        off, order = eng.schedule()
+        for s in range(4):
+            eng.sweep(1, "SLICE", "NONE", reverse=(s % 2 == 0))
+        d = eng.state()
+        for c in range(2):
+            oc = helpers.oracle_chain(net, arrv)
+            for s in range(4):
+                oc.slice_sweep(order[::-1] if s % 2 == 0 else order, eng.seed, c, s)
+            assert helpers.relerr(d[c], oc.d).max() < TOL
+        fwd = GibbsEngine(net, arrv, n_chains=2, seed=99)
+        fwd.sweep(1, "SLICE", "NONE")
+        assert not numpy.array_equal(fwd.state(), d)
+        fwd.close()
+    mus, arrvl = estimation.bayes(net, arrv.duplicate(), 3, reverse=True)
+    assert len(mus) == 3 and numpy.all(numpy.isfinite(mus))
+
+
 def test_bayes_and_stem_updates_match_oracle():
     """Fused sufficient statistics + parameter update after every sweep (qnet.pyx:882 / :844)."""
     for name, upd in (("qnet3", "BAYES"), ("lng1", "BAYES"), ("lng1", "STEM"), ("delay", "STEM")):
