@@ -54,6 +54,7 @@ SYMBOLS = {
     "bq_create": (ctypes.c_int, [ctypes.POINTER(BqModel), ctypes.POINTER(BqArrivals), c_f64p, ctypes.c_int32,
                                  ctypes.c_int64, ctypes.c_uint64, ctypes.c_int32, ctypes.POINTER(_H)]),
     "bq_destroy": (ctypes.c_int, [_H]),
+    "bq_gibbs_kernel": (ctypes.c_int, [_H, c_f64p, ctypes.c_int32, ctypes.c_int32, c_f64p]),
     "bq_set_params": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p]),
     "bq_get_params": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p]),
     "bq_set_state": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p]),

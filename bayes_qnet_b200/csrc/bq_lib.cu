@@ -18,6 +18,7 @@
 #include "../../include/bq_capi.h"
 #include "bq_static.cuh"
 #include "bq_dynamic.cuh"
+#include "bq_chib.cuh"
 #include "bq_host.h"
 
 using namespace bq;
@@ -982,6 +983,39 @@ extern "C" int bq_log_prob(bq_handle *h, double *out) {
 extern "C" int bq_suffstats(bq_handle *h, double *out) {
     if (!h || !out) return fail(BQ_ERR_INVALID, "null argument");
     return run_report(h, nullptr, out);
+}
+
+// Qnet.gibbs_kernel (qnet.pyx:741-809) for every chain: log T(d_to <- state of the chain) of one slice sweep
+extern "C" int bq_gibbs_kernel(bq_handle *h, const double *d_to, int32_t n_to, int32_t strict, double *out) {
+    if (!h || !d_to || !out) return fail(BQ_ERR_INVALID, "null argument");
+    if (n_to != 1 && n_to != h->C) return fail(BQ_ERR_INVALID, "n_to must be 1 or the number of chains");
+    if (!h->static_order)
+        return fail(BQ_ERR_UNSUPPORTED, "gibbs_kernel: networks with multi-server or PS queues are not supported");
+    CK(cudaSetDevice(h->device));
+    const size_t E = h->E, C = h->C, n_sched = h->order.size();
+    double *work = nullptr, *to = nullptr, *res = nullptr;
+    unsigned char *done = nullptr;
+    int rc = BQ_OK;
+    auto cleanup = [&]() { cudaFree(work); cudaFree(to); cudaFree(res); cudaFree(done); };
+#define CKG(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(BQ_ERR_CUDA, cudaGetErrorString(e_)); } } while (0)
+    CKG(cudaMalloc((void **)&work, C * E * sizeof(double)));
+    CKG(cudaMalloc((void **)&to, (size_t)n_to * E * sizeof(double)));
+    CKG(cudaMalloc((void **)&res, C * sizeof(double)));
+    CKG(cudaMalloc((void **)&done, std::max<size_t>(C * n_sched, 1)));
+    CKG(cudaMemcpyAsync(work, h->d_state, C * E * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CKG(cudaMemcpyAsync(to, d_to, (size_t)n_to * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CKG(cudaMemsetAsync(done, 0, std::max<size_t>(C * n_sched, 1), h->stream));
+    SweepArgs A;
+    fill_args(h, A);
+    const size_t sm = (34 * 8 + 8 + ((h->P + 1) & ~1)) * sizeof(double) + h->Q * (sizeof(QConst) + sizeof(int)) + 16;
+    gibbs_kernel_static<<<(unsigned)C, 256, sm, h->stream>>>(A, work, done, to, n_to, strict ? 1 : 0, res);
+    CKG(cudaGetLastError());
+    CKG(cudaMemcpyAsync(out, res, C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CKG(cudaStreamSynchronize(h->stream));
+#undef CKG
+    cleanup();
+    h->n_launches += 1;
+    return rc;
 }
 
 extern "C" int bq_stats(bq_handle *h, bq_stats_t *out) {

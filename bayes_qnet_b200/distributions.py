@@ -27,6 +27,11 @@ class Distribution(object):
     def numParameters(self):
         return len(self.parameters)
 
+    def parameter_kernel(self, theta_from, theta_to, data):
+        """Log-density of the posterior draw theta_to given the services `data`: the transition kernel of
+        sample_parameters (used by Qnet.parameter_kernel / estimation.chib_evidence)."""
+        raise NotImplementedError()
+
     def _rng(self):
         return numpy.random
 
@@ -63,6 +68,13 @@ class Exponential(Distribution):
 
     def as_yaml(self):
         return "[M, %s]" % self.scale
+
+    def parameter_kernel(self, theta_from, theta_to, data):
+        """distributions.pyx:98-104: the new scale ~ InverseGamma(N, sum of the services)."""
+        from math import lgamma
+        mu, N = float(numpy.sum(data)), len(data)
+        x = theta_to[0]
+        return -(N + 1) * math.log(x) - mu / x - lgamma(N) + N * math.log(mu)  # InverseGamma.lpdf, distributions.pyx:224
 
 
 class Gamma(Distribution):
@@ -102,6 +114,18 @@ class Gamma(Distribution):
     def as_yaml(self):
         return "[G, %s, %s]" % (self.shape, self.scale)
 
+    def parameter_kernel(self, theta_from, theta_to, data):
+        """netutils.gamma_transition_kernel (netutils.py:44-60): the two conditionals of the slice-within-Gibbs draw."""
+        from math import lgamma
+        shape0, scale0 = theta_from
+        shape1, scale1 = theta_to
+        data = numpy.asarray(data, dtype=numpy.float64)
+        S, Slog, N = float(data.sum()), float(numpy.log(data).sum()), len(data)
+        logP, q, r, s = 1.0 + Slog, 1.0 + S, 1.0 + N, 1.0 + N
+        p_shape = (shape1 - 1) * logP - q / scale0 - r * lgamma(shape1) - (shape1 * s) * math.log(scale0)
+        p_scale = (shape1 - 1) * logP - q / scale1 - r * lgamma(shape1) - (shape1 * s) * math.log(scale1)
+        return p_shape + p_scale
+
 
 class LogNormal(Distribution):
     """distributions.pyx:245-345.  parameters = [meanlog, sdlog]."""
@@ -140,3 +164,21 @@ class LogNormal(Distribution):
 
     def as_yaml(self):
         return "[LN, %s, %s]" % (self.meanlog, self.sdlog)
+
+    def parameter_kernel(self, theta_from, theta_to, data):
+        """distributions.pyx:323-338: tau ~ Gamma((n+1)/2, 2/(n sd^2)), mu ~ N(mean, sd_new) of the logs."""
+        from math import lgamma
+        logs = numpy.log(numpy.asarray([x for x in data if x >= 1e-50], dtype=numpy.float64))
+        ns = len(data)
+        if ns == 0 or len(logs) == 0:
+            return 0.0
+        mean = float(logs.mean())
+        sd = max(float(numpy.sqrt(numpy.mean((logs - mean) ** 2))), 1e-10)  # distributions.pyx:276-299
+        if sd <= 1e-5:
+            return 0.0
+        alpha, beta = (ns + 1) / 2.0, 2.0 / (ns * sd * sd)
+        mu_new, sd_new = theta_to
+        tau = 1.0 / (sd_new * sd_new)
+        lpdf_tau = (alpha - 1) * math.log(tau) - tau / beta - lgamma(alpha) - alpha * math.log(beta)
+        lpdf_mu = -0.5 * math.log(2 * math.pi) - math.log(sd_new) - (mu_new - mean) ** 2 / (2 * sd_new * sd_new)
+        return lpdf_mu + lpdf_tau

@@ -227,6 +227,19 @@ class GibbsEngine(object):
                                           capi.ptr(out, capi.c_f64p)))
         return out
 
+    def gibbs_kernel(self, d_to, strict=False):
+        """log T(d_to <- chain) of one slice sweep in the scan order, per chain (Qnet.gibbs_kernel, qnet.pyx:741).
+        d_to: [E] (one target for every chain) or [n_chains, E].  strict: -inf instead of the reference's retry passes
+        when an event's target is outside its support at its turn."""
+        d_to = numpy.ascontiguousarray(d_to, dtype=numpy.float64)
+        n_to = 1 if d_to.ndim == 1 else d_to.shape[0]
+        if d_to.size != n_to * self.E:
+            raise ValueError("d_to must have n_events entries per target")
+        out = numpy.empty(self.n_chains, dtype=numpy.float64)
+        capi.check(self._L.bq_gibbs_kernel(self._h, capi.ptr(d_to, capi.c_f64p), n_to, 1 if strict else 0,
+                                            capi.ptr(out, capi.c_f64p)))
+        return out
+
     def log_prob(self):
         out = numpy.empty(self.n_chains, dtype=numpy.float64)
         capi.check(self._L.bq_log_prob(self._h, capi.ptr(out, capi.c_f64p)))

@@ -100,6 +100,63 @@ def bayes(net, arrv, num_iter, report_fn=None, return_arrv=False, reverse=False,
     return _run(net, arrv, num_iter, "BAYES", n_chains, seed, device, report_fn, return_arrv, reverse=reverse)
 
 
+def _logsumexp(v):
+    v = numpy.asarray(v, dtype=numpy.float64)
+    m = numpy.max(v)
+    if not numpy.isfinite(m):
+        return float(m)
+    return float(m + numpy.log(numpy.sum(numpy.exp(v - m))))
+
+
+def chib_evidence(net, obs, M_special=100, M=100, debug=False, seed=None, device=0, strict=True):
+    """Chib's estimate of the log evidence log p(observed) with the Murray-Salakhutdinov correction
+    (estimation.py:274-330): p(v) = p(v, h*, theta*) / p(h*, theta* | v), the denominator averaged over a forward and
+    a backward (reverse-scan) chain started at the special state of the transition densities
+    Qnet.gibbs_kernel + Qnet.parameter_kernel into it.  Slice sampler only; single-server FIFO / delay networks.
+    strict (default): an event whose target lies outside its support when its turn comes makes the transition
+    impossible (density 0) -- the reference instead retries such events after the others (qnet.pyx:756-805), which
+    is not the density of the sweep and biases the estimate (tests/test_gpu_chib.py); strict=False reproduces it."""
+    if _mode() != "SLICE":
+        raise NotImplementedError("chib_evidence with the MH sampler")
+    net.estimate(obs)
+    rs = numpy.random.RandomState(seed)
+    with GibbsEngine(net, obs, n_chains=1, seed=seed, device=device) as eng:
+        # 1. the special state: the most probable one of a first run (Reporter, estimation.py:343-366)
+        best = (-numpy.inf, None, None)
+        for i in range(M_special):
+            eng.sweep(1, "SLICE", "NONE")
+            lp = float(eng.log_prob()[0])
+            if i > M_special // 2 and lp > best[0]:
+                best = (lp, eng.state(0, 1)[0].copy(), eng.params(0, 1)[0].copy())
+            _qnet.capi_update_only(eng, "BAYES")
+        if best[1] is None:
+            best = (float(eng.log_prob()[0]), eng.state(0, 1)[0].copy(), eng.params(0, 1)[0].copy())
+        _, d_star, theta_star = best
+        arrv_star = obs.duplicate()
+        eng.set_state(d_star)
+        eng.set_params(theta_star)
+        eng.write_back(arrv_star, 0)
+        p_v_hstar = float(eng.log_prob()[0])  # log p(v, h* | theta*), improper prior on theta as in the reference
+        # 2./3. forward chain of M - u steps, backward chain of u steps, both from the special state
+        u = int(rs.randint(M))
+        cnd = []
+        for n_steps, reverse in ((M - u, False), (u, True)):
+            eng.set_state(d_star)
+            eng.set_params(theta_star)
+            for _ in range(n_steps):
+                eng.sweep(1, "SLICE", "NONE", reverse=reverse)
+                theta = list(eng.params(0, 1)[0])
+                snap = eng.to_arrivals(0)
+                val = float(eng.gibbs_kernel(d_star, strict=strict)[0]) + net.parameter_kernel(theta, list(theta_star), snap)
+                cnd.append(val)
+                _qnet.capi_update_only(eng, "BAYES")
+        net.parameters = list(theta_star)
+    p_hstar_given_v = _logsumexp(cnd) - numpy.log(M)
+    if debug:
+        print("CHIB log(p (v, h*)) = %.5f\nCHIB log(p (h*|v)) = %.5f" % (p_v_hstar, p_hstar_given_v))
+    return p_v_hstar - p_hstar_given_v
+
+
 def sem(net, arrv, burn, num_iter, gibbs_iter=1, momentum=0, return_arrv=False, report_fn=None,
         burn_report_fn=None, debug=False, n_chains=1, seed=None, device=0):
     """Stochastic EM (estimation.py:29-100)."""

@@ -261,6 +261,26 @@ class Qnet(object):
         """Sum over events of the service log-density (qnet.pyx:1032)."""
         return float(self._engine_for(arrv).log_prob()[0])
 
+    def gibbs_kernel(self, arrv_from, arrv_to, lik=None, strict=False):
+        """log T(arrv_to <- arrv_from) of one slice sweep in the kernel's scan order (qnet.pyx:741-809): minus the sum
+        over the resampled events of the log normaliser of their conditional, each event moved to its target before
+        the next.  -inf when the target cannot be reached.  Like the reference, events whose target is not reachable at
+        their turn are retried after the others; strict=True returns -inf instead (the density of the sweep itself).
+        Single-server FIFO / delay-station networks."""
+        return float(self._engine_for(arrv_from).gibbs_kernel(arrv_to.soa()["d"], strict=strict)[0])
+
+    def parameter_kernel(self, theta_from, theta_to, arrvl):
+        """Log-density of the transition sample_parameters makes from theta_from to theta_to given arrvl (qnet.pyx:811-837)."""
+        if isinstance(arrvl, _arrivals.Arrivals):
+            arrvl = [arrvl]
+        ret, off = 0.0, 0
+        for q in self.queues:
+            s_obs = [e.s for a in arrvl for e in a.events_of_queue(q) if e.s > 0]  # queues.pyx:1320-1322
+            n = q.service.numParameters()
+            ret += q.service.f.parameter_kernel(list(theta_from[off:off + n]), list(theta_to[off:off + n]), s_obs)
+            off += n
+        return ret
+
 
 def capi_update_only(eng, update):
     """Run just the parameter update (no hidden-time sweep) on an engine."""

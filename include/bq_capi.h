@@ -141,6 +141,15 @@ int bq_logcond(bq_handle *h, int32_t chain, int32_t eid, const double *x, int32_
 /* Parity hook for the MH path: the TWOS proposal log-density departureLik(e) + arrivalLik(e') at n points
  * (queues.pair_proposal / departure_proposal, queues.pyx:1239-1283; -inf outside its support). */
 int bq_mh_proposal(bq_handle *h, int32_t chain, int32_t eid, const double *x, int32_t n, double *out);
+/* Qnet.gibbs_kernel (qnet.pyx:741-809), the transition density estimation.chib_evidence (estimation.py:274-330)
+ * averages: out[c] = log T(d_to <- state of chain c) of one slice sweep in the handle's scan order = minus the sum over
+ * the resampled events of log integral exp(g(x) - g(d_to[e])) dx (GGkGibbs.integrate, qnet.pyx:1361-1372), each event
+ * moved to its target before the next one is taken; events whose target is not reachable yet are retried in later
+ * passes and -inf is returned when a pass moves nothing (qnet.pyx:756-805).  strict != 0: no later passes -- an
+ * unreachable target gives -inf, the density of the fixed-scan sweep itself (what Chib's identity needs).  d_to:
+ * n_to * n_events doubles, n_to = 1 (one target for all chains) or n_chains.  The chains' states are not modified.
+ * Static-order networks only. */
+int bq_gibbs_kernel(bq_handle *h, const double *d_to, int32_t n_to, int32_t strict, double *out);
 /* Qnet.log_prob (qnet.pyx:1032): out[n_chains] */
 int bq_log_prob(bq_handle *h, double *out);
 /* Per chain per queue sufficient statistics over events with s>0 (queues.pyx:1317):

@@ -492,6 +492,111 @@ void bqo_mh_proposal(const bqo_state *st, int e, const double *x, int n, double 
 }
 
 /* ---------------------------------------------------------------------------------------------- */
+/* exact Gibbs transition density: Qnet.gibbs_kernel (qnet.pyx:741-809)                             */
+/* ---------------------------------------------------------------------------------------------- */
+typedef struct { const bqo_state *st; int e; double lf; } kern_fn;
+static double kern_eval(const kern_fn *k, double x) { return exp(bqo_logcond1(k->st, k->e, x) - k->lf); }
+
+/* adaptive Simpson with Richardson correction; the integrand may jump (edges of the support).  The first 5 levels
+ * are always split: with Gamma(2) services the integrand is piecewise polynomial with a kink next to the edge of
+ * the support where both pieces vanish, and five samples that miss the short piece fit one cubic exactly. */
+static double simpson_rec(const kern_fn *k, double a, double b, double fa, double fm, double fb, double whole,
+                          double tol, int depth) {
+    double m = 0.5 * (a + b), lm = 0.5 * (a + m), rm = 0.5 * (m + b);
+    double flm = kern_eval(k, lm), frm = kern_eval(k, rm);
+    double left = (m - a) / 6.0 * (fa + 4.0 * flm + fm), right = (b - m) / 6.0 * (fm + 4.0 * frm + fb);
+    double delta = left + right - whole;
+    if (depth <= 0 || (depth <= 43 && fabs(delta) <= 15.0 * tol) || (b - a) < 1e-14 * (fabs(a) + fabs(b) + 1e-300))
+        return left + right + delta / 15.0;
+    return simpson_rec(k, a, m, fa, flm, fm, left, 0.5 * tol, depth - 1) +
+           simpson_rec(k, m, b, fm, frm, fb, right, 0.5 * tol, depth - 1);
+}
+static double simpson(const kern_fn *k, double a, double b, double tol) {
+    /* end points nudged inside: a service of exactly zero has log-density -inf or +inf */
+    double w = b - a, a1 = a + 1e-13 * w, b1 = b - 1e-13 * w, m = 0.5 * (a1 + b1);
+    double fa = kern_eval(k, a1), fm = kern_eval(k, m), fb = kern_eval(k, b1);
+    if (!(fa == fa) || fa > 1e300) fa = 0.0;
+    if (!(fb == fb) || fb > 1e300) fb = 0.0;
+    return simpson_rec(k, a1, b1, fa, fm, fb, (b1 - a1) / 6.0 * (fa + 4.0 * fm + fb), tol, 48);
+}
+
+static int cmp_double(const void *x, const void *y) {
+    double a = *(const double *)x, b = *(const double *)y;
+    return (a > b) - (a < b);
+}
+
+/* GGkGibbs.integrate (qnet.pyx:1361-1388): the range is cut at the departures of the 3 queue neighbours of e on
+ * either side and at the arrivals of the 3 neighbours of its task successor; an infinite upper end (final events)
+ * is integrated in doubling steps until the tail no longer matters. */
+static double kern_normaliser(const bqo_state *st, int e, double lf, double lower, double upper) {
+    double pts[32], z = 0.0;
+    int n = 0, i, j, c, e1 = st->next_byt[e];
+    kern_fn k;
+    k.st = st; k.e = e; k.lf = lf;
+    pts[n++] = lower;
+    for (c = e, i = 0; i < 3 && c >= 0; ++i, c = st->prev_byq[c])
+        if (st->d[c] >= lower && st->d[c] <= upper) pts[n++] = st->d[c];
+    for (c = st->next_byq[e], i = 0; i < 3 && c >= 0; ++i, c = st->next_byq[c])
+        if (st->d[c] >= lower && st->d[c] <= upper) pts[n++] = st->d[c];
+    if (e1 >= 0) {
+        for (c = e1, i = 0; i < 3 && c >= 0; ++i, c = st->prev_byq[c])
+            if (st->a[c] >= lower && st->a[c] <= upper) pts[n++] = st->a[c];
+        for (c = st->next_byq[e1], i = 0; i < 3 && c >= 0; ++i, c = st->next_byq[c])
+            if (st->a[c] >= lower && st->a[c] <= upper) pts[n++] = st->a[c];
+    }
+    if (upper < INFINITY) pts[n++] = upper;
+    qsort(pts, (size_t)n, sizeof(double), cmp_double);
+    for (i = 0, j = 0; i < n; ++i)
+        if (j == 0 || pts[i] > pts[j - 1]) pts[j++] = pts[i];
+    n = j;
+    for (i = 0; i + 1 < n; ++i) z += simpson(&k, pts[i], pts[i + 1], 1e-13);
+    if (!(upper < INFINITY)) {
+        double t0 = pts[n - 1], w = fmax(1.0, fabs(st->d[e] - lower));
+        for (i = 0; i < 200; ++i) {
+            double part = simpson(&k, t0, t0 + w, 1e-13);
+            z += part;
+            t0 += w;
+            w *= 2.0;
+            if (i > 2 && part <= 1e-15 * z) break;
+        }
+    }
+    return z;
+}
+
+/* the normaliser of one event's conditional relative to its value at x (parity hook) */
+double bqo_kernel_normaliser(const bqo_state *st, int e, double x) {
+    int e1 = st->next_byt[e];
+    return kern_normaliser(st, e, bqo_logcond1(st, e, x), st->a[e], e1 >= 0 ? st->d[e1] : INFINITY);
+}
+
+/* log T(d_to <- st) of one sweep over `order`; st is left at d_to for the events that were moved */
+double bqo_gibbs_kernel(bqo_state *st, const int *order, int n_order, const double *d_to, int strict) {
+    int *todo = (int *)malloc((size_t)(n_order > 0 ? n_order : 1) * sizeof(int));
+    int n = 0, i, progress;
+    double prob = 0.0;
+    for (i = 0; i < n_order; ++i)
+        if (bqo_eligible(st, order[i])) todo[n++] = order[i];
+    while (n > 0) {
+        int kept = 0;
+        progress = 0;
+        for (i = 0; i < n; ++i) {
+            int e = todo[i], e1 = st->next_byt[e];
+            double lower = st->a[e], upper = e1 >= 0 ? st->d[e1] : INFINITY, x = d_to[e], lf, z;
+            lf = bqo_logcond1(st, e, x);
+            if (x <= lower || upper <= x || !(lf > -INFINITY)) { todo[kept++] = e; continue; } /* deferred */
+            z = kern_normaliser(st, e, lf, lower, upper);
+            prob -= log(z);
+            bqo_apply(st, e, x);
+            ++progress;
+        }
+        n = kept;
+        if (!progress || (strict && n > 0)) { prob = -INFINITY; break; } /* strict: the fixed-scan sweep itself */
+    }
+    free(todo);
+    return prob;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
 /* sufficient statistics and parameter updates                                                      */
 /* ---------------------------------------------------------------------------------------------- */
 /* out[q*8 + ..] = n(s>0), sum s, sum log s, sum (log s - mean)^2, #log terms, sum wait, n events, #(s==0) */

@@ -313,6 +313,32 @@ def do_mh(name):
     print("mh_%s: %d events on grids" % (name, len(rows)))
 
 
+def do_kern(name):
+    """Qnet.gibbs_kernel (qnet.pyx:741-809) and Qnet.parameter_kernel (qnet.pyx:811-837): the transition densities
+    estimation.chib_evidence averages, from a state one slice sweep away from the target."""
+    ntasks, pct, init, seed, nsweeps = COND[name]
+    net, arrv = make_state(name, ntasks, pct, init, seed)
+    qnetu.set_seed(seed + 3000)
+    with quiet():
+        star = net.slice_resample(arrv.duplicate(), 3)[-1]
+        frm = net.slice_resample(star.duplicate(), 1)[-1]
+        order_evts = frm.duplicate().all_events()
+        kp = net.gibbs_kernel(frm, star)
+        theta_from = list(net.parameters)
+        theta_to = [1.1 * t if i % 2 == 0 else 0.9 * t for i, t in enumerate(theta_from)]
+        pk = net.parameter_kernel(theta_from, theta_to, frm)
+    flat, evts = flatten(frm)
+    flat_to, _ = flatten(star)
+    row = dict((e.eid, i) for i, e in enumerate(evts))
+    out = dict(yaml=NETS[name], theta=numpy.array(net.parameters, dtype=numpy.float64), kernel=float(kp),
+               order=numpy.array([row[e.eid] for e in order_evts], dtype=numpy.int32), to_d=flat_to["d"],
+               theta_to=numpy.array(theta_to), param_kernel=float(pk))
+    for k, v in flat.items():
+        out["s0_" + k] = v
+    numpy.savez_compressed(os.path.join(OUT, "kern_%s.npz" % name), **out)
+    print("kern_%s: gibbs_kernel %.6f parameter_kernel %.6f" % (name, kp, pk))
+
+
 def do_qstats(name):
     """Every exported statistic of the reference's qstats.py (qstats.py:174-184, plus the task-level ones) on the
     cond_<name> initial state."""
@@ -421,6 +447,11 @@ if __name__ == "__main__":
     for n in ("qnet3", "mm3", "psdelay"):
         if args.only in (None, n) and not args.skip_cond:
             do_qstats(n)
+    for n in ("mm1", "qnet3", "lng1", "delay", "mm3"):  # transition densities (Chib evidence)
+        if args.only in (None, n, "kern"):
+            do_kern(n)
+    if args.only == "kern":
+        sys.exit(0)
     if not args.skip_mh:  # MH-within-Gibbs (gibbs_resample): proposal grids and long reference runs; no PS (queues.pyx:1140)
         for n in COND:
             if n != "psdelay" and args.only in (None, n):

@@ -151,6 +151,15 @@ class OracleChain(object):
         lib().bqo_mh_proposal(ctypes.byref(self._st), int(e), xs.ctypes.data_as(f64p), len(xs), out.ctypes.data_as(f64p))
         return out
 
+    def gibbs_kernel(self, order, d_to, strict=False):
+        """log T(d_to <- this state) of one slice sweep over `order` (Qnet.gibbs_kernel); moves the chain to d_to."""
+        order = numpy.ascontiguousarray(order, dtype=numpy.int32)
+        d_to = numpy.ascontiguousarray(d_to, dtype=numpy.float64)
+        f = lib().bqo_gibbs_kernel
+        f.restype = ctypes.c_double
+        return float(f(ctypes.byref(self._st), order.ctypes.data_as(i32p), len(order), d_to.ctypes.data_as(f64p),
+                       1 if strict else 0))
+
     def suffstats(self):
         out = numpy.zeros((self.Q, 8))
         lib().bqo_suffstats(ctypes.byref(self._st), out.ctypes.data_as(f64p))
