@@ -985,13 +985,60 @@ extern "C" int bq_suffstats(bq_handle *h, double *out) {
     return run_report(h, nullptr, out);
 }
 
+// dynamic-order networks: the kernel commits with the sweep kernels' own code, in place; every per-chain array is
+// saved before and put back after
+static int gibbs_kernel_dynamic_path(bq_handle *h, const double *d_to, int32_t n_to, int32_t strict, double *out) {
+    const size_t E = h->E, C = h->C, n_order = h->dyn_order.size();
+    struct Saved { void *dev; void *copy; size_t bytes; };
+    std::vector<Saved> saved = {{h->d_state, nullptr, C * E * sizeof(double)},
+                                {h->d_prec, nullptr, C * E * h->recS * sizeof(double)},
+                                {h->d_ord, nullptr, C * E * sizeof(int)},
+                                {h->d_pos, nullptr, C * E * sizeof(int)}};
+    if (h->has_ps) {
+        saved.push_back({h->d_dord, nullptr, C * E * sizeof(int)});
+        saved.push_back({h->d_dpos, nullptr, C * E * sizeof(int)});
+        saved.push_back({h->d_dt, nullptr, C * E * sizeof(double)});
+        saved.push_back({h->d_sq, nullptr, C * E * sizeof(double)});
+    }
+    double *to = nullptr, *res = nullptr;
+    unsigned char *done = nullptr;
+    auto cleanup = [&]() {
+        for (auto &sv : saved) cudaFree(sv.copy);
+        cudaFree(to); cudaFree(res); cudaFree(done);
+    };
+#define CKG(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(BQ_ERR_CUDA, cudaGetErrorString(e_)); } } while (0)
+    for (auto &sv : saved) {
+        CKG(cudaMalloc(&sv.copy, sv.bytes));
+        CKG(cudaMemcpyAsync(sv.copy, sv.dev, sv.bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CKG(cudaMalloc((void **)&to, (size_t)n_to * E * sizeof(double)));
+    CKG(cudaMalloc((void **)&res, C * sizeof(double)));
+    CKG(cudaMalloc((void **)&done, std::max<size_t>(C * n_order, 1)));
+    CKG(cudaMemcpyAsync(to, d_to, (size_t)n_to * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CKG(cudaMemsetAsync(done, 0, std::max<size_t>(C * n_order, 1), h->stream));
+    DynArgs D;
+    fill_dyn_args(h, D);
+    const int G = 4;
+    const size_t sm = (size_t)G * dyn_group_smem(h->Q, h->P);
+    const unsigned blocks = (unsigned)((C + G - 1) / G);
+    if (h->kmax <= 4) gibbs_kernel_dynamic<4><<<blocks, 32 * G, sm, h->stream>>>(D, to, n_to, strict ? 1 : 0, done, res);
+    else gibbs_kernel_dynamic<8><<<blocks, 32 * G, sm, h->stream>>>(D, to, n_to, strict ? 1 : 0, done, res);
+    CKG(cudaGetLastError());
+    for (auto &sv : saved) CKG(cudaMemcpyAsync(sv.dev, sv.copy, sv.bytes, cudaMemcpyDeviceToDevice, h->stream));
+    CKG(cudaMemcpyAsync(out, res, C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CKG(cudaStreamSynchronize(h->stream));
+#undef CKG
+    cleanup();
+    h->n_launches += 1;
+    return BQ_OK;
+}
+
 // Qnet.gibbs_kernel (qnet.pyx:741-809) for every chain: log T(d_to <- state of the chain) of one slice sweep
 extern "C" int bq_gibbs_kernel(bq_handle *h, const double *d_to, int32_t n_to, int32_t strict, double *out) {
     if (!h || !d_to || !out) return fail(BQ_ERR_INVALID, "null argument");
     if (n_to != 1 && n_to != h->C) return fail(BQ_ERR_INVALID, "n_to must be 1 or the number of chains");
-    if (!h->static_order)
-        return fail(BQ_ERR_UNSUPPORTED, "gibbs_kernel: networks with multi-server or PS queues are not supported");
     CK(cudaSetDevice(h->device));
+    if (!h->static_order) return gibbs_kernel_dynamic_path(h, d_to, n_to, strict, out);
     const size_t E = h->E, C = h->C, n_sched = h->order.size();
     double *work = nullptr, *to = nullptr, *res = nullptr;
     unsigned char *done = nullptr;

@@ -112,7 +112,7 @@ def chib_evidence(net, obs, M_special=100, M=100, debug=False, seed=None, device
     """Chib's estimate of the log evidence log p(observed) with the Murray-Salakhutdinov correction
     (estimation.py:274-330): p(v) = p(v, h*, theta*) / p(h*, theta* | v), the denominator averaged over a forward and
     a backward (reverse-scan) chain started at the special state of the transition densities
-    Qnet.gibbs_kernel + Qnet.parameter_kernel into it.  Slice sampler only; single-server FIFO / delay networks.
+    Qnet.gibbs_kernel + Qnet.parameter_kernel into it.  Slice sampler only.
     strict (default): an event whose target lies outside its support when its turn comes makes the transition
     impossible (density 0) -- the reference instead retries such events after the others (qnet.pyx:756-805), which
     is not the density of the sweep and biases the estimate (tests/test_gpu_chib.py); strict=False reproduces it."""

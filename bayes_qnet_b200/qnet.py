@@ -265,8 +265,7 @@ class Qnet(object):
         """log T(arrv_to <- arrv_from) of one slice sweep in the kernel's scan order (qnet.pyx:741-809): minus the sum
         over the resampled events of the log normaliser of their conditional, each event moved to its target before
         the next.  -inf when the target cannot be reached.  Like the reference, events whose target is not reachable at
-        their turn are retried after the others; strict=True returns -inf instead (the density of the sweep itself).
-        Single-server FIFO / delay-station networks."""
+        their turn are retried after the others; strict=True returns -inf instead (the density of the sweep itself)."""
         return float(self._engine_for(arrv_from).gibbs_kernel(arrv_to.soa()["d"], strict=strict)[0])
 
     def parameter_kernel(self, theta_from, theta_to, arrvl):

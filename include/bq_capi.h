@@ -147,8 +147,8 @@ int bq_mh_proposal(bq_handle *h, int32_t chain, int32_t eid, const double *x, in
  * moved to its target before the next one is taken; events whose target is not reachable yet are retried in later
  * passes and -inf is returned when a pass moves nothing (qnet.pyx:756-805).  strict != 0: no later passes -- an
  * unreachable target gives -inf, the density of the fixed-scan sweep itself (what Chib's identity needs).  d_to:
- * n_to * n_events doubles, n_to = 1 (one target for all chains) or n_chains.  The chains' states are not modified.
- * Static-order networks only. */
+ * n_to * n_events doubles, n_to = 1 (one target for all chains) or n_chains.  The chains' states are not modified
+ * (networks with multi-server or PS queues are evaluated in place and restored).  Every supported discipline. */
 int bq_gibbs_kernel(bq_handle *h, const double *d_to, int32_t n_to, int32_t strict, double *out);
 /* Qnet.log_prob (qnet.pyx:1032): out[n_chains] */
 int bq_log_prob(bq_handle *h, double *out);

@@ -511,13 +511,17 @@ static double simpson_rec(const kern_fn *k, double a, double b, double fa, doubl
     return simpson_rec(k, a, m, fa, flm, fm, left, 0.5 * tol, depth - 1) +
            simpson_rec(k, m, b, fm, frm, fb, right, 0.5 * tol, depth - 1);
 }
-static double simpson(const kern_fn *k, double a, double b, double tol) {
+/* rel: tolerance relative to the larger of this piece's first estimate and what has been integrated so far (zref) */
+static double simpson(const kern_fn *k, double a, double b, double rel, double zref) {
     /* end points nudged inside: a service of exactly zero has log-density -inf or +inf */
     double w = b - a, a1 = a + 1e-13 * w, b1 = b - 1e-13 * w, m = 0.5 * (a1 + b1);
-    double fa = kern_eval(k, a1), fm = kern_eval(k, m), fb = kern_eval(k, b1);
+    double fa = kern_eval(k, a1), fm = kern_eval(k, m), fb = kern_eval(k, b1), whole, tol;
     if (!(fa == fa) || fa > 1e300) fa = 0.0;
     if (!(fb == fb) || fb > 1e300) fb = 0.0;
-    return simpson_rec(k, a1, b1, fa, fm, fb, (b1 - a1) / 6.0 * (fa + 4.0 * fm + fb), tol, 48);
+    whole = (b1 - a1) / 6.0 * (fa + 4.0 * fm + fb);
+    tol = rel * fmax(fabs(whole), zref);
+    if (!(tol > 1e-300)) tol = 1e-300;
+    return simpson_rec(k, a1, b1, fa, fm, fb, whole, tol, 48);
 }
 
 static int cmp_double(const void *x, const void *y) {
@@ -549,11 +553,11 @@ static double kern_normaliser(const bqo_state *st, int e, double lf, double lowe
     for (i = 0, j = 0; i < n; ++i)
         if (j == 0 || pts[i] > pts[j - 1]) pts[j++] = pts[i];
     n = j;
-    for (i = 0; i + 1 < n; ++i) z += simpson(&k, pts[i], pts[i + 1], 1e-13);
+    for (i = 0; i + 1 < n; ++i) z += simpson(&k, pts[i], pts[i + 1], 1e-12, z);
     if (!(upper < INFINITY)) {
         double t0 = pts[n - 1], w = fmax(1.0, fabs(st->d[e] - lower));
         for (i = 0; i < 200; ++i) {
-            double part = simpson(&k, t0, t0 + w, 1e-13);
+            double part = simpson(&k, t0, t0 + w, 1e-12, z);
             z += part;
             t0 += w;
             w *= 2.0;

@@ -55,12 +55,51 @@ def test_gibbs_kernel_matches_oracle(name):
             assert (strict[c] == ref == -numpy.inf) or abs(strict[c] - ref) < 1e-7 * max(1.0, abs(ref)), (c, strict[c], ref)
 
 
-def test_gibbs_kernel_refused_for_dynamic_order_networks():
-    g = helpers.golden("kern_mm3")
+@pytest.mark.parametrize("name", ["mm3", "lnk", "psdelay"])
+def test_gibbs_kernel_dynamic_order_networks(name):
+    """Multi-server FIFO and PS queues: the warp-per-chain kernel (15 Kronrod nodes side by side, commits with the
+    sweep kernels' dyn_commit) against the oracle, there and back between states one sweep apart; the chains' own
+    arrays are restored afterwards (the next sweeps reproduce an undisturbed run)."""
+    g = helpers.golden("cond_" + name)
     net, arrv = helpers.golden_state(g, "s0")
-    with GibbsEngine(net, arrv, n_chains=1) as eng:
-        with pytest.raises(capi.BqError):
-            eng.gibbs_kernel(g["to_d"])
+    d0 = arrv.soa()["d"].copy()
+    with GibbsEngine(net, arrv, n_chains=2, seed=77) as eng, GibbsEngine(net, arrv, n_chains=2, seed=77) as twin:
+        order = eng.sequential_order()
+        eng.sweep(1, "SLICE", "NONE")
+        twin.sweep(1, "SLICE", "NONE")
+        d1 = eng.state()
+        back = eng.gibbs_kernel(d0)
+        back_strict = eng.gibbs_kernel(d0, strict=True)
+        for c in range(2):
+            oc = helpers.oracle_chain(net, arrv)
+            oc.slice_sweep(order, eng.seed, c, 0)
+            assert helpers.relerr(oc.d, d1[c]).max() < 1e-12
+            ref = oc.gibbs_kernel(order, d0)
+            assert (back[c] == ref == -numpy.inf) or abs(back[c] - ref) < 1e-5 * max(1.0, abs(ref)), (c, back[c], ref)
+            oc = helpers.oracle_chain(net, arrv)
+            oc.slice_sweep(order, eng.seed, c, 0)
+            ref = oc.gibbs_kernel(order, d0, strict=True)
+            assert (back_strict[c] == ref == -numpy.inf) or abs(back_strict[c] - ref) < 1e-5 * max(1.0, abs(ref))
+        with GibbsEngine(net, arrv, n_chains=2, seed=77) as fresh:
+            there = fresh.gibbs_kernel(d1)
+            for c in range(2):
+                oc = helpers.oracle_chain(net, arrv)
+                ref = oc.gibbs_kernel(order, d1[c])
+                assert numpy.isfinite(ref)
+                assert abs(there[c] - ref) < 1e-5 * max(1.0, abs(ref)), (c, there[c], ref)
+        # nothing was disturbed
+        assert numpy.array_equal(eng.state(), d1)
+        eng.sweep(2, "SLICE", "BAYES")
+        twin.sweep(2, "SLICE", "BAYES")
+        assert numpy.array_equal(eng.state(), twin.state()) and numpy.array_equal(eng.params(), twin.params())
+    if name == "mm3":  # the reference's own value, in the reference's event order is pinned through the oracle;
+        gk = helpers.golden("kern_mm3")  # here: the same states under the kernel's scan order
+        net, frm = helpers.golden_state(gk, "s0")
+        with GibbsEngine(net, frm, n_chains=1) as eng:
+            dev = eng.gibbs_kernel(gk["to_d"])[0]
+            oc = helpers.oracle_chain(net, frm)
+            ref = oc.gibbs_kernel(eng.sequential_order(), gk["to_d"])
+            assert abs(dev - ref) < 1e-5 * max(1.0, abs(ref)), (dev, ref)
 
 
 INI_ONLY = """
