@@ -77,6 +77,8 @@ struct DynArgs {
     double *state;        // [C][E]  d by event
     int *ord, *pos;       // [C][E]
     double *rec;          // [C][E][S] by position: {arrival, departure, log service, free-time vector F[0..k), pad}
+    unsigned char *flag;  // [C][FW] one byte per position: the event arrived before the second server was free
+    int FW;               // bytes per chain (a multiple of 32)
     int *dord, *dpos;     // [C][E]  PS
     double *dt, *sq;      // [C][E]  PS
     double *theta;        // [C][P]
@@ -126,6 +128,7 @@ struct Chain {
     int *ord, *pos;
     double *rec;  // one record of S doubles per position: the neighbourhood of an event is one or two cache lines
     int S, ols;   // ols: slot of the log service
+    unsigned char *flag;  // flag[p] = at(p) < F[p][1] ("contended arrival", multi-server FIFO queues; see ggk_dep_delta)
     int *dord, *dpos;
     double *dt, *sq;
     const QInfo *qi;
@@ -139,6 +142,7 @@ struct Chain {
         rec = a.rec + c * a.E * a.S;
         S = a.S;
         ols = rec_ls_slot(a.S);
+        flag = a.flag + c * a.FW;
         dord = a.dord ? a.dord + c * a.E : nullptr;
         dpos = a.dpos ? a.dpos + c * a.E : nullptr;
         dt = a.dt ? a.dt + c * a.E : nullptr;
@@ -151,6 +155,12 @@ struct Chain {
     BQ_HDF double &ls(int p) const { return rec[(size_t)p * S + ols]; }  // log of its service time (Gamma / LogNormal)
     // server-free times seen by position p of a FIFO queue; the next position's vector is S doubles further
     BQ_HDF double *fvec(const QInfo &, int p) const { return rec + (size_t)p * S + BQ_REC_F; }
+    // one byte per position: lanes of a warp that commit different positions never write the same byte
+    BQ_HDF void set_contended(int p, bool on) const { flag[p] = on ? 1 : 0; }
+    // the flags of positions 8 g .. 8 g + 7, one per byte
+    BQ_HDF unsigned long long contended8(int g) const {
+        return reinterpret_cast<const unsigned long long *>(flag)[g];
+    }
 };
 
 // the event being resampled and its task successor, with their positions and current times
@@ -251,6 +261,9 @@ BQ_HDI int free_min_bound(const double *f, int k, int lo, int hi, double t, bool
 #ifndef BQ_WALK_U
 #define BQ_WALK_U 2
 #endif
+#ifndef BQ_SCAN_LOCAL
+#define BQ_SCAN_LOCAL 8  // positions scanned from their records before the flags take over (a multiple of BQ_WALK_U)
+#endif
 template <int KMAX>
 BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, Touch &tc) {
     const QInfo &q = c.qi[ev.q0];
@@ -274,8 +287,10 @@ BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, Touch 
     const double stop = later ? x : x0;
     // the positions are independent: fetch BQ_WALK_U of them at once so their cache misses overlap
     const int last = q.hi - 1;
+    const bool flagmode = later && k > 1;
+    const int p_local = p + BQ_SCAN_LOCAL;
     bool done = false;
-    while (p <= last && !done) {
+    while (p <= last && !done && !(flagmode && p >= p_local)) {
         double bo_[BQ_WALK_U], bx_[BQ_WALK_U], ai_[BQ_WALK_U], di_[BQ_WALK_U];
 #pragma unroll
         for (int u = 0; u < BQ_WALK_U; ++u) {
@@ -303,6 +318,52 @@ BQ_HDI double ggk_dep_delta(const Chain &c, const EventCtx &ev, double x, Touch 
             }
             ++p;
         }
+    }
+    if (flagmode && !done && p <= last) {
+        // Only an event that arrived before the second server was free (flag bit) can start later when the minimum
+        // free time is taken away: for the others a_p >= F[p][1] >= b_new >= b_old, nothing changes.  The flags are
+        // read 8 positions at a time (one record per 32 to find the end of the range), so the long feasible scans
+        // of lightly loaded queues cost a few bytes per event instead of a record.  Short scans never get here: the
+        // first BQ_SCAN_LOCAL positions are taken from their records, which are next to the event's own.
+        const int last_ = q.hi - 1;
+        while (p <= last_) {
+            const int bbase = p & ~31;
+            const int bend = (bbase + 32 < q.hi) ? bbase + 32 : q.hi;   // exclusive
+            const bool inside = f[(size_t)(bend - 1 - p0) * S] < x;    // F[.][0] is nondecreasing: whole block in range
+            bool ended = false;
+            for (int g = p >> 3; g < ((bend + 7) >> 3) && !ended; ++g) {
+                unsigned long long w = c.contended8(g);
+                const int gb = g << 3;
+                if (gb < p) w &= ~0ull << (8 * (p - gb));                       // positions before the range
+                if (gb + 8 > bend) w &= (1ull << (8 * (bend - gb))) - 1ull;      // the next queue's positions
+                while (w) {
+#ifdef __CUDA_ARCH__
+                    const int by = (__ffsll((long long)w) - 1) >> 3;
+#else
+                    const int by = __builtin_ctzll(w) >> 3;
+#endif
+                    w &= ~(0xffull << (8 * by));
+                    const int pp = gb + by;
+                    const double *fp = f + (size_t)(pp - p0) * S;
+                    const double bo = fp[0];
+                    if (bo >= x) { ended = true; break; }  // same free times as before from here on
+                    ++tc.steps;
+                    const double f1 = fp[1];
+                    const double bn = (f1 < x) ? f1 : x;
+                    if (bn != bo) {
+                        const double ai = fp[BQ_REC_AT - BQ_REC_F], di = fp[BQ_REC_DQ - BQ_REC_F];
+                        const double sn = di - dmax(ai, bn);
+                        if (sn < 0.0) { tc.p0(pp); return BQ_NEG_INF; }
+                        const double so = di - dmax(ai, bo);
+                        if (sn != so) acc += lpdf(qc, sn) - lpdf_ls(qc, so, c.ls(pp));
+                    }
+                }
+            }
+            tc.p0(bend - 1);
+            if (ended || !inside) break;
+            p = bend;
+        }
+        return acc;
     }
     tc.p0(p < q.hi ? p : q.hi - 1);
     return acc;
@@ -691,6 +752,7 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
             if (lane == 0) {
                 if (log0 && M.v[0] != fi[0]) c.ls(p) = log_d(di - dmax(c.at(p), M.v[0]));
                 M.store(fi, k);
+                if (k > 1) c.set_contended(p, c.at(p) < M.v[1]);
             }
             M.replace_min(di);
         }
@@ -726,6 +788,7 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
             if (lane == 0) {
                 if (log1 && (t <= pe || M.v[0] != fi[0])) c.ls(t) = log_d(di - dmax(c.at(t), M.v[0]));
                 M.store(fi, k);
+                if (k > 1) c.set_contended(t, c.at(t) < M.v[1]);
             }
             M.replace_min(di);
         }
@@ -1372,6 +1435,7 @@ __global__ void rebuild_positions_kernel(const DynArgs A, const int *ev_pt) {
         r[BQ_REC_AT] = ai;
         if (qi.type == Q_GGK) {
             M.store(r + BQ_REC_F, qi.k);
+            if (qi.k > 1) A.flag[(size_t)chain * A.FW + p] = (ai < M.v[1]) ? 1 : 0;
             if (qi.dist != D_EXP) r[rec_ls_slot(A.S)] = log_d(di - dmax(ai, M.v[0]));
             M.replace_min(di);
         } else if (qi.type == Q_DELAY && qi.dist != D_EXP) {

@@ -83,6 +83,8 @@ struct bq_handle {
     QInfo *d_qinfo = nullptr;
     int *d_ord = nullptr, *d_pos = nullptr, *d_dord = nullptr, *d_dpos = nullptr;
     double *d_prec = nullptr, *d_sq = nullptr, *d_dt = nullptr;  // position records (DynArgs::rec), PS arrays
+    unsigned char *d_flag = nullptr;  // contended-arrival flags (DynArgs::flag)
+    int FW = 32;                      // bytes per chain
     int recS = 4;  // doubles per position record
     HostNet net() const {
         HostNet n;
@@ -251,7 +253,7 @@ static void fill_dyn_args(const bq_handle *h, DynArgs &A) {
     A.n_order = (int)h->dyn_order.size();
     A.order = h->d_order;
     A.qinfo = h->d_qinfo; A.q_poff = h->d_q_poff;
-    A.state = h->d_state; A.ord = h->d_ord; A.pos = h->d_pos; A.rec = h->d_prec;
+    A.state = h->d_state; A.ord = h->d_ord; A.pos = h->d_pos; A.rec = h->d_prec; A.flag = h->d_flag; A.FW = h->FW;
     A.dord = h->d_dord; A.dpos = h->d_dpos; A.dt = h->d_dt; A.sq = h->d_sq;
     A.theta = h->d_theta; A.stats = h->d_stats;
     A.tr_theta = h->d_tr_theta; A.tr_wait = h->d_tr_wait; A.tr_logp = h->d_tr_logp;
@@ -263,6 +265,7 @@ struct HostRows {
     std::vector<int> ord, pos, dord, dpos;
     std::vector<double> at, dq, ls, F, dt, sq;
     std::vector<double> rec;  // at, dq, ls and F interleaved by position, as the device holds them
+    std::vector<unsigned char> flag;  // contended-arrival flags
     // one record per position: {at, dq, F[0], F[1], ls, F[2..k)} (bq_dynamic.cuh, BQ_REC_*)
     void pack(const bq_handle *h, size_t rows);
     void alloc(size_t rows, size_t E, size_t EF, bool ps) {
@@ -285,6 +288,7 @@ struct HostRows {
 void HostRows::pack(const bq_handle *h, size_t rows) {
     const size_t E = h->E, S = h->recS, EF = h->EF;
     rec.assign(rows * E * S, 0.0);
+    flag.assign(rows * (size_t)h->FW, 0);
     for (size_t i = 0; i < rows; ++i)
         for (int q = 0; q < h->Q; ++q) {
             const int lo = h->q_off[q], hi = h->q_off[q + 1], k = (h->q_type[q] == Q_GGK) ? h->q_k[q] : 0;
@@ -292,6 +296,7 @@ void HostRows::pack(const bq_handle *h, size_t rows) {
                 double *r = &rec[(i * E + p) * S];
                 r[BQ_REC_AT] = at[i * E + p]; r[BQ_REC_DQ] = dq[i * E + p]; r[rec_ls_slot((int)S)] = ls[i * E + p];
                 for (int j = 0; j < k; ++j) r[BQ_REC_F + BQ_FSLOT(j)] = F[i * EF + h->q_foff[q] + (size_t)(p - lo) * k + j];
+                if (k > 1 && r[BQ_REC_AT] < r[BQ_REC_F + 1]) flag[i * h->FW + p] = 1;
             }
         }
 }
@@ -309,6 +314,7 @@ static int upload_rows(bq_handle *h, HostRows &r, int lo, size_t rows, size_t n,
     CK(put(h->d_ord + o, r.ord, E));
     CK(put(h->d_pos + o, r.pos, E));
     CK(put(h->d_prec + o * h->recS, r.rec, E * h->recS));
+    CK(put(h->d_flag + (size_t)lo * h->FW, r.flag, (size_t)h->FW));
     if (h->has_ps) {
         CK(put(h->d_dord + o, r.dord, E));
         CK(put(h->d_dpos + o, r.dpos, E));
@@ -372,6 +378,7 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
         }
     if (h->kmax > 8) return fail(BQ_ERR_UNSUPPORTED, "more than 8 processors per queue");
     h->recS = rec_stride(h->kmax);
+    h->FW = ((E + 31) & ~31) + 32;
     HostRows r0;
     r0.alloc(1, E, h->EF, h->has_ps);
     memcpy(r0.ord.data(), h->ord0.data(), E * sizeof(int));
@@ -402,6 +409,8 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
     CK(cudaMalloc((void **)&h->d_ord, C * E * sizeof(int)));
     CK(cudaMalloc((void **)&h->d_pos, C * E * sizeof(int)));
     CK(cudaMalloc((void **)&h->d_prec, C * E * h->recS * sizeof(double)));
+    CK(cudaMalloc((void **)&h->d_flag, C * h->FW));
+    CK(cudaMemsetAsync(h->d_flag, 0, C * h->FW, h->stream));
     {   // log of small counts for the PS terms, computed with the host's log()
         double tab[256];
         tab[0] = -INFINITY;
@@ -500,7 +509,7 @@ extern "C" int bq_destroy(bq_handle *h) {
     void *ptrs[] = {h->d_rec, h->d_color_off, h->d_ev_q, h->d_ev_p, h->d_ev_pt, h->d_q_events, h->d_q_off,
                     h->d_q_type, h->d_q_dist, h->d_q_poff, h->d_state, h->d_theta, h->d_stats,
                     h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch, h->d_order, h->d_qinfo,
-                    h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_prec, h->d_sq, h->d_dt, h->d_claim,
+                    h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_prec, h->d_flag, h->d_sq, h->d_dt, h->d_claim,
                     h->d_claimd};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -993,7 +1002,8 @@ static int gibbs_kernel_dynamic_path(bq_handle *h, const double *d_to, int32_t n
     std::vector<Saved> saved = {{h->d_state, nullptr, C * E * sizeof(double)},
                                 {h->d_prec, nullptr, C * E * h->recS * sizeof(double)},
                                 {h->d_ord, nullptr, C * E * sizeof(int)},
-                                {h->d_pos, nullptr, C * E * sizeof(int)}};
+                                {h->d_pos, nullptr, C * E * sizeof(int)},
+                                {h->d_flag, nullptr, C * (size_t)h->FW}};
     if (h->has_ps) {
         saved.push_back({h->d_dord, nullptr, C * E * sizeof(int)});
         saved.push_back({h->d_dpos, nullptr, C * E * sizeof(int)});

@@ -23,6 +23,7 @@ struct Emul {
     std::vector<QConst> qc;
     std::vector<QInfo> qinfo;
     std::vector<double> recs;  // at, dq, ls, F interleaved by position: what the kernels work on
+    std::vector<unsigned long long> flags;  // contended-arrival flags, one byte per position (8-byte aligned storage)
     int EF, S;
     DynArgs A;
     Chain c;
@@ -37,12 +38,14 @@ struct Emul {
     // at / dq / ls / F (host_rebuild's separate arrays) <-> position records
     void pack() {
         recs.assign((size_t)E * S, 0.0);
+        flags.assign((size_t)(((E + 31) & ~31) + 32) / 8, 0ull);
         for (int q = 0; q < Q; ++q)
             for (int p = q_off[q]; p < q_off[q + 1]; ++p) {
                 double *r = &recs[(size_t)p * S];
                 r[BQ_REC_AT] = at[p]; r[BQ_REC_DQ] = dq[p]; r[rec_ls_slot(S)] = ls[p];
                 if (q_type[q] == Q_GGK)
                     for (int j = 0; j < q_k[q]; ++j) r[BQ_REC_F + BQ_FSLOT(j)] = F[q_foff[q] + (size_t)(p - q_off[q]) * q_k[q] + j];
+                if (q_type[q] == Q_GGK && q_k[q] > 1 && r[BQ_REC_AT] < r[BQ_REC_F + 1]) reinterpret_cast<unsigned char *>(flags.data())[p] = 1;
             }
     }
     void unpack() {
@@ -58,7 +61,7 @@ struct Emul {
         memset(&A, 0, sizeof(A));
         A.E = E; A.Q = Q; A.P = P; A.n_chains = 1; A.S = S;
         A.qinfo = qinfo.data(); A.q_poff = q_poff.data();
-        A.state = d.data(); A.ord = ord.data(); A.pos = pos.data(); A.rec = recs.data();
+        A.state = d.data(); A.ord = ord.data(); A.pos = pos.data(); A.rec = recs.data(); A.flag = reinterpret_cast<unsigned char *>(flags.data()); A.FW = (int)flags.size() * 8;
         A.dord = dord.data(); A.dpos = dpos.data(); A.dt = dt.data(); A.sq = sq.data();
         A.theta = theta.data();
         c.bind(A, 0, qinfo.data(), qc.data());
@@ -329,6 +332,13 @@ int bqe_check(void *h) {
             if (fabs(sq[p] - m->sq[p]) > 1e-9 * fmax(1.0, fabs(sq[p]))) return 7;
         }
     }
+    for (int q = 0; q < m->Q; ++q)  // the contended-arrival bits of multi-server FIFO queues
+        if (m->q_type[q] == Q_GGK && m->q_k[q] > 1)
+            for (int p = m->q_off[q]; p < m->q_off[q + 1]; ++p) {
+                const double f1 = F[m->q_foff[q] + (size_t)(p - m->q_off[q]) * m->q_k[q] + 1];
+                const bool want = at[p] < f1, have = reinterpret_cast<const unsigned char *>(m->flags.data())[p] != 0;
+                if (want != have) return 11;
+            }
     // every non-delay queue must be sorted by arrival
     for (int q = 0; q < m->Q; ++q) {
         if (m->q_type[q] == Q_DELAY) continue;
