@@ -449,17 +449,34 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
 // the derived arrays are rebuilt on the host
 static int dynamic_set_rows(bq_handle *h, int lo, int hi, const double *d, bool same_for_all) {
     const size_t E = h->E, n = (size_t)(hi - lo);
-    const size_t rows = same_for_all ? 1 : n;
-    HostRows r;
-    r.alloc(rows, E, h->EF, h->has_ps);
     const HostNet hn = h->net();
-    for (size_t i = 0; i < rows; ++i) {
-        memcpy(&r.ord[i * E], h->ord0.data(), E * sizeof(int));
-        host_rebuild(&hn, d + i * E, r.chain(i, E, h->EF), true);
+    if (same_for_all) {
+        HostRows r;
+        r.alloc(1, E, h->EF, h->has_ps);
+        memcpy(r.ord.data(), h->ord0.data(), E * sizeof(int));
+        host_rebuild(&hn, d, r.chain(0, E, h->EF), true);
+        CK(cudaMemcpyAsync(h->d_state + (size_t)lo * E, d, E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(replicate_rows(h->d_state + (size_t)lo * E, E, n, h->stream));
+        return upload_rows(h, r, lo, 1, n, true);
     }
-    CK(cudaMemcpyAsync(h->d_state + (size_t)lo * E, d, rows * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (same_for_all) CK(replicate_rows(h->d_state + (size_t)lo * E, E, n, h->stream));
-    return upload_rows(h, r, lo, rows, n, true);
+    // chains with their own states: staged in slices of at most ~256 MB of derived arrays on the host
+    const size_t per_row = E * (size_t)(8 * (h->recS + 8) + 24) + (size_t)h->EF * 8 + 64;
+    size_t budget = (size_t)256 << 20;
+    if (const char *env = getenv("BQ_STAGE_MB")) budget = (size_t)atol(env) << 20;  // test hook: 0 = one chain per slice
+    const size_t slice = std::max<size_t>(1, budget / per_row);
+    for (size_t i0 = 0; i0 < n; i0 += slice) {
+        const size_t rows = std::min(slice, n - i0);
+        HostRows r;
+        r.alloc(rows, E, h->EF, h->has_ps);
+        for (size_t i = 0; i < rows; ++i) {
+            memcpy(&r.ord[i * E], h->ord0.data(), E * sizeof(int));
+            host_rebuild(&hn, d + (i0 + i) * E, r.chain(i, E, h->EF), true);
+        }
+        CK(cudaMemcpyAsync(h->d_state + ((size_t)lo + i0) * E, d + i0 * E, rows * E * sizeof(double),
+                           cudaMemcpyHostToDevice, h->stream));
+        if (int rc = upload_rows(h, r, lo + (int)i0, rows, rows, true)) return rc;  // synchronises: r may go
+    }
+    return BQ_OK;
 }
 
 template <int W>

@@ -389,6 +389,30 @@ def test_dynamic_set_state_and_sharding():
         assert numpy.all(eng.state(full=True)["s"] >= 0) and numpy.all(numpy.isfinite(eng.log_prob()))
 
 
+def test_per_chain_states_are_staged_in_slices(monkeypatch):
+    """set_state with one state per chain stages the derived arrays slice by slice on the host; the result does not
+    depend on the slice size (BQ_STAGE_MB=0: one chain per slice)."""
+    g = helpers.golden("cond_mm3")
+    net, arrv = helpers.golden_state(g, "s0")
+    with GibbsEngine(net, arrv, n_chains=5, seed=9) as eng:
+        eng.sweep(2, "SLICE", "BAYES")
+        d, th = eng.state(), eng.params()
+    outs = []
+    for mb in (None, "0"):
+        if mb is None:
+            monkeypatch.delenv("BQ_STAGE_MB", raising=False)
+        else:
+            monkeypatch.setenv("BQ_STAGE_MB", mb)
+        with GibbsEngine(net, arrv, n_chains=5, seed=9) as eng:
+            eng.set_state(d)
+            eng.set_params(th)
+            full = eng.state(full=True)
+            eng.sweep(2, "SLICE", "BAYES")
+            outs.append((full["s"], full["proc"], full["next_byq"], eng.state(), eng.params()))
+    for a, b in zip(outs[0], outs[1]):
+        assert numpy.array_equal(a, b)
+
+
 @pytest.mark.parametrize("name", sorted(helpers.MIXED))
 def test_mixed_disciplines_match_oracle(name):
     """PS with LogNormal / Gamma service, PS -> PS, multi-server FIFO next to PS, delay stations in parallel with
