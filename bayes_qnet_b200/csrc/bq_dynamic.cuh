@@ -586,14 +586,15 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, Touch &t
 // ---------------------------------------------------------------------------------------------
 // the conditional of d_e: inner_dfun(x) - lik0   (qnet.pyx:1340-1357)
 // ---------------------------------------------------------------------------------------------
-template <int KMAX>
+// PS = false: a build for networks without processor-sharing queues (their code is half of the kernel)
+template <int KMAX, bool PS = true>
 BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, Touch &tc) {
     double g;
     tc.p0(ev.p0);
     if (ev.e1 >= 0) tc.p1(ev.p1);
     if (ev.t0 == Q_GGK) {
         g = ggk_dep_delta<KMAX>(c, ev, x, tc);
-    } else if (ev.t0 == Q_PS) {
+    } else if (PS && ev.t0 == Q_PS) {
         if (x < ev.a_e) return BQ_NEG_INF;
         g = 0.0;
         if (x != ev.x0) {
@@ -610,7 +611,7 @@ BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, Touch &t
     double g1;
     if (ev.t1 == Q_GGK) {
         g1 = ggk_arr_delta<KMAX>(c, ev, x, tc);
-    } else if (ev.t1 == Q_PS) {
+    } else if (PS && ev.t1 == Q_PS) {
         if (x > ev.d1) return BQ_NEG_INF;
         g1 = 0.0;
         if (x != ev.x0) {
@@ -708,7 +709,7 @@ BQ_HDI void reslot(double *v, int sv, int *ev, int *inv, double *pay0, int s0, d
 #undef P1_
 }
 
-template <int W, int KMAX>
+template <int W, int KMAX, bool PS = true>
 BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, unsigned gmask) {
     // ---- everything that is computed on the old state first ------------------------------------------------
     int j1 = ev.p1;
@@ -717,19 +718,19 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         Touch tmp;
         tmp.reset();
         if (ev.t1 == Q_GGK) j1 = new_rank(c, q1, ev.p1, x, ev.x0, tmp);
-        else {  // PS: rank among the other arrivals
+        else if (PS) {  // PS: rank among the other arrivals
             j1 = upper_from(c.rec + BQ_REC_AT, q1.lo, q1.hi, ev.p1, x, c.S);
             if (c.at(ev.p1) <= x) --j1;
         }
     }
     Touch dummy;
     dummy.reset();
-    if (ev.t0 == Q_PS) {  // new service times of everything that overlaps the moved interval
+    if (PS && ev.t0 == Q_PS) {  // new service times of everything that overlaps the moved interval
         PsMove mv;
         ps_move_setup(c, ev.q0, ev.p0, ev.e, true, ev.x0, x, mv, dummy);
         ps_apply_move<true>(c, mv, lane, dummy);
     }
-    if (ev.e1 >= 0 && ev.t1 == Q_PS) {
+    if (PS && ev.e1 >= 0 && ev.t1 == Q_PS) {
         PsMove mv;
         ps_move_setup(c, ev.q1, ev.p1, ev.e1, false, ev.x0, x, mv, dummy);
         ps_apply_move<true>(c, mv, lane, dummy);
@@ -752,7 +753,7 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
             if (lane == 0) {
                 if (log0 && M.v[0] != fi[0]) c.ls(p) = log_d(di - dmax(c.at(p), M.v[0]));
                 M.store(fi, k);
-                if (k > 1) c.set_contended(p, c.at(p) < M.v[1]);
+                if (KMAX > 1 && k > 1) c.set_contended(p, c.at(p) < M.v[KMAX > 1 ? 1 : 0]);
             }
             M.replace_min(di);
         }
@@ -760,7 +761,7 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         if (log0 && lane == 0) c.ls(ev.p0) = log_d(x - ev.a_e);
     }
     BQ_SYNCG(gmask);
-    if (ev.t0 == Q_PS) {  // the departure changes rank among the queue's sorted departures
+    if (PS && ev.t0 == Q_PS) {  // the departure changes rank among the queue's sorted departures
         const QInfo &q = c.qi[ev.q0];
         const int pd = c.dpos[ev.e];
         int j = upper_from(c.dt, q.lo, q.hi, pd, x);
@@ -788,12 +789,12 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
             if (lane == 0) {
                 if (log1 && (t <= pe || M.v[0] != fi[0])) c.ls(t) = log_d(di - dmax(c.at(t), M.v[0]));
                 M.store(fi, k);
-                if (k > 1) c.set_contended(t, c.at(t) < M.v[1]);
+                if (KMAX > 1 && k > 1) c.set_contended(t, c.at(t) < M.v[KMAX > 1 ? 1 : 0]);
             }
             M.replace_min(di);
         }
         BQ_SYNCG(gmask);
-    } else if (ev.t1 == Q_PS) {
+    } else if (PS && ev.t1 == Q_PS) {
         reslot<W>(c.rec + BQ_REC_AT, c.S, c.ord, c.pos, c.rec + BQ_REC_DQ, c.S, c.sq, 1, ev.p1, j1, x, lane, gmask);
     } else {
         if (lane == 0) {
@@ -824,7 +825,7 @@ struct LaneParams {
     double tmax;
 };
 
-template <int KMAX, bool MH = true, bool SLICE = true>
+template <int KMAX, bool MH = true, bool SLICE = true, bool PS = true>
 BQ_HDI void lane_update(const Chain &c, const EventCtx &ev, const LaneParams &P, LaneUpdate &out) {
     out.x_new = ev.x0; out.changed = 0; out.counted = 0; out.rejected = 0; out.stuck = 0; out.evals = 0;
     out.R.reset(); out.Wt.reset();
@@ -834,7 +835,7 @@ BQ_HDI void lane_update(const Chain &c, const EventCtx &ev, const LaneParams &P,
     last.reset();
     auto g = [&](double x) {
         last.reset();
-        const double v = dyn_logcond<KMAX>(c, ev, x, last);
+        const double v = dyn_logcond<KMAX, PS>(c, ev, x, last);
         out.R.merge(last);
         return v;
     };
@@ -1225,7 +1226,7 @@ __device__ __forceinline__ bool claimed_before(const int *claim, int lo, int hi,
 // chains are resident; with more than 16 x 148 chains the 8-CTA build (64 registers, some spilling, 32 warps/SM) avoids
 // a second, partly filled wave (measured: +12 % at 4096 chains, -17 % at 2048)
 // MHK: the build for MH sweeps; the slice build carries no proposal code (fewer registers, less spilling).
-template <int KMAX, int MINB, bool MHK>
+template <int KMAX, int MINB, bool MHK, bool PS>
 __global__ void __launch_bounds__(128, MINB) sweep_batch_kernel(const DynArgs A, int *claim_all, int *claimd_all) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int W = 32;
@@ -1281,7 +1282,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_batch_kernel(const DynArgs A,
                 const int4 r4 = __ldg(&order4[(A.flags & FLAG_REVERSE) ? n_order - 1 - idx : idx]);
                 const DynRec rec = {r4.x, r4.y, r4.z, r4.w};
                 event_load(c, rec, ev);
-                lane_update<KMAX, MHK, !MHK>(c, ev, LP, up);
+                lane_update<KMAX, MHK, !MHK, PS>(c, ev, LP, up);
             }
             __syncwarp();
             if (active && up.changed) {  // publish what this lane will write
@@ -1303,7 +1304,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_batch_kernel(const DynArgs A,
             if (active && lane < fc) {
                 n_ev += up.counted; n_evals += up.evals; n_reject += up.rejected; n_steps += up.R.steps;
                 if (LP.mode != MODE_MH) n_stuck += up.stuck;
-                if (up.changed) dyn_commit<1, KMAX>(c, ev, up.x_new, 0, 1u << lane);
+                if (up.changed) dyn_commit<1, KMAX, PS>(c, ev, up.x_new, 0, 1u << lane);
             }
             n_redo += (lane == 0) ? (nact - fc) : 0;
             __syncwarp();

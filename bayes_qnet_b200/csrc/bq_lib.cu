@@ -501,7 +501,10 @@ static void launch_dynamic(bq_handle *h, const DynArgs &A) {
 #define BQ_DENSE_MINB 8
 #endif
 #define BQ_LAUNCH_BATCH(K, MINB, MHK) \
-    sweep_batch_kernel<K, MINB, MHK><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd)
+    do { \
+        if (h->has_ps) sweep_batch_kernel<K, MINB, MHK, true><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd); \
+        else sweep_batch_kernel<K, MINB, MHK, false><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd); \
+    } while (0)
         const bool mh = (A.mode == MODE_MH);
         if (h->kmax <= 4) {
             if (dense) { if (mh) BQ_LAUNCH_BATCH(4, BQ_DENSE_MINB, true); else BQ_LAUNCH_BATCH(4, BQ_DENSE_MINB, false); }

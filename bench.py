@@ -76,9 +76,9 @@ WORKLOADS = {
     "config2": dict(yaml=QNET3, init="DFN2", tasks=5000, chains=1024, sweeps=20, ref_tasks=5000, bytes=16.0,
                     kernel="sweep_static_kernel<true>", name="3-tier web-service network (qnet3)"),
     "config3": dict(yaml=TANDEM3, init="DFN2", tasks=20000, chains=4096, sweeps=2, ref_tasks=1000, bytes=32.0,
-                    kernel="sweep_batch_kernel<4, 8, false>", name="tandem source -> G/G/3 -> G/G/3, LogNormal service"),
+                    kernel="sweep_batch_kernel<4, 8, false, false>", name="tandem source -> G/G/3 -> G/G/3, LogNormal service"),
     "config4": dict(yaml=PSDELAY, init="PS", tasks=50000, chains=2048, sweeps=2, ref_tasks=2000, bytes=80.0 / 3.0,
-                    kernel="sweep_batch_kernel<4, 4, false>", name="source -> processor sharing -> delay station (one GPU's share "
+                    kernel="sweep_batch_kernel<4, 4, false, true>", name="source -> processor sharing -> delay station (one GPU's share "
                                                          "of the 16384 chains)"),
 }
 BYTES_PER_RESAMPLE = 16.0  # source / GGk k=1 / DELAY visits
