@@ -11,29 +11,33 @@
 // walk is a stream of consecutive loads with no pointer chasing:
 //
 //   ord[p], pos[e]   the event at position p / the position of event e
-//   at[p], dq[p]     arrival and departure time of the event at position p
-//   ls[p]            log of its service time, for FIFO queues and delay stations with Gamma / LogNormal service:
-//                    the "old" half of every lpdf(s_new) - lpdf(s_old) then costs no transcendental
-//   F[p][k]          k-server FIFO queues: the k server-free times seen by the event at position p, ascending
-//                    (the reference's Event.d_proc_prev, arrivals.pxd:30, as a sorted multiset: services
-//                    depend only on min F, and replacing the minimum by the event's own departure is the
-//                    whole recursion of queues.pyx:654-680)
+//   rec[p]           one record per position (BQ_REC_*): arrival and departure time of the event there, the k
+//                    server-free times it sees, ascending (the reference's Event.d_proc_prev, arrivals.pxd:30, as
+//                    a sorted multiset: services depend only on min F, and replacing the minimum by the event's
+//                    own departure is the whole recursion of queues.pyx:654-680), and the log of its service time
+//                    (Gamma / LogNormal service: the "old" half of every lpdf(s_new) - lpdf(s_old) then costs no
+//                    transcendental).  The first 32-byte sector holds what the departure-side scan reads.
+//   flag[p]          multi-server FIFO queues: the event arrived before the second server was free -- the only
+//                    events a later departure upstream can delay (skip predicate of the scan)
 //   dt[p], dord[p], dpos[e], sq[p]   PS queues: departure times sorted (with their events and the inverse
 //                    map), and the service time of the event at arrival-position p
 //   d[e]             departure times by event: the chain state as the C-ABI exposes it, kept in step
 //
-// A walk starts from the stored vector of the first position whose predecessors are unchanged, replays the
-// recursion with the modified time, and stops as soon as the running vector equals the stored one of the
-// next position (nothing further can change) or a service time goes negative (-inf).  Moving an arrival
-// re-inserts the event at its new rank (stable sort by arrival, queues.pyx:537) on the fly.
+// Departure side (ggk_dep_delta): F[p] is the k largest departures before p, so the effect of moving one departure
+// on every later position has a closed form and the diff list is an index range found by galloping -- no running
+// vector.  Arrival side (ggk_arr_delta): a short walk that starts from the stored vector of the first position whose
+// predecessors are unchanged, replays the recursion with the event re-inserted at its new rank (stable sort by
+// arrival, queues.pyx:537) and stops past the moved window, where the vectors agree again.  A negative service
+// time anywhere gives -inf.
 //
-// Execution model: a GROUP of W lanes (W = 8, 16 or 32; 32/W chains per warp) owns one chain and visits
-// its resample-eligible events one after another in a fixed order.  The lanes of the group evaluate W
-// consecutive shrink candidates of sampling._slice side by side: a candidate's position depends only on
-// where the earlier candidates fell, never on their densities, so the first accepted candidate in order
-// is exactly the outcome of the sequential loop.  All lanes of a group read the same addresses (broadcast
-// loads); the accepted move is committed cooperatively (order shift across lanes, vector refresh).
-// Sufficient statistics, parameter updates and traces are fused, as in the static kernel.
+// Execution models.  sweep_batch_kernel (default): a warp owns a chain and updates 32 events of it per round,
+// every lane its own event on the unchanged state; read / write ranges are recorded, the longest conflict-free
+// prefix of the round is committed, the rest redone -- exactly the sequential sweep.  sweep_dynamic_kernel: a
+// GROUP of W lanes (W = 4..32; 32/W chains per warp) owns one chain and visits its events one after another; the
+// lanes evaluate W consecutive shrink candidates of sampling._slice side by side: a candidate's position depends
+// only on where the earlier candidates fell, never on their densities, so the first accepted candidate in order
+// is exactly the outcome of the sequential loop.  Sufficient statistics, parameter updates and traces are fused,
+// as in the static kernel.
 #pragma once
 #include "bq_static.cuh"
 
