@@ -85,6 +85,8 @@ BYTES_PER_RESAMPLE = 16.0  # source / GGk k=1 / DELAY visits
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the default configuration, from the ncu --set full
 # capture summarised in profiles/r1_static_final_ncu_full.txt (166.0 MB + 108.0 MB)
 NCU_TRAFFIC_DEFAULT = 273.98e6
+# dram read + write of one sweep_batch_kernel launch of the default config-3 step (profiles/r1_config3_dram_traffic.csv)
+NCU_TRAFFIC_CONFIG3 = 762250469376.0 + 251954478592.0
 WORKLOAD = "%s, %d tasks, 20%% observed, %d chains/GPU x %d sweeps per step"
 
 
@@ -376,11 +378,15 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak,
-                         "traffic": NCU_TRAFFIC_DEFAULT if (args.workload, args.tasks, C, S) == ("config2", 5000, 1024, 20) else None,
+                         "traffic": NCU_TRAFFIC_DEFAULT if (args.workload, args.tasks, C, S) == ("config2", 5000, 1024, 20) else
+                                    (NCU_TRAFFIC_CONFIG3 if (args.workload, args.tasks, C, S) == ("config3", 20000, 4096, 2) else None),
                          "traffic_note": ("bytes per launch from profiles/r1_static_final_ncu_full.txt; far BELOW the "
                                           "algorithmic 16 B x resamples because the chain state stays in shared memory "
                                           "for all sweeps of a launch") if args.workload == "config2" else
-                                         "see profiles/r1_batch_tandem_4096_ncu_full.txt (259 GB per launch of 98 M resamples on the 2000-task tandem)",
+                                         ("bytes per launch from profiles/r1_config3_dram_traffic.csv: 80x the algorithmic 32 B x resamples -- every "
+                                          "evaluation re-reads the event's neighbourhood from HBM (L1 hit rate 54 %, "
+                                          "profiles/r1_batch_tandem_4096_ncu_full.txt)") if args.workload == "config3" else
+                                         "see profiles/r1_batch_tandem_4096_ncu_full.txt (256 GB per launch of 98 M resamples on the 2000-task tandem)",
                          "peak_kind": peak_kind,
                          "kernel": wl["kernel"], "bytes_per_resample": wl["bytes"],
                          "resamples_per_launch": resamples_per_step, "launch_ms_mean": mean_ms, "launch_ms_max": worst_ms},
