@@ -263,7 +263,7 @@ BQ_HDI int free_min_bound(const double *f, int k, int lo, int hi, double t, bool
 }
 
 #ifndef BQ_WALK_U
-#define BQ_WALK_U 2
+#define BQ_WALK_U 1
 #endif
 #ifndef BQ_SCAN_LOCAL
 #define BQ_SCAN_LOCAL 8  // positions scanned from their records before the flags take over (a multiple of BQ_WALK_U)
