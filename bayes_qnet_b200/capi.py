@@ -80,6 +80,10 @@ SYMBOLS = {
     "bq_get_mh_order": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), c_i32p]),
     "bq_rng_uniforms": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint32,
                                        ctypes.c_uint32, ctypes.c_int32, c_f64p]),
+    "bq_rng_slice_uniforms": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.c_uint32, ctypes.c_int32, c_f64p]),
+    "bq_philox_block": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.c_int32,
+                                       ctypes.POINTER(ctypes.c_uint32)]),
     "bq_kernel_info": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                       ctypes.POINTER(ctypes.c_int32)]),
     "bq_get_sweep_counter": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint32)]),
@@ -133,3 +137,19 @@ def rng_uniforms(seed, chain, sweep, ident, tag, n):
     out = numpy.empty(n, dtype=numpy.float64)
     check(lib().bq_rng_uniforms(seed, chain, sweep, ident, tag, n, ptr(out, c_f64p)))
     return out
+
+
+def rng_slice_uniforms(seed, chain, sweep, ident, tag, n):
+    """Uniforms of one finite-bound slice update in consumption order (level, candidate 1, 32-bit candidates 2..)."""
+    out = numpy.empty(n, dtype=numpy.float64)
+    check(lib().bq_rng_slice_uniforms(seed, chain, sweep, ident, tag, n, ptr(out, c_f64p)))
+    return out
+
+
+def philox_block(ctr, key, rounds):
+    """One raw Philox4x32 block (known-answer hook)."""
+    c = (ctypes.c_uint32 * 4)(*[int(x) & 0xFFFFFFFF for x in ctr])
+    k = (ctypes.c_uint32 * 2)(*[int(x) & 0xFFFFFFFF for x in key])
+    o = (ctypes.c_uint32 * 4)()
+    check(lib().bq_philox_block(c, k, int(rounds), o))
+    return [int(x) for x in o]

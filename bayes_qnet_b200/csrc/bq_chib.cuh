@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(256) gibbs_kernel_static(const SweepArgs A, do
     for (int i = threadIdx.x; i < P; i += blockDim.x) th[i] = A.theta[(size_t)chain * P + i];
     for (int i = threadIdx.x; i < Q; i += blockDim.x) q_type[i] = A.q_type[i];
     __syncthreads();
-    if (threadIdx.x < Q) {
-        const int q = threadIdx.x, o = A.q_poff[q], dist = A.q_dist[q];
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+        const int o = A.q_poff[q], dist = A.q_dist[q];
         qconst_set(qc[q], dist, th[o], (dist == D_EXP) ? 0.0 : th[o + 1]);
     }
     const int n_sched = A.color_off[A.n_colors];

@@ -242,7 +242,7 @@ BQ_HDI double slice_finite_seq(const G &g, double x0, double lower, double upper
     if (!(logy > BQ_NEG_INF)) return x0;
     double L = lower, R = upper;
     for (int it = 0; it < 1000; ++it) {
-        const double x1 = L + (R - L) * rng.uniform();
+        const double x1 = L + (R - L) * (it == 0 ? rng.uniform() : rng.uniform32());  // bq_rng.cuh: candidate uniforms
         ++evals;
         if (g(x1) >= logy) return x1;
         if (x1 > x0) R = x1; else L = x1;

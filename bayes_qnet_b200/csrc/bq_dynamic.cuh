@@ -988,9 +988,7 @@ __device__ __forceinline__ bool group_slice(const G &g, double x0, double lower,
     double L = lower, R = upper, logy = 0.0;
     for (int cbase = 0;; cbase += W) {
         const unsigned int cidx = (unsigned int)(cbase + gl.lane);
-        double ua, ub;
-        stream_pair(rng, cidx >> 1, ua, ub);
-        const double u = (cidx & 1u) ? ub : ua;
+        const double u = cand_uniform(rng, cidx);  // candidate cidx >= 1 (lane 0 of the first round holds x0 itself)
         double myx = x0, myL = L, myR = R;
 #pragma unroll 4
         for (int jj = (cbase == 0) ? 1 : 0; jj < W; ++jj) {

@@ -377,6 +377,13 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
             h->EF += h->q_k[q] * (h->q_off[q + 1] - h->q_off[q]);
         }
     if (h->kmax > 8) return fail(BQ_ERR_UNSUPPORTED, "more than 8 processors per queue");
+    {
+        int max_optin = 0;
+        CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+        if (4 * dyn_group_smem(h->Q, h->P) > (size_t)max_optin)
+            return fail(BQ_ERR_UNSUPPORTED, "too many queues for the dynamic-order kernels (per-chain tables of 4 chains must "
+                                            "fit the shared memory of a CTA, about 400 queues)");
+    }
     h->recS = rec_stride(h->kmax);
     h->FW = ((E + 31) & ~31) + 32;
     HostRows r0;
@@ -479,6 +486,11 @@ static int dynamic_set_rows(bq_handle *h, int lo, int hi, const double *d, bool 
     return BQ_OK;
 }
 
+// dynamic shared memory above the default 48 KB needs an explicit opt-in per kernel (networks with ~90+ queues)
+static void smem_optin(const void *fn, size_t sm) {
+    if (sm > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+}
+
 template <int W>
 static void launch_dynamic_w(bq_handle *h, const DynArgs &A) {
     const int G = h->dyn_threads / W, blocks = (h->C + G - 1) / G;
@@ -502,8 +514,10 @@ static void launch_dynamic(bq_handle *h, const DynArgs &A) {
 #endif
 #define BQ_LAUNCH_BATCH(K, MINB, MHK) \
     do { \
-        if (h->has_ps) sweep_batch_kernel<K, MINB, MHK, true><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd); \
-        else sweep_batch_kernel<K, MINB, MHK, false><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd); \
+        if (h->has_ps) { smem_optin((const void *)sweep_batch_kernel<K, MINB, MHK, true>, sm); \
+            sweep_batch_kernel<K, MINB, MHK, true><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd); } \
+        else { smem_optin((const void *)sweep_batch_kernel<K, MINB, MHK, false>, sm); \
+            sweep_batch_kernel<K, MINB, MHK, false><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd); } \
     } while (0)
         const bool mh = (A.mode == MODE_MH);
         if (h->kmax <= 4) {
@@ -951,6 +965,8 @@ static int eval_hook(bq_handle *h, int32_t chain, int32_t eid, const double *x, 
         const size_t sm = dyn_group_smem(h->Q, h->P);
         const int e1 = h->next_byt[eid];
         const DynRec rec = {eid, e1, h->qid[eid], e1 >= 0 ? h->qid[e1] : -1};
+        smem_optin((const void *)logcond_dynamic_kernel<4>, sm);
+        smem_optin((const void *)logcond_dynamic_kernel<8>, sm);
         if (h->kmax <= 4)
             logcond_dynamic_kernel<4><<<1, 32, sm, h->stream>>>(D, chain, rec, h->d_scratch, n, h->d_scratch + n, what);
         else
@@ -985,6 +1001,7 @@ static int run_report(bq_handle *h, double *logp_host, double *ss_host) {
     if (!h->static_order) {
         DynArgs D;
         fill_dyn_args(h, D);
+        smem_optin((const void *)report_dynamic_kernel, 4 * dyn_group_smem(h->Q, h->P));
         report_dynamic_kernel<<<(h->C + 3) / 4, 128, 4 * dyn_group_smem(h->Q, h->P), h->stream>>>(D, d_lp, d_ss);
     } else {
         SweepArgs A;
@@ -1032,11 +1049,18 @@ static int gibbs_kernel_dynamic_path(bq_handle *h, const double *d_to, int32_t n
     }
     double *to = nullptr, *res = nullptr;
     unsigned char *done = nullptr;
+    bool dirty = false;  // the kernel has (possibly) overwritten the live arrays and they are not restored yet
     auto cleanup = [&]() {
+        if (dirty) {  // error after the launch: put the chains back before the copies go (best effort)
+            cudaGetLastError();
+            for (auto &sv : saved)
+                if (sv.copy) cudaMemcpyAsync(sv.dev, sv.copy, sv.bytes, cudaMemcpyDeviceToDevice, h->stream);
+            cudaStreamSynchronize(h->stream);
+        }
         for (auto &sv : saved) cudaFree(sv.copy);
         cudaFree(to); cudaFree(res); cudaFree(done);
     };
-#define CKG(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(BQ_ERR_CUDA, cudaGetErrorString(e_)); } } while (0)
+#define CKG(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::string m_ = cudaGetErrorString(e_); cleanup(); return fail(BQ_ERR_CUDA, m_); } } while (0)
     for (auto &sv : saved) {
         CKG(cudaMalloc(&sv.copy, sv.bytes));
         CKG(cudaMemcpyAsync(sv.copy, sv.dev, sv.bytes, cudaMemcpyDeviceToDevice, h->stream));
@@ -1051,12 +1075,16 @@ static int gibbs_kernel_dynamic_path(bq_handle *h, const double *d_to, int32_t n
     const int G = 4;
     const size_t sm = (size_t)G * dyn_group_smem(h->Q, h->P);
     const unsigned blocks = (unsigned)((C + G - 1) / G);
+    smem_optin((const void *)gibbs_kernel_dynamic<4>, sm);
+    smem_optin((const void *)gibbs_kernel_dynamic<8>, sm);
     if (h->kmax <= 4) gibbs_kernel_dynamic<4><<<blocks, 32 * G, sm, h->stream>>>(D, to, n_to, strict ? 1 : 0, done, res);
     else gibbs_kernel_dynamic<8><<<blocks, 32 * G, sm, h->stream>>>(D, to, n_to, strict ? 1 : 0, done, res);
+    dirty = true;
     CKG(cudaGetLastError());
     for (auto &sv : saved) CKG(cudaMemcpyAsync(sv.dev, sv.copy, sv.bytes, cudaMemcpyDeviceToDevice, h->stream));
     CKG(cudaMemcpyAsync(out, res, C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CKG(cudaStreamSynchronize(h->stream));
+    dirty = false;
 #undef CKG
     cleanup();
     h->n_launches += 1;
@@ -1188,6 +1216,23 @@ extern "C" int bq_rng_uniforms(uint64_t seed, int64_t chain, uint32_t sweep, uin
     Rng r;
     r.init(seed, (uint64_t)chain, sweep, id, tag);
     for (int i = 0; i < n; ++i) out[i] = r.uniform();
+    return BQ_OK;
+}
+
+extern "C" int bq_rng_slice_uniforms(uint64_t seed, int64_t chain, uint32_t sweep, uint32_t id, uint32_t tag,
+                                     int32_t n, double *out) {
+    if (!out || n < 0) return fail(BQ_ERR_INVALID, "bad argument");
+    Rng r;
+    r.init(seed, (uint64_t)chain, sweep, id, tag);
+    for (int i = 0; i < n; ++i) out[i] = (i < 2) ? r.uniform() : r.uniform32();
+    return BQ_OK;
+}
+
+extern "C" int bq_philox_block(const uint32_t ctr[4], const uint32_t key[2], int32_t rounds, uint32_t out[4]) {
+    if (!ctr || !key || !out) return fail(BQ_ERR_INVALID, "null argument");
+    if (rounds == 7) philox4x32<7>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+    else if (rounds == 10) philox4x32<10>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+    else return fail(BQ_ERR_INVALID, "bq_philox_block: rounds must be 7 or 10");
     return BQ_OK;
 }
 

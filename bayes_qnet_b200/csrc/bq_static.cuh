@@ -124,26 +124,6 @@ __device__ __forceinline__ void cond_load(Cond &c, const SchedRec &r, const doub
     c.flo = flo; c.fhi = fhi;
 }
 
-// sampling._slice with finite bounds (sampling.pyx:283-298, 344-366): no stepping out, shrink on
-// rejection.  Deviation, documented in DESIGN.md: when the bracket collapses below 1e-10 the reference
-// returns L (sampling.pyx:360-362), which may lie outside the support and poison the chain; we keep x0.
-__device__ __forceinline__ double slice_update(const Cond &c, double x0, double L, double R, Rng &rng,
-                                               int &evals, int &stuck) {
-    double g0 = c.eval(x0);
-    ++evals;
-    double logy = g0 - (-log(1.0 - rng.uniform()));  // rk_exponential: -log(1 - U)   (cdist.c:107-110)
-    if (!(logy > BQ_NEG_INF)) { ++stuck; return x0; }  // point mass guard (sampling.pyx:289-291)
-    for (int it = 0; it < BQ_SLICE_MAX_ITERS; ++it) {
-        double x1 = L + (R - L) * rng.uniform();
-        ++evals;
-        if (c.eval(x1) >= logy) return x1;
-        if (x1 > x0) R = x1; else L = x1;
-        if (R - L < 1e-10) { ++stuck; return x0; }
-    }
-    ++stuck;
-    return x0;
-}
-
 // All-exponential networks (the paper's M/M/1 tiers): lpdf(s) = -log(mu) - s/mu, so up to a constant
 // that cancels in every slice comparison G(d) is a sum of three linear pieces -- evaluated branch-free.
 struct CondExp {
@@ -187,7 +167,7 @@ struct CondGen : Cond {
 };
 
 #ifndef BQ_CAND
-#define BQ_CAND 4  // candidates per trip (even)
+#define BQ_CAND 4  // candidates per trip (a multiple of 4: one Philox block feeds four)
 #endif
 #ifndef BQ_REFILL_THRESH
 #define BQ_REFILL_THRESH 20
@@ -202,7 +182,7 @@ struct CondGen : Cond {
 // Two 53-bit uniforms of block `blk` of the (chain, sweep, event) stream.
 __device__ __forceinline__ void stream_pair(const Rng &r, unsigned int blk, double &ua, double &ub) {
     uint32_t o[4];
-    philox4x32_10(blk, r.c1, r.c2, r.c3, r.k0, r.k1, o);
+    philox4x32(blk, r.c1, r.c2, r.c3, r.k0, r.k1, o);
     ua = u53(o[0], o[1]);
     ub = u53(o[2], o[3]);
 }
@@ -264,7 +244,7 @@ __device__ __forceinline__ void run_class(const SweepArgs &A, double *d, const i
             if (exhausted) break;
             continue;
         }
-        // BQ_CAND shrink steps of sampling._slice (sampling.pyx:344-364) per trip, BQ_CAND/2 Philox blocks.
+        // BQ_CAND shrink steps of sampling._slice (sampling.pyx:344-364) per trip, BQ_CAND/4 Philox blocks.
         // A candidate's position depends on where the earlier ones fell, never on their densities, so all
         // positions are known up front and the densities are evaluated side by side (instruction-level
         // parallelism for a latency-bound loop); the first accepted one in order wins, which is exactly the
@@ -272,7 +252,11 @@ __device__ __forceinline__ void run_class(const SweepArgs &A, double *d, const i
         // predicated.
         double u[BQ_CAND], x[BQ_CAND], La[BQ_CAND], Ra[BQ_CAND];
 #pragma unroll
-        for (int b = 0; b < BQ_CAND / 2; ++b) stream_pair(rng, blk + (unsigned)b, u[2 * b], u[2 * b + 1]);
+        for (int b = 0; b < BQ_CAND / 4; ++b) {  // four 32-bit candidate uniforms per Philox block (bq_rng.cuh)
+            uint32_t o[4];
+            philox4x32(blk + (unsigned)b, rng.c1, rng.c2, rng.c3, rng.k0, rng.k1, o);
+            u[4 * b] = u32(o[0]); u[4 * b + 1] = u32(o[1]); u[4 * b + 2] = u32(o[2]); u[4 * b + 3] = u32(o[3]);
+        }
         {
             double Lk = L, Rk = R;
 #pragma unroll
@@ -309,7 +293,7 @@ __device__ __forceinline__ void run_class(const SweepArgs &A, double *d, const i
             active = going;
         }
         L = La[BQ_CAND - 1]; R = Ra[BQ_CAND - 1];
-        blk += BQ_CAND / 2;
+        blk += BQ_CAND / 4;
     }
     n_ev += nev; n_evals += ev; n_stuck += stuck;
 }
@@ -535,8 +519,8 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
         }
     }
     __syncthreads();
-    if (threadIdx.x < Q) {
-        int q = threadIdx.x, o = q_poff[q];
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {  // Q may exceed the CTA (bq_create takes up to 1024 queues)
+        const int o = q_poff[q];
         qconst_set(qc[q], q_dist[q], th[o], (q_dist[q] == D_EXP) ? 0.0 : th[o + 1]);
     }
     __syncthreads();
@@ -575,13 +559,12 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
         if (A.update != UPD_NONE || trace) {
             chain_suffstats(A, d, q_type, q_dist, qc, ss, scratch, red_out, trace, &logp_sh);
             const size_t recno = (size_t)(A.trace_base + sw);
-            if (trace && threadIdx.x < Q) {
-                int q = threadIdx.x;
-                A.tr_wait[(recno * A.n_chains + chain) * Q + q] = (ss[q].nall > 0.0) ? ss[q].wait / ss[q].nall : 0.0;
-            }
+            if (trace)
+                for (int q = threadIdx.x; q < Q; q += blockDim.x)
+                    A.tr_wait[(recno * A.n_chains + chain) * Q + q] = (ss[q].nall > 0.0) ? ss[q].wait / ss[q].nall : 0.0;
             if (trace && threadIdx.x == 0) A.tr_logp[recno * A.n_chains + chain] = logp_sh;
-            if (A.update != UPD_NONE && threadIdx.x < Q) {
-                int q = threadIdx.x, o = q_poff[q], dist = q_dist[q];
+            for (int q = threadIdx.x; A.update != UPD_NONE && q < Q; q += blockDim.x) {
+                const int o = q_poff[q], dist = q_dist[q];
                 double p0 = th[o], p1 = (dist == D_EXP) ? 0.0 : th[o + 1];
                 if (A.update == UPD_BAYES) {
                     Rng rng;

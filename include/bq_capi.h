@@ -181,12 +181,20 @@ int bq_get_sequential_order(bq_handle *h, int32_t *n_eligible, int32_t *order);
  * bq_get_schedule for static-order networks, the sequential order otherwise. */
 int bq_get_mh_order(bq_handle *h, int32_t *n_eligible, int32_t *order);
 
-/* Raw counter-based RNG stream (Philox4x32-10) exactly as the kernels consume it: n uniforms in [0,1)
- * for (seed, global chain id, sweep index, event or queue id, stream tag: 1 slice, 2 parameters, 3/4 the two slice
- * steps of an MH proposal, 5 MH accept + re-initialisation).
+/* Raw counter-based RNG stream (Philox4x32 with SEVEN rounds, csrc/bq_rng.cuh) exactly as the kernels consume it:
+ * n 53-bit uniforms in [0,1), two per block, for (seed, global chain id, sweep index, event or queue id, stream tag:
+ * 1 slice, 2 parameters, 3/4 the two slice steps of an MH proposal, 5 MH accept + re-initialisation).
  * Pure host function, needs no device.  Replaces rk_double (randomkit.c:264). */
 int bq_rng_uniforms(uint64_t seed, int64_t chain, uint32_t sweep, uint32_t id, uint32_t tag, int32_t n,
                     double *out);
+/* The uniforms of one finite-bound slice update (sampling._slice, sampling.pyx:283-298, 344-366) in the order it
+ * consumes them: out[0] the slice level's uniform and out[1] the first shrink candidate (block 0, 53 bits each), then
+ * out[c], c >= 2, candidate c from one 32-bit word, (word + 0.5) 2^-32, four per block.  Same stream keys as above. */
+int bq_rng_slice_uniforms(uint64_t seed, int64_t chain, uint32_t sweep, uint32_t id, uint32_t tag, int32_t n,
+                          double *out);
+/* One raw Philox4x32 block with `rounds` rounds (7 = what the kernels run, 10 = the customary count): the hook the
+ * known-answer test against the Random123 vectors goes through. */
+int bq_philox_block(const uint32_t ctr[4], const uint32_t key[2], int32_t rounds, uint32_t out[4]);
 
 /* Launch geometry the handle chose: threads per CTA, dynamic shared memory per CTA, and whether the
  * chain state is staged in shared memory for the whole launch. */

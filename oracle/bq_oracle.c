@@ -30,8 +30,9 @@
  * Random numbers: the reference draws from a global MT19937 (randomkit.c); stream parity is not a goal
  * (SURVEY.md section 8a).  So that whole sweeps can be compared with the kernels, this file restates the
  * product's documented stream convention (Philox4x32-7, Salmon et al. 2011; counter = (block, id, sweep,
- * chain lo), key = (seed lo ^ tag*0x9E3779B9, seed hi ^ chain hi); two 53-bit uniforms per block) -- the
- * convention is part of the C-ABI contract (include/bq_capi.h: bq_rng_uniforms).
+ * chain lo), key = (seed lo ^ tag*0x9E3779B9, seed hi ^ chain hi); two 53-bit uniforms per block; in a finite-bound
+ * slice update block 0 = level + first candidate, every later block = four candidates from one 32-bit word each) --
+ * the convention is part of the C-ABI contract (include/bq_capi.h: bq_rng_uniforms, bq_rng_slice_uniforms).
  *
  * Documented deviation shared with the product: when the slice bracket collapses below 1e-10 the reference
  * returns L (sampling.pyx:360-362), which can lie outside the support; both implementations keep x0.
@@ -279,21 +280,29 @@ void bqo_apply(bqo_state *st, int e, double x) {
 /* ---------------------------------------------------------------------------------------------- */
 /* counter-based RNG: the C-ABI's documented stream convention (see header comment)                 */
 /* ---------------------------------------------------------------------------------------------- */
-typedef struct { uint32_t k0, k1, c1, c2, c3, blk; double spare; int has; } bqo_rng;
+typedef struct { uint32_t k0, k1, c1, c2, c3, blk; double spare; int has; uint32_t w[4]; int nw; } bqo_rng;
 
-static void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
+static void philox_r(uint32_t c[4], uint32_t k0, uint32_t k1, int rounds) {
     int r;
-    for (r = 0; r < 7; ++r) { /* Philox4x32-7 */
+    for (r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
         c[0] = n0; c[1] = (uint32_t)p1; c[2] = n2; c[3] = (uint32_t)p0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 }
+static void philox(uint32_t c[4], uint32_t k0, uint32_t k1) { philox_r(c, k0, k1, 7); } /* Philox4x32-7 */
+/* one raw block with a chosen round count: known-answer tests against the Random123 vectors */
+void bqo_philox_block(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]) {
+    uint32_t c[4];
+    memcpy(c, ctr, sizeof(c));
+    philox_r(c, key[0], key[1], rounds);
+    memcpy(out, c, sizeof(c));
+}
 static void rng_init(bqo_rng *r, uint64_t seed, uint64_t chain, uint32_t sweep, uint32_t id, uint32_t tag) {
     r->k0 = (uint32_t)seed ^ (tag * 0x9E3779B9u);
     r->k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(chain >> 32);
-    r->c1 = id; r->c2 = sweep; r->c3 = (uint32_t)chain; r->blk = 0; r->has = 0; r->spare = 0.0;
+    r->c1 = id; r->c2 = sweep; r->c3 = (uint32_t)chain; r->blk = 0; r->has = 0; r->spare = 0.0; r->nw = 0;
 }
 static double to_u53(uint32_t lo, uint32_t hi) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
@@ -308,6 +317,18 @@ static double rng_uniform(bqo_rng *r) {
     r->has = 1;
     return to_u53(c[0], c[1]);
 }
+/* 32-bit uniform in (0,1), four per block: shrink candidates 2, 3, ... of a finite-bound slice update */
+static double rng_uniform32(bqo_rng *r) {
+    uint32_t v;
+    if (r->nw == 0) {
+        r->w[0] = r->blk++; r->w[1] = r->c1; r->w[2] = r->c2; r->w[3] = r->c3;
+        philox(r->w, r->k0, r->k1);
+        r->nw = 4;
+    }
+    v = r->w[4 - r->nw];
+    r->nw--;
+    return ((double)v + 0.5) * (1.0 / 4294967296.0);
+}
 static uint32_t rng_word(bqo_rng *r) {
     uint32_t c[4];
     c[0] = r->blk++; c[1] = r->c1; c[2] = r->c2; c[3] = r->c3;
@@ -319,6 +340,14 @@ void bqo_rng_uniforms(uint64_t seed, int64_t chain, uint32_t sweep, uint32_t id,
     int i;
     rng_init(&r, seed, (uint64_t)chain, sweep, id, tag);
     for (i = 0; i < n; ++i) out[i] = rng_uniform(&r);
+}
+
+void bqo_rng_slice_uniforms(uint64_t seed, int64_t chain, uint32_t sweep, uint32_t id, uint32_t tag, int n,
+                            double *out) {
+    bqo_rng r;
+    int i;
+    rng_init(&r, seed, (uint64_t)chain, sweep, id, tag);
+    for (i = 0; i < n; ++i) out[i] = (i < 2) ? rng_uniform(&r) : rng_uniform32(&r);
 }
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -339,6 +368,7 @@ long bqo_slice_sweep(bqo_state *st, const int *order, int n_order, uint64_t seed
         int e = order[i], e1 = st->next_byt[e];
         bqo_rng rng;
         double x0, lower, upper, L, R, g0, logy, x1;
+        int ncand;
         if (!bqo_eligible(st, e)) continue;
         x0 = st->d[e];
         lower = st->a[e];
@@ -352,9 +382,9 @@ long bqo_slice_sweep(bqo_state *st, const int *order, int n_order, uint64_t seed
         ++ne;
         if (!(logy > -INFINITY)) continue;
         L = lower; R = upper; x1 = x0;
-        for (;;) {
+        for (ncand = 0;; ++ncand) {
             double g1;
-            x1 = L + (R - L) * rng_uniform(&rng);
+            x1 = L + (R - L) * (ncand == 0 ? rng_uniform(&rng) : rng_uniform32(&rng));
             g1 = bqo_logcond1(st, e, x1);
             if (evals) ++*evals;
             if (g1 >= logy) break;
@@ -428,7 +458,8 @@ static double mh_slice(const bqo_state *st, const mhprop *pr, double x0, bqo_rng
         if (R > pr->U) R = pr->U;
     }
     for (it = 0; it < 100000; ++it) {
-        double x1 = L + (R - L) * rng_uniform(rng);
+        /* finite bounds: candidate 1 from the level's block (53 bits), the rest 32-bit; stepping out: all 53-bit */
+        double x1 = L + (R - L) * ((pr->U < INFINITY && it > 0) ? rng_uniform32(rng) : rng_uniform(rng));
         ++*evals;
         if (mh_eval(st, pr, x1) >= logy) return x1;
         if (x1 > x0) R = x1; else L = x1;

@@ -58,6 +58,10 @@ def lib():
                                         ctypes.c_uint32, f64p, f64p]
         L.bqo_rng_uniforms.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint32,
                                        ctypes.c_uint32, ctypes.c_int, f64p]
+        L.bqo_philox_block.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_uint32)]
+        L.bqo_rng_slice_uniforms.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.c_uint32, ctypes.c_int, f64p]
         _lib = L
     return _lib
 
@@ -70,6 +74,20 @@ def rng_uniforms(seed, chain, sweep, ident, tag, n):
     out = numpy.empty(n)
     lib().bqo_rng_uniforms(seed, chain, sweep, ident, tag, n, out.ctypes.data_as(f64p))
     return out
+
+
+def rng_slice_uniforms(seed, chain, sweep, ident, tag, n):
+    out = numpy.empty(n)
+    lib().bqo_rng_slice_uniforms(seed, chain, sweep, ident, tag, n, out.ctypes.data_as(f64p))
+    return out
+
+
+def philox_block(ctr, key, rounds):
+    c = (ctypes.c_uint32 * 4)(*[int(x) & 0xFFFFFFFF for x in ctr])
+    k = (ctypes.c_uint32 * 2)(*[int(x) & 0xFFFFFFFF for x in key])
+    o = (ctypes.c_uint32 * 4)()
+    lib().bqo_philox_block(c, k, int(rounds), o)
+    return [int(x) for x in o]
 
 
 class OracleChain(object):

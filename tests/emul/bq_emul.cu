@@ -153,7 +153,7 @@ void bqe_apply(void *h, int e, double x) {
 }
 
 // one sweep over `order`, same stream convention as the kernels: uniform 0 of (chain, sweep, event) is the slice
-// level, uniform c >= 1 the c-th shrink candidate
+// level, uniform c >= 1 the c-th shrink candidate (c = 1 from the level's block, 53 bits; c >= 2 one 32-bit word each)
 long bqe_slice_sweep(void *h, const int *order, int n_order, uint64_t seed, int64_t chain, uint32_t sweep, double tmax) {
     Emul *m = (Emul *)h;
     long ne = 0;
@@ -172,7 +172,7 @@ long bqe_slice_sweep(void *h, const int *order, int n_order, uint64_t seed, int6
         if (!(logy > BQ_NEG_INF)) continue;
         double L = lower, R = upper, x1 = ev.x0;
         for (int it = 0; it < BQ_SLICE_MAX_ITERS; ++it) {
-            x1 = L + (R - L) * rng.uniform();
+            x1 = L + (R - L) * (it == 0 ? rng.uniform() : rng.uniform32());  // candidate uniforms, bq_rng.cuh
             m->evals++;
             if (dyn_logcond<8>(m->c, ev, x1, tc) >= logy) break;
             if (x1 > ev.x0) R = x1; else L = x1;
@@ -226,7 +226,7 @@ long bqe_mh_sweep(void *h, const int *order, int n_order, uint64_t seed, int64_t
                 if (!(logy > BQ_NEG_INF)) continue;
                 double L = pr.Lh, R = pr.Uh;
                 for (int it = 0; it < BQ_SLICE_MAX_ITERS; ++it) {
-                    const double x1 = L + (R - L) * rng.uniform();
+                    const double x1 = L + (R - L) * (it == 0 ? rng.uniform() : rng.uniform32());
                     if (pr.eval(x1) >= logy) { x_new = x1; break; }
                     if (x1 > x0) R = x1; else L = x1;
                     if (R - L < 1e-10) break;
