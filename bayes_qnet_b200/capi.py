@@ -64,6 +64,7 @@ SYMBOLS = {
     "bq_sweep": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32]),
     "bq_synchronize": (ctypes.c_int, [_H]),
     "bq_update_params": (ctypes.c_int, [_H, ctypes.c_int32]),
+    "bq_update_params_from": (ctypes.c_int, [_H, ctypes.c_int32, c_f64p, ctypes.c_int32]),
     "bq_logcond": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p, ctypes.c_int32, c_f64p]),
     "bq_mh_proposal": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p, ctypes.c_int32, c_f64p]),
     "bq_log_prob": (ctypes.c_int, [_H, c_f64p]),

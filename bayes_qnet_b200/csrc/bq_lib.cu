@@ -51,6 +51,7 @@ struct bq_handle {
     size_t smem_bytes = 0;
     // host copies
     std::vector<int> q_type, q_k, q_dist, q_poff;
+    std::vector<int> q_wide;  // FIFO queues with k >= #events, run as delay stations
     std::vector<int> qid, tid, prev_byt, next_byt, prev_byq, next_byq;
     std::vector<uint8_t> obs_a, obs_d;
     std::vector<int> color_off, order;
@@ -75,6 +76,7 @@ struct bq_handle {
     std::vector<int> q_off, q_foff, ord0;  // queue position ranges, F offsets, initial order
     std::vector<int> dyn_order;          // sweep order of the dynamic-order kernels
     bool dyn_batch = true;               // dynamic-order kernels: warp-per-chain batches (else W-lane groups, BQ_DYN_BATCH=0)
+    int order_stride = 0;                // batch order: 0 = lanes 1/32 of the queue apart; r > 0 = windows of 32 r events
     int *d_claim = nullptr, *d_claimd = nullptr;
     bool mh_dynamic = false;             // static-order handle: run MH sweeps in the dynamic-order kernel (BQ_MH_DYNAMIC)
     bool dyn_ready = false;              // dynamic arrays allocated
@@ -346,21 +348,38 @@ static int build_sequential_order(bq_handle *h) {
     }
     h->dyn_order.clear();
     if (const char *env = getenv("BQ_DYN_BATCH")) h->dyn_batch = (env[0] != '0');
-    if (!h->dyn_batch) {
+    bool batch_order = h->dyn_batch;
+    if (const char *env = getenv("BQ_DYN_ORDER")) batch_order = (env[0] == 'b');  // "batch" | "seq": test hook, so that
+    if (!batch_order) {                                                            // both kernels can walk one order
         for (int p = 0; p < E; ++p)
             if (eligible(h, h->ord0[p])) h->dyn_order.push_back(h->ord0[p]);
         return BQ_OK;
     }
     // batch kernel: each queue's eligible events interleaved with a stride of 1/32 of the queue, so that any 32
     // consecutive events of the order are far apart in their queue (and rarely touch each other's neighbourhoods)
+    // BQ_ORDER_STRIDE = r > 0: windows of 32 r consecutive eligible events, interleaved with stride r INSIDE the window,
+    // so the 32 lanes of a round work r positions apart and stay in one window of the queue for r rounds (their
+    // records share cache lines and stay in L1 / L2 between rounds); 0 = stride of 1/32 of the whole queue.
+    int win_stride = h->order_stride;
+    if (const char *env = getenv("BQ_ORDER_STRIDE")) win_stride = atoi(env);
     std::vector<int> lst;
     for (int q = 0; q < Q; ++q) {
         lst.clear();
         for (int p = h->q_off[q]; p < h->q_off[q + 1]; ++p)
             if (eligible(h, h->ord0[p])) lst.push_back(h->ord0[p]);
-        const int n = (int)lst.size(), st = (n + 31) / 32;
-        for (int r = 0; r < st; ++r)
-            for (int i = r; i < n; i += st) h->dyn_order.push_back(lst[i]);
+        const int n = (int)lst.size();
+        if (win_stride <= 0) {
+            const int st = (n + 31) / 32;
+            for (int r = 0; r < st; ++r)
+                for (int i = r; i < n; i += st) h->dyn_order.push_back(lst[i]);
+        } else {
+            const int win = 32 * win_stride;
+            for (int w0 = 0; w0 < n; w0 += win) {
+                const int m = std::min(win, n - w0), st = (m + 31) / 32;
+                for (int r = 0; r < st; ++r)
+                    for (int i = r; i < m; i += st) h->dyn_order.push_back(lst[w0 + i]);
+            }
+        }
     }
     return BQ_OK;
 }
@@ -376,7 +395,9 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
             h->q_foff[q] = h->EF;
             h->EF += h->q_k[q] * (h->q_off[q + 1] - h->q_off[q]);
         }
-    if (h->kmax > 8) return fail(BQ_ERR_UNSUPPORTED, "more than 8 processors per queue");
+    if (h->kmax > 8)
+        return fail(BQ_ERR_UNSUPPORTED, "a FIFO queue with more than 8 processors and more events than processors (queues "
+                                        "with at least as many processors as events run as delay stations)");
     {
         int max_optin = 0;
         CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
@@ -584,6 +605,20 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
     h->next_byq.assign(a->next_byq, a->next_byq + E);
 
     auto bail = [&](int code, const std::string &msg) { bq_destroy(h); return fail(code, msg); };
+    // A FIFO queue with at least as many servers as it has events never makes anyone wait: min F = 0 <= a at every
+    // position, s = d - a, no diff list reaches another event -- exactly a delay station (the reference's own check:
+    // test_mh_ggk.py:778-784, DELAY == GGk(k = 100)).  Such queues run as delay stations; only `proc` is reported
+    // the GGk way (every event takes a fresh server).
+    h->q_wide.assign(Q, 0);
+    {
+        std::vector<int> cnt(Q, 0);
+        for (int e = 0; e < E; ++e)
+            if (h->qid[e] >= 0 && h->qid[e] < Q) cnt[h->qid[e]]++;
+        for (int q = 0; q < Q; ++q)
+            if (h->q_type[q] == Q_GGK && h->q_k[q] > 1 && h->q_k[q] >= cnt[q]) {
+                h->q_wide[q] = 1; h->q_type[q] = Q_DELAY; h->q_k[q] = 1;
+            }
+    }
     int pcount = 0;
     for (int q = 0; q < Q; ++q) {
         int t = h->q_type[q], dd = h->q_dist[q];
@@ -756,6 +791,16 @@ extern "C" int bq_broadcast_state(bq_handle *h, const double *d) {
     return BQ_OK;
 }
 
+// proc of the events of a "wide" FIFO queue (k >= #events, run as a delay station): the i-th event of the queue takes
+// server i -- the first arg-min of a vector that still holds a zero (queues.pyx:1518-1527)
+static void wide_procs(const bq_handle *h, int32_t *proc, size_t n_chains) {
+    for (int q = 0; q < h->Q; ++q) {
+        if (!h->q_wide[q]) continue;
+        for (size_t c = 0; c < n_chains; ++c)
+            for (int p = h->q_off[q]; p < h->q_off[q + 1]; ++p) proc[c * h->E + h->ord0[p]] = p - h->q_off[q];
+    }
+}
+
 extern "C" int bq_get_state(bq_handle *h, int32_t lo, int32_t hi, double *d, double *a, double *s,
                             int32_t *proc, int32_t *prev_byq, int32_t *next_byq) {
     if (int r = check_range(h, lo, hi)) return r;
@@ -780,6 +825,7 @@ extern "C" int bq_get_state(bq_handle *h, int32_t lo, int32_t hi, double *d, dou
             host_derive(&hn, dd + c * E, &ord[c * E], a ? a + c * E : nullptr, s ? s + c * E : nullptr,
                         proc ? proc + c * E : nullptr, prev_byq ? prev_byq + c * E : nullptr,
                         next_byq ? next_byq + c * E : nullptr, h->has_ps ? &svc[c * E] : nullptr, h->ord0.data());
+        if (proc) wide_procs(h, proc, n);
         return BQ_OK;
     }
     CK(cudaStreamSynchronize(h->stream));
@@ -799,6 +845,7 @@ extern "C" int bq_get_state(bq_handle *h, int32_t lo, int32_t hi, double *d, dou
             if (next_byq) next_byq[c * E + e] = h->next_byq[e];
         }
     }
+    if (proc) wide_procs(h, proc, n);
     return BQ_OK;
 }
 
@@ -906,6 +953,59 @@ extern "C" int bq_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t up
 extern "C" int bq_update_params(bq_handle *h, int32_t update) {
     if (update != BQ_UPD_BAYES && update != BQ_UPD_STEM) return fail(BQ_ERR_INVALID, "bad param_update");
     return launch_sweep(h, 1, BQ_MODE_SLICE, update, FLAG_PARAMS_ONLY);
+}
+
+// Parameter update from sufficient statistics supplied by the caller instead of the chains' own state: what
+// Qnet.estimate / Qnet.sample_parameters do when they are given a LIST of Arrivals (qnet.pyx:844-858, 882-896: the
+// events of all of them are pooled per queue).  One thread per (chain, queue).
+__global__ void update_from_suffstats_kernel(int C, int Q, int P, const int *q_dist, const int *q_poff, const double *ss,
+                                             int n_ss, double *theta, int update, unsigned long long seed,
+                                             long long chain_offset, unsigned int sweep, long long *stats) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= C * Q) return;
+    const int chain = t / Q, q = t % Q;
+    SuffStat st;
+    const double *src = ss + ((size_t)(n_ss > 1 ? chain : 0) * Q + q) * 8;
+    st.n = src[0]; st.sum = src[1]; st.sumlog = src[2]; st.sumsq = src[3]; st.nlog = src[4]; st.wait = src[5];
+    st.nall = src[6]; st.nzero = src[7];
+    const int o = q_poff[q], dist = q_dist[q];
+    double *th = theta + (size_t)chain * P;
+    double p0 = th[o], p1 = (dist == D_EXP) ? 0.0 : th[o + 1];
+    long long pevals = 0;
+    if (update == UPD_BAYES) {
+        Rng rng;
+        rng.init(seed, (unsigned long long)(chain_offset + chain), sweep, (unsigned int)q, TAG_PARAM);
+        sample_params(dist, st, rng, p0, p1, &pevals);
+    } else {
+        estimate_params(dist, st, p0, p1);
+    }
+    th[o] = p0;
+    if (dist != D_EXP) th[o + 1] = p1;
+    if (pevals) atomicAdd((unsigned long long *)&stats[(size_t)chain * BQ_NSTAT + 2], (unsigned long long)pevals);
+}
+
+extern "C" int bq_update_params_from(bq_handle *h, int32_t update, const double *suffstats, int32_t n_ss) {
+    if (!h || !suffstats) return fail(BQ_ERR_INVALID, "null argument");
+    if (update != BQ_UPD_BAYES && update != BQ_UPD_STEM) return fail(BQ_ERR_INVALID, "bad param_update");
+    if (n_ss != 1 && n_ss != h->C) return fail(BQ_ERR_INVALID, "n_ss must be 1 or the number of chains");
+    CK(cudaSetDevice(h->device));
+    double *d_ss = nullptr;
+    const size_t n = (size_t)n_ss * h->Q * 8;
+    CK(cudaMalloc((void **)&d_ss, n * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d_ss, suffstats, n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        const int total = h->C * h->Q;
+        update_from_suffstats_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(
+            h->C, h->Q, h->P, h->d_q_dist, h->d_q_poff, d_ss, n_ss, h->d_theta, update, h->seed, h->chain_offset,
+            h->sweep_counter, h->d_stats);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_ss);
+    if (e != cudaSuccess) return fail(BQ_ERR_CUDA, cudaGetErrorString(e));
+    h->n_launches += 1;
+    h->sweep_counter += 1;
+    return BQ_OK;
 }
 
 extern "C" int bq_synchronize(bq_handle *h) {

@@ -58,33 +58,56 @@ def last_run():
     return _last
 
 
-def _run(net, arrv, num_iter, update, n_chains, seed, device, report_fn, return_arrv, gibbs_iter=1, reverse=False):
+def _run(net, arrv, num_iter, update, n_chains, seed, device, report_fn, return_arrv, gibbs_iter=1, reverse=False,
+         burn=0, burn_report_fn=None, momentum=0):
+    """num_iter outer iterations of sweep(s) + parameter update.  Without per-iteration callbacks the whole run is
+    one kernel launch; with them every iteration is launched separately and the callbacks see what the reference's
+    see: in ``bayes`` the state after the sweep with the parameters the sweep USED (estimation.py:148-155: report_fn
+    runs before sample_parameters), in ``sem`` the state with the NEW estimate (estimation.py:65-79)."""
     global _last
     reverse = bool(reverse) and _mode() == "SLICE"  # the reference only reverses slice sweeps (estimation.py:135)
     eng = GibbsEngine(net, arrv, n_chains=n_chains, seed=seed, device=device)
     t0 = time.time()
     all_sampled = []
-    if report_fn or return_arrv or gibbs_iter != 1:
+    stepwise = bool(report_fn or burn_report_fn or return_arrv or gibbs_iter != 1 or momentum)
+    if stepwise:
+        thetas = []
+        mu_old = None
         for i in range(num_iter):
             if gibbs_iter > 1:
                 eng.sweep(gibbs_iter - 1, _mode(), "NONE", tmax_per_sweep=False, reverse=reverse)
-            eng.sweep(1, _mode(), update, trace=True, reverse=reverse)
-            if report_fn or return_arrv:
+            split = (update == "BAYES") and bool(report_fn or return_arrv)
+            eng.sweep(1, _mode(), "NONE" if split else update, trace=True, reverse=reverse)
+            if update == "STEM" and momentum > 0 and mu_old is not None:  # estimation.py:64-66
+                eng.set_params(momentum * mu_old + (1.0 - momentum) * eng.params())
+            if not split:
+                net.parameters = list(eng.params(0, 1)[0])
+            cb = report_fn if i >= burn else burn_report_fn
+            if cb or (return_arrv and i >= burn):
                 snap = eng.to_arrivals(0)
-                if report_fn:
-                    report_fn(net, snap, i, float(eng.traces()[2][-1, 0]))
-                if return_arrv:
+                if cb is report_fn and cb:
+                    cb(net, snap, i, float(eng.traces()[2][-1, 0]))
+                elif cb:
+                    cb(net, snap, i)  # burn_report_fn takes no log-prob (estimation.py:79)
+                if return_arrv and i >= burn:
                     all_sampled.append(snap)
+            if split:  # posterior draw after the callback, as the reference orders them
+                _qnet.capi_update_only(eng, "BAYES")
+                net.parameters = list(eng.params(0, 1)[0])
+            mu_old = eng.params()
+            thetas.append(mu_old)
+        _, mw, lp = eng.traces()
+        theta = numpy.stack(thetas) if thetas else numpy.empty((0, n_chains, eng.P))
     else:
         eng.sweep(num_iter, _mode(), update, trace=True, reverse=reverse)
-    theta, mw, lp = eng.traces()
+        theta, mw, lp = eng.traces()
     secs = time.time() - t0
     eng.write_back(arrv, 0)
     net.parameters = list(eng.params(0, 1)[0])
     st = eng.stats()
     _qnet._absorb(dict(nevents=0, nreject=0, num_diff=0, diff_len=0), st)
-    _last = Run(eng, theta, mw, lp, secs)
-    mus = [list(theta[i, 0, :]) for i in range(theta.shape[0])]
+    _last = Run(eng, theta[burn:], mw[burn:], lp[burn:], secs)
+    mus = [list(theta[i, 0, :]) for i in range(burn, theta.shape[0])]
     if not return_arrv:
         all_sampled = [arrv]
     return mus, all_sampled
@@ -108,14 +131,15 @@ def _logsumexp(v):
     return float(m + numpy.log(numpy.sum(numpy.exp(v - m))))
 
 
-def chib_evidence(net, obs, M_special=100, M=100, debug=False, seed=None, device=0, strict=True):
+def chib_evidence(net, obs, M_special=100, M=100, debug=False, seed=None, device=0, strict=False):
     """Chib's estimate of the log evidence log p(observed) with the Murray-Salakhutdinov correction
     (estimation.py:274-330): p(v) = p(v, h*, theta*) / p(h*, theta* | v), the denominator averaged over a forward and
     a backward (reverse-scan) chain started at the special state of the transition densities
     Qnet.gibbs_kernel + Qnet.parameter_kernel into it.  Slice sampler only.
-    strict (default): an event whose target lies outside its support when its turn comes makes the transition
-    impossible (density 0) -- the reference instead retries such events after the others (qnet.pyx:756-805), which
-    is not the density of the sweep and biases the estimate (tests/test_gpu_chib.py); strict=False reproduces it."""
+    strict=False (default) is the reference's transition density: events whose target lies outside their support
+    when their turn comes are retried after the others (qnet.pyx:756-805).  That is not the density of the sweep
+    itself and biases the estimate by 0.15-0.25 nats on the reference's own closed-form check (tests/test_gpu_chib.py);
+    strict=True makes such a transition impossible (density 0), with which Chib's identity holds."""
     if _mode() != "SLICE":
         raise NotImplementedError("chib_evidence with the MH sampler")
     net.estimate(obs)
@@ -159,13 +183,13 @@ def chib_evidence(net, obs, M_special=100, M=100, debug=False, seed=None, device
 
 def sem(net, arrv, burn, num_iter, gibbs_iter=1, momentum=0, return_arrv=False, report_fn=None,
         burn_report_fn=None, debug=False, n_chains=1, seed=None, device=0):
-    """Stochastic EM (estimation.py:29-100)."""
-    if momentum:
-        raise NotImplementedError("momentum in sem()")
+    """Stochastic EM (estimation.py:29-100): burn + num_iter iterations of gibbs_iter sweeps followed by the ML
+    update, optionally damped -- theta <- momentum * theta_old + (1 - momentum) * theta_ML (estimation.py:64-66).
+    report_fn(net, arrv, i, lp) runs after every post-burn iteration, burn_report_fn(net, arrv, i) before that."""
     _qnet.reset_stats()
     net.estimate(arrv)
-    mus, arrvl = _run(net, arrv, burn + num_iter, "STEM", n_chains, seed, device, None, return_arrv, gibbs_iter)
-    return mus[burn:], (arrvl[burn:] if return_arrv else arrvl)
+    return _run(net, arrv, burn + num_iter, "STEM", n_chains, seed, device, report_fn, return_arrv, gibbs_iter,
+                burn=burn, burn_report_fn=burn_report_fn, momentum=float(momentum))
 
 
 def sample_departures(net, arrv, num_iter, report_fn=None, debug=False, n_chains=1, seed=None, device=0):

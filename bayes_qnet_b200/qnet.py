@@ -181,13 +181,21 @@ class Qnet(object):
         return GibbsEngine(self, arrv, n_chains=n_chains, seed=seed, device=device, chain_offset=chain_offset)
 
     def _engine_for(self, arrv):
-        """The single-chain engine behind the in-place reference API, cached per Arrivals object."""
-        eng = self._engines.get(arrv)
-        if eng is None or eng.E != arrv.num_events():
+        """The single-chain engine behind the in-place reference API, cached per Arrivals object and rebuilt when
+        the structure the engine froze at creation (observation flags, task and queue links, queue membership)
+        has changed since."""
+        soa = arrv.soa()
+        fp = _fingerprint(soa)
+        hit = self._engines.get(arrv)
+        if hit is None or hit[1] != fp:
+            if hit is not None:
+                hit[0].close()
             eng = GibbsEngine(self, arrv, n_chains=1)
-            self._engines[arrv] = eng
+            eng.arrv = weakref.proxy(arrv)  # no strong reference: the engine (and its GPU memory) goes with the Arrivals
+            self._engines[arrv] = (eng, fp)
         else:
-            eng.set_state(arrv.soa()["d"])
+            eng = hit[0]
+            eng.set_state(soa["d"])
         eng.set_params(self.parameters)
         return eng
 
@@ -242,10 +250,20 @@ class Qnet(object):
     def _update_parameters(self, arrvl, update):
         if isinstance(arrvl, _arrivals.Arrivals):
             arrvl = [arrvl]
-        if len(arrvl) != 1:
-            raise NotImplementedError("parameter updates from several Arrivals at once")
-        eng = self._engine_for(arrvl[0])
-        capi_update_only(eng, update)
+        if len(arrvl) == 0:
+            raise ValueError("no Arrivals given")
+        if len(arrvl) == 1:
+            eng = self._engine_for(arrvl[0])
+            capi_update_only(eng, update)
+        else:
+            # several Arrivals: the events of all of them are pooled per queue (qnet.pyx:844-858, 882-896); the
+            # per-Arrivals sufficient statistics come from the GPU, their sum goes back for the update
+            from . import capi
+            parts = [self._engine_for(a).suffstats()[0] for a in arrvl]  # each [Q, 8]
+            pooled = pool_suffstats(parts)
+            eng = self._engine_for(arrvl[0])
+            capi.check(eng._L.bq_update_params_from(eng._h, {"BAYES": capi.BQ_UPD_BAYES, "STEM": capi.BQ_UPD_STEM}[update],
+                                                    capi.ptr(pooled, capi.c_f64p), 1))
         self.parameters = list(eng.params(0, 1)[0])
         return self.parameters
 
@@ -279,6 +297,31 @@ class Qnet(object):
             ret += q.service.f.parameter_kernel(list(theta_from[off:off + n]), list(theta_to[off:off + n]), s_obs)
             off += n
         return ret
+
+
+def _fingerprint(soa):
+    """Hash of everything a GibbsEngine fixes at creation."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for k in ("qid", "tid", "obs_a", "obs_d", "prev_byt", "next_byt", "prev_byq", "next_byq"):
+        h.update(numpy.ascontiguousarray(soa[k]).tobytes())
+    return h.digest()
+
+
+def pool_suffstats(parts):
+    """Sum of per-Arrivals sufficient statistics [Q, 8] (engine.SUFFSTAT_FIELDS order: n, sum, sumlog, sumsq, nlog,
+    wait, nall, nzero); the squared deviations are re-centred on the pooled mean of the logs (the reference's
+    LogNormal estimate is two-pass over the pooled list, distributions.pyx:276-299)."""
+    parts = [numpy.asarray(p, dtype=numpy.float64) for p in parts]
+    out = numpy.sum(parts, axis=0)
+    nlog = out[:, 4]
+    mean = numpy.where(nlog > 0, out[:, 2] / numpy.maximum(nlog, 1.0), 0.0)
+    sq = numpy.zeros(out.shape[0])
+    for p in parts:
+        m_i = numpy.where(p[:, 4] > 0, p[:, 2] / numpy.maximum(p[:, 4], 1.0), 0.0)
+        sq += p[:, 3] + p[:, 4] * (m_i - mean) ** 2
+    out[:, 3] = sq
+    return numpy.ascontiguousarray(out)
 
 
 def capi_update_only(eng, update):

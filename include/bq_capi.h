@@ -135,6 +135,12 @@ int bq_synchronize(bq_handle *h);
  * BQ_UPD_BAYES) or Qnet.estimate (qnet.pyx:844, BQ_UPD_STEM) as separate calls. */
 int bq_update_params(bq_handle *h, int32_t param_update);
 
+/* The same update from sufficient statistics the CALLER supplies (layout of bq_suffstats; n_ss = 1: one set for every
+ * chain, n_ss = n_chains: one per chain): Qnet.estimate / Qnet.sample_parameters given a LIST of Arrivals pool the
+ * events of all of them per queue (qnet.pyx:844-858, 882-896) -- the host adds the per-Arrivals statistics and passes
+ * the sum here. */
+int bq_update_params_from(bq_handle *h, int32_t param_update, const double *suffstats, int32_t n_ss);
+
 /* Parity hook: GGkGibbs.inner_dfun(x) - lik0 (qnet.pyx:1340-1357) for event `eid` of chain `chain`
  * at n points. */
 int bq_logcond(bq_handle *h, int32_t chain, int32_t eid, const double *x, int32_t n, double *out);

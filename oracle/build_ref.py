@@ -154,6 +154,10 @@ def patch_module(name, text):
         text = _sub(text, "def all_tasks (self): return self.byt.keys()", "def all_tasks (self): return list(self.byt.keys())")
         text = _sub(text, "        for tid in self.byt.keys():", "        for tid in list(self.byt.keys()):")
         text = text.replace(".iteritems()", ".items()").replace(".iterkeys()", ".keys()")
+        # capacity knob, default unchanged: the reference sizes its per-queue sorted arrays for at most BIG_N = 10000
+        # events per queue (arrivals.pyx:237, cninq.pyx:146-147) and raises beyond; BASELINE configs 3 and 4 have
+        # 20 000 / 50 000 events per queue, so the config-size golden vectors and CPU baselines set BQ_REF_BIG_N
+        text = _sub(text, "BIG_N = 10000\n", "import os as _os\nBIG_N = int(_os.environ.get('BQ_REF_BIG_N', '10000'))\n")
     elif name == "cninq.pyx":
         text = CMP_DEF + text
         text = _sub(text, "lst.sort(cmp_knots)", "lst.sort(%s)" % (CMP_KEY % "cmp_knots"))

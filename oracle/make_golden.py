@@ -17,6 +17,11 @@ The reference cannot travel to the GPU box, so its outputs are committed as smal
                       initial state: service parameters per iteration and per-queue mean waiting time -- the
                       statistical pin for posterior agreement.
 
+  big_<cfg>.npz       the same kind of vectors on states at BASELINE.json sizes (5 000-task 3-tier network, 20 000-task
+                      G/G/3 tandem, 50 000-task PS + delay network), after the reference's initialisation and after one
+                      reference sweep, including final events with candidates up to Tmax and far moves.  Run one at a
+                      time: --only big_qnet3_5k | big_lnk_20k | big_psdelay_50k | ...
+
 Usage: python oracle/make_golden.py [--only NAME] [--skip-post]
 """
 import argparse
@@ -30,6 +35,9 @@ import numpy
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref")
+# the reference holds at most 10 000 events per queue unless told otherwise (arrivals.pyx:237; knob added by
+# oracle/build_ref.py): the config-size states need more
+os.environ.setdefault("BQ_REF_BIG_N", "65536")
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 sys.path.insert(0, REF)
 
@@ -430,6 +438,110 @@ def do_lpdf():
         len(cases), distributions.Gamma(3.0, 0.5).lpdf(2.0)))
 
 
+# ---- states at BASELINE.json sizes ------------------------------------------------------------------------------
+# name -> (network, tasks, pct observed, initializer, seed, events on grids after init, after one reference sweep)
+BIG = {
+    "qnet3_5k": ("qnet3", 5000, 0.2, "DFN2", 13, 220, 120),      # BASELINE configs[1]
+    "lnk_5k": ("lnk", 5000, 0.2, "DFN2", 13, 220, 120),          # configs[2] network at a quarter of its size
+    "lnk_20k": ("lnk", 20000, 0.2, "DFN2", 13, 260, 140),        # configs[2]
+    "psdelay_10k": ("psdelay", 10000, 0.2, "PS", 13, 220, 120),  # configs[3] network at a fifth of its size
+    "psdelay_50k": ("psdelay", 50000, 0.2, "PS", 13, 260, 140),  # configs[3]
+}
+
+
+def big_grid(net, arrv, evts, n_events, rng):
+    """inner_dfun on grids for n_events resample-eligible events of a config-size state, chosen so that what only
+    happens at scale is covered: final events (bracket up to Tmax = 2 max d, qnet.pyx:672, 698-699), candidates far
+    from the current value (long diff lists, re-ranking of the next event by many positions), as well as near ones."""
+    elig = [i for i, e in enumerate(evts)
+            if not e.obs_d and (e.next_by_task() is None or not e.next_by_task().obs_a)]
+    finals = [i for i in elig if evts[i].next_by_task() is None]
+    others = [i for i in elig if evts[i].next_by_task() is not None]
+    rng.shuffle(finals)
+    rng.shuffle(others)
+    n_fin = min(len(finals), n_events // 3)
+    pick = sorted(finals[:n_fin] + others[:n_events - n_fin])
+    tmax = 2 * max(e.d for e in evts)
+    is_ps = any(type(q).__name__ == "QueuePS" for q in net.queues)
+    rows, xs, vals = [], [], []
+    for i in pick:
+        e = evts[i]
+        nxt = e.next_by_task()
+        lo = e.a
+        hi = nxt.d if nxt is not None else tmax
+        span = hi - lo
+        near = min(e.d - lo, hi - e.d)
+        pts = [e.d, lo + 0.03 * span, lo + 0.5 * span, lo + 0.97 * span, lo + span * rng.rand(), lo + span * rng.rand(),
+               e.d - 0.3 * near, e.d + 0.3 * near, e.d - 0.02 * near, e.d + 0.02 * near]
+        if nxt is None:  # final event: the reference's bracket reaches Tmax; also moderately far points
+            scale = max(e.d - e.a, 1e-3)
+            pts += [e.d + 5.0 * scale, e.d + 50.0 * scale, e.d + 500.0 * scale, 0.5 * (e.d + tmax), tmax * (1.0 - 1e-9)]
+        if not is_ps:  # QueuePS asserts (queues.pyx:1068) when evaluated outside [a_e, upper]
+            pts += [lo - 0.1, hi + 0.1]
+        g = numpy.array(pts)
+        dfn = qnet.GGkGibbs(net, arrv, e, 0.0).dfn()
+        with quiet():
+            v = numpy.array([dfn(float(x)) for x in g])
+        pad = 17 - len(g)
+        rows.append(i)
+        xs.append(numpy.concatenate((g, numpy.full(pad, numpy.nan))))
+        vals.append(numpy.concatenate((v, numpy.full(pad, numpy.nan))))
+    return numpy.array(rows, dtype=numpy.int32), numpy.array(xs), numpy.array(vals)
+
+
+def do_big(name):
+    """A state of BASELINE size produced by the reference (sample -> subset_by_task -> gibbs_initialize), inner_dfun
+    grids on it, one reference slice sweep, grids again.  Stored compactly: rows are task-major (each task's events in
+    visit order), a / s / proc / by-task links are derivable, the by-queue order is the order by arrival (queue 0 by
+    departure), which tests/helpers.py re-derives (checked here before saving)."""
+    netname, ntasks, pct, init, seed, n0, n1 = BIG[name]
+    t0 = time.time()
+    net = qnetu.qnet_from_text(NETS[netname])
+    qnetu.set_seed(seed)
+    with quiet():
+        qnet.set_initialization_type(init)
+        smp = net.sample(ntasks)
+        sub = smp.subset_by_task(pct)
+        ini = net.gibbs_initialize(sub)
+        qnet.set_initialization_type("DFN2")
+    ini.validate()
+    print("big_%s: reference init of %d tasks took %.0f s" % (name, ntasks, time.time() - t0), flush=True)
+    rng = numpy.random.RandomState(seed + 7000)
+    out = dict(yaml=NETS[netname], theta=numpy.array(net.parameters, dtype=numpy.float64))
+    arrv = ini
+    for tag, n_ev in (("s0", n0), ("s1", n1)):
+        flat, evts = flatten(arrv)
+        if tag == "s0":
+            for k in ("tid", "qid", "state", "obs_a", "obs_d", "eid"):
+                out[k] = flat[k]
+        # the by-queue order must be derivable from the times (no ties inside a queue but queue 0's zero arrivals)
+        for q in range(len(net.queues)):
+            rws = numpy.flatnonzero(flat["qid"] == q)
+            if type(net.queues[q]).__name__ in ("QueuePS", "DelayStation") and tag == "s1":
+                continue  # the reference never relinks a PS queue or a delay station (queues.pyx:1149-1183, 745-784)
+            key = flat["d"][rws] if q == 0 else flat["a"][rws]
+            order = rws[numpy.argsort(key, kind="stable")]
+            assert numpy.all(flat["prev_byq"][order[1:]] == order[:-1]), "queue %d is not in arrival order" % q
+        t1 = time.time()
+        rows, xs, vals = big_grid(net, arrv, evts, n_ev, rng)
+        out[tag + "_d"] = flat["d"]
+        out.update({tag + "_rows": rows, tag + "_x": xs, tag + "_g": vals, tag + "_logprob": net.log_prob(arrv)})
+        print("big_%s %s: %d events on grids (%d final) in %.0f s" % (
+            name, tag, len(rows), sum(1 for i in rows if evts[i].next_by_task() is None), time.time() - t1), flush=True)
+        if tag == "s0":
+            t1 = time.time()
+            qnet.reset_stats()
+            with quiet():
+                net.slice_resample(arrv, 1)
+            dt = time.time() - t1
+            arrv.validate()
+            out["ref_sweep_seconds"] = dt
+            out["ref_sweep_resamples"] = qnet.stats()["nevents"]
+            print("big_%s: one reference sweep: %d resamples in %.0f s" % (name, qnet.stats()["nevents"], dt), flush=True)
+    numpy.savez_compressed(os.path.join(OUT, "big_%s.npz" % name), **out)
+    print("big_%s: E=%d written (%.1f MB)" % (name, len(out["s0_d"]), os.path.getsize(os.path.join(OUT, "big_%s.npz" % name)) / 1e6))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -438,6 +550,9 @@ if __name__ == "__main__":
     ap.add_argument("--skip-mh", action="store_true")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
+    if args.only and args.only.startswith("big_"):
+        do_big(args.only[4:])
+        sys.exit(0)
     if args.only in (None, "lpdf"):
         do_lpdf()
     if not args.skip_cond:

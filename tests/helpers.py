@@ -66,6 +66,42 @@ def golden_state(g, prefix, theta=None):
     return net, arrv
 
 
+BIG = ["qnet3_5k", "lnk_5k", "lnk_20k", "psdelay_10k", "psdelay_50k"]  # tests/golden/big_*.npz (oracle/make_golden.py)
+
+
+def big_state(g, tag, theta=None):
+    """(net, arrv) from a config-size state of the reference (compact fixture: rows task-major in visit order, arrivals
+    and by-task links implied, by-queue order = order by arrival, queue 0 by departure)."""
+    net = qnetu.qnet_from_text(str(g["yaml"]))
+    net.parameters = list(g["theta"] if theta is None else theta)
+    d = g[tag + "_d"]
+    tid = g["tid"]
+    a = numpy.zeros_like(d)
+    same = tid[1:] == tid[:-1]
+    a[1:][same] = d[:-1][same]
+    arrv = Arrivals.from_arrays(net, tid, g["qid"], g["state"], a, d, g["obs_a"], g["obs_d"], eid=g["eid"])
+    return net, arrv
+
+
+def check_grid(fn, g, tag, tol=1e-9, rows=None):
+    """fn(row, xs) -> values, against the reference's inner_dfun grid of state `tag`: identical support, finite values
+    within tol relative.  Returns the number of finite points compared."""
+    total = 0
+    for r, xs, ref in zip(g[tag + "_rows"], g[tag + "_x"], g[tag + "_g"]):
+        if rows is not None and int(r) not in rows:
+            continue
+        keep = ~numpy.isnan(xs)
+        xs, ref = xs[keep], ref[keep]
+        v = numpy.asarray(fn(int(r), xs))
+        assert numpy.array_equal(numpy.isfinite(v), numpy.isfinite(ref)), "support differs at row %d: %r vs %r" % (r, v, ref)
+        m = numpy.isfinite(ref)
+        if m.any():
+            err = relerr(v[m], ref[m]).max()
+            assert err < tol, "row %d: relative error %g" % (r, err)
+            total += int(m.sum())
+    return total
+
+
 def oracle_chain(net, arrv, theta=None):
     return orc.OracleChain.from_arrivals(net, arrv, theta)
 

@@ -261,7 +261,8 @@ def test_full_size_invariants_dynamic(workload):
     import bench
     from bayes_qnet_b200 import qnet
     wl = bench.WORKLOADS[workload]
-    tasks = 20000
+    tasks = wl["tasks"]  # 20 000 (config 3) / 50 000 (config 4)
+    assert tasks == (20000 if workload == "config3" else 50000)
     net, ini = bench.make_input(tasks, yaml_text=wl["yaml"], init=wl["init"])
     soa = ini.soa()
     C = 64
@@ -727,7 +728,7 @@ def test_dynamic_edge_cases(batch, monkeypatch):
         finally:
             qnet.set_initialization_type(old)
     wide = str(helpers.golden("cond_mm3")["yaml"]).replace("processors: 3", "processors: 9")
-    net, smp, sub, ini = helpers.synthetic(wide, 20, 0.5, seed=1)
+    net, smp, sub, ini = helpers.synthetic(wide, 200, 0.5, seed=1)  # 9 servers, ~100 events per queue
     with pytest.raises(capi.BqError):
         GibbsEngine(net, ini, n_chains=1, seed=1)
 
