@@ -2,7 +2,7 @@
 reference's inner_dfun vectors on states of BASELINE size -- 5 000-task 3-tier network (chromatic kernel's closed
 form), G/G/3 LogNormal tandem at 5 000 / 20 000 tasks, PS + delay network at 10 000 / 50 000 tasks (position-indexed
 walks: galloping, flag scans, re-ranking), 1e-9 relative with identical support; then one full sweep of the batch
-kernel, the group kernel and the host emulation of the same walk code, bit for bit, at full size; and BASELINE
+kernel and the group kernel, bit for bit, and of the host emulation of the same walk code (to rounding), at full size; and BASELINE
 configs[0] as the reference states it (one chain, 1000 sweeps)."""
 import os
 
@@ -53,7 +53,8 @@ def test_logcond_static_global_memory_path_at_config_size(name, monkeypatch):
 def test_full_sweep_batch_group_emulation_identical(name, monkeypatch):
     """One full sweep of 4 chains from the reference's config-size state: the batch kernel (32 events of a chain per
     round, conflicts redone), the group kernel (W = 32 lanes on one event) walking the same order, and the host
-    emulation of the same walk / commit code run sequentially give the SAME departure times, bit for bit."""
+    emulation of the same walk / commit code run sequentially give the SAME departure times: the two kernels bit for bit,
+    the host run to the last-bit differences of libm vs libdevice."""
     g = _load(name)
     net, arrv = helpers.big_state(g, "s0")
     with GibbsEngine(net, arrv, n_chains=4, seed=99, chain_offset=3) as eng:
@@ -75,7 +76,9 @@ def test_full_sweep_batch_group_emulation_identical(name, monkeypatch):
         em = emul_helper.EmulChain(net, arrv)
         em.slice_sweep(order, 99, 3 + c, 0, tmax=tmax)
         assert em.check() == 0
-        assert numpy.array_equal(em.d, d_batch[c]), "chain %d differs from the host emulation" % c
+        # host libm vs device libdevice and FMA contraction differ in the last bit: 1e-12 instead of bit equality (a
+        # flipped accept decision anywhere in the sweep would show as a difference of the order of a service time)
+        assert helpers.relerr(em.d, d_batch[c]).max() < 1e-12, "chain %d differs from the host emulation" % c
 
 
 def test_config1_single_chain_1000_sweeps():

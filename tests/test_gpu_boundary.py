@@ -65,7 +65,8 @@ def test_parameter_updates_from_a_list_of_arrivals():
     """Qnet.estimate / sample_parameters given a list pool the events of all Arrivals per queue (qnet.pyx:844-896)."""
     yaml_text = helpers.MIXED["delay_gg1_gg4"]
     net, smp, sub, ini = helpers.synthetic(yaml_text, 80, 0.25, seed=21)
-    _, smp2, _, ini2 = helpers.synthetic(yaml_text, 50, 0.5, seed=22)
+    qnetu.set_seed(22)
+    ini2 = net.gibbs_initialize(net.sample(50).subset_by_task(0.5))
     theta = net.estimate([ini, ini2])
     off = 0
     for qi, q in enumerate(net.queues):
@@ -185,11 +186,10 @@ def test_gibbs_cli_stem_mode_writes_statistics(tmp_path):
     net, smp, sub, ini = helpers.synthetic(helpers.MM1, 60, 0.5, seed=2)
     netf, arrf = tmp_path / "net.yml", tmp_path / "arrv.txt"
     netf.write_text(helpers.MM1)
-    with open(arrf, "w") as f:
-        ini.write_csv(f)
+    qnetu.write_to_table(str(arrf), ini)
     env = dict(os.environ, PYTHONPATH=ROOT)
-    r = subprocess.run([sys.executable, "-m", "bayes_qnet_b200.gibbs", "--network", str(netf), "--arrivals", str(arrf),
-                        "--gibbs-iter", "6", "--burn", "2", "--statistics", "mean_wait,mean_service", "--do-init", "0",
+    r = subprocess.run([sys.executable, "-m", "bayes_qnet_b200.gibbs", "--network", str(netf), "--arrvtbl", str(arrf),
+                        "--gibbs-iter", "6", "--burn", "2", "--statistics", "mean_wait,mean_service", "--do-init", "1",
                         "--output-mu", "mu.txt", "--seed", "5"], cwd=str(tmp_path), env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     for name in ("train_mean_wait.txt", "train_mean_service.txt"):

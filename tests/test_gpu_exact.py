@@ -112,9 +112,19 @@ def test_kernels_agree_at_scale(monkeypatch):
                 if which == "batch":
                     assert st["n_redone"] < 0.2 * st["nevents"]
             runs[(which, mode)] = (th[100:], mw[100:, :, 1:])
-    ref = runs[("chromatic", "SLICE")]
-    for key, (th, mw) in runs.items():
+    # kernel against kernel for each sampler.  (MH against slice is a different question: the reference's MH step
+    # treats two slice steps on the proposal as an exact draw from it, qnet.pyx:1292-1300, so its stationary law is
+    # only approximately the slice sampler's; MH is pinned on the reference's own MH runs in test_gpu_parity.py.)
+    for mode in ("SLICE", "MH"):
+        ref = runs[("chromatic", mode)]
+        th, mw = runs[("batch", mode)]
         for ours, other, what in ((th, ref[0], "theta"), (mw, ref[1], "mean wait")):
             se = numpy.sqrt(diagnostics.mcse(ours) ** 2 + diagnostics.mcse(other) ** 2)
             z = numpy.abs(ours.mean(axis=(0, 1)) - other.mean(axis=(0, 1))) / numpy.maximum(se, 1e-12)
-            assert numpy.all(z < 4.5), (key, what, z)
+            assert numpy.all(z < 4.5), (mode, what, z)
+    # and the two samplers against each other, loosely: a gross error in either would still show
+    for what, i in (("theta", 0), ("mean wait", 1)):
+        a, b = runs[("chromatic", "SLICE")][i], runs[("chromatic", "MH")][i]
+        se = numpy.sqrt(diagnostics.mcse(a) ** 2 + diagnostics.mcse(b) ** 2)
+        z = numpy.abs(a.mean(axis=(0, 1)) - b.mean(axis=(0, 1))) / numpy.maximum(se, 1e-12)
+        assert numpy.all(z < 8.0), (what, z)
