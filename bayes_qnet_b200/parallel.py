@@ -45,3 +45,78 @@ def gather_traces(x, world=None):
 def gather_summaries(theta, mean_wait, logp):
     """Gather the three trace arrays of GibbsEngine.traces() over all ranks."""
     return gather_traces(theta), gather_traces(mean_wait), gather_traces(logp[:, :, None])[:, :, 0]
+
+
+# ---- summaries on the device: no host bounce ---------------------------------------------------------------------
+class _DeviceArray(object):
+    """A raw device pointer dressed for torch.as_tensor (CUDA array interface, fp64, C order)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def device_traces(eng):
+    """Zero-copy torch views of the engine's device-resident traces (bq_trace_dev): theta [n_rec, C, P],
+    mean_wait [n_rec, C, Q], logp [n_rec, C].  The engine must be synchronised."""
+    import torch
+    n = eng.trace_len()
+    p = eng.device_pointers()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mk = lambda ptr, shape: torch.as_tensor(_DeviceArray(ptr, shape), device=dev)
+    return (mk(p["tr_theta"], (n, eng.n_chains, eng.P)), mk(p["tr_wait"], (n, eng.n_chains, eng.Q)),
+            mk(p["tr_logp"], (n, eng.n_chains)))
+
+
+def gather_summaries_device(eng, world=None):
+    """Per-chain summaries of every rank -- the traces of the service parameters and of the per-queue mean waits
+    (source queue dropped) -- as ONE device tensor [n_rec, total chains, P + Q - 1], chains in global order:
+    ncclAllGather straight from the engines' trace buffers, no host copy."""
+    import torch
+    import torch.distributed as dist
+    th, mw, _ = device_traces(eng)
+    local = torch.cat((th, mw[:, :, 1:]), dim=2).contiguous()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    w = dist.get_world_size()
+    out = torch.empty((w,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local)  # equal chain counts per rank (bench / GibbsEngine sharding)
+    return out.permute(1, 0, 2, 3).reshape(local.shape[0], w * local.shape[1], local.shape[2])
+
+
+def device_diagnostics(x):
+    """Split R-hat over the ensemble and per-chain effective sample sizes, computed where the summaries live (any torch
+    device).  x: [n_iter, n_chains, K].  Returns small host arrays: rhat [K]; ess_per_chain_sum [K] = sum over chains of
+    the chain's own ESS (Geyer's initial positive sequence on its autocorrelation); ess_per_chain_min [K]."""
+    import torch
+    n, m, K = x.shape
+    out = {}
+    h = n // 2
+    if h >= 2:
+        halves = torch.cat((x[:h], x[h:2 * h]), dim=1)
+        cm = halves.mean(dim=0)
+        W = halves.var(dim=0, unbiased=True).mean(dim=0)
+        B = h * cm.var(dim=0, unbiased=True)
+        rhat = torch.sqrt(((h - 1.0) / h * W + B / h) / W)
+    else:
+        rhat = torch.full((K,), float("nan"), dtype=x.dtype, device=x.device)
+    out["rhat"] = rhat.cpu().numpy()
+    if n >= 4:
+        xc = x - x.mean(dim=0, keepdim=True)
+        f = torch.fft.rfft(xc, n=2 * n, dim=0)
+        ac = torch.fft.irfft(f * torch.conj(f), n=2 * n, dim=0)[:n] / n     # [n, m, K]
+        var0 = ac[0].clamp_min(1e-300)
+        rho = ac / var0
+        t2 = (n // 2) * 2
+        pairs = rho[0:t2:2] + rho[1:t2:2]                                   # [n/2, m, K]
+        alive = torch.cumprod((pairs >= 0).to(x.dtype), dim=0)
+        tau = -1.0 + 2.0 * (pairs * alive).sum(dim=0)                       # [m, K]
+        ess = n / tau.clamp_min(1.0 / max(torch.log10(torch.tensor(float(max(n, 10)))).item(), 1.0))
+        ess = torch.where(ac[0] > 0, ess, torch.zeros_like(ess))
+        out["ess_per_chain_sum"] = ess.sum(dim=0).cpu().numpy()
+        out["ess_per_chain_min"] = ess.min(dim=0).values.cpu().numpy()
+    else:
+        nan = torch.full((K,), float("nan"), dtype=x.dtype)
+        out["ess_per_chain_sum"] = nan.numpy()
+        out["ess_per_chain_min"] = nan.numpy()
+    return out

@@ -1,21 +1,27 @@
 #!/usr/bin/env python3
 """bench.py -- chain-task resamples/sec of the hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--chains C] [--tasks T] [--sweeps S]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|config3|config4] [--chains C] ...
   python bench.py --impl reference ...        # the reference's own CPU path on the host cores
+  python bench.py --workload config5 [--gpus N]   # chain-count sweep 1..65536 (strong and weak), one JSON line
 
-A "step" is S Gibbs sweeps (hidden-time slice resampling + posterior draw of the service parameters, the
-work of one estimation.bayes iteration each) of C chains per GPU on BASELINE.json configs[1]: the paper's
-3-tier web-service network, 5000 tasks (E = 20000 events), 20% of the tasks observed.  Inputs are synthetic:
-simulated, sub-sampled and initialised by the package's own host code; every chain starts from the same state.
+A "step" is S Gibbs sweeps (hidden-time slice resampling + posterior draw of the service parameters, the work of one
+estimation.bayes iteration each) of C chains per GPU.  Headline workload = BASELINE.json configs[1]: the paper's
+3-tier web-service network, 5000 tasks (E = 20000 events), 20% of the tasks observed, 1024 chains per GPU.  The
+initial state is the one the REFERENCE generated (sample -> subset_by_task -> gibbs_initialize, seed 13), committed as
+tests/golden/big_*.npz by oracle/make_golden.py, so the GPU arm and the reference arm start from the identical
+state; when a fixture is absent the package's own host code simulates and initialises one.
 
 value  = resamples of all ranks / device time of the K timed steps, chain state resident in HBM.
-e2e    = the same through the public host API with HOST buffers: initial state host->device, the sweeps,
-         and parameters + per-sweep summaries device->host inside the timed region.
-roofline.achieved = 16 B per resample (read + write of one fp64 departure time) x resamples of
-         one launch / CUDA-event duration of that launch, against the measured HBM copy bandwidth.
-Under torchrun every rank owns C chains on its GPU (weak scaling, no data-path collective); per-chain
-summaries are gathered over NCCL once per step only to report R-hat / ESS.
+e2e    = the same through the public host API with HOST buffers: initial state host->device, the sweeps, parameters
+         + per-sweep summaries device->host, and (N > 1) the NCCL all-gather of the per-chain summaries plus the
+         R-hat / ESS reductions on the device, all inside the timed region.
+roofline.achieved = algorithmic bytes per resample (16 B source / single-server / delay visits, 32 B
+         multi-server, 48 B PS) x resamples of one launch / CUDA-event duration of that launch, against the measured
+         HBM copy bandwidth.
+extra_workloads = short sub-runs of BASELINE configs[0], [2], [3] in the same process (same measurement rules), so that
+         every config has a driver-timed figure; cpu_baseline beside each.
+Under torchrun every rank owns C chains on its GPU (weak scaling, no data-path collective).
 """
 import argparse
 import json
@@ -27,7 +33,16 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+MM1 = """
+states:
+  - {name: INITIAL, queues: [INITIAL], successors: [TIER1], initial: TRUE}
+  - {name: TIER1, queues: [WEB1]}
+queues:
+  - { name: INITIAL, service: [M, 1.0] }
+  - { name: WEB1, service: [M, 0.7] }
+"""
 QNET3 = """
 states:
   - name: INITIAL
@@ -71,23 +86,35 @@ queues:
   - { name: QPS, type: PS, service: [M, 0.5] }
   - { name: QDELAY, type: DELAY, service: [M, 2.0] }
 """
-# BASELINE.json configs[1..3] (the headline is configs[1]); algorithmic bytes per resample from SURVEY.md 8d
+# BASELINE.json configs[0..3] (the headline is configs[1]); algorithmic bytes per resample from SURVEY.md 8d.
+# fixture / ref_fixture: reference-generated initial states (tests/golden/big_<name>.npz) for the GPU arm and for the
+# bounded CPU sample; ref_tasks: size of the CPU sample when no fixture applies.
 WORKLOADS = {
-    "config2": dict(yaml=QNET3, init="DFN2", tasks=5000, chains=1024, sweeps=20, ref_tasks=5000, bytes=16.0,
-                    kernel="sweep_static_kernel<true>", name="3-tier web-service network (qnet3)"),
-    "config3": dict(yaml=TANDEM3, init="DFN2", tasks=20000, chains=4096, sweeps=2, ref_tasks=1000, bytes=32.0,
-                    kernel="sweep_batch_kernel<4, 8, false, false>", name="tandem source -> G/G/3 -> G/G/3, LogNormal service"),
-    "config4": dict(yaml=PSDELAY, init="PS", tasks=50000, chains=2048, sweeps=2, ref_tasks=2000, bytes=80.0 / 3.0,
-                    kernel="sweep_batch_kernel<4, 4, false, true>", name="source -> processor sharing -> delay station (one GPU's share "
-                                                         "of the 16384 chains)"),
+    "config1": dict(yaml=MM1, init="DFN2", tasks=200, pct=0.5, chains=1, sweeps=1000, ref_tasks=200, bytes=16.0,
+                    fixture=None, ref_fixture=None, kernel="sweep_static_kernel<true, true>",
+                    name="single M/M/1 queue (configs[0])"),
+    "config2": dict(yaml=QNET3, init="DFN2", tasks=5000, pct=0.2, chains=1024, sweeps=20, ref_tasks=5000, bytes=16.0,
+                    fixture="qnet3_5k", ref_fixture="qnet3_5k", kernel="sweep_static_kernel<true, true>",
+                    name="3-tier web-service network (qnet3)"),
+    "config3": dict(yaml=TANDEM3, init="DFN2", tasks=20000, pct=0.2, chains=4096, sweeps=2, ref_tasks=1000, bytes=32.0,
+                    fixture="lnk_20k", ref_fixture=None, kernel="sweep_batch_kernel<4, 8, false, false>",
+                    name="tandem source -> G/G/3 -> G/G/3, LogNormal service"),
+    "config4": dict(yaml=PSDELAY, init="PS", tasks=50000, pct=0.2, chains=2048, sweeps=2, ref_tasks=2000, bytes=80.0 / 3.0,
+                    fixture="psdelay_50k", ref_fixture=None, kernel="sweep_batch_kernel<4, 4, false, true>",
+                    name="source -> processor sharing -> delay station (one GPU's share of the 16384 chains)"),
 }
-BYTES_PER_RESAMPLE = 16.0  # SURVEY.md 8d: source / GGk k=1 / DELAY visits
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the default configuration, from the ncu --set full
-# capture summarised in profiles/r1_static_final_ncu_full.txt (166.0 MB + 108.0 MB)
-NCU_TRAFFIC_DEFAULT = 273.98e6
-# dram read + write of one sweep_batch_kernel launch of the default config-3 step (profiles/r1_config3_dram_traffic.csv)
-NCU_TRAFFIC_CONFIG3 = 762250469376.0 + 251954478592.0
-WORKLOAD = "%s, %d tasks, 20%% observed, %d chains/GPU x %d sweeps per step"
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch, from ncu --set full captures under profiles/
+NCU_TRAFFIC = {
+    ("config2", 5000, 1024, 20): (273.98e6, "profiles/r1_static_final_ncu_full.txt (166.0 MB read + 108.0 MB written): far BELOW "
+                                            "the algorithmic 16 B x resamples because the chain state stays in shared memory "
+                                            "for all sweeps of a launch"),
+    ("config3", 20000, 4096, 2): (762250469376.0 + 251954478592.0, "profiles/r1_config3_dram_traffic.csv: 80x the algorithmic "
+                                  "32 B x resamples -- every evaluation re-reads the event's neighbourhood from HBM"),
+}
+WORKLOAD = "%s, %d tasks, %d%% observed, %d chains/GPU x %d sweeps per step"
+# measured once, offline, at the REAL size on this repository's build container (tools/ref_fullsize.py; BASELINE.md
+# section 3: "run a fixed small number of sweeps at the real size ... do not extrapolate"): profiles/r2_reference_fullsize.json
+FULLSIZE = os.path.join(ROOT, "profiles", "r2_reference_fullsize.json")
 
 
 def peaks():
@@ -154,51 +181,114 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def make_input(tasks, seed=13, yaml_text=QNET3, init="DFN2"):
+# ---------------------------------------------------------------------------------------------------------------
+# inputs
+# ---------------------------------------------------------------------------------------------------------------
+def fixture_path(name):
+    p = os.path.join(GOLDEN, "big_%s.npz" % name) if name else None
+    return p if p and os.path.exists(p) else None
+
+
+def fixture_arrays(path, tag="s0"):
+    """Flat arrays of a reference-generated state (layout of oracle/make_golden.py do_big): rows task-major in visit
+    order, arrival = departure of the task's previous event (0 for its first)."""
+    import numpy
+    g = numpy.load(path, allow_pickle=False)
+    d, tid = g[tag + "_d"], g["tid"]
+    a = numpy.zeros_like(d)
+    same = tid[1:] == tid[:-1]
+    a[1:][same] = d[:-1][same]
+    return dict(yaml=str(g["yaml"]), theta=g["theta"], tid=tid, qid=g["qid"], state=g["state"], a=a, d=d,
+                obs_a=g["obs_a"], obs_d=g["obs_d"], eid=g["eid"])
+
+
+def make_input(tasks, seed=13, yaml_text=QNET3, init="DFN2", fixture=None, pct=0.2):
+    """(net, initialised Arrivals, description).  From the reference-generated fixture when there is one of this
+    size, else simulated, sub-sampled and initialised by the package's own host code."""
     from bayes_qnet_b200 import qnet, qnetu
+    from bayes_qnet_b200.arrivals import Arrivals
+    path = fixture_path(fixture)
+    if path is not None:
+        f = fixture_arrays(path)
+        if len(set(f["tid"].tolist())) == tasks:
+            net = qnetu.qnet_from_text(f["yaml"])
+            net.parameters = list(f["theta"])
+            ini = Arrivals.from_arrays(net, f["tid"], f["qid"], f["state"], f["a"], f["d"], f["obs_a"], f["obs_d"], eid=f["eid"])
+            return net, ini, "reference-generated state tests/golden/big_%s.npz (sample -> subset_by_task -> gibbs_initialize, seed 13)" % fixture
     net = qnetu.qnet_from_text(yaml_text)
     qnetu.set_seed(seed)
     smp = net.sample(tasks)
-    sub = smp.subset_by_task(0.2)
+    sub = smp.subset_by_task(pct)
     qnet.set_initialization_type(init)
     try:
         ini = net.gibbs_initialize(sub)
     finally:
         qnet.set_initialization_type("DFN2")
-    return net, ini
+    return net, ini, "simulated, sub-sampled and initialised by the package's host code (seed %d)" % seed
 
 
-def cpu_baseline_reference(tasks, sweeps, seed=13, yaml_text=QNET3, init="DFN2"):
-    """The reference's own single-chain Cython path (oracle/_ref) on the same kind of input, one process per
-    host core, each running `sweeps` iterations of estimation.bayes; returns resamples/s summed over cores."""
-    ref = os.path.join(ROOT, "oracle", "_ref")
-    if not os.path.exists(os.path.join(ref, ".built")):
-        return None
-    ncores = os.cpu_count() or 1
-    code = r"""
-import sys, io, contextlib, time
-sys.path.insert(0, %r)
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's own CPU path (oracle/_ref), in subprocesses
+# ---------------------------------------------------------------------------------------------------------------
+REF_CODE = r"""
+import sys, io, os, contextlib, time
+os.environ.setdefault("BQ_REF_BIG_N", "65536")
+sys.path.insert(0, %(ref)r)
+import numpy
 with contextlib.redirect_stdout(io.StringIO()):
     import qnetu, qnet, sampling, estimation
     sampling.DEBUG = 0
-    net = qnetu.qnet_from_text(%r)
-    qnetu.set_seed(%d + int(sys.argv[1]))
-    qnet.set_initialization_type(%r)
-    smp = net.sample(%d); sub = smp.subset_by_task(0.2); ini = net.gibbs_initialize(sub)
+    estimation.set_sampler(%(sampler)r)
+    fixture = %(fixture)r
+    if fixture:   # the committed reference-generated state, through the reference's own table reader (qnetu.py:474)
+        g = numpy.load(fixture, allow_pickle=False)
+        d, tid = g["s0_d"], g["tid"]
+        a = numpy.zeros_like(d); same = tid[1:] == tid[:-1]; a[1:][same] = d[:-1][same]
+        lines = ["eid tid qid a d s w state proc obs_a obs_d"]
+        for i in range(len(d)):
+            lines.append("%%d %%d %%d %%r %%r 0.0 0.0 %%d 0 %%d %%d" %% (g["eid"][i], tid[i], g["qid"][i], float(a[i]), float(d[i]),
+                                                                   g["state"][i], g["obs_a"][i], g["obs_d"][i]))
+        net = qnetu.qnet_from_text(str(g["yaml"]))
+        net.parameters = list(g["theta"])
+        ini = qnetu.read_csv_from_lines(net, lines)
+        qnetu.set_seed(%(seed)d + int(sys.argv[1]))
+    else:
+        net = qnetu.qnet_from_text(%(yaml)r)
+        qnetu.set_seed(%(seed)d + int(sys.argv[1]))
+        qnet.set_initialization_type(%(init)r)
+        smp = net.sample(%(tasks)d); sub = smp.subset_by_task(%(pct)r); ini = net.gibbs_initialize(sub)
     qnet.reset_stats()
     t0 = time.time()
-    estimation.bayes(net, ini, %d)
+    if %(sampler)r == "MH":   # estimation.bayes with sampling_type MH cannot report (estimation.py:141); its loop spelled out
+        net.estimate(ini)
+        arrv = ini
+        for i in range(%(iters)d):
+            arrv = net.gibbs_resample(arrv, burn=0, num_iter=1, return_arrv=False)[-1]
+            net.sample_parameters(arrv)
+    else:
+        estimation.bayes(net, ini, %(iters)d)
     dt = time.time() - t0
     ne = qnet.stats()['nevents']
 print("RESULT %%d %%.6f" %% (ne, dt))
-""" % (ref, yaml_text, seed, init, tasks, sweeps)
+"""
+
+
+def reference_run(wl, iters, nproc, sampler="SLICE", seed=13, use_fixture=True, tasks=None):
+    """`nproc` pinned single-chain processes of the reference, each running `iters` iterations of estimation.bayes
+    (timed region: that call only); returns resamples/s summed over the processes."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, ".built")):
+        return None
+    fx = fixture_path(wl.get("ref_fixture")) if use_fixture else None
+    code = REF_CODE % dict(ref=ref, sampler=sampler, fixture=fx, yaml=wl["yaml"], seed=seed, init=wl["init"],
+                           tasks=tasks or wl["ref_tasks"], pct=wl["pct"], iters=iters)
     procs = []
-    for c in range(ncores):
+    for c in range(nproc):
         cmd = [sys.executable, "-c", code, str(c)]
         if os.path.exists("/usr/bin/taskset"):
             cmd = ["taskset", "-c", str(c)] + cmd
         procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
-    total, per = 0.0, []
+    per = []
     for p in procs:
         out, err = p.communicate()
         for line in out.splitlines():
@@ -207,7 +297,46 @@ print("RESULT %%d %%.6f" %% (ne, dt))
                 per.append(int(ne) / float(dt))
     if not per:
         return None
-    return {"value": sum(per), "per_core": sum(per) / len(per), "cores": len(per)}
+    return {"value": sum(per), "per_core": sum(per) / len(per), "cores": len(per),
+            "state": ("identical initial state (tests/golden/big_%s.npz through the reference's table reader)" % wl["ref_fixture"])
+                     if fx else "own %d-task state (same generator and seed)" % (tasks or wl["ref_tasks"])}
+
+
+def fullsize_record(workload):
+    try:
+        with open(FULLSIZE) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+def cpu_baseline_block(wl, workload, iters, with_single=True, with_mh=True):
+    """The reference on this box's host cores: all cores concurrently (value), one process alone (per_core_1proc),
+    and the MH sampler, each a bounded sample; plus the committed real-size figure for configs 3 / 4."""
+    ncores = os.cpu_count() or 1
+    t0 = time.time()
+    allc = reference_run(wl, iters, ncores)
+    if allc is None:
+        return None
+    out = {"value": allc["value"], "unit": "resamples/s", "cores": allc["cores"], "kind": "reference",
+           "per_core": allc["per_core"]}
+    if with_single:
+        one = reference_run(wl, iters, 1)
+        if one:
+            out["per_core_1proc"] = one["value"]
+    if with_mh and "type: PS" not in wl["yaml"]:
+        mh = reference_run(wl, iters, ncores, sampler="MH")
+        if mh:
+            out["mh_per_core"] = mh["per_core"]
+            out["mh_unit"] = "MH proposals/s per core (Qnet.gibbs_resample + sample_parameters)"
+    size = wl["tasks"] if fixture_path(wl.get("ref_fixture")) else wl["ref_tasks"]
+    out["sample"] = ("reference Cython estimation.bayes (slice), one pinned single-chain process per core, %d-task %s, %s, "
+                     "%d iterations each, timed region = the estimation.bayes call (%.0f s wall for all legs)"
+                     % (size, workload, allc["state"], iters, time.time() - t0))
+    fs = fullsize_record(workload)
+    if fs:
+        out["fullsize"] = fs
+    return out
 
 
 def run_reference_arm(args):
@@ -216,11 +345,11 @@ def run_reference_arm(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    tasks = args.ref_tasks
+    ncores = os.cpu_count() or 1
     per_step = []
     for i in range(args.warmup + args.steps):
         t0 = time.time()
-        r = cpu_baseline_reference(tasks, args.ref_sweeps, seed=13 + i, yaml_text=wl["yaml"], init=wl["init"])
+        r = reference_run(wl, args.ref_sweeps if i >= args.warmup else 1, ncores, seed=13 + i)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built on this box"}))
             return
@@ -229,18 +358,227 @@ def run_reference_arm(args):
             per_step.append(r)
     v = sum(r["value"] for r in per_step) / len(per_step)
     cores = per_step[0]["cores"]
-    sample = ("reference Cython estimation.bayes (slice), one pinned single-chain process per core, %d-task %s, "
-              "%d iterations per step" % (tasks, args.workload, args.ref_sweeps))
+    size = wl["tasks"] if fixture_path(wl.get("ref_fixture")) else wl["ref_tasks"]
+    sample = ("reference Cython estimation.bayes (slice), one pinned single-chain process per core, %d-task %s, %s, "
+              "%d iterations per step (warm-up steps: 1), timed region = the estimation.bayes call"
+              % (size, args.workload, per_step[0]["state"], args.ref_sweeps))
+    one = reference_run(wl, args.ref_sweeps, 1)
+    cb = {"value": v, "unit": "resamples/s", "cores": cores, "kind": "reference", "sample": sample, "per_core": v / cores}
+    if one:
+        cb["per_core_1proc"] = one["value"]
+    if "type: PS" not in wl["yaml"]:
+        mh = reference_run(wl, args.ref_sweeps, ncores, sampler="MH")
+        if mh:
+            cb["mh_per_core"] = mh["per_core"]
+    fs = fullsize_record(args.workload)
+    if fs:
+        cb["fullsize"] = fs
     line = {"impl": "reference", "metric": "chain-task resamples/sec", "value": v, "unit": "resamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(r["sec"] for r in per_step) / len(per_step), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD % (wl["name"], args.tasks, args.chains, args.sweeps), "reference_sample": sample},
-            "cpu_baseline": {"value": v, "unit": "resamples/s", "cores": cores, "kind": "reference", "sample": sample,
-                             "per_core": v / cores},
+            "config": {"workload": WORKLOAD % (wl["name"], args.tasks, int(100 * wl["pct"]), args.chains, args.sweeps),
+                       "baseline_config": args.workload, "reference_sample": sample},
+            "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "resamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+class Ctx(object):
+    """Process-wide handles shared by the sub-runs."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            dist.barrier()
+        self.l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+        self.hbm_peak, self.peak_kind = peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+
+def measure(ctx, workload, tasks, C, S, steps, warmup, mode="SLICE", tight=False, e2e_steps=None, sampler=None):
+    """One workload on this rank's GPU: device-resident arm, end-to-end arm, roofline.  Returns (dict, engine pieces)."""
+    import numpy
+    from bayes_qnet_b200 import GibbsEngine, parallel
+    wl = WORKLOADS[workload]
+    net, ini, how = make_input(tasks, yaml_text=wl["yaml"], init=wl["init"], fixture=wl["fixture"], pct=wl["pct"])
+    eng = GibbsEngine(net, ini, n_chains=C, seed=20261019, device=ctx.local, chain_offset=ctx.rank * C)
+    n_elig = len(eng.sequential_order())
+    resamples_per_step = C * S * n_elig
+    d0 = ini.soa()["d"].copy()
+    theta0 = numpy.array(net.parameters, dtype=numpy.float64)
+
+    # ---- device-resident arm ------------------------------------------------------------------------------------
+    for _ in range(warmup):
+        eng.sweep(S, mode, "BAYES", sync=True, tight=tight)
+    launch_ms = []
+    ctx.barrier()
+    if sampler is not None:
+        sampler.active = True
+    launches0 = eng.stats()["n_launches"]
+    for _ in range(steps):
+        ctx.l2_flush.zero_()
+        ctx.barrier()
+        eng.sweep(S, mode, "BAYES", sync=True, tight=tight)
+        launch_ms.append(eng.last_sweep_ms())  # CUDA events on the handle's own stream around the launch
+    if sampler is not None:
+        sampler.active = False
+    launches = eng.stats()["n_launches"] - launches0
+    t_local = sum(launch_ms) / 1e3
+    ctx.barrier()
+
+    # ---- end-to-end arm: host buffers in, summaries (+ gather, diagnostics) out, inside the timed region ----------
+    e2e_times, gather_ms, d2h = [], [], 0
+    n_e2e = steps if e2e_steps is None else e2e_steps
+    for i in range(min(warmup, 1) + n_e2e):
+        ctx.barrier()
+        t0 = time.perf_counter()
+        eng.broadcast_state(d0)                # host -> device: the initial state, replicated on the device
+        eng.set_params(theta0)
+        eng.clear_traces()
+        eng.sweep(S, mode, "BAYES", trace=True, sync=True, tight=tight)
+        tg = time.perf_counter()
+        summ = parallel.gather_summaries_device(eng, ctx.world)     # NCCL all-gather on the device trace buffers
+        diag = parallel.device_diagnostics(summ)                   # R-hat / ESS reductions on the device -> small host arrays
+        gms = 1e3 * (time.perf_counter() - tg)
+        th, mw, lp = eng.traces()               # device -> host: per-sweep theta / mean wait / log-prob of this rank
+        final = eng.params()
+        dt = time.perf_counter() - t0
+        d2h = th.nbytes + mw.nbytes + lp.nbytes + final.nbytes + sum(v.nbytes for v in diag.values())
+        if i >= min(warmup, 1):
+            e2e_times.append(dt)
+            gather_ms.append(gms)
+    h2d = d0.nbytes + C * 8 * eng.P
+    t_dev, t_e2e = ctx.max_over_ranks([t_local, sum(e2e_times)])
+    world = ctx.world
+    mean_ms = sum(launch_ms) / len(launch_ms)
+    achieved = resamples_per_step * wl["bytes"] / (mean_ms / 1e3) / 1e9
+    traffic = NCU_TRAFFIC.get((workload, tasks, C, S))
+    info = eng.kernel_info()
+    st = eng.stats()
+    res = {
+        "value": world * resamples_per_step * steps / t_dev,
+        "ms_per_step": 1e3 * t_dev / steps,
+        "e2e": {"value": world * resamples_per_step * n_e2e / t_e2e, "unit": "resamples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / n_e2e,
+                "gather_ms": sum(gather_ms) / max(len(gather_ms), 1),
+                "returns": "per-sweep theta / mean wait / log-prob of every chain and the final parameters; the per-chain "
+                           "END STATE (%.0f MB here) stays on the device -- estimation.bayes copies back chain 0 only"
+                           % (8e-6 * eng.E * C)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": ctx.hbm_peak, "unit": "GB/s",
+                     "frac": achieved / ctx.hbm_peak, "traffic": traffic[0] if traffic else None,
+                     "traffic_note": traffic[1] if traffic else "no ncu --set full capture of this exact launch shape",
+                     "peak_kind": ctx.peak_kind, "kernel": wl["kernel"], "bytes_per_resample": wl["bytes"],
+                     "resamples_per_launch": resamples_per_step, "launch_ms_mean": mean_ms, "launch_ms_max": max(launch_ms)},
+        "config": {"workload": WORKLOAD % (wl["name"], tasks, int(100 * wl["pct"]), C, S), "baseline_config": workload,
+                   "initial_state": how, "events_per_chain": eng.E, "resampled_events_per_chain": n_elig,
+                   "chains_total": world * C, "sweeps_per_step": S, "param_update": "BAYES (posterior draw every sweep)",
+                   "sampler": ("slice" if mode == "SLICE" else "MH") + (" tight" if tight else ""),
+                   "l2": "256 MiB buffer written between timed steps (L2 flush); chain state 8*E*C = %.0f MB" % (8e-6 * eng.E * C),
+                   "threads_per_cta": info["threads"], "state_in_smem": info["state_in_smem"],
+                   "smem_bytes_per_cta": info["smem_bytes"]},
+        "slice_evals_per_resample": st["slice_evals"] / max(st["nevents"], 1),
+        "redone_frac": st["n_redone"] / max(st["nevents"], 1),
+    }
+    return res, (net, ini, eng)
+
+
+def convergence(ctx, net, ini, C, S):
+    """R-hat and ESS that mean something: every chain gets its own over-dispersed start, the ensemble runs until the
+    largest split R-hat over the service parameters and per-queue mean waits is below 1.05 (blocks of 5 S sweeps, at
+    most 60 blocks), then ESS is computed per chain on a fresh window and SUMMED over the chains."""
+    import numpy
+    from bayes_qnet_b200 import GibbsEngine, diagnostics, parallel
+    eng = GibbsEngine(net, ini, n_chains=C, seed=777, device=ctx.local, chain_offset=ctx.rank * C)
+    eng.disperse(sweeps=3, scale=0.7, seed=1 + ctx.rank)
+    block = 5 * S
+    swept, rh, ok = 0, None, False
+    for b in range(60):
+        eng.clear_traces()
+        eng.sweep(block, "SLICE", "BAYES", trace=True, sync=True)
+        swept += block
+        summ = parallel.gather_summaries_device(eng, ctx.world)
+        diag = parallel.device_diagnostics(summ)
+        rh = float(numpy.nanmax(diag["rhat"]))
+        if rh < 1.05:
+            ok = True
+            break
+    eng.clear_traces()
+    eng.sweep(block, "SLICE", "BAYES", trace=True, sync=True)
+    ms = eng.last_sweep_ms()
+    summ = parallel.gather_summaries_device(eng, ctx.world)
+    diag = parallel.device_diagnostics(summ)
+    ess_sum = diag["ess_per_chain_sum"]          # [K] sum over chains of the per-chain ESS of each summary
+    out = {"rhat_max": float(numpy.nanmax(diag["rhat"])), "ess_valid": bool(ok and numpy.nanmax(diag["rhat"]) < 1.05),
+           "sweeps_to_rhat_1.05": swept if ok else None, "window_sweeps": block, "chains": C * ctx.world,
+           "starts": "over-dispersed per chain (GibbsEngine.disperse: 3 sweeps under parameters perturbed by exp(0.7 N(0,1)))",
+           "ess_note": "min over service parameters and per-queue mean waits of the SUM over chains of per-chain ESS "
+                       "(Geyer initial positive sequence), on %d sweeps after R-hat < 1.05" % block}
+    if out["ess_valid"]:
+        out["ess_per_s"] = float(numpy.min(ess_sum)) / (ms / 1e3)
+        out["ess_per_sweep_per_chain"] = float(numpy.min(ess_sum)) / (block * C * ctx.world)
+    else:
+        out["ess_per_s"] = None
+    ref = fullsize_record("config2_ess")
+    if ref:
+        out["reference"] = ref
+    eng.close()
+    return out
+
+
+def chain_sweep(ctx, counts=(1, 16, 148, 1024, 8192)):
+    """BASELINE configs[4] in short: resamples/s of the 3-tier model at a few chain counts on this GPU (the full sweep
+    1..65536 at 1/2/4/8 GPUs is `--workload config5`, profiles/r2_config5_*.json)."""
+    out = []
+    for c in counts:
+        r, (net, ini, eng) = measure(ctx, "config2", 5000, c, 20, 2, 1, e2e_steps=1)
+        eng.close()
+        out.append({"chains_per_gpu": c, "value": r["value"], "e2e": r["e2e"]["value"], "ms_per_step": r["ms_per_step"]})
+    return out
+
+
+def run_config5(ctx, args):
+    """Chain-count sweep: C total chains in {1, 2, 4, ..., 65536}; strong = split over the ranks, weak = per GPU."""
+    rows = []
+    c = 1
+    while c <= 65536:
+        for kind in ("strong", "weak"):
+            per = c if kind == "weak" else (c + ctx.world - 1) // ctx.world
+            if kind == "strong" and ctx.world == 1:
+                continue
+            if kind == "strong" and c < ctx.world:
+                continue
+            r, (net, ini, eng) = measure(ctx, "config2", 5000, per, 20, 2, 1, e2e_steps=1)
+            eng.close()
+            rows.append({"total_chains": per * ctx.world, "chains_per_gpu": per, "scaling": kind, "value": r["value"],
+                         "e2e": r["e2e"]["value"], "ms_per_step": r["ms_per_step"]})
+        c *= 2
+    if ctx.rank == 0:
+        print(json.dumps({"metric": "chain-task resamples/sec", "unit": "resamples/s", "n_gpus": ctx.world,
+                          "workload": "config5: chain-count sweep on the 3-tier model, 20 sweeps per step, 2 timed steps",
+                          "rows": rows}))
 
 
 def main():
@@ -249,17 +587,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
-                    help="BASELINE.json configs[1] (default, the headline), configs[2] or configs[3]")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS) + ["config5"],
+                    help="BASELINE.json configs[1] (default, the headline), configs[0], [2], [3], or the chain sweep [4]")
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU")
     ap.add_argument("--tasks", type=int, default=None)
     ap.add_argument("--sweeps", type=int, default=None, help="Gibbs sweeps per step")
     ap.add_argument("--ref-tasks", type=int, default=None)
     ap.add_argument("--ref-sweeps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 1 / 3 / 4 sub-runs, convergence and chain sweep")
     ap.add_argument("--tight", action="store_true", help="BQ_FLAG_TIGHT bracket (not the default sampler)")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS["config2" if args.workload == "config5" else args.workload]
     for k in ("chains", "tasks", "sweeps", "ref_tasks"):
         if getattr(args, k) is None:
             setattr(args, k, wl[k])
@@ -267,149 +606,62 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
-    import numpy
     import torch
-    import torch.distributed as dist
     import __graft_entry__ as ge
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if rank == 0:
+    if int(os.environ.get("RANK", "0")) == 0:
         ge.build(quiet=True)
-    from bayes_qnet_b200 import GibbsEngine, capi, diagnostics, parallel
+    from bayes_qnet_b200 import capi
     if not torch.cuda.is_available() or capi.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: bayes_qnet_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
+    ctx = Ctx(args)
+    if args.workload == "config5":
+        run_config5(ctx, args)
+        if ctx.world > 1:
+            ctx.dist.destroy_process_group()
+        return
 
-    net, ini = make_input(args.tasks, yaml_text=wl["yaml"], init=wl["init"])  # same seed on every rank -> identical data
-    C, S = args.chains, args.sweeps
-    eng = GibbsEngine(net, ini, n_chains=C, seed=20261019, device=local, chain_offset=rank * C)
-    n_elig = len(eng.schedule()[1])
-    resamples_per_step = C * S * n_elig
-    d0 = ini.soa()["d"].copy()
-    hbm_peak, peak_kind = peaks()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident arm ---------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        eng.sweep(S, "SLICE", "BAYES", sync=True)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(ctx.local)
     sampler.start()
-    launch_ms = []
-    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    barrier()
-    sampler.active = True
-    t_total = 0.0
-    launches0 = eng.stats()["n_launches"]
-    for _ in range(args.steps):
-        l2_flush.zero_()
-        barrier()
-        eng.sweep(S, "SLICE", "BAYES", sync=True)
-        launch_ms.append(eng.last_sweep_ms())  # CUDA events on the handle's own stream around the launch
-    sampler.active = False
-    launches = eng.stats()["n_launches"] - launches0
-    t_local = sum(launch_ms) / 1e3
-    barrier()
-    # ---- ESS / R-hat: the warmed-up chains continue for 5 untimed steps with traces recorded ----------------------
-    eng.clear_traces()
-    eng.sweep(5 * S, "SLICE", "BAYES", trace=True, sync=True)
-    th_ess, mw_ess, _ = eng.traces()
-    ess_ms = eng.last_sweep_ms()
-
-    # ---- end-to-end arm: host buffers in, summaries out, inside the timed region ----------------------------
-    h2d = d0.nbytes * 1 + 8 * eng.P
-    e2e_times = []
-    d2h = 0
-    for i in range(args.warmup + args.steps):
-        barrier()
-        t0 = time.perf_counter()
-        eng.broadcast_state(d0)                # host -> device: the initial state, replicated on the device
-        eng.set_params(net.parameters)
-        eng.clear_traces()
-        eng.sweep(S, "SLICE", "BAYES", trace=True, sync=True)
-        th, mw, lp = eng.traces()               # device -> host: per-sweep theta / mean wait / log-prob
-        final = eng.params()
-        dt = time.perf_counter() - t0
-        d2h = th.nbytes + mw.nbytes + lp.nbytes + final.nbytes
-        if i >= args.warmup:
-            e2e_times.append(dt)
-    h2d = d0.nbytes + C * 8 * eng.P
-    t_e2e_local = sum(e2e_times)
-
-    # ---- max over ranks, summaries over NCCL -------------------------------------------------------------------
-    times = torch.tensor([t_local, t_e2e_local], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e = float(times[0]), float(times[1])
-    summ = numpy.concatenate((parallel.gather_traces(th_ess, world), parallel.gather_traces(mw_ess[:, :, 1:], world)),
-                             axis=2)  # [n_rec, world*C, P + Q-1] on every rank
-    barrier()
-    sampler.stop_flag = True
-
-    if rank == 0:
-        value = world * resamples_per_step * args.steps / t_dev
-        e2e = world * resamples_per_step * args.steps / t_e2e
-        worst_ms = max(launch_ms)
-        mean_ms = sum(launch_ms) / len(launch_ms)
-        achieved = resamples_per_step * wl["bytes"] / (mean_ms / 1e3) / 1e9
-        ess = diagnostics.ess(summ)
-        rhat = diagnostics.rhat(summ)
-        info = eng.kernel_info()
-        line = {
-            "metric": "chain-task resamples/sec", "value": value, "unit": "resamples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD % (wl["name"], args.tasks, C, S), "baseline_config": args.workload,
-                       "events_per_chain": eng.E,
-                       "resampled_events_per_chain": n_elig, "chains_total": world * C, "sweeps_per_step": S,
-                       "param_update": "BAYES (posterior draw every sweep)", "sampler": "slice" + (" tight" if args.tight else ""),
-                       "l2": "256 MiB buffer written between timed steps (L2 flush); chain state 8*E*C = %.0f MB" % (8e-6 * eng.E * C),
-                       "threads_per_cta": info["threads"], "state_in_smem": info["state_in_smem"],
-                       "smem_bytes_per_cta": info["smem_bytes"], "n_colors": len(eng.schedule()[0]) - 1},
-            "e2e": {"value": e2e, "unit": "resamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * t_e2e / args.steps},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak,
-                         "traffic": NCU_TRAFFIC_DEFAULT if (args.workload, args.tasks, C, S) == ("config2", 5000, 1024, 20) else
-                                    (NCU_TRAFFIC_CONFIG3 if (args.workload, args.tasks, C, S) == ("config3", 20000, 4096, 2) else None),
-                         "traffic_note": ("bytes per launch from profiles/r1_static_final_ncu_full.txt; far BELOW the "
-                                          "algorithmic 16 B x resamples because the chain state stays in shared memory "
-                                          "for all sweeps of a launch") if args.workload == "config2" else
-                                         ("bytes per launch from profiles/r1_config3_dram_traffic.csv: 80x the algorithmic 32 B x resamples -- every "
-                                          "evaluation re-reads the event's neighbourhood from HBM (L1 hit rate 54 %, "
-                                          "profiles/r1_batch_tandem_4096_ncu_full.txt)") if args.workload == "config3" else
-                                         "see profiles/r1_batch_tandem_4096_ncu_full.txt (256 GB per launch of 98 M resamples on the 2000-task tandem)",
-                         "peak_kind": peak_kind,
-                         "kernel": wl["kernel"], "bytes_per_resample": wl["bytes"],
-                         "resamples_per_launch": resamples_per_step, "launch_ms_mean": mean_ms, "launch_ms_max": worst_ms},
-            "clocks": sampler.summary(),
-            "ess_per_s": float(numpy.min(ess)) / (ess_ms / 1e3) if numpy.all(numpy.isfinite(ess)) else None,
-            "ess_note": "min over service parameters and per-queue mean waits, all chains pooled, %d traced sweeps "
-                        "after %d warm-up sweeps" % (5 * S, (args.warmup + args.steps) * S),
-            "rhat_max": float(numpy.max(rhat)) if numpy.all(numpy.isfinite(rhat)) else None,
-            "slice_evals_per_resample": eng.stats()["slice_evals"] / max(eng.stats()["nevents"], 1),
-        }
-        if not args.no_cpu_baseline and world == 1:
-            t0 = time.time()
-            cb = cpu_baseline_reference(args.ref_tasks, args.ref_sweeps, yaml_text=wl["yaml"], init=wl["init"])
-            if cb is not None:
-                line["cpu_baseline"] = {
-                    "value": cb["value"], "unit": "resamples/s", "cores": cb["cores"], "kind": "reference",
-                    "per_core": cb["per_core"],
-                    "sample": "reference Cython estimation.bayes (slice), one pinned single-chain process per core, "
-                              "%d-task %s, %d iterations each (%.0f s wall)" % (args.ref_tasks, args.workload, args.ref_sweeps, time.time() - t0)}
-        print(json.dumps(line))
+    res, (net, ini, eng) = measure(ctx, args.workload, args.tasks, args.chains, args.sweeps, args.steps, args.warmup,
+                                   tight=args.tight, sampler=sampler)
     eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    line = {"metric": "chain-task resamples/sec", "value": res["value"], "unit": "resamples/s", "n_gpus": ctx.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": res["config"],
+            "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "roofline": res["roofline"],
+            "slice_evals_per_resample": res["slice_evals_per_resample"]}
+    extras = not args.no_extras and args.workload == "config2"
+    if extras:
+        line["convergence"] = convergence(ctx, net, ini, min(args.chains, 1024), args.sweeps)
+        line["ess_per_s"] = line["convergence"]["ess_per_s"]
+        line["rhat_max"] = line["convergence"]["rhat_max"]
+    sampler.stop_flag = True
+    line["clocks"] = sampler.summary()
+    if extras:
+        xs = []
+        for name in ("config3", "config4", "config1"):
+            w = WORKLOADS[name]
+            r, (n2, i2, e2) = measure(ctx, name, w["tasks"], w["chains"], w["sweeps"], 2, 1, e2e_steps=1)
+            e2.close()
+            x = {"config": name, "workload": r["config"]["workload"], "initial_state": r["config"]["initial_state"],
+                 "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": 2, "warmup": 1, "e2e": r["e2e"],
+                 "roofline": r["roofline"], "gpu_launches": r["gpu_launches"],
+                 "slice_evals_per_resample": r["slice_evals_per_resample"], "redone_frac": r["redone_frac"]}
+            if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+                cb = cpu_baseline_block(w, name, 2 if name != "config1" else 200, with_single=False, with_mh=(name != "config1"))
+                if cb:
+                    x["cpu_baseline"] = cb
+            xs.append(x)
+        line["extra_workloads"] = xs
+        line["chain_sweep"] = chain_sweep(ctx)
+    if ctx.rank == 0:
+        if not args.no_cpu_baseline and ctx.world == 1:
+            cb = cpu_baseline_block(wl, args.workload, args.ref_sweeps)
+            if cb:
+                line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":
