@@ -958,30 +958,36 @@ extern "C" int bq_update_params(bq_handle *h, int32_t update) {
 // Parameter update from sufficient statistics supplied by the caller instead of the chains' own state: what
 // Qnet.estimate / Qnet.sample_parameters do when they are given a LIST of Arrivals (qnet.pyx:844-858, 882-896: the
 // events of all of them are pooled per queue).  One thread per (chain, queue).
-__global__ void update_from_suffstats_kernel(int C, int Q, int P, const int *q_dist, const int *q_poff, const double *ss,
-                                             int n_ss, double *theta, int update, unsigned long long seed,
-                                             long long chain_offset, unsigned int sweep, long long *stats) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= C * Q) return;
-    const int chain = t / Q, q = t % Q;
-    SuffStat st;
-    const double *src = ss + ((size_t)(n_ss > 1 ? chain : 0) * Q + q) * 8;
-    st.n = src[0]; st.sum = src[1]; st.sumlog = src[2]; st.sumsq = src[3]; st.nlog = src[4]; st.wait = src[5];
-    st.nall = src[6]; st.nzero = src[7];
-    const int o = q_poff[q], dist = q_dist[q];
+__global__ void __launch_bounds__(128) update_from_suffstats_kernel(int C, int Q, int P, const int *q_dist, const int *q_poff,
+                                                                    const double *ss_in, int n_ss, double *theta, int update,
+                                                                    unsigned long long seed, long long chain_offset,
+                                                                    unsigned int sweep, long long *stats) {
+    // one warp per chain, the statistics staged in shared memory: the same shape as the fused update of the sweep kernels
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chain = blockIdx.x * (blockDim.x >> 5) + gib;
+    if (chain >= C) return;
+    SuffStat *ss = reinterpret_cast<SuffStat *>(smem_raw) + (size_t)gib * Q;
+    const double *src = ss_in + (size_t)(n_ss > 1 ? chain : 0) * Q * 8;
+    for (int i = lane; i < Q * 8; i += 32) reinterpret_cast<double *>(ss)[i] = src[i];
+    __syncwarp();
     double *th = theta + (size_t)chain * P;
-    double p0 = th[o], p1 = (dist == D_EXP) ? 0.0 : th[o + 1];
-    long long pevals = 0;
-    if (update == UPD_BAYES) {
-        Rng rng;
-        rng.init(seed, (unsigned long long)(chain_offset + chain), sweep, (unsigned int)q, TAG_PARAM);
-        sample_params(dist, st, rng, p0, p1, &pevals);
-    } else {
-        estimate_params(dist, st, p0, p1);
+    long long n_pevals = 0;
+    for (int q = lane; q < Q; q += 32) {
+        const int o = q_poff[q], dist = q_dist[q];
+        double p0 = th[o], p1 = (dist == D_EXP) ? 0.0 : th[o + 1];
+        if (update == UPD_BAYES) {
+            Rng prng;
+            prng.init(seed, (unsigned long long)(chain_offset + chain), sweep, (unsigned int)q, TAG_PARAM);
+            sample_params(dist, ss[q], prng, p0, p1, &n_pevals);
+        } else {
+            estimate_params(dist, ss[q], p0, p1);
+        }
+        th[o] = p0;
+        if (dist != D_EXP) th[o + 1] = p1;
     }
-    th[o] = p0;
-    if (dist != D_EXP) th[o + 1] = p1;
-    if (pevals) atomicAdd((unsigned long long *)&stats[(size_t)chain * BQ_NSTAT + 2], (unsigned long long)pevals);
+    n_pevals = (long long)group_sum<32>((double)n_pevals, 0xffffffffu);
+    if (lane == 0) stats[(size_t)chain * BQ_NSTAT + 2] += n_pevals;
 }
 
 extern "C" int bq_update_params_from(bq_handle *h, int32_t update, const double *suffstats, int32_t n_ss) {
@@ -994,8 +1000,9 @@ extern "C" int bq_update_params_from(bq_handle *h, int32_t update, const double 
     CK(cudaMalloc((void **)&d_ss, n * sizeof(double)));
     cudaError_t e = cudaMemcpyAsync(d_ss, suffstats, n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
-        const int total = h->C * h->Q;
-        update_from_suffstats_kernel<<<(total + 127) / 128, 128, 0, h->stream>>>(
+        const size_t sm = 4 * (size_t)h->Q * sizeof(SuffStat);
+        smem_optin((const void *)update_from_suffstats_kernel, sm);
+        update_from_suffstats_kernel<<<(h->C + 3) / 4, 128, sm, h->stream>>>(
             h->C, h->Q, h->P, h->d_q_dist, h->d_q_poff, d_ss, n_ss, h->d_theta, update, h->seed, h->chain_offset,
             h->sweep_counter, h->d_stats);
         e = cudaGetLastError();
