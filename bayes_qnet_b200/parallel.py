@@ -79,9 +79,10 @@ def gather_summaries_device(eng, world=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return local
     w = dist.get_world_size()
-    out = torch.empty((w,) + tuple(local.shape), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local)  # equal chain counts per rank (bench / GibbsEngine sharding)
-    return out.permute(1, 0, 2, 3).reshape(local.shape[0], w * local.shape[1], local.shape[2])
+    n = local.shape[0]
+    out = torch.empty((w * n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local)  # rank-major concatenation; equal chain counts per rank
+    return out.view(w, n, local.shape[1], local.shape[2]).permute(1, 0, 2, 3).reshape(n, w * local.shape[1], local.shape[2])
 
 
 def device_diagnostics(x):
@@ -102,19 +103,23 @@ def device_diagnostics(x):
         rhat = torch.full((K,), float("nan"), dtype=x.dtype, device=x.device)
     out["rhat"] = rhat.cpu().numpy()
     if n >= 4:
-        xc = x - x.mean(dim=0, keepdim=True)
-        f = torch.fft.rfft(xc, n=2 * n, dim=0)
-        ac = torch.fft.irfft(f * torch.conj(f), n=2 * n, dim=0)[:n] / n     # [n, m, K]
-        var0 = ac[0].clamp_min(1e-300)
-        rho = ac / var0
-        t2 = (n // 2) * 2
-        pairs = rho[0:t2:2] + rho[1:t2:2]                                   # [n/2, m, K]
-        alive = torch.cumprod((pairs >= 0).to(x.dtype), dim=0)
-        tau = -1.0 + 2.0 * (pairs * alive).sum(dim=0)                       # [m, K]
-        ess = n / tau.clamp_min(1.0 / max(torch.log10(torch.tensor(float(max(n, 10)))).item(), 1.0))
-        ess = torch.where(ac[0] > 0, ess, torch.zeros_like(ess))
-        out["ess_per_chain_sum"] = ess.sum(dim=0).cpu().numpy()
-        out["ess_per_chain_min"] = ess.min(dim=0).values.cpu().numpy()
+        sums, mins = [], []
+        floor = 1.0 / max(torch.log10(torch.tensor(float(max(n, 10)))).item(), 1.0)
+        for k in range(K):  # one summary at a time: the padded FFT of a long window is the memory peak
+            xc = x[:, :, k] - x[:, :, k].mean(dim=0, keepdim=True)
+            f = torch.fft.rfft(xc, n=2 * n, dim=0)
+            ac = torch.fft.irfft(f * torch.conj(f), n=2 * n, dim=0)[:n] / n     # [n, m]
+            rho = ac / ac[0].clamp_min(1e-300)
+            t2 = (n // 2) * 2
+            pairs = rho[0:t2:2] + rho[1:t2:2]                                   # [n/2, m]
+            alive = torch.cumprod((pairs >= 0).to(x.dtype), dim=0)
+            tau = -1.0 + 2.0 * (pairs * alive).sum(dim=0)                       # [m]
+            ess = n / tau.clamp_min(floor)
+            ess = torch.where(ac[0] > 0, ess, torch.zeros_like(ess))
+            sums.append(ess.sum())
+            mins.append(ess.min())
+        out["ess_per_chain_sum"] = torch.stack(sums).cpu().numpy()
+        out["ess_per_chain_min"] = torch.stack(mins).cpu().numpy()
     else:
         nan = torch.full((K,), float("nan"), dtype=x.dtype)
         out["ess_per_chain_sum"] = nan.numpy()

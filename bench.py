@@ -506,39 +506,41 @@ def measure(ctx, workload, tasks, C, S, steps, warmup, mode="SLICE", tight=False
 
 
 def convergence(ctx, net, ini, C, S):
-    """R-hat and ESS that mean something: every chain gets its own over-dispersed start, the ensemble runs until the
-    largest split R-hat over the service parameters and per-queue mean waits is below 1.05 (blocks of 5 S sweeps, at
-    most 60 blocks), then ESS is computed per chain on a fresh window and SUMMED over the chains."""
+    """R-hat and ESS that mean something: every chain gets its own over-dispersed start; the ensemble then runs windows
+    of 1000, 2000, 4000, ... sweeps (earlier windows are warm-up) until the largest split R-hat over the service
+    parameters and per-queue mean waits of a window is below 1.05 (at most 16000 sweeps per window); ESS is computed per
+    chain on that window and SUMMED over the chains."""
     import numpy
-    from bayes_qnet_b200 import GibbsEngine, diagnostics, parallel
+    from bayes_qnet_b200 import GibbsEngine, parallel
     eng = GibbsEngine(net, ini, n_chains=C, seed=777, device=ctx.local, chain_offset=ctx.rank * C)
     eng.disperse(sweeps=3, scale=0.7, seed=1 + ctx.rank)
-    block = 5 * S
-    swept, rh, ok = 0, None, False
-    for b in range(60):
+    window, swept, ok, diag, ms = 1000, 0, False, None, 0.0
+    history = []
+    while window <= 16000:
         eng.clear_traces()
-        eng.sweep(block, "SLICE", "BAYES", trace=True, sync=True)
-        swept += block
+        eng.sweep(window, "SLICE", "BAYES", trace=True, sync=True)
+        ms = eng.last_sweep_ms()
         summ = parallel.gather_summaries_device(eng, ctx.world)
         diag = parallel.device_diagnostics(summ)
         rh = float(numpy.nanmax(diag["rhat"]))
+        history.append([window, round(rh, 4)])
         if rh < 1.05:
             ok = True
             break
-    eng.clear_traces()
-    eng.sweep(block, "SLICE", "BAYES", trace=True, sync=True)
-    ms = eng.last_sweep_ms()
-    summ = parallel.gather_summaries_device(eng, ctx.world)
-    diag = parallel.device_diagnostics(summ)
+        swept += window
+        window *= 2
     ess_sum = diag["ess_per_chain_sum"]          # [K] sum over chains of the per-chain ESS of each summary
-    out = {"rhat_max": float(numpy.nanmax(diag["rhat"])), "ess_valid": bool(ok and numpy.nanmax(diag["rhat"]) < 1.05),
-           "sweeps_to_rhat_1.05": swept if ok else None, "window_sweeps": block, "chains": C * ctx.world,
+    window = history[-1][0]
+    out = {"rhat_max": float(numpy.nanmax(diag["rhat"])), "ess_valid": bool(ok), "warmup_sweeps_before_window": swept,
+           "window_sweeps": window, "rhat_by_window": history, "chains": C * ctx.world,
            "starts": "over-dispersed per chain (GibbsEngine.disperse: 3 sweeps under parameters perturbed by exp(0.7 N(0,1)))",
            "ess_note": "min over service parameters and per-queue mean waits of the SUM over chains of per-chain ESS "
-                       "(Geyer initial positive sequence), on %d sweeps after R-hat < 1.05" % block}
-    if out["ess_valid"]:
+                       "(Geyer initial positive sequence) on the first window whose split R-hat is below 1.05, divided by "
+                       "the device time of that window"}
+    if ok:
         out["ess_per_s"] = float(numpy.min(ess_sum)) / (ms / 1e3)
-        out["ess_per_sweep_per_chain"] = float(numpy.min(ess_sum)) / (block * C * ctx.world)
+        out["ess_per_sweep_per_chain"] = float(numpy.min(ess_sum)) / (window * C * ctx.world)
+        out["slowest_summary"] = int(numpy.argmin(ess_sum))
     else:
         out["ess_per_s"] = None
     ref = fullsize_record("config2_ess")
@@ -632,7 +634,7 @@ def main():
             "slice_evals_per_resample": res["slice_evals_per_resample"]}
     extras = not args.no_extras and args.workload == "config2"
     if extras:
-        line["convergence"] = convergence(ctx, net, ini, min(args.chains, 1024), args.sweeps)
+        line["convergence"] = convergence(ctx, net, ini, min(args.chains, 256), args.sweeps)
         line["ess_per_s"] = line["convergence"]["ess_per_s"]
         line["rhat_max"] = line["convergence"]["rhat_max"]
     sampler.stop_flag = True

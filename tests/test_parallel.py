@@ -54,3 +54,53 @@ def test_gather_world_size_2_gloo(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "rank 0 ok 0..4" in out.stdout and "rank 1 ok 4..7" in out.stdout
+
+
+def test_device_diagnostics_match_the_host_versions():
+    """parallel.device_diagnostics (torch ops, meant to run where the gathered summaries live) on AR(1) chains: split
+    R-hat equals diagnostics.rhat; the summed per-chain ESS is near n m (1 - phi) / (1 + phi)."""
+    import torch
+    from bayes_qnet_b200 import diagnostics
+    rs = numpy.random.RandomState(0)
+    n, m = 2000, 24
+    phi = numpy.array([0.0, 0.5, 0.9])
+    x = numpy.zeros((n, m, 3))
+    e = rs.standard_normal((n, m, 3))
+    for t in range(1, n):
+        x[t] = phi * x[t - 1] + e[t]
+    d = parallel.device_diagnostics(torch.from_numpy(x))
+    assert numpy.allclose(d["rhat"], diagnostics.rhat(x), rtol=1e-10)
+    theory = n * m * (1 - phi) / (1 + phi)
+    assert numpy.all(numpy.abs(d["ess_per_chain_sum"] / theory - 1.0) < 0.2), (d["ess_per_chain_sum"], theory)
+    assert numpy.all(d["ess_per_chain_min"] > 0)
+
+
+def test_allgather_into_tensor_layout_world_size_2_gloo(tmp_path):
+    """The rank-major -> chain-major reshape of gather_summaries_device, exercised with the same torch calls on gloo."""
+    worker = r"""
+import os, sys, numpy, torch
+sys.path.insert(0, %r)
+import torch.distributed as dist
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+full = torch.arange(5 * 6 * 2, dtype=torch.float64).reshape(5, 6, 2)
+local = full[:, 3 * r:3 * r + 3].contiguous()
+n = local.shape[0]
+out = torch.empty((w * n,) + tuple(local.shape[1:]), dtype=local.dtype)
+dist.all_gather_into_tensor(out, local)
+got = out.view(w, n, local.shape[1], local.shape[2]).permute(1, 0, 2, 3).reshape(n, w * local.shape[1], local.shape[2])
+assert torch.equal(got, full)
+print("rank %%d layout ok" %% r)
+dist.destroy_process_group()
+"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker2.py"
+    script.write_text(worker % ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "rank 0 layout ok" in out.stdout and "rank 1 layout ok" in out.stdout
