@@ -263,7 +263,7 @@ def test_full_size_invariants_dynamic(workload):
     wl = bench.WORKLOADS[workload]
     tasks = wl["tasks"]  # 20 000 (config 3) / 50 000 (config 4)
     assert tasks == (20000 if workload == "config3" else 50000)
-    net, ini = bench.make_input(tasks, yaml_text=wl["yaml"], init=wl["init"])
+    net, ini, _ = bench.make_input(tasks, yaml_text=wl["yaml"], init=wl["init"], fixture=wl["fixture"], pct=wl["pct"])
     soa = ini.soa()
     C = 64
     with GibbsEngine(net, ini, n_chains=C, seed=77) as eng:

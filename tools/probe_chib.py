@@ -16,7 +16,7 @@ def main():
     ap.add_argument("--tasks", type=int, default=5000)
     ap.add_argument("--chains", type=int, default=1024)
     args = ap.parse_args()
-    net, ini = bench.make_input(args.tasks)
+    net, ini, _ = bench.make_input(args.tasks)
     with GibbsEngine(net, ini, n_chains=args.chains, seed=3) as eng:
         eng.sweep(20, "SLICE", "BAYES")
         d_star = eng.state(0, 1)[0].copy()
