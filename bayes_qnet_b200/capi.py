@@ -63,6 +63,7 @@ SYMBOLS = {
     "bq_state_dev": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64)]),
     "bq_sweep": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32]),
     "bq_synchronize": (ctypes.c_int, [_H]),
+    "bq_init_chains": (ctypes.c_int, [_H, ctypes.c_double]),
     "bq_update_params": (ctypes.c_int, [_H, ctypes.c_int32]),
     "bq_update_params_from": (ctypes.c_int, [_H, ctypes.c_int32, c_f64p, ctypes.c_int32]),
     "bq_logcond": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p, ctypes.c_int32, c_f64p]),

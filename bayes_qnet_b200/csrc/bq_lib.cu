@@ -66,6 +66,9 @@ struct bq_handle {
     double *d_tr_theta = nullptr, *d_tr_wait = nullptr, *d_tr_logp = nullptr;
     int trace_cap = 0, trace_len = 0;
     double *d_scratch = nullptr;  // logcond x/out
+    int *d_init_topo = nullptr;   // per-chain initialiser: topological order of the schedule records, upper bounds
+    double *d_init_ub = nullptr;
+    unsigned int init_counter = 0;
     int scratch_n = 0;
     long long n_sweeps = 0, n_launches = 0;
     float last_ms = 0.f;
@@ -565,7 +568,7 @@ extern "C" int bq_destroy(bq_handle *h) {
                     h->d_q_type, h->d_q_dist, h->d_q_poff, h->d_state, h->d_theta, h->d_stats,
                     h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch, h->d_order, h->d_qinfo,
                     h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_prec, h->d_flag, h->d_sq, h->d_dt, h->d_claim,
-                    h->d_claimd};
+                    h->d_claimd, h->d_init_topo, h->d_init_ub};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1012,6 +1015,89 @@ extern "C" int bq_update_params_from(bq_handle *h, int32_t update, const double 
     if (e != cudaSuccess) return fail(BQ_ERR_CUDA, cudaGetErrorString(e));
     h->n_launches += 1;
     h->sweep_counter += 1;
+    return BQ_OK;
+}
+
+// Plan of the per-chain initialiser (init_chains_kernel): a topological order of the resample-eligible events under
+// "lower neighbour before upper neighbour" and, for each, the upper bound the fixed (observed / determined) times
+// impose on it through its upper neighbours.  d0: the handle's current chain-0 state (only fixed entries are read).
+static int build_init_plan(bq_handle *h, const double *d0) {
+    const int n = (int)h->recs.size();
+    std::vector<int> slot(h->E, -1);
+    for (int i = 0; i < n; ++i) slot[h->recs[i].e] = i;
+    auto lowers = [&](const SchedRec &r, int out[3]) {
+        int m = 0;
+        if (r.pt_e >= 0) out[m++] = r.pt_e;
+        if (h->q_type[r.q0] == Q_GGK && r.p >= 0) out[m++] = r.p;
+        if (r.e1 >= 0 && h->q_type[r.q1] == Q_GGK && r.pt_p1 >= 0) out[m++] = r.pt_p1;
+        return m;
+    };
+    auto uppers = [&](const SchedRec &r, int out[3]) {
+        int m = 0;
+        if (h->q_type[r.q0] == Q_GGK && r.n >= 0) out[m++] = r.n;
+        if (r.e1 >= 0) out[m++] = r.e1;
+        if (r.e1 >= 0 && h->q_type[r.q1] == Q_GGK && r.pt_n1 >= 0) out[m++] = r.pt_n1;
+        return m;
+    };
+    std::vector<int> indeg(n, 0), topo;
+    std::vector<std::vector<int>> succ(n);
+    for (int i = 0; i < n; ++i) {
+        int lo[3];
+        const int m = lowers(h->recs[i], lo);
+        for (int k = 0; k < m; ++k)
+            if (slot[lo[k]] >= 0 && slot[lo[k]] != i) { succ[slot[lo[k]]].push_back(i); indeg[i]++; }
+    }
+    topo.reserve(n);
+    std::vector<int> stack;
+    for (int i = n - 1; i >= 0; --i)
+        if (!indeg[i]) stack.push_back(i);
+    while (!stack.empty()) {
+        const int i = stack.back();
+        stack.pop_back();
+        topo.push_back(i);
+        for (int j : succ[i])
+            if (--indeg[j] == 0) stack.push_back(j);
+    }
+    if ((int)topo.size() != n) return fail(BQ_ERR_STATE, "bq_init_chains: the ordering constraints of the state are cyclic");
+    std::vector<double> ub(n, INFINITY);
+    for (int t = n - 1; t >= 0; --t) {
+        const int i = topo[t];
+        int up[3];
+        const int m = uppers(h->recs[i], up);
+        double b = INFINITY;
+        for (int k = 0; k < m; ++k) b = std::min(b, slot[up[k]] >= 0 ? ub[slot[up[k]]] : d0[up[k]]);
+        ub[i] = b;
+    }
+    CK(upload(&h->d_init_topo, topo.data(), topo.size()));
+    CK(upload(&h->d_init_ub, ub.data(), ub.size()));
+    return BQ_OK;
+}
+
+extern "C" int bq_init_chains(bq_handle *h, double sigma) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    if (!(sigma >= 0.0)) return fail(BQ_ERR_INVALID, "bq_init_chains: sigma must be >= 0");
+    if (!h->static_order)
+        return fail(BQ_ERR_UNSUPPORTED, "bq_init_chains: per-chain starts are built for static-order networks (single-server "
+                                        "FIFO queues and delay stations); multi-server and PS networks share one start");
+    CK(cudaSetDevice(h->device));
+    if (!h->d_init_topo) {
+        std::vector<double> d0(h->E);
+        CK(cudaMemcpyAsync(d0.data(), h->d_state, (size_t)h->E * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (int rc = build_init_plan(h, d0.data())) return rc;
+    }
+    InitArgs I;
+    memset(&I, 0, sizeof(I));
+    I.E = h->E; I.Q = h->Q; I.P = h->P; I.n_chains = h->C; I.n = (int)h->recs.size();
+    I.rec = h->d_rec; I.topo = h->d_init_topo; I.ub = h->d_init_ub;
+    I.q_type = h->d_q_type; I.q_dist = h->d_q_dist; I.q_poff = h->d_q_poff;
+    I.state = h->d_state; I.theta = h->d_theta; I.sigma = sigma;
+    I.seed = h->seed; I.chain_offset = h->chain_offset; I.counter = h->init_counter++;
+    init_chains_kernel<<<(h->C + 63) / 64, 64, 0, h->stream>>>(I);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_launches += 1;
+    h->dyn_stale = true;
     return BQ_OK;
 }
 

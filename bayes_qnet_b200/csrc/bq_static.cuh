@@ -604,6 +604,65 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
     if (threadIdx.x < 5) A.stats[(size_t)chain * BQ_NSTAT + threadIdx.x] += (long long)cnt[threadIdx.x];
 }
 
+// ---- per-chain starting states -------------------------------------------------------------------
+// The reference initialises ONE state (gibbs_initialize_via_dfn, qnet.pyx:1454-1554: every hidden task threaded through
+// the network with departures drawn from exponentials fitted to the observed data, accepted while all services stay
+// non-negative).  Many chains want many starts, and here all chains of a handle share the queue order, so the batched
+// version draws, for every chain on its own RNG stream, a state that keeps that order: the resample-eligible events
+// are visited in a topological order of the constraint graph (a_e <= d_e, FIFO departure order, FIFO arrival order --
+// the lower / upper neighbours are the ones SchedRec lists), each departure is drawn as lower bound + Exp(mean
+// service of its queue x the chain's dispersion factor), truncated to the upper bound that the OBSERVED times impose
+// on it through its descendants (ub[], the same for all chains, computed once on the host).  One thread per chain.
+struct InitArgs {
+    int E, Q, P, n_chains, n;      // n = eligible events
+    const int4 *rec;               // SchedRec in schedule order
+    const int *topo;               // [n] schedule indices in topological order
+    const double *ub;              // [n] by schedule index
+    const int *q_type, *q_dist, *q_poff;
+    double *state;                 // [C][E]
+    const double *theta;           // [C][P]
+    double sigma;                  // log-sd of the per-chain dispersion factor
+    unsigned long long seed;
+    long long chain_offset;
+    unsigned int counter;
+};
+
+__global__ void init_chains_kernel(const InitArgs A) {
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= A.n_chains) return;
+    double *d = A.state + (size_t)chain * A.E;
+    const double *th = A.theta + (size_t)chain * A.P;
+    const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain);
+    Rng rc;
+    rc.init(A.seed, gchain, A.counter, 0xffffffffu, TAG_INIT);
+    const double kappa = exp(A.sigma * draw_normal(rc));  // one dispersion factor per chain
+    for (int i = 0; i < A.n; ++i) {
+        const int k = A.topo[i];
+        union { int4 v[3]; SchedRec r; } u;
+        u.v[0] = __ldg(&A.rec[3 * k]); u.v[1] = __ldg(&A.rec[3 * k + 1]); u.v[2] = __ldg(&A.rec[3 * k + 2]);
+        const SchedRec &r = u.r;
+        double lb = (r.pt_e >= 0) ? d[r.pt_e] : 0.0;
+        if (A.q_type[r.q0] == Q_GGK && r.p >= 0) lb = fmax(lb, d[r.p]);
+        if (r.e1 >= 0 && A.q_type[r.q1] == Q_GGK && r.pt_p1 >= 0) lb = fmax(lb, d[r.pt_p1]);
+        const double ub = A.ub[k];
+        const int o = A.q_poff[r.q0], dist = A.q_dist[r.q0];
+        double mean = th[o];                                       // Exponential: scale
+        if (dist == D_GAMMA) mean = th[o] * th[o + 1];
+        else if (dist == D_LOGNORMAL) mean = exp(th[o] + 0.5 * th[o + 1] * th[o + 1]);
+        mean *= kappa;
+        Rng rng;
+        rng.init(A.seed, gchain, A.counter, (unsigned int)r.e, TAG_INIT);
+        double x = lb;
+        bool ok = false;
+        for (int t = 0; t < 8 && !ok; ++t) {
+            x = lb + mean * (-log_d(1.0 - rng.uniform()));
+            ok = x < ub;
+        }
+        if (!ok) x = lb + (ub - lb) * rng.uniform();               // tight window: uniform inside it
+        d[r.e] = x;
+    }
+}
+
 // ---- parity / reporting kernels ---------------------------------------------------------------
 
 // out[j] = inner_dfun(x[j]) - lik0 for event described by `r` on chain `chain` (qnet.pyx:1340-1357).

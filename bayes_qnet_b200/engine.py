@@ -96,6 +96,13 @@ class GibbsEngine(object):
         if sync:
             self.synchronize()
 
+    def init_chains(self, sigma=0.7):
+        """Every chain gets a starting state of its own (new; the reference initialises one state per call of
+        Qnet.gibbs_initialize): all hidden departures redrawn on the device, chain by chain on separate RNG streams,
+        from exponentials scaled by a per-chain factor exp(sigma N(0,1)), keeping the observed times, the queue
+        order and s >= 0.  Static-order networks only (raises BqError otherwise; use `disperse` there)."""
+        capi.check(self._L.bq_init_chains(self._h, float(sigma)))
+
     def disperse(self, sweeps=20, scale=0.7, seed=0, mode="SLICE"):
         """Over-dispersed starting points for convergence diagnostics (new; the reference is single-chain): every
         chain runs `sweeps` sweeps under its own perturbed parameters theta * exp(scale * N(0, 1)) -- held fixed --

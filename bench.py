@@ -506,14 +506,14 @@ def measure(ctx, workload, tasks, C, S, steps, warmup, mode="SLICE", tight=False
 
 
 def convergence(ctx, net, ini, C, S):
-    """R-hat and ESS that mean something: every chain gets its own over-dispersed start; the ensemble then runs windows
+    """R-hat and ESS that mean something: every chain gets its own over-dispersed start (bq_init_chains); the ensemble then runs windows
     of 1000, 2000, 4000, ... sweeps (earlier windows are warm-up) until the largest split R-hat over the service
     parameters and per-queue mean waits of a window is below 1.05 (at most 16000 sweeps per window); ESS is computed per
     chain on that window and SUMMED over the chains."""
     import numpy
     from bayes_qnet_b200 import GibbsEngine, parallel
     eng = GibbsEngine(net, ini, n_chains=C, seed=777, device=ctx.local, chain_offset=ctx.rank * C)
-    eng.disperse(sweeps=3, scale=0.7, seed=1 + ctx.rank)
+    eng.init_chains(0.7)       # a starting state of its own for every chain, drawn on the device (bq_init_chains)
     window, swept, ok, diag, ms = 1000, 0, False, None, 0.0
     history = []
     while window <= 16000:
@@ -533,7 +533,8 @@ def convergence(ctx, net, ini, C, S):
     window = history[-1][0]
     out = {"rhat_max": float(numpy.nanmax(diag["rhat"])), "ess_valid": bool(ok), "warmup_sweeps_before_window": swept,
            "window_sweeps": window, "rhat_by_window": history, "chains": C * ctx.world,
-           "starts": "over-dispersed per chain (GibbsEngine.disperse: 3 sweeps under parameters perturbed by exp(0.7 N(0,1)))",
+           "starts": "one per chain, drawn on the device (bq_init_chains: every hidden departure redrawn from exponentials "
+                     "scaled by a per-chain factor exp(0.7 N(0,1)), observed times and queue order kept)",
            "ess_note": "min over service parameters and per-queue mean waits of the SUM over chains of per-chain ESS "
                        "(Geyer initial positive sequence) on the first window whose split R-hat is below 1.05, divided by "
                        "the device time of that window"}

@@ -125,6 +125,14 @@ int bq_get_state(bq_handle *h, int32_t chain_lo, int32_t chain_hi, double *d, do
 /* Same, but d is DEVICE memory laid out [n_chains][E] (zero-copy access for torch callers). */
 int bq_state_dev(bq_handle *h, double **d_dev, int64_t *chain_stride);
 
+/* A starting state of its own for every chain (replaces one call of Qnet.gibbs_initialize, qnet.pyx:531 / 1454-1554, per
+ * chain): every resample-eligible departure is redrawn, in a topological order of the ordering constraints, as its lower
+ * bound plus an exponential with the mean service of its queue (from the chain's current parameters) times a per-chain
+ * factor exp(sigma N(0,1)), truncated to the upper bound the observed times impose; the queue order of the handle and
+ * every observed time are kept, every service stays >= 0.  sigma = 0: same scale for all chains (still different
+ * draws).  Static-order networks (single-server FIFO queues, delay stations); BQ_ERR_UNSUPPORTED otherwise. */
+int bq_init_chains(bq_handle *h, double sigma);
+
 /* n_sweeps full Gibbs sweeps over every chain, each followed by the requested parameter update:
  * Qnet.slice_resample (qnet.pyx:659) / Qnet.gibbs_resample (qnet.pyx:337) + Qnet.sample_parameters
  * (qnet.pyx:882) / Qnet.estimate (qnet.pyx:844).  Asynchronous on the handle's stream;
