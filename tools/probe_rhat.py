@@ -18,7 +18,9 @@ disperse = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 wl = bench.WORKLOADS["config2"]
 net, ini, how = bench.make_input(tasks, yaml_text=wl["yaml"], init=wl["init"], fixture=wl["fixture"] if tasks == 5000 else None)
 eng = GibbsEngine(net, ini, n_chains=C, seed=777)
-if disperse:
+if disperse == 2:
+    eng.init_chains(0.7)
+elif disperse:
     eng.disperse(sweeps=3, scale=0.7, seed=1)
 for b in range(nblocks):
     eng.clear_traces()
