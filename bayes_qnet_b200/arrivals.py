@@ -28,7 +28,8 @@ class Event(object):
         self.arrv = None
         self.i = -1
         self._v = dict(eid=int(eid), tid=int(tid), qid=int(qid), state=int(state), a=float(a), d=float(d),
-                       s=float(s), obs_a=int(obs_a), obs_d=int(obs_d), proc=int(proc) if proc else 0, q=q)
+                       s=float(s), obs_a=int(obs_a), obs_d=int(obs_d), proc=int(proc) if proc else 0, q=q,
+                       aux=int(aux) if isinstance(aux, (int, numpy.integer)) else 0)
 
     @classmethod
     def _view(cls, arrv, i):
@@ -59,6 +60,15 @@ class Event(object):
     obs_a = property(lambda self: self._get("obs_a"), lambda self, v: self._set("obs_a", v))
     obs_d = property(lambda self: self._get("obs_d"), lambda self, v: self._set("obs_d", v))
     proc = property(lambda self: self._get("proc"), lambda self, v: self._set("proc", v))
+    aux = property(lambda self: self._get("aux"), lambda self, v: self._set("aux", v))
+
+    # the one auxiliary variable an event can carry: the component of its queue's mixture template
+    # (Event.variable / set_variable, arrivals.pyx; MixtureTemplate.var_name = "COMPONENT_<queue>")
+    def variable(self, name=None):
+        return self.aux
+
+    def set_variable(self, name, value):
+        self.aux = int(value)
 
     @property
     def q(self):
@@ -127,7 +137,7 @@ class Event(object):
 
 _INT = ("eid", "tid", "qid", "state", "proc")
 _DBL = ("a", "d", "s")
-_FLG = ("obs_a", "obs_d")
+_FLG = ("obs_a", "obs_d", "aux")  # aux: mixture component of the event (Event.auxiliaries, arrivals.pxd:36)
 _LNK = ("prev_byt", "next_byt", "prev_byq", "next_byq")
 
 
@@ -150,7 +160,7 @@ class Arrivals(object):
     # ---- construction -------------------------------------------------------------------------
     @classmethod
     def from_arrays(cls, net, tid, qid, state, a, d, obs_a=None, obs_d=None, eid=None, proc=None, s=None,
-                    recompute=True, prev_byq=None, next_byq=None):
+                    recompute=True, prev_byq=None, next_byq=None, aux=None):
         """Rows must list each task's events in visit order (any interleaving between tasks).  The by-queue
         order is derived from the times unless explicit prev_byq/next_byq links are given."""
         self = cls(net)
@@ -166,6 +176,7 @@ class Arrivals(object):
         self._obs_d = numpy.ones(n, dtype=numpy.uint8) if obs_d is None else numpy.asarray(obs_d, dtype=numpy.uint8).copy()
         self._eid = numpy.arange(n, dtype=numpy.int32) if eid is None else numpy.asarray(eid, dtype=numpy.int32).copy()
         self._proc = numpy.zeros(n, dtype=numpy.int32) if proc is None else numpy.asarray(proc, dtype=numpy.int32).copy()
+        self._aux = numpy.zeros(n, dtype=numpy.uint8) if aux is None else numpy.asarray(aux, dtype=numpy.uint8).copy()
         self._relink()
         if prev_byq is not None:
             self._prev_byq = numpy.asarray(prev_byq, dtype=numpy.int32).copy()
@@ -402,14 +413,14 @@ class Arrivals(object):
         rows = numpy.nonzero(keep)[0]
         return Arrivals.from_arrays(self.net, self._tid[rows], self._qid[rows], self._state[rows], self._a[rows],
                                     self._d[rows], self._obs_a[rows], self._obs_d[rows], eid=self._eid[rows],
-                                    proc=self._proc[rows])
+                                    proc=self._proc[rows], aux=self._aux[rows])
 
     def delete_task(self, tid):
         self._flush()
         rows = numpy.nonzero(self._tid != tid)[0]
         new = Arrivals.from_arrays(self.net, self._tid[rows], self._qid[rows], self._state[rows], self._a[rows],
                                    self._d[rows], self._obs_a[rows], self._obs_d[rows], eid=self._eid[rows],
-                                   proc=self._proc[rows])
+                                   proc=self._proc[rows], aux=self._aux[rows])
         self.__dict__.update(new.__dict__)
 
     # ---- flat views for the C-ABI -------------------------------------------------------------------

@@ -24,7 +24,8 @@ c_f64p = ctypes.POINTER(ctypes.c_double)
 
 class BqModel(ctypes.Structure):
     _fields_ = [("n_queues", ctypes.c_int32), ("n_params", ctypes.c_int32), ("q_type", c_i32p),
-                ("q_k", c_i32p), ("q_dist", c_i32p), ("q_param_off", c_i32p)]
+                ("q_k", c_i32p), ("q_dist", c_i32p), ("q_param_off", c_i32p),
+                ("n_slots", ctypes.c_int32), ("q_slot_off", c_i32p), ("slot_dist", c_i32p)]
 
 
 class BqArrivals(ctypes.Structure):
@@ -60,6 +61,8 @@ SYMBOLS = {
     "bq_set_state": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p]),
     "bq_broadcast_state": (ctypes.c_int, [_H, c_f64p]),
     "bq_get_state": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_f64p, c_f64p, c_f64p, c_i32p, c_i32p, c_i32p]),
+    "bq_set_aux": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_u8p]),
+    "bq_get_aux": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, c_u8p]),
     "bq_state_dev": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64)]),
     "bq_sweep": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32]),
     "bq_synchronize": (ctypes.c_int, [_H]),

@@ -52,6 +52,12 @@ struct bq_handle {
     // host copies
     std::vector<int> q_type, q_k, q_dist, q_poff;
     std::vector<int> q_wide;  // FIFO queues with k >= #events, run as delay stations
+    // distribution slots (mixture templates): per-slot family / parameter offset, first slot and mixing offset per queue
+    int NS = 0;
+    bool has_mix = false;
+    std::vector<int> slot_dist, slot_poff, q_slot, q_mixoff;
+    int *d_slot_dist = nullptr, *d_slot_poff = nullptr, *d_q_slot = nullptr, *d_q_mixoff = nullptr;
+    unsigned char *d_aux = nullptr;  // [C][E] mixture component of every event
     std::vector<int> qid, tid, prev_byt, next_byt, prev_byq, next_byq;
     std::vector<uint8_t> obs_a, obs_d;
     std::vector<int> color_off, order;
@@ -220,7 +226,7 @@ static cudaError_t upload(T **dst, const void *src, size_t n) {
 static size_t static_smem_bytes(const bq_handle *h, bool smem_state) {
     size_t Epad = smem_state ? (size_t)((h->E + 1) & ~1) : 0;
     size_t b = (Epad + 34 * 8 + 8 + ((h->P + 1) & ~1)) * sizeof(double);
-    b += (size_t)h->Q * (sizeof(QConst) + sizeof(SuffStat)) + (size_t)h->Q * 3 * sizeof(int);
+    b += (size_t)h->NS * (sizeof(QConst) + sizeof(SuffStat)) + (size_t)(2 * h->Q + 2 * h->NS + 2) * sizeof(int);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -231,7 +237,8 @@ static void fill_args(const bq_handle *h, SweepArgs &A) {
     A.rec = h->d_rec; A.color_off = h->d_color_off;
     A.ev_q = h->d_ev_q; A.ev_p = h->d_ev_p; A.ev_pt = h->d_ev_pt;
     A.q_events = h->d_q_events; A.q_off = h->d_q_off;
-    A.q_type = h->d_q_type; A.q_dist = h->d_q_dist; A.q_poff = h->d_q_poff;
+    A.q_type = h->d_q_type; A.q_dist = h->d_slot_dist; A.q_poff = h->d_slot_poff;
+    A.NS = h->NS; A.q_slot = h->d_q_slot; A.q_mixoff = h->d_q_mixoff; A.aux = h->d_aux;
     A.state = h->d_state; A.theta = h->d_theta; A.stats = h->d_stats;
     A.tr_theta = h->d_tr_theta; A.tr_wait = h->d_tr_wait; A.tr_logp = h->d_tr_logp;
     A.seed = h->seed; A.chain_offset = h->chain_offset; A.sweep_base = h->sweep_counter;
@@ -568,7 +575,8 @@ extern "C" int bq_destroy(bq_handle *h) {
                     h->d_q_type, h->d_q_dist, h->d_q_poff, h->d_state, h->d_theta, h->d_stats,
                     h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch, h->d_order, h->d_qinfo,
                     h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_prec, h->d_flag, h->d_sq, h->d_dt, h->d_claim,
-                    h->d_claimd, h->d_init_topo, h->d_init_ub};
+                    h->d_claimd, h->d_init_topo, h->d_init_ub, h->d_slot_dist, h->d_slot_poff, h->d_q_slot, h->d_q_mixoff,
+                    h->d_aux};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -622,16 +630,44 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
                 h->q_wide[q] = 1; h->q_type[q] = Q_DELAY; h->q_k[q] = 1;
             }
     }
+    // distribution slots: one per plain queue, one per component of a mixture template
+    h->q_slot.assign(Q + 1, 0);
+    if (m->n_slots > 0) {
+        if (!m->q_slot_off || !m->slot_dist) return bail(BQ_ERR_INVALID, "n_slots > 0 without q_slot_off / slot_dist");
+        h->q_slot.assign(m->q_slot_off, m->q_slot_off + Q + 1);
+        h->slot_dist.assign(m->slot_dist, m->slot_dist + m->n_slots);
+        if (h->q_slot[0] != 0 || h->q_slot[Q] != m->n_slots) return bail(BQ_ERR_INVALID, "q_slot_off does not cover the slots");
+        for (int q = 0; q < Q; ++q) {
+            const int nc = h->q_slot[q + 1] - h->q_slot[q];
+            if (nc < 1 || nc > 255) return bail(BQ_ERR_INVALID, "a queue needs 1..255 distribution slots");
+            h->q_dist[q] = h->slot_dist[h->q_slot[q]];
+        }
+    } else {
+        for (int q = 0; q <= Q; ++q) h->q_slot[q] = q;
+        h->slot_dist = h->q_dist;
+    }
+    h->NS = h->q_slot[Q];
+    h->slot_poff.assign(h->NS, 0);
+    h->q_mixoff.assign(Q, -1);
     int pcount = 0;
     for (int q = 0; q < Q; ++q) {
-        int t = h->q_type[q], dd = h->q_dist[q];
+        const int t = h->q_type[q], nc = h->q_slot[q + 1] - h->q_slot[q];
         if (t != Q_GGK && t != Q_DELAY && t != Q_PS) return bail(BQ_ERR_INVALID, "unknown queue type");
-        if (dd != D_EXP && dd != D_GAMMA && dd != D_LOGNORMAL) return bail(BQ_ERR_INVALID, "unknown service family");
         if (h->q_poff[q] != pcount) return bail(BQ_ERR_INVALID, "q_param_off is not the running parameter count");
-        pcount += (dd == D_EXP) ? 1 : 2;
+        if (nc > 1) { h->has_mix = true; h->q_mixoff[q] = pcount; pcount += nc; }
+        for (int sl = h->q_slot[q]; sl < h->q_slot[q + 1]; ++sl) {
+            const int dd = h->slot_dist[sl];
+            if (dd != D_EXP && dd != D_GAMMA && dd != D_LOGNORMAL) return bail(BQ_ERR_INVALID, "unknown service family");
+            h->slot_poff[sl] = pcount;
+            pcount += (dd == D_EXP) ? 1 : 2;
+            if (dd != D_EXP) h->all_exp = false;
+        }
         if (t == Q_PS || (t == Q_GGK && h->q_k[q] != 1)) h->static_order = false;
-        if (dd != D_EXP) h->all_exp = false;
     }
+    if (h->has_mix) h->all_exp = false;  // the branch-free exponential path carries no per-event component
+    if (h->has_mix && !h->static_order)
+        return bail(BQ_ERR_UNSUPPORTED, "mixture service templates are built for static-order networks (single-server FIFO "
+                                        "queues and delay stations), not next to multi-server or PS queues");
     if (pcount != h->P) return bail(BQ_ERR_INVALID, "n_params does not match the service families");
     for (int e = 0; e < E; ++e) {
         if (h->qid[e] < 0 || h->qid[e] >= Q) return bail(BQ_ERR_INVALID, "event with bad qid");
@@ -649,7 +685,7 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         if (h->q_k[q] < 1) return bail(BQ_ERR_INVALID, "queue with fewer than one processor");
     }
     if (const char *env = getenv("BQ_FORCE_DYNAMIC"))
-        if (env[0] == '1') h->static_order = false;  // run a static-order network through the dynamic kernels
+        if (env[0] == '1' && !h->has_mix) h->static_order = false;  // run a static-order network through the dynamic kernels
 
     cudaError_t ce = cudaSetDevice(device);
     if (ce != cudaSuccess) return bail(BQ_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
@@ -684,6 +720,14 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
     CKB(upload(&h->d_q_type, h->q_type.data(), Q));
     CKB(upload(&h->d_q_dist, h->q_dist.data(), Q));
     CKB(upload(&h->d_q_poff, h->q_poff.data(), Q));
+    CKB(upload(&h->d_slot_dist, h->slot_dist.data(), h->NS));
+    CKB(upload(&h->d_slot_poff, h->slot_poff.data(), h->NS));
+    CKB(upload(&h->d_q_slot, h->q_slot.data(), Q + 1));
+    CKB(upload(&h->d_q_mixoff, h->q_mixoff.data(), Q));
+    if (h->has_mix) {
+        CKB(cudaMalloc((void **)&h->d_aux, (size_t)n_chains * E));
+        CKB(cudaMemset(h->d_aux, 0, (size_t)n_chains * E));
+    }
 
     const size_t C = (size_t)n_chains;
     CKB(cudaMalloc((void **)&h->d_state, C * E * sizeof(double)));
@@ -734,7 +778,7 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         CKB(set_max((const void *)sweep_static_kernel<false, false>));
     }
     if (getenv("BQ_NO_EXP_FASTPATH")) h->all_exp = false;
-    if (const char *env = getenv("BQ_MH_DYNAMIC")) h->mh_dynamic = (env[0] == '1');
+    if (const char *env = getenv("BQ_MH_DYNAMIC")) h->mh_dynamic = (env[0] == '1') && !h->has_mix;
     if (const char *env = getenv("BQ_REFILL")) {
         int t = atoi(env);
         if (t >= 1 && t <= 32) h->refill = t;
@@ -852,6 +896,28 @@ extern "C" int bq_get_state(bq_handle *h, int32_t lo, int32_t hi, double *d, dou
     return BQ_OK;
 }
 
+extern "C" int bq_set_aux(bq_handle *h, int32_t lo, int32_t hi, const uint8_t *aux) {
+    if (int r = check_range(h, lo, hi)) return r;
+    if (!h->d_aux || !aux) return fail(BQ_ERR_INVALID, "bq_set_aux: the handle has no mixture templates");
+    CK(cudaSetDevice(h->device));
+    std::vector<int> ncomp(h->E);
+    for (int e = 0; e < h->E; ++e) ncomp[e] = h->q_slot[h->qid[e] + 1] - h->q_slot[h->qid[e]];
+    for (size_t c = 0; c < (size_t)(hi - lo); ++c)
+        for (int e = 0; e < h->E; ++e)
+            if (aux[c * h->E + e] >= ncomp[e]) return fail(BQ_ERR_INVALID, "bq_set_aux: component index out of range");
+    CK(cudaMemcpyAsync(h->d_aux + (size_t)lo * h->E, aux, (size_t)(hi - lo) * h->E, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BQ_OK;
+}
+extern "C" int bq_get_aux(bq_handle *h, int32_t lo, int32_t hi, uint8_t *aux) {
+    if (int r = check_range(h, lo, hi)) return r;
+    if (!h->d_aux || !aux) return fail(BQ_ERR_INVALID, "bq_get_aux: the handle has no mixture templates");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(aux, h->d_aux + (size_t)lo * h->E, (size_t)(hi - lo) * h->E, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BQ_OK;
+}
+
 extern "C" int bq_state_dev(bq_handle *h, double **d_dev, int64_t *chain_stride) {
     if (!h) return fail(BQ_ERR_INVALID, "null handle");
     if (d_dev) *d_dev = h->d_state;
@@ -911,6 +977,9 @@ static int launch_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t up
     if (mode != BQ_MODE_SLICE && mode != BQ_MODE_MH) return fail(BQ_ERR_INVALID, "bad sweep mode");
     if (mode == BQ_MODE_MH && h->has_ps)
         return fail(BQ_ERR_UNSUPPORTED, "MH sweeps need arrivalLik, which PS queues do not have (queues.pyx:1140): use BQ_MODE_SLICE");
+    if (mode == BQ_MODE_MH && h->has_mix)
+        return fail(BQ_ERR_UNSUPPORTED, "MH sweeps: the reference's proposals take a DistributionTemplate only (queues.pyx:394-442), "
+                                        "not a mixture: use BQ_MODE_SLICE");
     if (update < 0 || update > 2) return fail(BQ_ERR_INVALID, "bad param_update");
     if (n_sweeps == 0) return BQ_OK;
     CK(cudaSetDevice(h->device));
@@ -997,6 +1066,7 @@ extern "C" int bq_update_params_from(bq_handle *h, int32_t update, const double 
     if (!h || !suffstats) return fail(BQ_ERR_INVALID, "null argument");
     if (update != BQ_UPD_BAYES && update != BQ_UPD_STEM) return fail(BQ_ERR_INVALID, "bad param_update");
     if (n_ss != 1 && n_ss != h->C) return fail(BQ_ERR_INVALID, "n_ss must be 1 or the number of chains");
+    if (h->has_mix) return fail(BQ_ERR_UNSUPPORTED, "bq_update_params_from: mixture templates");
     CK(cudaSetDevice(h->device));
     double *d_ss = nullptr;
     const size_t n = (size_t)n_ss * h->Q * 8;
@@ -1090,7 +1160,7 @@ extern "C" int bq_init_chains(bq_handle *h, double sigma) {
     memset(&I, 0, sizeof(I));
     I.E = h->E; I.Q = h->Q; I.P = h->P; I.n_chains = h->C; I.n = (int)h->recs.size();
     I.rec = h->d_rec; I.topo = h->d_init_topo; I.ub = h->d_init_ub;
-    I.q_type = h->d_q_type; I.q_dist = h->d_q_dist; I.q_poff = h->d_q_poff;
+    I.q_type = h->d_q_type; I.q_dist = h->d_slot_dist; I.q_poff = h->d_slot_poff; I.q_slot = h->d_q_slot;
     I.state = h->d_state; I.theta = h->d_theta; I.sigma = sigma;
     I.seed = h->seed; I.chain_offset = h->chain_offset; I.counter = h->init_counter++;
     init_chains_kernel<<<(h->C + 63) / 64, 64, 0, h->stream>>>(I);
@@ -1138,6 +1208,8 @@ extern "C" int bq_stream(bq_handle *h, void **stream) {
 
 static int eval_hook(bq_handle *h, int32_t chain, int32_t eid, const double *x, int32_t n, double *out, int what) {
     if (int r = check_range(h, chain, chain + 1)) return r;
+    if (what == 1 && h->has_mix)
+        return fail(BQ_ERR_UNSUPPORTED, "bq_mh_proposal: not built for mixture templates");
     if (what == 1 && h->has_ps)
         return fail(BQ_ERR_UNSUPPORTED, "PS queues have no arrivalLik (queues.pyx:1140): no MH proposal");
     if (eid < 0 || eid >= h->E || n < 0) return fail(BQ_ERR_INVALID, "bad event id / n");
@@ -1189,7 +1261,7 @@ static int run_report(bq_handle *h, double *logp_host, double *ss_host) {
     const size_t C = h->C;
     double *d_lp = nullptr, *d_ss = nullptr;
     CK(cudaMalloc((void **)&d_lp, C * sizeof(double)));
-    cudaError_t e = cudaMalloc((void **)&d_ss, C * h->Q * 8 * sizeof(double));
+    cudaError_t e = cudaMalloc((void **)&d_ss, C * h->NS * 8 * sizeof(double));
     if (e != cudaSuccess) { cudaFree(d_lp); return fail(BQ_ERR_CUDA, cudaGetErrorString(e)); }
     if (!h->static_order) {
         DynArgs D;
@@ -1207,7 +1279,7 @@ static int run_report(bq_handle *h, double *logp_host, double *ss_host) {
     if (e == cudaSuccess && logp_host)
         e = cudaMemcpyAsync(logp_host, d_lp, C * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && ss_host)
-        e = cudaMemcpyAsync(ss_host, d_ss, C * h->Q * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        e = cudaMemcpyAsync(ss_host, d_ss, C * h->NS * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(d_lp);
     cudaFree(d_ss);
@@ -1288,6 +1360,7 @@ static int gibbs_kernel_dynamic_path(bq_handle *h, const double *d_to, int32_t n
 extern "C" int bq_gibbs_kernel(bq_handle *h, const double *d_to, int32_t n_to, int32_t strict, double *out) {
     if (!h || !d_to || !out) return fail(BQ_ERR_INVALID, "null argument");
     if (n_to != 1 && n_to != h->C) return fail(BQ_ERR_INVALID, "n_to must be 1 or the number of chains");
+    if (h->has_mix) return fail(BQ_ERR_UNSUPPORTED, "bq_gibbs_kernel: mixture templates (the reference's parameter_kernel raises too, queues.pyx:1453)");
     CK(cudaSetDevice(h->device));
     if (!h->static_order) return gibbs_kernel_dynamic_path(h, d_to, n_to, strict, out);
     const size_t E = h->E, C = h->C, n_sched = h->order.size();

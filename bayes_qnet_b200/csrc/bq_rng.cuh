@@ -40,6 +40,7 @@ enum : uint32_t {
     TAG_MH = 3,      // MH-within-Gibbs: first slice step on the proposal (qnet.pyx:337, 1292-1300)
     TAG_MH2 = 4,     //   second slice step (thin = 2)
     TAG_MH_AUX = 5,  //   accept uniform (number 0) and re-initialisation draws (qnet.pyx:389-397, 444-451)
+    TAG_AUX = 6,     // mixture components (MixtureTemplate.resample_auxiliaries, queues.pyx:1402)
     TAG_TEST = 7,
     TAG_INIT = 8     // per-chain starting states (bq_init_chains)
 };

@@ -51,7 +51,14 @@ struct SweepArgs {
     const int *color_off;
     const int *ev_q, *ev_p, *ev_pt;  // per event: queue, prev-by-queue, prev-by-task
     const int *q_events, *q_off;     // events grouped by queue
-    const int *q_type, *q_dist, *q_poff;
+    const int *q_type;               // [Q]
+    // Service distributions live in SLOTS: a plain queue owns one slot, a queue with a mixture template
+    // (MixtureTemplate, queues.pyx:1373-1509) one per component.  Without mixtures NS == Q and slot == queue.
+    int NS;                          // number of slots
+    const int *q_dist, *q_poff;      // [NS] family and offset of the first distribution parameter of each SLOT
+    const int *q_slot;               // [Q+1] first slot of each queue
+    const int *q_mixoff;             // [Q] offset of the queue's mixing weights in theta, or -1
+    unsigned char *aux;              // [C][E] mixture component of every event (Event.auxiliaries), or null
     double *state;      // [C][E]
     double *theta;      // [C][P]
     long long *stats;   // [C][BQ_NSTAT]: nevents, slice_evals, param_evals, stuck, ...
@@ -74,25 +81,28 @@ struct Cond {
     double d_e1, d_p1;   // next-by-task event and its queue predecessor's departure
     double flo, fhi;     // feasible interval (all services >= 0, arrival order kept)
     int has_n, has_e1, e1_fifo;
-    const QConst *c0, *c1;
+    const QConst *c0, *cn, *c1;  // service density of e, of its queue successor, of the task's next event
 
     __device__ __forceinline__ double eval(double d) const {
         if (d < flo || d > fhi) return BQ_NEG_INF;
         double v = lpdf(*c0, d - b);
-        if (has_n) v += lpdf(*c0, d_n - dmax(a_n, d));
+        if (has_n) v += lpdf(*cn, d_n - dmax(a_n, d));
         if (has_e1) v += lpdf(*c1, d_e1 - (e1_fifo ? dmax(d, d_p1) : d));
         return v;
     }
 };
 
+// qc is indexed by slot; with mixture templates (aux != null) an event's slot is its queue's first slot plus its
+// component, otherwise the queue index itself
 __device__ __forceinline__ void cond_load(Cond &c, const SchedRec &r, const double *d, const int *q_type,
                                           const QConst *qc, double &x0, double &lower, double &upper,
-                                          double tmax) {
+                                          double tmax, const int *q_slot = nullptr, const unsigned char *aux = nullptr) {
     x0 = d[r.e];
     double a_e = (r.pt_e >= 0) ? d[r.pt_e] : 0.0;
     int fifo0 = (q_type[r.q0] == Q_GGK);
     c.b = a_e;
-    c.c0 = &qc[r.q0];
+    c.c0 = &qc[aux ? q_slot[r.q0] + aux[r.e] : r.q0];
+    c.cn = c.c0;
     c.c1 = c.c0;
     double flo = a_e, fhi = INFINITY;
     if (fifo0 && r.p >= 0) { c.b = fmax(a_e, d[r.p]); flo = c.b; }
@@ -102,6 +112,7 @@ __device__ __forceinline__ void cond_load(Cond &c, const SchedRec &r, const doub
         c.d_n = d[r.n];
         c.a_n = (r.pt_n >= 0) ? d[r.pt_n] : 0.0;
         fhi = c.d_n;
+        if (aux) c.cn = &qc[q_slot[r.q0] + aux[r.n]];
     }
     c.has_e1 = (r.e1 >= 0);
     c.e1_fifo = 0; c.d_e1 = 0.0; c.d_p1 = 0.0;
@@ -109,7 +120,7 @@ __device__ __forceinline__ void cond_load(Cond &c, const SchedRec &r, const doub
     upper = tmax;
     if (c.has_e1) {
         c.d_e1 = d[r.e1];
-        c.c1 = &qc[r.q1];
+        c.c1 = &qc[aux ? q_slot[r.q1] + aux[r.e1] : r.q1];
         upper = fmin(c.d_e1, tmax);
         fhi = fmin(fhi, c.d_e1);
         c.e1_fifo = (q_type[r.q1] == Q_GGK);
@@ -141,12 +152,13 @@ struct CondExp {
         return (d >= flo && d <= fhi) ? v : BQ_NEG_INF;
     }
     __device__ __forceinline__ void load(const SchedRec &r, const double *d, const int *q_type, const QConst *qc,
-                                         double &x0, double &lower, double &upper, double tmax) {
+                                         double &x0, double &lower, double &upper, double tmax, const int *q_slot,
+                                         const unsigned char *aux) {
         Cond c;
-        cond_load(c, r, d, q_type, qc, x0, lower, upper, tmax);
+        cond_load(c, r, d, q_type, qc, x0, lower, upper, tmax, q_slot, aux);
         b = c.b; flo = c.flo; fhi = c.fhi;
         inv0 = c.c0->inv;
-        invn = c.has_n ? inv0 : 0.0;
+        invn = c.has_n ? c.cn->inv : 0.0;
         a_n = c.a_n; d_n = c.d_n;                    // both 0 when absent: the term vanishes
         inv1 = c.has_e1 ? c.c1->inv : 0.0;
         d_e1 = c.d_e1;
@@ -158,11 +170,12 @@ struct CondExp {
 struct CondGen : Cond {
     // lanes that hold no event still run the branch-free shrink step: give them something harmless to evaluate
     __device__ __forceinline__ void idle(const QConst *qc) {
-        b = a_n = d_n = d_e1 = d_p1 = 0.0; flo = 1.0; fhi = 0.0; has_n = has_e1 = e1_fifo = 0; c0 = c1 = qc;
+        b = a_n = d_n = d_e1 = d_p1 = 0.0; flo = 1.0; fhi = 0.0; has_n = has_e1 = e1_fifo = 0; c0 = cn = c1 = qc;
     }
     __device__ __forceinline__ void load(const SchedRec &r, const double *d, const int *q_type, const QConst *qc,
-                                         double &x0, double &lower, double &upper, double tmax) {
-        cond_load(*this, r, d, q_type, qc, x0, lower, upper, tmax);
+                                         double &x0, double &lower, double &upper, double tmax, const int *q_slot,
+                                         const unsigned char *aux) {
+        cond_load(*this, r, d, q_type, qc, x0, lower, upper, tmax, q_slot, aux);
     }
 };
 
@@ -191,7 +204,7 @@ template <class CondT>
 __device__ __forceinline__ void run_class(const SweepArgs &A, double *d, const int *q_type, const QConst *qc,
                                           int hi, int *ctr, double tmax, unsigned long long gchain,
                                           unsigned int gsw, long long &n_ev, long long &n_evals,
-                                          long long &n_stuck) {
+                                          long long &n_stuck, const int *q_slot, const unsigned char *aux) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     bool active = false, exhausted = false;
@@ -218,7 +231,7 @@ __device__ __forceinline__ void run_class(const SweepArgs &A, double *d, const i
                 u.v[1] = __ldg(&A.rec[3 * my + 1]);
                 u.v[2] = __ldg(&A.rec[3 * my + 2]);
                 double lower, upper, ua, ub;
-                cd.load(u.r, d, q_type, qc, x0, lower, upper, tmax);
+                cd.load(u.r, d, q_type, qc, x0, lower, upper, tmax, q_slot, aux);
                 if (A.flags & FLAG_TIGHT) { lower = fmax(lower, cd.flo); upper = fmin(upper, cd.fhi); }
                 e = u.r.e;
                 rng.init(A.seed, gchain, gsw, (unsigned int)e, TAG_SLICE);
@@ -318,7 +331,8 @@ struct MhPropStatic {
 
 __device__ __forceinline__ void run_class_mh(const SweepArgs &A, double *d, const int *q_type, const QConst *qc, int hi,
                                              int *ctr, unsigned long long gchain, unsigned int gsw, long long &n_ev,
-                                             long long &n_evals, long long &n_reject) {
+                                             long long &n_evals, long long &n_reject, const int *q_slot,
+                                             const unsigned char *aux) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -334,7 +348,7 @@ __device__ __forceinline__ void run_class_mh(const SweepArgs &A, double *d, cons
             u.v[2] = __ldg(&A.rec[3 * my + 2]);
             Cond cd;
             double x0, a_e, upper;
-            cond_load(cd, u.r, d, q_type, qc, x0, a_e, upper, INFINITY);
+            cond_load(cd, u.r, d, q_type, qc, x0, a_e, upper, INFINITY, q_slot, aux);
             const bool final_evt = !cd.has_e1;
             MhPropStatic h;
             h.c = &cd;
@@ -424,60 +438,105 @@ __device__ __forceinline__ void event_service(const double *d, int i, int fifo, 
     s = di - c;
 }
 
-// Per-queue sufficient statistics for the whole chain; result in ss[Q] (shared), logp in *logp_out.
-// Two passes for LogNormal queues (distributions.pyx:276-299 is two-pass).
+// Sufficient statistics per distribution SLOT for the whole chain (a plain queue has one slot; a mixture queue one
+// per component, fed by the events currently assigned to it: MixtureTemplate.collect_sobs, queues.pyx:1416-1432);
+// result in ss[NS] (shared), logp in *logp_out.  Two passes for LogNormal slots (distributions.pyx:276-299 is two-pass).
 __device__ inline void chain_suffstats(const SweepArgs &A, const double *d, const int *q_type,
                                        const int *q_dist, const QConst *qc, SuffStat *ss, double *scratch,
-                                       double *red_out, bool want_logp, double *logp_out) {
+                                       double *red_out, bool want_logp, double *logp_out, const int *q_slot,
+                                       const unsigned char *aux) {
     double logp_acc = 0.0;
     for (int q = 0; q < A.Q; ++q) {
         const int lo = A.q_off[q], hi = A.q_off[q + 1];
-        const int fifo = (q_type[q] == Q_GGK), dist = q_dist[q];
-        const bool need_log = (dist != D_EXP);
-        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // n, sum, sumlog, nlog, wait, nzero, logp, bad
-        for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) {
-            int i = A.q_events[j];
-            double a, s;
-            event_service(d, i, fifo, A.ev_p[i], A.ev_pt[i], a, s);
-            double w = d[i] - a - s;
-            v[4] += (w > 0.0) ? w : 0.0;
-            if (s > 0.0) {
-                v[0] += 1.0; v[1] += s;
-                if (need_log) {
-                    double ls = log(s);
-                    if (dist == D_GAMMA) { v[2] += ls; v[3] += 1.0; }
-                    else if (s >= 1e-50) { v[2] += ls; v[3] += 1.0; }
-                }
-            } else if (s == 0.0) v[5] += 1.0;
-            if (want_logp) {
-                if (s < 0.0) v[7] += 1.0; else v[6] += lpdf(qc[q], s);
-            }
-        }
-        block_reduce_sum<8>(v, scratch, red_out);
-        double mean_log = (red_out[3] > 0.0) ? red_out[2] / red_out[3] : 0.0;
-        double sq[1] = {0.0};
-        if (dist == D_LOGNORMAL) {
+        const int fifo = (q_type[q] == Q_GGK);
+        const int s0 = aux ? q_slot[q] : q, ncomp = aux ? q_slot[q + 1] - q_slot[q] : 1;
+        for (int comp = 0; comp < ncomp; ++comp) {
+            const int sl = s0 + comp, dist = q_dist[sl];
+            const bool need_log = (dist != D_EXP);
+            double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // n, sum, sumlog, nlog, wait, nzero, logp, #(s < 0)
             for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) {
                 int i = A.q_events[j];
+                if (ncomp > 1 && aux[i] != comp) continue;
                 double a, s;
                 event_service(d, i, fifo, A.ev_p[i], A.ev_pt[i], a, s);
-                if (s >= 1e-50) { double z = log(s) - mean_log; sq[0] += z * z; }
+                double w = d[i] - a - s;
+                v[4] += (w > 0.0) ? w : 0.0;
+                if (s > 0.0) {
+                    v[0] += 1.0; v[1] += s;
+                    if (need_log) {
+                        double ls = log(s);
+                        if (dist == D_GAMMA) { v[2] += ls; v[3] += 1.0; }
+                        else if (s >= 1e-50) { v[2] += ls; v[3] += 1.0; }
+                    }
+                } else if (s == 0.0) v[5] += 1.0;
+                else v[7] += 1.0;
+                if (want_logp && !(s < 0.0)) v[6] += lpdf(qc[sl], s);
             }
-        }
-        if (threadIdx.x == 0) {
-            SuffStat &t = ss[q];
-            t.n = red_out[0]; t.sum = red_out[1]; t.sumlog = red_out[2]; t.nlog = red_out[3];
-            t.wait = red_out[4]; t.nzero = red_out[5]; t.nall = (double)(hi - lo); t.sumsq = 0.0;
-            logp_acc += (red_out[7] > 0.0) ? BQ_NEG_INF : red_out[6];
-        }
-        __syncthreads();
-        if (dist == D_LOGNORMAL) {
-            block_reduce_sum<1>(sq, scratch, red_out);
-            if (threadIdx.x == 0) ss[q].sumsq = red_out[0];
+            block_reduce_sum<8>(v, scratch, red_out);
+            double mean_log = (red_out[3] > 0.0) ? red_out[2] / red_out[3] : 0.0;
+            double sq[1] = {0.0};
+            if (dist == D_LOGNORMAL) {
+                for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+                    int i = A.q_events[j];
+                    if (ncomp > 1 && aux[i] != comp) continue;
+                    double a, s;
+                    event_service(d, i, fifo, A.ev_p[i], A.ev_pt[i], a, s);
+                    if (s >= 1e-50) { double z = log(s) - mean_log; sq[0] += z * z; }
+                }
+            }
+            if (threadIdx.x == 0) {
+                SuffStat &t = ss[sl];
+                t.n = red_out[0]; t.sum = red_out[1]; t.sumlog = red_out[2]; t.nlog = red_out[3];
+                t.wait = red_out[4]; t.nzero = red_out[5]; t.nall = red_out[0] + red_out[5] + red_out[7]; t.sumsq = 0.0;
+                logp_acc += (want_logp && red_out[7] > 0.0) ? BQ_NEG_INF : red_out[6];
+            }
             __syncthreads();
+            if (dist == D_LOGNORMAL) {
+                block_reduce_sum<1>(sq, scratch, red_out);
+                if (threadIdx.x == 0) ss[sl].sumsq = red_out[0];
+                __syncthreads();
+            }
         }
     }
     if (threadIdx.x == 0 && logp_out) *logp_out = logp_acc;
+    __syncthreads();
+}
+
+// MixtureTemplate.resample_auxiliaries for every event of every mixture queue (qnet.pyx:679-680 -> queues.pyx:1402-1410):
+// z_e ~ Cat(pi_i exp(lpdf_i(s_e))), one uniform of the (chain, sweep, event) stream TAG_AUX; when all weights vanish
+// (_roll_die_unnorm, sampling.pyx:215-229: Z < 1e-50) a uniformly random component.
+__device__ inline void resample_auxiliaries(const SweepArgs &A, const double *d, const int *q_type, const int *q_slot,
+                                            const QConst *qc, const double *th, unsigned char *aux,
+                                            unsigned long long gchain, unsigned int gsw) {
+    for (int q = 0; q < A.Q; ++q) {
+        const int ncomp = q_slot[q + 1] - q_slot[q];
+        if (ncomp < 2) continue;
+        const int lo = A.q_off[q], hi = A.q_off[q + 1], fifo = (q_type[q] == Q_GGK), s0 = q_slot[q];
+        const double *mix = th + A.q_mixoff[q];
+        for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+            const int i = A.q_events[j];
+            double a, s;
+            event_service(d, i, fifo, A.ev_p[i], A.ev_pt[i], a, s);
+            double Z = 0.0;
+            for (int c = 0; c < ncomp; ++c) Z += mix[c] * exp(lpdf(qc[s0 + c], s));
+            Rng rng;
+            rng.init(A.seed, gchain, gsw, (unsigned int)i, TAG_AUX);
+            const double u = rng.uniform();
+            int pick = ncomp - 1;
+            if (Z < 1e-50) {
+                pick = (int)(u * ncomp);
+                if (pick >= ncomp) pick = ncomp - 1;
+            } else {
+                const double t = Z * u;
+                double S = 0.0;
+                for (int c = 0; c < ncomp; ++c) {
+                    S += mix[c] * exp(lpdf(qc[s0 + c], s));
+                    if (t < S) { pick = c; break; }
+                }
+            }
+            aux[i] = (unsigned char)pick;
+        }
+    }
     __syncthreads();
 }
 
@@ -487,7 +546,8 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
     const int chain = blockIdx.x;
     const int E = A.E, Q = A.Q, P = A.P;
     double *dg = A.state + (size_t)chain * E;
-    // shared layout: [d (E padded to even)] [scratch 34*8] [red_out 8] [theta P] [qc Q] [ss Q] [ints 3Q]
+    // shared layout: [d (E padded to even)] [scratch 34*8] [red_out 8] [theta P] [qc NS] [ss NS] [ints Q + 2 NS + Q + 1]
+    const int NS = A.NS;
     double *sm = reinterpret_cast<double *>(smem_raw);
     const int Epad = SMEM ? ((E + 1) & ~1) : 0;
     double *d = SMEM ? sm : dg;
@@ -495,18 +555,20 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
     double *red_out = scratch + 34 * 8;
     double *th = red_out + 8;
     QConst *qc = reinterpret_cast<QConst *>(th + ((P + 1) & ~1));
-    SuffStat *ss = reinterpret_cast<SuffStat *>(qc + Q);
-    int *q_type = reinterpret_cast<int *>(ss + Q);
-    int *q_dist = q_type + Q;
-    int *q_poff = q_dist + Q;
+    SuffStat *ss = reinterpret_cast<SuffStat *>(qc + NS);
+    int *q_type = reinterpret_cast<int *>(ss + NS);
+    int *q_dist = q_type + Q;      // per slot
+    int *q_poff = q_dist + NS;     // per slot
+    int *q_slot = q_poff + NS;     // [Q + 1]
+    unsigned char *aux = A.aux ? A.aux + (size_t)chain * E : nullptr;
     __shared__ unsigned long long cnt[5];
     __shared__ double logp_sh;
     __shared__ int work_ctr[2];
 
     for (int i = threadIdx.x; i < P; i += blockDim.x) th[i] = A.theta[(size_t)chain * P + i];
-    for (int i = threadIdx.x; i < Q; i += blockDim.x) {
-        q_type[i] = A.q_type[i]; q_dist[i] = A.q_dist[i]; q_poff[i] = A.q_poff[i];
-    }
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) q_type[i] = A.q_type[i];
+    for (int i = threadIdx.x; i <= Q; i += blockDim.x) q_slot[i] = A.q_slot[i];
+    for (int i = threadIdx.x; i < NS; i += blockDim.x) { q_dist[i] = A.q_dist[i]; q_poff[i] = A.q_poff[i]; }
     if (threadIdx.x < 5) cnt[threadIdx.x] = 0ull;
     if (SMEM) {
         // coalesced 16-byte loads; each chain's row is 16 B aligned when E is even, else fall back
@@ -519,7 +581,7 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
         }
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < Q; q += blockDim.x) {  // Q may exceed the CTA (bq_create takes up to 1024 queues)
+    for (int q = threadIdx.x; q < NS; q += blockDim.x) {  // slots may exceed the CTA (bq_create takes up to 1024 queues)
         const int o = q_poff[q];
         qconst_set(qc[q], q_dist[q], th[o], (q_dist[q] == D_EXP) ? 0.0 : th[o + 1]);
     }
@@ -537,6 +599,8 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
             tmax = 2.0 * block_reduce_max(m, scratch);
         }
         const int n_colors = (A.flags & FLAG_PARAMS_ONLY) ? 0 : A.n_colors;
+        if (aux && n_colors > 0)  // mixture components first (qnet.pyx:679-680)
+            resample_auxiliaries(A, d, q_type, q_slot, qc, th, aux, gchain, gsw);
         // reverse scan (slice_resample(reverse=True), qnet.pyx:683-684): the classes in reverse order; the events of a
         // class are conditionally independent, so the order inside a class is immaterial
         const bool rev = (A.flags & FLAG_REVERSE) != 0;
@@ -548,22 +612,27 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
             if (threadIdx.x == 0 && c + 1 < n_colors)  // where the next class starts
                 work_ctr[(c + 1) & 1] = A.color_off[rev ? cc - 1 : cc + 1];
             if (A.mode == MODE_MH)
-                run_class_mh(A, d, q_type, qc, hi, &work_ctr[c & 1], gchain, gsw, n_ev, n_evals, n_reject);
+                run_class_mh(A, d, q_type, qc, hi, &work_ctr[c & 1], gchain, gsw, n_ev, n_evals, n_reject, q_slot, aux);
             else if (ALL_EXP)
-                run_class<CondExp>(A, d, q_type, qc, hi, &work_ctr[c & 1], tmax, gchain, gsw, n_ev, n_evals, n_stuck);
+                run_class<CondExp>(A, d, q_type, qc, hi, &work_ctr[c & 1], tmax, gchain, gsw, n_ev, n_evals, n_stuck,
+                                   q_slot, nullptr);
             else
-                run_class<CondGen>(A, d, q_type, qc, hi, &work_ctr[c & 1], tmax, gchain, gsw, n_ev, n_evals, n_stuck);
+                run_class<CondGen>(A, d, q_type, qc, hi, &work_ctr[c & 1], tmax, gchain, gsw, n_ev, n_evals, n_stuck,
+                                   q_slot, aux);
             __syncthreads();
         }
         const bool trace = (A.flags & FLAG_TRACE) != 0;
         if (A.update != UPD_NONE || trace) {
-            chain_suffstats(A, d, q_type, q_dist, qc, ss, scratch, red_out, trace, &logp_sh);
+            chain_suffstats(A, d, q_type, q_dist, qc, ss, scratch, red_out, trace, &logp_sh, q_slot, aux);
             const size_t recno = (size_t)(A.trace_base + sw);
             if (trace)
-                for (int q = threadIdx.x; q < Q; q += blockDim.x)
-                    A.tr_wait[(recno * A.n_chains + chain) * Q + q] = (ss[q].nall > 0.0) ? ss[q].wait / ss[q].nall : 0.0;
+                for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+                    double w = 0.0, na = 0.0;
+                    for (int sl = q_slot[q]; sl < q_slot[q + 1]; ++sl) { w += ss[sl].wait; na += ss[sl].nall; }
+                    A.tr_wait[(recno * A.n_chains + chain) * Q + q] = (na > 0.0) ? w / na : 0.0;
+                }
             if (trace && threadIdx.x == 0) A.tr_logp[recno * A.n_chains + chain] = logp_sh;
-            for (int q = threadIdx.x; A.update != UPD_NONE && q < Q; q += blockDim.x) {
+            for (int q = threadIdx.x; A.update != UPD_NONE && q < NS; q += blockDim.x) {  // one update per slot
                 const int o = q_poff[q], dist = q_dist[q];
                 double p0 = th[o], p1 = (dist == D_EXP) ? 0.0 : th[o + 1];
                 if (A.update == UPD_BAYES) {
@@ -576,6 +645,15 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
                 th[o] = p0;
                 if (dist != D_EXP) th[o + 1] = p1;
                 qconst_set(qc[q], dist, p0, p1);
+            }
+            // mixing proportions: (1 + #events of the component) / (#components + #events), the same rule in estimate
+            // and in sample_parameters (queues.pyx:1416-1451: counts start at 1, N at the number of components)
+            for (int q = threadIdx.x; aux && A.update != UPD_NONE && q < Q; q += blockDim.x) {
+                const int mo = A.q_mixoff[q], s0 = q_slot[q], nc = q_slot[q + 1] - s0;
+                if (mo < 0) continue;
+                double N = (double)nc;
+                for (int c = 0; c < nc; ++c) N += ss[s0 + c].nall;
+                for (int c = 0; c < nc; ++c) th[mo + c] = (1.0 + ss[s0 + c].nall) / N;
             }
             __syncthreads();
             if (trace)
@@ -618,7 +696,7 @@ struct InitArgs {
     const int4 *rec;               // SchedRec in schedule order
     const int *topo;               // [n] schedule indices in topological order
     const double *ub;              // [n] by schedule index
-    const int *q_type, *q_dist, *q_poff;
+    const int *q_type, *q_dist, *q_poff, *q_slot;  // q_dist / q_poff per slot (SweepArgs); the first slot of a queue is used
     double *state;                 // [C][E]
     const double *theta;           // [C][P]
     double sigma;                  // log-sd of the per-chain dispersion factor
@@ -645,7 +723,7 @@ __global__ void init_chains_kernel(const InitArgs A) {
         if (A.q_type[r.q0] == Q_GGK && r.p >= 0) lb = fmax(lb, d[r.p]);
         if (r.e1 >= 0 && A.q_type[r.q1] == Q_GGK && r.pt_p1 >= 0) lb = fmax(lb, d[r.pt_p1]);
         const double ub = A.ub[k];
-        const int o = A.q_poff[r.q0], dist = A.q_dist[r.q0];
+        const int sl = A.q_slot[r.q0], o = A.q_poff[sl], dist = A.q_dist[sl];
         double mean = th[o];                                       // Exponential: scale
         if (dist == D_GAMMA) mean = th[o] * th[o + 1];
         else if (dist == D_LOGNORMAL) mean = exp(th[o] + 0.5 * th[o + 1] * th[o + 1]);
@@ -668,20 +746,20 @@ __global__ void init_chains_kernel(const InitArgs A) {
 // out[j] = inner_dfun(x[j]) - lik0 for event described by `r` on chain `chain` (qnet.pyx:1340-1357).
 __global__ void logcond_static_kernel(const SweepArgs A, int chain, SchedRec r, const double *x, int n,
                                       double *out) {
-    __shared__ QConst qc[2];
-    __shared__ int qt[64];
+    __shared__ QConst qc[3];  // service densities of e, of its queue successor, of the task's next event
+    __shared__ int qt[2];
     const double *d = A.state + (size_t)chain * A.E;
     const double *th = A.theta + (size_t)chain * A.P;
-    // only the two queues involved are needed; map them to slots 0/1
+    const unsigned char *aux = A.aux ? A.aux + (size_t)chain * A.E : nullptr;
     if (threadIdx.x == 0) {
-        int q = r.q0, o = A.q_poff[q], dist = A.q_dist[q];
-        qconst_set(qc[0], dist, th[o], dist == D_EXP ? 0.0 : th[o + 1]);
-        qt[0] = A.q_type[q];
-        if (r.e1 >= 0) {
-            q = r.q1; o = A.q_poff[q]; dist = A.q_dist[q];
-            qconst_set(qc[1], dist, th[o], dist == D_EXP ? 0.0 : th[o + 1]);
-            qt[1] = A.q_type[q];
+        const int ev[3] = {r.e, r.n, r.e1}, qq[3] = {r.q0, r.q0, r.q1};
+        for (int k = 0; k < 3; ++k) {
+            if (ev[k] < 0) { qc[k] = qc[0]; continue; }
+            const int sl = A.q_slot[qq[k]] + (aux ? aux[ev[k]] : 0), o = A.q_poff[sl], dist = A.q_dist[sl];
+            qconst_set(qc[k], dist, th[o], dist == D_EXP ? 0.0 : th[o + 1]);
         }
+        qt[0] = A.q_type[r.q0];
+        qt[1] = (r.e1 >= 0) ? A.q_type[r.q1] : Q_DELAY;
     }
     __syncthreads();
     SchedRec rr = r;
@@ -690,36 +768,41 @@ __global__ void logcond_static_kernel(const SweepArgs A, int chain, SchedRec r, 
     Cond cd;
     double x0, lower, upper;
     cond_load(cd, rr, d, qt, qc, x0, lower, upper, tmax);
+    cd.c0 = &qc[0]; cd.cn = &qc[1]; cd.c1 = &qc[2];
     double g0 = cd.eval(x0);
     for (int j = threadIdx.x; j < n; j += blockDim.x) out[j] = cd.eval(x[j]) - g0;
 }
 
-// Qnet.log_prob (qnet.pyx:1032) and the fused sufficient statistics, one CTA per chain.
+// Qnet.log_prob (qnet.pyx:1032) and the fused sufficient statistics (per slot), one CTA per chain.
 __global__ void __launch_bounds__(256) report_static_kernel(const SweepArgs A, double *logp_out,
                                                              double *ss_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int chain = blockIdx.x, Q = A.Q;
+    const int chain = blockIdx.x, Q = A.Q, NS = A.NS;
     const double *d = A.state + (size_t)chain * A.E;
     double *sm = reinterpret_cast<double *>(smem_raw);
     double *scratch = sm;
     double *red_out = scratch + 34 * 8;
     QConst *qc = reinterpret_cast<QConst *>(red_out + 8);
-    SuffStat *ss = reinterpret_cast<SuffStat *>(qc + Q);
-    int *q_type = reinterpret_cast<int *>(ss + Q);
+    SuffStat *ss = reinterpret_cast<SuffStat *>(qc + NS);
+    int *q_type = reinterpret_cast<int *>(ss + NS);
     int *q_dist = q_type + Q;
+    int *q_slot = q_dist + NS;
+    const unsigned char *aux = A.aux ? A.aux + (size_t)chain * A.E : nullptr;
     __shared__ double logp_sh;
-    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
-        q_type[q] = A.q_type[q]; q_dist[q] = A.q_dist[q];
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) q_type[q] = A.q_type[q];
+    for (int q = threadIdx.x; q <= Q; q += blockDim.x) q_slot[q] = A.q_slot[q];
+    for (int q = threadIdx.x; q < NS; q += blockDim.x) {
+        q_dist[q] = A.q_dist[q];
         int o = A.q_poff[q];
         const double *th = A.theta + (size_t)chain * A.P;
         qconst_set(qc[q], q_dist[q], th[o], q_dist[q] == D_EXP ? 0.0 : th[o + 1]);
     }
     __syncthreads();
-    chain_suffstats(A, d, q_type, q_dist, qc, ss, scratch, red_out, true, &logp_sh);
+    chain_suffstats(A, d, q_type, q_dist, qc, ss, scratch, red_out, true, &logp_sh, q_slot, aux);
     if (threadIdx.x == 0 && logp_out) logp_out[chain] = logp_sh;
     if (ss_out)
-        for (int i = threadIdx.x; i < Q * 8; i += blockDim.x)
-            ss_out[(size_t)chain * Q * 8 + i] = reinterpret_cast<double *>(ss)[i];
+        for (int i = threadIdx.x; i < NS * 8; i += blockDim.x)
+            ss_out[(size_t)chain * NS * 8 + i] = reinterpret_cast<double *>(ss)[i];
 }
 
 }  // namespace bq

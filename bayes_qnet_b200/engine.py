@@ -19,12 +19,17 @@ SUFFSTAT_FIELDS = ("n", "sum", "sumlog", "sumsq", "nlog", "wait", "nall", "nzero
 
 
 def flatten_model(net):
+    """The bq_model arrays: per queue discipline / servers / family / parameter offset, and -- when some queue has a
+    mixture template -- the distribution slots (one per plain queue, one per mixture component)."""
     q_type = capi.as_i32([q.code for q in net.queues])
     q_k = capi.as_i32([q.k for q in net.queues])
     q_dist = capi.as_i32([q.service.code for q in net.queues])
     npar = [q.service.numParameters() for q in net.queues]
     q_poff = capi.as_i32(numpy.concatenate(([0], numpy.cumsum(npar)[:-1])))
-    return q_type, q_k, q_dist, q_poff, int(sum(npar))
+    comps = [q.service.component_codes() for q in net.queues]
+    q_slot = capi.as_i32(numpy.concatenate(([0], numpy.cumsum([len(c) for c in comps]))))
+    slot_dist = capi.as_i32([f for c in comps for f in c])
+    return q_type, q_k, q_dist, q_poff, int(sum(npar)), q_slot, slot_dist
 
 
 class GibbsEngine(object):
@@ -38,10 +43,15 @@ class GibbsEngine(object):
         soa = arrv.soa()
         self.E = len(soa["d"])
         self.Q = len(net.queues)
-        q_type, q_k, q_dist, q_poff, self.P = flatten_model(net)
-        self._keep = [q_type, q_k, q_dist, q_poff]
+        q_type, q_k, q_dist, q_poff, self.P, q_slot, slot_dist = flatten_model(net)
+        self._keep = [q_type, q_k, q_dist, q_poff, q_slot, slot_dist]
+        self.q_slot = q_slot
+        self.NS = int(q_slot[-1])
+        self.has_mix = self.NS > self.Q
         m = capi.BqModel(self.Q, self.P, capi.ptr(q_type, capi.c_i32p), capi.ptr(q_k, capi.c_i32p),
-                         capi.ptr(q_dist, capi.c_i32p), capi.ptr(q_poff, capi.c_i32p))
+                         capi.ptr(q_dist, capi.c_i32p), capi.ptr(q_poff, capi.c_i32p),
+                         self.NS if self.has_mix else 0, capi.ptr(q_slot, capi.c_i32p) if self.has_mix else None,
+                         capi.ptr(slot_dist, capi.c_i32p) if self.has_mix else None)
         arrs = dict((k, capi.as_i32(soa[k])) for k in ("qid", "tid", "prev_byt", "next_byt", "prev_byq", "next_byq"))
         oa = numpy.ascontiguousarray(soa["obs_a"], dtype=numpy.uint8)
         od = numpy.ascontiguousarray(soa["obs_d"], dtype=numpy.uint8)
@@ -57,6 +67,8 @@ class GibbsEngine(object):
                                self.chain_offset, self.seed, int(device), ctypes.byref(h)))
         self._h = h
         self._L = L
+        if self.has_mix:  # the events' components travel with the state (Event.auxiliaries)
+            self.set_aux(soa["aux"])
 
     # ---- lifetime -----------------------------------------------------------------------------------
     def close(self):
@@ -188,6 +200,18 @@ class GibbsEngine(object):
         dd = numpy.ascontiguousarray(numpy.broadcast_to(numpy.asarray(d, dtype=numpy.float64), (hi - lo, self.E)))
         capi.check(self._L.bq_set_state(self._h, lo, hi, capi.ptr(dd, capi.c_f64p)))
 
+    def aux(self, lo=0, hi=None):
+        """Mixture component of every event [hi-lo, E] (zeros for plain queues); mixture networks only."""
+        hi = self.n_chains if hi is None else hi
+        out = numpy.empty((hi - lo, self.E), dtype=numpy.uint8)
+        capi.check(self._L.bq_get_aux(self._h, lo, hi, capi.ptr(out, capi.c_u8p)))
+        return out
+
+    def set_aux(self, aux, lo=0, hi=None):
+        hi = self.n_chains if hi is None else hi
+        z = numpy.ascontiguousarray(numpy.broadcast_to(numpy.asarray(aux, dtype=numpy.uint8), (hi - lo, self.E)))
+        capi.check(self._L.bq_set_aux(self._h, lo, hi, capi.ptr(z, capi.c_u8p)))
+
     def broadcast_state(self, d):
         """One chain's departure times [E] replicated to every chain (only E*8 bytes cross PCIe)."""
         dd = capi.as_f64(d)
@@ -204,7 +228,8 @@ class GibbsEngine(object):
         out._proc[:] = st["proc"][0]
         out._prev_byq[:] = st["prev_byq"][0]
         out._next_byq[:] = st["next_byq"][0]
-        has = out._prev_byq >= 0
+        if self.has_mix:
+            out._aux[:] = self.aux(chain, chain + 1)[0]
         return out
 
     def write_back(self, arrv, chain=0):
@@ -216,6 +241,8 @@ class GibbsEngine(object):
         arrv._proc[:] = st["proc"][0]
         arrv._prev_byq[:] = st["prev_byq"][0]
         arrv._next_byq[:] = st["next_byq"][0]
+        if self.has_mix:
+            arrv._aux[:] = self.aux(chain, chain + 1)[0]
 
     # ---- parity hooks and reporting ---------------------------------------------------------------------
     def logcond(self, chain, row, xs):
@@ -253,14 +280,17 @@ class GibbsEngine(object):
         return out
 
     def suffstats(self):
-        """[n_chains, n_queues, 8]: see SUFFSTAT_FIELDS."""
-        out = numpy.empty((self.n_chains, self.Q, 8), dtype=numpy.float64)
+        """[n_chains, n_queues, 8]: see SUFFSTAT_FIELDS.  With mixture templates one row per distribution slot
+        ([n_chains, n_slots, 8]; slots of queue q: q_slot[q] .. q_slot[q+1]-1)."""
+        out = numpy.empty((self.n_chains, self.NS, 8), dtype=numpy.float64)
         capi.check(self._L.bq_suffstats(self._h, capi.ptr(out, capi.c_f64p)))
         return out
 
     def mean_wait(self):
         ss = self.suffstats()
-        return ss[:, :, 5] / numpy.maximum(ss[:, :, 6], 1.0)
+        w = numpy.add.reduceat(ss[:, :, 5], self.q_slot[:-1], axis=1)
+        n = numpy.add.reduceat(ss[:, :, 6], self.q_slot[:-1], axis=1)
+        return w / numpy.maximum(n, 1.0)
 
     def stats(self):
         st = capi.BqStats()

@@ -241,6 +241,14 @@ def initialize(net, arrv, kind="DFN2", sample_paths=True):
     d = numpy.concatenate((osoa["d"], numpy.asarray(new["d"], dtype=numpy.float64)))
     eid = numpy.concatenate((osoa["eid"], numpy.asarray(new["eid"], dtype=numpy.int32)))
     flag = numpy.concatenate((numpy.ones(len(rows_obs), dtype=numpy.uint8), numpy.zeros(nh, dtype=numpy.uint8)))
-    result = _arrivals.Arrivals.from_arrays(net, tid, qid, state, a, d, flag, flag.copy(), eid=eid)
+    # mixture components: observed events keep theirs, hidden events of a mixture queue get a uniformly random one
+    # (initialize_auxiliaries, queues.pyx:1394-1400); every sweep starts by resampling them anyway
+    aux = numpy.zeros(len(tid), dtype=numpy.uint8)
+    aux[:len(rows_obs)] = soa["aux"][rows_obs]
+    for q in range(nq):
+        if net.queues[q].is_mixture():
+            rows = len(rows_obs) + numpy.nonzero(qid[len(rows_obs):] == q)[0]
+            aux[rows] = numpy.random.randint(len(net.queues[q].service.mixing), size=len(rows))
+    result = _arrivals.Arrivals.from_arrays(net, tid, qid, state, a, d, flag, flag.copy(), eid=eid, aux=aux)
     result.validate()
     return result

@@ -196,6 +196,8 @@ class Qnet(object):
         else:
             eng = hit[0]
             eng.set_state(soa["d"])
+        if eng.has_mix:
+            eng.set_aux(soa["aux"])
         eng.set_params(self.parameters)
         return eng
 
@@ -348,7 +350,7 @@ def _simulate(net, n):
     ps_clock = [0.0] * nq
     ps_active = [dict() for _ in range(nq)]
     ps_version = [0] * nq
-    rows = dict(tid=[], qid=[], state=[], a=[], d=[], proc=[])
+    rows = dict(tid=[], qid=[], state=[], a=[], d=[], proc=[], aux=[])
     heap = []
     seq = 0
     s0 = fsm.initial_state()
@@ -383,6 +385,10 @@ def _simulate(net, n):
             qid = fsm.sample_one_obs(sid)
             q = net.queues[qid]
             s = q.sample_service()
+            comp = 0
+            if isinstance(s, tuple):  # mixture template: (service time, component)   (queues.pyx:1459-1462)
+                s, comp = s
+            rows["aux"].append(comp)
             row = len(rows["tid"])
             rows["tid"].append(tid); rows["qid"].append(qid); rows["state"].append(sid); rows["a"].append(t)
             if q.code == _queues.Q_PS:
@@ -418,4 +424,4 @@ def _simulate(net, n):
                 seq += 1
 
     return _arrivals.Arrivals.from_arrays(net, rows["tid"], rows["qid"], rows["state"], rows["a"], rows["d"],
-                                          proc=rows["proc"])
+                                          proc=rows["proc"], aux=rows["aux"])

@@ -113,9 +113,16 @@ def _parse_args(tag):
 
 def _tmpl_from_yaml(tag, qname, universe):
     dist_type, args = _parse_args(tag)
-    if dist_type == "MIX":
-        raise NotImplementedError("queue %s: mixture service templates are outside the GPU hot path "
-                                  "(SURVEY.md section 8f N4)" % qname)
+    if dist_type == "MIX":  # [MIX, w0, [M, 3.0], w1, [LN, 0.0, 1.0], ...]   (qnetu.py:142-155)
+        ws, dists = [], []
+        for i in range(0, len(args), 2):
+            ws.append(args[i])
+            subtype, subargs = _parse_args(args[i + 1])
+            dists.append(_dist_from_yaml(subtype, subargs))
+        var_name = "COMPONENT_%s" % qname
+        if universe is not None:
+            universe[var_name] = list(range(len(ws)))
+        return queues.MixtureTemplate(var_name, ws, dists)
     return queues.DistributionTemplate(_dist_from_yaml(dist_type, args))
 
 

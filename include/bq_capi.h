@@ -64,6 +64,14 @@ typedef struct {
     const int32_t *q_k;         /* [n_queues] processors (1 for DELAY / PS)                             */
     const int32_t *q_dist;      /* [n_queues] BQ_D_*                                                    */
     const int32_t *q_param_off; /* [n_queues] offset of the queue's first parameter                     */
+    /* Mixture service templates (MixtureTemplate, queues.pyx:1373-1509; YAML [MIX, w0, [..], w1, [..], ...]).  n_slots = 0:
+     * none, q_dist holds each queue's family.  Otherwise every queue owns the distribution slots q_slot_off[q] ..
+     * q_slot_off[q+1]-1 (one for a plain queue, one per component for a mixture), slot_dist gives their families and
+     * q_dist is ignored.  Parameters of a mixture queue: its mixing weights, then each component's parameters
+     * (MixtureTemplate.getParameters, queues.pyx:1470-1474).  Static-order networks only. */
+    int32_t n_slots;
+    const int32_t *q_slot_off;  /* [n_queues + 1] */
+    const int32_t *slot_dist;   /* [n_slots] BQ_D_* */
 } bq_model;
 
 /* Flattened Arrivals (arrivals.pxd:11-37 Event fields, arrivals.pyx:240 Arrivals).  Event index =
@@ -122,6 +130,11 @@ int bq_set_state(bq_handle *h, int32_t chain_lo, int32_t chain_hi, const double 
 int bq_broadcast_state(bq_handle *h, const double *d);
 int bq_get_state(bq_handle *h, int32_t chain_lo, int32_t chain_hi, double *d, double *a, double *s,
                  int32_t *proc, int32_t *prev_byq, int32_t *next_byq);
+/* Mixture component of every event (Event.auxiliaries / Event.variable, arrivals.pxd:36): aux[(chain_hi-chain_lo) * E],
+ * 0 for events of plain queues.  Only handles created with mixture templates hold them (BQ_ERR_INVALID otherwise).
+ * New handles start with component 0 everywhere; every sweep resamples them first (qnet.pyx:679-680). */
+int bq_set_aux(bq_handle *h, int32_t chain_lo, int32_t chain_hi, const uint8_t *aux);
+int bq_get_aux(bq_handle *h, int32_t chain_lo, int32_t chain_hi, uint8_t *aux);
 /* Same, but d is DEVICE memory laid out [n_chains][E] (zero-copy access for torch callers). */
 int bq_state_dev(bq_handle *h, double **d_dev, int64_t *chain_stride);
 
@@ -166,7 +179,8 @@ int bq_mh_proposal(bq_handle *h, int32_t chain, int32_t eid, const double *x, in
 int bq_gibbs_kernel(bq_handle *h, const double *d_to, int32_t n_to, int32_t strict, double *out);
 /* Qnet.log_prob (qnet.pyx:1032): out[n_chains] */
 int bq_log_prob(bq_handle *h, double *out);
-/* Per chain per queue sufficient statistics over events with s>0 (queues.pyx:1317):
+/* Per chain per queue (with mixture templates: per distribution slot, n_slots of them) sufficient statistics over
+ * events with s>0 (queues.pyx:1317):
  * out[n_chains * n_queues * 8] = {N, sum s, sum log s, sum (log s - mean log s)^2, #log terms, sum wait,
  * n_events, #(s == 0)} */
 int bq_suffstats(bq_handle *h, double *out);

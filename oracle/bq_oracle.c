@@ -53,6 +53,10 @@ typedef struct {
     const uint8_t *obs_a, *obs_d;              /* [E] */
     double *a, *d, *s;                         /* [E] chain state */
     int *proc, *prev_byq, *next_byq;           /* [E] chain state */
+    /* mixture templates (MixtureTemplate, queues.pyx:1373-1509): NULL aux = none.  Otherwise every event's service
+     * density is the one of slot q_slot[qid] + aux[e] (serviceLikelihood, queues.pyx:1455-1457) */
+    const int *q_slot, *slot_dist, *slot_poff; /* [Q+1], [NS], [NS] */
+    const uint8_t *aux;                        /* [E] component of each event */
 } bqo_state;
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -71,9 +75,13 @@ double bqo_lpdf(int dist, double p0, double p1, double x) {
     }
 }
 
-static double q_lpdf(const bqo_state *st, int q, double x) {
-    int o = st->q_poff[q];
-    return bqo_lpdf(st->q_dist[q], st->theta[o], st->q_dist[q] == D_EXP ? 0.0 : st->theta[o + 1], x);
+static double q_lpdf(const bqo_state *st, int q, int e, double x) {
+    int o = st->q_poff[q], dist = st->q_dist[q];
+    if (st->aux) {
+        int sl = st->q_slot[q] + st->aux[e];
+        o = st->slot_poff[sl]; dist = st->slot_dist[sl];
+    }
+    return bqo_lpdf(dist, st->theta[o], dist == D_EXP ? 0.0 : st->theta[o + 1], x);
 }
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -175,7 +183,7 @@ double bqo_log_prob(const bqo_state *st) {
     int e;
     for (e = 0; e < st->E; ++e) {
         if (st->s[e] < 0.0) return -INFINITY;
-        r += q_lpdf(st, st->qid[e], st->s[e]);
+        r += q_lpdf(st, st->qid[e], e, st->s[e]);
     }
     return r;
 }
@@ -212,7 +220,7 @@ static double queue_delta(const bqo_state *st, int q, const int *lst_new, int n,
     if (!bad) {
         for (i = 0; i < n; ++i) {
             int e = lst_new[i];
-            if (s[i] != st->s[e] || st->q_type[q] == Q_PS) delta += q_lpdf(st, q, s[i]) - q_lpdf(st, q, st->s[e]);
+            if (s[i] != st->s[e] || st->q_type[q] == Q_PS) delta += q_lpdf(st, q, e, s[i]) - q_lpdf(st, q, e, st->s[e]);
         }
         if (st->q_type[q] == Q_PS) {
             for (i = 0; i < n; ++i) {
@@ -411,11 +419,11 @@ static double prev_by_proc_d(const bqo_state *st, int e) {
 
 /* TWOS proposal (queues.pyx:1239-1256): departureLik(e) + arrivalLik(e1) on the intersection of their supports
  * (pwfun.pyx:183-202).  GGk: queues.pyx:394-430, 458-468; DelayStation: queues.pyx:750-756.  -inf outside. */
-typedef struct { double b0, d1, dp1, L, U; int q0, q1, has1, fifo1; } mhprop;
+typedef struct { double b0, d1, dp1, L, U; int q0, q1, has1, fifo1, e0, e1; } mhprop;
 
 static void mh_setup(const bqo_state *st, int e, mhprop *pr) {
     int e1 = st->next_byt[e];
-    pr->q0 = st->qid[e]; pr->q1 = -1; pr->has1 = 0; pr->fifo1 = 0; pr->d1 = 0.0; pr->dp1 = 0.0;
+    pr->e0 = e; pr->e1 = e1; pr->q0 = st->qid[e]; pr->q1 = -1; pr->has1 = 0; pr->fifo1 = 0; pr->d1 = 0.0; pr->dp1 = 0.0;
     pr->b0 = st->a[e];
     if (st->q_type[pr->q0] == Q_GGK) { double dp = prev_by_proc_d(st, e); if (dp > pr->b0) pr->b0 = dp; }
     pr->L = pr->b0; pr->U = INFINITY;
@@ -428,11 +436,11 @@ static void mh_setup(const bqo_state *st, int e, mhprop *pr) {
 static double mh_eval(const bqo_state *st, const mhprop *pr, double x) {
     double v;
     if (x < pr->L || x > pr->U) return -INFINITY;
-    v = q_lpdf(st, pr->q0, x - pr->b0);
+    v = q_lpdf(st, pr->q0, pr->e0, x - pr->b0);
     if (pr->has1) {
         double m = x;
         if (pr->fifo1 && pr->dp1 > m) m = pr->dp1;
-        v += q_lpdf(st, pr->q1, pr->d1 - m);
+        v += q_lpdf(st, pr->q1, pr->e1, pr->d1 - m);
     }
     return v;
 }

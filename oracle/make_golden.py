@@ -158,6 +158,23 @@ queues:
   - { name: WEB1, processors: 3, type: GGk, service: [LN, 1.75, 1.0] }
   - { name: APP1, processors: 3, type: GGk, service: [LN, 0.1, 2.0] }
 """,
+    # mixture service templates (test_mixture_template.py:41, test_qnet.py:1165-1199) on single-server queues
+    "mix": """
+states:
+  - name: INITIAL
+    queues: [ INITIAL ]
+    successors: [ TIER1 ]
+    initial: TRUE
+  - name: TIER1
+    queues: [ Q1 ]
+    successors: [ TIER2 ]
+  - name: TIER2
+    queues: [ Q2 ]
+queues:
+  - { name: INITIAL, service: [M, 1.0] }
+  - { name: Q1, service: [ MIX, 0.6, [M, 0.3], 0.4, [LN, 0.0, 0.7] ] }
+  - { name: Q2, service: [ MIX, 0.5, [G, 2.0, 0.2], 0.5, [M, 1.0] ] }
+""",
     # processor sharing + delay station (test_ps.py:266-292 + test_delay_station.py:116-126): config 4's shape
     "psdelay": """
 states:
@@ -185,6 +202,7 @@ COND = {
     "mm3": (80, 0.2, "DFN2", 17, 5),
     "lnk": (60, 0.2, "DFN2", 18, 5),
     "psdelay": (50, 0.2, "PS", 19, 3),
+    "mix": (70, 0.3, "DFN2", 20, 3),
 }
 
 # name -> (tasks, pct, initializer, seed, iterations, replicas)
@@ -219,8 +237,19 @@ def flatten(arrv):
         next_byt=numpy.array([lk(e.next_by_task()) for e in evts], dtype=numpy.int32),
         prev_byq=numpy.array([lk(e.previous_by_queue()) for e in evts], dtype=numpy.int32),
         next_byq=numpy.array([lk(e.next_by_queue()) for e in evts], dtype=numpy.int32),
+        aux=numpy.array([_component(e) for e in evts], dtype=numpy.uint8),
     )
     return out, evts
+
+
+def _component(e):
+    """Mixture component of the event (Event.variable of its queue's template), 0 for plain queues."""
+    name = "COMPONENT_%s" % e.queue().name
+    try:
+        v = e.variable(name)
+        return int(v) if v is not None else 0
+    except Exception:
+        return 0
 
 
 def make_state(name, ntasks, pct, init, seed):
@@ -569,8 +598,8 @@ if __name__ == "__main__":
         sys.exit(0)
     if not args.skip_mh:  # MH-within-Gibbs (gibbs_resample): proposal grids and long reference runs; no PS (queues.pyx:1140)
         for n in COND:
-            if n != "psdelay" and args.only in (None, n):
-                do_mh(n)
+            if n not in ("psdelay", "mix") and args.only in (None, n):  # no MH proposal for PS (queues.pyx:1140) nor for
+                do_mh(n)                                               # mixture templates (DepartureProposal wants a DistributionTemplate)
         for n in ("mm1", "qnet3", "mm3"):
             if args.only in (None, n) and not args.skip_post:
                 do_post(n, "MH")

@@ -19,7 +19,8 @@ class _State(ctypes.Structure):
     _fields_ = [("E", ctypes.c_int), ("Q", ctypes.c_int), ("q_type", i32p), ("q_k", i32p), ("q_dist", i32p),
                 ("q_poff", i32p), ("theta", f64p), ("qid", i32p), ("prev_byt", i32p), ("next_byt", i32p),
                 ("obs_a", u8p), ("obs_d", u8p), ("a", f64p), ("d", f64p), ("s", f64p), ("proc", i32p),
-                ("prev_byq", i32p), ("next_byq", i32p)]
+                ("prev_byq", i32p), ("next_byq", i32p), ("q_slot", i32p), ("slot_dist", i32p), ("slot_poff", i32p),
+                ("aux", u8p)]
 
 
 def build(force=False):
@@ -93,11 +94,38 @@ def philox_block(ctr, key, rounds):
 class OracleChain(object):
     """One chain of the CPU oracle.  Built from flat arrays (row indices as event ids)."""
 
-    def __init__(self, q_type, q_k, q_dist, theta, qid, prev_byt, next_byt, obs_a, obs_d, d, prev_byq, next_byq):
+    def __init__(self, q_type, q_k, q_dist, theta, qid, prev_byt, next_byt, obs_a, obs_d, d, prev_byq, next_byq,
+                 comp_dists=None, aux=None):
+        """comp_dists: per queue the list of its components' families (a one-element list for a plain queue) when the
+        network has mixture templates; aux: component of every event."""
         I = lambda x: numpy.ascontiguousarray(x, dtype=numpy.int32).copy()
         self.q_type, self.q_k, self.q_dist = I(q_type), I(q_k), I(q_dist)
-        npar = numpy.where(self.q_dist == 0, 1, 2)
-        self.q_poff = I(numpy.concatenate(([0], numpy.cumsum(npar)[:-1])))
+        self.mix = comp_dists is not None and any(len(c) > 1 for c in comp_dists)
+        if self.mix:
+            ncomp = [len(c) for c in comp_dists]
+            self.q_slot = I(numpy.concatenate(([0], numpy.cumsum(ncomp))))
+            self.slot_dist = I([f for c in comp_dists for f in c])
+            self.q_mixoff, self.slot_poff, off, poff = [], [], 0, []
+            for c in comp_dists:
+                poff.append(off)
+                if len(c) > 1:
+                    self.q_mixoff.append(off)
+                    off += len(c)
+                else:
+                    self.q_mixoff.append(-1)
+                for f in c:
+                    self.slot_poff.append(off)
+                    off += 1 if f == 0 else 2
+            self.slot_poff, self.q_poff = I(self.slot_poff), I(poff)
+            self.q_dist = I([c[0] for c in comp_dists])
+            self.aux = numpy.ascontiguousarray(numpy.zeros(len(d)) if aux is None else aux, dtype=numpy.uint8).copy()
+        else:
+            npar = numpy.where(self.q_dist == 0, 1, 2)
+            self.q_poff = I(numpy.concatenate(([0], numpy.cumsum(npar)[:-1])))
+            self.q_slot = I(numpy.arange(len(self.q_type) + 1))
+            self.slot_dist, self.slot_poff = self.q_dist, self.q_poff
+            self.q_mixoff = [-1] * len(self.q_type)
+            self.aux = None
         self.theta = numpy.ascontiguousarray(theta, dtype=numpy.float64).copy()
         self.qid, self.prev_byt, self.next_byt = I(qid), I(prev_byt), I(next_byt)
         self.obs_a = numpy.ascontiguousarray(obs_a, dtype=numpy.uint8).copy()
@@ -115,15 +143,76 @@ class OracleChain(object):
                           self.obs_a.ctypes.data_as(u8p), self.obs_d.ctypes.data_as(u8p),
                           self.a.ctypes.data_as(f64p), self.d.ctypes.data_as(f64p), self.s.ctypes.data_as(f64p),
                           self.proc.ctypes.data_as(i32p), self.prev_byq.ctypes.data_as(i32p),
-                          self.next_byq.ctypes.data_as(i32p))
+                          self.next_byq.ctypes.data_as(i32p), self.q_slot.ctypes.data_as(i32p),
+                          self.slot_dist.ctypes.data_as(i32p), self.slot_poff.ctypes.data_as(i32p),
+                          self.aux.ctypes.data_as(u8p) if self.mix else None)
         self.recompute()
 
     @classmethod
     def from_arrivals(cls, net, arrv, theta=None):
         soa = arrv.soa()
+        comps = [q.service.component_codes() for q in net.queues]
+        mix = any(len(c) > 1 for c in comps)
         return cls([q.code for q in net.queues], [q.k for q in net.queues], [q.service.code for q in net.queues],
                    net.parameters if theta is None else theta, soa["qid"], soa["prev_byt"], soa["next_byt"],
-                   soa["obs_a"], soa["obs_d"], soa["d"], soa["prev_byq"], soa["next_byq"])
+                   soa["obs_a"], soa["obs_d"], soa["d"], soa["prev_byq"], soa["next_byq"],
+                   comp_dists=comps if mix else None, aux=soa["aux"] if mix else None)
+
+    # ---- mixture templates (MixtureTemplate, queues.pyx:1373-1509), restated in Python on top of the C density ----
+    def resample_aux(self, seed, chain, sweep):
+        """z_e ~ Cat(pi_i exp(lpdf_i(s_e))) for every event of every mixture queue, from uniform 0 of the stream
+        (chain, sweep, event, tag 6); all weights below 1e-50 in total: a uniformly random component
+        (_roll_die_unnorm, sampling.pyx:215-229)."""
+        if not self.mix:
+            return
+        for e in range(self.E):
+            q = int(self.qid[e])
+            s0, nc = int(self.q_slot[q]), int(self.q_slot[q + 1] - self.q_slot[q])
+            if nc < 2:
+                continue
+            w = []
+            for c in range(nc):
+                o, f = int(self.slot_poff[s0 + c]), int(self.slot_dist[s0 + c])
+                lp = lpdf(f, self.theta[o], self.theta[o + 1] if f != 0 else 0.0, self.s[e])
+                w.append(self.theta[self.q_mixoff[q] + c] * numpy.exp(lp))
+            u = rng_uniforms(seed, chain, sweep, e, 6, 1)[0]
+            Z = sum(w)
+            if Z < 1e-50:
+                pick = min(int(u * nc), nc - 1)
+            else:
+                t, S, pick = Z * u, 0.0, nc - 1
+                for c in range(nc):
+                    S += w[c]
+                    if t < S:
+                        pick = c
+                        break
+            self.aux[e] = pick
+
+    def slot_suffstats(self):
+        """[NS, 8] in engine.SUFFSTAT_FIELDS order, each slot over the events currently assigned to it."""
+        out = numpy.zeros((len(self.slot_dist), 8))
+        for e in range(self.E):
+            q = int(self.qid[e])
+            sl = int(self.q_slot[q]) + (int(self.aux[e]) if self.mix else 0)
+            f, s = int(self.slot_dist[sl]), self.s[e]
+            w = self.d[e] - self.a[e] - s
+            o = out[sl]
+            o[5] += w if w > 0 else 0.0
+            o[6] += 1.0
+            if s > 0:
+                o[0] += 1.0; o[1] += s
+                if f == 1 or (f == 2 and s >= 1e-50):
+                    o[2] += numpy.log(s); o[4] += 1.0
+            elif s == 0:
+                o[7] += 1.0
+        for sl in range(len(self.slot_dist)):
+            if self.slot_dist[sl] == 2 and out[sl, 4] > 0:
+                mean = out[sl, 2] / out[sl, 4]
+                q = int(numpy.searchsorted(self.q_slot, sl, side="right") - 1)
+                for e in range(self.E):
+                    if self.qid[e] == q and (not self.mix or self.q_slot[q] + self.aux[e] == sl) and self.s[e] >= 1e-50:
+                        out[sl, 3] += (numpy.log(self.s[e]) - mean) ** 2
+        return out
 
     def set_theta(self, theta):
         self.theta[:] = theta
@@ -184,19 +273,28 @@ class OracleChain(object):
         return out
 
     def update_params(self, update, seed=0, chain=0, sweep=0):
-        """update in {'BAYES','STEM'}: applies Qnet.sample_parameters / Qnet.estimate to self.theta."""
-        ss = self.suffstats()
-        for q in range(self.Q):
-            o = int(self.q_poff[q])
+        """update in {'BAYES','STEM'}: applies Qnet.sample_parameters / Qnet.estimate to self.theta (per distribution
+        slot; mixing proportions (1 + count_i) / (n_components + N), queues.pyx:1416-1451)."""
+        ss = self.slot_suffstats() if self.mix else self.suffstats()
+        for sl in range(len(self.slot_dist)):
+            o, f = int(self.slot_poff[sl]), int(self.slot_dist[sl])
             p0 = ctypes.c_double(self.theta[o])
-            p1 = ctypes.c_double(self.theta[o + 1] if self.q_dist[q] != 0 else 0.0)
-            row = numpy.ascontiguousarray(ss[q])
+            p1 = ctypes.c_double(self.theta[o + 1] if f != 0 else 0.0)
+            row = numpy.ascontiguousarray(ss[sl])
             if update == "STEM":
-                lib().bqo_estimate(int(self.q_dist[q]), row.ctypes.data_as(f64p), ctypes.byref(p0), ctypes.byref(p1))
+                lib().bqo_estimate(f, row.ctypes.data_as(f64p), ctypes.byref(p0), ctypes.byref(p1))
             else:
-                lib().bqo_sample_params(int(self.q_dist[q]), row.ctypes.data_as(f64p), seed, chain, sweep, q,
+                lib().bqo_sample_params(f, row.ctypes.data_as(f64p), seed, chain, sweep, sl,
                                         ctypes.byref(p0), ctypes.byref(p1))
             self.theta[o] = p0.value
-            if self.q_dist[q] != 0:
+            if f != 0:
                 self.theta[o + 1] = p1.value
+        if self.mix:
+            for q in range(self.Q):
+                mo, s0, nc = self.q_mixoff[q], int(self.q_slot[q]), int(self.q_slot[q + 1] - self.q_slot[q])
+                if mo < 0:
+                    continue
+                N = nc + ss[s0:s0 + nc, 6].sum()
+                for c in range(nc):
+                    self.theta[mo + c] = (1.0 + ss[s0 + c, 6]) / N
         return self.theta.copy()

@@ -62,7 +62,8 @@ def golden_state(g, prefix, theta=None):
     p = prefix + "_"
     arrv = Arrivals.from_arrays(net, g[p + "tid"], g[p + "qid"], g[p + "state"], g[p + "a"], g[p + "d"],
                                 g[p + "obs_a"], g[p + "obs_d"], eid=g[p + "eid"],
-                                prev_byq=g[p + "prev_byq"], next_byq=g[p + "next_byq"])
+                                prev_byq=g[p + "prev_byq"], next_byq=g[p + "next_byq"],
+                                aux=g[p + "aux"] if (p + "aux") in g else None)
     return net, arrv
 
 
