@@ -560,7 +560,8 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_static_kernel(const S
     int *q_dist = q_type + Q;      // per slot
     int *q_poff = q_dist + NS;     // per slot
     int *q_slot = q_poff + NS;     // [Q + 1]
-    unsigned char *aux = A.aux ? A.aux + (size_t)chain * E : nullptr;
+    // the all-exponential build never carries mixtures (bq_create): a compile-time null keeps its code as it was
+    unsigned char *aux = (!ALL_EXP && A.aux) ? A.aux + (size_t)chain * E : nullptr;
     __shared__ unsigned long long cnt[5];
     __shared__ double logp_sh;
     __shared__ int work_ctr[2];
