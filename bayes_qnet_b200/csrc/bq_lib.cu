@@ -19,6 +19,7 @@
 #include "bq_static.cuh"
 #include "bq_dynamic.cuh"
 #include "bq_chib.cuh"
+#include "bq_cluster.cuh"
 #include "bq_host.h"
 
 using namespace bq;
@@ -58,6 +59,11 @@ struct bq_handle {
     std::vector<int> slot_dist, slot_poff, q_slot, q_mixoff;
     int *d_slot_dist = nullptr, *d_slot_poff = nullptr, *d_q_slot = nullptr, *d_q_mixoff = nullptr;
     unsigned char *d_aux = nullptr;  // [C][E] mixture component of every event
+    // thread-block cluster path (bq_cluster.cuh): CTAs per chain (1 = off), partition size, encoding shift, tables
+    int ncta = 1, cpart = 0, ck = 0;
+    size_t csmem = 0;
+    int4 *d_crec = nullptr;
+    int *d_class_off = nullptr, *d_qe_idx = nullptr, *d_qe_p = nullptr, *d_qe_pt = nullptr;
     std::vector<int> qid, tid, prev_byt, next_byt, prev_byq, next_byq;
     std::vector<uint8_t> obs_a, obs_d;
     std::vector<int> color_off, order;
@@ -132,7 +138,7 @@ static SchedRec make_rec(const bq_handle *h, int e) {
     r.p1 = -1; r.pt_p1 = -1; r.pt_n1 = -1;
     r.q0 = h->qid[e];
     r.q1 = -1;
-    r.pad = 0;
+    r.pad = e;
     if (r.e1 >= 0) {
         r.q1 = h->qid[r.e1];
         r.p1 = h->prev_byq[r.e1];
@@ -567,6 +573,9 @@ static void launch_dynamic(bq_handle *h, const DynArgs &A) {
     else launch_dynamic_w<32>(h, A);
 }
 
+static size_t cluster_smem_bytes(const bq_handle *h, int part);
+static int build_cluster_plan(bq_handle *h, int ncta);
+
 extern "C" int bq_destroy(bq_handle *h) {
     if (!h) return BQ_OK;
     cudaSetDevice(h->device);
@@ -576,7 +585,7 @@ extern "C" int bq_destroy(bq_handle *h) {
                     h->d_tr_theta, h->d_tr_wait, h->d_tr_logp, h->d_scratch, h->d_order, h->d_qinfo,
                     h->d_ord, h->d_pos, h->d_dord, h->d_dpos, h->d_prec, h->d_flag, h->d_sq, h->d_dt, h->d_claim,
                     h->d_claimd, h->d_init_topo, h->d_init_ub, h->d_slot_dist, h->d_slot_poff, h->d_q_slot, h->d_q_mixoff,
-                    h->d_aux};
+                    h->d_aux, h->d_crec, h->d_class_off, h->d_qe_idx, h->d_qe_p, h->d_qe_pt};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -784,6 +793,27 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         if (t >= 1 && t <= 32) h->refill = t;
     }
 #undef CKB
+    // thread-block clusters (bq_cluster.cuh): when one CTA's shared memory cannot hold the chain, or when there are too
+    // few chains to fill the GPU with one CTA each.  BQ_CLUSTER=n forces n CTAs per chain (1 = never).
+    if (h->static_order && !h->has_mix) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        int want = 1;
+        if (!h->use_smem) {
+            for (int n = 2; n <= 8 && want == 1; n *= 2)
+                if (cluster_smem_bytes(h, (((E + n - 1) / n) + 1) & ~1) + 1024 <= (size_t)max_optin) want = n;
+        } else if (h->C * 8 <= sms - sms % 8) want = 8;
+        else if (h->C * 4 <= sms) want = 4;
+        else if (h->C * 2 <= sms) want = 2;
+        if (const char *env = getenv("BQ_CLUSTER")) {
+            const int n = atoi(env);
+            if (n == 1 || n == 2 || n == 4 || n == 8) want = n;
+        }
+        if (getenv("BQ_FORCE_GLOBAL")) want = (getenv("BQ_CLUSTER") ? want : 1);
+        if (want > 1 && cluster_smem_bytes(h, (((E + want - 1) / want) + 1) & ~1) + 1024 <= (size_t)max_optin) {
+            if (int rc = build_cluster_plan(h, want)) { std::string msg = g_err; bq_destroy(h); return fail(rc, msg); }
+        }
+    }
     *out = h;
     return BQ_OK;
 }
@@ -971,6 +1001,78 @@ static int ensure_dynamic(bq_handle *h) {
     return BQ_OK;
 }
 
+// ---- cluster path: the chain state partitioned over the shared memories of ncta CTAs -------------------------------
+static size_t cluster_smem_bytes(const bq_handle *h, int part) {
+    size_t b = ((size_t)part + 34 * 8 + 8 + 64 + ((h->P + 1) & ~1)) * sizeof(double);
+    b += (size_t)h->NS * (sizeof(QConst) + sizeof(SuffStat)) + (size_t)(2 * h->Q + 2 * h->NS + 2) * sizeof(int);
+    return (b + 15) & ~(size_t)15;
+}
+
+static int build_cluster_plan(bq_handle *h, int ncta) {
+    const int E = h->E, n = (int)h->recs.size(), n_colors = (int)h->color_off.size() - 1;
+    int part = (E + ncta - 1) / ncta;
+    part = (part + 1) & ~1;
+    int k = 0;
+    while ((1 << k) < part) ++k;
+    auto enc = [&](int e) { return e < 0 ? -1 : (((e / part) << k) | (e % part)); };
+    std::vector<SchedRec> crec;
+    crec.reserve(n);
+    std::vector<int> class_off((size_t)n_colors * (ncta + 1), 0);
+    for (int c = 0; c < n_colors; ++c)
+        for (int r = 0; r <= ncta; ++r) {
+            class_off[(size_t)c * (ncta + 1) + r] = (int)crec.size();
+            if (r == ncta) break;
+            for (int i = h->color_off[c]; i < h->color_off[c + 1]; ++i) {
+                const SchedRec &s = h->recs[i];
+                if (s.e / part != r) continue;
+                SchedRec t = s;
+                t.e = enc(s.e); t.pt_e = enc(s.pt_e); t.p = enc(s.p); t.n = enc(s.n); t.pt_n = enc(s.pt_n);
+                t.e1 = enc(s.e1); t.p1 = enc(s.p1); t.pt_p1 = enc(s.pt_p1); t.pt_n1 = enc(s.pt_n1);
+                t.pad = s.e;
+                crec.push_back(t);
+            }
+        }
+    std::vector<int> qe_idx(E), qe_p(E), qe_pt(E), fill(h->q_off.begin(), h->q_off.end() - 1);
+    for (int e = 0; e < E; ++e) {
+        const int j = fill[h->qid[e]]++;
+        qe_idx[j] = enc(e); qe_p[j] = enc(h->prev_byq[e]); qe_pt[j] = enc(h->prev_byt[e]);
+    }
+    CK(upload(&h->d_crec, crec.data(), crec.size() * 3));
+    CK(upload(&h->d_class_off, class_off.data(), class_off.size()));
+    CK(upload(&h->d_qe_idx, qe_idx.data(), (size_t)E));
+    CK(upload(&h->d_qe_p, qe_p.data(), (size_t)E));
+    CK(upload(&h->d_qe_pt, qe_pt.data(), (size_t)E));
+    h->ncta = ncta; h->cpart = part; h->ck = k;
+    h->csmem = cluster_smem_bytes(h, part);
+    return BQ_OK;
+}
+
+static int launch_cluster(bq_handle *h, const SweepArgs &A) {
+    ClusterArgs CA;
+    CA.A = A;
+    CA.A.rec = h->d_crec;
+    CA.ncta = h->ncta; CA.part = h->cpart; CA.k = h->ck;
+    CA.class_off = h->d_class_off; CA.qe_idx = h->d_qe_idx; CA.qe_p = h->d_qe_p; CA.qe_pt = h->d_qe_pt;
+    const void *fn = h->all_exp ? (const void *)sweep_cluster_kernel<true> : (const void *)sweep_cluster_kernel<false>;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->csmem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(h->C * h->ncta), 1, 1);
+    cfg.blockDim = dim3((unsigned)h->threads, 1, 1);
+    cfg.dynamicSmemBytes = h->csmem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)h->ncta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (h->all_exp) CK(cudaLaunchKernelEx(&cfg, sweep_cluster_kernel<true>, CA));
+    else CK(cudaLaunchKernelEx(&cfg, sweep_cluster_kernel<false>, CA));
+    return BQ_OK;
+}
+
 static int launch_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t update, uint32_t flags) {
     if (!h) return fail(BQ_ERR_INVALID, "null handle");
     if (n_sweeps < 0) return fail(BQ_ERR_INVALID, "n_sweeps < 0");
@@ -999,6 +1101,9 @@ static int launch_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t up
         fill_dyn_args(h, D);
         D.n_sweeps = n_sweeps; D.update = update; D.flags = (int)flags; D.trace_base = h->trace_len; D.mode = mode;
         launch_dynamic(h, D);
+    } else if (h->ncta > 1) {
+        h->dyn_stale = true;
+        if (int rc = launch_cluster(h, A)) return rc;
     } else if (h->use_smem) {
         h->dyn_stale = true;
         if (h->all_exp) sweep_static_kernel<true, true><<<h->C, h->threads, h->smem_bytes, h->stream>>>(A);
@@ -1499,6 +1604,12 @@ extern "C" int bq_philox_block(const uint32_t ctr[4], const uint32_t key[2], int
     if (rounds == 7) philox4x32<7>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
     else if (rounds == 10) philox4x32<10>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
     else return fail(BQ_ERR_INVALID, "bq_philox_block: rounds must be 7 or 10");
+    return BQ_OK;
+}
+
+extern "C" int bq_cluster_size(bq_handle *h, int32_t *ncta) {
+    if (!h || !ncta) return fail(BQ_ERR_INVALID, "null argument");
+    *ncta = h->ncta;
     return BQ_OK;
 }
 

@@ -42,7 +42,7 @@ struct SchedRec {
     int pt_n1;  // previous-by-task of e1's queue successor: a_{n1}
     int q0;     // queue of e
     int q1;     // queue of e1
-    int pad;
+    int pad;    // the event's id for the RNG stream (= e, except in the cluster kernel's re-encoded records)
 };
 
 struct SweepArgs {
@@ -94,7 +94,10 @@ struct Cond {
 
 // qc is indexed by slot; with mixture templates (aux != null) an event's slot is its queue's first slot plus its
 // component, otherwise the queue index itself
-__device__ __forceinline__ void cond_load(Cond &c, const SchedRec &r, const double *d, const int *q_type,
+// DT: how the chain's departure times are addressed -- a plain pointer (shared or global memory), or a view that spreads
+// them over the shared memories of a thread-block cluster (bq_cluster.cuh)
+template <class DT>
+__device__ __forceinline__ void cond_load(Cond &c, const SchedRec &r, const DT &d, const int *q_type,
                                           const QConst *qc, double &x0, double &lower, double &upper,
                                           double tmax, const int *q_slot = nullptr, const unsigned char *aux = nullptr) {
     x0 = d[r.e];
@@ -151,7 +154,8 @@ struct CondExp {
         double v = fma(invn, dmax(a_n, d), fma(inv1, dmax(d, d_p1), -inv0 * d));
         return (d >= flo && d <= fhi) ? v : BQ_NEG_INF;
     }
-    __device__ __forceinline__ void load(const SchedRec &r, const double *d, const int *q_type, const QConst *qc,
+    template <class DT>
+    __device__ __forceinline__ void load(const SchedRec &r, const DT &d, const int *q_type, const QConst *qc,
                                          double &x0, double &lower, double &upper, double tmax, const int *q_slot,
                                          const unsigned char *aux) {
         Cond c;
@@ -172,7 +176,8 @@ struct CondGen : Cond {
     __device__ __forceinline__ void idle(const QConst *qc) {
         b = a_n = d_n = d_e1 = d_p1 = 0.0; flo = 1.0; fhi = 0.0; has_n = has_e1 = e1_fifo = 0; c0 = cn = c1 = qc;
     }
-    __device__ __forceinline__ void load(const SchedRec &r, const double *d, const int *q_type, const QConst *qc,
+    template <class DT>
+    __device__ __forceinline__ void load(const SchedRec &r, const DT &d, const int *q_type, const QConst *qc,
                                          double &x0, double &lower, double &upper, double tmax, const int *q_slot,
                                          const unsigned char *aux) {
         cond_load(*this, r, d, q_type, qc, x0, lower, upper, tmax, q_slot, aux);
@@ -200,8 +205,8 @@ __device__ __forceinline__ void stream_pair(const Rng &r, unsigned int blk, doub
     ub = u53(o[2], o[3]);
 }
 
-template <class CondT>
-__device__ __forceinline__ void run_class(const SweepArgs &A, double *d, const int *q_type, const QConst *qc,
+template <class CondT, class DT>
+__device__ __forceinline__ void run_class(const SweepArgs &A, DT d, const int *q_type, const QConst *qc,
                                           int hi, int *ctr, double tmax, unsigned long long gchain,
                                           unsigned int gsw, long long &n_ev, long long &n_evals,
                                           long long &n_stuck, const int *q_slot, const unsigned char *aux) {
@@ -234,7 +239,7 @@ __device__ __forceinline__ void run_class(const SweepArgs &A, double *d, const i
                 cd.load(u.r, d, q_type, qc, x0, lower, upper, tmax, q_slot, aux);
                 if (A.flags & FLAG_TIGHT) { lower = fmax(lower, cd.flo); upper = fmin(upper, cd.fhi); }
                 e = u.r.e;
-                rng.init(A.seed, gchain, gsw, (unsigned int)e, TAG_SLICE);
+                rng.init(A.seed, gchain, gsw, (unsigned int)u.r.pad, TAG_SLICE);
                 stream_pair(rng, 0u, ua, ub);
                 blk = 1u;
                 const double g0 = cd.eval(x0);
@@ -329,7 +334,8 @@ struct MhPropStatic {
     }
 };
 
-__device__ __forceinline__ void run_class_mh(const SweepArgs &A, double *d, const int *q_type, const QConst *qc, int hi,
+template <class DT>
+__device__ __forceinline__ void run_class_mh(const SweepArgs &A, DT d, const int *q_type, const QConst *qc, int hi,
                                              int *ctr, unsigned long long gchain, unsigned int gsw, long long &n_ev,
                                              long long &n_evals, long long &n_reject, const int *q_slot,
                                              const unsigned char *aux) {
@@ -354,7 +360,7 @@ __device__ __forceinline__ void run_class_mh(const SweepArgs &A, double *d, cons
             h.c = &cd;
             h.Lh = cd.has_e1 ? dmax(cd.b, 0.0) : cd.b;
             h.Uh = cd.has_e1 ? cd.d_e1 : INFINITY;
-            const unsigned int e = (unsigned int)u.r.e;
+            const unsigned int e = (unsigned int)u.r.pad;  // stream id
             bool skip = (final_evt && (A.flags & FLAG_NO_FINAL)) || (h.Uh - h.Lh < 1e-10) ||
                         (!final_evt && cd.d_e1 - a_e < 1e-10);  // qnet.pyx:361, 385, 440
             if (!skip) {
@@ -429,7 +435,8 @@ __device__ __forceinline__ double block_reduce_max(double v, double *scratch) {
 }
 
 // service time of event i under the static order (queues.pyx:610-612 with k = 1; queues.pyx:771)
-__device__ __forceinline__ void event_service(const double *d, int i, int fifo, int p, int pt, double &a,
+template <class DT>
+__device__ __forceinline__ void event_service(const DT &d, int i, int fifo, int p, int pt, double &a,
                                               double &s) {
     double di = d[i];
     a = (pt >= 0) ? d[pt] : 0.0;

@@ -347,7 +347,9 @@ class GibbsEngine(object):
     def kernel_info(self):
         t, s, m = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         capi.check(self._L.bq_kernel_info(self._h, ctypes.byref(t), ctypes.byref(s), ctypes.byref(m)))
-        return dict(threads=int(t.value), smem_bytes=int(s.value), state_in_smem=bool(m.value))
+        n = ctypes.c_int32()
+        capi.check(self._L.bq_cluster_size(self._h, ctypes.byref(n)))
+        return dict(threads=int(t.value), smem_bytes=int(s.value), state_in_smem=bool(m.value), cluster=int(n.value))
 
     def device_pointers(self):
         """Raw device addresses (state, trace arrays) for zero-copy wrapping by torch / NCCL code."""

@@ -228,6 +228,10 @@ int bq_philox_block(const uint32_t ctr[4], const uint32_t key[2], int32_t rounds
  * chain state is staged in shared memory for the whole launch. */
 int bq_kernel_info(bq_handle *h, int32_t *threads, int32_t *smem_bytes, int32_t *state_in_smem);
 
+/* CTAs per chain of the chromatic sweep: 1, or 2 / 4 / 8 when the handle runs it on thread-block clusters with the chain
+ * state spread over their shared memories (few chains, or a chain too large for one CTA's shared memory). */
+int bq_cluster_size(bq_handle *h, int32_t *ncta);
+
 /* Checkpoint / resume (the reference restarts from 5-decimal CSV snapshots, gibbs.py:137-160, arrivals.pyx:97 -- lossy;
  * here a run resumes exactly): the index of the next sweep, which with the seed, the global chain ids, the departure
  * times (bq_get_state / bq_set_state) and the parameters fixes every random number that follows. */
