@@ -129,57 +129,88 @@ __global__ void __launch_bounds__(BQ_MAX_THREADS, 1) sweep_cluster_kernel(const 
         }
         const bool trace = (A.flags & FLAG_TRACE) != 0;
         if (A.update != UPD_NONE || trace) {
-            // sufficient statistics: every CTA takes a share of each queue's events, partials summed in rank order
+            // sufficient statistics: every CTA takes a share of each queue's events; the per-CTA partials of up to 8
+            // queues are exchanged with ONE pair of cluster barriers and summed in rank order by every CTA
             double logp_acc = 0.0;
             const int gtid = rank * blockDim.x + threadIdx.x, gstride = ncta * blockDim.x;
-            for (int q = 0; q < Q; ++q) {
-                const int lo = A.q_off[q], hi = A.q_off[q + 1];
-                const int fifo = (q_type[q] == Q_GGK), dist = q_dist[q];
-                const bool need_log = (dist != D_EXP);
-                double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // n, sum, sumlog, nlog, wait, nzero, logp, #(s < 0)
-                for (int j = lo + gtid; j < hi; j += gstride) {
-                    const int i = CA.qe_idx[j];
-                    double a, s;
-                    event_service(d, i, fifo, CA.qe_p[j], CA.qe_pt[j], a, s);
-                    const double w = d[i] - a - s;
-                    v[4] += (w > 0.0) ? w : 0.0;
-                    if (s > 0.0) {
-                        v[0] += 1.0; v[1] += s;
-                        if (need_log) {
-                            const double ls = log(s);
-                            if (dist == D_GAMMA) { v[2] += ls; v[3] += 1.0; }
-                            else if (s >= 1e-50) { v[2] += ls; v[3] += 1.0; }
-                        }
-                    } else if (s == 0.0) v[5] += 1.0;
-                    else v[7] += 1.0;
-                    if (trace && !(s < 0.0)) v[6] += lpdf(qc[q], s);
-                }
-                cluster_reduce_sum<8>(v, scratch, red_out, part_sh, rank, ncta);
-                const double mean_log = (red_out[3] > 0.0) ? red_out[2] / red_out[3] : 0.0;
-                if (threadIdx.x == 0) {
-                    SuffStat &t = ss[q];
-                    t.n = red_out[0]; t.sum = red_out[1]; t.sumlog = red_out[2]; t.nlog = red_out[3];
-                    t.wait = red_out[4]; t.nzero = red_out[5]; t.nall = red_out[0] + red_out[5] + red_out[7]; t.sumsq = 0.0;
-                }
-                logp_acc += (trace && red_out[7] > 0.0) ? BQ_NEG_INF : red_out[6];
-                __syncthreads();
-                if (dist == D_LOGNORMAL) {
-                    double sq[1] = {0.0};
+            for (int q0 = 0; q0 < Q; q0 += 8) {
+                const int nq = min(8, Q - q0);
+                for (int qq = 0; qq < nq; ++qq) {
+                    const int q = q0 + qq, lo = A.q_off[q], hi = A.q_off[q + 1];
+                    const int fifo = (q_type[q] == Q_GGK), dist = q_dist[q];
+                    const bool need_log = (dist != D_EXP);
+                    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // n, sum, sumlog, nlog, wait, nzero, logp, #(s < 0)
                     for (int j = lo + gtid; j < hi; j += gstride) {
+                        const int i = CA.qe_idx[j];
                         double a, s;
-                        event_service(d, CA.qe_idx[j], fifo, CA.qe_p[j], CA.qe_pt[j], a, s);
-                        if (s >= 1e-50) { const double z = log(s) - mean_log; sq[0] += z * z; }
+                        event_service(d, i, fifo, CA.qe_p[j], CA.qe_pt[j], a, s);
+                        const double w = d[i] - a - s;
+                        v[4] += (w > 0.0) ? w : 0.0;
+                        if (s > 0.0) {
+                            v[0] += 1.0; v[1] += s;
+                            if (need_log) {
+                                const double ls = log(s);
+                                if (dist == D_GAMMA) { v[2] += ls; v[3] += 1.0; }
+                                else if (s >= 1e-50) { v[2] += ls; v[3] += 1.0; }
+                            }
+                        } else if (s == 0.0) v[5] += 1.0;
+                        else v[7] += 1.0;
+                        if (trace && !(s < 0.0)) v[6] += lpdf(qc[q], s);
                     }
-                    cluster_reduce_sum<1>(sq, scratch, red_out, part_sh, rank, ncta);
-                    if (threadIdx.x == 0) ss[q].sumsq = red_out[0];
-                    __syncthreads();
+                    block_reduce_sum<8>(v, scratch, red_out);
+                    if (threadIdx.x < 8) part_sh[qq * 8 + threadIdx.x] = red_out[threadIdx.x];
+                }
+                cl.sync();
+                if (threadIdx.x < nq * 8) {   // thread t sums value (t & 7) of queue q0 + (t >> 3) over the ranks
+                    double x = 0.0;
+                    for (int r = 0; r < ncta; ++r) x += cl.map_shared_rank(part_sh, r)[threadIdx.x];
+                    reinterpret_cast<double *>(ss + q0)[threadIdx.x] = x;   // staged in ss, unpacked below
+                }
+                cl.sync();
+                if (threadIdx.x == 0) {
+                    for (int qq = 0; qq < nq; ++qq) {
+                        double r8[8];
+                        for (int i = 0; i < 8; ++i) r8[i] = reinterpret_cast<double *>(ss + q0 + qq)[i];
+                        SuffStat &t = ss[q0 + qq];
+                        t.n = r8[0]; t.sum = r8[1]; t.sumlog = r8[2]; t.nlog = r8[3]; t.wait = r8[4]; t.nzero = r8[5];
+                        t.nall = r8[0] + r8[5] + r8[7]; t.sumsq = 0.0;
+                        logp_acc += (trace && r8[7] > 0.0) ? BQ_NEG_INF : r8[6];
+                    }
+                }
+                __syncthreads();
+                bool any_ln = false;
+                for (int qq = 0; qq < nq; ++qq) any_ln = any_ln || (q_dist[q0 + qq] == D_LOGNORMAL);
+                if (any_ln) {  // second pass (distributions.pyx:276-299 is two-pass), again one exchange per 8 queues
+                    for (int qq = 0; qq < nq; ++qq) {
+                        const int q = q0 + qq, lo = A.q_off[q], hi = A.q_off[q + 1];
+                        const int fifo = (q_type[q] == Q_GGK);
+                        double sq[1] = {0.0};
+                        if (q_dist[q] == D_LOGNORMAL) {
+                            const double mean_log = (ss[q].nlog > 0.0) ? ss[q].sumlog / ss[q].nlog : 0.0;
+                            for (int j = lo + gtid; j < hi; j += gstride) {
+                                double a, s;
+                                event_service(d, CA.qe_idx[j], fifo, CA.qe_p[j], CA.qe_pt[j], a, s);
+                                if (s >= 1e-50) { const double z = log(s) - mean_log; sq[0] += z * z; }
+                            }
+                        }
+                        block_reduce_sum<1>(sq, scratch, red_out);
+                        if (threadIdx.x == 0) part_sh[qq] = red_out[0];
+                    }
+                    cl.sync();
+                    if (threadIdx.x < nq) {
+                        double x = 0.0;
+                        for (int r = 0; r < ncta; ++r) x += cl.map_shared_rank(part_sh, r)[threadIdx.x];
+                        ss[q0 + threadIdx.x].sumsq = x;
+                    }
+                    cl.sync();
                 }
             }
+            __syncthreads();
             const size_t recno = (size_t)(A.trace_base + sw);
             if (trace && rank == 0) {
                 for (int q = threadIdx.x; q < Q; q += blockDim.x)
                     A.tr_wait[(recno * A.n_chains + chain) * Q + q] = (ss[q].nall > 0.0) ? ss[q].wait / ss[q].nall : 0.0;
-                if (threadIdx.x == 0) A.tr_logp[recno * A.n_chains + chain] = logp_acc;
+                if (threadIdx.x == 0) A.tr_logp[recno * A.n_chains + chain] = logp_acc;  // accumulated by thread 0
             }
             // every CTA repeats the (deterministic) parameter update on the same statistics: no broadcast needed
             for (int q = threadIdx.x; A.update != UPD_NONE && q < NS; q += blockDim.x) {

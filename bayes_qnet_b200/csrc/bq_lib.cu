@@ -798,13 +798,16 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
     if (h->static_order && !h->has_mix) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        // measured on B200 (tools/probe_cluster.py, profiles/r2_probe_cluster.jsonl): a 20 000-event chain sweeps in
+        // 134 / 106 / 79 / 65 us on 1 / 2 / 4 / 8 CTAs, so clusters pay only while CTAs would otherwise be idle (and lose
+        // against one CTA per chain as soon as the chains fill the SMs, even when the state then has to live in L2);
+        // a 400-event chain is slower on a cluster (barrier cost exceeds the work)
         int want = 1;
-        if (!h->use_smem) {
-            for (int n = 2; n <= 8 && want == 1; n *= 2)
-                if (cluster_smem_bytes(h, (((E + n - 1) / n) + 1) & ~1) + 1024 <= (size_t)max_optin) want = n;
-        } else if (h->C * 8 <= sms - sms % 8) want = 8;
-        else if (h->C * 4 <= sms) want = 4;
-        else if (h->C * 2 <= sms) want = 2;
+        if ((int)h->recs.size() >= 2048) {
+            if (h->C <= 8) want = 8;
+            else if (h->C * 4 <= sms) want = 4;
+            else if (h->C * 2 <= sms) want = 2;
+        }
         if (const char *env = getenv("BQ_CLUSTER")) {
             const int n = atoi(env);
             if (n == 1 || n == 2 || n == 4 || n == 8) want = n;

@@ -65,30 +65,31 @@ def test_cluster_kernel_mh_and_reverse(ncta, monkeypatch):
 
 
 def test_automatic_choice(monkeypatch):
+    """Clusters only while CTAs would otherwise be idle, and only for chains with enough work per class."""
     monkeypatch.delenv("BQ_CLUSTER", raising=False)
-    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 200, 0.3, seed=5)
-    for chains, want in ((1, 8), (16, 8), (30, 4), (70, 2), (200, 1)):
+    net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 1500, 0.3, seed=5)
+    for chains, want in ((1, 8), (8, 8), (16, 4), (37, 4), (70, 2), (200, 1)):
         with GibbsEngine(net, ini, n_chains=chains, seed=1) as eng:
             assert eng.kernel_info()["cluster"] == want, (chains, eng.kernel_info())
             eng.sweep(2, "SLICE", "BAYES")
             assert numpy.all(eng.state(full=True)["s"] >= 0)
+    small = helpers.synthetic(helpers.QNET3, 100, 0.3, seed=5)
+    with GibbsEngine(small[0], small[3], n_chains=1, seed=1) as eng:
+        assert eng.kernel_info()["cluster"] == 1   # a few hundred events: the cluster barrier would cost more than it saves
 
 
 def test_chain_too_large_for_one_cta_stays_on_chip(monkeypatch):
-    """E = 32 000 events (8 000 tasks): one CTA's shared memory holds about 27 000; the cluster path keeps the state on
-    chip with two CTAs and gives what the global-memory build of the one-CTA kernel gives."""
+    """E = 32 000 events (8 000 tasks): one CTA's shared memory holds about 27 000; with few chains the cluster path keeps
+    the state on chip with two CTAs per chain and gives what the global-memory build of the one-CTA kernel gives."""
     monkeypatch.delenv("BQ_CLUSTER", raising=False)
     net, smp, sub, ini = helpers.synthetic(helpers.QNET3, 8000, 0.2, seed=9)
-    with GibbsEngine(net, ini, n_chains=150, seed=4) as eng:
+    with GibbsEngine(net, ini, n_chains=60, seed=4) as eng:
         info = eng.kernel_info()
         assert info["cluster"] == 2 and not info["state_in_smem"]
         eng.sweep(2, "SLICE", "NONE")
         d_cluster = eng.state(0, 4)
-        ms_cluster = eng.last_sweep_ms()
     monkeypatch.setenv("BQ_CLUSTER", "1")
-    with GibbsEngine(net, ini, n_chains=150, seed=4) as eng:
+    with GibbsEngine(net, ini, n_chains=60, seed=4) as eng:
         assert eng.kernel_info()["cluster"] == 1
         eng.sweep(2, "SLICE", "NONE")
         assert numpy.array_equal(eng.state(0, 4), d_cluster)
-        ms_global = eng.last_sweep_ms()
-    print("E=32000, 150 chains x 2 sweeps: cluster of 2 %.2f ms, global-memory path %.2f ms" % (ms_cluster, ms_global))
