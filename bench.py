@@ -303,11 +303,20 @@ def reference_run(wl, iters, nproc, sampler="SLICE", seed=13, use_fixture=True, 
 
 
 def fullsize_record(workload):
+    """The committed real-size measurement of the reference for this config: the estimation.bayes run (>= 2 iterations)
+    when it exists, and the one-sweep figure taken while the fixture was generated."""
     try:
         with open(FULLSIZE) as f:
-            return json.load(f).get(workload)
+            data = json.load(f)
     except Exception:
         return None
+    rec = data.get(workload)
+    one = data.get(workload + "_one_sweep")
+    if rec is None:
+        return one
+    if one is not None:
+        rec = dict(rec, one_sweep=one)
+    return rec
 
 
 def cpu_baseline_block(wl, workload, iters, with_single=True, with_mh=True):
