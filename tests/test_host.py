@@ -220,3 +220,64 @@ def test_qstats_match_reference(name):
         assert numpy.array_equal(numpy.isfinite(ours), m), n
         assert numpy.allclose(ours[m], ref[m], rtol=1e-9, atol=1e-12), (n, ours, ref)
     assert qstats.all_stats_string().split() == [str(n) for n in g["stat_names"]][:len(qstats.STATS)]
+
+
+def test_mixture_template_host_surface():
+    """MixtureTemplate on the host (queues.pyx:1373-1509): the reference's own pins for mean / std
+    (test_mixture_template.py:20-26), the parameter layout (mixing proportions, then each component,
+    queues.pyx:1470-1486), YAML round trip, components recorded by the forward simulation."""
+    text = """
+states:
+  - name: INITIAL
+    queues: [ INITIAL ]
+    successors: [ TIER1 ]
+  - name: TIER1
+    queues: [ Q ]
+queues:
+  - { name: INITIAL, service: [M, 10.0]  }
+  - { name: Q, service: [ MIX, 0.75, [M, 3.0], 0.25, [LN, 0.0, 1.0] ] }
+"""
+    net = qnetu.qnet_from_text(text)
+    q = net.queue_by_name("Q")
+    assert abs(q.service.mean() - 2.662180) < 1e-5 and abs(q.service.std() - 2.813840) < 1e-5
+    assert net.parameters == [10.0, 0.75, 0.25, 3.0, 0.0, 1.0]
+    net.parameters = [9.0, 0.6, 0.4, 2.0, 0.1, 0.9]
+    assert q.service.mixing == [0.6, 0.4] and q.service.dists[0].parameters == [2.0] and q.service.dists[1].parameters == [0.1, 0.9]
+    again = qnetu.qnet_from_text(net.as_yaml())
+    assert numpy.allclose(again.parameters, net.parameters, atol=1e-5)
+    assert q.service.component_codes() == [0, 2] and q.is_mixture() and not net.queue_by_name("INITIAL").is_mixture()
+    qnetu.set_seed(7)
+    smp = net.sample(600)
+    soa = smp.soa()
+    frac = soa["aux"][soa["qid"] == 1].mean()
+    assert abs(frac - 0.4) < 0.08 and numpy.all(soa["aux"][soa["qid"] == 0] == 0)
+    ev = [e for e in smp if e.qid == 1][0]
+    assert ev.variable("COMPONENT_Q") in (0, 1)
+    dup = smp.duplicate()
+    assert numpy.array_equal(dup.soa()["aux"], soa["aux"])
+    ini = net.gibbs_initialize(smp.subset_by_task(0.5))
+    isoa = ini.soa()
+    obs = isoa["obs_d"] == 1
+    assert set(numpy.unique(isoa["aux"][isoa["qid"] == 1])) <= {0, 1} and obs.sum() > 0
+
+
+def test_pooled_sufficient_statistics_and_engine_fingerprint():
+    """Qnet.estimate / sample_parameters given several Arrivals pool the data per queue (qnet.pyx:844-896): the host
+    adds the per-Arrivals statistics and re-centres the squared log deviations on the pooled mean; the engine cache
+    key changes with the structure an engine freezes."""
+    from bayes_qnet_b200 import qnet as _q
+    rs = numpy.random.RandomState(0)
+    data = [numpy.exp(rs.normal(0.3, 0.8, n)) for n in (40, 75, 13)]
+
+    def stats(x):
+        ls = numpy.log(x)
+        return numpy.array([[len(x), x.sum(), ls.sum(), ((ls - ls.mean()) ** 2).sum(), len(x), 0.0, len(x), 0.0]])
+
+    pooled = _q.pool_suffstats([stats(x) for x in data])
+    assert numpy.allclose(pooled, stats(numpy.concatenate(data)), rtol=1e-12)
+    net, smp, sub, ini = __import__("helpers").synthetic(__import__("helpers").MM1, 30, 0.5, seed=1)
+    f0 = _q._fingerprint(ini.soa())
+    assert f0 == _q._fingerprint(ini.duplicate().soa())
+    ev = [e for e in ini if not e.obs_d][0]
+    ev.obs_d = 1
+    assert _q._fingerprint(ini.soa()) != f0
