@@ -191,6 +191,40 @@ queues:
   - { name: Q1, service: [M, 0.5], type: PS }
   - { name: Q2, service: [M, 2.0], type: DELAY }
 """,
+    # random-order single-server queues (QueueGG1R; test_gg1r.py:436-451 m2one, test_likdelta.py:119-137 mmrss)
+    "gg1r": """
+states:
+ - name: I0
+   queues: [I0]
+   successors: [S1]
+ - name: S1
+   queues: [Q1,Q2]
+   successors: [S2]
+ - name: S2
+   queues: [Q11]
+queues:
+  - { name: I0, service: [M, 1.0] }
+  - { name: Q1, service: [M, 1.2], type: GG1R }
+  - { name: Q2, service: [G, 2.0, 0.6], type: GG1R }
+  - { name: Q11, service: [M, 0.75], type: GG1R }
+""",
+    # the same with exponential service everywhere (test_gg1r.py:436-451): long posterior runs
+    "gg1rm": """
+states:
+ - name: I0
+   queues: [I0]
+   successors: [S1]
+ - name: S1
+   queues: [Q1,Q2]
+   successors: [S2]
+ - name: S2
+   queues: [Q11]
+queues:
+  - { name: I0, service: [M, 1.0] }
+  - { name: Q1, service: [M, 1.2], type: GG1R }
+  - { name: Q2, service: [M, 1.5], type: GG1R }
+  - { name: Q11, service: [M, 0.75], type: GG1R }
+""",
 }
 
 # name -> (tasks, pct observed, initializer, seed, sweeps before the second snapshot)
@@ -203,6 +237,10 @@ COND = {
     "lnk": (60, 0.2, "DFN2", 18, 5),
     "psdelay": (50, 0.2, "PS", 19, 3),
     "mix": (70, 0.3, "DFN2", 20, 3),
+    # the reference's initialisers do not pass its own validate() on GG1R networks (validate_caches, queues.pyx:843-853,
+    # on the partially filled queue); its tests start from the sampled state with the hidden flags set
+    # (test_likdelta.py:43-48), and so does this: initializer "TRUE"
+    "gg1r": (70, 0.3, "TRUE", 31, 3),
 }
 
 # name -> (tasks, pct, initializer, seed, iterations, replicas)
@@ -212,6 +250,7 @@ POST = {
     "lng1": (100, 0.3, "DFN2", 22, 3000, 8),     # slow-mixing Gamma scale: needs long runs for a usable MCSE
     "mm3": (100, 0.3, "DFN2", 23, 2500, 8),       # heavily loaded 3-server queue: waits mix slowly
     "psdelay": (80, 0.3, "PS", 24, 1500, 8),
+    "gg1rm": (80, 0.3, "TRUE", 32, 1500, 8),
 }
 
 
@@ -256,11 +295,15 @@ def make_state(name, ntasks, pct, init, seed):
     net = qnetu.qnet_from_text(NETS[name])
     qnetu.set_seed(seed)
     with quiet():
-        qnet.set_initialization_type(init)
-        smp = net.sample(ntasks)
-        sub = smp.subset_by_task(pct)
-        ini = net.gibbs_initialize(sub)
-        qnet.set_initialization_type("DFN2")
+        if init == "TRUE":  # the sampled state itself, hidden flags set
+            smp = net.sample(ntasks)
+            ini = smp.subset_by_task(pct)
+        else:
+            qnet.set_initialization_type(init)
+            smp = net.sample(ntasks)
+            sub = smp.subset_by_task(pct)
+            ini = net.gibbs_initialize(sub)
+            qnet.set_initialization_type("DFN2")
     ini.validate()
     return net, ini
 
@@ -528,11 +571,15 @@ def do_big(name):
     net = qnetu.qnet_from_text(NETS[netname])
     qnetu.set_seed(seed)
     with quiet():
-        qnet.set_initialization_type(init)
-        smp = net.sample(ntasks)
-        sub = smp.subset_by_task(pct)
-        ini = net.gibbs_initialize(sub)
-        qnet.set_initialization_type("DFN2")
+        if init == "TRUE":  # the sampled state itself, hidden flags set
+            smp = net.sample(ntasks)
+            ini = smp.subset_by_task(pct)
+        else:
+            qnet.set_initialization_type(init)
+            smp = net.sample(ntasks)
+            sub = smp.subset_by_task(pct)
+            ini = net.gibbs_initialize(sub)
+            qnet.set_initialization_type("DFN2")
     ini.validate()
     print("big_%s: reference init of %d tasks took %.0f s" % (name, ntasks, time.time() - t0), flush=True)
     rng = numpy.random.RandomState(seed + 7000)
@@ -598,8 +645,10 @@ if __name__ == "__main__":
         sys.exit(0)
     if not args.skip_mh:  # MH-within-Gibbs (gibbs_resample): proposal grids and long reference runs; no PS (queues.pyx:1140)
         for n in COND:
-            if n not in ("psdelay", "mix") and args.only in (None, n):  # no MH proposal for PS (queues.pyx:1140) nor for
-                do_mh(n)                                               # mixture templates (DepartureProposal wants a DistributionTemplate)
+            # no MH proposal for PS (queues.pyx:1140), for mixture templates (DepartureProposal wants a
+            # DistributionTemplate) nor for random-order queues (QueueGG1R.arrivalLik raises, queues.pyx:856-857)
+            if n not in ("psdelay", "mix", "gg1r") and args.only in (None, n):
+                do_mh(n)
         for n in ("mm1", "qnet3", "mm3"):
             if args.only in (None, n) and not args.skip_post:
                 do_post(n, "MH")
