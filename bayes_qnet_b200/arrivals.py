@@ -288,6 +288,12 @@ class Arrivals(object):
             elif queue.code == _queues.Q_PS:  # queues.pyx:1049-1070
                 self._s[rows] = ps_service(a, d)
                 self._proc[rows] = 0
+            elif queue.code == _queues.Q_GG1R:  # queues.pyx:808-816: rows are in departure order
+                dprev = numpy.concatenate(([0.0], d[:-1]))
+                s = d - numpy.maximum(a, dprev)
+                s[0] = d[0] - a[0]
+                self._s[rows] = s
+                self._proc[rows] = 0
             else:
                 raise Exception("unknown queue type for %s" % queue)
 

@@ -350,6 +350,9 @@ def _simulate(net, n):
     ps_clock = [0.0] * nq
     ps_active = [dict() for _ in range(nq)]
     ps_version = [0] * nq
+    # random-order queues (QueueGG1R, select_job_for_service: queues.pyx:1026-1027): jobs waiting, server busy
+    rs_wait = [[] for _ in range(nq)]
+    rs_busy = [False] * nq
     rows = dict(tid=[], qid=[], state=[], a=[], d=[], proc=[], aux=[])
     heap = []
     seq = 0
@@ -397,6 +400,15 @@ def _simulate(net, n):
                 ps_active[qid][row] = s
                 ps_plan(qid)
                 continue
+            if q.code == _queues.Q_GG1R:
+                rows["d"].append(numpy.nan); rows["proc"].append(0)
+                if rs_busy[qid]:
+                    rs_wait[qid].append((row, s))
+                else:
+                    rs_busy[qid] = True
+                    heapq.heappush(heap, (t + s, seq, 2, qid, row))
+                    seq += 1
+                continue
             if q.code == _queues.Q_DELAY:
                 d, p = t + s, 0
             else:
@@ -408,6 +420,19 @@ def _simulate(net, n):
             nxt = fsm.sample_state(sid)
             if nxt:
                 heapq.heappush(heap, (d, seq, 0, tid, nxt))
+                seq += 1
+        elif kind == 2:  # service completion at random-order queue x: the next job is drawn among those waiting
+            qid, row = x, y
+            rows["d"][row] = t
+            if rs_wait[qid]:
+                r2, s2 = rs_wait[qid].pop(int(numpy.random.randint(len(rs_wait[qid]))))
+                heapq.heappush(heap, (t + s2, seq, 2, qid, r2))
+                seq += 1
+            else:
+                rs_busy[qid] = False
+            nxt = fsm.sample_state(rows["state"][row])
+            if nxt:
+                heapq.heappush(heap, (t, seq, 0, rows["tid"][row], nxt))
                 seq += 1
         else:  # planned PS departure from queue x
             qid = x

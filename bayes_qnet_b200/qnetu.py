@@ -80,7 +80,7 @@ def queue_from_text(text, universe):
 
 
 def queue_from_yhash(qhash, universe):
-    """qnetu.py:96-122: GG1 -> QueueGGk(k=1), GGK, DELAY, PS."""
+    """qnetu.py:96-122: GG1 -> QueueGGk(k=1), GGK, DELAY, PS, GG1R."""
     qname = qhash["name"]
     sdist = _tmpl_from_yaml(qhash["service"], qname, universe)
     num_procs = qhash.get("processors", 1)
@@ -100,8 +100,7 @@ def queue_from_yhash(qhash, universe):
     if qtype == "PS":
         return queues.QueuePS(qname, sdist)
     if qtype == "GG1R":
-        raise NotImplementedError("queue %s: GG1R (random-order service) is outside the GPU hot path "
-                                  "(SURVEY.md section 8f N4)" % qname)
+        return queues.QueueGG1R(qname, sdist)
     raise Exception("Could not understand queue %s type %s" % (qname, qtype))
 
 

@@ -3,12 +3,12 @@
 The reference's ``queues.pyx`` Queue vtable (queues.pxd:19-37) -- diff lists, likelihood deltas, service
 recomputation -- is what the CUDA kernels subsume; what stays on the host is the *description* of each
 station: its discipline, processor count and service template.  Class names follow the reference so that
-``qnetu`` can build the same objects: QueueGGk (queues.pyx:444), DelayStation (:745), QueuePS (:1032),
+``qnetu`` can build the same objects: QueueGGk (queues.pyx:444), DelayStation (:745), QueueGG1R (:788), QueuePS (:1032),
 DistributionTemplate (:1305).
 """
 from . import distributions
 
-Q_GGK, Q_DELAY, Q_PS = 0, 1, 2
+Q_GGK, Q_DELAY, Q_PS, Q_GG1R = 0, 1, 2, 3
 ARRV_BY_A, ARRV_BY_D = 0, 1
 
 
@@ -189,3 +189,16 @@ class QueuePS(Queue):
 
     def as_yaml(self):
         return "  - { name: %s, type: PS, service: %s }" % (self.name, self.service.as_yaml())
+
+
+class QueueGG1R(Queue):
+    """One server that takes the next job uniformly at random among those waiting (queues.pyx:788-1027): the
+    queue's list is ordered by departure, s = d - max(a, previous departure); the likelihood carries
+    - log N(commencement) per event and the rule "started on arrival => arrived to an empty queue"."""
+    code = Q_GG1R
+
+    def queue_order(self):
+        return ARRV_BY_D
+
+    def as_yaml(self):
+        return "  - { name: %s, type: GG1R, service: %s }" % (self.name, self.service.as_yaml())

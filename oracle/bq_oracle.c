@@ -10,7 +10,10 @@
  * keeps it obviously right and limits it to small cases):
  *   - service-time semantics: QueueGGk any k (queues.pyx:610-680: s = d - max(a, min_p last departure on p),
  *     proc = first argmin), DelayStation (queues.pyx:771: s = d - a), QueuePS (queues.pyx:1049-1070:
- *     s = integral over [a,d] of dt/N(t), N(t) = #{a<=t} - #{d<=t}, cninq.pyx:55-58);
+ *     s = integral over [a,d] of dt/N(t), N(t) = #{a<=t} - #{d<=t}, cninq.pyx:55-58), QueueGG1R (queues.pyx:788-1027:
+ *     one server taking waiting jobs in random order -- the queue's list is ordered by departure, s = d - max(a, d of
+ *     the previous departure); the likelihood carries -log N(commencement) per event and the feasibility rule "started
+ *     on arrival => arrived to an empty queue", queues.pyx:956-1027);
  *   - the per-event conditional GGkGibbs.inner_dfun(d) - lik0 (qnet.pyx:1340-1357) =
  *     likelihoodDelta(q0, diffListForDeparture(e, d)) + likelihoodDelta(q1, diffListForArrival(e', d))
  *     (queues.pyx:83-95, 470-591, 1149-1183, 1220-1232), including the re-sort of q1 by arrival time
@@ -42,7 +45,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { Q_GGK = 0, Q_DELAY = 1, Q_PS = 2 };
+enum { Q_GGK = 0, Q_DELAY = 1, Q_PS = 2, Q_GG1R = 3 };
 enum { D_EXP = 0, D_GAMMA = 1, D_LN = 2 };
 
 typedef struct {
@@ -116,6 +119,13 @@ static void queue_services(const bqo_state *st, int q, const int *lst, int n, co
             free_t[p] = d[e];
         }
         free(free_t);
+    } else if (type == Q_GG1R) { /* recompute_service, queues.pyx:808-816: the list is in departure order */
+        for (i = 0; i < n; ++i) {
+            int e = lst[i];
+            double dp = i > 0 ? d[lst[i - 1]] : 0.0;
+            s_out[i] = (i > 0) ? d[e] - (a[e] > dp ? a[e] : dp) : d[e] - a[e];
+            proc_out[i] = 0;
+        }
     } else { /* PS: piecewise integration between consecutive breakpoints inside [a_e, d_e] */
         double *pts = (double *)malloc((size_t)(2 * n + 2) * sizeof(double));
         for (i = 0; i < n; ++i) {
@@ -180,10 +190,28 @@ void bqo_recompute(bqo_state *st) {
 /* Qnet.log_prob (qnet.pyx:1032): sum of service log-densities, -inf if any s < 0 */
 double bqo_log_prob(const bqo_state *st) {
     double r = 0.0;
-    int e;
+    int e, q;
     for (e = 0; e < st->E; ++e) {
         if (st->s[e] < 0.0) return -INFINITY;
         r += q_lpdf(st, st->qid[e], e, st->s[e]);
+    }
+    /* QueueGG1R.allEventLik (queues.pyx:1009-1024): - log N(commencement) per event with s != 0; an event that
+     * started on arrival (wait < 1e-10) must have found the queue empty */
+    for (q = 0; q < st->Q; ++q) {
+        int *lst, n, i;
+        if (st->q_type[q] != Q_GG1R) continue;
+        lst = (int *)malloc((size_t)st->E * sizeof(int));
+        n = queue_list(st, q, lst);
+        for (i = 0; i < n; ++i) {
+            int ev = lst[i];
+            double w = st->d[ev] - st->a[ev] - st->s[ev], c;
+            if (w < 0.0) w = 0.0;
+            c = st->d[ev] - st->s[ev];
+            if (st->a[ev] > c) c = st->a[ev];
+            if (st->s[ev] != 0.0) r -= log((double)ps_N(lst, n, st->a, st->d, c));
+            if (w < 1e-10 && ps_N(lst, n, st->a, st->d, st->a[ev]) > 1) { free(lst); return -INFINITY; }
+        }
+        free(lst);
     }
     return r;
 }
@@ -235,6 +263,84 @@ static double queue_delta(const bqo_state *st, int q, const int *lst_new, int n,
     return bad ? -INFINITY : delta;
 }
 
+/* QueueGG1R: likelihoodDelta(diffListForDeparture(m, x)) (is_dep) or likelihoodDelta(diffListForArrival(m, x))
+ * (queues.pyx:859-1006).  Departure move: m takes its new place in the departure order (the two while loops of
+ * queues.pyx:871-880); the diff list is the run of the OLD list from the earlier of the old / new predecessor to the
+ * later of the old / new successor (to the end of the queue if either successor is missing), re-sorted, services
+ * recomputed.  Arrival move: the diff list is m alone (queues.pyx:859-864).  On top of the sum of lpdf(s_new) -
+ * lpdf(s_old): for every event of the diff list, and after an arrival move every event whose commencement lies in
+ * [min(a_old, a_new), max(a_old, a_new)] (c2e_range), + log N_old(c_old) [s_old != 0] - log N_new(c_new) [s_new != 0],
+ * and -inf if such an event starts on arrival (wait < 1e-10) while N_new(a) > 1 -- where N(t) = #{a <= t} - #{d <= t}
+ * over the queue (cninq.pyx:55-58) with the moved time in N_new.  If new_list is given the new order is returned. */
+static double gg1r_delta(const bqo_state *st, int q, int m, int is_dep, double x, int *new_list) {
+    int E = st->E, n, i, i0 = -1, g, g2, lo, hi, bad = 0;
+    int *old = (int *)malloc((size_t)E * sizeof(int)), *neu = (int *)malloc((size_t)E * sizeof(int));
+    int *pr = (int *)malloc((size_t)E * sizeof(int));
+    unsigned char *member = (unsigned char *)calloc((size_t)E, 1);
+    double *a2 = (double *)malloc((size_t)E * sizeof(double)), *d2 = (double *)malloc((size_t)E * sizeof(double));
+    double *sn = (double *)malloc((size_t)E * sizeof(double));
+    double delta = 0.0;
+    memcpy(a2, st->a, (size_t)E * sizeof(double));
+    memcpy(d2, st->d, (size_t)E * sizeof(double));
+    n = queue_list(st, q, old);
+    for (i = 0; i < n; ++i) if (old[i] == m) i0 = i;
+    if (is_dep) {
+        /* others = old without m; m sits in gap g (between others[g-1] and others[g]) and moves to gap g2 */
+#define OTH(j) (old[(j) < i0 ? (j) : (j) + 1])
+        d2[m] = x;
+        g = g2 = i0;
+        while (g2 > 0 && !(st->d[OTH(g2 - 1)] <= x)) --g2;
+        while (g2 < n - 1 && !(x <= st->d[OTH(g2)])) ++g2;
+        for (i = 0; i < n - 1; ++i) neu[i < g2 ? i : i + 1] = OTH(i);
+        neu[g2] = m;
+#undef OTH
+        lo = (g < g2 ? g : g2) - 1;
+        if (lo < 0) lo = 0;
+        hi = (g == n - 1 || g2 == n - 1) ? n - 1 : (g > g2 ? g : g2) + 1;
+        for (i = lo; i <= hi; ++i) member[old[i]] = 1;
+    } else {
+        double l = st->a[m] < x ? st->a[m] : x, r = st->a[m] < x ? x : st->a[m];
+        a2[m] = x;
+        memcpy(neu, old, (size_t)n * sizeof(int));
+        member[m] = 1;
+        for (i = 0; i < n; ++i) { /* c2e_range(l, r): current commencements, both ends included */
+            int ev = old[i];
+            double c = st->d[ev] - st->s[ev];
+            if (st->a[ev] > c) c = st->a[ev];
+            if (c >= l && c <= r) member[ev] = 2;
+        }
+        member[m] = 1;
+    }
+    queue_services(st, q, neu, n, a2, d2, sn, pr);
+    /* Queue.likelihoodDelta over the diff list (members marked 1) */
+    for (i = 0; i < n; ++i)
+        if (member[neu[i]] == 1 && sn[i] < 0.0) bad = 1;
+    if (!bad) {
+        for (i = 0; i < n; ++i) {
+            int ev = neu[i];
+            if (member[ev] == 1 && sn[i] != st->s[ev]) delta += q_lpdf(st, q, ev, sn[i]) - q_lpdf(st, q, ev, st->s[ev]);
+        }
+        for (i = 0; i < n && !bad; ++i) {
+            int ev = neu[i];
+            double s_new, w, c_old, c_new;
+            if (!member[ev]) continue;
+            s_new = (member[ev] == 1) ? sn[i] : st->s[ev]; /* c2e_range members are the current events */
+            w = d2[ev] - a2[ev] - s_new;
+            if (w < 0.0) w = 0.0;
+            if (w < 1e-10 && ps_N(neu, n, a2, d2, a2[ev]) > 1) { bad = 1; break; }
+            c_old = st->d[ev] - st->s[ev];
+            if (st->a[ev] > c_old) c_old = st->a[ev];
+            c_new = d2[ev] - s_new;
+            if (a2[ev] > c_new) c_new = a2[ev];
+            if (st->s[ev] != 0.0) delta += log((double)ps_N(old, n, st->a, st->d, c_old));
+            if (s_new != 0.0) delta -= log((double)ps_N(neu, n, a2, d2, c_new));
+        }
+    }
+    if (new_list) memcpy(new_list, neu, (size_t)n * sizeof(int));
+    free(old); free(neu); free(pr); free(member); free(a2); free(d2); free(sn);
+    return bad ? -INFINITY : delta;
+}
+
 double bqo_logcond1(const bqo_state *st, int e, double x) {
     int E = st->E, q0 = st->qid[e], e1 = st->next_byt[e], n;
     double *a2 = (double *)malloc((size_t)E * sizeof(double));
@@ -244,16 +350,22 @@ double bqo_logcond1(const bqo_state *st, int e, double x) {
     memcpy(a2, st->a, (size_t)E * sizeof(double));
     memcpy(d2, st->d, (size_t)E * sizeof(double));
     d2[e] = x;
-    n = queue_list(st, q0, lst); /* a departure move never reorders its queue (queues.pyx:470-511) */
-    r = queue_delta(st, q0, lst, n, st->a, d2);
+    if (st->q_type[q0] == Q_GG1R) r = gg1r_delta(st, q0, e, 1, x, NULL);
+    else {
+        n = queue_list(st, q0, lst); /* a departure move never reorders its queue (queues.pyx:470-511) */
+        r = queue_delta(st, q0, lst, n, st->a, d2);
+    }
     if (e1 >= 0) {
         int q1 = st->qid[e1];
         double r1;
         /* diffListForArrival sees the OLD departure times of q1 and the new arrival of e1 */
         a2[e1] = x;
-        if (st->q_type[q1] == Q_GGK) n = resorted_list(st, q1, e1, x, st->a, lst);
-        else n = queue_list(st, q1, lst);
-        r1 = queue_delta(st, q1, lst, n, a2, st->d);
+        if (st->q_type[q1] == Q_GG1R) r1 = gg1r_delta(st, q1, e1, 0, x, NULL);
+        else {
+            if (st->q_type[q1] == Q_GGK) n = resorted_list(st, q1, e1, x, st->a, lst);
+            else n = queue_list(st, q1, lst);
+            r1 = queue_delta(st, q1, lst, n, a2, st->d);
+        }
         r += r1;
     }
     free(a2); free(d2); free(lst);
@@ -268,6 +380,17 @@ void bqo_logcond(const bqo_state *st, int e, const double *x, int n, double *out
 /* commit d_e := x (apply_departure, qnet.pyx:2166-2178 -> applyDiffList, arrivals.pyx:542-604) */
 void bqo_apply(bqo_state *st, int e, double x) {
     int e1 = st->next_byt[e], i, n;
+    if (st->q_type[st->qid[e]] == Q_GG1R) { /* the departure order changes with the move (queues.pyx:866-940) */
+        int *lst = (int *)malloc((size_t)st->E * sizeof(int));
+        (void)gg1r_delta(st, st->qid[e], e, 1, x, lst);
+        n = 0;
+        for (i = 0; i < st->E; ++i) if (st->qid[i] == st->qid[e]) ++n;
+        for (i = 0; i < n; ++i) {
+            st->prev_byq[lst[i]] = i > 0 ? lst[i - 1] : -1;
+            st->next_byq[lst[i]] = i + 1 < n ? lst[i + 1] : -1;
+        }
+        free(lst);
+    }
     st->d[e] = x;
     if (e1 >= 0) {
         int q1 = st->qid[e1];

@@ -298,6 +298,11 @@ def make_state(name, ntasks, pct, init, seed):
         if init == "TRUE":  # the sampled state itself, hidden flags set
             smp = net.sample(ntasks)
             ini = smp.subset_by_task(pct)
+            # as after loading the state from a file: s = d - max(a, previous departure) in floating point, not the
+            # simulator's draw, so that the commencement max(a, d - s) (arrivals.pyx:190-192), at which QueueGG1R counts
+            # the jobs present, is the number any holder of (a, d) alone computes
+            ini.recompute_all_service()
+            ini.regenerate_all_caches()
         else:
             qnet.set_initialization_type(init)
             smp = net.sample(ntasks)
@@ -574,6 +579,11 @@ def do_big(name):
         if init == "TRUE":  # the sampled state itself, hidden flags set
             smp = net.sample(ntasks)
             ini = smp.subset_by_task(pct)
+            # as after loading the state from a file: s = d - max(a, previous departure) in floating point, not the
+            # simulator's draw, so that the commencement max(a, d - s) (arrivals.pyx:190-192), at which QueueGG1R counts
+            # the jobs present, is the number any holder of (a, d) alone computes
+            ini.recompute_all_service()
+            ini.regenerate_all_caches()
         else:
             qnet.set_initialization_type(init)
             smp = net.sample(ntasks)
