@@ -39,7 +39,7 @@ __host__ __device__ __forceinline__ double log_count(int n) {
 #endif
 }
 
-enum { Q_GGK = 0, Q_DELAY = 1, Q_PS = 2 };
+enum { Q_GGK = 0, Q_DELAY = 1, Q_PS = 2, Q_GG1R = 3 };
 enum { D_EXP = 0, D_GAMMA = 1, D_LOGNORMAL = 2 };
 
 #define BQ_NEG_INF (-INFINITY)

@@ -231,6 +231,30 @@ BQ_HDI int upper_from(const double *v, int lo, int hi, int hint, double t, int s
     return r;
 }
 
+// first index in [lo, hi) whose value is >= t, galloping forward from `hint`
+BQ_HDI int lower_from(const double *v, int lo, int hi, int hint, double t) {
+    if (hint < lo) hint = lo;
+    if (hint > hi) hint = hi;
+    int l = lo - 1, r = hint;  // v[l] < t (or l == lo - 1), v[r] >= t (or r == hi)
+    if (hint < hi && v[hint] < t) {
+        l = hint;
+        int step = 1;
+        r = l + step;
+        while (r < hi && v[r] < t) { l = r; step <<= 1; r = l + step; }
+        if (r > hi) r = hi;
+    } else {
+        int step = 1;
+        l = r - step;
+        while (l >= lo && v[l] >= t) { r = l; step <<= 1; l = r - step; }
+        if (l < lo - 1) l = lo - 1;
+    }
+    while (r - l > 1) {
+        const int m = (l + r) >> 1;
+        if (v[m] < t) l = m; else r = m;
+    }
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // FIFO queue with k servers: likelihoodDelta(diffListForDeparture(e, x))   (queues.pyx:470-511, 83-95)
 //
@@ -588,6 +612,176 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, Touch &t
 }
 
 // ---------------------------------------------------------------------------------------------
+// Random-order single server (QueueGG1R, queues.pyx:788-1027).  The queue's list is ordered by DEPARTURE
+// (queue_order ARRV_BY_D), s_i = d_i - max(a_i, previous departure) (recompute_service, :808-816), and the
+// likelihood carries, per event, - log N(c_i) at its commencement c_i = max(a_i, d_i - s_i) (the server picked it
+// among the N jobs present) plus the rule that an event which started on arrival (wait < 1e-10) found the queue
+// empty, N(a_i) = 1 (likelihoodDelta, :956-1006).  N(t) = #{a <= t} - #{d <= t} over the queue (cninq.pyx:55-58).
+// It lives on the arrays processor sharing already keeps: positions by arrival (rec.at sorted: #{a <= t} is a
+// search), dt[] / dord[] / dpos[] the departures sorted, and sq[j] = ARRIVAL time of the event in departure slot j
+// (for PS queues sq holds service times by arrival position), so that a diff list is a run of consecutive slots.
+//   departure move x0 -> x of m (diffListForDeparture, :866-954): m takes its new place in the departure order;
+//     the diff list is the run of slots from the earlier of the old / new predecessor to the later of the old /
+//     new successor.  Only m, its old successor and its new successor change service; every slot of the run
+//     contributes + log N_old(c_old) [s_old != 0] - log N_new(c_new) [s_new != 0] with
+//     N_new(t) = N_old(t) + [x0 <= t] - [x <= t].
+//   arrival move a0 -> x of m (diffListForArrival, :859-864): the diff list is m alone; the same terms for m and
+//     for every event whose commencement lies in [min(a0, x), max(a0, x)] (c2e_range) -- commencements are
+//     nondecreasing along the departure order, so again a run of slots -- with N_new(t) = N_old(t) + [x <= t] - [a0 <= t].
+// ---------------------------------------------------------------------------------------------
+struct Gg1rMove {
+    double plus, minus;  // N_new(t) = N_old(t) + [plus <= t] - [minus <= t]
+    int ha, hd;          // search hints: an arrival position and a departure slot near the last answers
+    bool first;          // the queue is the one of e (Touch ranges 0) or of the task's next event (ranges 1)
+};
+
+// the positions / slots a galloping search from `hint` that ended at r may have probed
+BQ_HDF void gg1r_touch(Touch &tc, bool first, bool slots, int lo, int hi, int hint, int r) {
+    int far = 2 * r - hint;
+    far = far < lo ? lo : (far >= hi ? hi - 1 : far);
+    int h = hint < lo ? lo : (hint >= hi ? hi - 1 : hint);
+    int rr = r < hi ? r : hi - 1;
+    if (slots) { tc.pd(h); tc.pd(far); tc.pd(rr); if (r > lo) tc.pd(r - 1); }
+    else { tc.pa(first, h); tc.pa(first, far); tc.pa(first, rr); if (r > lo) tc.pa(first, r - 1); }
+}
+
+BQ_HDI int gg1r_count(const Chain &c, const QInfo &q, Gg1rMove &mv, double t, Touch &tc) {  // N_old(t)
+    const int ia = upper_from(c.rec + BQ_REC_AT, q.lo, q.hi, mv.ha, t, c.S);
+    gg1r_touch(tc, mv.first, false, q.lo, q.hi, mv.ha, ia);
+    const int id = upper_from(c.dt, q.lo, q.hi, mv.hd, t);
+    gg1r_touch(tc, mv.first, true, q.lo, q.hi, mv.hd, id);
+    mv.ha = ia; mv.hd = id;
+    return ia - id;
+}
+BQ_HDF int gg1r_adjust(const Gg1rMove &mv, double t) { return ((mv.plus <= t) ? 1 : 0) - ((mv.minus <= t) ? 1 : 0); }
+
+// one event of the set whose N(.) terms are re-evaluated; false = the start-on-arrival rule is violated
+BQ_HDI bool gg1r_member(const Chain &c, const QInfo &q, Gg1rMove &mv, double a_old, double d_old, double s_old, double a_new,
+                        double d_new, double s_new, double &acc, Touch &tc) {
+    double w = d_new - a_new - s_new;
+    if (w < 0.0) w = 0.0;
+    if (w < 1e-10 && gg1r_count(c, q, mv, a_new, tc) + gg1r_adjust(mv, a_new) > 1) return false;
+    ++tc.steps;
+    if (s_old != 0.0) {
+        const double c_old = dmax(a_old, d_old - s_old);
+        acc += log_count(gg1r_count(c, q, mv, c_old, tc));
+    }
+    if (s_new != 0.0) {
+        const double c_new = dmax(a_new, d_new - s_new);
+        acc -= log_count(gg1r_count(c, q, mv, c_new, tc) + gg1r_adjust(mv, c_new));
+    }
+    return true;
+}
+
+// the departure slot m (now in slot j0) takes when its departure becomes x: `later` = it moves towards the tail.
+// later: it sits just before jn, the first slot after j0 with dt >= x; earlier: just after jp, the last slot before
+// j0 with dt <= x (the two while loops of queues.pyx:871-880)
+BQ_HDI int gg1r_new_slot(const Chain &c, const QInfo &q, int j0, double x0, double x, int &jp, int &jn, Touch &tc) {
+    jp = j0 - 1; jn = j0 + 1;
+    if (x > x0) {
+        jn = lower_from(c.dt, j0 + 1, q.hi, j0 + 1, x);
+        gg1r_touch(tc, true, true, q.lo, q.hi, j0 + 1, jn);
+        return jn - 1;
+    }
+    if (x < x0) {
+        jp = upper_from(c.dt, q.lo, j0, j0 - 1, x) - 1;
+        gg1r_touch(tc, true, true, q.lo, q.hi, j0 - 1, jp + 1);
+        return jp + 1;
+    }
+    return j0;
+}
+
+// likelihoodDelta(diffListForDeparture(e, x))
+BQ_HDI double gg1r_dep_delta(const Chain &c, const EventCtx &ev, double x, Touch &tc) {
+    const QInfo &q = c.qi[ev.q0];
+    const QConst &qc = c.qc[ev.q0];
+    const int lo = q.lo, hi = q.hi, j0 = c.dpos[ev.e];
+    tc.p0(ev.p0); tc.pd(j0);
+    const double x0 = ev.x0, a_m = ev.a_e;
+    if (x < a_m) return BQ_NEG_INF;  // m's own service x - max(a_m, d_prev) with d_prev <= x; nobody else's can go negative
+    int jp, jn;
+    const int jnew = gg1r_new_slot(c, q, j0, x0, x, jp, jn, tc);
+    const bool later = x > x0;
+    const int mlo = later ? (j0 - 1 > lo ? j0 - 1 : lo) : (x < x0 ? (jp > lo ? jp : lo) : (j0 - 1 > lo ? j0 - 1 : lo));
+    const int mhi = later ? (jn < hi - 1 ? jn : hi - 1) : (j0 + 1 < hi - 1 ? j0 + 1 : hi - 1);
+    tc.pd(mlo); tc.pd(mhi);
+    if (mlo > lo) tc.pd(mlo - 1);
+    Gg1rMove mv;
+    mv.plus = x0; mv.minus = x; mv.ha = ev.p0; mv.hd = j0; mv.first = true;
+    const double dprev_m_old = (j0 > lo) ? c.dt[j0 - 1] : 0.0;
+    double dprev_m_new = dprev_m_old;
+    if (later && jn - 1 > j0) dprev_m_new = c.dt[jn - 1];
+    if (x < x0) dprev_m_new = (jp >= lo) ? c.dt[jp] : 0.0;
+    const double s_old_m = x0 - dmax(a_m, dprev_m_old), s_new_m = x - dmax(a_m, dprev_m_new);
+    if (s_new_m < 0.0) return BQ_NEG_INF;
+    double acc = 0.0;
+    if (s_new_m != s_old_m) acc = lpdf(qc, s_new_m) - lpdf(qc, s_old_m);
+    // the run of slots in the NEW order: m is inserted before old slot `ins` (hi: behind everything; -1: it keeps
+    // its slot)
+    const int ins = (jnew == j0) ? -1 : (later ? jn : jp + 1);
+    for (int j = mlo; j <= mhi; ++j) {
+        if (j == j0) {
+            if (ins == -1 && !gg1r_member(c, q, mv, a_m, x0, s_old_m, a_m, x, s_new_m, acc, tc)) return BQ_NEG_INF;
+            continue;
+        }
+        if (j == ins && !gg1r_member(c, q, mv, a_m, x0, s_old_m, a_m, x, s_new_m, acc, tc)) return BQ_NEG_INF;
+        const double a_j = c.sq[j], d_j = c.dt[j];
+        const double dp_old = (j > lo) ? c.dt[j - 1] : 0.0;
+        double dp_new = dp_old;
+        if (j == ins) dp_new = x;  // m is the new predecessor
+        else if (j == j0 + 1) dp_new = (ins == -1) ? x : ((j0 > lo) ? c.dt[j0 - 1] : 0.0);  // m stayed / m left
+        const double s_old = d_j - dmax(a_j, dp_old), s_new = d_j - dmax(a_j, dp_new);
+        if (s_new < 0.0) return BQ_NEG_INF;
+        if (s_new != s_old) acc += lpdf(qc, s_new) - lpdf(qc, s_old);
+        if (!gg1r_member(c, q, mv, a_j, d_j, s_old, a_j, d_j, s_new, acc, tc)) return BQ_NEG_INF;
+    }
+    if (ins > mhi && !gg1r_member(c, q, mv, a_m, x0, s_old_m, a_m, x, s_new_m, acc, tc)) return BQ_NEG_INF;  // m is last
+    return acc;
+}
+
+// likelihoodDelta(diffListForArrival(e1, x))
+BQ_HDI double gg1r_arr_delta(const Chain &c, const EventCtx &ev, double x, Touch &tc) {
+    const QInfo &q = c.qi[ev.q1];
+    const QConst &qc = c.qc[ev.q1];
+    const int lo = q.lo, hi = q.hi, j1 = c.dpos[ev.e1], p1 = ev.p1;
+    tc.p1(p1); tc.pd(j1);
+    if (j1 > lo) tc.pd(j1 - 1);
+    const double a0 = ev.x0, d1 = ev.d1;
+    const double dprev = (j1 > lo) ? c.dt[j1 - 1] : 0.0;
+    const double s_old = d1 - dmax(a0, dprev), s_new = d1 - dmax(x, dprev);
+    if (s_new < 0.0) return BQ_NEG_INF;
+    double acc = 0.0;
+    if (s_new != s_old) acc = lpdf(qc, s_new) - lpdf(qc, s_old);
+    {   // the arrival position e1 will take (the commit re-ranks rec.at): the accepted candidate claims the range
+        int r = upper_from(c.rec + BQ_REC_AT, lo, hi, p1, x, c.S);
+        gg1r_touch(tc, false, false, lo, hi, p1, r);
+    }
+    Gg1rMove mv;
+    mv.plus = x; mv.minus = a0; mv.ha = p1; mv.hd = j1; mv.first = false;
+    const double l = (x < a0) ? x : a0, r = (x < a0) ? a0 : x;
+    // slots after e1's: commencements >= d1 >= r, members only on a tie
+    for (int j = j1 + 1; j < hi; ++j) {
+        tc.pd(j);
+        const double a_j = c.sq[j], d_j = c.dt[j];
+        const double s_j = d_j - dmax(a_j, c.dt[j - 1]);
+        const double c_j = dmax(a_j, d_j - s_j);
+        if (c_j > r) break;
+        if (c_j >= l && !gg1r_member(c, q, mv, a_j, d_j, s_j, a_j, d_j, s_j, acc, tc)) return BQ_NEG_INF;
+    }
+    if (!gg1r_member(c, q, mv, a0, d1, s_old, x, d1, s_new, acc, tc)) return BQ_NEG_INF;
+    for (int j = j1 - 1; j >= lo; --j) {
+        tc.pd(j);
+        if (j > lo) tc.pd(j - 1);
+        const double a_j = c.sq[j], d_j = c.dt[j];
+        const double s_j = d_j - dmax(a_j, (j > lo) ? c.dt[j - 1] : 0.0);
+        const double c_j = dmax(a_j, d_j - s_j);
+        if (c_j < l) break;
+        if (c_j <= r && !gg1r_member(c, q, mv, a_j, d_j, s_j, a_j, d_j, s_j, acc, tc)) return BQ_NEG_INF;
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // the conditional of d_e: inner_dfun(x) - lik0   (qnet.pyx:1340-1357)
 // ---------------------------------------------------------------------------------------------
 // PS = false: a build for networks without processor-sharing queues (their code is half of the kernel)
@@ -606,6 +800,8 @@ BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, Touch &t
             ps_move_setup(c, ev.q0, ev.p0, ev.e, true, ev.x0, x, mv, tc);
             g = ps_apply_move<false>(c, mv, 0, tc);
         }
+    } else if (PS && ev.t0 == Q_GG1R) {
+        g = gg1r_dep_delta(c, ev, x, tc);
     } else {  // DelayStation: s = d - a, single-event diff list (queues.pyx:745-784)
         const double sn = x - ev.a_e, so = ev.x0 - ev.a_e;
         if (sn < 0.0) return BQ_NEG_INF;
@@ -623,6 +819,8 @@ BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, Touch &t
             ps_move_setup(c, ev.q1, ev.p1, ev.e1, false, ev.x0, x, mv, tc);
             g1 = ps_apply_move<false>(c, mv, 0, tc);
         }
+    } else if (PS && ev.t1 == Q_GG1R) {
+        g1 = gg1r_arr_delta(c, ev, x, tc);
     } else {
         const double sn = ev.d1 - x, so = ev.d1 - ev.x0;
         if (sn < 0.0) return BQ_NEG_INF;
@@ -722,7 +920,7 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         Touch tmp;
         tmp.reset();
         if (ev.t1 == Q_GGK) j1 = new_rank(c, q1, ev.p1, x, ev.x0, tmp);
-        else if (PS) {  // PS: rank among the other arrivals
+        else if (PS) {  // PS, GG1R: rank among the other arrivals
             j1 = upper_from(c.rec + BQ_REC_AT, q1.lo, q1.hi, ev.p1, x, c.S);
             if (c.at(ev.p1) <= x) --j1;
         }
@@ -772,6 +970,13 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         if (c.dt[pd] <= x) --j;
         reslot<W>(c.dt, 1, c.dord, c.dpos, nullptr, 1, nullptr, 1, pd, j, x, lane, gmask);
     }
+    if (PS && ev.t0 == Q_GG1R) {  // the event takes its new place in the departure order, its arrival time with it
+        const QInfo &q = c.qi[ev.q0];
+        const int pd = c.dpos[ev.e];
+        int jp, jn;
+        const int j = gg1r_new_slot(c, q, pd, ev.x0, x, jp, jn, dummy);
+        reslot<W>(c.dt, 1, c.dord, c.dpos, c.sq, 1, nullptr, 1, pd, j, x, lane, gmask);
+    }
     if (lane == 0) { c.d[ev.e] = x; c.dq(ev.p0) = x; }
     BQ_SYNCG(gmask);
     // ---- arrival side ------------------------------------------------------------------------------------------
@@ -800,6 +1005,10 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         BQ_SYNCG(gmask);
     } else if (PS && ev.t1 == Q_PS) {
         reslot<W>(c.rec + BQ_REC_AT, c.S, c.ord, c.pos, c.rec + BQ_REC_DQ, c.S, c.sq, 1, ev.p1, j1, x, lane, gmask);
+    } else if (PS && ev.t1 == Q_GG1R) {  // new rank among the arrivals; the departure order is untouched
+        reslot<W>(c.rec + BQ_REC_AT, c.S, c.ord, c.pos, c.rec + BQ_REC_DQ, c.S, nullptr, 1, ev.p1, j1, x, lane, gmask);
+        if (lane == 0) c.sq[c.dpos[ev.e1]] = x;
+        BQ_SYNCG(gmask);
     } else {
         if (lane == 0) {
             c.at(ev.p1) = x;
@@ -905,7 +1114,27 @@ BQ_HDF bool touch_conflict(const Touch &r, const Touch &w) {
 BQ_HDF double dyn_service(const Chain &c, const QInfo &q, int p) {
     if (q.type == Q_GGK) return c.dq(p) - dmax(c.at(p), c.fvec(q, p)[0]);
     if (q.type == Q_DELAY) return c.dq(p) - c.at(p);
+    if (q.type == Q_GG1R) {  // previous departure of the queue (queues.pyx:808-816)
+        const int j = c.dpos[c.ord[p]];
+        return c.dq(p) - dmax(c.at(p), (j > q.lo) ? c.dt[j - 1] : 0.0);
+    }
     return c.sq[p];
+}
+
+// QueueGG1R.allEventLik beyond the service densities (queues.pyx:1009-1024): - log N(commencement) for an event with
+// s != 0; *bad when it started on arrival with others present
+BQ_HDI double gg1r_event_term(const Chain &c, const QInfo &q, int p, double s, bool *bad) {
+    const int j = c.dpos[c.ord[p]];
+    const double a = c.at(p), d = c.dq(p);
+    double w = d - a - s;
+    if (w < 0.0) w = 0.0;
+    if (w < 1e-10) {
+        const int na = upper_from(c.rec + BQ_REC_AT, q.lo, q.hi, p, a, c.S) - upper_from(c.dt, q.lo, q.hi, j, a);
+        if (na > 1) *bad = true;
+    }
+    if (s == 0.0) return 0.0;
+    const double cm = dmax(a, d - s);
+    return -log_count(upper_from(c.rec + BQ_REC_AT, q.lo, q.hi, p, cm, c.S) - upper_from(c.dt, q.lo, q.hi, j, cm));
 }
 
 #if defined(__CUDACC__)
@@ -941,12 +1170,17 @@ __device__ BQ_NOINLINE void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, i
             if (s > 0.0) {
                 v[0] += 1.0; v[1] += s;
                 if (dist != D_EXP) {
-                    if (dist == D_GAMMA || s >= 1e-50) { v[2] += (qi.type == Q_PS) ? log_d(s) : c.ls(p); v[3] += 1.0; }
+                    if (dist == D_GAMMA || s >= 1e-50) { v[2] += (qi.type >= Q_PS) ? log_d(s) : c.ls(p); v[3] += 1.0; }
                 }
             } else if (s == 0.0) v[5] += 1.0;
             if (want_logp) {
                 if (s < 0.0) v[7] += 1.0;
-                else v[6] += (qi.type == Q_PS) ? lpdf(c.qc[q], s) : lpdf_ls(c.qc[q], s, c.ls(p));
+                else v[6] += (qi.type >= Q_PS) ? lpdf(c.qc[q], s) : lpdf_ls(c.qc[q], s, c.ls(p));
+                if (qi.type == Q_GG1R && s >= 0.0) {
+                    bool bad = false;
+                    v[6] += gg1r_event_term(c, qi, p, s, &bad);
+                    if (bad) v[7] += 1.0;
+                }
             }
         }
 #pragma unroll
@@ -956,7 +1190,7 @@ __device__ BQ_NOINLINE void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, i
             const double mean_log = (v[3] > 0.0) ? v[2] / v[3] : 0.0;
             for (int p = qi.lo + lane; p < qi.hi; p += W) {
                 const double s = dyn_service(c, qi, p);
-                if (s >= 1e-50) { const double z = ((qi.type == Q_PS) ? log_d(s) : c.ls(p)) - mean_log; sq += z * z; }
+                if (s >= 1e-50) { const double z = ((qi.type >= Q_PS) ? log_d(s) : c.ls(p)) - mean_log; sq += z * z; }
             }
             sq = group_sum<W>(sq, gmask);
         }

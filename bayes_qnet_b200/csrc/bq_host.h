@@ -60,7 +60,13 @@ static void host_rebuild(const HostNet *h, const double *d, const HostChain &c, 
     std::vector<double> M;
     for (int q = 0; q < h->Q; ++q) {
         const int lo = h->q_off[q], hi = h->q_off[q + 1], type = h->q_type[q];
-        if (resort && type != 1 /* Q_DELAY */)
+        if (type == 3 /* Q_GG1R */ && c.dt) {
+            // the caller's list is the departure order (queues.pyx:796; equal departures keep the caller's order);
+            // positions are by arrival, like everyone's
+            for (int p = lo; p < hi; ++p) c.dord[p] = c.ord[p];
+            std::stable_sort(c.dord + lo, c.dord + hi, [&](int x, int y) { return d[x] < d[y]; });
+        }
+        if ((resort && type != 1 /* Q_DELAY */) || type == 3)
             std::stable_sort(c.ord + lo, c.ord + hi, [&](int x, int y) {
                 const double ax = arr(x), ay = arr(y);
                 if (ax != ay) return ax < ay;
@@ -90,6 +96,8 @@ static void host_rebuild(const HostNet *h, const double *d, const HostChain &c, 
             for (int p = lo; p < hi; ++p) { c.dt[p] = d[c.dord[p]]; c.dpos[c.dord[p]] = p; }
             for (int p = lo; p < hi; ++p) c.sq[p] = host_ps_service(c.at + lo, c.dt + lo, hi - lo, c.at[p], c.dq[p]);
         }
+        if (type == 3 /* Q_GG1R */ && c.dt)  // departures in order, with the arrival time of the event in each slot
+            for (int p = lo; p < hi; ++p) { c.dt[p] = d[c.dord[p]]; c.dpos[c.dord[p]] = p; c.sq[p] = arr(c.dord[p]); }
     }
 }
 
@@ -108,6 +116,19 @@ static void host_derive(const HostNet *h, const double *d, const int *ord, doubl
         fr.assign(std::max(k, 1), 0.0);
         // the reference never relinks a PS queue (queues.pyx:1149-1183 touch only a, d, s): report the initial links
         const int *lk = (t == 2 /* Q_PS */ && ord0) ? ord0 : ord;
+        std::vector<int> bydep;
+        if (t == 3 /* Q_GG1R */) {  // its list is the departure order (queues.pyx:796); s = d - max(a, previous departure)
+            bydep.assign(ord + lo, ord + hi);
+            std::stable_sort(bydep.begin(), bydep.end(), [&](int x, int y) { return d[x] < d[y]; });
+            for (int p = lo; p < hi; ++p) {
+                const int i = bydep[p - lo];
+                if (prev_byq) prev_byq[i] = p > lo ? bydep[p - lo - 1] : -1;
+                if (next_byq) next_byq[i] = p + 1 < hi ? bydep[p - lo + 1] : -1;
+                if (proc) proc[i] = 0;
+                if (s) s[i] = d[i] - std::max(av[i], p > lo ? d[bydep[p - lo - 1]] : 0.0);
+            }
+            continue;
+        }
         for (int p = lo; p < hi; ++p) {
             if (prev_byq) prev_byq[lk[p]] = p > lo ? lk[p - 1] : -1;
             if (next_byq) next_byq[lk[p]] = p + 1 < hi ? lk[p + 1] : -1;

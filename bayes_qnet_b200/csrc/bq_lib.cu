@@ -86,7 +86,8 @@ struct bq_handle {
     float last_ms = 0.f;
     bool timed = false;
     // ---- dynamic-order networks (k > 1, PS): per-chain queue order and free-time vectors ----
-    bool has_ps = false;
+    bool has_ps = false;    // a PS or random-order queue: sorted-departure arrays, claim array for their slots
+    bool has_gg1r = false;
     int EF = 0, kmax = 1, dyn_w = 32, dyn_threads = 128;
     std::vector<int> q_off, q_foff, ord0;  // queue position ranges, F offsets, initial order
     std::vector<int> dyn_order;          // sweep order of the dynamic-order kernels
@@ -661,7 +662,7 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
     int pcount = 0;
     for (int q = 0; q < Q; ++q) {
         const int t = h->q_type[q], nc = h->q_slot[q + 1] - h->q_slot[q];
-        if (t != Q_GGK && t != Q_DELAY && t != Q_PS) return bail(BQ_ERR_INVALID, "unknown queue type");
+        if (t != Q_GGK && t != Q_DELAY && t != Q_PS && t != Q_GG1R) return bail(BQ_ERR_INVALID, "unknown queue type");
         if (h->q_poff[q] != pcount) return bail(BQ_ERR_INVALID, "q_param_off is not the running parameter count");
         if (nc > 1) { h->has_mix = true; h->q_mixoff[q] = pcount; pcount += nc; }
         for (int sl = h->q_slot[q]; sl < h->q_slot[q + 1]; ++sl) {
@@ -671,7 +672,7 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
             pcount += (dd == D_EXP) ? 1 : 2;
             if (dd != D_EXP) h->all_exp = false;
         }
-        if (t == Q_PS || (t == Q_GGK && h->q_k[q] != 1)) h->static_order = false;
+        if (t == Q_PS || t == Q_GG1R || (t == Q_GGK && h->q_k[q] != 1)) h->static_order = false;
     }
     if (h->has_mix) h->all_exp = false;  // the branch-free exponential path carries no per-event component
     if (h->has_mix && !h->static_order)
@@ -690,7 +691,9 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
             return bail(BQ_ERR_UNSUPPORTED, "a task visits the same queue twice in a row");
     }
     for (int q = 0; q < Q; ++q) {
-        if (h->q_type[q] == Q_PS) h->has_ps = true;
+        // random-order queues live on the sorted-departure arrays of processor sharing (bq_dynamic.cuh)
+        if (h->q_type[q] == Q_PS || h->q_type[q] == Q_GG1R) h->has_ps = true;
+        if (h->q_type[q] == Q_GG1R) h->has_gg1r = true;
         if (h->q_k[q] < 1) return bail(BQ_ERR_INVALID, "queue with fewer than one processor");
     }
     if (const char *env = getenv("BQ_FORCE_DYNAMIC"))
@@ -1081,7 +1084,7 @@ static int launch_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t up
     if (n_sweeps < 0) return fail(BQ_ERR_INVALID, "n_sweeps < 0");
     if (mode != BQ_MODE_SLICE && mode != BQ_MODE_MH) return fail(BQ_ERR_INVALID, "bad sweep mode");
     if (mode == BQ_MODE_MH && h->has_ps)
-        return fail(BQ_ERR_UNSUPPORTED, "MH sweeps need arrivalLik, which PS queues do not have (queues.pyx:1140): use BQ_MODE_SLICE");
+        return fail(BQ_ERR_UNSUPPORTED, "MH sweeps need arrivalLik, which PS and GG1R queues do not have (queues.pyx:1140, 856): use BQ_MODE_SLICE");
     if (mode == BQ_MODE_MH && h->has_mix)
         return fail(BQ_ERR_UNSUPPORTED, "MH sweeps: the reference's proposals take a DistributionTemplate only (queues.pyx:394-442), "
                                         "not a mixture: use BQ_MODE_SLICE");
@@ -1469,6 +1472,7 @@ extern "C" int bq_gibbs_kernel(bq_handle *h, const double *d_to, int32_t n_to, i
     if (!h || !d_to || !out) return fail(BQ_ERR_INVALID, "null argument");
     if (n_to != 1 && n_to != h->C) return fail(BQ_ERR_INVALID, "n_to must be 1 or the number of chains");
     if (h->has_mix) return fail(BQ_ERR_UNSUPPORTED, "bq_gibbs_kernel: mixture templates (the reference's parameter_kernel raises too, queues.pyx:1453)");
+    if (h->has_gg1r) return fail(BQ_ERR_UNSUPPORTED, "bq_gibbs_kernel: not built for random-order (GG1R) queues");
     CK(cudaSetDevice(h->device));
     if (!h->static_order) return gibbs_kernel_dynamic_path(h, d_to, n_to, strict, out);
     const size_t E = h->E, C = h->C, n_sched = h->order.size();

@@ -32,8 +32,9 @@ typedef enum {
 } bq_status;
 
 /* queue disciplines: queues.pyx:444 (QueueGGk; YAML GG1 -> k=1, qnetu.py:109), :745 (DelayStation),
- * :1032 (QueuePS) */
-enum { BQ_Q_GGK = 0, BQ_Q_DELAY = 1, BQ_Q_PS = 2 };
+ * :1032 (QueuePS), :788 (QueueGG1R: one server, waiting jobs taken in random order; its by-queue list is ordered by
+ * departure, and so are the links bq_create takes and bq_get_state returns for it) */
+enum { BQ_Q_GGK = 0, BQ_Q_DELAY = 1, BQ_Q_PS = 2, BQ_Q_GG1R = 3 };
 /* service families: distributions.pyx:52 (Exponential), :107 (Gamma), :245 (LogNormal) */
 enum { BQ_D_EXP = 0, BQ_D_GAMMA = 1, BQ_D_LOGNORMAL = 2 };
 /* sweep kinds: qnet.pyx:659 slice_resample, qnet.pyx:337 gibbs_resample (MH-within-Gibbs) */

@@ -321,7 +321,7 @@ int bqe_check(void *h) {
         if (dq[p] != m->dq[p]) return 9;
     }
     for (int q = 0; q < m->Q; ++q)  // the cached log services of non-exponential FIFO / delay queues
-        if (m->q_dist[q] != D_EXP && m->q_type[q] != Q_PS)
+        if (m->q_dist[q] != D_EXP && m->q_type[q] != Q_PS && m->q_type[q] != Q_GG1R)
             for (int p = m->q_off[q]; p < m->q_off[q + 1]; ++p)
                 if (ls[p] != m->ls[p] && !(ls[p] != ls[p] && m->ls[p] != m->ls[p])) return 10;
     for (int q = 0; q < m->Q; ++q) {
@@ -330,6 +330,15 @@ int bqe_check(void *h) {
             if (dt[p] != m->dt[p]) return 5;
             if (dt[p] != m->d[m->dord[p]] || m->dpos[m->dord[p]] != p) return 6;
             if (fabs(sq[p] - m->sq[p]) > 1e-9 * fmax(1.0, fabs(sq[p]))) return 7;
+        }
+    }
+    for (int q = 0; q < m->Q; ++q) {  // random-order queues: departures in order, each slot with its event's arrival
+        if (m->q_type[q] != Q_GG1R) continue;
+        for (int p = m->q_off[q]; p < m->q_off[q + 1]; ++p) {
+            if (dt[p] != m->dt[p]) return 12;
+            if (dt[p] != m->d[m->dord[p]] || m->dpos[m->dord[p]] != p) return 13;
+            if (m->sq[p] != m->at[m->pos[m->dord[p]]]) return 14;
+            if (p > m->q_off[q] && m->dt[p] < m->dt[p - 1]) return 15;
         }
     }
     for (int q = 0; q < m->Q; ++q)  // the contended-arrival bits of multi-server FIFO queues

@@ -8,10 +8,10 @@ from bayes_qnet_b200 import qnetu
 from bayes_qnet_b200.arrivals import Arrivals
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-COND_NETS = ["mm1", "qnet3", "delay", "lng1", "mm3", "lnk", "psdelay"]
+COND_NETS = ["mm1", "qnet3", "delay", "lng1", "mm3", "lnk", "psdelay", "gg1r"]
 MH_NETS = ["mm1", "qnet3", "delay", "lng1", "mm3", "lnk"]  # PS has no arrivalLik (queues.pyx:1140): slice only
 STATIC_NETS = ["mm1", "qnet3", "delay", "lng1"]  # single-server FIFO + delay stations: queue order is static
-DYNAMIC_NETS = ["mm3", "lnk", "psdelay"]  # multi-server FIFO (k = 3, 4) and processor sharing: per-chain order
+DYNAMIC_NETS = ["mm3", "lnk", "psdelay", "gg1r"]  # multi-server FIFO (k = 3, 4), processor sharing, random order: per-chain order
 
 QNET3 = """
 states:
@@ -161,6 +161,23 @@ queues:
   - { name: QB, type: GGk, processors: 4, service: [LN, 0.3, 0.7] }
   - { name: QC, service: [G, 3.0, 0.1] }
 """,
+    # random-order queues (QueueGG1R) next to every other discipline; started from the sampled state with the hidden
+    # flags set, as the reference's own GG1R tests are (test_likdelta.py:43-48)
+    "gg1r_ps_gg2": """
+states:
+  - {name: INITIAL, queues: [INITIAL], successors: [A], initial: TRUE}
+  - {name: A, queues: [QA1, QA2], successors: [B]}
+  - {name: B, queues: [QB], successors: [C]}
+  - {name: C, queues: [QC], successors: [D]}
+  - {name: D, queues: [QD]}
+queues:
+  - { name: INITIAL, service: [M, 0.8] }
+  - { name: QA1, type: GG1R, service: [LN, -0.3, 0.6] }
+  - { name: QA2, type: DELAY, service: [M, 0.9] }
+  - { name: QB, type: PS, service: [M, 0.5] }
+  - { name: QC, type: GG1R, service: [G, 2.0, 0.25] }
+  - { name: QD, type: GGk, processors: 2, service: [M, 1.1] }
+""",
 }
 
 
@@ -169,6 +186,12 @@ def mixed(name, ntasks=80, pct=0.25, seed=21):
     old = qnet.get_initializer()
     qnet.set_initialization_type("PS" if "PS" in MIXED[name] else "DFN2")
     try:
+        if "GG1R" in MIXED[name]:
+            net = qnetu.qnet_from_text(MIXED[name])
+            qnetu.set_seed(seed)
+            smp = net.sample(ntasks)
+            sub = smp.subset_by_task(pct)
+            return net, smp, sub, sub
         return synthetic(MIXED[name], ntasks, pct, seed)
     finally:
         qnet.set_initialization_type(old)

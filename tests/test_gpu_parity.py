@@ -308,7 +308,7 @@ def test_full_size_invariants_dynamic(workload):
     qnet.set_initialization_type("DFN2")
 
 
-@pytest.mark.parametrize("name", ["mm1", "qnet3", "lng1", "mm3", "psdelay"])
+@pytest.mark.parametrize("name", ["mm1", "qnet3", "lng1", "mm3", "psdelay", "gg1rm"])
 def test_posterior_agrees_with_long_reference_runs(name):
     """estimation.bayes from the same initial state: posterior means of the service parameters and of the
     per-queue mean waiting time vs the reference's own long runs (tests/golden/post_*.npz), within 4 combined
@@ -630,12 +630,13 @@ def test_gibbs_front_end(tmp_path, monkeypatch, capsys):
     assert rc == 0 and numpy.loadtxt("mu2.txt").shape == (5, 7)
 
 
-@pytest.mark.parametrize("name", ["qnet3", "lng1", "mm3", "lnk", "delay_gg1_gg4"])
+@pytest.mark.parametrize("name", ["qnet3", "lng1", "mm3", "lnk", "delay_gg1_gg4", "gg1r"])
 def test_incremental_conditional_equals_log_prob_difference(name):
     """The identity the reference checks in test_likdelta.py:43-75: for hidden events and several offsets, the
     incrementally evaluated conditional inner_dfun(d1) - lik0 equals log_prob after physically moving the departure
     (queues re-ranked by arrival, services recomputed from scratch) minus log_prob before.  Here at a few hundred
-    tasks, on static- and dynamic-order networks, without the oracle."""
+    tasks, on static- and dynamic-order networks, without the oracle.  (Not on PS networks: there the reference's
+    sampling target carries log N terms that its log_prob lacks)"""
     if name in helpers.MIXED:
         net, smp, sub, ini = helpers.mixed(name, ntasks=300, pct=0.2, seed=33)
     else:
@@ -643,7 +644,9 @@ def test_incremental_conditional_equals_log_prob_difference(name):
         net = qnetu.qnet_from_text(str(g["yaml"]))
         net.parameters = list(g["theta"])
         qnetu.set_seed(44)
-        ini = net.gibbs_initialize(net.sample(300).subset_by_task(0.2))
+        ini = net.sample(300).subset_by_task(0.2)
+        if name != "gg1r":  # random-order networks start from the sampled state, as in test_likdelta.py:43-48
+            ini = net.gibbs_initialize(ini)
     rs = numpy.random.RandomState(9)
     # only feasible moves are compared: where the conditional is -inf (a service would go negative in the current
     # order) "the state after the move" is not defined -- re-ranking the queue from scratch can make it feasible again

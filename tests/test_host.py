@@ -281,3 +281,34 @@ def test_pooled_sufficient_statistics_and_engine_fingerprint():
     ev = [e for e in ini if not e.obs_d][0]
     ev.obs_d = 1
     assert _q._fingerprint(ini.soa()) != f0
+
+
+def test_gg1r_loader_simulator_and_state():
+    """QueueGG1R on the host (queues.pyx:788-1027): YAML `type: GG1R`, the simulator's random choice among the waiting
+    jobs (select_job_for_service, :1026), by-queue links in departure order, s = d - max(a, previous departure); the
+    simulated state satisfies the start-on-arrival rule, so the oracle's log_prob (which carries it) is finite."""
+    import helpers
+    from bayes_qnet_b200 import queues
+    net = qnetu.qnet_from_text(helpers.MIXED["gg1r_ps_gg2"])
+    assert [q.code for q in net.queues] == [0, 3, 1, 2, 3, 0]
+    assert net.queues[1].queue_order() == queues.ARRV_BY_D and "type: GG1R" in net.as_yaml()
+    net2 = qnetu.qnet_from_text(net.as_yaml())
+    assert [type(q).__name__ for q in net2.queues] == [type(q).__name__ for q in net.queues]
+    qnetu.set_seed(3)
+    smp = net.sample(400)
+    smp.validate()
+    soa = smp.soa()
+    inversions = 0
+    for q in (1, 4):
+        rows = smp._rows_of_queue(q)
+        d, a, s = soa["d"][rows], soa["a"][rows], soa["s"][rows]
+        assert numpy.all(numpy.diff(d) >= 0)                       # the list is the departure order
+        assert numpy.all(s > 0)
+        want = d - numpy.maximum(a, numpy.concatenate(([0.0], d[:-1])))
+        assert numpy.abs(want - s).max() < 1e-12
+        inversions += int(numpy.sum(numpy.diff(a) < 0))
+    assert inversions > 0                                          # jobs do overtake each other
+    oc = helpers.oracle_chain(net, smp)
+    assert numpy.isfinite(oc.log_prob())
+    sub = smp.subset_by_task(0.3)
+    assert numpy.isfinite(helpers.oracle_chain(net, sub).log_prob())
