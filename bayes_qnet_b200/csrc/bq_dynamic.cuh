@@ -784,8 +784,9 @@ BQ_HDI double gg1r_arr_delta(const Chain &c, const EventCtx &ev, double x, Touch
 // ---------------------------------------------------------------------------------------------
 // the conditional of d_e: inner_dfun(x) - lik0   (qnet.pyx:1340-1357)
 // ---------------------------------------------------------------------------------------------
-// PS = false: a build for networks without processor-sharing queues (their code is half of the kernel)
-template <int KMAX, bool PS = true>
+// PS = 0: a build for networks without processor-sharing queues (their code is half of the kernel); 1: with them;
+// 2: with the random-order queues as well (their code in the processor-sharing build cost config 4 a quarter of its rate)
+template <int KMAX, int PS = 2>
 BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, Touch &tc) {
     double g;
     tc.p0(ev.p0);
@@ -800,7 +801,7 @@ BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, Touch &t
             ps_move_setup(c, ev.q0, ev.p0, ev.e, true, ev.x0, x, mv, tc);
             g = ps_apply_move<false>(c, mv, 0, tc);
         }
-    } else if (PS && ev.t0 == Q_GG1R) {
+    } else if (PS >= 2 && ev.t0 == Q_GG1R) {
         g = gg1r_dep_delta(c, ev, x, tc);
     } else {  // DelayStation: s = d - a, single-event diff list (queues.pyx:745-784)
         const double sn = x - ev.a_e, so = ev.x0 - ev.a_e;
@@ -819,7 +820,7 @@ BQ_HDI double dyn_logcond(const Chain &c, const EventCtx &ev, double x, Touch &t
             ps_move_setup(c, ev.q1, ev.p1, ev.e1, false, ev.x0, x, mv, tc);
             g1 = ps_apply_move<false>(c, mv, 0, tc);
         }
-    } else if (PS && ev.t1 == Q_GG1R) {
+    } else if (PS >= 2 && ev.t1 == Q_GG1R) {
         g1 = gg1r_arr_delta(c, ev, x, tc);
     } else {
         const double sn = ev.d1 - x, so = ev.d1 - ev.x0;
@@ -911,7 +912,7 @@ BQ_HDI void reslot(double *v, int sv, int *ev, int *inv, double *pay0, int s0, d
 #undef P1_
 }
 
-template <int W, int KMAX, bool PS = true>
+template <int W, int KMAX, int PS = 2>
 BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, unsigned gmask) {
     // ---- everything that is computed on the old state first ------------------------------------------------
     int j1 = ev.p1;
@@ -970,7 +971,7 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         if (c.dt[pd] <= x) --j;
         reslot<W>(c.dt, 1, c.dord, c.dpos, nullptr, 1, nullptr, 1, pd, j, x, lane, gmask);
     }
-    if (PS && ev.t0 == Q_GG1R) {  // the event takes its new place in the departure order, its arrival time with it
+    if (PS >= 2 && ev.t0 == Q_GG1R) {  // the event takes its new place in the departure order, its arrival time with it
         const QInfo &q = c.qi[ev.q0];
         const int pd = c.dpos[ev.e];
         int jp, jn;
@@ -1005,7 +1006,7 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
         BQ_SYNCG(gmask);
     } else if (PS && ev.t1 == Q_PS) {
         reslot<W>(c.rec + BQ_REC_AT, c.S, c.ord, c.pos, c.rec + BQ_REC_DQ, c.S, c.sq, 1, ev.p1, j1, x, lane, gmask);
-    } else if (PS && ev.t1 == Q_GG1R) {  // new rank among the arrivals; the departure order is untouched
+    } else if (PS >= 2 && ev.t1 == Q_GG1R) {  // new rank among the arrivals; the departure order is untouched
         reslot<W>(c.rec + BQ_REC_AT, c.S, c.ord, c.pos, c.rec + BQ_REC_DQ, c.S, nullptr, 1, ev.p1, j1, x, lane, gmask);
         if (lane == 0) c.sq[c.dpos[ev.e1]] = x;
         BQ_SYNCG(gmask);
@@ -1038,7 +1039,7 @@ struct LaneParams {
     double tmax;
 };
 
-template <int KMAX, bool MH = true, bool SLICE = true, bool PS = true>
+template <int KMAX, bool MH = true, bool SLICE = true, int PS = 2>
 BQ_HDI void lane_update(const Chain &c, const EventCtx &ev, const LaneParams &P, LaneUpdate &out) {
     out.x_new = ev.x0; out.changed = 0; out.counted = 0; out.rejected = 0; out.stuck = 0; out.evals = 0;
     out.R.reset(); out.Wt.reset();
@@ -1462,7 +1463,7 @@ __device__ __forceinline__ bool claimed_before(const int *claim, int lo, int hi,
 // chains are resident; with more than 16 x 148 chains the 8-CTA build (64 registers, some spilling, 32 warps/SM) avoids
 // a second, partly filled wave (measured: +12 % at 4096 chains, -17 % at 2048)
 // MHK: the build for MH sweeps; the slice build carries no proposal code (fewer registers, less spilling).
-template <int KMAX, int MINB, bool MHK, bool PS>
+template <int KMAX, int MINB, bool MHK, int PS>
 __global__ void __launch_bounds__(128, MINB) sweep_batch_kernel(const DynArgs A, int *claim_all, int *claimd_all) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int W = 32;

@@ -552,12 +552,17 @@ static void launch_dynamic(bq_handle *h, const DynArgs &A) {
 #endif
 #define BQ_LAUNCH_BATCH(K, MINB, MHK) \
     do { \
-        if (h->has_ps) { smem_optin((const void *)sweep_batch_kernel<K, MINB, MHK, true>, sm); \
-            sweep_batch_kernel<K, MINB, MHK, true><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd); } \
-        else { smem_optin((const void *)sweep_batch_kernel<K, MINB, MHK, false>, sm); \
-            sweep_batch_kernel<K, MINB, MHK, false><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd); } \
+        if (h->has_ps) { smem_optin((const void *)sweep_batch_kernel<K, MINB, MHK, 1>, sm); \
+            sweep_batch_kernel<K, MINB, MHK, 1><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd); } \
+        else { smem_optin((const void *)sweep_batch_kernel<K, MINB, MHK, 0>, sm); \
+            sweep_batch_kernel<K, MINB, MHK, 0><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd); } \
     } while (0)
         const bool mh = (A.mode == MODE_MH);
+        if (h->has_gg1r) {  // random-order queues: one build (slice only, any k), 16 warps per SM
+            smem_optin((const void *)sweep_batch_kernel<8, 4, false, 2>, sm);
+            sweep_batch_kernel<8, 4, false, 2><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
+            return;
+        }
         if (h->kmax <= 4) {
             if (dense) { if (mh) BQ_LAUNCH_BATCH(4, BQ_DENSE_MINB, true); else BQ_LAUNCH_BATCH(4, BQ_DENSE_MINB, false); }
             else { if (mh) BQ_LAUNCH_BATCH(4, 4, true); else BQ_LAUNCH_BATCH(4, 4, false); }

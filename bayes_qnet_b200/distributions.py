@@ -8,7 +8,7 @@ import math
 
 import numpy
 
-D_EXP, D_GAMMA, D_LOGNORMAL = 0, 1, 2
+D_EXP, D_GAMMA, D_LOGNORMAL, D_DIRAC = 0, 1, 2, 3
 HALF_LOG_2PI = -0.918938533204673  # distributions.pyx:243
 
 
@@ -182,3 +182,42 @@ class LogNormal(Distribution):
         lpdf_tau = (alpha - 1) * math.log(tau) - tau / beta - lgamma(alpha) - alpha * math.log(beta)
         lpdf_mu = -0.5 * math.log(2 * math.pi) - math.log(sd_new) - (mu_new - mean) ** 2 / (2 * sd_new * sd_new)
         return lpdf_mu + lpdf_tau
+
+
+class Dirac(Distribution):
+    """distributions.pyx:347-375: a constant service time.  parameters = [loc].  Like the reference's class it has no
+    log-density -- it serves forward simulation (Qnet.sample) and reporting; the samplers refuse a network that
+    carries one (bq_create: unknown service family), where the reference fails at its first lpdf call."""
+    code = D_DIRAC
+
+    def __init__(self, loc):
+        self.loc = float(loc)
+
+    def __repr__(self):
+        return "<DIRAC LOC=%s/>" % self.loc
+
+    def mean(self):
+        return self.loc
+
+    def std(self):
+        return 0.0
+
+    def sample(self, N):
+        return numpy.full(N, self.loc)
+
+    def quantile(self, p):
+        return self.loc
+
+    def estimate(self, data):
+        self.loc = float(numpy.mean(data))
+
+    @property
+    def parameters(self):
+        return [self.loc]
+
+    @parameters.setter
+    def parameters(self, v):
+        self.loc = float(v[0])
+
+    def as_yaml(self):
+        return "[D, %s]" % self.loc

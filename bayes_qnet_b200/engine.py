@@ -44,6 +44,9 @@ class GibbsEngine(object):
         self.E = len(soa["d"])
         self.Q = len(net.queues)
         q_type, q_k, q_dist, q_poff, self.P, q_slot, slot_dist = flatten_model(net)
+        if numpy.any(slot_dist == 3):
+            raise NotImplementedError("a Dirac service time has no density (distributions.pyx:347-375): such a network can "
+                                      "be simulated, not sampled")
         self._keep = [q_type, q_k, q_dist, q_poff, q_slot, slot_dist]
         self.q_slot = q_slot
         self.NS = int(q_slot[-1])

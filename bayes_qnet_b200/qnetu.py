@@ -150,7 +150,7 @@ def _dist_from_yaml(dist_type, args):
             mu, sig = 0, 1
         return distributions.LogNormal(mu, sig)
     if dist_type == "D":
-        raise NotImplementedError("Dirac service is outside the GPU hot path")
+        return distributions.Dirac(args[0])
     raise Exception("Could not understand tag %s" % dist_type)
 
 

@@ -312,3 +312,48 @@ def test_gg1r_loader_simulator_and_state():
     assert numpy.isfinite(oc.log_prob())
     sub = smp.subset_by_task(0.3)
     assert numpy.isfinite(helpers.oracle_chain(net, sub).log_prob())
+
+
+def test_dirac_service_simulates_and_is_refused_by_the_samplers():
+    """[D, loc] (qnetu.py:183-184, distributions.pyx:347-375): constant service times in Qnet.sample; no density, so the
+    engine refuses the network before touching the device."""
+    from bayes_qnet_b200 import GibbsEngine, distributions
+    text = """
+states:
+  - {name: I0, queues: [I0], successors: [S1], initial: TRUE}
+  - {name: S1, queues: [Q1]}
+queues:
+  - { name: I0, service: [M, 1.0] }
+  - { name: Q1, service: [D, 0.25] }
+"""
+    net = qnetu.qnet_from_text(text)
+    assert isinstance(net.queues[1].service.f, distributions.Dirac) and net.parameters == [1.0, 0.25]
+    assert "[D, 0.25]" in net.as_yaml()
+    qnetu.set_seed(2)
+    smp = net.sample(50)
+    smp.validate()
+    soa = smp.soa()
+    assert numpy.allclose(soa["s"][soa["qid"] == 1], 0.25)
+    with pytest.raises(NotImplementedError):
+        GibbsEngine(net, smp.subset_by_task(0.5), n_chains=1)
+
+
+def test_initialiser_on_random_order_networks_adds_no_violation():
+    """gibbs_initialize on a GG1R network: hidden jobs are placed so that none of them starts on arrival with other
+    jobs present and none makes a job already placed do so; what remains are observed jobs whose waiting was caused by
+    a hidden departure (the reference's initialisers stop there with an assertion, queues.pyx:843-853)."""
+    import helpers
+    from bayes_qnet_b200 import initialize
+    g = helpers.golden("cond_gg1r")
+    net = qnetu.qnet_from_text(str(g["yaml"]))
+    qnetu.set_seed(5)
+    smp = net.sample(300)
+    assert initialize.random_order_violations(net, smp) == []
+    sub = smp.subset_by_task(0.3)
+    ini = net.gibbs_initialize(sub)
+    ini.validate()
+    soa = ini.soa()
+    assert numpy.all(soa["s"] >= 0)
+    bad = initialize.random_order_violations(net, ini)
+    assert all(soa["obs_d"][r] == 1 for r in bad)
+    assert len(bad) < 0.05 * len(soa["d"])
