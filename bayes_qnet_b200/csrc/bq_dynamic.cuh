@@ -1020,6 +1020,126 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
 }
 
 // ---------------------------------------------------------------------------------------------
+// Where the conditional is -inf, known BEFORE the shrink loop (batch kernel).  Two thirds of all evaluations on the
+// G/G/3 tandem return -inf -- the bracket [a_e, min(d_e', Tmax)] is far wider than the support -- and they hold 70 %
+// of the walk steps (host emulation, 5 000-task tandem).  Each of the four ways a move can make a service negative
+// has a WITNESS that a short scan next to the event finds once per update:
+//   d_e later:    a position p behind e (F[p][0] >= d_e) that leaves before the second server is free, F[p][1] > d_p:
+//                 it would have to wait for min(F[p][1], x) > d_p as soon as x > d_p  ->  -inf for every x > d_p
+//   d_e earlier:  only e's own service, x - max(a_e, F[p0][0]) < 0                     ->  -inf for every x < that start
+//   a_e' earlier: an event p that e' would overtake (a_p > x) with F[p][1] > d_p and d_e' > d_p: with e' ahead of it
+//                 its server is free at min(F[p][1], d_e') > d_p                        ->  -inf for every x < a_p
+//   a_e' later:   the event p at which the departures later than d_e' among the predecessors of e' reach k (those in
+//                 F[p1] plus the events e' lets pass): every server is busy past d_e'     ->  -inf for every x >= a_p
+// A candidate beyond a witness is rejected without a walk; it still counts as an evaluation, and every candidate that
+// is not provably outside is evaluated as before, so the update is exactly the sequential sampling._slice (the scans are
+// bounded: a missing witness only means less pruning).  Delay stations have their support in closed form; processor
+// sharing and random-order queues are left to their evaluations.  The positions scanned are part of the read set.
+// ---------------------------------------------------------------------------------------------
+#ifndef BQ_SUPPORT_SCAN
+#define BQ_SUPPORT_SCAN 24
+#endif
+struct Support {
+    double lo, hi, hi_open;  // x < x0 needs x >= lo; x > x0 needs x <= hi and x < hi_open
+    BQ_HDF bool outside(double x, double x0) const { return (x > x0) ? (x > hi || x >= hi_open) : (x < x0 && x < lo); }
+};
+
+template <int KMAX>
+BQ_HDI void dyn_support(const Chain &c, const EventCtx &ev, double lower, double upper, Support &sp, Touch &tc) {
+    sp.lo = -INFINITY; sp.hi = INFINITY; sp.hi_open = INFINITY;
+    const int S = c.S;
+    if (ev.t0 == Q_GGK) {
+        const QInfo &q = c.qi[ev.q0];
+        const int k = q.k, p0 = ev.p0;
+        const double *f = c.fvec(q, p0);
+        sp.lo = dmax(ev.a_e, f[0]);
+        if (p0 + 1 < q.hi && upper > ev.x0) {
+            int far;
+            int p = free_min_bound(f + S, S, p0 + 1, q.hi, ev.x0, false, &far);
+            tc.p0(far);
+            double T = INFINITY;
+            bool stop = false;
+            for (int n = 0; p < q.hi && n < BQ_SUPPORT_SCAN && !stop; p += 4, n += 4) {
+                double f0_[4], f1_[4], dp_[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int pu = (p + u < q.hi - 1) ? p + u : q.hi - 1;
+                    const double *fp = f + (size_t)(pu - p0) * S;
+                    f0_[u] = fp[0]; f1_[u] = (k > 1) ? fp[1] : INFINITY; dp_[u] = fp[BQ_REC_DQ - BQ_REC_F];
+                }
+                tc.p0(p);
+                tc.p0(p + 3 < q.hi - 1 ? p + 3 : q.hi - 1);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (stop || p + u >= q.hi) break;
+                    if (f0_[u] >= ((T < upper) ? T : upper)) { stop = true; break; }  // nobody further on leaves before T, or is reached at all
+                    if (f1_[u] > dp_[u] && dp_[u] < T) T = dp_[u];
+                }
+            }
+            sp.hi = T;
+        }
+    } else if (ev.t0 == Q_DELAY) {
+        sp.lo = ev.a_e;
+    }
+    if (ev.e1 < 0) return;
+    if (ev.t1 == Q_GGK) {
+        const QInfo &q = c.qi[ev.q1];
+        const int k = q.k, p1 = ev.p1;
+        const double d1 = ev.d1;
+        if (lower < ev.x0) {
+            // four records per trip, fetched before any of them is looked at: their misses overlap
+            bool stop = false;
+            for (int base = p1 - 1, n = 0; base >= q.lo && n < BQ_SUPPORT_SCAN && !stop; base -= 4, n += 4) {
+                double ap_[4], f1_[4], dp_[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int pu = (base - u > q.lo) ? base - u : q.lo;
+                    const double *r = c.rec + (size_t)pu * S;
+                    ap_[u] = r[BQ_REC_AT]; f1_[u] = (k > 1) ? r[BQ_REC_F + 1] : INFINITY; dp_[u] = r[BQ_REC_DQ];
+                }
+                tc.p1(base - 3 > q.lo ? base - 3 : q.lo);
+                tc.p1(base);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (stop || base - u < q.lo) break;
+                    if (!(ap_[u] > lower)) { stop = true; break; }  // no candidate overtakes this one
+                    if (f1_[u] > dp_[u] && d1 > dp_[u]) { sp.lo = dmax(sp.lo, ap_[u]); stop = true; break; }
+                }
+            }
+        }
+        if (upper > ev.x0) {
+            const double *f1v = c.fvec(q, p1);
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j)
+                if (j < k && f1v[BQ_FSLOT(j)] > d1) ++cnt;
+            if (cnt < k) {
+                bool stop = false;
+                for (int base = p1 + 1, n = 0; base < q.hi && n < BQ_SUPPORT_SCAN && !stop; base += 4, n += 4) {
+                    double ap_[4], dp_[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int pu = (base + u < q.hi - 1) ? base + u : q.hi - 1;
+                        const double *r = c.rec + (size_t)pu * S;
+                        ap_[u] = r[BQ_REC_AT]; dp_[u] = r[BQ_REC_DQ];
+                    }
+                    tc.p1(base);
+                    tc.p1(base + 3 < q.hi - 1 ? base + 3 : q.hi - 1);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (stop || base + u >= q.hi) break;
+                        if (ap_[u] > upper) { stop = true; break; }  // no candidate lets this one pass
+                        if (dp_[u] > d1 && ++cnt >= k) { sp.hi_open = ap_[u]; stop = true; break; }
+                    }
+                }
+            }
+        }
+    } else if (ev.t1 == Q_DELAY) {
+        sp.hi = (ev.d1 < sp.hi) ? ev.d1 : sp.hi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // One lane, one event: the whole update computed WITHOUT writing anything -- one step of sampling._slice on the exact
 // conditional (sequential candidates) or one MH-within-Gibbs proposal + accept decision -- together with the ranges
 // it read (R) and the ranges the accepted move will write (Wt = what the accepted candidate's evaluation touched).
@@ -1058,8 +1178,38 @@ BQ_HDI void lane_update(const Chain &c, const EventCtx &ev, const LaneParams &P,
         Rng rng;
         rng.init(P.seed, P.gchain, P.gsw, (unsigned int)ev.e, TAG_SLICE);
         out.counted = 1;
-        const double x1 = slice_finite_seq(g, ev.x0, lower, upper, rng, out.evals);
-        if (x1 != ev.x0) { out.changed = 1; out.x_new = x1; out.Wt = last; }
+        Support sp;
+        dyn_support<KMAX>(c, ev, lower, upper, sp, out.R);
+        // sampling._slice with finite bounds (slice_finite_seq, bq_dist.cuh), arranged for a warp whose lanes run it
+        // side by side: a lane first passes over the candidates that are provably outside the support -- arithmetic
+        // only -- and the lanes then walk their next real candidate TOGETHER, so a round of the warp costs as many
+        // walks as its busiest lane needs instead of one sparsely populated walk per candidate index.
+        const double x0 = ev.x0;
+        const double gx0 = g(x0);
+        ++out.evals;
+        const double logy = gx0 - (-log_d(1.0 - rng.uniform()));
+        double x1 = x0;
+        if (logy > BQ_NEG_INF) {
+            double L = lower, R = upper;
+            int it = 0;
+            for (;;) {
+                bool have = false;
+                double xc = x0;
+                while (it < 1000) {
+                    xc = L + (R - L) * (it == 0 ? rng.uniform() : rng.uniform32());  // bq_rng.cuh: candidate uniforms
+                    ++it;
+                    ++out.evals;
+                    if (!sp.outside(xc, x0)) { have = true; break; }
+                    if (xc > x0) R = xc; else L = xc;
+                    if (R - L < 1e-10) break;
+                }
+                if (!have) break;
+                if (g(xc) >= logy) { x1 = xc; break; }
+                if (xc > x0) R = xc; else L = xc;
+                if (R - L < 1e-10) break;
+            }
+        }
+        if (x1 != x0) { out.changed = 1; out.x_new = x1; out.Wt = last; }
         else out.stuck = 1;
         return;
     }
@@ -1394,8 +1544,10 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
             rng.init(A.seed, gchain, gsw, (unsigned int)ev.e, TAG_SLICE);
             n_ev += 1;
             double xacc = ev.x0;
-            const bool accepted = group_slice<W>([&](double x) { return dyn_logcond<KMAX>(c, ev, x, tc); }, ev.x0, lower,
-                                                 upper, rng, gl, xacc, n_evals, n_stuck);
+            Support sp;  // candidates provably outside the support need no walk (dyn_support)
+            dyn_support<KMAX>(c, ev, lower, upper, sp, tc);
+            const bool accepted = group_slice<W>([&](double x) { return sp.outside(x, ev.x0) ? BQ_NEG_INF : dyn_logcond<KMAX>(c, ev, x, tc); },
+                                                 ev.x0, lower, upper, rng, gl, xacc, n_evals, n_stuck);
             n_steps += tc.steps;
             if (accepted && xacc != ev.x0) dyn_commit<W, KMAX>(c, ev, xacc, lane, gmask);
             __syncwarp(gmask);

@@ -77,6 +77,9 @@ for r in csv.reader(src.splitlines()):
 print("\nSASS opcode mix (%% of warp instructions executed / %% of stall samples), total %.3e warp instructions:" % tot)
 osum, ssum = sum(ops.values()), sum(ops_s.values())
 print("  " + "  ".join("%s=%.1f/%.1f" % (op, 100.0 * n / osum, 100.0 * ops_s[op] / max(ssum, 1)) for op, n in ops.most_common(18)))
-print("\nhottest source lines (%% warp instructions, %% samples, mean active lanes):")
-for k, (n, s, t) in sorted(lines.items(), key=lambda kv: -kv[1][0])[:30]:
+print("\nhottest source lines by warp instructions (%% warp instructions, %% samples, mean active lanes):")
+for k, (n, s_, t) in sorted(lines.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[2]) if len(sys.argv) > 2 else 30]:
+    print("  %5.1f%% %5.1f%% %5.1f  %s:%s  %s" % (100.0 * n / tot, 100.0 * s_ / max(tots, 1), t / max(n, 1), k[0], k[1], k[2]))
+print("\nhottest source lines by stall samples (%% warp instructions, %% samples, mean active lanes):")
+for k, (n, s, t) in sorted(lines.items(), key=lambda kv: -kv[1][1])[:int(sys.argv[2]) if len(sys.argv) > 2 else 30]:
     print("  %5.1f%% %5.1f%% %5.1f  %s:%s  %s" % (100.0 * n / tot, 100.0 * s / max(tots, 1), t / max(n, 1), k[0], k[1], k[2]))
