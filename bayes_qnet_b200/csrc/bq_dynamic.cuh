@@ -74,7 +74,7 @@ struct DynRec {
 };
 
 struct DynArgs {
-    int E, Q, P, n_order, n_sweeps, update, flags, trace_base, n_chains, S, mode;
+    int E, Q, P, n_order, n_sweeps, update, flags, trace_base, n_chains, S, mode, scan;
     const DynRec *order;  // [n_order]
     const QInfo *qinfo;   // [Q]
     const int *q_poff;    // [Q] offset of the queue's first parameter
@@ -1037,7 +1037,7 @@ BQ_HDI void dyn_commit(const Chain &c, const EventCtx &ev, double x, int lane, u
 // sharing and random-order queues are left to their evaluations.  The positions scanned are part of the read set.
 // ---------------------------------------------------------------------------------------------
 #ifndef BQ_SUPPORT_SCAN
-#define BQ_SUPPORT_SCAN 24
+#define BQ_SUPPORT_SCAN 96  // default number of positions a witness scan looks at (DynArgs::scan; measured: profiles/r2_support_scan.log)
 #endif
 struct Support {
     double lo, hi, hi_open;  // x < x0 needs x >= lo; x > x0 needs x <= hi and x < hi_open
@@ -1045,7 +1045,8 @@ struct Support {
 };
 
 template <int KMAX>
-BQ_HDI void dyn_support(const Chain &c, const EventCtx &ev, double lower, double upper, Support &sp, Touch &tc) {
+BQ_HDI void dyn_support(const Chain &c, const EventCtx &ev, double lower, double upper, Support &sp, Touch &tc,
+                        int scan = BQ_SUPPORT_SCAN) {
     sp.lo = -INFINITY; sp.hi = INFINITY; sp.hi_open = INFINITY;
     const int S = c.S;
     if (ev.t0 == Q_GGK) {
@@ -1059,7 +1060,7 @@ BQ_HDI void dyn_support(const Chain &c, const EventCtx &ev, double lower, double
             tc.p0(far);
             double T = INFINITY;
             bool stop = false;
-            for (int n = 0; p < q.hi && n < BQ_SUPPORT_SCAN && !stop; p += 4, n += 4) {
+            for (int n = 0; p < q.hi && n < scan && !stop; p += 4, n += 4) {
                 double f0_[4], f1_[4], dp_[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -1089,7 +1090,7 @@ BQ_HDI void dyn_support(const Chain &c, const EventCtx &ev, double lower, double
         if (lower < ev.x0) {
             // four records per trip, fetched before any of them is looked at: their misses overlap
             bool stop = false;
-            for (int base = p1 - 1, n = 0; base >= q.lo && n < BQ_SUPPORT_SCAN && !stop; base -= 4, n += 4) {
+            for (int base = p1 - 1, n = 0; base >= q.lo && n < scan && !stop; base -= 4, n += 4) {
                 double ap_[4], f1_[4], dp_[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -1115,7 +1116,7 @@ BQ_HDI void dyn_support(const Chain &c, const EventCtx &ev, double lower, double
                 if (j < k && f1v[BQ_FSLOT(j)] > d1) ++cnt;
             if (cnt < k) {
                 bool stop = false;
-                for (int base = p1 + 1, n = 0; base < q.hi && n < BQ_SUPPORT_SCAN && !stop; base += 4, n += 4) {
+                for (int base = p1 + 1, n = 0; base < q.hi && n < scan && !stop; base += 4, n += 4) {
                     double ap_[4], dp_[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -1157,6 +1158,7 @@ struct LaneParams {
     unsigned int gsw;
     int mode, flags;
     double tmax;
+    int scan = BQ_SUPPORT_SCAN;
 };
 
 template <int KMAX, bool MH = true, bool SLICE = true, int PS = 2>
@@ -1179,13 +1181,28 @@ BQ_HDI void lane_update(const Chain &c, const EventCtx &ev, const LaneParams &P,
         rng.init(P.seed, P.gchain, P.gsw, (unsigned int)ev.e, TAG_SLICE);
         out.counted = 1;
         Support sp;
-        dyn_support<KMAX>(c, ev, lower, upper, sp, out.R);
+        dyn_support<KMAX>(c, ev, lower, upper, sp, out.R, P.scan);
         // sampling._slice with finite bounds (slice_finite_seq, bq_dist.cuh), arranged for a warp whose lanes run it
         // side by side: a lane first passes over the candidates that are provably outside the support -- arithmetic
         // only -- and the lanes then walk their next real candidate TOGETHER, so a round of the warp costs as many
         // walks as its busiest lane needs instead of one sparsely populated walk per candidate index.
         const double x0 = ev.x0;
-        const double gx0 = g(x0);
+        // g(x0) is the likelihood delta of not moving: exactly 0 when the two services it would touch are non-negative
+        // (no term of a FIFO / delay / PS diff list changes at x = x0), so the walk is only taken when the state is
+        // invalid there -- or a random-order queue is involved, whose feasibility rule can fail at x0 itself
+        double gx0;
+        {
+            bool plain = (ev.t0 == Q_GGK || ev.t0 == Q_DELAY) && (ev.e1 < 0 || ev.t1 == Q_GGK || ev.t1 == Q_DELAY);
+            if (plain) {
+                const double st0 = (ev.t0 == Q_GGK) ? dmax(ev.a_e, c.fvec(c.qi[ev.q0], ev.p0)[0]) : ev.a_e;
+                plain = (x0 - st0 >= 0.0);
+                if (plain && ev.e1 >= 0) {
+                    const double st1 = (ev.t1 == Q_GGK) ? dmax(x0, c.fvec(c.qi[ev.q1], ev.p1)[0]) : x0;
+                    plain = (ev.d1 - st1 >= 0.0);
+                }
+            }
+            gx0 = plain ? 0.0 : g(x0);
+        }
         ++out.evals;
         const double logy = gx0 - (-log_d(1.0 - rng.uniform()));
         double x1 = x0;
@@ -1545,7 +1562,7 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
             n_ev += 1;
             double xacc = ev.x0;
             Support sp;  // candidates provably outside the support need no walk (dyn_support)
-            dyn_support<KMAX>(c, ev, lower, upper, sp, tc);
+            dyn_support<KMAX>(c, ev, lower, upper, sp, tc, A.scan);
             const bool accepted = group_slice<W>([&](double x) { return sp.outside(x, ev.x0) ? BQ_NEG_INF : dyn_logcond<KMAX>(c, ev, x, tc); },
                                                  ev.x0, lower, upper, rng, gl, xacc, n_evals, n_stuck);
             n_steps += tc.steps;
@@ -1646,6 +1663,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_batch_kernel(const DynArgs A,
 
     LaneParams LP;
     LP.seed = A.seed; LP.gchain = (unsigned long long)(A.chain_offset + chain); LP.mode = A.mode; LP.flags = A.flags;
+    LP.scan = A.scan;
     long long n_ev = 0, n_evals = 0, n_stuck = 0, n_pevals = 0, n_steps = 0, n_reject = 0, n_redo = 0;
     const int4 *order4 = reinterpret_cast<const int4 *>(A.order);
     int round = 0;

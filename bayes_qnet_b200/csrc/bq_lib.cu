@@ -277,6 +277,8 @@ static void fill_dyn_args(const bq_handle *h, DynArgs &A) {
     A.theta = h->d_theta; A.stats = h->d_stats;
     A.tr_theta = h->d_tr_theta; A.tr_wait = h->d_tr_wait; A.tr_logp = h->d_tr_logp;
     A.seed = h->seed; A.chain_offset = h->chain_offset; A.sweep_base = h->sweep_counter;
+    A.scan = BQ_SUPPORT_SCAN;
+    if (const char *env = getenv("BQ_SUPPORT_SCAN")) A.scan = std::max(0, atoi(env));  // tuning / test hook: 0 = no pruning
 }
 
 // host staging of the per-chain derived arrays for `rows` chains

@@ -40,8 +40,8 @@ queues:
 """)
     assert [(q.code, q.k, q.service.code) for q in mm3.queues] == [(0, 1, 0), (0, 3, 2), (1, 1, 1), (2, 1, 0)]
     assert mm3.parameters == [10.0, 1.75, 1.0, 2.0, 0.5, 0.5]
-    with pytest.raises(NotImplementedError):
-        qnetu.qnet_from_text(helpers.MM1.replace("[M, 0.7]", "[M, 0.7], type: GG1R"))
+    rnd = qnetu.qnet_from_text(helpers.MM1.replace("[M, 0.7]", "[M, 0.7], type: GG1R"))  # qnetu.py:115-116
+    assert type(rnd.queues[1]).__name__ == "QueueGG1R" and rnd.queues[1].code == 3
     with pytest.raises(Exception):
         qnetu.qnet_from_text("- 1\n- 2\n")
 
