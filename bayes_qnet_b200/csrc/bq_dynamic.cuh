@@ -1068,11 +1068,10 @@ BQ_HDI void dyn_support(const Chain &c, const EventCtx &ev, double lower, double
                     const double *fp = f + (size_t)(pu - p0) * S;
                     f0_[u] = fp[0]; f1_[u] = (k > 1) ? fp[1] : INFINITY; dp_[u] = fp[BQ_REC_DQ - BQ_REC_F];
                 }
-                tc.p0(p);
-                tc.p0(p + 3 < q.hi - 1 ? p + 3 : q.hi - 1);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 4; ++u) {  // only the records the decision looked at belong to the read set
                     if (stop || p + u >= q.hi) break;
+                    tc.p0(p + u);
                     if (f0_[u] >= ((T < upper) ? T : upper)) { stop = true; break; }  // nobody further on leaves before T, or is reached at all
                     if (f1_[u] > dp_[u] && dp_[u] < T) T = dp_[u];
                 }
@@ -1098,11 +1097,10 @@ BQ_HDI void dyn_support(const Chain &c, const EventCtx &ev, double lower, double
                     const double *r = c.rec + (size_t)pu * S;
                     ap_[u] = r[BQ_REC_AT]; f1_[u] = (k > 1) ? r[BQ_REC_F + 1] : INFINITY; dp_[u] = r[BQ_REC_DQ];
                 }
-                tc.p1(base - 3 > q.lo ? base - 3 : q.lo);
-                tc.p1(base);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (stop || base - u < q.lo) break;
+                    tc.p1(base - u);
                     if (!(ap_[u] > lower)) { stop = true; break; }  // no candidate overtakes this one
                     if (f1_[u] > dp_[u] && d1 > dp_[u]) { sp.lo = dmax(sp.lo, ap_[u]); stop = true; break; }
                 }
@@ -1124,11 +1122,10 @@ BQ_HDI void dyn_support(const Chain &c, const EventCtx &ev, double lower, double
                         const double *r = c.rec + (size_t)pu * S;
                         ap_[u] = r[BQ_REC_AT]; dp_[u] = r[BQ_REC_DQ];
                     }
-                    tc.p1(base);
-                    tc.p1(base + 3 < q.hi - 1 ? base + 3 : q.hi - 1);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         if (stop || base + u >= q.hi) break;
+                        tc.p1(base + u);
                         if (ap_[u] > upper) { stop = true; break; }  // no candidate lets this one pass
                         if (dp_[u] > d1 && ++cnt >= k) { sp.hi_open = ap_[u]; stop = true; break; }
                     }
@@ -1620,12 +1617,20 @@ __global__ void __launch_bounds__(128) sweep_dynamic_kernel(const DynArgs A) {
 __device__ __forceinline__ void claim_range(int *claim, int lo, int hi, int stamp) {
     for (int p = lo; p <= hi; ++p) atomicMax(&claim[p], stamp);
 }
+// no early exit: the loads of a range are independent of each other and stay in flight together (the read ranges hold
+// the witness scans, up to a few hundred positions)
 __device__ __forceinline__ bool claimed_before(const int *claim, int lo, int hi, int round_base, int lane) {
-    for (int p = lo; p <= hi; ++p) {
-        const int v = __ldcg(&claim[p]);
-        if (v >= round_base && 31 - (v - round_base) < lane) return true;
+    if (lo > hi) return false;  // an unset range is (INT_MAX, -1): nothing below may add to lo
+    const int thr = round_base + 31 - lane;  // stamps of this round from earlier lanes are > thr
+    bool hit = false;
+    int p = lo;
+    for (; p <= hi && (reinterpret_cast<size_t>(claim + p) & 15); ++p) hit |= __ldcg(&claim[p]) > thr;  // per-chain rows start anywhere
+    for (; p + 3 <= hi; p += 4) {
+        const int4 v = __ldcg(reinterpret_cast<const int4 *>(claim + p));
+        hit |= (v.x > thr) | (v.y > thr) | (v.z > thr) | (v.w > thr);
     }
-    return false;
+    for (; p <= hi; ++p) hit |= __ldcg(&claim[p]) > thr;
+    return hit;
 }
 
 // MINB = CTAs of 128 threads resident per SM: 4 (128 registers per thread, 16 warps/SM) is fastest as long as all
