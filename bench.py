@@ -108,8 +108,11 @@ NCU_TRAFFIC = {
     ("config2", 5000, 1024, 20): (273.98e6, "profiles/r1_static_final_ncu_full.txt (166.0 MB read + 108.0 MB written): far BELOW "
                                             "the algorithmic 16 B x resamples because the chain state stays in shared memory "
                                             "for all sweeps of a launch"),
-    ("config3", 20000, 4096, 2): (762250469376.0 + 251954478592.0, "profiles/r1_config3_dram_traffic.csv: 80x the algorithmic "
-                                  "32 B x resamples -- every evaluation re-reads the event's neighbourhood from HBM"),
+    ("config3", 20000, 4096, 2): (1006938248960.0 + 291083597056.0, "profiles/r2_config3_dram_traffic.csv (round 2, witness pruning): "
+                                  "3.3 KB per resample, 100x the algorithmic 32 B -- the witness scans (up to 96 records per update) "
+                                  "and the walks re-read each event's neighbourhood from HBM; round 1: 1014 GB per launch at 0.76x the rate"),
+    ("config4", 50000, 2048, 2): (400272155648.0 + 128419334400.0, "profiles/r2_config4_dram_traffic.csv: 1.1 KB per resample, 40x the "
+                                  "algorithmic 26.7 B"),
 }
 WORKLOAD = "%s, %d tasks, %d%% observed, %d chains/GPU x %d sweeps per step"
 # measured once, offline, at the REAL size on this repository's build container (tools/ref_fullsize.py; BASELINE.md
