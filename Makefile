@@ -8,8 +8,9 @@ ORACLE = oracle/libbq_oracle.so
 
 all: $(LIB) $(ORACLE)
 
-$(LIB): bayes_qnet_b200/csrc/bq_lib.cu $(wildcard bayes_qnet_b200/csrc/*.cuh) include/bq_capi.h
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ bayes_qnet_b200/csrc/bq_lib.cu -lcudart
+SRCS = bayes_qnet_b200/csrc/bq_lib.cu bayes_qnet_b200/csrc/bq_batch_nw.cu
+$(LIB): $(SRCS) $(wildcard bayes_qnet_b200/csrc/*.cuh) bayes_qnet_b200/csrc/bq_host.h include/bq_capi.h
+	$(NVCC) $(NVCCFLAGS) --threads 2 -shared -o $@ $(SRCS) -lcudart
 
 $(ORACLE): oracle/bq_oracle.c
 	gcc -O2 -ffp-contract=off -fPIC -shared -o $@ oracle/bq_oracle.c -lm

@@ -1,0 +1,48 @@
+// The batch kernel with two warps per chain (sweep_batch_kernel_nw, bq_dynamic.cuh), in a translation unit of its own.
+// Compiled together with the one-warp kernels it changed their inlining: the processor-sharing build of
+// sweep_batch_kernel went from 272 to 432 bytes of stack and config 4 from 7.7e8 to 5.5e8 resamples/s, with not a line
+// of that kernel touched.  Here the two sets of instantiations cannot influence each other.
+#include <cuda_runtime.h>
+
+#include "bq_dynamic.cuh"
+
+namespace bq {
+
+#ifndef BQ_DENSE_MINB
+#define BQ_DENSE_MINB 8
+#endif
+
+cudaError_t batch_nw_set_log_table(const double *tab256) {
+    return cudaMemcpyToSymbol(c_log_count, tab256, 256 * sizeof(double));
+}
+
+template <int K, int MINB, int PSV>
+static void launch_one(const DynArgs &A, int *claim, int *claimd, int blocks, size_t sm, cudaStream_t stream) {
+    if (sm > 48 * 1024)
+        cudaFuncSetAttribute((const void *)sweep_batch_kernel_nw<K, MINB, false, PSV, 2>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    sweep_batch_kernel_nw<K, MINB, false, PSV, 2><<<blocks, 128, sm, stream>>>(A, claim, claimd);
+}
+
+template <int K>
+static void launch_k(const DynArgs &A, int *claim, int *claimd, bool has_ps, bool dense, int blocks, size_t sm,
+                     cudaStream_t stream) {
+    if (has_ps) {
+        if (dense) launch_one<K, BQ_DENSE_MINB, 1>(A, claim, claimd, blocks, sm, stream);
+        else launch_one<K, 4, 1>(A, claim, claimd, blocks, sm, stream);
+    } else {
+        if (dense) launch_one<K, BQ_DENSE_MINB, 0>(A, claim, claimd, blocks, sm, stream);
+        else launch_one<K, 4, 0>(A, claim, claimd, blocks, sm, stream);
+    }
+}
+
+// slice sweeps of a dynamic-order network, two chains per CTA of four warps
+void launch_batch_nw2(const DynArgs &A, int *claim, int *claimd, int kmax, bool has_ps, bool dense, int n_chains, int Q, int P,
+                      cudaStream_t stream) {
+    const int G = 2, blocks = (n_chains + G - 1) / G;
+    const size_t sm = (size_t)G * dyn_group_smem(Q, P);
+    if (kmax <= 4) launch_k<4>(A, claim, claimd, has_ps, dense, blocks, sm, stream);
+    else launch_k<8>(A, claim, claimd, has_ps, dense, blocks, sm, stream);
+}
+
+}  // namespace bq

@@ -29,7 +29,7 @@ __host__ __device__ BQ_NOINLINE inline double lgamma_d(double x) { return lgamma
 // log of a small positive integer (the N(t) + 1 of processor sharing, queues.pyx:1225-1230): table in constant
 // memory on the device, filled by the library with the host's log(); plain log() on the host
 #if defined(__CUDACC__)
-__constant__ double c_log_count[256];
+static __constant__ double c_log_count[256];  // one copy per translation unit (bq_lib.cu, bq_batch_nw.cu)
 #endif
 __host__ __device__ __forceinline__ double log_count(int n) {
 #if defined(__CUDA_ARCH__)
@@ -264,7 +264,7 @@ struct SuffStat {
 };
 
 // Posterior draw of one queue's parameters (DistributionTemplate.sample_parameters, queues.pyx:1316).
-__device__ BQ_NOINLINE void sample_params(int dist, const SuffStat &st, Rng &rng, double &p0, double &p1,
+static __device__ BQ_NOINLINE void sample_params(int dist, const SuffStat &st, Rng &rng, double &p0, double &p1,
                                      long long *evals) {
     if (dist == D_EXP) {  // distributions.pyx:92-96: scale = 1 / Gamma(N, 1/sum)
         if (st.n < 1.0 || !(st.sum > 0.0)) return;
@@ -298,7 +298,7 @@ __device__ BQ_NOINLINE void sample_params(int dist, const SuffStat &st, Rng &rng
 }
 
 // ML update of one queue's parameters (DistributionTemplate.estimate, queues.pyx:1324).
-__device__ BQ_NOINLINE void estimate_params(int dist, const SuffStat &st, double &p0, double &p1) {
+static __device__ BQ_NOINLINE void estimate_params(int dist, const SuffStat &st, double &p0, double &p1) {
     if (dist == D_EXP) {  // distributions.pyx:65-74
         if (st.n < 1.0) { p0 = 1.0; return; }
         double mu = st.sum / st.n;

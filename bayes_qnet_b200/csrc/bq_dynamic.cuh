@@ -1321,7 +1321,7 @@ __device__ __forceinline__ double group_max(double x, unsigned gmask) {
 
 // per-queue sufficient statistics of one chain (queues.pyx:1316-1336), every lane returns with ss[] filled
 template <int W>
-__device__ BQ_NOINLINE void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, int lane, unsigned gmask, bool want_logp,
+static __device__ BQ_NOINLINE void dyn_suffstats(const Chain &c, int Q, SuffStat *ss, int lane, unsigned gmask, bool want_logp,
                               double *logp_out) {
     double logp_acc = 0.0;
     for (int q = 0; q < Q; ++q) {
@@ -1424,7 +1424,7 @@ __device__ __forceinline__ bool group_slice(const G &g, double x0, double lower,
 // Streams of (chain, sweep, event): TAG_MH and TAG_MH2 feed the two slice steps on the proposal, TAG_MH_AUX holds the
 // accept uniform (number 0) and the re-initialisation draws (numbers 2..).
 template <int W, int KMAX>
-__device__ BQ_NOINLINE void mh_update(const Chain &c, const EventCtx &ev, const DynArgs &A, unsigned long long gchain,
+static __device__ BQ_NOINLINE void mh_update(const Chain &c, const EventCtx &ev, const DynArgs &A, unsigned long long gchain,
                           unsigned int gsw, const GroupLane &gl, long long &n_ev, long long &n_evals, long long &n_stuck,
                           long long &n_reject, Touch &tc) {
     const bool final_evt = (ev.e1 < 0);
@@ -1633,6 +1633,21 @@ __device__ __forceinline__ bool claimed_before(const int *claim, int lo, int hi,
     return hit;
 }
 
+// the same with the lane's own stamp given (rounds of more than 32 events)
+__device__ __forceinline__ bool claimed_before_thr(const int *claim, int lo, int hi, int thr) {
+    if (lo > hi) return false;  // an unset range is (INT_MAX, -1): nothing below may add to lo
+    // thr = the lane's own stamp: the stamps of earlier events of this round are larger, everything older is smaller
+    bool hit = false;
+    int p = lo;
+    for (; p <= hi && (reinterpret_cast<size_t>(claim + p) & 15); ++p) hit |= __ldcg(&claim[p]) > thr;  // per-chain rows start anywhere
+    for (; p + 3 <= hi; p += 4) {
+        const int4 v = __ldcg(reinterpret_cast<const int4 *>(claim + p));
+        hit |= (v.x > thr) | (v.y > thr) | (v.z > thr) | (v.w > thr);
+    }
+    for (; p <= hi; ++p) hit |= __ldcg(&claim[p]) > thr;
+    return hit;
+}
+
 // MINB = CTAs of 128 threads resident per SM: 4 (128 registers per thread, 16 warps/SM) is fastest as long as all
 // chains are resident; with more than 16 x 148 chains the 8-CTA build (64 registers, some spilling, 32 warps/SM) avoids
 // a second, partly filled wave (measured: +12 % at 4096 chains, -17 % at 2048)
@@ -1766,6 +1781,168 @@ __global__ void __launch_bounds__(128, MINB) sweep_batch_kernel(const DynArgs A,
     }
 }
 
+// The same with NW warps per chain (round 2; a separate kernel so that the one-warp build above keeps its register
+// allocation): with few chains per SM one warp per chain leaves the memory latency uncovered
+// (config 4's share of a GPU is 2048 chains = 14 warps per SM), so NW warps of a CTA share a chain and a round
+// holds 32 NW events: every warp computes its 32 updates, the claims of all of them are published, the first
+// conflict of the whole round is found through shared memory and the prefix is committed by whichever warp holds
+// each event -- the same sequential-sweep semantics, three named barriers per round.
+template <int KMAX, int MINB, bool MHK, int PS, int NW>
+__global__ void __launch_bounds__(128, MINB) sweep_batch_kernel_nw(const DynArgs A, int *claim_all, int *claimd_all) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned s_ballot[4];
+    constexpr int W = 32;
+    constexpr int RB = 32 * NW;  // events per round
+    const unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gib = warp / NW, wic = warp % NW;  // the chain's slot in the CTA, the warp's rank within the chain
+    const int chain = blockIdx.x * ((blockDim.x >> 5) / NW) + gib;
+    if (chain >= A.n_chains) return;  // all warps of a chain leave together
+    auto chain_sync = [&]() {
+        if (NW > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + gib), "r"(32 * NW) : "memory");
+        else __syncwarp();
+    };
+    GroupSmem sm;
+    sm.carve(smem_raw + (size_t)gib * dyn_group_smem(A.Q, A.P), A.Q, A.P);
+    QConst *qc = sm.qc;
+    SuffStat *ss = sm.ss;
+    double *th = sm.th;
+    const int Q = A.Q, P = A.P, E = A.E;
+    int *claim = claim_all + (size_t)chain * E;
+    int *claimd = claimd_all ? claimd_all + (size_t)chain * E : nullptr;
+
+    if (wic == 0) {
+        for (int i = lane; i < P; i += W) th[i] = A.theta[(size_t)chain * P + i];
+        for (int q = lane; q < Q; q += W) sm.qi[q] = A.qinfo[q];
+    }
+    for (int i = wic * W + lane; i < E; i += RB) { claim[i] = 0; if (claimd) claimd[i] = 0; }
+    chain_sync();
+    if (wic == 0)
+        for (int q = lane; q < Q; q += W) {
+            const int o = __ldg(&A.q_poff[q]), dist = sm.qi[q].dist;
+            qconst_set(qc[q], dist, th[o], (dist == D_EXP) ? 0.0 : th[o + 1]);
+        }
+    chain_sync();
+    Chain c;
+    c.bind(A, chain, sm.qi, qc);
+
+    LaneParams LP;
+    LP.seed = A.seed; LP.gchain = (unsigned long long)(A.chain_offset + chain); LP.mode = A.mode; LP.flags = A.flags;
+    LP.scan = A.scan;
+    long long n_ev = 0, n_evals = 0, n_stuck = 0, n_pevals = 0, n_steps = 0, n_reject = 0, n_redo = 0;
+    const int4 *order4 = reinterpret_cast<const int4 *>(A.order);
+    int round = 0;
+    const int i_in = wic * W + lane;  // this lane's place in a round
+
+    for (int sw = 0; sw < A.n_sweeps; ++sw) {
+        LP.gsw = A.sweep_base + (unsigned int)sw;
+        if (sw == 0 || (A.flags & FLAG_TMAX_PER_SWEEP)) {  // Tmax = 2 max d   (qnet.pyx:672)
+            double m = 0.0;
+            for (int i = lane; i < E; i += W) m = fmax(m, c.d[i]);
+            LP.tmax = 2.0 * group_max<W>(m, FULL);
+        }
+        const int n_order = (A.flags & FLAG_PARAMS_ONLY) ? 0 : A.n_order;
+        for (int s = 0; s < n_order;) {
+            ++round;
+            const int round_base = round * RB;
+            const int idx = s + i_in;
+            const bool active = idx < n_order;
+            EventCtx ev;
+            LaneUpdate up;
+            up.changed = 0; up.counted = 0; up.rejected = 0; up.stuck = 0; up.evals = 0;
+            up.R.reset(); up.Wt.reset();
+            if (active) {
+                const int4 r4 = __ldg(&order4[(A.flags & FLAG_REVERSE) ? n_order - 1 - idx : idx]);
+                const DynRec rec = {r4.x, r4.y, r4.z, r4.w};
+                event_load(c, rec, ev);
+                lane_update<KMAX, MHK, !MHK, PS>(c, ev, LP, up);
+            }
+            __syncwarp();
+            const int stamp = round_base + RB - 1 - i_in;  // larger = earlier in the round
+            if (active && up.changed) {  // publish what this lane will write
+                claim_range(claim, up.Wt.lo0, up.Wt.hi0, stamp);
+                claim_range(claim, up.Wt.lo1, up.Wt.hi1, stamp);
+                if (claimd) claim_range(claimd, up.Wt.dlo, up.Wt.dhi, stamp);
+            }
+            chain_sync();
+            bool conflict = false;
+            if (active && i_in > 0) {
+                conflict = claimed_before_thr(claim, up.R.lo0, up.R.hi0, stamp) ||
+                           claimed_before_thr(claim, up.R.lo1, up.R.hi1, stamp) ||
+                           (claimd && claimed_before_thr(claimd, up.R.dlo, up.R.dhi, stamp));
+            }
+            const unsigned cm = __ballot_sync(FULL, conflict);
+            const int nact = (n_order - s < RB) ? n_order - s : RB;
+            int fc = nact;
+            if (NW > 1) {
+                if (lane == 0) s_ballot[warp] = cm;
+                chain_sync();
+#pragma unroll
+                for (int w = NW - 1; w >= 0; --w) {
+                    const unsigned b = s_ballot[gib * NW + w];
+                    if (b) fc = w * W + __ffs(b) - 1;
+                }
+            } else if (cm) fc = __ffs(cm) - 1;
+            if (active && i_in < fc) {
+                n_ev += up.counted; n_evals += up.evals; n_reject += up.rejected; n_steps += up.R.steps;
+                if (LP.mode != MODE_MH) n_stuck += up.stuck;
+                if (up.changed) dyn_commit<1, KMAX, PS>(c, ev, up.x_new, 0, 1u << lane);
+            }
+            n_redo += (i_in == 0) ? (nact - fc) : 0;
+            chain_sync();  // the commits are in place (and s_ballot is free) before anybody reads the next round
+            s += fc;
+        }
+        const bool trace = (A.flags & FLAG_TRACE) != 0;
+        if (A.update != UPD_NONE || trace) {
+            if (wic == 0) {
+                double logp = 0.0;
+                dyn_suffstats<W>(c, Q, ss, lane, FULL, trace, &logp);
+                const size_t recno = (size_t)(A.trace_base + sw);
+                if (trace) {
+                    for (int q = lane; q < Q; q += W)
+                        A.tr_wait[(recno * A.n_chains + chain) * Q + q] = (ss[q].nall > 0.0) ? ss[q].wait / ss[q].nall : 0.0;
+                    if (lane == 0) A.tr_logp[recno * A.n_chains + chain] = logp;
+                }
+                if (A.update != UPD_NONE) {
+                    for (int q = lane; q < Q; q += W) {
+                        const int o = __ldg(&A.q_poff[q]), dist = sm.qi[q].dist;
+                        double p0 = th[o], p1 = (dist == D_EXP) ? 0.0 : th[o + 1];
+                        if (A.update == UPD_BAYES) {
+                            Rng prng;
+                            prng.init(A.seed, LP.gchain, LP.gsw, (unsigned int)q, TAG_PARAM);
+                            sample_params(dist, ss[q], prng, p0, p1, &n_pevals);
+                        } else {
+                            estimate_params(dist, ss[q], p0, p1);
+                        }
+                        th[o] = p0;
+                        if (dist != D_EXP) th[o + 1] = p1;
+                        qconst_set(qc[q], dist, p0, p1);
+                    }
+                }
+                __syncwarp();
+                if (trace)
+                    for (int i = lane; i < P; i += W) A.tr_theta[(recno * A.n_chains + chain) * P + i] = th[i];
+            }
+            chain_sync();  // the new densities are in shared memory before the next sweep
+        }
+    }
+    if (wic == 0)
+        for (int i = lane; i < P; i += W) A.theta[(size_t)chain * P + i] = th[i];
+    // per-lane counters -> the chain's totals
+    double tot[7] = {(double)n_ev, (double)n_evals, (double)n_pevals, (double)n_stuck, (double)n_reject, (double)n_steps,
+                     (double)n_redo};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) tot[i] = group_sum<W>(tot[i], FULL);
+    if (lane == 0) {
+        unsigned long long *st = reinterpret_cast<unsigned long long *>(A.stats + (size_t)chain * BQ_NSTAT);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            if (NW > 1) atomicAdd(&st[i], (unsigned long long)(long long)tot[i]);
+            else st[i] += (unsigned long long)(long long)tot[i];
+        }
+    }
+}
+
 // ---- parity / reporting kernels ---------------------------------------------------------------
 
 // out[j] = inner_dfun(x[j]) - lik0 for the event of `rec` on one chain (qnet.pyx:1340-1357); one warp.
@@ -1800,7 +1977,7 @@ __global__ void logcond_dynamic_kernel(const DynArgs A, int chain, DynRec rec, c
 }
 
 // Qnet.log_prob (qnet.pyx:1032) and the sufficient statistics, one warp per chain
-__global__ void __launch_bounds__(128) report_dynamic_kernel(const DynArgs A, double *logp_out, double *ss_out) {
+static __global__ void __launch_bounds__(128) report_dynamic_kernel(const DynArgs A, double *logp_out, double *ss_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int gib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chain = blockIdx.x * (blockDim.x >> 5) + gib;

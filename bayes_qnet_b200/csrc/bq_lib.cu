@@ -22,6 +22,14 @@
 #include "bq_cluster.cuh"
 #include "bq_host.h"
 
+// bq_batch_nw.cu: the batch kernel with two warps per chain, and its copy of the log-count table
+namespace bq {
+void launch_batch_nw2(const DynArgs &A, int *claim, int *claimd, int kmax, bool has_ps, bool dense, int n_chains, int Q, int P,
+                      cudaStream_t stream);
+cudaError_t batch_nw_set_log_table(const double *tab256);
+}
+
+
 using namespace bq;
 
 static thread_local std::string g_err;
@@ -93,6 +101,7 @@ struct bq_handle {
     std::vector<int> dyn_order;          // sweep order of the dynamic-order kernels
     bool dyn_batch = true;               // dynamic-order kernels: warp-per-chain batches (else W-lane groups, BQ_DYN_BATCH=0)
     int order_stride = 0;                // batch order: 0 = lanes 1/32 of the queue apart; r > 0 = windows of 32 r events
+    int batch_nw = 1;                    // warps per chain of the batch kernel (rounds of 32 batch_nw events), fixed at create
     int *d_claim = nullptr, *d_claimd = nullptr;
     bool mh_dynamic = false;             // static-order handle: run MH sweeps in the dynamic-order kernel (BQ_MH_DYNAMIC)
     bool dyn_ready = false;              // dynamic arrays allocated
@@ -382,13 +391,23 @@ static int build_sequential_order(bq_handle *h) {
     int win_stride = h->order_stride;
     if (const char *env = getenv("BQ_ORDER_STRIDE")) win_stride = atoi(env);
     std::vector<int> lst;
+    if (h->batch_nw > 1 && !getenv("BQ_BATCH_NW")) {
+        // rounds of 64 events need queues long enough for 64 far-apart events: below ~4096 eligible events per queue the
+        // witness scans of neighbouring lanes overlap and most of a round is redone (profiles/r2_batch_nw.log)
+        for (int q = 0; q < Q; ++q) {
+            int n = 0;
+            for (int p = h->q_off[q]; p < h->q_off[q + 1]; ++p) n += eligible(h, h->ord0[p]) ? 1 : 0;
+            if (n > 0 && n < 4096) h->batch_nw = 1;
+        }
+    }
     for (int q = 0; q < Q; ++q) {
         lst.clear();
         for (int p = h->q_off[q]; p < h->q_off[q + 1]; ++p)
             if (eligible(h, h->ord0[p])) lst.push_back(h->ord0[p]);
         const int n = (int)lst.size();
         if (win_stride <= 0) {
-            const int st = (n + 31) / 32;
+            const int rb = 32 * h->batch_nw;  // events per round: consecutive entries of the order are 1/rb of the queue apart
+            const int st = (n + rb - 1) / rb;
             for (int r = 0; r < st; ++r)
                 for (int i = r; i < n; i += st) h->dyn_order.push_back(lst[i]);
         } else {
@@ -463,6 +482,7 @@ static int setup_dynamic(bq_handle *h, const double *d0) {
         tab[0] = -INFINITY;
         for (int i = 1; i < 256; ++i) tab[i] = log((double)i);
         CK(cudaMemcpyToSymbol(c_log_count, tab, sizeof(tab)));
+        CK(batch_nw_set_log_table(tab));
     }
     if (h->has_ps) {
         CK(cudaMalloc((void **)&h->d_dord, C * E * sizeof(int)));
@@ -560,6 +580,12 @@ static void launch_dynamic(bq_handle *h, const DynArgs &A) {
             sweep_batch_kernel<K, MINB, MHK, 0><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd); } \
     } while (0)
         const bool mh = (A.mode == MODE_MH);
+        // two warps per chain (rounds of 64 events) while the chains alone would leave half of the SM's warp slots empty
+        const int nw = mh ? 1 : h->batch_nw;  // MH sweeps: one warp per chain on the same order (any batch size is exact)
+        if (nw == 2) {  // compiled in its own translation unit (bq_batch_nw.cu): see there
+            launch_batch_nw2(A, h->d_claim, h->d_claimd, h->kmax, h->has_ps, 2 * h->C > 16 * sms, h->C, h->Q, h->P, h->stream);
+            return;
+        }
         if (h->has_gg1r) {  // random-order queues: one build (slice only, any k), 16 warps per SM
             smem_optin((const void *)sweep_batch_kernel<8, 4, false, 2>, sm);
             sweep_batch_kernel<8, 4, false, 2><<<blocks, 32 * G, sm, h->stream>>>(A, h->d_claim, h->d_claimd);
@@ -768,6 +794,13 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         CKB(cudaMemcpy(h->d_theta, th.data(), th.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
 
+    {   // two warps per chain (rounds of 64 events) while the chains alone would leave half of the SM's warp slots empty;
+        // slice sweeps only -- a handle that may run MH sweeps through these kernels keeps one warp per chain
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        h->batch_nw = (!h->static_order && !h->has_gg1r && 2 * h->C <= 16 * sms) ? 2 : 1;  // measured: profiles/r2_batch_nw.log
+        if (const char *env = getenv("BQ_BATCH_NW")) h->batch_nw = (atoi(env) == 2 && !h->has_gg1r) ? 2 : 1;
+    }
     if (int rc = build_sequential_order(h)) { std::string msg = g_err; bq_destroy(h); return fail(rc, msg); }
     if (!h->static_order)
         if (int rc = setup_dynamic(h, a->d)) { std::string msg = g_err; bq_destroy(h); return fail(rc, msg); }

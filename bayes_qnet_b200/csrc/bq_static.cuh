@@ -713,7 +713,7 @@ struct InitArgs {
     unsigned int counter;
 };
 
-__global__ void init_chains_kernel(const InitArgs A) {
+static __global__ void init_chains_kernel(const InitArgs A) {
     const int chain = blockIdx.x * blockDim.x + threadIdx.x;
     if (chain >= A.n_chains) return;
     double *d = A.state + (size_t)chain * A.E;
@@ -752,7 +752,7 @@ __global__ void init_chains_kernel(const InitArgs A) {
 // ---- parity / reporting kernels ---------------------------------------------------------------
 
 // out[j] = inner_dfun(x[j]) - lik0 for event described by `r` on chain `chain` (qnet.pyx:1340-1357).
-__global__ void logcond_static_kernel(const SweepArgs A, int chain, SchedRec r, const double *x, int n,
+static __global__ void logcond_static_kernel(const SweepArgs A, int chain, SchedRec r, const double *x, int n,
                                       double *out) {
     __shared__ QConst qc[3];  // service densities of e, of its queue successor, of the task's next event
     __shared__ int qt[2];
@@ -782,7 +782,7 @@ __global__ void logcond_static_kernel(const SweepArgs A, int chain, SchedRec r, 
 }
 
 // Qnet.log_prob (qnet.pyx:1032) and the fused sufficient statistics (per slot), one CTA per chain.
-__global__ void __launch_bounds__(256) report_static_kernel(const SweepArgs A, double *logp_out,
+static __global__ void __launch_bounds__(256) report_static_kernel(const SweepArgs A, double *logp_out,
                                                              double *ss_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int chain = blockIdx.x, Q = A.Q, NS = A.NS;
