@@ -3,6 +3,7 @@
 // sweep_batch_kernel went from 272 to 432 bytes of stack and config 4 from 7.7e8 to 5.5e8 resamples/s, with not a line
 // of that kernel touched.  Here the two sets of instantiations cannot influence each other.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "bq_dynamic.cuh"
 
@@ -39,10 +40,28 @@ static void launch_k(const DynArgs &A, int *claim, int *claimd, bool has_ps, boo
 // slice sweeps of a dynamic-order network, two chains per CTA of four warps
 void launch_batch_nw2(const DynArgs &A, int *claim, int *claimd, int kmax, bool has_ps, bool dense, int n_chains, int Q, int P,
                       cudaStream_t stream) {
-    const int G = 2, blocks = (n_chains + G - 1) / G;
+    // Waves: two warps per chain pay while all of them fit the 16-warps-per-SM (128-register) build, so more chains
+    // than that run as equal waves, one launch after the other on the handle's stream -- every chain does all the
+    // sweeps of the call inside its wave.  `dense` (the caller's wish for the 64-register build) is kept for the test
+    // hook BQ_BATCH_WAVE=0.
+    const int G = 2;
     const size_t sm = (size_t)G * dyn_group_smem(Q, P);
-    if (kmax <= 4) launch_k<4>(A, claim, claimd, has_ps, dense, blocks, sm, stream);
-    else launch_k<8>(A, claim, claimd, has_ps, dense, blocks, sm, stream);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int cap = (16 * sms) / 2;  // chains resident at once
+    if (const char *env = getenv("BQ_BATCH_WAVE")) cap = atoi(env) > 0 ? atoi(env) : n_chains;
+    const int waves = (n_chains + cap - 1) / cap;
+    const int per = (n_chains + waves - 1) / waves;
+    for (int lo = 0; lo < n_chains; lo += per) {
+        DynArgs W = A;
+        W.chain_lo = lo;
+        W.chain_hi = (lo + per < n_chains) ? lo + per : n_chains;
+        const int nc = W.chain_hi - W.chain_lo, blocks = (nc + G - 1) / G;
+        const bool d2 = dense && 2 * nc > 16 * sms;
+        if (kmax <= 4) launch_k<4>(W, claim, claimd, has_ps, d2, blocks, sm, stream);
+        else launch_k<8>(W, claim, claimd, has_ps, d2, blocks, sm, stream);
+    }
 }
 
 }  // namespace bq

@@ -75,6 +75,7 @@ struct DynRec {
 
 struct DynArgs {
     int E, Q, P, n_order, n_sweeps, update, flags, trace_base, n_chains, S, mode, scan;
+    int chain_lo, chain_hi;  // sweep_batch_kernel_nw: the chains of this launch (a wave), [chain_lo, chain_hi)
     const DynRec *order;  // [n_order]
     const QInfo *qinfo;   // [Q]
     const int *q_poff;    // [Q] offset of the queue's first parameter
@@ -1796,8 +1797,8 @@ __global__ void __launch_bounds__(128, MINB) sweep_batch_kernel_nw(const DynArgs
     const unsigned FULL = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gib = warp / NW, wic = warp % NW;  // the chain's slot in the CTA, the warp's rank within the chain
-    const int chain = blockIdx.x * ((blockDim.x >> 5) / NW) + gib;
-    if (chain >= A.n_chains) return;  // all warps of a chain leave together
+    const int chain = A.chain_lo + blockIdx.x * ((blockDim.x >> 5) / NW) + gib;
+    if (chain >= A.chain_hi) return;  // all warps of a chain leave together
     auto chain_sync = [&]() {
         if (NW > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + gib), "r"(32 * NW) : "memory");
         else __syncwarp();

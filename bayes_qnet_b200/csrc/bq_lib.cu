@@ -798,7 +798,7 @@ extern "C" int bq_create(const bq_model *m, const bq_arrivals *a, const double *
         // slice sweeps only -- a handle that may run MH sweeps through these kernels keeps one warp per chain
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        h->batch_nw = (!h->static_order && !h->has_gg1r && 2 * h->C <= 16 * sms) ? 2 : 1;  // measured: profiles/r2_batch_nw.log
+        h->batch_nw = (!h->static_order && !h->has_gg1r) ? 2 : 1;  // in waves of at most 8 sms chains; measured: profiles/r2_batch_nw.log
         if (const char *env = getenv("BQ_BATCH_NW")) h->batch_nw = (atoi(env) == 2 && !h->has_gg1r) ? 2 : 1;
     }
     if (int rc = build_sequential_order(h)) { std::string msg = g_err; bq_destroy(h); return fail(rc, msg); }
