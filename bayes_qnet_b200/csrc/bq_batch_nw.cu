@@ -38,8 +38,8 @@ static void launch_k(const DynArgs &A, int *claim, int *claimd, bool has_ps, boo
 }
 
 // slice sweeps of a dynamic-order network, two chains per CTA of four warps
-void launch_batch_nw2(const DynArgs &A, int *claim, int *claimd, int kmax, bool has_ps, bool dense, int n_chains, int Q, int P,
-                      cudaStream_t stream) {
+int launch_batch_nw2(const DynArgs &A, int *claim, int *claimd, int kmax, bool has_ps, bool dense, int n_chains, int Q, int P,
+                     cudaStream_t stream) {
     // Waves: two warps per chain pay while all of them fit the 16-warps-per-SM (128-register) build, so more chains
     // than that run as equal waves, one launch after the other on the handle's stream -- every chain does all the
     // sweeps of the call inside its wave.  `dense` (the caller's wish for the 64-register build) is kept for the test
@@ -62,6 +62,7 @@ void launch_batch_nw2(const DynArgs &A, int *claim, int *claimd, int kmax, bool 
         if (kmax <= 4) launch_k<4>(W, claim, claimd, has_ps, d2, blocks, sm, stream);
         else launch_k<8>(W, claim, claimd, has_ps, d2, blocks, sm, stream);
     }
+    return waves;
 }
 
 }  // namespace bq

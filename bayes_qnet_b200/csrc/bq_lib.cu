@@ -24,8 +24,8 @@
 
 // bq_batch_nw.cu: the batch kernel with two warps per chain, and its copy of the log-count table
 namespace bq {
-void launch_batch_nw2(const DynArgs &A, int *claim, int *claimd, int kmax, bool has_ps, bool dense, int n_chains, int Q, int P,
-                      cudaStream_t stream);
+int launch_batch_nw2(const DynArgs &A, int *claim, int *claimd, int kmax, bool has_ps, bool dense, int n_chains, int Q, int P,
+                     cudaStream_t stream);  // returns the number of kernel launches (waves)
 cudaError_t batch_nw_set_log_table(const double *tab256);
 }
 
@@ -583,7 +583,8 @@ static void launch_dynamic(bq_handle *h, const DynArgs &A) {
         // two warps per chain (rounds of 64 events) while the chains alone would leave half of the SM's warp slots empty
         const int nw = mh ? 1 : h->batch_nw;  // MH sweeps: one warp per chain on the same order (any batch size is exact)
         if (nw == 2) {  // compiled in its own translation unit (bq_batch_nw.cu): see there
-            launch_batch_nw2(A, h->d_claim, h->d_claimd, h->kmax, h->has_ps, 2 * h->C > 16 * sms, h->C, h->Q, h->P, h->stream);
+            h->n_launches += launch_batch_nw2(A, h->d_claim, h->d_claimd, h->kmax, h->has_ps, 2 * h->C > 16 * sms, h->C, h->Q, h->P,
+                                              h->stream) - 1;  // the caller counts one
             return;
         }
         if (h->has_gg1r) {  // random-order queues: one build (slice only, any k), 16 warps per SM

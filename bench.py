@@ -97,22 +97,24 @@ WORKLOADS = {
                     fixture="qnet3_5k", ref_fixture="qnet3_5k", kernel="sweep_static_kernel<true, true>",
                     name="3-tier web-service network (qnet3)"),
     "config3": dict(yaml=TANDEM3, init="DFN2", tasks=20000, pct=0.2, chains=4096, sweeps=2, ref_tasks=1000, bytes=32.0,
-                    fixture="lnk_20k", ref_fixture=None, kernel="sweep_batch_kernel<4, 8, false, false>",
+                    fixture="lnk_20k", ref_fixture=None, kernel="sweep_batch_kernel_nw<4, 4, false, 0, 2> (4 waves of 1024 chains)",
                     name="tandem source -> G/G/3 -> G/G/3, LogNormal service"),
     "config4": dict(yaml=PSDELAY, init="PS", tasks=50000, pct=0.2, chains=2048, sweeps=2, ref_tasks=2000, bytes=80.0 / 3.0,
-                    fixture="psdelay_50k", ref_fixture=None, kernel="sweep_batch_kernel<4, 4, false, true>",
+                    fixture="psdelay_50k", ref_fixture=None, kernel="sweep_batch_kernel_nw<4, 4, false, 1, 2> (2 waves of 1024 chains)",
                     name="source -> processor sharing -> delay station (one GPU's share of the 16384 chains)"),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch, from ncu --set full captures under profiles/
+# dram__bytes_read.sum + dram__bytes_write.sum of one STEP (all its launches), from ncu captures under profiles/; the line
+# reports it per launch
 NCU_TRAFFIC = {
     ("config2", 5000, 1024, 20): (273.98e6, "profiles/r1_static_final_ncu_full.txt (166.0 MB read + 108.0 MB written): far BELOW "
                                             "the algorithmic 16 B x resamples because the chain state stays in shared memory "
                                             "for all sweeps of a launch"),
-    ("config3", 20000, 4096, 2): (1006938248960.0 + 291083597056.0, "profiles/r2_config3_dram_traffic.csv (round 2, witness pruning): "
-                                  "3.3 KB per resample, 100x the algorithmic 32 B -- the witness scans (up to 96 records per update) "
-                                  "and the walks re-read each event's neighbourhood from HBM; round 1: 1014 GB per launch at 0.76x the rate"),
-    ("config4", 50000, 2048, 2): (400272155648.0 + 128419334400.0, "profiles/r2_config4_dram_traffic.csv: 1.1 KB per resample, 40x the "
-                                  "algorithmic 26.7 B"),
+    ("config3", 20000, 4096, 2): (553471957504.0 + 163293786368.0, "profiles/r2_config3_dram_traffic.csv (launches 4-7 = the timed step, "
+                                  "four waves of 1024 chains): 1.8 KB per resample, 57x the algorithmic 32 B -- witness scans and walks "
+                                  "re-read each event's neighbourhood; round 1: 1014 GB per step (2.6 KB per resample) at 0.70x the rate, "
+                                  "all 4096 chains resident at once: 1298 GB"),
+    ("config4", 50000, 2048, 2): (405891099392.0 + 132882565888.0, "profiles/r2_config4_dram_traffic.csv (launches 2-3 = the timed step, two "
+                                  "waves of 1024 chains): 1.1 KB per resample, 41x the algorithmic 26.7 B"),
 }
 WORKLOAD = "%s, %d tasks, %d%% observed, %d chains/GPU x %d sweeps per step"
 # measured once, offline, at the REAL size on this repository's build container (tools/ref_fullsize.py; BASELINE.md
@@ -500,10 +502,14 @@ def measure(ctx, workload, tasks, C, S, steps, warmup, mode="SLICE", tight=False
                            % (8e-6 * eng.E * C)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": ctx.hbm_peak, "unit": "GB/s",
-                     "frac": achieved / ctx.hbm_peak, "traffic": traffic[0] if traffic else None,
+                     "frac": achieved / ctx.hbm_peak, "traffic": traffic[0] / max(launches / steps, 1) if traffic else None,
                      "traffic_note": traffic[1] if traffic else "no ncu --set full capture of this exact launch shape",
                      "peak_kind": ctx.peak_kind, "kernel": wl["kernel"], "bytes_per_resample": wl["bytes"],
-                     "resamples_per_launch": resamples_per_step, "launch_ms_mean": mean_ms, "launch_ms_max": max(launch_ms)},
+                     "resamples_per_launch": resamples_per_step / max(launches / steps, 1),
+                     "launch_ms_mean": mean_ms / max(launches / steps, 1), "launch_ms_max": max(launch_ms) / max(launches / steps, 1),
+                     "launches_per_step": launches / steps,
+                     "launch_note": "a step of the dynamic-order kernels is one launch per wave of chains (two warps per chain, "
+                                    "at most 8 x SMs chains resident); times are per launch = step time / launches per step"},
         "config": {"workload": WORKLOAD % (wl["name"], tasks, int(100 * wl["pct"]), C, S), "baseline_config": workload,
                    "initial_state": how, "events_per_chain": eng.E, "resampled_events_per_chain": n_elig,
                    "chains_total": world * C, "sweeps_per_step": S, "param_update": "BAYES (posterior draw every sweep)",
