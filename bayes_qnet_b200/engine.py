@@ -118,6 +118,40 @@ class GibbsEngine(object):
         order and s >= 0.  Static-order networks only (raises BqError otherwise; use `disperse` there)."""
         capi.check(self._L.bq_init_chains(self._h, float(sigma)))
 
+    def init_chains_host(self, n_starts=8, seed=0, kind=None, slice_chains=256):
+        """Starting states of their own for the chains of a dynamic-order network (multi-server, processor-sharing or
+        random-order queues), where the device initialiser does not apply: `n_starts` independent runs of the host
+        initialiser on the handle's data -- same observed times, same task paths, different random draws, hence different
+        hidden times AND different queue orders -- chain c starting from run c % n_starts.  The reference initialises one
+        state per call of Qnet.gibbs_initialize (qnet.pyx:531-540); this is that call repeated.  Returns the starts
+        [n_starts, E]."""
+        from . import initialize as _init
+        from . import queues as _queues
+        codes = [q.code for q in self.net.queues]
+        if not any(c in (_queues.Q_PS, _queues.Q_GG1R) or (c == _queues.Q_GGK and q.k > 1)
+                   for c, q in zip(codes, self.net.queues)):
+            raise ValueError("static-order network: the queue order is shared by all chains of a handle, use init_chains()")
+        if kind is None:
+            kind = "PS" if _queues.Q_PS in codes else "DFN2"
+        soa = self.arrv.soa()
+        row_of = dict((int(e), i) for i, e in enumerate(soa["eid"]))
+        keep = numpy.random.get_state()
+        starts = numpy.empty((int(n_starts), self.E), dtype=numpy.float64)
+        try:
+            for i in range(int(n_starts)):
+                numpy.random.seed((int(seed) * 1000003 + i) % (2 ** 32))
+                s2 = _init.initialize(self.net, self.arrv, kind=kind, sample_paths=False).soa()
+                rows = numpy.fromiter((row_of[int(e)] for e in s2["eid"]), dtype=numpy.int64, count=self.E)
+                starts[i, rows] = s2["d"]
+        finally:
+            numpy.random.set_state(keep)
+        obs = soa["obs_d"] == 1
+        assert numpy.all(starts[:, obs] == soa["d"][obs]), "the initialiser moved an observed departure"
+        for lo in range(0, self.n_chains, int(slice_chains)):
+            hi = min(self.n_chains, lo + int(slice_chains))
+            self.set_state(starts[numpy.arange(lo, hi) % int(n_starts)], lo, hi)
+        return starts
+
     def disperse(self, sweeps=20, scale=0.7, seed=0, mode="SLICE"):
         """Over-dispersed starting points for convergence diagnostics (new; the reference is single-chain): every
         chain runs `sweeps` sweeps under its own perturbed parameters theta * exp(scale * N(0, 1)) -- held fixed --

@@ -5,7 +5,7 @@ import numpy
 import pytest
 
 import helpers
-from bayes_qnet_b200 import GibbsEngine, capi, diagnostics
+from bayes_qnet_b200 import GibbsEngine, capi, diagnostics, qnetu
 
 pytestmark = pytest.mark.gpu
 
@@ -93,3 +93,49 @@ def test_dynamic_order_networks_refuse():
         with pytest.raises(capi.BqError) as ei:
             eng.init_chains(0.5)
         assert ei.value.code == capi.BQ_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("name", ["lnk", "psdelay", "delay_gg1_gg4"])
+def test_host_starts_for_dynamic_order_networks(name):
+    """GibbsEngine.init_chains_host: independent runs of the host initialiser as per-chain starts of a multi-server /
+    processor-sharing network (where the device initialiser does not apply): observed times kept, every start valid
+    (finite log_prob, s >= 0), starts differ in times and in queue order, chain c uses start c mod n_starts, sweeps go
+    on from there and the chains of one start separate."""
+    if name in helpers.MIXED:
+        net, smp, sub, ini = helpers.mixed(name, ntasks=120, pct=0.25, seed=7)
+    else:
+        g = helpers.golden("cond_" + name)
+        net = qnetu.qnet_from_text(str(g["yaml"]))
+        net.parameters = list(g["theta"])
+        from bayes_qnet_b200 import qnet as _q
+        old = _q.get_initializer()
+        _q.set_initialization_type("PS" if name == "psdelay" else "DFN2")
+        try:
+            qnetu.set_seed(3)
+            ini = net.gibbs_initialize(net.sample(120).subset_by_task(0.25))
+        finally:
+            _q.set_initialization_type(old)
+    soa = ini.soa()
+    obs = soa["obs_d"] == 1
+    with GibbsEngine(net, ini, n_chains=12, seed=5) as eng:
+        starts = eng.init_chains_host(n_starts=4, seed=11)
+        assert starts.shape == (4, eng.E)
+        d = eng.state()
+        for c in range(12):
+            assert numpy.array_equal(d[c], starts[c % 4])
+            assert numpy.array_equal(d[c][obs], soa["d"][obs])
+        assert len(set(map(bytes, starts))) == 4
+        assert numpy.all(numpy.isfinite(eng.log_prob()))
+        full = eng.state(full=True)
+        assert numpy.all(full["s"] >= 0)
+        if name != "psdelay":  # PS queues report their initial links, as in the reference (DESIGN.md section 2, deviation 4)
+            assert any(not numpy.array_equal(full["next_byq"][0], full["next_byq"][c]) for c in (1, 2, 3))
+        eng.sweep(5, "SLICE", "BAYES")
+        d2 = eng.state()
+        assert numpy.all(numpy.isfinite(eng.log_prob()))
+        assert not numpy.array_equal(d2[0], d2[4])      # same start, different RNG streams
+        assert numpy.array_equal(d2[:, obs], numpy.broadcast_to(soa["d"][obs], (12, int(obs.sum()))))
+    net2, smp2, sub2, ini2 = helpers.synthetic(helpers.QNET3, 40, 0.3, seed=5)
+    with GibbsEngine(net2, ini2, n_chains=2, seed=1) as eng:
+        with pytest.raises(ValueError):
+            eng.init_chains_host(2)
