@@ -759,3 +759,30 @@ def test_checkpoint_resume_is_exact(name, tmp_path):
         with GibbsEngine(net, arrv, n_chains=3, seed=556, chain_offset=2) as other:
             with pytest.raises(ValueError):
                 other.load(ck)
+
+
+@pytest.mark.parametrize("name", ["mm3", "lnk", "psdelay", "gg2_to_ps_to_ps", "delay_gg1_gg4"])
+def test_two_warps_per_chain_is_the_sequential_sweep(name, monkeypatch):
+    """sweep_batch_kernel_nw (rounds of 64 events shared by two warps, named barriers, first conflict found through
+    shared memory), forced onto small networks where most of a round conflicts and is redone: the result must still
+    be the oracle's sequential sweep in the handle's order, with parameter updates, for every chain -- also when the
+    number of chains is odd (the second chain slot of the last CTA is empty)."""
+    monkeypatch.setenv("BQ_BATCH_NW", "2")
+    if name in helpers.MIXED:
+        net, smp, sub, arrv = helpers.mixed(name)
+    else:
+        net, arrv = helpers.golden_state(helpers.golden("cond_" + name), "s0")
+    with GibbsEngine(net, arrv, n_chains=5, seed=321, chain_offset=1) as eng:
+        off, order = eng.schedule()
+        eng.sweep(4, "SLICE", "BAYES", trace=True)
+        d = eng.state()
+        tr_th = eng.traces()[0]
+        st = eng.stats()
+        assert st["nevents"] == 5 * 4 * len(order) and st["n_redone"] > 0
+        for c in (0, 3, 4):
+            oc = helpers.oracle_chain(net, arrv)
+            for s in range(4):
+                oc.slice_sweep(order, eng.seed, 1 + c, s)
+                oc.update_params("BAYES", eng.seed, 1 + c, s)
+                assert helpers.relerr(tr_th[s, c], oc.theta).max() < 1e-7
+            assert helpers.relerr(d[c], oc.d).max() < 1e-7

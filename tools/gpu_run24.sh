@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_init.py -q -x 2>&1 | tail -12
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "two_warps" 2>&1 | tail -12
