@@ -1144,10 +1144,23 @@ static int launch_sweep(bq_handle *h, int32_t n_sweeps, int32_t mode, int32_t up
         if (int rc = ensure_dynamic(h)) return rc;
     CK(cudaEventRecord(h->ev0, h->stream));
     if (use_dynamic) {
-        DynArgs D;
-        fill_dyn_args(h, D);
-        D.n_sweeps = n_sweeps; D.update = update; D.flags = (int)flags; D.trace_base = h->trace_len; D.mode = mode;
-        launch_dynamic(h, D);
+        // The batch kernels stamp their claims with round * events-per-round in an int, and a round commits at least one
+        // event: a launch may hold at most 2^31 / (64 * n_order) sweeps (699 at config 3's size -- minutes of GPU time).
+        // Longer calls run as several launches; Tmax (2 max d, qnet.pyx:672) is then taken at the start of each launch
+        // instead of once per call unless BQ_FLAG_TMAX_PER_SWEEP asks for every sweep anyway (estimation.bayes does).
+        const long long n_ord = std::max<long long>(1, (long long)h->dyn_order.size());
+        int per_launch = (int)std::max<long long>(1, std::min<long long>(n_sweeps, ((1LL << 31) - 1) / (64 * n_ord)));
+        if (const char *env = getenv("BQ_MAX_SWEEPS_PER_LAUNCH")) per_launch = std::max(1, std::min(per_launch, atoi(env)));  // test hook
+        for (int done = 0; done < n_sweeps; done += per_launch) {
+            DynArgs D;
+            fill_dyn_args(h, D);
+            D.n_sweeps = std::min(per_launch, n_sweeps - done);
+            D.update = update; D.flags = (int)flags; D.mode = mode;
+            D.trace_base = h->trace_len + ((flags & BQ_FLAG_TRACE) ? done : 0);
+            D.sweep_base = h->sweep_counter + (unsigned int)done;
+            launch_dynamic(h, D);
+            if (done + per_launch < n_sweeps) h->n_launches += 1;
+        }
     } else if (h->ncta > 1) {
         h->dyn_stale = true;
         if (int rc = launch_cluster(h, A)) return rc;

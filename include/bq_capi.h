@@ -46,7 +46,8 @@ enum { BQ_UPD_NONE = 0, BQ_UPD_BAYES = 1, BQ_UPD_STEM = 2 };
 enum {
     BQ_FLAG_TMAX_PER_SWEEP = 1, /* recompute Tmax = 2 max d before every sweep (one slice_resample call per
                                    sweep, as estimation.bayes does); otherwise once per bq_sweep call
-                                   (qnet.pyx:672) */
+                                   (qnet.pyx:672) -- or, on dynamic-order networks, once per launch when a call
+                                   holds more sweeps than one launch may (2^31 / (64 x resampled events)) */
     BQ_FLAG_NO_FINAL = 2,       /* MH only: sample_final=False (qnet.pyx:337)                              */
     BQ_FLAG_TRACE = 4,          /* record per-sweep theta / mean wait / log-prob traces                    */
     BQ_FLAG_TIGHT = 8,          /* start the slice bracket at the support of the conditional instead of

@@ -786,3 +786,23 @@ def test_two_warps_per_chain_is_the_sequential_sweep(name, monkeypatch):
                 oc.update_params("BAYES", eng.seed, 1 + c, s)
                 assert helpers.relerr(tr_th[s, c], oc.theta).max() < 1e-7
             assert helpers.relerr(d[c], oc.d).max() < 1e-7
+
+
+@pytest.mark.parametrize("name", ["lnk", "psdelay"])
+def test_long_calls_split_into_several_launches(name, monkeypatch):
+    """A call with more sweeps than one launch of the batch kernels may hold (round stamps are ints) runs as several
+    launches: with Tmax taken every sweep (what estimation.bayes does) the result -- states, parameters, traces,
+    counters -- is that of the single launch."""
+    g = helpers.golden("cond_" + name)
+    net, arrv = helpers.golden_state(g, "s0")
+    outs = []
+    for hook in (None, "3"):
+        if hook:
+            monkeypatch.setenv("BQ_MAX_SWEEPS_PER_LAUNCH", hook)
+        with GibbsEngine(net, arrv, n_chains=3, seed=17) as eng:
+            eng.sweep(8, "SLICE", "BAYES", trace=True)      # 3 + 3 + 2 with the hook
+            outs.append((eng.state(), eng.params(), eng.traces(), eng.stats()["nevents"], eng.stats()["n_launches"]))
+    assert numpy.array_equal(outs[0][0], outs[1][0]) and numpy.array_equal(outs[0][1], outs[1][1])
+    for a, b in zip(outs[0][2], outs[1][2]):
+        assert numpy.array_equal(a, b)
+    assert outs[0][3] == outs[1][3] and outs[1][4] == outs[0][4] + 2
