@@ -92,6 +92,7 @@ SYMBOLS = {
     "bq_kernel_info": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                       ctypes.POINTER(ctypes.c_int32)]),
     "bq_cluster_size": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32)]),
+    "bq_set_relaxed": (ctypes.c_int, [_H, ctypes.c_int32]),
     "bq_get_sweep_counter": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_uint32)]),
     "bq_set_sweep_counter": (ctypes.c_int, [_H, ctypes.c_uint32]),
     "bq_last_sweep_ms": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_float)]),

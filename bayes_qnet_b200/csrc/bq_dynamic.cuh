@@ -630,6 +630,9 @@ BQ_HDI double ps_apply_move(const Chain &c, const PsMove &mv, int lane, Touch &t
 //     for every event whose commencement lies in [min(a0, x), max(a0, x)] (c2e_range) -- commencements are
 //     nondecreasing along the departure order, so again a run of slots -- with N_new(t) = N_old(t) + [x <= t] - [a0 <= t].
 // ---------------------------------------------------------------------------------------------
+#ifndef BQ_RSS_PENALTY
+#define BQ_RSS_PENALTY 30.0
+#endif
 struct Gg1rMove {
     double plus, minus;  // N_new(t) = N_old(t) + [plus <= t] - [minus <= t]
     int ha, hd;          // search hints: an arrival position and a departure slot near the last answers
@@ -659,9 +662,21 @@ BQ_HDF int gg1r_adjust(const Gg1rMove &mv, double t) { return ((mv.plus <= t) ? 
 // one event of the set whose N(.) terms are re-evaluated; false = the start-on-arrival rule is violated
 BQ_HDI bool gg1r_member(const Chain &c, const QInfo &q, Gg1rMove &mv, double a_old, double d_old, double s_old, double a_new,
                         double d_new, double s_new, double &acc, Touch &tc) {
+    // QInfo::k of a random-order queue: 1 = the reference's rule (-inf), 2 = the soft rule of the repair sweeps
+    // (bq_set_relaxed): a violation costs BQ_RSS_PENALTY nats, counted as the CHANGE of the event's status so that
+    // events the move does not concern cancel -- a state that breaks the rule somewhere can then be walked out of
+    const bool relaxed = q.k > 1;
     double w = d_new - a_new - s_new;
     if (w < 0.0) w = 0.0;
-    if (w < 1e-10 && gg1r_count(c, q, mv, a_new, tc) + gg1r_adjust(mv, a_new) > 1) return false;
+    if (w < 1e-10 && gg1r_count(c, q, mv, a_new, tc) + gg1r_adjust(mv, a_new) > 1) {
+        if (!relaxed) return false;
+        acc -= BQ_RSS_PENALTY;
+    }
+    if (relaxed) {
+        double w0 = d_old - a_old - s_old;
+        if (w0 < 0.0) w0 = 0.0;
+        if (w0 < 1e-10 && gg1r_count(c, q, mv, a_old, tc) > 1) acc += BQ_RSS_PENALTY;
+    }
     ++tc.steps;
     if (s_old != 0.0) {
         const double c_old = dmax(a_old, d_old - s_old);

@@ -1345,6 +1345,23 @@ extern "C" int bq_synchronize(bq_handle *h) {
 
 // The sweep index that the next bq_sweep call will use as its first counter value: together with the seed, the chain
 // ids, the departure times and the parameters it determines everything that follows (checkpoint / resume).
+// The soft start-on-arrival rule of random-order queues for repair sweeps (gg1r_member, bq_dynamic.cuh): the per-queue
+// table goes to the device again with k = 2 for those queues.
+extern "C" int bq_set_relaxed(bq_handle *h, int32_t on) {
+    if (!h) return fail(BQ_ERR_INVALID, "null handle");
+    if (!h->has_gg1r) return fail(BQ_ERR_UNSUPPORTED, "bq_set_relaxed: the network has no random-order (GG1R) queue");
+    CK(cudaSetDevice(h->device));
+    std::vector<QInfo> qinfo(h->Q);
+    for (int q = 0; q < h->Q; ++q) {
+        qinfo[q].type = h->q_type[q]; qinfo[q].k = h->q_k[q]; qinfo[q].lo = h->q_off[q]; qinfo[q].hi = h->q_off[q + 1];
+        qinfo[q].foff = h->q_foff[q]; qinfo[q].dist = h->q_dist[q];
+        if (h->q_type[q] == Q_GG1R) qinfo[q].k = on ? 2 : 1;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->d_qinfo, qinfo.data(), qinfo.size() * sizeof(QInfo), cudaMemcpyHostToDevice));
+    return BQ_OK;
+}
+
 extern "C" int bq_get_sweep_counter(bq_handle *h, uint32_t *counter) {
     if (!h || !counter) return fail(BQ_ERR_INVALID, "null argument");
     *counter = h->sweep_counter;

@@ -152,6 +152,29 @@ class GibbsEngine(object):
             self.set_state(starts[numpy.arange(lo, hi) % int(n_starts)], lo, hi)
         return starts
 
+    def repair_random_order(self, max_sweeps=400, check_every=10):
+        """Walk every chain into the support of a random-order network's likelihood (QueueGG1R: an event that starts
+        on arrival must have found the queue empty).  gibbs_initialize cannot always satisfy that rule for observed
+        jobs whose wait was caused by a hidden departure; here slice sweeps run with the rule softened to a penalty
+        (bq_set_relaxed) until every chain's log_prob is finite, then the reference's rule is restored.  Returns the
+        number of sweeps used; raises if violations remain after max_sweeps."""
+        if numpy.all(numpy.isfinite(self.log_prob())):
+            return 0
+        capi.check(self._L.bq_set_relaxed(self._h, 1))
+        used = 0
+        try:
+            while used < max_sweeps:
+                self.sweep(check_every, "SLICE", "NONE")
+                used += check_every
+                if numpy.all(numpy.isfinite(self.log_prob())):
+                    break
+        finally:
+            capi.check(self._L.bq_set_relaxed(self._h, 0))
+        if not numpy.all(numpy.isfinite(self.log_prob())):
+            raise RuntimeError("random-order queues: %d of %d chains still break the start-on-arrival rule after %d repair "
+                               "sweeps" % (int(numpy.sum(~numpy.isfinite(self.log_prob()))), self.n_chains, used))
+        return used
+
     def disperse(self, sweeps=20, scale=0.7, seed=0, mode="SLICE"):
         """Over-dispersed starting points for convergence diagnostics (new; the reference is single-chain): every
         chain runs `sweeps` sweeps under its own perturbed parameters theta * exp(scale * N(0, 1)) -- held fixed --

@@ -237,6 +237,11 @@ int bq_cluster_size(bq_handle *h, int32_t *ncta);
 /* Checkpoint / resume (the reference restarts from 5-decimal CSV snapshots, gibbs.py:137-160, arrivals.pyx:97 -- lossy;
  * here a run resumes exactly): the index of the next sweep, which with the seed, the global chain ids, the departure
  * times (bq_get_state / bq_set_state) and the parameters fixes every random number that follows. */
+/* Random-order queues only (round 2): on != 0 replaces the rule "an event that started on arrival found the queue empty"
+ * (-inf in QueueGG1R.likelihoodDelta, queues.pyx:984-989) by a penalty per violation, so that slice sweeps can walk a
+ * state that breaks it -- what gibbs_initialize leaves when the departure that made an observed job wait is hidden --
+ * into the support; on = 0 restores the reference's rule.  Not a sampler of the posterior while on. */
+int bq_set_relaxed(bq_handle *h, int32_t on);
 int bq_get_sweep_counter(bq_handle *h, uint32_t *counter);
 int bq_set_sweep_counter(bq_handle *h, uint32_t counter);
 

@@ -110,3 +110,37 @@ def test_what_the_reference_cannot_do_is_refused():
             eng.mh_proposal(0, int(eng.schedule()[1][0]), numpy.array([1.0]))
         with pytest.raises(capi.BqError):
             eng.gibbs_kernel(arrv.soa()["d"])
+
+
+def test_repair_sweeps_walk_an_initialised_state_into_the_support():
+    """gibbs_initialize on a random-order network leaves a few observed jobs that start on arrival with others present
+    (log_prob = -inf; the reference's initialisers stop there with an assertion).  GibbsEngine.repair_random_order runs
+    slice sweeps with the rule softened to a penalty until every chain is inside the support, then restores the rule:
+    log_prob finite, observed times untouched, ordinary sweeps stay inside the support afterwards."""
+    from bayes_qnet_b200 import initialize
+    g = helpers.golden("cond_gg1r")
+    net = qnetu.qnet_from_text(str(g["yaml"]))
+    net.parameters = list(g["theta"])
+    qnetu.set_seed(1)
+    sub = net.sample(150).subset_by_task(0.2)
+    ini = net.gibbs_initialize(sub)
+    assert len(initialize.random_order_violations(net, ini)) > 0
+    soa = ini.soa()
+    obs = soa["obs_d"] == 1
+    with GibbsEngine(net, ini, n_chains=4, seed=4) as eng:
+        assert not numpy.any(numpy.isfinite(eng.log_prob()))
+        used = eng.repair_random_order(max_sweeps=600, check_every=20)
+        assert 0 < used <= 600
+        assert numpy.all(numpy.isfinite(eng.log_prob()))
+        for c in range(4):
+            assert initialize.random_order_violations(net, eng.to_arrivals(c)) == []
+        eng.sweep(10, "SLICE", "BAYES")
+        assert numpy.all(numpy.isfinite(eng.log_prob()))
+        d = eng.state()
+        assert numpy.array_equal(d[:, obs], numpy.broadcast_to(soa["d"][obs], (4, int(obs.sum()))))
+        assert eng.repair_random_order() == 0
+    net2, arrv2 = helpers.golden_state(helpers.golden("cond_mm3"), "s0")
+    with GibbsEngine(net2, arrv2, n_chains=1, seed=1) as eng:
+        with pytest.raises(capi.BqError):
+            eng._L.bq_set_relaxed  # symbol exists
+            capi.check(eng._L.bq_set_relaxed(eng._h, 1))
